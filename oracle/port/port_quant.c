@@ -1,0 +1,1127 @@
+/* oracle/port/port_quant.c - TEST INFRASTRUCTURE (see lame_port.h).
+ * Restates the CBR quantisation path: CBR_iteration_loop (quantize.c:1988), outer_loop (:1010) and
+ * its helpers, calc_xmin/calc_noise/on_pe/reduce_side (quantize_pvt.c), the quantiser and Huffman
+ * bit counting (takehiro.c) and the bit reservoir budget (reservoir.c). */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+#include "lame_port.h"
+#include "port_tables.inc"
+
+#define SQRT2_D 1.41421356237309504880
+#define LOG2_D 0.69314718055994530942
+#define LOG10_D 2.30258509299404568402
+#define FAST_LOG10_D(c, x) (lp_fast_log2(c, x) * (LOG2_D / LOG10_D))
+#define FAST_LOG10_X_D(c, x, y) (lp_fast_log2(c, x) * (LOG2_D / LOG10_D * (y)))
+
+typedef struct { float over_noise, tot_noise, max_noise; int over_count, over_SSD, bits; } noise_result;
+typedef struct { int global_gain, sfb_count1, step[39]; float noise[39], noise_log[39]; } noise_cache;
+
+static const uint8_t *hlen_of(int t) { return LGT_HUFF_LEN + LGT_HUFF_OFF[t]; }
+
+/* ------------------------------------------------------------------ bit reservoir (reservoir.c) */
+/* bitstream.c:65 getframebits */
+int lp_getframebits(const lp_encoder *e)
+{
+    return 8 * ((e->cfg.version + 1) * 72000 * e->cfg.brate / e->cfg.samplerate + e->padding);
+}
+/* reservoir.c:83 ResvFrameBegin */
+static int resv_frame_begin(lp_encoder *e, int *mean_bits)
+{
+    const lp_config *cfg = &e->cfg;
+    int frameLength = lp_getframebits(e);
+    int meanBits = (frameLength - cfg->sideinfo_len * 8) / cfg->mode_gr;
+    int resvLimit = (8 * 256) * cfg->mode_gr - 8;
+    int maxmp3buf = cfg->buffer_constraint;
+    int fullFrameBits;
+    e->resv_max = maxmp3buf - frameLength;
+    if (e->resv_max > resvLimit) e->resv_max = resvLimit;
+    if (e->resv_max < 0 || cfg->disable_reservoir) e->resv_max = 0;
+    fullFrameBits = meanBits * cfg->mode_gr + (e->resv_size < e->resv_max ? e->resv_size : e->resv_max);
+    if (fullFrameBits > maxmp3buf) fullFrameBits = maxmp3buf;
+    e->drain_pre = 0;
+    *mean_bits = meanBits;
+    return fullFrameBits;
+}
+/* reservoir.c:175 ResvMaxBits */
+static void resv_max_bits(lp_encoder *e, int mean_bits, int *targ_bits, int *extra_bits, int cbr)
+{
+    const lp_config *cfg = &e->cfg;
+    int add_bits, targBits, extraBits;
+    int ResvSize = e->resv_size, ResvMax = e->resv_max;
+    if (cbr) ResvSize += mean_bits;
+    targBits = mean_bits;
+    if (ResvSize * 10 > ResvMax * 9) {
+        add_bits = ResvSize - (ResvMax * 9) / 10;
+        targBits += add_bits;
+    }
+    else {
+        add_bits = 0;
+        if (!cfg->disable_reservoir) targBits -= .1 * mean_bits;
+    }
+    extraBits = (ResvSize < (e->resv_max * 6) / 10 ? ResvSize : (e->resv_max * 6) / 10);
+    extraBits -= add_bits;
+    if (extraBits < 0) extraBits = 0;
+    *targ_bits = targBits;
+    *extra_bits = extraBits;
+}
+/* reservoir.c:239 ResvFrameEnd */
+static void resv_frame_end(lp_encoder *e, int mean_bits)
+{
+    int stuffingBits = 0, over_bits, mdb_bytes;
+    e->resv_size += mean_bits * e->cfg.mode_gr;
+    e->drain_post = 0;
+    e->drain_pre = 0;
+    if ((over_bits = e->resv_size % 8) != 0) stuffingBits += over_bits;
+    over_bits = (e->resv_size - stuffingBits) - e->resv_max;
+    if (over_bits > 0) stuffingBits += over_bits;
+    mdb_bytes = (e->main_data_begin * 8 < stuffingBits ? e->main_data_begin * 8 : stuffingBits) / 8;
+    e->drain_pre += 8 * mdb_bytes;
+    stuffingBits -= 8 * mdb_bytes;
+    e->resv_size -= 8 * mdb_bytes;
+    e->main_data_begin -= mdb_bytes;
+    e->drain_post += stuffingBits;
+    e->resv_size -= stuffingBits;
+}
+
+/* quantize_pvt.c:428 on_pe */
+static int on_pe(lp_encoder *e, float pe[2][2], int targ_bits[2], int mean_bits, int gr, int cbr)
+{
+    const lp_config *cfg = &e->cfg;
+    int extra_bits = 0, tbits, bits, add_bits[2] = { 0, 0 }, max_bits, ch;
+    resv_max_bits(e, mean_bits, &tbits, &extra_bits, cbr);
+    max_bits = tbits + extra_bits;
+    if (max_bits > LP_MAX_BITS_PER_GRANULE) max_bits = LP_MAX_BITS_PER_GRANULE;
+    for (bits = 0, ch = 0; ch < cfg->channels; ++ch) {
+        targ_bits[ch] = LP_MAX_BITS_PER_CHANNEL < tbits / cfg->channels ? LP_MAX_BITS_PER_CHANNEL : tbits / cfg->channels;
+        add_bits[ch] = targ_bits[ch] * pe[gr][ch] / 700.0 - targ_bits[ch];
+        if (add_bits[ch] > mean_bits * 3 / 4) add_bits[ch] = mean_bits * 3 / 4;
+        if (add_bits[ch] < 0) add_bits[ch] = 0;
+        if (add_bits[ch] + targ_bits[ch] > LP_MAX_BITS_PER_CHANNEL)
+            add_bits[ch] = 0 > LP_MAX_BITS_PER_CHANNEL - targ_bits[ch] ? 0 : LP_MAX_BITS_PER_CHANNEL - targ_bits[ch];
+        bits += add_bits[ch];
+    }
+    if (bits > extra_bits && bits > 0)
+        for (ch = 0; ch < cfg->channels; ++ch) add_bits[ch] = extra_bits * add_bits[ch] / bits;
+    for (ch = 0; ch < cfg->channels; ++ch) {
+        targ_bits[ch] += add_bits[ch];
+        extra_bits -= add_bits[ch];
+    }
+    for (bits = 0, ch = 0; ch < cfg->channels; ++ch) bits += targ_bits[ch];
+    if (bits > LP_MAX_BITS_PER_GRANULE)
+        for (ch = 0; ch < cfg->channels; ++ch) {
+            targ_bits[ch] *= LP_MAX_BITS_PER_GRANULE;
+            targ_bits[ch] /= bits;
+        }
+    return max_bits;
+}
+/* quantize_pvt.c:492 reduce_side */
+static void reduce_side(int targ_bits[2], float ms_ener_ratio, int mean_bits, int max_bits)
+{
+    int move_bits;
+    float fac;
+    fac = .33 * (.5 - ms_ener_ratio) / .5;
+    if (fac < 0) fac = 0;
+    if (fac > .5) fac = .5;
+    move_bits = fac * .5 * (targ_bits[0] + targ_bits[1]);
+    if (move_bits > LP_MAX_BITS_PER_CHANNEL - targ_bits[0]) move_bits = LP_MAX_BITS_PER_CHANNEL - targ_bits[0];
+    if (move_bits < 0) move_bits = 0;
+    if (targ_bits[1] >= 125) {
+        if (targ_bits[1] - move_bits > 125) {
+            if (targ_bits[0] < mean_bits) targ_bits[0] += move_bits;
+            targ_bits[1] -= move_bits;
+        }
+        else {
+            targ_bits[0] += targ_bits[1] - 125;
+            targ_bits[1] = 125;
+        }
+    }
+    move_bits = targ_bits[0] + targ_bits[1];
+    if (move_bits > max_bits) {
+        targ_bits[0] = (max_bits * targ_bits[0]) / move_bits;
+        targ_bits[1] = (max_bits * targ_bits[1]) / move_bits;
+    }
+}
+
+/* ------------------------------------------------------------------ allowed noise (quantize_pvt.c) */
+/* quantize_pvt.c:554 athAdjust */
+static float ath_adjust(const lp_config *c, float a, float x, float athFloor, float ATHfixpoint)
+{
+    float const o = 90.30873362f;
+    float const p = (ATHfixpoint < 1.f) ? 94.82444863f : ATHfixpoint;
+    float u = FAST_LOG10_X_D(c, x, 10.0f);
+    float const v = a * a;
+    float w = 0.0f;
+    u -= athFloor;
+    if (v > 1E-20f) w = 1.f + FAST_LOG10_X_D(c, v, 10.0f / o);
+    if (w < 0) w = 0.f;
+    u *= w;
+    u += athFloor + o - p;
+    return powf(10.f, 0.1f * u);
+}
+
+/* quantize_pvt.c:589 calc_xmin */
+static int calc_xmin(lp_encoder *e, const lp_ratio *ratio, lp_granule *gi, float *pxmin)
+{
+    const lp_config *cfg = &e->cfg;
+    int sfb, gsfb, j = 0, ath_over = 0, k, max_nonzero;
+    const float *xr = gi->xr;
+    for (gsfb = 0; gsfb < gi->psy_lmax; gsfb++) {
+        float en0, xmin, rh1, rh2, rh3;
+        int width, l;
+        xmin = ath_adjust(cfg, e->ath_adjust_factor, cfg->ath_l[gsfb], cfg->ath_floor, cfg->athfixpoint);
+        xmin *= cfg->longfact[gsfb];
+        width = gi->width[gsfb];
+        rh1 = xmin / width;
+        rh2 = DBL_EPSILON;
+        en0 = 0.0;
+        for (l = 0; l < width; ++l) {
+            float const xa = xr[j++];
+            float const x2 = xa * xa;
+            en0 += x2;
+            rh2 += (x2 < rh1) ? x2 : rh1;
+        }
+        if (en0 > xmin) ath_over++;
+        if (en0 < xmin) rh3 = en0;
+        else if (rh2 < xmin) rh3 = xmin;
+        else rh3 = rh2;
+        xmin = rh3;
+        {
+            float const en = ratio->en.l[gsfb];
+            if (en > 1e-12f) {
+                float x = en0 * ratio->thm.l[gsfb] / en;
+                x *= cfg->longfact[gsfb];
+                if (xmin < x) xmin = x;
+            }
+        }
+        xmin = (xmin > DBL_EPSILON) ? xmin : DBL_EPSILON;
+        gi->energy_above_cutoff[gsfb] = (en0 > xmin + 1e-14f) ? 1 : 0;
+        *pxmin++ = xmin;
+    }
+    max_nonzero = 0;
+    for (k = 575; k > 0; --k)
+        if (fabs(xr[k]) > 1e-12f) { max_nonzero = k; break; }
+    if (gi->block_type != LP_SHORT) max_nonzero |= 1;
+    else { max_nonzero /= 6; max_nonzero *= 6; max_nonzero += 5; }
+    if (cfg->sfb21_extra == 0 && cfg->samplerate < 44000) {
+        int limit;
+        if (gi->block_type != LP_SHORT) limit = cfg->sfb_l[21] - 1;
+        else limit = 3 * cfg->sfb_s[12] - 1;
+        if (max_nonzero > limit) max_nonzero = limit;
+    }
+    gi->max_nonzero_coeff = max_nonzero;
+    for (sfb = gi->sfb_smin; gsfb < gi->psymax; sfb++, gsfb += 3) {
+        int width, b, l;
+        float tmpATH;
+        tmpATH = ath_adjust(cfg, e->ath_adjust_factor, cfg->ath_s[sfb], cfg->ath_floor, cfg->athfixpoint);
+        tmpATH *= cfg->shortfact[sfb];
+        width = gi->width[gsfb];
+        for (b = 0; b < 3; b++) {
+            float en0 = 0.0, xmin = tmpATH, rh1, rh2, rh3;
+            rh1 = tmpATH / width;
+            rh2 = DBL_EPSILON;
+            for (l = 0; l < width; ++l) {
+                float const xa = xr[j++];
+                float const x2 = xa * xa;
+                en0 += x2;
+                rh2 += (x2 < rh1) ? x2 : rh1;
+            }
+            if (en0 > tmpATH) ath_over++;
+            if (en0 < tmpATH) rh3 = en0;
+            else if (rh2 < tmpATH) rh3 = tmpATH;
+            else rh3 = rh2;
+            xmin = rh3;
+            {
+                float const en = ratio->en.s[sfb][b];
+                if (en > 1e-12f) {
+                    float x = en0 * ratio->thm.s[sfb][b] / en;
+                    x *= cfg->shortfact[sfb];
+                    if (xmin < x) xmin = x;
+                }
+            }
+            xmin = (xmin > DBL_EPSILON) ? xmin : DBL_EPSILON;
+            gi->energy_above_cutoff[gsfb + b] = (en0 > xmin + 1e-14f) ? 1 : 0;
+            *pxmin++ = xmin;
+        }
+        if (cfg->use_temporal) {
+            if (pxmin[-3] > pxmin[-3 + 1]) pxmin[-3 + 1] += (pxmin[-3] - pxmin[-3 + 1]) * cfg->decay;
+            if (pxmin[-3 + 1] > pxmin[-3 + 2]) pxmin[-3 + 2] += (pxmin[-3 + 1] - pxmin[-3 + 2]) * cfg->decay;
+        }
+    }
+    return ath_over;
+}
+
+/* quantize_pvt.c:750 calc_noise_core_c */
+static float noise_core(const lp_config *c, const lp_granule *gi, int *startline, int l, float step)
+{
+    float noise = 0;
+    int j = *startline;
+    const int *ix = gi->l3_enc;
+    if (j > gi->count1) {
+        while (l--) {
+            float t;
+            t = gi->xr[j]; j++; noise += t * t;
+            t = gi->xr[j]; j++; noise += t * t;
+        }
+    }
+    else if (j > gi->big_values) {
+        float ix01[2];
+        ix01[0] = 0; ix01[1] = step;
+        while (l--) {
+            float t;
+            t = fabs(gi->xr[j]) - ix01[ix[j]]; j++; noise += t * t;
+            t = fabs(gi->xr[j]) - ix01[ix[j]]; j++; noise += t * t;
+        }
+    }
+    else {
+        while (l--) {
+            float t;
+            t = fabs(gi->xr[j]) - c->pow43[ix[j]] * step; j++; noise += t * t;
+            t = fabs(gi->xr[j]) - c->pow43[ix[j]] * step; j++; noise += t * t;
+        }
+    }
+    *startline = j;
+    return noise;
+}
+
+/* quantize_pvt.c:815 calc_noise */
+static int calc_noise(const lp_config *c, const lp_granule *gi, const float *l3_xmin, float *distort,
+                      noise_result *res, noise_cache *prev)
+{
+    int sfb, l, over = 0, j = 0;
+    float over_noise_db = 0, tot_noise_db = 0, max_noise = -20.0;
+    const int *scalefac = gi->scalefac;
+    res->over_SSD = 0;
+    for (sfb = 0; sfb < gi->psymax; sfb++) {
+        int const s = gi->global_gain - (((*scalefac++) + (gi->preflag ? lp_pretab[sfb] : 0)) << (gi->scalefac_scale + 1))
+            - gi->subblock_gain[gi->window[sfb]] * 8;
+        float const r_l3_xmin = 1.f / *l3_xmin++;
+        float distort_ = 0.0f, noise = 0.0f;
+        if (prev && (prev->step[sfb] == s)) {
+            j += gi->width[sfb];
+            distort_ = r_l3_xmin * prev->noise[sfb];
+            noise = prev->noise_log[sfb];
+        }
+        else {
+            float const step = c->pow20[s + LP_QMAX2];
+            l = gi->width[sfb] >> 1;
+            if ((j + gi->width[sfb]) > gi->max_nonzero_coeff) {
+                int usefullsize = gi->max_nonzero_coeff - j + 1;
+                if (usefullsize > 0) l = usefullsize >> 1;
+                else l = 0;
+            }
+            noise = noise_core(c, gi, &j, l, step);
+            if (prev) { prev->step[sfb] = s; prev->noise[sfb] = noise; }
+            distort_ = r_l3_xmin * noise;
+            noise = FAST_LOG10_D(c, (distort_ > 1E-20f ? distort_ : 1E-20f));
+            if (prev) prev->noise_log[sfb] = noise;
+        }
+        *distort++ = distort_;
+        if (prev) prev->global_gain = gi->global_gain;
+        tot_noise_db += noise;
+        if (noise > 0.0) {
+            int tmp = (int) (noise * 10 + .5);
+            if (tmp < 1) tmp = 1;
+            res->over_SSD += tmp * tmp;
+            over++;
+            over_noise_db += noise;
+        }
+        max_noise = max_noise > noise ? max_noise : noise;
+    }
+    res->over_count = over;
+    res->tot_noise = tot_noise_db;
+    res->over_noise = over_noise_db;
+    res->max_noise = max_noise;
+    return over;
+}
+
+/* ------------------------------------------------------------------ quantiser + bit counting (takehiro.c) */
+/* takehiro.c:113 quantize_lines_xrpow_01 */
+static void quant_lines_01(unsigned l, float istep, const float *xr, int *ix)
+{
+    float const compareval0 = (1.0f - 0.4054f) / istep;
+    unsigned i;
+    for (i = 0; i < l; i += 2) {
+        ix[i + 0] = (compareval0 > xr[i + 0]) ? 0 : 1;
+        ix[i + 1] = (compareval0 > xr[i + 1]) ? 0 : 1;
+    }
+}
+/* takehiro.c:144 quantize_lines_xrpow (TAKEHIRO_IEEE754_HACK): double add of 2^23, float store, table
+ * lookup on the integer part, second double add, float store, subtract the magic integer. */
+static void quant_lines(const lp_config *c, unsigned l, float istep, const float *xp, int *pi)
+{
+    unsigned i;
+    l = (l >> 1) << 1;
+    for (i = 0; i < l; i++) {
+        union { float f; int i; } fi;
+        double x0 = istep * xp[i];
+        x0 += 8388608.0;
+        fi.f = x0;
+        fi.f = x0 + c->adj43asm[fi.i - 0x4b000000];
+        pi[i] = fi.i - 0x4b000000;
+    }
+}
+
+/* takehiro.c:281 quantize_xrpow: only the scalefactor bands whose step changed are re-quantised */
+static void quantize_xrpow(const lp_config *c, const float *xp, int *pi, float istep, const lp_granule *gi,
+                           const noise_cache *prev)
+{
+    int sfb, sfbmax, j = 0, prev_data_use, accumulate = 0, accumulate01 = 0;
+    int *iData = pi, *acc_iData = pi;
+    const float *acc_xp = xp;
+    prev_data_use = (prev && (gi->global_gain == prev->global_gain));
+    sfbmax = (gi->block_type == LP_SHORT) ? 38 : 21;
+    for (sfb = 0; sfb <= sfbmax; sfb++) {
+        int step = -1;
+        if (prev_data_use || gi->block_type == LP_NORM) {
+            step = gi->global_gain - ((gi->scalefac[sfb] + (gi->preflag ? lp_pretab[sfb] : 0)) << (gi->scalefac_scale + 1))
+                - gi->subblock_gain[gi->window[sfb]] * 8;
+        }
+        if (prev_data_use && (prev->step[sfb] == step)) {
+            if (accumulate) { quant_lines(c, accumulate, istep, acc_xp, acc_iData); accumulate = 0; }
+            if (accumulate01) { quant_lines_01(accumulate01, istep, acc_xp, acc_iData); accumulate01 = 0; }
+        }
+        else {
+            int l = gi->width[sfb];
+            int probe = sfb;
+            if ((j + gi->width[sfb]) > gi->max_nonzero_coeff) {
+                int usefullsize = gi->max_nonzero_coeff - j + 1;
+                memset(&pi[gi->max_nonzero_coeff], 0, sizeof(int) * (576 - gi->max_nonzero_coeff));
+                l = usefullsize;
+                if (l < 0) l = 0;
+                sfb = sfbmax + 1;
+                probe = sfb;
+            }
+            if (!accumulate && !accumulate01) { acc_iData = iData; acc_xp = xp; }
+            /* the reference indexes prev->step[] with the already-bumped sfb (takehiro.c:372): for a
+             * long block that is entry 22 (never written, 0); for a short block entry 39 aliases
+             * noise[0] reinterpreted as int - reproduced through the union below */
+            {
+                int use01 = 0;
+                if (prev && prev->sfb_count1 > 0 && probe >= prev->sfb_count1) {
+                    int pstep;
+                    if (probe < 39) pstep = prev->step[probe];
+                    else { union { float f; int i; } u; u.f = prev->noise[0]; pstep = u.i; }
+                    if (pstep > 0 && step >= pstep) use01 = 1;
+                }
+                if (use01) {
+                    if (accumulate) {
+                        quant_lines(c, accumulate, istep, acc_xp, acc_iData);
+                        accumulate = 0; acc_iData = iData; acc_xp = xp;
+                    }
+                    accumulate01 += l;
+                }
+                else {
+                    if (accumulate01) {
+                        quant_lines_01(accumulate01, istep, acc_xp, acc_iData);
+                        accumulate01 = 0; acc_iData = iData; acc_xp = xp;
+                    }
+                    accumulate += l;
+                }
+            }
+            if (l <= 0) {
+                if (accumulate01) { quant_lines_01(accumulate01, istep, acc_xp, acc_iData); accumulate01 = 0; }
+                if (accumulate) { quant_lines(c, accumulate, istep, acc_xp, acc_iData); accumulate = 0; }
+                break;
+            }
+        }
+        if (sfb <= sfbmax) {
+            iData += gi->width[sfb];
+            xp += gi->width[sfb];
+            j += gi->width[sfb];
+        }
+    }
+    if (accumulate) quant_lines(c, accumulate, istep, acc_xp, acc_iData);
+    if (accumulate01) quant_lines_01(accumulate01, istep, acc_xp, acc_iData);
+}
+
+/* takehiro.c:618 choose_table_nonMMX and the count_bit_* helpers (:449-:573) */
+static int choose_table(const int *ix, const int *end, int *_s)
+{
+    static const int huf_tbl_noESC[15] = { 1, 2, 5, 7, 7, 10, 10, 13, 13, 13, 13, 13, 13, 13, 13 };
+    unsigned *s = (unsigned *) _s;
+    unsigned max = 0;
+    const int *p;
+    int choice, choice2;
+    for (p = ix; p < end; p++) if ((unsigned) *p > max) max = *p;
+    if (max == 0) return 0;
+    if (max == 1) {
+        unsigned sum = 0;
+        const uint8_t *h = hlen_of(1);
+        for (p = ix; p < end; p += 2) sum += h[p[0] + p[0] + p[1]];
+        *s += sum;
+        return 1;
+    }
+    if (max <= 3) {
+        int t1 = huf_tbl_noESC[max - 1];
+        unsigned xlen = LGT_HUFF_XLEN[t1], sum = 0, sum2;
+        const uint32_t *table = (t1 == 2) ? LGT_TABLE23 : LGT_TABLE56;
+        for (p = ix; p < end; p += 2) sum += table[p[0] * xlen + p[1]];
+        sum2 = sum & 0xffffu;
+        sum >>= 16u;
+        if (sum > sum2) { sum = sum2; t1++; }
+        *s += sum;
+        return t1;
+    }
+    if (max <= 15) {
+        int t1 = huf_tbl_noESC[max - 1], t;
+        unsigned sum1 = 0, sum2 = 0, sum3 = 0, xlen = LGT_HUFF_XLEN[t1];
+        const uint8_t *h1 = hlen_of(t1), *h2 = hlen_of(t1 + 1), *h3 = hlen_of(t1 + 2);
+        for (p = ix; p < end; p += 2) {
+            unsigned x = p[0] * xlen + p[1];
+            sum1 += h1[x]; sum2 += h2[x]; sum3 += h3[x];
+        }
+        t = t1;
+        if (sum1 > sum2) { sum1 = sum2; t++; }
+        if (sum1 > sum3) { sum1 = sum3; t = t1 + 2; }
+        *s += sum1;
+        return t;
+    }
+    if (max > LP_IXMAX) { *s = LP_LARGE_BITS; return -1; }
+    max -= 15u;
+    for (choice2 = 24; choice2 < 32; choice2++) if (LGT_HUFF_LINMAX[choice2] >= max) break;
+    for (choice = choice2 - 8; choice < 24; choice++) if (LGT_HUFF_LINMAX[choice] >= max) break;
+    {
+        unsigned const linbits = LGT_HUFF_XLEN[choice] * 65536u + LGT_HUFF_XLEN[choice2];
+        unsigned sum = 0, sum2;
+        for (p = ix; p < end; p += 2) {
+            unsigned x = p[0], y = p[1];
+            if (x >= 15u) { x = 15u; sum += linbits; }
+            if (y >= 15u) { y = 15u; sum += linbits; }
+            sum += LGT_LARGETBL[(x << 4) + y];
+        }
+        sum2 = sum & 0xffffu;
+        sum >>= 16u;
+        if (sum > sum2) { sum = sum2; choice = choice2; }
+        *s += sum;
+        return choice;
+    }
+}
+
+static void best_huffman_divide(const lp_config *c, lp_granule *gi);
+
+/* takehiro.c:654 noquant_count_bits */
+static int noquant_count_bits(const lp_config *c, lp_granule *gi, noise_cache *prev)
+{
+    const uint8_t *t32l = hlen_of(32), *t33l = hlen_of(33);
+    int bits = 0, i, a1, a2;
+    const int *ix = gi->l3_enc;
+    i = ((gi->max_nonzero_coeff + 2) >> 1) << 1;
+    if (i > 576) i = 576;
+    if (prev) prev->sfb_count1 = 0;
+    for (; i > 1; i -= 2) if (ix[i - 1] | ix[i - 2]) break;
+    gi->count1 = i;
+    a1 = a2 = 0;
+    for (; i > 3; i -= 4) {
+        int x4 = ix[i - 4], x3 = ix[i - 3], x2 = ix[i - 2], x1 = ix[i - 1], p;
+        if ((unsigned) (x4 | x3 | x2 | x1) > 1) break;
+        p = ((x4 * 2 + x3) * 2 + x2) * 2 + x1;
+        a1 += t32l[p];
+        a2 += t33l[p];
+    }
+    bits = a1;
+    gi->count1table_select = 0;
+    if (a1 > a2) { bits = a2; gi->count1table_select = 1; }
+    gi->count1bits = bits;
+    gi->big_values = i;
+    if (i == 0) return bits;
+    if (gi->block_type == LP_SHORT) {
+        a1 = 3 * c->sfb_s[3];
+        if (a1 > gi->big_values) a1 = gi->big_values;
+        a2 = gi->big_values;
+    }
+    else if (gi->block_type == LP_NORM) {
+        a1 = gi->region0_count = c->bv_scf[i - 2];
+        a2 = gi->region1_count = c->bv_scf[i - 1];
+        a2 = c->sfb_l[a1 + a2 + 2];
+        a1 = c->sfb_l[a1 + 1];
+        if (a2 < i) gi->table_select[2] = choose_table(ix + a2, ix + i, &bits);
+    }
+    else {
+        gi->region0_count = 7;
+        gi->region1_count = LP_SBMAX_L - 1 - 7 - 1;
+        a1 = c->sfb_l[7 + 1];
+        a2 = i;
+        if (a1 > a2) a1 = a2;
+    }
+    a1 = a1 < i ? a1 : i;
+    a2 = a2 < i ? a2 : i;
+    if (0 < a1) gi->table_select[0] = choose_table(ix, ix + a1, &bits);
+    if (a1 < a2) gi->table_select[1] = choose_table(ix + a1, ix + a2, &bits);
+    if (c->use_best_huffman == 2) {
+        gi->part2_3_length = bits;
+        best_huffman_divide(c, gi);
+        bits = gi->part2_3_length;
+    }
+    if (prev && gi->block_type == LP_NORM) {
+        int sfb = 0;
+        while (c->sfb_l[sfb] < gi->big_values) sfb++;
+        prev->sfb_count1 = sfb;
+    }
+    return bits;
+}
+
+/* takehiro.c:767 count_bits */
+static int count_bits(const lp_config *c, const float *xr, lp_granule *gi, noise_cache *prev)
+{
+    float const w = (LP_IXMAX) / c->ipow20[gi->global_gain];
+    if (gi->xrpow_max > w) return LP_LARGE_BITS;
+    quantize_xrpow(c, xr, gi->l3_enc, c->ipow20[gi->global_gain], gi, prev);
+    return noquant_count_bits(c, gi, prev);
+}
+
+/* takehiro.c:809 recalc_divide_init / :847 recalc_divide_sub / :884 best_huffman_divide */
+static void recalc_divide_init(const lp_config *c, const lp_granule *gi, const int *ix, int r01_bits[], int r01_div[],
+                               int r0_tbl[], int r1_tbl[])
+{
+    int r0, r1, bigv = gi->big_values, r0t, r1t, bits;
+    for (r0 = 0; r0 <= 7 + 15; r0++) r01_bits[r0] = LP_LARGE_BITS;
+    for (r0 = 0; r0 < 16; r0++) {
+        int const a1 = c->sfb_l[r0 + 1];
+        int r0bits;
+        if (a1 >= bigv) break;
+        r0bits = 0;
+        r0t = choose_table(ix, ix + a1, &r0bits);
+        for (r1 = 0; r1 < 8; r1++) {
+            int const a2 = c->sfb_l[r0 + r1 + 2];
+            if (a2 >= bigv) break;
+            bits = r0bits;
+            r1t = choose_table(ix + a1, ix + a2, &bits);
+            if (r01_bits[r0 + r1] > bits) {
+                r01_bits[r0 + r1] = bits;
+                r01_div[r0 + r1] = r0;
+                r0_tbl[r0 + r1] = r0t;
+                r1_tbl[r0 + r1] = r1t;
+            }
+        }
+    }
+}
+static void recalc_divide_sub(const lp_config *c, const lp_granule *gi2, lp_granule *gi, const int *ix,
+                              const int r01_bits[], const int r01_div[], const int r0_tbl[], const int r1_tbl[])
+{
+    int bits, r2, a2, bigv = gi2->big_values, r2t;
+    for (r2 = 2; r2 < LP_SBMAX_L + 1; r2++) {
+        a2 = c->sfb_l[r2];
+        if (a2 >= bigv) break;
+        bits = r01_bits[r2 - 2] + gi2->count1bits;
+        if (gi->part2_3_length <= bits) break;
+        r2t = choose_table(ix + a2, ix + bigv, &bits);
+        if (gi->part2_3_length <= bits) continue;
+        memcpy(gi, gi2, sizeof(lp_granule));
+        gi->part2_3_length = bits;
+        gi->region0_count = r01_div[r2 - 2];
+        gi->region1_count = r2 - 2 - r01_div[r2 - 2];
+        gi->table_select[0] = r0_tbl[r2 - 2];
+        gi->table_select[1] = r1_tbl[r2 - 2];
+        gi->table_select[2] = r2t;
+    }
+}
+static void best_huffman_divide(const lp_config *c, lp_granule *gi)
+{
+    const uint8_t *t32l = hlen_of(32), *t33l = hlen_of(33);
+    int i, a1, a2;
+    static lp_granule gi2;
+    const int *ix = gi->l3_enc;
+    int r01_bits[7 + 15 + 1], r01_div[7 + 15 + 1], r0_tbl[7 + 15 + 1], r1_tbl[7 + 15 + 1];
+    memcpy(&gi2, gi, sizeof(lp_granule));
+    if (gi->block_type == LP_NORM) {
+        recalc_divide_init(c, gi, ix, r01_bits, r01_div, r0_tbl, r1_tbl);
+        recalc_divide_sub(c, &gi2, gi, ix, r01_bits, r01_div, r0_tbl, r1_tbl);
+    }
+    i = gi2.big_values;
+    if (i == 0 || (unsigned) (ix[i - 2] | ix[i - 1]) > 1) return;
+    i = gi->count1 + 2;
+    if (i > 576) return;
+    memcpy(&gi2, gi, sizeof(lp_granule));
+    gi2.count1 = i;
+    a1 = a2 = 0;
+    for (; i > gi2.big_values; i -= 4) {
+        int const p = ((ix[i - 4] * 2 + ix[i - 3]) * 2 + ix[i - 2]) * 2 + ix[i - 1];
+        a1 += t32l[p];
+        a2 += t33l[p];
+    }
+    gi2.big_values = i;
+    gi2.count1table_select = 0;
+    if (a1 > a2) { a1 = a2; gi2.count1table_select = 1; }
+    gi2.count1bits = a1;
+    if (gi2.block_type == LP_NORM) recalc_divide_sub(c, &gi2, gi, ix, r01_bits, r01_div, r0_tbl, r1_tbl);
+    else {
+        gi2.part2_3_length = a1;
+        a1 = c->sfb_l[7 + 1];
+        if (a1 > i) a1 = i;
+        if (a1 > 0) gi2.table_select[0] = choose_table(ix, ix + a1, &gi2.part2_3_length);
+        if (i > a1) gi2.table_select[1] = choose_table(ix + a1, ix + i, &gi2.part2_3_length);
+        if (gi->part2_3_length > gi2.part2_3_length) memcpy(gi, &gi2, sizeof(lp_granule));
+    }
+}
+
+/* takehiro.c:1135 mpeg1_scale_bitcount */
+static const int slen1_n[16] = { 1, 1, 1, 1, 8, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16 };
+static const int slen2_n[16] = { 1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2, 4, 8, 4, 8 };
+static const int slen1_tab[16] = { 0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4 };
+static const int slen2_tab[16] = { 0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3 };
+static int scale_bitcount(lp_granule *gi)
+{
+    static const int scale_short[16] = { 0, 18, 36, 54, 54, 36, 54, 72, 54, 72, 90, 72, 90, 108, 108, 126 };
+    static const int scale_mixed[16] = { 0, 18, 36, 54, 51, 35, 53, 71, 52, 70, 88, 69, 87, 105, 104, 122 };
+    static const int scale_long[16] = { 0, 10, 20, 30, 33, 21, 31, 41, 32, 42, 52, 43, 53, 63, 64, 74 };
+    int k, sfb, max_slen1 = 0, max_slen2 = 0;
+    const int *tab;
+    int *scalefac = gi->scalefac;
+    if (gi->block_type == LP_SHORT) {
+        tab = scale_short;
+        if (gi->mixed_block_flag) tab = scale_mixed;
+    }
+    else {
+        tab = scale_long;
+        if (!gi->preflag) {
+            for (sfb = 11; sfb < LP_SBPSY_L; sfb++) if (scalefac[sfb] < lp_pretab[sfb]) break;
+            if (sfb == LP_SBPSY_L) {
+                gi->preflag = 1;
+                for (sfb = 11; sfb < LP_SBPSY_L; sfb++) scalefac[sfb] -= lp_pretab[sfb];
+            }
+        }
+    }
+    for (sfb = 0; sfb < gi->sfbdivide; sfb++) if (max_slen1 < scalefac[sfb]) max_slen1 = scalefac[sfb];
+    for (; sfb < gi->sfbmax; sfb++) if (max_slen2 < scalefac[sfb]) max_slen2 = scalefac[sfb];
+    gi->part2_length = LP_LARGE_BITS;
+    for (k = 0; k < 16; k++)
+        if (max_slen1 < slen1_n[k] && max_slen2 < slen2_n[k] && gi->part2_length > tab[k]) {
+            gi->part2_length = tab[k];
+            gi->scalefac_compress = k;
+        }
+    return gi->part2_length == LP_LARGE_BITS;
+}
+
+/* takehiro.c:964 scfsi_calc */
+static void scfsi_calc(lp_encoder *e, int ch)
+{
+    unsigned i;
+    int s1, s2, c1, c2, sfb;
+    lp_granule *gi = &e->tt[1][ch];
+    const lp_granule *g0 = &e->tt[0][ch];
+    for (i = 0; i < 4; i++) {
+        for (sfb = LGT_SCFSI_BAND[i]; sfb < LGT_SCFSI_BAND[i + 1]; sfb++)
+            if (g0->scalefac[sfb] != gi->scalefac[sfb] && gi->scalefac[sfb] >= 0) break;
+        if (sfb == LGT_SCFSI_BAND[i + 1]) {
+            for (sfb = LGT_SCFSI_BAND[i]; sfb < LGT_SCFSI_BAND[i + 1]; sfb++) gi->scalefac[sfb] = -1;
+            e->scfsi[ch][i] = 1;
+        }
+    }
+    s1 = c1 = 0;
+    for (sfb = 0; sfb < 11; sfb++) {
+        if (gi->scalefac[sfb] == -1) continue;
+        c1++;
+        if (s1 < gi->scalefac[sfb]) s1 = gi->scalefac[sfb];
+    }
+    s2 = c2 = 0;
+    for (; sfb < LP_SBPSY_L; sfb++) {
+        if (gi->scalefac[sfb] == -1) continue;
+        c2++;
+        if (s2 < gi->scalefac[sfb]) s2 = gi->scalefac[sfb];
+    }
+    for (i = 0; i < 16; i++)
+        if (s1 < slen1_n[i] && s2 < slen2_n[i]) {
+            int const c = slen1_tab[i] * c1 + slen2_tab[i] * c2;
+            if (gi->part2_length > c) { gi->part2_length = c; gi->scalefac_compress = (int) i; }
+        }
+}
+
+/* takehiro.c:1021 best_scalefac_store */
+static void best_scalefac_store(lp_encoder *e, int gr, int ch)
+{
+    lp_granule *gi = &e->tt[gr][ch];
+    int sfb, i, j, l, recalc = 0;
+    j = 0;
+    for (sfb = 0; sfb < gi->sfbmax; sfb++) {
+        int const width = gi->width[sfb];
+        for (l = j, j += width; l < j; ++l) if (gi->l3_enc[l] != 0) break;
+        if (l == j) gi->scalefac[sfb] = recalc = -2;
+    }
+    if (!gi->scalefac_scale && !gi->preflag) {
+        int s = 0;
+        for (sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) s |= gi->scalefac[sfb];
+        if (!(s & 1) && s != 0) {
+            for (sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] >>= 1;
+            gi->scalefac_scale = recalc = 1;
+        }
+    }
+    if (!gi->preflag && gi->block_type != LP_SHORT && e->cfg.mode_gr == 2) {
+        for (sfb = 11; sfb < LP_SBPSY_L; sfb++)
+            if (gi->scalefac[sfb] < lp_pretab[sfb] && gi->scalefac[sfb] != -2) break;
+        if (sfb == LP_SBPSY_L) {
+            for (sfb = 11; sfb < LP_SBPSY_L; sfb++) if (gi->scalefac[sfb] > 0) gi->scalefac[sfb] -= lp_pretab[sfb];
+            gi->preflag = recalc = 1;
+        }
+    }
+    for (i = 0; i < 4; i++) e->scfsi[ch][i] = 0;
+    if (e->cfg.mode_gr == 2 && gr == 1 && e->tt[0][ch].block_type != LP_SHORT && e->tt[1][ch].block_type != LP_SHORT) {
+        scfsi_calc(e, ch);
+        recalc = 0;
+    }
+    for (sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
+    if (recalc) (void) scale_bitcount(gi);
+}
+
+/* ------------------------------------------------------------------ noise shaping loop (quantize.c) */
+/* quantize.c:226 init_outer_loop */
+static void init_outer_loop(const lp_config *c, lp_granule *gi)
+{
+    int sfb, j;
+    gi->part2_3_length = 0; gi->big_values = 0; gi->count1 = 0; gi->global_gain = 210; gi->scalefac_compress = 0;
+    gi->table_select[0] = gi->table_select[1] = gi->table_select[2] = 0;
+    gi->subblock_gain[0] = gi->subblock_gain[1] = gi->subblock_gain[2] = gi->subblock_gain[3] = 0;
+    gi->region0_count = 0; gi->region1_count = 0; gi->preflag = 0; gi->scalefac_scale = 0;
+    gi->count1table_select = 0; gi->part2_length = 0;
+    gi->sfb_lmax = LP_SBPSY_L; gi->sfb_smin = LP_SBPSY_S;
+    gi->psy_lmax = c->sfb21_extra ? LP_SBMAX_L : LP_SBPSY_L;
+    gi->psymax = gi->psy_lmax;
+    gi->sfbmax = gi->sfb_lmax;
+    gi->sfbdivide = 11;
+    for (sfb = 0; sfb < LP_SBMAX_L; sfb++) {
+        gi->width[sfb] = c->sfb_l[sfb + 1] - c->sfb_l[sfb];
+        gi->window[sfb] = 3;
+    }
+    if (gi->block_type == LP_SHORT) {
+        float ixwork[576];
+        float *ix;
+        gi->sfb_smin = 0;
+        gi->sfb_lmax = 0;
+        if (gi->mixed_block_flag) { gi->sfb_smin = 3; gi->sfb_lmax = c->mode_gr * 2 + 4; }
+        gi->psymax = gi->sfb_lmax + 3 * ((c->sfb21_extra ? LP_SBMAX_S : LP_SBPSY_S) - gi->sfb_smin);
+        gi->sfbmax = gi->sfb_lmax + 3 * (LP_SBPSY_S - gi->sfb_smin);
+        gi->sfbdivide = gi->sfbmax - 18;
+        gi->psy_lmax = gi->sfb_lmax;
+        ix = &gi->xr[c->sfb_l[gi->sfb_lmax]];
+        memcpy(ixwork, gi->xr, 576 * sizeof(float));
+        for (sfb = gi->sfb_smin; sfb < LP_SBMAX_S; sfb++) {
+            int const start = c->sfb_s[sfb], end = c->sfb_s[sfb + 1];
+            int window, l;
+            for (window = 0; window < 3; window++)
+                for (l = start; l < end; l++) *ix++ = ixwork[3 * l + window];
+        }
+        j = gi->sfb_lmax;
+        for (sfb = gi->sfb_smin; sfb < LP_SBMAX_S; sfb++) {
+            gi->width[j] = gi->width[j + 1] = gi->width[j + 2] = c->sfb_s[sfb + 1] - c->sfb_s[sfb];
+            gi->window[j] = 0; gi->window[j + 1] = 1; gi->window[j + 2] = 2;
+            j += 3;
+        }
+    }
+    gi->count1bits = 0;
+    gi->max_nonzero_coeff = 575;
+    memset(gi->scalefac, 0, sizeof gi->scalefac);
+}
+
+/* quantize.c:110 init_xrpow with :72 init_xrpow_core_c */
+static int init_xrpow(lp_granule *gi, float xrpow[576])
+{
+    float sum = 0;
+    int i;
+    int const upper = gi->max_nonzero_coeff;
+    gi->xrpow_max = 0;
+    memset(&(xrpow[upper]), 0, (576 - upper) * sizeof(xrpow[0]));
+    for (i = 0; i <= upper; ++i) {
+        float tmp = fabs(gi->xr[i]);
+        sum += tmp;
+        xrpow[i] = sqrt(tmp * sqrt(tmp));       /* double sqrt of the float, float product, double sqrt */
+        if (xrpow[i] > gi->xrpow_max) gi->xrpow_max = xrpow[i];
+    }
+    if (sum > (float) 1E-20) return 1;
+    memset(&gi->l3_enc[0], 0, sizeof(int) * 576);
+    return 0;
+}
+
+/* quantize.c:367 bin_search_StepSize */
+static int bin_search_stepsize(lp_encoder *e, lp_granule *gi, int desired_rate, int ch, const float xrpow[576])
+{
+    int nBits, CurrentStep = e->current_step[ch], flag_GoneOver = 0;
+    int const start = e->old_value[ch];
+    int Direction = 0;      /* 0 none, 1 up, 2 down */
+    gi->global_gain = start;
+    desired_rate -= gi->part2_length;
+    for (;;) {
+        int step;
+        nBits = count_bits(&e->cfg, xrpow, gi, 0);
+        if (CurrentStep == 1 || nBits == desired_rate) break;
+        if (nBits > desired_rate) {
+            if (Direction == 2) flag_GoneOver = 1;
+            if (flag_GoneOver) CurrentStep /= 2;
+            Direction = 1;
+            step = CurrentStep;
+        }
+        else {
+            if (Direction == 1) flag_GoneOver = 1;
+            if (flag_GoneOver) CurrentStep /= 2;
+            Direction = 2;
+            step = -CurrentStep;
+        }
+        gi->global_gain += step;
+        if (gi->global_gain < 0) { gi->global_gain = 0; flag_GoneOver = 1; }
+        if (gi->global_gain > 255) { gi->global_gain = 255; flag_GoneOver = 1; }
+    }
+    while (nBits > desired_rate && gi->global_gain < 255) {
+        gi->global_gain++;
+        nBits = count_bits(&e->cfg, xrpow, gi, 0);
+    }
+    e->current_step[ch] = (start - gi->global_gain >= 4) ? 4 : 2;
+    e->old_value[ch] = gi->global_gain;
+    gi->part2_3_length = nBits;
+    return nBits;
+}
+
+/* quantize.c:540 loop_break */
+static int loop_break(const lp_granule *gi)
+{
+    int sfb;
+    for (sfb = 0; sfb < gi->sfbmax; sfb++)
+        if (gi->scalefac[sfb] + gi->subblock_gain[gi->window[sfb]] == 0) return 0;
+    return 1;
+}
+
+/* quantize.c:585 quant_compare - only comparison mode 9 is reachable (every bitrate preset selects it,
+ * presets.c:241) */
+static int quant_compare(const noise_result *best, const noise_result *calc)
+{
+    int better;
+    if (best->over_count > 0) {
+        better = calc->over_SSD <= best->over_SSD;
+        if (calc->over_SSD == best->over_SSD) better = calc->bits < best->bits;
+    }
+    else {
+        better = ((calc->max_noise < 0) && ((calc->max_noise * 10 + calc->bits) <= (best->max_noise * 10 + best->bits)));
+    }
+    if (best->over_count == 0) better = better && calc->bits < best->bits;
+    return better;
+}
+
+/* quantize.c:720 amp_scalefac_bands */
+static void amp_scalefac_bands(const lp_config *c, lp_granule *gi, const float *distort, float xrpow[576], int bRefine)
+{
+    int j, sfb, noise_shaping_amp;
+    float ifqstep34, trigger;
+    if (gi->scalefac_scale == 0) ifqstep34 = 1.29683955465100964055;
+    else ifqstep34 = 1.68179283050742922612;
+    trigger = 0;
+    for (sfb = 0; sfb < gi->sfbmax; sfb++) if (trigger < distort[sfb]) trigger = distort[sfb];
+    noise_shaping_amp = c->noise_shaping_amp;
+    if (noise_shaping_amp == 3) noise_shaping_amp = (bRefine == 1) ? 2 : 1;
+    switch (noise_shaping_amp) {
+    case 2: break;
+    case 1:
+        if (trigger > 1.0) trigger = pow(trigger, .5);
+        else trigger *= .95;
+        break;
+    case 0:
+    default:
+        if (trigger > 1.0) trigger = 1.0;
+        else trigger *= .95;
+        break;
+    }
+    j = 0;
+    for (sfb = 0; sfb < gi->sfbmax; sfb++) {
+        int const width = gi->width[sfb];
+        int l;
+        j += width;
+        if (distort[sfb] < trigger) continue;
+        gi->scalefac[sfb]++;
+        for (l = -width; l < 0; l++) {
+            xrpow[j + l] *= ifqstep34;
+            if (xrpow[j + l] > gi->xrpow_max) gi->xrpow_max = xrpow[j + l];
+        }
+        if (c->noise_shaping_amp == 2) return;
+    }
+}
+
+/* quantize.c:808 inc_scalefac_scale */
+static void inc_scalefac_scale(lp_granule *gi, float xrpow[576])
+{
+    int l, j, sfb;
+    const float ifqstep34 = 1.29683955465100964055;
+    j = 0;
+    for (sfb = 0; sfb < gi->sfbmax; sfb++) {
+        int const width = gi->width[sfb];
+        int s = gi->scalefac[sfb];
+        if (gi->preflag) s += lp_pretab[sfb];
+        j += width;
+        if (s & 1) {
+            s++;
+            for (l = -width; l < 0; l++) {
+                xrpow[j + l] *= ifqstep34;
+                if (xrpow[j + l] > gi->xrpow_max) gi->xrpow_max = xrpow[j + l];
+            }
+        }
+        gi->scalefac[sfb] = s >> 1;
+    }
+    gi->preflag = 0;
+    gi->scalefac_scale = 1;
+}
+
+/* quantize.c:847 inc_subblock_gain */
+static int inc_subblock_gain(const lp_config *c, lp_granule *gi, float xrpow[576])
+{
+    int sfb, window;
+    int *scalefac = gi->scalefac;
+    for (sfb = 0; sfb < gi->sfb_lmax; sfb++) if (scalefac[sfb] >= 16) return 1;
+    for (window = 0; window < 3; window++) {
+        int s1, s2, l, j;
+        s1 = s2 = 0;
+        for (sfb = gi->sfb_lmax + window; sfb < gi->sfbdivide; sfb += 3) if (s1 < scalefac[sfb]) s1 = scalefac[sfb];
+        for (; sfb < gi->sfbmax; sfb += 3) if (s2 < scalefac[sfb]) s2 = scalefac[sfb];
+        if (s1 < 16 && s2 < 8) continue;
+        if (gi->subblock_gain[window] >= 7) return 1;
+        gi->subblock_gain[window]++;
+        j = c->sfb_l[gi->sfb_lmax];
+        for (sfb = gi->sfb_lmax + window; sfb < gi->sfbmax; sfb += 3) {
+            float amp;
+            int const width = gi->width[sfb];
+            int s = scalefac[sfb];
+            s = s - (4 >> gi->scalefac_scale);
+            if (s >= 0) { scalefac[sfb] = s; j += width * 3; continue; }
+            scalefac[sfb] = 0;
+            amp = c->ipow20[210 + (s << (gi->scalefac_scale + 1))];
+            j += width * (window + 1);
+            for (l = -width; l < 0; l++) {
+                xrpow[j + l] *= amp;
+                if (xrpow[j + l] > gi->xrpow_max) gi->xrpow_max = xrpow[j + l];
+            }
+            j += width * (3 - window - 1);
+        }
+        {
+            float const amp = c->ipow20[202];
+            j += gi->width[sfb] * (window + 1);
+            for (l = -gi->width[sfb]; l < 0; l++) {
+                xrpow[j + l] *= amp;
+                if (xrpow[j + l] > gi->xrpow_max) gi->xrpow_max = xrpow[j + l];
+            }
+        }
+    }
+    return 0;
+}
+
+/* quantize.c:940 balance_noise */
+static int balance_noise(const lp_config *c, lp_granule *gi, const float *distort, float xrpow[576], int bRefine)
+{
+    int status;
+    amp_scalefac_bands(c, gi, distort, xrpow, bRefine);
+    status = loop_break(gi);
+    if (status) return 0;
+    status = scale_bitcount(gi);
+    if (!status) return 1;
+    if (c->noise_shaping > 1) {
+        if (!gi->scalefac_scale) { inc_scalefac_scale(gi, xrpow); status = 0; }
+        else if (gi->block_type == LP_SHORT && c->subblock_gain > 0)
+            status = inc_subblock_gain(c, gi, xrpow) || loop_break(gi);
+    }
+    if (!status) status = scale_bitcount(gi);
+    return !status;
+}
+
+/* quantize.c:1010 outer_loop */
+static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float xrpow[576], int ch, int targ_bits)
+{
+    const lp_config *cfg = &e->cfg;
+    static lp_granule gi_w;
+    float save_xrpow[576], distort[LP_SFBMAX];
+    noise_result best_noise_info;
+    int huff_bits, better, age;
+    noise_cache prev_noise;
+    int best_part2_3_length = 9999999, bEndOfSearch = 0, bRefine = 0, best_ggain_pass1 = 0;
+
+    (void) bin_search_stepsize(e, gi, targ_bits, ch, xrpow);
+    if (!cfg->noise_shaping) return 100;
+    memset(&prev_noise, 0, sizeof prev_noise);
+    (void) calc_noise(cfg, gi, l3_xmin, distort, &best_noise_info, &prev_noise);
+    best_noise_info.bits = gi->part2_3_length;
+    gi_w = *gi;
+    age = 0;
+    memcpy(save_xrpow, xrpow, sizeof(float) * 576);
+    while (!bEndOfSearch) {
+        do {
+            noise_result noise_info;
+            int search_limit = 3, maxggain = 255;
+            if (cfg->sfb21_extra) {
+                if (distort[gi_w.sfbmax] > 1.0) break;
+                if (gi_w.block_type == LP_SHORT && (distort[gi_w.sfbmax + 1] > 1.0 || distort[gi_w.sfbmax + 2] > 1.0)) break;
+            }
+            if (balance_noise(cfg, &gi_w, distort, xrpow, bRefine) == 0) break;
+            if (gi_w.scalefac_scale) maxggain = 254;
+            huff_bits = targ_bits - gi_w.part2_length;
+            if (huff_bits <= 0) break;
+            while ((gi_w.part2_3_length = count_bits(cfg, xrpow, &gi_w, &prev_noise)) > huff_bits && gi_w.global_gain <= maxggain)
+                gi_w.global_gain++;
+            if (gi_w.global_gain > maxggain) break;
+            if (best_noise_info.over_count == 0) {
+                while ((gi_w.part2_3_length = count_bits(cfg, xrpow, &gi_w, &prev_noise)) > best_part2_3_length
+                       && gi_w.global_gain <= maxggain)
+                    gi_w.global_gain++;
+                if (gi_w.global_gain > maxggain) break;
+            }
+            (void) calc_noise(cfg, &gi_w, l3_xmin, distort, &noise_info, &prev_noise);
+            noise_info.bits = gi_w.part2_3_length;
+            better = quant_compare(&best_noise_info, &noise_info);
+            if (better) {
+                best_part2_3_length = gi->part2_3_length;
+                best_noise_info = noise_info;
+                *gi = gi_w;
+                age = 0;
+                memcpy(save_xrpow, xrpow, sizeof(float) * 576);
+            }
+            else {
+                if (cfg->full_outer_loop == 0) {
+                    if (++age > search_limit && best_noise_info.over_count == 0) break;
+                    if ((cfg->noise_shaping_amp == 3) && bRefine && age > 30) break;
+                    if ((cfg->noise_shaping_amp == 3) && bRefine && (gi_w.global_gain - best_ggain_pass1) > 15) break;
+                }
+            }
+        } while ((gi_w.global_gain + gi_w.scalefac_scale) < 255);
+        if (cfg->noise_shaping_amp == 3) {
+            if (!bRefine) {
+                gi_w = *gi;
+                memcpy(xrpow, save_xrpow, sizeof(float) * 576);
+                age = 0;
+                best_ggain_pass1 = gi_w.global_gain;
+                bRefine = 1;
+            }
+            else bEndOfSearch = 1;
+        }
+        else bEndOfSearch = 1;
+    }
+    return best_noise_info.over_count;
+}
+
+/* quantize.c:1988 CBR_iteration_loop (+ :48 ms_convert, :1213 iteration_finish_one) */
+void lp_cbr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2])
+{
+    const lp_config *cfg = &e->cfg;
+    float l3_xmin[LP_SFBMAX], xrpow[576];
+    int targ_bits[2], mean_bits, max_bits, gr, ch, i;
+    (void) resv_frame_begin(e, &mean_bits);
+    for (gr = 0; gr < cfg->mode_gr; gr++) {
+        max_bits = on_pe(e, pe, targ_bits, mean_bits, gr, gr);
+        if (e->mode_ext == 2) {
+            for (i = 0; i < 576; ++i) {
+                float l = e->tt[gr][0].xr[i], r = e->tt[gr][1].xr[i];
+                e->tt[gr][0].xr[i] = (l + r) * (float) (SQRT2_D * 0.5);
+                e->tt[gr][1].xr[i] = (l - r) * (float) (SQRT2_D * 0.5);
+            }
+            reduce_side(targ_bits, ms_ener_ratio[gr], mean_bits, max_bits);
+        }
+        for (ch = 0; ch < cfg->channels; ch++) {
+            lp_granule *gi = &e->tt[gr][ch];
+            float masking_lower_db;
+            if (gi->block_type != LP_SHORT) masking_lower_db = cfg->mask_adjust - 0;
+            else masking_lower_db = cfg->mask_adjust_short - 0;
+            e->masking_lower = pow(10.0, masking_lower_db * 0.1);
+            init_outer_loop(cfg, gi);
+            if (init_xrpow(gi, xrpow)) {
+                (void) calc_xmin(e, &ratio[gr][ch], gi, l3_xmin);
+                (void) outer_loop(e, gi, l3_xmin, xrpow, ch, targ_bits[ch]);
+            }
+            best_scalefac_store(e, gr, ch);
+            if (cfg->use_best_huffman == 1) best_huffman_divide(cfg, gi);
+            e->resv_size -= gi->part2_3_length + gi->part2_length;       /* reservoir.c:226 ResvAdjust */
+        }
+    }
+    resv_frame_end(e, mean_bits);
+}
