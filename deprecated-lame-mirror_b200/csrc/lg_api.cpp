@@ -1,0 +1,449 @@
+// lg_api.cpp - host side above the device engine: per-stream PCM buffering (the reference's mfbuf logic,
+// lame.c:1671-1775), the batch scheduler that turns "frames that became complete" into GPU launches, the
+// multi-threaded bit packing of the results, and the two C-ABI faces declared in include/lamegpu.h.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include <thread>
+#include <atomic>
+#include <algorithm>
+#include <functional>
+#include <new>
+#include "../../include/lamegpu.h"
+#include "lg_engine.h"
+#include "lg_bitstream.h"
+
+namespace {
+
+/* One stream = one lame_t of the reference.  The PCM timeline is the reference's zero-prefixed stream:
+ * 528 zeros (ENCDELAY - MDCTDELAY, lame.c:2302) then the user's samples; frame k is encodable once the
+ * timeline holds 1152*k + 1904 samples (calcNeeded, lame.c:1627). */
+struct Stream {
+    std::vector<int16_t> pcm16[2];     /* timeline samples from index tbase on */
+    std::vector<float> pcmf[2];        /* same, already through pcm_transform, once a float entry point was used */
+    bool float_mode = false;
+    long tbase = -LG_PCM_HIST;         /* timeline index of element 0 */
+    long frames_done = 0;
+    long mf_samples_to_encode = 576 + 1152;   /* ENCDELAY + POSTDELAY, lame.c:2299 */
+    int  last_padding = 0;
+    LgBitWriter bw;
+    std::vector<unsigned char> out;    /* packed bytes not yet handed to the caller */
+
+    void init()
+    {
+        for (int c = 0; c < 2; c++) { pcm16[c].assign(LG_PCM_HIST + 528, 0); pcmf[c].clear(); }
+        float_mode = false; tbase = -LG_PCM_HIST; frames_done = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
+        bw.reset(); out.clear();
+    }
+    long tend() const { return tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()); }
+    long frames_ready() const
+    {
+        long const have = tend();
+        long const k = frames_done;
+        if (have < 1152 * k + 1904) return 0;
+        return (have - 1904 - 1152 * k) / 1152 + 1;
+    }
+    void to_float(const LgDevCfg *cfg)
+    {
+        if (float_mode) return;
+        size_t const n = pcm16[0].size();
+        float const m00 = cfg->pcm_transform[0][0], m01 = cfg->pcm_transform[0][1];
+        float const m10 = cfg->pcm_transform[1][0], m11 = cfg->pcm_transform[1][1];
+        pcmf[0].resize(n); pcmf[1].resize(n);
+        for (size_t i = 0; i < n; i++) {
+            float const xl = pcm16[0][i], xr = pcm16[1][i];
+            pcmf[0][i] = xl * m00 + xr * m01;
+            pcmf[1][i] = xl * m10 + xr * m11;
+        }
+        pcm16[0].clear(); pcm16[1].clear();
+        float_mode = true;
+    }
+    void drop_consumed()
+    {
+        long const keep_from = 1152 * frames_done - LG_PCM_HIST;
+        long const d = keep_from - tbase;
+        if (d <= 0) return;
+        if (float_mode) for (int c = 0; c < 2; c++) pcmf[c].erase(pcmf[c].begin(), pcmf[c].begin() + d);
+        else for (int c = 0; c < 2; c++) pcm16[c].erase(pcm16[c].begin(), pcm16[c].begin() + d);
+        tbase = keep_from;
+    }
+};
+
+void parallel_for(int n, int nthreads, const std::function<void(int)> &fn)
+{
+    if (nthreads <= 1 || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::atomic<int> next(0);
+    auto work = [&]() { for (;;) { int const i = next.fetch_add(1); if (i >= n) break; fn(i); } };
+    std::vector<std::thread> th;
+    int const nt = std::min(nthreads, n);
+    for (int t = 1; t < nt; t++) th.emplace_back(work);
+    work();
+    for (auto &t : th) t.join();
+}
+
+} // namespace
+
+struct lamegpu_batch {
+    LgDevCfg cfg;
+    lg_engine *eng = nullptr;
+    int S = 0, F = 0, nthreads = 1;
+    std::vector<Stream> st;
+    long frames_total = 0;
+
+    /* encode every complete frame of every stream; returns frames encoded */
+    long pump()
+    {
+        long done = 0;
+        for (;;) {
+            int *nfr = lg_engine_host_nfr(eng);
+            int maxf = 0, any_float = 0;
+            for (int s = 0; s < S; s++) {
+                long const r = st[s].frames_ready();
+                nfr[s] = (int) std::min<long>(r, F);
+                maxf = std::max(maxf, nfr[s]);
+                if (nfr[s] > 0 && st[s].float_mode) any_float = 1;
+            }
+            if (maxf == 0) break;
+            size_t const stride = lg_engine_pcm_stride(eng);
+            if (any_float) {
+                if (lg_engine_need_float_pcm(eng) != 0) return -2;
+                float *hp = lg_engine_host_pcmf(eng);
+                parallel_for(S, nthreads, [&](int s) {
+                    if (!nfr[s]) return;
+                    st[s].to_float(&cfg);
+                    size_t const n = (size_t) nfr[s] * 1152 + LG_PCM_HALO;
+                    for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcmf[c].data(), n * sizeof(float));
+                });
+            }
+            else {
+                int16_t *hp = lg_engine_host_pcm16(eng);
+                parallel_for(S, nthreads, [&](int s) {
+                    if (!nfr[s]) return;
+                    size_t const n = (size_t) nfr[s] * 1152 + LG_PCM_HALO;
+                    for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcm16[c].data(), n * sizeof(int16_t));
+                });
+            }
+            if (lg_engine_encode(eng, maxf, any_float) != 0) return -2;
+            const LgGranuleOut *go = lg_engine_host_gout(eng);
+            const LgFrameOut *fo = lg_engine_host_fout(eng);
+            parallel_for(S, nthreads, [&](int s) {
+                Stream &x = st[s];
+                for (int f = 0; f < nfr[s]; f++) {
+                    const LgFrameOut *fr = fo + (size_t) s * F + f;
+                    lg_pack_frame(&x.bw, &cfg, fr, go + ((size_t) s * 2 * F + 2 * f) * 2);
+                    x.last_padding = fr->padding;
+                }
+                x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
+                x.bw.buf.clear();
+                x.frames_done += nfr[s];
+                x.mf_samples_to_encode -= 1152L * nfr[s];
+                x.drop_consumed();
+            });
+            for (int s = 0; s < S; s++) done += nfr[s];
+        }
+        frames_total += done;
+        return done;
+    }
+
+    void feed16(int s, const short *l, const short *r, int n)
+    {
+        Stream &x = st[s];
+        if (n <= 0) return;
+        if (!r) r = l;
+        if (x.float_mode) {
+            float const m00 = cfg.pcm_transform[0][0], m01 = cfg.pcm_transform[0][1];
+            float const m10 = cfg.pcm_transform[1][0], m11 = cfg.pcm_transform[1][1];
+            for (int i = 0; i < n; i++) {
+                float const xl = l[i], xr = r[i];
+                x.pcmf[0].push_back(xl * m00 + xr * m01);
+                x.pcmf[1].push_back(xl * m10 + xr * m11);
+            }
+        }
+        else {
+            x.pcm16[0].insert(x.pcm16[0].end(), l, l + n);
+            x.pcm16[1].insert(x.pcm16[1].end(), r, r + n);
+        }
+        if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;     /* lame.c:1735 */
+        x.mf_samples_to_encode += n;
+    }
+    /* lame.c:1786 lame_copy_inbuffer for non-int16 sample types: s = normalisation factor */
+    void feedf(int s, const float *l, const float *r, int n, float scale)
+    {
+        Stream &x = st[s];
+        if (n <= 0) return;
+        if (!r) r = l;
+        x.to_float(&cfg);
+        float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
+        float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
+        for (int i = 0; i < n; i++) {
+            float const xl = l[i], xr = r[i];
+            x.pcmf[0].push_back(xl * m00 + xr * m01);
+            x.pcmf[1].push_back(xl * m10 + xr * m11);
+        }
+        if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;
+        x.mf_samples_to_encode += n;
+    }
+    /* lame.c:2042 lame_encode_flush: how many zero samples stream s still needs */
+    void pad_for_flush(int s)
+    {
+        Stream &x = st[s];
+        if (x.mf_samples_to_encode < 1) return;
+        long const samples_to_encode = x.mf_samples_to_encode - 1152;
+        long end_padding = 1152 - (samples_to_encode % 1152);
+        if (end_padding < 576) end_padding += 1152;
+        long const frames_left = (samples_to_encode + end_padding) / 1152;
+        long const last = x.frames_done + frames_left - 1;
+        long const need = 1152 * last + 1904 - x.tend();
+        if (need > 0) {
+            if (x.float_mode) for (int c = 0; c < 2; c++) x.pcmf[c].insert(x.pcmf[c].end(), (size_t) need, 0.f);
+            else for (int c = 0; c < 2; c++) x.pcm16[c].insert(x.pcm16[c].end(), (size_t) need, (int16_t) 0);
+        }
+    }
+    int take(int s, unsigned char *out, int cap)
+    {
+        Stream &x = st[s];
+        int const n = (int) std::min<size_t>(x.out.size(), cap < 0 ? 0 : (size_t) cap);
+        if (n > 0) { memcpy(out, x.out.data(), n); x.out.erase(x.out.begin(), x.out.begin() + n); }
+        return n;
+    }
+};
+
+extern "C" {
+
+lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int mode, int quality, int nstreams, int frames_per_launch, int device)
+{
+    lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
+    if (!b) return NULL;
+    if (lg_setup(&b->cfg, samplerate, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality) != 0) {
+        fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d, channels %d, brate %d, mode %d, quality %d)\n",
+                samplerate, channels, brate, mode, quality);
+        delete b;
+        return NULL;
+    }
+    b->eng = lg_engine_create(&b->cfg, nstreams, frames_per_launch, device);
+    if (!b->eng) { delete b; return NULL; }
+    b->S = nstreams; b->F = frames_per_launch;
+    unsigned const hw = std::thread::hardware_concurrency();
+    b->nthreads = (int) std::max(1u, std::min(hw ? hw : 1u, 64u));
+    if (const char *e = getenv("LAMEGPU_THREADS")) b->nthreads = std::max(1, atoi(e));
+    b->st.resize(nstreams);
+    for (auto &s : b->st) s.init();
+    return b;
+}
+
+void lamegpu_batch_close(lamegpu_batch *b)
+{
+    if (!b) return;
+    lg_engine_destroy(b->eng);
+    delete b;
+}
+
+int lamegpu_batch_set_threads(lamegpu_batch *b, int n) { if (!b || n < 1) return -1; b->nthreads = n; return 0; }
+
+long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const short *const *pcm_r, const int *nsamples,
+                          unsigned char *const *out, const int *out_cap, int *out_bytes)
+{
+    if (!b) return -3;
+    for (int s = 0; s < b->S; s++) b->feed16(s, pcm_l[s], pcm_r ? pcm_r[s] : NULL, nsamples[s]);
+    long const done = b->pump();
+    if (done < 0) return done;
+    for (int s = 0; s < b->S; s++) out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0;
+    return done;
+}
+
+long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int *out_cap, int *out_bytes)
+{
+    if (!b) return -3;
+    for (int s = 0; s < b->S; s++) b->pad_for_flush(s);
+    long const done = b->pump();
+    if (done < 0) return done;
+    for (int s = 0; s < b->S; s++) {
+        Stream &x = b->st[s];
+        if (x.mf_samples_to_encode >= 1) {
+            x.mf_samples_to_encode = 0;
+            lg_pack_flush(&x.bw, &b->cfg, x.last_padding);
+            x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
+            x.bw.buf.clear();
+        }
+        out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0;
+    }
+    return done;
+}
+
+long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsamples, unsigned char *out, int out_stride, int *out_bytes)
+{
+    if (!b) return -3;
+    for (int s = 0; s < b->S; s++) b->feed16(s, pcm + ((size_t) s * 2) * nsamples, pcm + ((size_t) s * 2 + 1) * nsamples, nsamples);
+    long const done = b->pump();
+    if (done < 0) return done;
+    for (int s = 0; s < b->S; s++) out_bytes[s] = b->take(s, out + (size_t) s * out_stride, out_stride);
+    return done;
+}
+
+long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_stride, int *out_bytes)
+{
+    if (!b) return -3;
+    std::vector<unsigned char *> po(b->S);
+    std::vector<int> cap(b->S, out_stride);
+    for (int s = 0; s < b->S; s++) po[s] = out + (size_t) s * out_stride;
+    return lamegpu_batch_flush(b, po.data(), cap.data(), out_bytes);
+}
+
+/* bench hooks */
+int lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes)
+{
+    /* lay `nframes` frames of every stream (from a fresh stream start) into the pinned staging buffer and the
+     * device buffer; used to measure the device pipeline with inputs resident in HBM */
+    if (!b || nframes < 1 || nframes > b->F) return -1;
+    size_t const stride = lg_engine_pcm_stride(b->eng);
+    int16_t *hp = lg_engine_host_pcm16(b->eng);
+    int *nfr = lg_engine_host_nfr(b->eng);
+    size_t const nsamp = (size_t) nframes * 1152 + LG_PCM_HALO - LG_PCM_HIST - 528;   /* user samples consumed */
+    for (int s = 0; s < b->S; s++) {
+        nfr[s] = nframes;
+        for (int c = 0; c < 2; c++) {
+            int16_t *d = hp + ((size_t) s * 2 + c) * stride;
+            memset(d, 0, (LG_PCM_HIST + 528) * sizeof(int16_t));
+            memcpy(d + LG_PCM_HIST + 528, pcm + ((size_t) s * 2 + c) * nsamp, nsamp * sizeof(int16_t));
+        }
+    }
+    return lg_engine_encode(b->eng, nframes, 0);
+}
+int lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes)
+{
+    if (!b) return -1;
+    if (lg_engine_reset_streams(b->eng, 0, b->S) != 0) return -1;
+    if (lg_engine_run_device(b->eng, nframes, 0) != 0) return -1;
+    return lg_engine_sync(b->eng);
+}
+int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[4])
+{
+    if (!b) return -1;
+    const float *m = lg_engine_last_kernel_ms(b->eng);
+    for (int i = 0; i < 4; i++) ms[i] = m[i];
+    return 0;
+}
+long lamegpu_batch_kernel_launches(const lamegpu_batch *b) { return b ? lg_engine_launch_count(b->eng) : 0; }
+long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap) { return b ? lg_engine_debug_copy(b->eng, what, dst, cap) : -1; }
+size_t lamegpu_sizeof_granule_out(void) { return sizeof(LgGranuleOut); }
+size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }
+
+/* ------------------------------------------------------------------ libmp3lame-compatible face */
+#define LAME_ID 0xFFF88E3B      /* lame_global_flags.h / lame.c class_id check */
+
+struct lame_global_struct {
+    unsigned class_id;
+    int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag;
+    MPEG_mode mode;
+    vbr_mode VBR;
+    int launch_frames;
+    lamegpu_batch *b;            /* created by lame_init_params: a one-stream engine */
+    int initialised;
+};
+
+lame_global_flags *lame_init(void)
+{
+    lame_global_flags *g = (lame_global_flags *) calloc(1, sizeof *g);
+    if (!g) return NULL;
+    g->class_id = LAME_ID;
+    g->num_channels = 2; g->samplerate_in = 44100; g->samplerate_out = 0; g->brate = 0; g->quality = -1;
+    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16;
+    if (const char *e = getenv("LAMEGPU_HANDLE_FRAMES")) g->launch_frames = std::max(1, atoi(e));
+    return g;
+}
+static int ok(const lame_global_flags *g) { return g && g->class_id == LAME_ID; }
+int lame_set_in_samplerate(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->samplerate_in = v; return 0; }
+int lame_get_in_samplerate(const lame_global_flags *g) { return ok(g) ? g->samplerate_in : 0; }
+int lame_set_num_channels(lame_global_flags *g, int v) { if (!ok(g) || v < 1 || v > 2) return -1; g->num_channels = v; return 0; }
+int lame_get_num_channels(const lame_global_flags *g) { return ok(g) ? g->num_channels : 0; }
+int lame_set_out_samplerate(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->samplerate_out = v; return 0; }
+int lame_get_out_samplerate(const lame_global_flags *g) { return ok(g) ? g->samplerate_out : 0; }
+int lame_set_brate(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->brate = v; if (v > 320) return -1; return 0; }
+int lame_get_brate(const lame_global_flags *g) { return ok(g) ? g->brate : 0; }
+int lame_set_quality(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->quality = v < 0 ? 0 : v > 9 ? 9 : v; return 0; }
+int lame_get_quality(const lame_global_flags *g) { return ok(g) ? g->quality : 0; }
+int lame_set_mode(lame_global_flags *g, MPEG_mode m) { if (!ok(g) || (int) m < 0 || m >= MAX_INDICATOR) return -1; g->mode = m; return 0; }
+MPEG_mode lame_get_mode(const lame_global_flags *g) { return ok(g) ? g->mode : NOT_SET; }
+int lame_set_VBR(lame_global_flags *g, vbr_mode m) { if (!ok(g) || (int) m < 0 || m >= vbr_max_indicator) return -1; g->VBR = m; return 0; }
+vbr_mode lame_get_VBR(const lame_global_flags *g) { return ok(g) ? g->VBR : vbr_off; }
+int lame_set_bWriteVbrTag(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->write_lame_tag = v; return 0; }
+int lame_get_bWriteVbrTag(const lame_global_flags *g) { return ok(g) ? g->write_lame_tag : 0; }
+const char *get_lame_short_version(void) { return "3.99.5"; }
+
+int lame_init_params(lame_global_flags *g)
+{
+    if (!ok(g)) return -1;
+    if (g->VBR != vbr_off) { fprintf(stderr, "lamegpu: only CBR (vbr_off) is implemented on the GPU path\n"); return -1; }
+    if (g->samplerate_out && g->samplerate_out != g->samplerate_in) { fprintf(stderr, "lamegpu: resampling is not implemented\n"); return -1; }
+    if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
+    g->b = lamegpu_batch_open(g->samplerate_in, g->num_channels, g->brate, g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, 1, g->launch_frames, 0);
+    if (!g->b) return -1;
+    g->samplerate_out = g->samplerate_in;
+    g->brate = g->b->cfg.brate;
+    g->quality = g->b->cfg.quality;
+    g->mode = (MPEG_mode) g->b->cfg.mode;
+    g->initialised = 1;
+    return 0;
+}
+int lame_get_framesize(const lame_global_flags *g) { return ok(g) && g->initialised ? 1152 : 0; }
+int lame_get_frameNum(const lame_global_flags *g) { return ok(g) && g->b ? (int) g->b->st[0].frames_done : 0; }
+int lame_get_encoder_delay(const lame_global_flags *g) { return ok(g) ? 576 : 0; }
+
+static int handle_take(lame_global_flags *g, unsigned char *mp3buf, int mp3buf_size)
+{
+    Stream &x = g->b->st[0];
+    int const have = (int) x.out.size();
+    if (mp3buf_size != 0 && have > mp3buf_size) return -1;            /* lame.h:687: mp3buf too small */
+    if (have) { memcpy(mp3buf, x.out.data(), have); x.out.clear(); }
+    return have;
+}
+int lame_encode_buffer(lame_global_flags *g, const short int l[], const short int r[], const int nsamples, unsigned char *mp3buf, const int mp3buf_size)
+{
+    if (!ok(g) || !g->initialised) return -3;
+    if (nsamples == 0) return 0;
+    if (!l || (g->num_channels > 1 && !r)) return 0;                  /* lame.c:1856-1864 */
+    g->b->feed16(0, l, g->num_channels > 1 ? r : l, nsamples);
+    if (g->b->pump() < 0) return -2;
+    return handle_take(g, mp3buf, mp3buf_size);
+}
+int lame_encode_buffer_interleaved(lame_global_flags *g, short int pcm[], int nsamples, unsigned char *mp3buf, int mp3buf_size)
+{
+    if (!ok(g) || !g->initialised) return -3;
+    if (nsamples == 0) return 0;
+    std::vector<short> l(nsamples), r(nsamples);
+    for (int i = 0; i < nsamples; i++) { l[i] = pcm[2 * i]; r[i] = pcm[2 * i + 1]; }
+    return lame_encode_buffer(g, l.data(), r.data(), nsamples, mp3buf, mp3buf_size);
+}
+int lame_encode_buffer_ieee_float(lame_t g, const float l[], const float r[], const int nsamples, unsigned char *mp3buf, const int mp3buf_size)
+{
+    if (!ok(g) || !g->initialised) return -3;
+    if (nsamples == 0) return 0;
+    if (!l || (g->num_channels > 1 && !r)) return 0;
+    g->b->feedf(0, l, g->num_channels > 1 ? r : l, nsamples, 32767.0f);  /* lame.c:1911 */
+    if (g->b->pump() < 0) return -2;
+    return handle_take(g, mp3buf, mp3buf_size);
+}
+int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
+{
+    if (!ok(g) || !g->initialised) return -3;
+    Stream &x = g->b->st[0];
+    if (x.mf_samples_to_encode < 1) return 0;
+    g->b->pad_for_flush(0);
+    if (g->b->pump() < 0) return -2;
+    x.mf_samples_to_encode = 0;
+    lg_pack_flush(&x.bw, &g->b->cfg, x.last_padding);
+    x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
+    x.bw.buf.clear();
+    return handle_take(g, mp3buf, size);
+}
+int lame_close(lame_global_flags *g)
+{
+    if (!ok(g)) return -3;
+    if (g->b) lamegpu_batch_close(g->b);
+    g->class_id = 0;
+    free(g);
+    return 0;
+}
+
+} // extern "C"

@@ -1,0 +1,270 @@
+// lg_engine.cu - device side of the batch engine: owns the HBM buffers of one configuration
+// (S streams x up to F frames per launch), the four kernels and the copies.
+//
+//   H2D  pcm (int16 or float, pinned)  ->  A analysis  ->  B scan  ->  C mdct  ->  D quantise  ->  D2H out
+//
+// All work of one launch goes to one CUDA stream; the host packer (lg_bitstream.cpp) consumes the D2H
+// result.  There is no CPU fallback: without a CUDA device lg_engine_create() fails and says so.
+//
+// This translation unit is also compiled by g++ with -DLG_EMULATE for tests/emu (see lg_compat.h); that
+// build is test infrastructure and is never loaded by the product package.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include "lg_compat.h"
+#include "lg_types.h"
+#include "lg_k_analysis.cuh"
+#include "lg_k_scan.cuh"
+#include "lg_k_mdct.cuh"
+#include "lg_k_quant.cuh"
+#include "lg_engine.h"
+
+#ifdef LG_EMULATE
+typedef int lgStream_t;
+typedef struct { double t; } lgEvent_t;
+#define LG_CHECK(x) (x)
+static int lg_dev_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : -1; }
+static void lg_dev_free(void *p) { free(p); }
+static int lg_host_malloc(void **p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? 0 : -1; }
+static void lg_host_free(void *p) { free(p); }
+#define LG_COPY_H2D(dst, src, n, st) memcpy(dst, src, n)
+#define LG_COPY_D2H(dst, src, n, st) memcpy(dst, src, n)
+#define LG_MEMSET(dst, v, n, st) memset(dst, v, n)
+#else
+typedef cudaStream_t lgStream_t;
+#define LG_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "lamegpu: CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return -1; } } while (0)
+static int lg_dev_malloc(void **p, size_t n) { return cudaMalloc(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+static void lg_dev_free(void *p) { if (p) cudaFree(p); }
+static int lg_host_malloc(void **p, size_t n) { return cudaMallocHost(p, n ? n : 1) == cudaSuccess ? 0 : -1; }
+static void lg_host_free(void *p) { if (p) cudaFreeHost(p); }
+#define LG_COPY_H2D(dst, src, n, st) cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, st)
+#define LG_COPY_D2H(dst, src, n, st) cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st)
+#define LG_MEMSET(dst, v, n, st) cudaMemsetAsync(dst, v, n, st)
+#endif
+
+struct lg_engine {
+    LgDevCfg hcfg;
+    LgDevCfg *dcfg;
+    int S, F, device;
+    size_t pcm_stride;                /* samples per channel per stream */
+    int16_t *d_pcm16; float *d_pcmf;
+    float *d_sb, *d_xr;
+    LgAnalysis *d_ana; LgPsyOut *d_psy; LgFrameCtl *d_frm;
+    LgGranuleOut *d_gout; LgFrameOut *d_fout;
+    LgStreamState *d_state;
+    int *d_nfr;
+    /* pinned host staging */
+    int16_t *h_pcm16; float *h_pcmf; int *h_nfr;
+    LgGranuleOut *h_gout; LgFrameOut *h_fout;
+    lgStream_t stream;
+#ifndef LG_EMULATE
+    cudaEvent_t ev[6];
+#endif
+    float last_ms[5];
+    long launches;
+};
+
+extern "C" const LgDevCfg *lg_engine_config(const lg_engine *e) { return &e->hcfg; }
+extern "C" int lg_engine_streams(const lg_engine *e) { return e->S; }
+extern "C" int lg_engine_max_frames(const lg_engine *e) { return e->F; }
+extern "C" size_t lg_engine_pcm_stride(const lg_engine *e) { return e->pcm_stride; }
+extern "C" int16_t *lg_engine_host_pcm16(lg_engine *e) { return e->h_pcm16; }
+extern "C" float *lg_engine_host_pcmf(lg_engine *e) { return e->h_pcmf; }
+extern "C" int *lg_engine_host_nfr(lg_engine *e) { return e->h_nfr; }
+extern "C" const LgGranuleOut *lg_engine_host_gout(const lg_engine *e) { return e->h_gout; }
+extern "C" const LgFrameOut *lg_engine_host_fout(const lg_engine *e) { return e->h_fout; }
+extern "C" const float *lg_engine_last_kernel_ms(const lg_engine *e) { return e->last_ms; }
+extern "C" long lg_engine_launch_count(const lg_engine *e) { return e->launches; }
+extern "C" void *lg_engine_device_pcm16(lg_engine *e) { return e->d_pcm16; }
+
+/* initial per-stream state: lame.c:2274 lame_init_internal_flags, lame.c:962, psymodel.c:1897-1922 and :2075 */
+static void lg_initial_state(const LgDevCfg *c, LgStreamState *s)
+{
+    memset(s, 0, sizeof *s);
+    for (int i = 0; i < 4; ++i) {
+        for (int j = 0; j < LG_CBANDS; ++j) { s->nb_l1[i][j] = 1e20f; s->nb_l2[i][j] = 1e20f; }
+        for (int sb = 0; sb < LG_SBMAX_L; sb++) { s->en[i].l[sb] = 1e20f; s->thm[i].l[sb] = 1e20f; }
+        for (int j = 0; j < 3; ++j)
+            for (int sb = 0; sb < LG_SBMAX_S; sb++) { s->en[i].s[sb][j] = 1e20f; s->thm[i].s[sb][j] = 1e20f; }
+        for (int j = 0; j < 9; j++) s->last_en_subshort[i][j] = 10.f;
+    }
+    s->ath_adjust_factor = 0.01f;
+    s->ath_adjust_limit = 1.0f;
+    s->masking_lower = 1.f;
+    for (int i = 0; i < 19; i++) s->pefirbuf[i] = (float) (700 * c->mode_gr * c->channels);
+    s->slot_lag = c->frac_spf;
+    s->old_value[0] = s->old_value[1] = 180;
+    s->current_step[0] = s->current_step[1] = 4;
+}
+
+extern "C" void lg_engine_destroy(lg_engine *e)
+{
+    if (!e) return;
+    lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_xr);
+    lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout);
+    lg_dev_free(e->d_state); lg_dev_free(e->d_nfr);
+    lg_host_free(e->h_pcm16); lg_host_free(e->h_pcmf); lg_host_free(e->h_nfr); lg_host_free(e->h_gout); lg_host_free(e->h_fout);
+#ifndef LG_EMULATE
+    for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+#endif
+    free(e);
+}
+
+extern "C" int lg_engine_reset_streams(lg_engine *e, int first, int count)
+{
+    LgStreamState s0;
+    lg_initial_state(&e->hcfg, &s0);
+    for (int i = first; i < first + count && i < e->S; i++) {
+#ifdef LG_EMULATE
+        memcpy(e->d_state + i, &s0, sizeof s0);
+#else
+        LG_CHECK(cudaMemcpy(e->d_state + i, &s0, sizeof s0, cudaMemcpyHostToDevice));
+#endif
+    }
+    return 0;
+}
+
+extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device)
+{
+    if (nstreams < 1 || max_frames < 1) return NULL;
+#ifndef LG_EMULATE
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        fprintf(stderr, "lamegpu: no CUDA device available - this library has no CPU path\n");
+        return NULL;
+    }
+    if (device < 0 || device >= ndev) device = 0;
+    if (cudaSetDevice(device) != cudaSuccess) return NULL;
+#endif
+    lg_engine *e = (lg_engine *) calloc(1, sizeof *e);
+    if (!e) return NULL;
+    e->hcfg = *cfg;
+    e->S = nstreams; e->F = max_frames; e->device = device;
+    e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
+    size_t const S = nstreams, F = max_frames;
+    int bad = 0;
+    bad |= lg_dev_malloc((void **) &e->dcfg, sizeof(LgDevCfg));
+    bad |= lg_dev_malloc((void **) &e->d_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t));
+    bad |= lg_dev_malloc((void **) &e->d_sb, S * (2 * F + 1) * 2 * 576 * sizeof(float));
+    bad |= lg_dev_malloc((void **) &e->d_xr, S * 2 * F * 2 * 576 * sizeof(float));
+    bad |= lg_dev_malloc((void **) &e->d_ana, S * 2 * F * sizeof(LgAnalysis));
+    bad |= lg_dev_malloc((void **) &e->d_psy, S * 2 * F * sizeof(LgPsyOut));
+    bad |= lg_dev_malloc((void **) &e->d_frm, S * F * sizeof(LgFrameCtl));
+    bad |= lg_dev_malloc((void **) &e->d_gout, S * 2 * F * 2 * sizeof(LgGranuleOut));
+    bad |= lg_dev_malloc((void **) &e->d_fout, S * F * sizeof(LgFrameOut));
+    bad |= lg_dev_malloc((void **) &e->d_state, S * sizeof(LgStreamState));
+    bad |= lg_dev_malloc((void **) &e->d_nfr, S * sizeof(int));
+    bad |= lg_host_malloc((void **) &e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t));
+    bad |= lg_host_malloc((void **) &e->h_nfr, S * sizeof(int));
+    bad |= lg_host_malloc((void **) &e->h_gout, S * 2 * F * 2 * sizeof(LgGranuleOut));
+    bad |= lg_host_malloc((void **) &e->h_fout, S * F * sizeof(LgFrameOut));
+    if (bad) { fprintf(stderr, "lamegpu: out of memory (S=%d F=%d)\n", nstreams, max_frames); lg_engine_destroy(e); return NULL; }
+#ifdef LG_EMULATE
+    memcpy(e->dcfg, cfg, sizeof *cfg);
+#else
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+    for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
+    if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+    cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
+    cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+#endif
+    if (lg_engine_reset_streams(e, 0, nstreams) != 0) { lg_engine_destroy(e); return NULL; }
+    return e;
+}
+
+/* float staging is allocated on first use (only the float/int32/double entry points need it) */
+extern "C" int lg_engine_need_float_pcm(lg_engine *e)
+{
+    if (e->h_pcmf) return 0;
+    size_t const n = (size_t) e->S * 2 * e->pcm_stride * sizeof(float);
+    if (lg_host_malloc((void **) &e->h_pcmf, n) || lg_dev_malloc((void **) &e->d_pcmf, n)) return -1;
+    return 0;
+}
+
+/* Launch the four kernels on what is already in device memory (bench "value": inputs resident in HBM).
+ * nframes = max over streams of d_nfr[]. */
+extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
+{
+    int const S = e->S, F = e->F;
+    if (nframes < 1 || nframes > F) return -1;
+    (void) nframes;
+    const int16_t *p16 = use_float ? NULL : e->d_pcm16;
+    const float *pf = use_float ? e->d_pcmf : NULL;
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev[0], e->stream);
+#endif
+    LG_LAUNCH(lg_kernel_analysis, S * (2 * F + 1), 128, sizeof(LgSmemA), e->stream,
+              e->dcfg, p16, (int) e->pcm_stride, pf, e->d_sb, e->d_ana, e->d_nfr, 2 * F + 1);
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev[1], e->stream);
+#endif
+    LG_LAUNCH(lg_kernel_scan, S, 32, sizeof(LgSmemB), e->stream, e->dcfg, e->d_ana, e->d_psy, e->d_frm, e->d_state, e->d_nfr, F);
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev[2], e->stream);
+#endif
+    LG_LAUNCH(lg_kernel_mdct, S * 2 * F, 64, sizeof(LgSmemC), e->stream, e->dcfg, e->d_sb, e->d_psy, e->d_frm, e->d_xr, e->d_nfr, F);
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev[3], e->stream);
+#endif
+    LG_LAUNCH(lg_kernel_quant, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+              e->d_state, e->d_nfr, F);
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev[4], e->stream);
+    LG_CHECK(cudaGetLastError());
+#endif
+    e->launches += 4;
+    return 0;
+}
+
+extern "C" int lg_engine_sync(lg_engine *e)
+{
+#ifndef LG_EMULATE
+    LG_CHECK(cudaStreamSynchronize(e->stream));
+    for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->last_ms[i] = ms; }
+#endif
+    return 0;
+}
+
+/* Full step: H2D of the staged PCM + frame counts, kernels, D2H of the quantised frames, sync. */
+extern "C" int lg_engine_encode(lg_engine *e, int nframes, int use_float)
+{
+    size_t const S = e->S, F = e->F;
+    if (use_float) {
+        if (!e->h_pcmf) return -1;
+        LG_COPY_H2D(e->d_pcmf, e->h_pcmf, S * 2 * e->pcm_stride * sizeof(float), e->stream);
+    }
+    else LG_COPY_H2D(e->d_pcm16, e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t), e->stream);
+    LG_COPY_H2D(e->d_nfr, e->h_nfr, S * sizeof(int), e->stream);
+    if (lg_engine_run_device(e, nframes, use_float) != 0) return -1;
+    LG_COPY_D2H(e->h_gout, e->d_gout, S * 2 * F * 2 * sizeof(LgGranuleOut), e->stream);
+    LG_COPY_D2H(e->h_fout, e->d_fout, S * F * sizeof(LgFrameOut), e->stream);
+    return lg_engine_sync(e);
+}
+
+/* test/debug hook: copy an intermediate device buffer to the host.
+ * what: 0 sb, 1 ana, 2 psy, 3 frm, 4 xr, 5 gout, 6 fout, 7 state */
+extern "C" long lg_engine_debug_copy(lg_engine *e, int what, void *dst, size_t cap)
+{
+    size_t const S = e->S, F = e->F;
+    const void *src = NULL; size_t n = 0;
+    switch (what) {
+    case 0: src = e->d_sb; n = S * (2 * F + 1) * 2 * 576 * sizeof(float); break;
+    case 1: src = e->d_ana; n = S * 2 * F * sizeof(LgAnalysis); break;
+    case 2: src = e->d_psy; n = S * 2 * F * sizeof(LgPsyOut); break;
+    case 3: src = e->d_frm; n = S * F * sizeof(LgFrameCtl); break;
+    case 4: src = e->d_xr; n = S * 2 * F * 2 * 576 * sizeof(float); break;
+    case 5: src = e->d_gout; n = S * 2 * F * 2 * sizeof(LgGranuleOut); break;
+    case 6: src = e->d_fout; n = S * F * sizeof(LgFrameOut); break;
+    case 7: src = e->d_state; n = S * sizeof(LgStreamState); break;
+    default: return -1;
+    }
+    if (n > cap) n = cap;
+#ifdef LG_EMULATE
+    memcpy(dst, src, n);
+#else
+    if (cudaMemcpy(dst, src, n, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+#endif
+    return (long) n;
+}

@@ -1,0 +1,1308 @@
+// lg_k_quant.cuh - kernel D: the CBR quantisation / noise-shaping / Huffman bit-counting loop.
+//
+// One CTA per stream, one warp per channel ("one warp per granule/channel").  A stream's granules are
+// strictly ordered (bit reservoir ResvSize, OldValue/CurrentStep of the step-size search, scfsi between
+// granule 0 and 1), so the kernel walks frames and granules in order; the two channels of a granule are
+// independent (targ_bits is fixed before the channel loop, quantize.c:2008) and run concurrently.
+//
+// Inside a warp the 576 lines are owned pairwise (lane p owns pairs p, p+32, ... -> conflict-free 32-bit
+// shared-memory accesses of int16 pairs, 64-bit of float pairs); the 22/39 scalefactor bands are owned
+// one per lane for everything the reference sums serially per band (calc_xmin, calc_noise), so every
+// float sum keeps the reference's order.  All bit counting is integer and uses warp reductions.
+//
+// Reference: CBR_iteration_loop quantize.c:1988, outer_loop :1010, bin_search_StepSize :367,
+// balance_noise :940, amp_scalefac_bands :720, inc_scalefac_scale :808, inc_subblock_gain :847,
+// calc_xmin quantize_pvt.c:589, calc_noise :815, on_pe :428, reduce_side :492, count_bits takehiro.c:767,
+// quantize_xrpow :281, noquant_count_bits :654, choose_table :618, best_huffman_divide :884,
+// best_scalefac_store :1021, scale_bitcount :1318, reservoir.c:83-293.
+//
+// Algorithmic HBM bytes per gr.ch: read 2304 B MDCT lines + 488 B ratios, write sizeof(LgGranuleOut).
+#pragma once
+#include "lg_math.cuh"
+
+struct LgQInfo {                 /* the scalar part of the reference's gr_info (l3side.h:47), warp-uniform */
+    float xrpow_max;
+    int part2_3_length, big_values, count1, global_gain, scalefac_compress;
+    int table_select[3], subblock_gain[4];
+    int region0_count, region1_count, preflag, scalefac_scale, count1table_select, part2_length, count1bits;
+};
+struct LgQConst {                /* per gr.ch constants set by init_outer_loop / calc_xmin */
+    int block_type, sfb_lmax, sfb_smin, psy_lmax, sfbmax, psymax, sfbdivide, max_nonzero_coeff;
+};
+struct LgNoiseRes { float max_noise; int over_count, over_SSD, bits; };
+struct LgPrev { int valid, global_gain, sfb_count1; };   /* scalar part of calc_noise_data (quantize_pvt.h:75) */
+
+struct LgQWarp {
+    float xr[576], xrpow[576], save_xrpow[576];
+    int16_t ixw[576], ixb[576];
+    float l3_xmin[40], distort[40], pn_noise[40], pn_noise_log[40];
+    int   pn_step[40];
+    int   sfw[40], sfbst[40];
+    int   width[40], window[40], lstart[41];
+    int   act[64];
+    int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
+    int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
+    uint8_t line_sfb[576];
+};
+struct LgSmemD {
+    LgQWarp w[2];
+    int targ_bits[2];
+    int used_bits[2];
+    int sf_gr0[2][40];           /* granule-0 scalefactors for scfsi (takehiro.c:964) */
+    int bt_gr0[2];
+};
+
+__constant__ uint8_t LG_PRETAB[22] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0 };
+__constant__ int LG_SLEN1_N[16] = { 1, 1, 1, 1, 8, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16 };
+__constant__ int LG_SLEN2_N[16] = { 1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2, 4, 8, 4, 8 };
+__constant__ int LG_SLEN1_TAB[16] = { 0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4 };
+__constant__ int LG_SLEN2_TAB[16] = { 0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3 };
+__constant__ int LG_SCALE_SHORT[16] = { 0, 18, 36, 54, 54, 36, 54, 72, 54, 72, 90, 72, 90, 108, 108, 126 };
+__constant__ int LG_SCALE_MIXED[16] = { 0, 18, 36, 54, 51, 35, 53, 71, 52, 70, 88, 69, 87, 105, 104, 122 };
+__constant__ int LG_SCALE_LONG[16] = { 0, 10, 20, 30, 33, 21, 31, 41, 32, 42, 52, 43, 53, 63, 64, 74 };
+__constant__ int LG_HUF_NOESC[15] = { 1, 2, 5, 7, 7, 10, 10, 13, 13, 13, 13, 13, 13, 13, 13 };
+__constant__ int LG_SCFSI_BAND[5] = { 0, 6, 11, 16, 21 };
+
+/* ---------------------------------------------------------------- warp reductions (integer: order-free) */
+__device__ __forceinline__ int lg_wmax_i(int v)
+{
+#if defined(LG_EMULATE)
+    for (int d = 16; d > 0; d >>= 1) { int o = __shfl_xor_sync(LG_FULL, v, d); v = v > o ? v : o; }
+    return v;
+#else
+    return __reduce_max_sync(LG_FULL, v);
+#endif
+}
+__device__ __forceinline__ int lg_wmin_i(int v)
+{
+#if defined(LG_EMULATE)
+    for (int d = 16; d > 0; d >>= 1) { int o = __shfl_xor_sync(LG_FULL, v, d); v = v < o ? v : o; }
+    return v;
+#else
+    return __reduce_min_sync(LG_FULL, v);
+#endif
+}
+__device__ __forceinline__ unsigned lg_wsum_u(unsigned v)
+{
+#if defined(LG_EMULATE)
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(LG_FULL, v, d);
+    return v;
+#else
+    return __reduce_add_sync(LG_FULL, v);
+#endif
+}
+__device__ __forceinline__ unsigned lg_wor_u(unsigned v)
+{
+#if defined(LG_EMULATE)
+    for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(LG_FULL, v, d);
+    return v;
+#else
+    return __reduce_or_sync(LG_FULL, v);
+#endif
+}
+/* float max is exact and order-free */
+__device__ __forceinline__ float lg_wmax_f(float v)
+{
+    for (int d = 16; d > 0; d >>= 1) { float o = __shfl_xor_sync(LG_FULL, v, d); v = v > o ? v : o; }
+    return v;
+}
+
+__device__ __forceinline__ const uint8_t *lg_hlen(const LgDevCfg *__restrict__ c, int t) { return c->huff_len + c->huff_off[t]; }
+
+__device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const LgQWarp *w, const int *sf, int sfb)
+{
+    return gi.global_gain - ((sf[sfb] + (gi.preflag ? (int) LG_PRETAB[sfb < 22 ? sfb : 21] : 0)) << (gi.scalefac_scale + 1))
+         - gi.subblock_gain[w->window[sfb]] * 8;
+}
+
+/* ---------------------------------------------------------------- quantiser (takehiro.c:281 quantize_xrpow)
+ * Returns the lane's nine (x | y<<16) pairs in px[]. */
+__device__ __forceinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
+                                            const LgPrev &pv, int lane, unsigned px[9])
+{
+    int const nsfb = (qc.block_type == LG_SHORT) ? 39 : 22;
+    int const mnz = qc.max_nonzero_coeff;
+    int const prev_data_use = pv.valid && (gi.global_gain == pv.global_gain);
+    float const istep = __ldg(&c->ipow20[gi.global_gain]);
+    /* per scalefactor band: 0 keep old values, 1 quantise, 2 quantise with the 0/1 shortcut */
+    int T = 64;
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        int term = 0;
+        if (sfb < nsfb) {
+            int step = -1;
+            if (prev_data_use || qc.block_type == LG_NORM) step = lg_band_step(gi, w, w->sfw, sfb);
+            int const skip = prev_data_use && (w->pn_step[sfb] == step);
+            int const cross = (w->lstart[sfb] + w->width[sfb]) > mnz;
+            int const is01 = pv.valid && pv.sfb_count1 > 0 && sfb >= pv.sfb_count1 && w->pn_step[sfb] > 0 && step >= w->pn_step[sfb];
+            w->act[sfb] = skip ? 0 : (is01 ? 2 : 1);
+            term = !skip && cross;
+        }
+        unsigned const m = __ballot_sync(LG_FULL, term);
+        if (m && T == 64) T = 32 * r + (__ffs((int) m) - 1);
+    }
+    __syncwarp();
+    float const compareval0 = (1.0f - 0.4054f) / istep;
+    const float *adj = c->adj43asm;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        int const P = lane + 32 * j, i = 2 * P;
+        int const sfb = w->line_sfb[i];
+        int a0, a1;                       /* action for line i and i+1: 0 keep, 1 quantise, 2 shortcut, 3 zero */
+        if (T < 64) {
+            if (i > mnz) a0 = a1 = 3;
+            else {
+                a0 = (sfb == T) ? 1 : w->act[sfb];
+                a1 = (i + 1 == mnz) ? ((sfb == T) ? 1 : 3) : a0;
+            }
+        }
+        else a0 = a1 = w->act[sfb];
+        unsigned const old = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
+        float2 const xp = *reinterpret_cast<const float2 *>(&w->xrpow[i]);
+        int v0 = (int) (old & 0xffffu), v1 = (int) (old >> 16);
+        if (a0 == 1) {
+            float const xs = istep * xp.x;
+            double d = (double) xs + 8388608.0;
+            int const idx = __float_as_int((float) d) - 0x4b000000;
+            v0 = __float_as_int((float) (d + (double) __ldg(&adj[idx]))) - 0x4b000000;
+        }
+        else if (a0 == 2) v0 = (compareval0 > xp.x) ? 0 : 1;
+        else if (a0 == 3) v0 = 0;
+        if (a1 == 1) {
+            float const xs = istep * xp.y;
+            double d = (double) xs + 8388608.0;
+            int const idx = __float_as_int((float) d) - 0x4b000000;
+            v1 = __float_as_int((float) (d + (double) __ldg(&adj[idx]))) - 0x4b000000;
+        }
+        else if (a1 == 2) v1 = (compareval0 > xp.y) ? 0 : 1;
+        else if (a1 == 3) v1 = 0;
+        unsigned const nv = (unsigned) v0 | ((unsigned) v1 << 16);
+        px[j] = nv;
+        *reinterpret_cast<unsigned *>(&w->ixw[i]) = nv;
+    }
+    __syncwarp();
+}
+
+/* ---------------------------------------------------------------- Huffman table choice for one region, whole warp
+ * (takehiro.c:618 choose_table_nonMMX + count_bit_* :449-573).  The lane contributes the pairs it owns
+ * that fall in [lo, hi).  Adds the bits to *bits, returns the table. */
+__device__ __forceinline__ int lg_choose_table_warp(const LgDevCfg *__restrict__ c, const unsigned px[9], int lane, int lo, int hi, int *bits)
+{
+    int mx = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        int const i = 2 * (lane + 32 * j);
+        if (i >= lo && i < hi) {
+            int const x = (int) (px[j] & 0xffffu), y = (int) (px[j] >> 16);
+            mx = max(mx, max(x, y));
+        }
+    }
+    mx = lg_wmax_i(mx);
+    if (mx == 0) return 0;
+    if (mx > 15) {
+        if (mx > LG_IXMAX) { *bits = LG_LARGE_BITS; return -1; }
+        int const m = mx - 15;
+        int choice, choice2;
+        for (choice2 = 24; choice2 < 32; choice2++) if ((int) c->huff_linmax[choice2] >= m) break;
+        for (choice = choice2 - 8; choice < 24; choice++) if ((int) c->huff_linmax[choice] >= m) break;
+        unsigned const linbits = c->huff_xlen[choice] * 65536u + c->huff_xlen[choice2];
+        unsigned sum = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            int const i = 2 * (lane + 32 * j);
+            if (i >= lo && i < hi) {
+                unsigned x = px[j] & 0xffffu, y = px[j] >> 16;
+                if (x >= 15u) { x = 15u; sum += linbits; }
+                if (y >= 15u) { y = 15u; sum += linbits; }
+                sum += __ldg(&c->largetbl[(x << 4) + y]);
+            }
+        }
+        sum = lg_wsum_u(sum);
+        unsigned const sum2 = sum & 0xffffu;
+        sum >>= 16u;
+        if (sum > sum2) { sum = sum2; choice = choice2; }
+        *bits += (int) sum;
+        return choice;
+    }
+    int t1 = LG_HUF_NOESC[mx - 1];
+    unsigned const xlen = c->huff_xlen[t1];
+    if (mx == 1) {
+        const uint8_t *h = lg_hlen(c, 1);
+        unsigned sum = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            int const i = 2 * (lane + 32 * j);
+            if (i >= lo && i < hi) sum += __ldg(&h[2 * (px[j] & 0xffffu) + (px[j] >> 16)]);
+        }
+        *bits += (int) lg_wsum_u(sum);
+        return 1;
+    }
+    if (mx <= 3) {
+        const uint32_t *table = (t1 == 2) ? c->table23 : c->table56;
+        unsigned sum = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            int const i = 2 * (lane + 32 * j);
+            if (i >= lo && i < hi) sum += __ldg(&table[(px[j] & 0xffffu) * xlen + (px[j] >> 16)]);
+        }
+        sum = lg_wsum_u(sum);
+        unsigned const sum2 = sum & 0xffffu;
+        sum >>= 16u;
+        if (sum > sum2) { sum = sum2; t1++; }
+        *bits += (int) sum;
+        return t1;
+    }
+    {
+        const uint8_t *h1 = lg_hlen(c, t1), *h2 = lg_hlen(c, t1 + 1), *h3 = lg_hlen(c, t1 + 2);
+        unsigned s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            int const i = 2 * (lane + 32 * j);
+            if (i >= lo && i < hi) {
+                unsigned const x = (px[j] & 0xffffu) * xlen + (px[j] >> 16);
+                s1 += __ldg(&h1[x]); s2 += __ldg(&h2[x]); s3 += __ldg(&h3[x]);
+            }
+        }
+        /* each total < 2^13: two fields per word */
+        unsigned const a = lg_wsum_u(s1 | (s2 << 16));
+        s3 = lg_wsum_u(s3);
+        s1 = a & 0xffffu; s2 = a >> 16;
+        int t = t1;
+        if (s1 > s2) { s1 = s2; t++; }
+        if (s1 > s3) { s1 = s3; t = t1 + 2; }
+        *bits += (int) s1;
+        return t;
+    }
+}
+
+/* same decision by ONE lane over ix[lo..hi) in shared memory (used where many ranges are evaluated at
+ * once, one per lane: best_huffman_divide) */
+__device__ __forceinline__ int lg_choose_table_serial(const LgDevCfg *__restrict__ c, const int16_t *ix, int lo, int hi, int *bits)
+{
+    unsigned mx = 0;
+    for (int i = lo; i < hi; i++) { unsigned const v = (unsigned) ix[i]; if (v > mx) mx = v; }
+    if (mx == 0) return 0;
+    if (mx > 15) {
+        if (mx > LG_IXMAX) { *bits = LG_LARGE_BITS; return -1; }
+        int const m = (int) mx - 15;
+        int choice, choice2;
+        for (choice2 = 24; choice2 < 32; choice2++) if ((int) c->huff_linmax[choice2] >= m) break;
+        for (choice = choice2 - 8; choice < 24; choice++) if ((int) c->huff_linmax[choice] >= m) break;
+        unsigned const linbits = c->huff_xlen[choice] * 65536u + c->huff_xlen[choice2];
+        unsigned sum = 0;
+        for (int i = lo; i < hi; i += 2) {
+            unsigned x = (unsigned) ix[i], y = (unsigned) ix[i + 1];
+            if (x >= 15u) { x = 15u; sum += linbits; }
+            if (y >= 15u) { y = 15u; sum += linbits; }
+            sum += __ldg(&c->largetbl[(x << 4) + y]);
+        }
+        unsigned const sum2 = sum & 0xffffu;
+        sum >>= 16u;
+        if (sum > sum2) { sum = sum2; choice = choice2; }
+        *bits += (int) sum;
+        return choice;
+    }
+    int t1 = LG_HUF_NOESC[mx - 1];
+    unsigned const xlen = c->huff_xlen[t1];
+    if (mx == 1) {
+        const uint8_t *h = lg_hlen(c, 1);
+        unsigned sum = 0;
+        for (int i = lo; i < hi; i += 2) sum += __ldg(&h[2 * ix[i] + ix[i + 1]]);
+        *bits += (int) sum;
+        return 1;
+    }
+    if (mx <= 3) {
+        const uint32_t *table = (t1 == 2) ? c->table23 : c->table56;
+        unsigned sum = 0;
+        for (int i = lo; i < hi; i += 2) sum += __ldg(&table[(unsigned) ix[i] * xlen + (unsigned) ix[i + 1]]);
+        unsigned const sum2 = sum & 0xffffu;
+        sum >>= 16u;
+        if (sum > sum2) { sum = sum2; t1++; }
+        *bits += (int) sum;
+        return t1;
+    }
+    const uint8_t *h1 = lg_hlen(c, t1), *h2 = lg_hlen(c, t1 + 1), *h3 = lg_hlen(c, t1 + 2);
+    unsigned s1 = 0, s2 = 0, s3 = 0;
+    for (int i = lo; i < hi; i += 2) {
+        unsigned const x = (unsigned) ix[i] * xlen + (unsigned) ix[i + 1];
+        s1 += __ldg(&h1[x]); s2 += __ldg(&h2[x]); s3 += __ldg(&h3[x]);
+    }
+    int t = t1;
+    if (s1 > s2) { s1 = s2; t++; }
+    if (s1 > s3) { s1 = s3; t = t1 + 2; }
+    *bits += (int) s1;
+    return t;
+}
+
+/* count1 quadruples [bigv, count1) counted with both count1 books (warp) */
+__device__ __forceinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, const int16_t *ix, int bigv, int count1, int lane, int *a1, int *a2)
+{
+    const uint8_t *t32l = lg_hlen(c, 32), *t33l = lg_hlen(c, 33);
+    unsigned s1 = 0, s2 = 0;
+    int const nq = (count1 - bigv) >> 2;
+    for (int k = lane; k < nq; k += 32) {
+        int const i = count1 - 4 * k;
+        int const p = ((ix[i - 4] * 2 + ix[i - 3]) * 2 + ix[i - 2]) * 2 + ix[i - 1];
+        s1 += __ldg(&t32l[p]); s2 += __ldg(&t33l[p]);
+    }
+    unsigned const a = lg_wsum_u(s1 | (s2 << 16));
+    *a1 = (int) (a & 0xffffu);
+    *a2 = (int) (a >> 16);
+}
+
+/* takehiro.c:654 noquant_count_bits (use_best_huffman == 2 is not on this path) */
+__device__ __forceinline__ int lg_noquant_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
+                                                     LgPrev *pv, const unsigned px[9], int lane)
+{
+    int bits = 0, a1, a2;
+    int i = ((qc.max_nonzero_coeff + 2) >> 1) << 1;
+    if (i > 576) i = 576;
+    if (pv) pv->sfb_count1 = 0;
+    int hi_nz = -1, hi_big = -1;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        int const P = lane + 32 * j;
+        if (2 * P < i) {
+            if (px[j] != 0u) hi_nz = P;
+            if ((px[j] & 0xfffefffeu) != 0u) hi_big = P;
+        }
+    }
+    hi_nz = lg_wmax_i(hi_nz);
+    hi_big = lg_wmax_i(hi_big);
+    int const c1p = hi_nz + 1;
+    gi.count1 = 2 * c1p;
+    int const nquads = (c1p - 1 - hi_big) >> 1;
+    i = gi.count1 - 4 * nquads;
+    lg_count1_bits(c, w->ixw, i, gi.count1, lane, &a1, &a2);
+    bits = a1;
+    gi.count1table_select = 0;
+    if (a1 > a2) { bits = a2; gi.count1table_select = 1; }
+    gi.count1bits = bits;
+    gi.big_values = i;
+    if (i == 0) return bits;
+    if (qc.block_type == LG_SHORT) {
+        a1 = 3 * c->sfb_s[3];
+        if (a1 > gi.big_values) a1 = gi.big_values;
+        a2 = gi.big_values;
+    }
+    else if (qc.block_type == LG_NORM) {
+        a1 = gi.region0_count = c->bv_scf[i - 2];
+        a2 = gi.region1_count = c->bv_scf[i - 1];
+        a2 = c->sfb_l[a1 + a2 + 2];
+        a1 = c->sfb_l[a1 + 1];
+        if (a2 < i) gi.table_select[2] = lg_choose_table_warp(c, px, lane, a2, i, &bits);
+    }
+    else {
+        gi.region0_count = 7;
+        gi.region1_count = LG_SBMAX_L - 1 - 7 - 1;
+        a1 = c->sfb_l[7 + 1];
+        a2 = i;
+        if (a1 > a2) a1 = a2;
+    }
+    a1 = a1 < i ? a1 : i;
+    a2 = a2 < i ? a2 : i;
+    if (0 < a1) gi.table_select[0] = lg_choose_table_warp(c, px, lane, 0, a1, &bits);
+    if (a1 < a2) gi.table_select[1] = lg_choose_table_warp(c, px, lane, a1, a2, &bits);
+    if (pv && qc.block_type == LG_NORM) {
+        int sfb = 0;
+        while (c->sfb_l[sfb] < gi.big_values) sfb++;
+        pv->sfb_count1 = sfb;
+    }
+    return bits;
+}
+
+/* takehiro.c:767 count_bits; pv == nullptr is the reference's prev_noise == 0 */
+__device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev *pv, int lane)
+{
+    float const wlim = (LG_IXMAX) / __ldg(&c->ipow20[gi.global_gain]);
+    if (gi.xrpow_max > wlim) return LG_LARGE_BITS;
+    unsigned px[9];
+    LgPrev none; none.valid = 0; none.global_gain = 0; none.sfb_count1 = 0;
+    lg_quantize(c, w, gi, qc, pv ? *pv : none, lane, px);
+    return lg_noquant_count_bits(c, w, gi, qc, pv, px, lane);
+}
+
+/* ---------------------------------------------------------------- quantize_pvt.c:815 calc_noise: one lane per band */
+__device__ __forceinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
+                                              LgNoiseRes *res, LgPrev *pv, int lane)
+{
+    int over = 0, ssd = 0;
+    float max_noise = -20.0f;
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        if (sfb < qc.psymax) {
+            int const s = lg_band_step(gi, w, w->sfw, sfb);
+            float const r_l3_xmin = 1.f / w->l3_xmin[sfb];
+            float distort_, noise;
+            if (pv->valid && w->pn_step[sfb] == s) {
+                distort_ = r_l3_xmin * w->pn_noise[sfb];
+                noise = w->pn_noise_log[sfb];
+            }
+            else {
+                float const step = __ldg(&c->pow20[s + LG_QMAX2]);
+                int const width = w->width[sfb];
+                int j = w->lstart[sfb];
+                int l = width >> 1;
+                if ((j + width) > qc.max_nonzero_coeff) {
+                    int const usefullsize = qc.max_nonzero_coeff - j + 1;
+                    l = usefullsize > 0 ? usefullsize >> 1 : 0;
+                }
+                /* quantize_pvt.c:750 calc_noise_core_c */
+                noise = 0;
+                if (j > gi.count1) {
+                    while (l--) {
+                        float t;
+                        t = w->xr[j]; j++; noise += t * t;
+                        t = w->xr[j]; j++; noise += t * t;
+                    }
+                }
+                else if (j > gi.big_values) {
+                    while (l--) {
+                        float t;
+                        t = fabsf(w->xr[j]) - (w->ixw[j] ? step : 0.f); j++; noise += t * t;
+                        t = fabsf(w->xr[j]) - (w->ixw[j] ? step : 0.f); j++; noise += t * t;
+                    }
+                }
+                else {
+                    while (l--) {
+                        float t;
+                        t = fabsf(w->xr[j]) - __ldg(&c->pow43[w->ixw[j]]) * step; j++; noise += t * t;
+                        t = fabsf(w->xr[j]) - __ldg(&c->pow43[w->ixw[j]]) * step; j++; noise += t * t;
+                    }
+                }
+                w->pn_step[sfb] = s;
+                w->pn_noise[sfb] = noise;
+                distort_ = r_l3_xmin * noise;
+                noise = (float) LG_FAST_LOG10_D(c->log_table, (distort_ > 1E-20f ? distort_ : 1E-20f));
+                w->pn_noise_log[sfb] = noise;
+            }
+            w->distort[sfb] = distort_;
+            if (noise > 0.0) {
+                int tmp = (int) (noise * 10 + .5);
+                if (tmp < 1) tmp = 1;
+                ssd += tmp * tmp;
+                over++;
+            }
+            max_noise = max_noise > noise ? max_noise : noise;
+        }
+    }
+    pv->global_gain = gi.global_gain;
+    res->over_count = (int) lg_wsum_u((unsigned) over);
+    res->over_SSD = (int) lg_wsum_u((unsigned) ssd);
+    res->max_noise = lg_wmax_f(max_noise);
+    __syncwarp();
+}
+
+/* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount */
+__device__ __forceinline__ int lg_scale_bitcount(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int *sf, int lane)
+{
+    const int *tab;
+    if (qc.block_type == LG_SHORT) tab = LG_SCALE_SHORT;
+    else {
+        tab = LG_SCALE_LONG;
+        if (!gi.preflag) {
+            int bad = 0;
+            if (lane >= 11 && lane < LG_SBPSY_L) bad = sf[lane] < (int) LG_PRETAB[lane];
+            if (!__any_sync(LG_FULL, bad)) {
+                gi.preflag = 1;
+                if (lane >= 11 && lane < LG_SBPSY_L) sf[lane] -= LG_PRETAB[lane];
+                __syncwarp();
+            }
+        }
+    }
+    int m1 = 0, m2 = 0;
+    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) {
+        if (sfb < qc.sfbdivide) m1 = max(m1, sf[sfb]); else m2 = max(m2, sf[sfb]);
+    }
+    m1 = lg_wmax_i(m1);
+    m2 = lg_wmax_i(m2);
+    gi.part2_length = LG_LARGE_BITS;
+    for (int k = 0; k < 16; k++)
+        if (m1 < LG_SLEN1_N[k] && m2 < LG_SLEN2_N[k] && gi.part2_length > tab[k]) {
+            gi.part2_length = tab[k];
+            gi.scalefac_compress = k;
+        }
+    return gi.part2_length == LG_LARGE_BITS;
+}
+
+/* quantize.c:540 loop_break */
+__device__ __forceinline__ int lg_loop_break(const LgQWarp *w, const LgQInfo &gi, const LgQConst &qc, const int *sf, int lane)
+{
+    int unamp = 0;
+    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32)
+        if (sf[sfb] + gi.subblock_gain[w->window[sfb]] == 0) unamp = 1;
+    return __any_sync(LG_FULL, unamp) ? 0 : 1;
+}
+
+/* multiply the lines of the flagged bands (act[sfb] != 0 -> factor in fac[]) and track xrpow_max */
+__device__ __forceinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const float *fac /* shared, per sfb, 0 = untouched */, int lane)
+{
+    float mx = gi.xrpow_max;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        int const i = 2 * (lane + 32 * j);
+        float const f = fac[w->line_sfb[i]];
+        if (f != 0.f) {
+            float2 v = *reinterpret_cast<float2 *>(&w->xrpow[i]);
+            v.x *= f; v.y *= f;
+            *reinterpret_cast<float2 *>(&w->xrpow[i]) = v;
+            if (v.x > mx) mx = v.x;
+            if (v.y > mx) mx = v.y;
+        }
+    }
+    gi.xrpow_max = lg_wmax_f(mx);
+    __syncwarp();
+}
+
+/* quantize.c:720 amp_scalefac_bands (noise_shaping_amp 0 and 1; 2/3 belong to quality <= 1) */
+__device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+{
+    float const ifqstep34 = (gi.scalefac_scale == 0) ? (float) 1.29683955465100964055 : (float) 1.68179283050742922612;
+    float trigger = 0;
+    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (trigger < w->distort[sfb]) trigger = w->distort[sfb];
+    trigger = lg_wmax_f(trigger);
+    if (c->noise_shaping_amp == 1) {
+        if (trigger > 1.0) trigger = (float) sqrt((double) trigger);      /* pow(trigger, .5), see lg_math.cuh */
+        else trigger = (float) (trigger * .95);
+    }
+    else {
+        if (trigger > 1.0) trigger = 1.0f;
+        else trigger = (float) (trigger * .95);
+    }
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        if (sfb < 40) {
+            float f = 0.f;
+            if (sfb < qc.sfbmax && !(w->distort[sfb] < trigger)) { w->sfw[sfb]++; f = ifqstep34; }
+            reinterpret_cast<float *>(w->act)[sfb] = f;
+        }
+    }
+    __syncwarp();
+    lg_scale_bands(w, gi, reinterpret_cast<const float *>(w->act), lane);
+}
+
+/* quantize.c:808 inc_scalefac_scale */
+__device__ __forceinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+{
+    float const ifqstep34 = (float) 1.29683955465100964055;
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        if (sfb < 40) {
+            float f = 0.f;
+            if (sfb < qc.sfbmax) {
+                int s = w->sfw[sfb];
+                if (gi.preflag) s += LG_PRETAB[sfb < 22 ? sfb : 21];
+                if (s & 1) { s++; f = ifqstep34; }
+                w->sfw[sfb] = s >> 1;
+            }
+            reinterpret_cast<float *>(w->act)[sfb] = f;
+        }
+    }
+    __syncwarp();
+    lg_scale_bands(w, gi, reinterpret_cast<const float *>(w->act), lane);
+    gi.preflag = 0;
+    gi.scalefac_scale = 1;
+}
+
+/* quantize.c:847 inc_subblock_gain (short blocks only; sfb_lmax == 0 because mixed blocks are never used) */
+__device__ __forceinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+{
+    int *scalefac = w->sfw;
+    float *fac = reinterpret_cast<float *>(w->act);
+    for (int window = 0; window < 3; window++) {
+        int s1 = 0, s2 = 0;
+        for (int sfb = qc.sfb_lmax + window + 3 * lane; sfb < qc.sfbmax; sfb += 96) {
+            if (sfb < qc.sfbdivide) s1 = max(s1, scalefac[sfb]); else s2 = max(s2, scalefac[sfb]);
+        }
+        s1 = lg_wmax_i(s1);
+        s2 = lg_wmax_i(s2);
+        if (s1 < 16 && s2 < 8) continue;
+        if (gi.subblock_gain[window] >= 7) return 1;
+        gi.subblock_gain[window]++;
+        for (int r = 0; r < 2; r++) { int const k = lane + 32 * r; if (k < 40) fac[k] = 0.f; }
+        __syncwarp();
+        {
+            int const sfb = qc.sfb_lmax + window + 3 * lane;
+            if (sfb < qc.sfbmax) {
+                int s = scalefac[sfb];
+                s = s - (4 >> gi.scalefac_scale);
+                if (s >= 0) scalefac[sfb] = s;
+                else {
+                    scalefac[sfb] = 0;
+                    fac[sfb] = __ldg(&c->ipow20[210 + (s << (gi.scalefac_scale + 1))]);
+                }
+            }
+            /* the band after sfbmax in this window (sfb12) always follows the gain: IPOW20(202) */
+            if (lane == 0) fac[qc.sfbmax + window] = __ldg(&c->ipow20[202]);
+        }
+        __syncwarp();
+        lg_scale_bands(w, gi, fac, lane);
+    }
+    return 0;
+}
+
+/* quantize.c:940 balance_noise */
+__device__ __forceinline__ int lg_balance_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+{
+    lg_amp_scalefac_bands(c, w, gi, qc, lane);
+    int status = lg_loop_break(w, gi, qc, w->sfw, lane);
+    if (status) return 0;
+    status = lg_scale_bitcount(w, gi, qc, w->sfw, lane);
+    if (!status) return 1;
+    if (c->noise_shaping > 1) {
+        if (!gi.scalefac_scale) { lg_inc_scalefac_scale(w, gi, qc, lane); status = 0; }
+        else if (qc.block_type == LG_SHORT && c->subblock_gain > 0)
+            status = lg_inc_subblock_gain(c, w, gi, qc, lane) || lg_loop_break(w, gi, qc, w->sfw, lane);
+    }
+    if (!status) status = lg_scale_bitcount(w, gi, qc, w->sfw, lane);
+    return !status;
+}
+
+/* quantize.c:585 quant_compare, mode 9 (the only one the bitrate presets select) */
+__device__ __forceinline__ int lg_quant_compare(const LgNoiseRes &best, const LgNoiseRes &calc)
+{
+    int better;
+    if (best.over_count > 0) {
+        better = calc.over_SSD <= best.over_SSD;
+        if (calc.over_SSD == best.over_SSD) better = calc.bits < best.bits;
+    }
+    else better = ((calc.max_noise < 0) && ((calc.max_noise * 10 + calc.bits) <= (best.max_noise * 10 + best.bits)));
+    if (best.over_count == 0) better = better && calc.bits < best.bits;
+    return better;
+}
+
+/* copy work -> best or best -> work (the reference's gr_info struct assignment) */
+__device__ __forceinline__ void lg_copy_ix_sf(int16_t *dix, const int16_t *six, int *dsf, const int *ssf, int lane)
+{
+    for (int i = lane; i < 288; i += 32) reinterpret_cast<unsigned *>(dix)[i] = reinterpret_cast<const unsigned *>(six)[i];
+    for (int i = lane; i < 40; i += 32) dsf[i] = ssf[i];
+    __syncwarp();
+}
+__device__ __forceinline__ void lg_copy_f576(float *d, const float *s, int lane)
+{
+    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(d)[i] = reinterpret_cast<const float4 *>(s)[i];
+    __syncwarp();
+}
+
+/* quantize.c:367 bin_search_StepSize */
+__device__ __forceinline__ int lg_bin_search(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int desired_rate,
+                                             int *old_value, int *current_step, int lane)
+{
+    int nBits, CurrentStep = *current_step, flag_GoneOver = 0;
+    int const start = *old_value;
+    int Direction = 0;
+    gi.global_gain = start;
+    desired_rate -= gi.part2_length;
+    for (;;) {
+        int step;
+        nBits = lg_count_bits(c, w, gi, qc, nullptr, lane);
+        if (CurrentStep == 1 || nBits == desired_rate) break;
+        if (nBits > desired_rate) {
+            if (Direction == 2) flag_GoneOver = 1;
+            if (flag_GoneOver) CurrentStep /= 2;
+            Direction = 1;
+            step = CurrentStep;
+        }
+        else {
+            if (Direction == 1) flag_GoneOver = 1;
+            if (flag_GoneOver) CurrentStep /= 2;
+            Direction = 2;
+            step = -CurrentStep;
+        }
+        gi.global_gain += step;
+        if (gi.global_gain < 0) { gi.global_gain = 0; flag_GoneOver = 1; }
+        if (gi.global_gain > 255) { gi.global_gain = 255; flag_GoneOver = 1; }
+    }
+    while (nBits > desired_rate && gi.global_gain < 255) {
+        gi.global_gain++;
+        nBits = lg_count_bits(c, w, gi, qc, nullptr, lane);
+    }
+    *current_step = (start - gi.global_gain >= 4) ? 4 : 2;
+    *old_value = gi.global_gain;
+    gi.part2_3_length = nBits;
+    return nBits;
+}
+
+/* quantize.c:1010 outer_loop.  On return the work set (gi, sfw, ixw) holds the chosen quantisation. */
+__device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int targ_bits,
+                                              int *old_value, int *current_step, int lane)
+{
+    (void) lg_bin_search(c, w, gi, qc, targ_bits, old_value, current_step, lane);
+    if (!c->noise_shaping) return;
+    LgPrev pv; pv.valid = 1; pv.global_gain = 0; pv.sfb_count1 = 0;
+    for (int i = lane; i < 40; i += 32) { w->pn_step[i] = 0; w->pn_noise[i] = 0; w->pn_noise_log[i] = 0; }
+    __syncwarp();
+    LgNoiseRes best_noise;
+    lg_calc_noise(c, w, gi, qc, &best_noise, &pv, lane);
+    best_noise.bits = gi.part2_3_length;
+    LgQInfo best = gi;                            /* cod_info_w = *cod_info: from here gi is the work copy */
+    lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
+    lg_copy_f576(w->save_xrpow, w->xrpow, lane);
+    int age = 0, best_part2_3_length = 9999999, bEndOfSearch = 0, bRefine = 0, best_ggain_pass1 = 0;
+    while (!bEndOfSearch) {
+        do {
+            LgNoiseRes noise_info;
+            int const search_limit = 3;
+            int maxggain = 255;
+            if (c->sfb21_extra) {
+                if (w->distort[qc.sfbmax] > 1.0) break;
+                if (qc.block_type == LG_SHORT && (w->distort[qc.sfbmax + 1] > 1.0 || w->distort[qc.sfbmax + 2] > 1.0)) break;
+            }
+            if (lg_balance_noise(c, w, gi, qc, lane) == 0) break;
+            if (gi.scalefac_scale) maxggain = 254;
+            int const huff_bits = targ_bits - gi.part2_length;
+            if (huff_bits <= 0) break;
+            while ((gi.part2_3_length = lg_count_bits(c, w, gi, qc, &pv, lane)) > huff_bits && gi.global_gain <= maxggain)
+                gi.global_gain++;
+            if (gi.global_gain > maxggain) break;
+            if (best_noise.over_count == 0) {
+                while ((gi.part2_3_length = lg_count_bits(c, w, gi, qc, &pv, lane)) > best_part2_3_length && gi.global_gain <= maxggain)
+                    gi.global_gain++;
+                if (gi.global_gain > maxggain) break;
+            }
+            lg_calc_noise(c, w, gi, qc, &noise_info, &pv, lane);
+            noise_info.bits = gi.part2_3_length;
+            if (lg_quant_compare(best_noise, noise_info)) {
+                best_part2_3_length = best.part2_3_length;
+                best_noise = noise_info;
+                best = gi;
+                lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
+                age = 0;
+                lg_copy_f576(w->save_xrpow, w->xrpow, lane);
+            }
+            else if (c->full_outer_loop == 0) {
+                if (++age > search_limit && best_noise.over_count == 0) break;
+                if ((c->noise_shaping_amp == 3) && bRefine && age > 30) break;
+                if ((c->noise_shaping_amp == 3) && bRefine && (gi.global_gain - best_ggain_pass1) > 15) break;
+            }
+        } while ((gi.global_gain + gi.scalefac_scale) < 255);
+        if (c->noise_shaping_amp == 3) {
+            if (!bRefine) {
+                gi = best;
+                lg_copy_ix_sf(w->ixw, w->ixb, w->sfw, w->sfbst, lane);
+                lg_copy_f576(w->xrpow, w->save_xrpow, lane);
+                age = 0;
+                best_ggain_pass1 = gi.global_gain;
+                bRefine = 1;
+            }
+            else bEndOfSearch = 1;
+        }
+        else bEndOfSearch = 1;
+    }
+    gi = best;
+    lg_copy_ix_sf(w->ixw, w->ixb, w->sfw, w->sfbst, lane);
+}
+
+/* ---------------------------------------------------------------- quantize_pvt.c:589 calc_xmin: one lane per band */
+__device__ __forceinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQConst &qc, const LgXmin *en, const LgXmin *thm,
+                                             float ath_adjust_factor, int lane)
+{
+    float const eps = (float) 2.2204460492503131e-016;   /* DBL_EPSILON stored in a float */
+    /* long bands */
+    if (lane < qc.psy_lmax) {
+        int const gsfb = lane;
+        float xmin = lg_ath_adjust(c, ath_adjust_factor, c->ath_l[gsfb], c->ath_floor, c->athfixpoint);
+        xmin *= c->longfact[gsfb];
+        int const width = w->width[gsfb];
+        int j = w->lstart[gsfb];
+        float const rh1 = xmin / width;
+        float rh2 = eps, en0 = 0.0f, rh3;
+        for (int l = 0; l < width; ++l) {
+            float const xa = w->xr[j++];
+            float const x2 = xa * xa;
+            en0 += x2;
+            rh2 += (x2 < rh1) ? x2 : rh1;
+        }
+        if (en0 < xmin) rh3 = en0;
+        else if (rh2 < xmin) rh3 = xmin;
+        else rh3 = rh2;
+        xmin = rh3;
+        float const e = en->l[gsfb];
+        if (e > 1e-12f) {
+            float x = en0 * thm->l[gsfb] / e;
+            x *= c->longfact[gsfb];
+            if (xmin < x) xmin = x;
+        }
+        xmin = ((double) xmin > 2.2204460492503131e-016) ? xmin : eps;
+        w->l3_xmin[gsfb] = xmin;
+    }
+    /* highest non-zero line */
+    int k = 0;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+        int const i = 2 * (lane + 32 * j);
+        if (fabsf(w->xr[i + 1]) > 1e-12f) k = i + 1;
+        else if (i > 0 && fabsf(w->xr[i]) > 1e-12f && k < i) k = i;
+    }
+    int max_nonzero = lg_wmax_i(k);
+    if (qc.block_type != LG_SHORT) max_nonzero |= 1;
+    else { max_nonzero /= 6; max_nonzero *= 6; max_nonzero += 5; }
+    if (c->sfb21_extra == 0 && c->samplerate < 44000) {
+        int const limit = (qc.block_type != LG_SHORT) ? c->sfb_l[21] - 1 : 3 * c->sfb_s[12] - 1;
+        if (max_nonzero > limit) max_nonzero = limit;
+    }
+    qc.max_nonzero_coeff = max_nonzero;
+    /* short bands: one lane per sfb handles its three windows */
+    {
+        int const sfb = qc.sfb_smin + lane;
+        int const gsfb = qc.psy_lmax + 3 * lane;
+        if (gsfb < qc.psymax) {
+            float tmpATH = lg_ath_adjust(c, ath_adjust_factor, c->ath_s[sfb], c->ath_floor, c->athfixpoint);
+            tmpATH *= c->shortfact[sfb];
+            int const width = w->width[gsfb];
+            int j = w->lstart[gsfb];
+            float xm[3];
+            for (int b = 0; b < 3; b++) {
+                float en0 = 0.0f, xmin, rh2 = eps, rh3;
+                float const rh1 = tmpATH / width;
+                for (int l = 0; l < width; ++l) {
+                    float const xa = w->xr[j++];
+                    float const x2 = xa * xa;
+                    en0 += x2;
+                    rh2 += (x2 < rh1) ? x2 : rh1;
+                }
+                if (en0 < tmpATH) rh3 = en0;
+                else if (rh2 < tmpATH) rh3 = tmpATH;
+                else rh3 = rh2;
+                xmin = rh3;
+                float const e = en->s[sfb][b];
+                if (e > 1e-12f) {
+                    float x = en0 * thm->s[sfb][b] / e;
+                    x *= c->shortfact[sfb];
+                    if (xmin < x) xmin = x;
+                }
+                xmin = ((double) xmin > 2.2204460492503131e-016) ? xmin : eps;
+                xm[b] = xmin;
+            }
+            if (c->use_temporal) {
+                if (xm[0] > xm[1]) xm[1] += (xm[0] - xm[1]) * c->decay;
+                if (xm[1] > xm[2]) xm[2] += (xm[1] - xm[2]) * c->decay;
+            }
+            w->l3_xmin[gsfb] = xm[0]; w->l3_xmin[gsfb + 1] = xm[1]; w->l3_xmin[gsfb + 2] = xm[2];
+        }
+    }
+    __syncwarp();
+}
+
+/* ---------------------------------------------------------------- takehiro.c:884 best_huffman_divide */
+__device__ __forceinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict__ c, LgQWarp *w, int bigv, int lane)
+{
+    const int16_t *ix = w->ixw;
+    if (lane < 23) w->r01_bits[lane] = LG_LARGE_BITS;
+    if (lane < 16) {
+        int const a1 = c->sfb_l[lane + 1];
+        int bits = 0, t = 0;
+        if (a1 < bigv) t = lg_choose_table_serial(c, ix, 0, a1, &bits);
+        w->r0b[lane] = bits; w->r0t[lane] = t;
+    }
+    for (int q = lane; q < 128; q += 32) {
+        int const r0 = q >> 3, r1 = q & 7;
+        int const a1 = c->sfb_l[r0 + 1], a2 = c->sfb_l[r0 + r1 + 2];
+        int bits = LG_LARGE_BITS, t = 0;
+        if (a1 < bigv && a2 < bigv) { bits = 0; t = lg_choose_table_serial(c, ix, a1, a2, &bits); }
+        w->comb_bits[q] = bits; w->comb_tbl[q] = t;
+    }
+    __syncwarp();
+    if (lane < 23) {
+        int best = LG_LARGE_BITS, div = 0, t0 = 0, t1 = 0;
+        for (int r0 = 0; r0 < 16; r0++) {
+            int const r1 = lane - r0;
+            if (r1 < 0 || r1 > 7) continue;
+            if (w->comb_bits[r0 * 8 + r1] == LG_LARGE_BITS) continue;
+            int const bits = w->r0b[r0] + w->comb_bits[r0 * 8 + r1];
+            if (best > bits) { best = bits; div = r0; t0 = w->r0t[r0]; t1 = w->comb_tbl[r0 * 8 + r1]; }
+        }
+        w->r01_bits[lane] = best; w->r01_div[lane] = div; w->r0_tbl[lane] = t0; w->r1_tbl[lane] = t1;
+    }
+    __syncwarp();
+}
+/* takehiro.c:847 recalc_divide_sub: g2 is the candidate base, gi the current best */
+__device__ __forceinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &g2, LgQInfo &gi, int lane)
+{
+    int const bigv = g2.big_values;
+    /* every lane evaluates one r2 candidate; the sequential scan then replays the reference's order */
+    int r2 = lane + 2, bits_l = LG_LARGE_BITS, r2t = 0, a2 = 0;
+    if (r2 < LG_SBMAX_L + 1) {
+        a2 = c->sfb_l[r2];
+        if (a2 < bigv && w->r01_bits[r2 - 2] != LG_LARGE_BITS) {
+            bits_l = w->r01_bits[r2 - 2] + g2.count1bits;
+            r2t = lg_choose_table_serial(c, w->ixw, a2, bigv, &bits_l);
+        }
+    }
+    for (r2 = 2; r2 < LG_SBMAX_L + 1; r2++) {
+        int const a = c->sfb_l[r2];
+        if (a >= bigv) break;
+        int const base = w->r01_bits[r2 - 2] + g2.count1bits;
+        if (gi.part2_3_length <= base) break;
+        int const bits = __shfl_sync(LG_FULL, bits_l, r2 - 2);
+        int const tbl = __shfl_sync(LG_FULL, r2t, r2 - 2);
+        if (gi.part2_3_length <= bits) continue;
+        gi = g2;
+        gi.part2_3_length = bits;
+        gi.region0_count = w->r01_div[r2 - 2];
+        gi.region1_count = r2 - 2 - w->r01_div[r2 - 2];
+        gi.table_select[0] = w->r0_tbl[r2 - 2];
+        gi.table_select[1] = w->r1_tbl[r2 - 2];
+        gi.table_select[2] = tbl;
+    }
+}
+__device__ __forceinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+{
+    const int16_t *ix = w->ixw;
+    LgQInfo g2 = gi;
+    if (qc.block_type == LG_NORM) {
+        lg_recalc_divide_init(c, w, gi.big_values, lane);
+        lg_recalc_divide_sub(c, w, g2, gi, lane);
+    }
+    int i = g2.big_values;
+    if (i == 0 || (unsigned) (ix[i - 2] | ix[i - 1]) > 1) return;
+    i = gi.count1 + 2;
+    if (i > 576) return;
+    g2 = gi;
+    g2.count1 = i;
+    int a1, a2;
+    lg_count1_bits(c, ix, g2.big_values - 2, i, lane, &a1, &a2);
+    i = g2.big_values - 2;
+    g2.big_values = i;
+    g2.count1table_select = 0;
+    if (a1 > a2) { a1 = a2; g2.count1table_select = 1; }
+    g2.count1bits = a1;
+    if (qc.block_type == LG_NORM) lg_recalc_divide_sub(c, w, g2, gi, lane);
+    else {
+        g2.part2_3_length = a1;
+        a1 = c->sfb_l[7 + 1];
+        if (a1 > i) a1 = i;
+        int t0 = g2.table_select[0], t1 = g2.table_select[1], bits = g2.part2_3_length;
+        if (lane == 0) {
+            if (a1 > 0) t0 = lg_choose_table_serial(c, ix, 0, a1, &bits);
+            if (i > a1) t1 = lg_choose_table_serial(c, ix, a1, i, &bits);
+        }
+        g2.table_select[0] = __shfl_sync(LG_FULL, t0, 0);
+        g2.table_select[1] = __shfl_sync(LG_FULL, t1, 0);
+        g2.part2_3_length = __shfl_sync(LG_FULL, bits, 0);
+        if (gi.part2_3_length > g2.part2_3_length) gi = g2;
+    }
+}
+
+/* ---------------------------------------------------------------- takehiro.c:1021 best_scalefac_store (+ :964 scfsi_calc) */
+__device__ __forceinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
+                                                       int gr, const int *sf_gr0, int bt_gr0, uint8_t scfsi[4], int lane)
+{
+    int *sf = w->sfw;
+    int recalc = 0;
+    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) {
+        int const j0 = w->lstart[sfb], j1 = j0 + w->width[sfb];
+        int l = j0;
+        for (; l < j1; ++l) if (w->ixw[l] != 0) break;
+        if (l == j1) { sf[sfb] = -2; recalc = 1; }
+    }
+    recalc = __any_sync(LG_FULL, recalc) ? -2 : 0;
+    __syncwarp();
+    if (!gi.scalefac_scale && !gi.preflag) {
+        unsigned s = 0;
+        for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (sf[sfb] > 0) s |= (unsigned) sf[sfb];
+        s = lg_wor_u(s);
+        if (!(s & 1) && s != 0) {
+            for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (sf[sfb] > 0) sf[sfb] >>= 1;
+            gi.scalefac_scale = recalc = 1;
+            __syncwarp();
+        }
+    }
+    if (!gi.preflag && qc.block_type != LG_SHORT && c->mode_gr == 2) {
+        int bad = 0;
+        if (lane >= 11 && lane < LG_SBPSY_L) bad = (sf[lane] < (int) LG_PRETAB[lane] && sf[lane] != -2);
+        if (!__any_sync(LG_FULL, bad)) {
+            if (lane >= 11 && lane < LG_SBPSY_L && sf[lane] > 0) sf[lane] -= LG_PRETAB[lane];
+            gi.preflag = recalc = 1;
+            __syncwarp();
+        }
+    }
+    for (int i = 0; i < 4; i++) scfsi[i] = 0;
+    if (c->mode_gr == 2 && gr == 1 && bt_gr0 != LG_SHORT && qc.block_type != LG_SHORT) {
+        /* scfsi_calc */
+        for (int i = 0; i < 4; i++) {
+            int diff = 0;
+            int const sfb = LG_SCFSI_BAND[i] + lane;
+            if (sfb < LG_SCFSI_BAND[i + 1]) diff = (sf_gr0[sfb] != sf[sfb] && sf[sfb] >= 0);
+            if (!__any_sync(LG_FULL, diff)) {
+                if (sfb < LG_SCFSI_BAND[i + 1]) sf[sfb] = -1;
+                scfsi[i] = 1;
+            }
+        }
+        __syncwarp();
+        int s1 = 0, c1 = 0, s2 = 0, c2 = 0;
+        if (lane < 11) { if (sf[lane] != -1) { c1 = 1; s1 = sf[lane]; } }
+        else if (lane < LG_SBPSY_L) { if (sf[lane] != -1) { c2 = 1; s2 = sf[lane]; } }
+        /* the reference's max starts at 0, so negative entries (-2) never raise it */
+        s1 = lg_wmax_i(s1 > 0 ? s1 : 0); s2 = lg_wmax_i(s2 > 0 ? s2 : 0);
+        unsigned const cc = lg_wsum_u((unsigned) c1 | ((unsigned) c2 << 8));
+        c1 = (int) (cc & 0xff); c2 = (int) (cc >> 8);
+        for (int i = 0; i < 16; i++)
+            if (s1 < LG_SLEN1_N[i] && s2 < LG_SLEN2_N[i]) {
+                int const cbits = LG_SLEN1_TAB[i] * c1 + LG_SLEN2_TAB[i] * c2;
+                if (gi.part2_length > cbits) { gi.part2_length = cbits; gi.scalefac_compress = i; }
+            }
+        recalc = 0;
+    }
+    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (sf[sfb] == -2) sf[sfb] = 0;
+    __syncwarp();
+    if (recalc) (void) lg_scale_bitcount(w, gi, qc, sf, lane);
+}
+
+/* ---------------------------------------------------------------- bit budget (reservoir.c, quantize_pvt.c:428/:492): lane-uniform scalar code */
+__device__ __forceinline__ int lg_frame_bits(const LgDevCfg *__restrict__ c, int padding)
+{
+    return 8 * ((c->version + 1) * 72000 * c->brate / c->samplerate + padding);
+}
+__device__ __forceinline__ void lg_resv_max_bits(const LgDevCfg *__restrict__ c, int resv_size, int resv_max, int mean_bits, int *targ_bits, int *extra_bits, int cbr)
+{
+    int add_bits, targBits, extraBits;
+    int ResvSize = resv_size;
+    if (cbr) ResvSize += mean_bits;
+    targBits = mean_bits;
+    if (ResvSize * 10 > resv_max * 9) {
+        add_bits = ResvSize - (resv_max * 9) / 10;
+        targBits += add_bits;
+    }
+    else {
+        add_bits = 0;
+        if (!c->disable_reservoir) targBits = (int) (targBits - .1 * mean_bits);
+    }
+    extraBits = (ResvSize < (resv_max * 6) / 10 ? ResvSize : (resv_max * 6) / 10);
+    extraBits -= add_bits;
+    if (extraBits < 0) extraBits = 0;
+    *targ_bits = targBits;
+    *extra_bits = extraBits;
+}
+__device__ __forceinline__ int lg_on_pe(const LgDevCfg *__restrict__ c, int resv_size, int resv_max, const float pe[2], int targ_bits[2], int mean_bits, int cbr)
+{
+    int extra_bits = 0, tbits, bits, add_bits[2] = { 0, 0 }, max_bits, ch;
+    int const nch = c->channels;
+    lg_resv_max_bits(c, resv_size, resv_max, mean_bits, &tbits, &extra_bits, cbr);
+    max_bits = tbits + extra_bits;
+    if (max_bits > LG_MAX_BITS_PER_GRANULE) max_bits = LG_MAX_BITS_PER_GRANULE;
+    for (bits = 0, ch = 0; ch < nch; ++ch) {
+        targ_bits[ch] = LG_MAX_BITS_PER_CHANNEL < tbits / nch ? LG_MAX_BITS_PER_CHANNEL : tbits / nch;
+        add_bits[ch] = (int) ((double) (targ_bits[ch] * pe[ch]) / 700.0 - targ_bits[ch]);
+        if (add_bits[ch] > mean_bits * 3 / 4) add_bits[ch] = mean_bits * 3 / 4;
+        if (add_bits[ch] < 0) add_bits[ch] = 0;
+        if (add_bits[ch] + targ_bits[ch] > LG_MAX_BITS_PER_CHANNEL)
+            add_bits[ch] = 0 > LG_MAX_BITS_PER_CHANNEL - targ_bits[ch] ? 0 : LG_MAX_BITS_PER_CHANNEL - targ_bits[ch];
+        bits += add_bits[ch];
+    }
+    if (bits > extra_bits && bits > 0)
+        for (ch = 0; ch < nch; ++ch) add_bits[ch] = extra_bits * add_bits[ch] / bits;
+    for (ch = 0; ch < nch; ++ch) { targ_bits[ch] += add_bits[ch]; extra_bits -= add_bits[ch]; }
+    for (bits = 0, ch = 0; ch < nch; ++ch) bits += targ_bits[ch];
+    if (bits > LG_MAX_BITS_PER_GRANULE)
+        for (ch = 0; ch < nch; ++ch) { targ_bits[ch] *= LG_MAX_BITS_PER_GRANULE; targ_bits[ch] /= bits; }
+    return max_bits;
+}
+__device__ __forceinline__ void lg_reduce_side(int targ_bits[2], float ms_ener_ratio, int mean_bits, int max_bits)
+{
+    int move_bits;
+    float fac = (float) (.33 * (.5 - ms_ener_ratio) / .5);
+    if (fac < 0) fac = 0;
+    if (fac > .5) fac = .5f;
+    move_bits = (int) (fac * .5 * (targ_bits[0] + targ_bits[1]));
+    if (move_bits > LG_MAX_BITS_PER_CHANNEL - targ_bits[0]) move_bits = LG_MAX_BITS_PER_CHANNEL - targ_bits[0];
+    if (move_bits < 0) move_bits = 0;
+    if (targ_bits[1] >= 125) {
+        if (targ_bits[1] - move_bits > 125) {
+            if (targ_bits[0] < mean_bits) targ_bits[0] += move_bits;
+            targ_bits[1] -= move_bits;
+        }
+        else { targ_bits[0] += targ_bits[1] - 125; targ_bits[1] = 125; }
+    }
+    move_bits = targ_bits[0] + targ_bits[1];
+    if (move_bits > max_bits) {
+        targ_bits[0] = (max_bits * targ_bits[0]) / move_bits;
+        targ_bits[1] = (max_bits * targ_bits[1]) / move_bits;
+    }
+}
+
+/* ---------------------------------------------------------------- the kernel */
+__global__ void __launch_bounds__(64)
+lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy,
+                const LgFrameCtl *__restrict__ frm, LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout,
+                LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes)
+{
+    LG_DYN_SMEM(LgSmemD, sm);
+    int const lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
+    int const stream = blockIdx.x;
+    int const nch = cfg->channels;
+    LgStreamState *st = state + stream;
+    LgQWarp *w = &sm->w[ch];
+    int resv_size = st->resv_size, main_data_begin = st->main_data_begin;
+    int old_value = st->old_value[ch], current_step = st->current_step[ch];
+
+    int const my_frames = nfr[stream];
+    for (int frame = 0; frame < my_frames; frame++) {
+        const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
+        int const padding = F->padding, mode_ext = F->mode_ext;
+        /* reservoir.c:83 ResvFrameBegin */
+        int const frameLength = lg_frame_bits(cfg, padding);
+        int const mean_bits = (frameLength - cfg->sideinfo_len * 8) / cfg->mode_gr;
+        int resv_max = cfg->buffer_constraint - frameLength;
+        {
+            int const resvLimit = (8 * 256) * cfg->mode_gr - 8;
+            if (resv_max > resvLimit) resv_max = resvLimit;
+            if (resv_max < 0 || cfg->disable_reservoir) resv_max = 0;
+        }
+        uint8_t scfsi[4] = { 0, 0, 0, 0 };
+        for (int gr = 0; gr < 2; gr++) {
+            int const gb = 2 * frame + gr;
+            const LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
+            int targ_bits[2];
+            float pe[2] = { F->pe_use[gr][0], F->pe_use[gr][1] };
+            int const max_bits = lg_on_pe(cfg, resv_size, resv_max, pe, targ_bits, mean_bits, gr);
+            if (mode_ext == 2) lg_reduce_side(targ_bits, F->ms_ener_ratio[gr], mean_bits, max_bits);
+            int used = 0;
+            if (ch < nch) {
+                LgQInfo gi;
+                LgQConst qc;
+                int const rch = (mode_ext == 2) ? ch + 2 : ch;
+                const LgXmin *en = &P->en[rch], *thm = &P->thm[rch];
+                /* quantize.c:226 init_outer_loop (the short-block reorder was done by kernel C) */
+                gi.part2_3_length = 0; gi.big_values = 0; gi.count1 = 0; gi.global_gain = 210; gi.scalefac_compress = 0;
+                gi.table_select[0] = gi.table_select[1] = gi.table_select[2] = 0;
+                gi.subblock_gain[0] = gi.subblock_gain[1] = gi.subblock_gain[2] = gi.subblock_gain[3] = 0;
+                gi.region0_count = 0; gi.region1_count = 0; gi.preflag = 0; gi.scalefac_scale = 0;
+                gi.count1table_select = 0; gi.part2_length = 0; gi.count1bits = 0; gi.xrpow_max = 0;
+                qc.block_type = P->block_type[ch];
+                qc.sfb_lmax = LG_SBPSY_L; qc.sfb_smin = LG_SBPSY_S;
+                qc.psy_lmax = cfg->sfb21_extra ? LG_SBMAX_L : LG_SBPSY_L;
+                qc.psymax = qc.psy_lmax; qc.sfbmax = qc.sfb_lmax; qc.sfbdivide = 11;
+                if (qc.block_type == LG_SHORT) {
+                    qc.sfb_smin = 0; qc.sfb_lmax = 0;
+                    qc.psymax = 3 * (cfg->sfb21_extra ? LG_SBMAX_S : LG_SBPSY_S);
+                    qc.sfbmax = 3 * LG_SBPSY_S;
+                    qc.sfbdivide = qc.sfbmax - 18;
+                    qc.psy_lmax = 0;
+                }
+                qc.max_nonzero_coeff = 575;
+                for (int r = 0; r < 2; r++) {
+                    int const k = lane + 32 * r;
+                    if (k <= 40) {
+                        int ws = 0, wn = 3, ls = 576;
+                        if (qc.block_type == LG_SHORT) {
+                            if (k < 39) {
+                                int const sfb = k / 3;
+                                ws = cfg->sfb_s[sfb + 1] - cfg->sfb_s[sfb];
+                                wn = k % 3;
+                                ls = 3 * cfg->sfb_s[sfb] + wn * ws;
+                            }
+                        }
+                        else if (k < LG_SBMAX_L) { ws = cfg->sfb_l[k + 1] - cfg->sfb_l[k]; ls = cfg->sfb_l[k]; }
+                        if (k < 40) { w->width[k] = ws; w->window[k] = wn; w->sfw[k] = 0; }
+                        w->lstart[k] = ls;
+                    }
+                }
+                __syncwarp();
+                {   /* line -> band map and the lines themselves */
+                    const float *src = xr_in + (((size_t) stream * 2 * nframes + gb) * 2 + ch) * 576;
+                    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(w->xr)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                    int const nb = (qc.block_type == LG_SHORT) ? 39 : 22;
+                    for (int b = lane; b < nb; b += 32)
+                        for (int i = w->lstart[b]; i < w->lstart[b] + w->width[b]; i++) w->line_sfb[i] = (uint8_t) b;
+                }
+                __syncwarp();
+                /* quantize.c:110 init_xrpow (upper = 575) */
+                float mx = 0.f, amax = 0.f;
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    int const i = 2 * (lane + 32 * j);
+                    float const t0 = fabsf(w->xr[i]), t1 = fabsf(w->xr[i + 1]);
+                    float const p0 = (float) sqrt((double) t0 * sqrt((double) t0));
+                    float const p1 = (float) sqrt((double) t1 * sqrt((double) t1));
+                    w->xrpow[i] = p0; w->xrpow[i + 1] = p1;
+                    if (p0 > mx) mx = p0;
+                    if (p1 > mx) mx = p1;
+                    if (t0 > amax) amax = t0;
+                    if (t1 > amax) amax = t1;
+                    *reinterpret_cast<unsigned *>(&w->ixw[i]) = 0u;
+                }
+                gi.xrpow_max = lg_wmax_f(mx);
+                amax = lg_wmax_f(amax);
+                __syncwarp();
+                /* sum > 1e-20 ?  A serial non-negative float sum is >= its largest term, so only a spectrum
+                 * whose largest magnitude is itself <= 1e-20 needs the exact serial sum of the reference. */
+                int nonzero = amax > (float) 1E-20;
+                if (!nonzero && amax > 0.f) {
+                    float sum = 0;
+                    for (int i = 0; i < 576; ++i) sum += fabsf(w->xr[i]);
+                    nonzero = sum > (float) 1E-20;
+                }
+                if (nonzero) {
+                    lg_calc_xmin(cfg, w, qc, en, thm, F->ath_adjust_factor, lane);
+                    lg_outer_loop(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, lane);
+                }
+                /* quantize.c:1213 iteration_finish_one */
+                lg_best_scalefac_store(cfg, w, gi, qc, gr, sm->sf_gr0[ch], sm->bt_gr0[ch], scfsi, lane);
+                if (cfg->use_best_huffman == 1) lg_best_huffman_divide(cfg, w, gi, qc, lane);
+                used = gi.part2_3_length + gi.part2_length;
+                if (gr == 0) {
+                    for (int i = lane; i < 40; i += 32) sm->sf_gr0[ch][i] = w->sfw[i];
+                    if (lane == 0) sm->bt_gr0[ch] = qc.block_type;
+                }
+                /* hand the granule to the bit packer */
+                LgGranuleOut *o = gout + (((size_t) stream * 2 * nframes + gb) * 2 + ch);
+#pragma unroll
+                for (int j = 0; j < 9; j++) {
+                    int const i = 2 * (lane + 32 * j);
+                    int v0 = w->ixw[i], v1 = w->ixw[i + 1];
+                    if (w->xr[i] < 0.0f) v0 = -v0;
+                    if (w->xr[i + 1] < 0.0f) v1 = -v1;
+                    *reinterpret_cast<unsigned *>(&o->ix[i]) = ((unsigned) v0 & 0xffffu) | ((unsigned) v1 << 16);
+                }
+                for (int i = lane; i < 40; i += 32) o->scalefac[i] = (int8_t) (i < 39 ? w->sfw[i] : 0);
+                if (lane == 0) {
+                    o->part2_3_length = (int16_t) gi.part2_3_length; o->part2_length = (int16_t) gi.part2_length;
+                    o->big_values = (int16_t) gi.big_values; o->count1 = (int16_t) gi.count1;
+                    o->global_gain = (uint8_t) gi.global_gain; o->scalefac_compress = (uint8_t) gi.scalefac_compress;
+                    o->block_type = (uint8_t) qc.block_type; o->mixed_block_flag = 0;
+                    for (int i = 0; i < 3; i++) { o->table_select[i] = (uint8_t) gi.table_select[i]; o->subblock_gain[i] = (uint8_t) gi.subblock_gain[i]; }
+                    o->region0_count = (uint8_t) gi.region0_count; o->region1_count = (uint8_t) gi.region1_count;
+                    o->preflag = (uint8_t) gi.preflag; o->scalefac_scale = (uint8_t) gi.scalefac_scale;
+                    o->count1table_select = (uint8_t) gi.count1table_select;
+                    o->sfbmax = (uint8_t) qc.sfbmax; o->sfbdivide = (uint8_t) qc.sfbdivide; o->pad_ = 0;
+                    sm->used_bits[ch] = used;
+                }
+            }
+            else if (lane == 0) sm->used_bits[ch] = 0;
+            __syncthreads();
+            resv_size -= sm->used_bits[0] + sm->used_bits[1];        /* reservoir.c:226 ResvAdjust */
+            __syncthreads();
+        }
+        /* reservoir.c:239 ResvFrameEnd + the main_data_begin recurrence of format_bitstream (bitstream.c:937) */
+        {
+            int stuffingBits = 0, over_bits, drain_pre = 0, drain_post = 0;
+            resv_size += mean_bits * cfg->mode_gr;
+            if ((over_bits = resv_size % 8) != 0) stuffingBits += over_bits;
+            over_bits = (resv_size - stuffingBits) - resv_max;
+            if (over_bits > 0) stuffingBits += over_bits;
+            int const mdb_bytes = (main_data_begin * 8 < stuffingBits ? main_data_begin * 8 : stuffingBits) / 8;
+            drain_pre += 8 * mdb_bytes;
+            stuffingBits -= 8 * mdb_bytes;
+            resv_size -= 8 * mdb_bytes;
+            int const mdb_header = main_data_begin - mdb_bytes;   /* value written into this frame's side info */
+            drain_post += stuffingBits;
+            resv_size -= stuffingBits;
+            main_data_begin = resv_size / 8;                       /* bitstream.c:937-951: mdb*8 == ResvSize */
+            LgFrameOut *fo = fout + (size_t) stream * nframes + frame;
+            if (lane == 0) {
+                if (ch == 0) {
+                    fo->main_data_begin = mdb_header; fo->drain_pre = drain_pre; fo->drain_post = drain_post;
+                    fo->padding = padding; fo->mode_ext = mode_ext; fo->resv_size = resv_size;
+                }
+                if (ch < nch) for (int i = 0; i < 4; i++) fo->scfsi[ch][i] = scfsi[i];
+                else for (int i = 0; i < 4; i++) fo->scfsi[ch][i] = 0;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (ch == 0) { st->resv_size = resv_size; st->main_data_begin = main_data_begin; }
+        st->old_value[ch] = old_value;
+        st->current_step[ch] = current_step;
+    }
+}

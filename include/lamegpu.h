@@ -1,0 +1,105 @@
+/* lamegpu.h - C ABI of the B200 batched MP3 encode library (liblamegpu.so).
+ *
+ * Two faces:
+ *
+ *  1. The libmp3lame entry points of the hot path, with the reference's names, argument meaning and
+ *     error codes, so an application written against include/lame.h of LAME 3.99.5 links unchanged.
+ *     Each declaration cites the reference declaration it replaces.  A handle is a lane of a GPU batch
+ *     engine: lame_encode_buffer() queues PCM and returns whatever finished bytes exist (the reference
+ *     already documents that the return value "can be 0", lame.h:687); lame_encode_flush() drains.
+ *
+ *  2. An additive batch interface (lamegpu_batch_*) that feeds many independent streams per call - the
+ *     form a GPU needs and what bench.py measures.  Plain pointers and sizes only.
+ *
+ * Scope of this build: MPEG-1 Layer III, 32/44.1/48 kHz, CBR 112..320 kbps (no resampling), stereo /
+ * joint stereo / mono, quality 3..9.  Anything else makes lame_init_params()/lamegpu_batch_open() fail
+ * with -1 - there is no silent fallback and no CPU path.
+ */
+#ifndef LAMEGPU_H
+#define LAMEGPU_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ 1. libmp3lame-compatible face */
+struct lame_global_struct;
+typedef struct lame_global_struct lame_global_flags;          /* include/lame.h:149-150 */
+typedef lame_global_flags *lame_t;
+
+typedef enum vbr_mode_e { vbr_off = 0, vbr_mt, vbr_rh, vbr_abr, vbr_mtrh, vbr_max_indicator, vbr_default = vbr_mtrh } vbr_mode; /* lame.h:49-57 */
+typedef enum MPEG_mode_e { STEREO = 0, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET, MAX_INDICATOR } MPEG_mode;               /* lame.h:61-68 */
+
+lame_global_flags *lame_init(void);                                                  /* lame.h:168  NULL on OOM */
+int  lame_set_in_samplerate(lame_global_flags *, int);                               /* lame.h:194 */
+int  lame_get_in_samplerate(const lame_global_flags *);                              /* lame.h:195 */
+int  lame_set_num_channels(lame_global_flags *, int);                                /* lame.h:198 */
+int  lame_get_num_channels(const lame_global_flags *);                               /* lame.h:199 */
+int  lame_set_out_samplerate(lame_global_flags *, int);                              /* lame.h:222 */
+int  lame_get_out_samplerate(const lame_global_flags *);                             /* lame.h:223 */
+int  lame_set_brate(lame_global_flags *, int);                                       /* lame.h:330 */
+int  lame_get_brate(const lame_global_flags *);                                      /* lame.h:331 */
+int  lame_set_quality(lame_global_flags *, int);                                     /* lame.h:282 */
+int  lame_get_quality(const lame_global_flags *);                                    /* lame.h:283 */
+int  lame_set_mode(lame_global_flags *, MPEG_mode);                                  /* lame.h:290 */
+MPEG_mode lame_get_mode(const lame_global_flags *);                                  /* lame.h:291 */
+int  lame_set_VBR(lame_global_flags *, vbr_mode);                                    /* lame.h:433  only vbr_off is accepted */
+vbr_mode lame_get_VBR(const lame_global_flags *);                                    /* lame.h:434 */
+int  lame_set_bWriteVbrTag(lame_global_flags *, int);                                /* lame.h:244  the Info tag frame is not produced */
+int  lame_get_bWriteVbrTag(const lame_global_flags *);                               /* lame.h:245 */
+int  lame_init_params(lame_global_flags *);                                          /* lame.h:636  <0 on error/unsupported */
+int  lame_get_framesize(const lame_global_flags *);                                  /* lame.h:602 */
+int  lame_get_frameNum(const lame_global_flags *);                                   /* lame.h:608 */
+int  lame_get_encoder_delay(const lame_global_flags *);                              /* lame.h:588 */
+int  lame_encode_buffer(lame_global_flags *, const short int pcm_l[], const short int pcm_r[], const int nsamples,
+                        unsigned char *mp3buf, const int mp3buf_size);               /* lame.h:715 */
+int  lame_encode_buffer_interleaved(lame_global_flags *, short int pcm[], int num_samples,
+                                    unsigned char *mp3buf, int mp3buf_size);         /* lame.h:730 */
+int  lame_encode_buffer_ieee_float(lame_t, const float pcm_l[], const float pcm_r[], const int nsamples,
+                                   unsigned char *mp3buf, const int mp3buf_size);    /* lame.h:760  +/-1.0 full scale */
+int  lame_encode_flush(lame_global_flags *, unsigned char *mp3buf, int size);        /* lame.h:856 */
+int  lame_close(lame_global_flags *);                                                /* lame.h:977 */
+const char *get_lame_short_version(void);                                            /* lame.h:646 */
+
+/* ------------------------------------------------------------------ 2. batch face */
+typedef struct lamegpu_batch lamegpu_batch;
+
+/* One engine for `nstreams` independent streams that share a configuration.  `frames_per_launch` is how
+ * many frames of every stream one GPU launch covers (the reservoir makes a stream's frames sequential,
+ * so parallelism comes from the number of streams).  Returns NULL on unsupported configuration, missing
+ * GPU or allocation failure (a message goes to stderr). */
+lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int mode /* MPEG_mode or -1 */,
+                                  int quality /* 0..9 or -1 */, int nstreams, int frames_per_launch, int device);
+void lamegpu_batch_close(lamegpu_batch *b);
+
+/* Feed nsamples[i] samples to stream i (pcm_l[i]/pcm_r[i]; pcm_r may be NULL for mono) and encode every
+ * frame that became complete.  Bytes produced for stream i are appended at out[i] (capacity out_cap[i]);
+ * out_bytes[i] receives the count.  Bytes that do not fit stay queued for the next call.
+ * Returns the number of frames encoded over all streams, or <0 on error. */
+long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const short *const *pcm_r, const int *nsamples,
+                          unsigned char *const *out, const int *out_cap, int *out_bytes);
+
+/* Same contract as lame_encode_flush for every stream: pads, encodes the last frames, drains the bit
+ * reservoir into ancillary data. */
+long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int *out_cap, int *out_bytes);
+
+/* contiguous convenience form used by language bindings: pcm is [nstreams][2][nsamples] int16, out is
+ * [nstreams][out_stride] bytes */
+long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsamples, unsigned char *out, int out_stride, int *out_bytes);
+long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_stride, int *out_bytes);
+
+/* measurement hooks (bench.py): run the device pipeline once more on the PCM already resident in HBM,
+ * without copies or packing; per-kernel CUDA-event times of the last launch in ms [analysis, scan, mdct, quant] */
+int  lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes);
+int  lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes);
+int  lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[4]);
+long lamegpu_batch_kernel_launches(const lamegpu_batch *b);
+int  lamegpu_batch_set_threads(lamegpu_batch *b, int nthreads);
+long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap);   /* tests: intermediate device buffers */
+size_t lamegpu_sizeof_granule_out(void);
+size_t lamegpu_sizeof_analysis(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -2,6 +2,7 @@
  * Restates the per-frame driver lame_encode_mp3_frame (encoder.c:305) with adjust_ATH (:56) and
  * the PCM buffering of lame_encode_buffer_sample_t (lame.c:1671) / lame_encode_flush (lame.c:2042). */
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 #include "lame_port.h"
 
@@ -128,6 +129,7 @@ static int encode_frame(lp_encoder *e, const float *inbuf_l, const float *inbuf_
             }
         }
     }
+    if (getenv("LP_DEBUG")) fprintf(stderr, "port frame %d: pe %g %g %g %g peMS %g %g %g %g bt %d %d %d %d\n", e->frame_number, pe[0][0], pe[0][1], pe[1][0], pe[1][1], pe_MS[0][0], pe_MS[0][1], pe_MS[1][0], pe_MS[1][1], e->tt[0][0].block_type, e->tt[0][1].block_type, e->tt[1][0].block_type, e->tt[1][1].block_type);
     adjust_ath(e);
     lp_mdct_sub48(e, inbuf[0], inbuf[1]);
     e->mode_ext = 0;

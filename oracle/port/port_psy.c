@@ -603,6 +603,9 @@ static void ms_thresholds(const float eb[4][LP_CBANDS], float thr[4][LP_CBANDS],
     }
 }
 
+/* test hook: the en/thm state right after each of the two calls of a frame */
+lp_xmin lp_dbg_en_after[2][4], lp_dbg_thm_after[2][4];
+
 /* psymodel.c:1397 L3psycho_anal_vbr */
 int lp_psycho(lp_encoder *e, const float *const buffer[2], int gr_out, lp_ratio masking_ratio[2][2],
               lp_ratio masking_ms[2][2], float percep_entropy[2], float percep_ms_entropy[2], float energy[4],
@@ -720,6 +723,8 @@ int lp_psycho(lp_encoder *e, const float *const buffer[2], int gr_out, lp_ratio 
         }
     }
     for (chn = 0; chn < n_chn_psy; chn++) psv->last_attacks[chn] = ns_attacks[chn][2];
+    memcpy(lp_dbg_en_after[gr_out], psv->en, sizeof psv->en);
+    memcpy(lp_dbg_thm_after[gr_out], psv->thm, sizeof psv->thm);
 
     /* psymodel.c:1289 vbrpsy_apply_block_type */
     for (chn = 0; chn < cfg->channels; chn++) {

@@ -14,6 +14,7 @@ static int siggen(const char *kind, short *l, short *r, int n, int sr, const cha
     int i;
     sg_state = 88172645463325252ULL;
     if (!strcmp(kind, "noise")) { for (i = 0; i < n; i++) { l[i] = sg_uniform(12000); r[i] = sg_uniform(12000); } return 0; }
+    if (!strcmp(kind, "gap")) { for (i = 0; i < n; i++) { l[i] = sg_uniform(12000); r[i] = sg_uniform(12000); if (i < 6000 || (i > 20000 && i < 23000)) l[i] = r[i] = 0; } return 0; }
     if (!strcmp(kind, "silence")) { memset(l, 0, n * 2); memset(r, 0, n * 2); return 0; }
     if (!strcmp(kind, "sine")) {
         for (i = 0; i < n; i++) {
