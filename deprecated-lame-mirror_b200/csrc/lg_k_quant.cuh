@@ -32,7 +32,7 @@ struct LgQConst {                /* per gr.ch constants set by init_outer_loop /
 struct LgNoiseRes { float max_noise; int over_count, over_SSD, bits; };
 struct LgPrev { int valid, global_gain, sfb_count1; };   /* scalar part of calc_noise_data (quantize_pvt.h:75) */
 
-struct LgQWarp {
+struct __attribute__((aligned(16))) LgQWarp {
     float xr[576], xrpow[576], save_xrpow[576];
     int16_t ixw[576], ixb[576];
     float l3_xmin[40], distort[40], pn_noise[40], pn_noise_log[40];

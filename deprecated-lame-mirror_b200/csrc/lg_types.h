@@ -128,7 +128,7 @@ typedef struct {
     uint8_t global_gain, scalefac_compress, block_type, mixed_block_flag;
     uint8_t table_select[3], subblock_gain[3];
     uint8_t region0_count, region1_count, preflag, scalefac_scale, count1table_select, sfbmax, sfbdivide, pad_;
-} LgGranuleOut;
+} __attribute__((aligned(16))) LgGranuleOut;
 
 typedef struct {
     int32_t main_data_begin, drain_pre, drain_post, padding, mode_ext, resv_size;

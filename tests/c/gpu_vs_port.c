@@ -46,6 +46,7 @@ int main(int argc, char **argv)
     for (s = 0; s < S; s++) { po[s] = out[s] + olen[s]; ocap[s] = cap - olen[s]; }
     frames += lamegpu_batch_flush(b, po, ocap, ob);
     for (s = 0; s < S; s++) olen[s] += ob[s];
+    { float ms[4]; lamegpu_batch_kernel_ms(b, ms); printf("last launch kernel ms: analysis %.3f scan %.3f mdct %.3f quant %.3f\n", ms[0], ms[1], ms[2], ms[3]); }
     lamegpu_batch_close(b);
     for (s = 0; s < S; s++) {
         lp_encoder *e = lp_open(sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality);
