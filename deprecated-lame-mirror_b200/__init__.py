@@ -1,0 +1,234 @@
+"""B200 batched MP3 (MPEG-1 Layer III, CBR) encoder behind the libmp3lame API - Python host side.
+
+The product is the C-ABI library ``liblamegpu.so`` (``csrc/``, declared in ``include/lamegpu.h``): hand-written
+sm_100a CUDA kernels for the encode hot path plus the thin host code the reference keeps serial (PCM
+buffering, bit packing).  This module is only the ctypes binding to it, mirroring the reference's operator
+interface:
+
+* :class:`Encoder` - one stream, same call sequence and return conventions as ``lame_init`` /
+  ``lame_set_*`` / ``lame_init_params`` / ``lame_encode_buffer`` / ``lame_encode_flush`` / ``lame_close``
+  (``include/lame.h`` of LAME 3.99.5).
+* :class:`BatchEncoder` - many independent streams per call (``lamegpu_batch_*``), the form the GPU needs.
+
+There is no CPU path: if ``liblamegpu.so`` is missing or no CUDA device is visible, construction raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblamegpu.so")
+
+STEREO, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET = 0, 1, 2, 3, 4
+VBR_OFF = 0
+
+_lib = None
+
+
+class LameGpuError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen liblamegpu.so and declare every prototype of include/lamegpu.h.  Raises if it is not built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise LameGpuError("%s is not built - run `python __graft_entry__.py build` (nvcc, sm_100a); "
+                           "there is no CPU fallback" % p)
+    lib = ctypes.CDLL(p)
+    c_int, c_long, c_void_p, c_char_p = ctypes.c_int, ctypes.c_long, ctypes.c_void_p, ctypes.c_char_p
+    P = ctypes.POINTER
+    sig = {
+        "lame_init": (c_void_p, []),
+        "lame_set_in_samplerate": (c_int, [c_void_p, c_int]), "lame_get_in_samplerate": (c_int, [c_void_p]),
+        "lame_set_num_channels": (c_int, [c_void_p, c_int]), "lame_get_num_channels": (c_int, [c_void_p]),
+        "lame_set_out_samplerate": (c_int, [c_void_p, c_int]), "lame_get_out_samplerate": (c_int, [c_void_p]),
+        "lame_set_brate": (c_int, [c_void_p, c_int]), "lame_get_brate": (c_int, [c_void_p]),
+        "lame_set_quality": (c_int, [c_void_p, c_int]), "lame_get_quality": (c_int, [c_void_p]),
+        "lame_set_mode": (c_int, [c_void_p, c_int]), "lame_get_mode": (c_int, [c_void_p]),
+        "lame_set_VBR": (c_int, [c_void_p, c_int]), "lame_get_VBR": (c_int, [c_void_p]),
+        "lame_set_bWriteVbrTag": (c_int, [c_void_p, c_int]), "lame_get_bWriteVbrTag": (c_int, [c_void_p]),
+        "lame_init_params": (c_int, [c_void_p]),
+        "lame_get_framesize": (c_int, [c_void_p]), "lame_get_frameNum": (c_int, [c_void_p]),
+        "lame_get_encoder_delay": (c_int, [c_void_p]),
+        "lame_encode_buffer": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_interleaved": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_ieee_float": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_flush": (c_int, [c_void_p, c_void_p, c_int]),
+        "lame_close": (c_int, [c_void_p]),
+        "get_lame_short_version": (c_char_p, []),
+        "lamegpu_batch_open": (c_void_p, [c_int] * 8),
+        "lamegpu_batch_close": (None, [c_void_p]),
+        "lamegpu_batch_encode": (c_long, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "lamegpu_batch_flush": (c_long, [c_void_p, c_void_p, c_void_p, c_void_p]),
+        "lamegpu_batch_encode_packed": (c_long, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+        "lamegpu_batch_flush_packed": (c_long, [c_void_p, c_void_p, c_int, c_void_p]),
+        "lamegpu_batch_rerun_device": (c_int, [c_void_p, c_int]),
+        "lamegpu_batch_stage_packed": (c_int, [c_void_p, c_void_p, c_int]),
+        "lamegpu_batch_kernel_ms": (c_int, [c_void_p, P(ctypes.c_float)]),
+        "lamegpu_batch_kernel_launches": (c_long, [c_void_p]),
+        "lamegpu_batch_set_threads": (c_int, [c_void_p, c_int]),
+        "lamegpu_batch_debug_copy": (c_long, [c_void_p, c_int, c_void_p, ctypes.c_size_t]),
+        "lamegpu_sizeof_granule_out": (ctypes.c_size_t, []),
+        "lamegpu_sizeof_analysis": (ctypes.c_size_t, []),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)          # AttributeError here = the library does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = [
+    "lame_init", "lame_set_in_samplerate", "lame_get_in_samplerate", "lame_set_num_channels", "lame_get_num_channels",
+    "lame_set_out_samplerate", "lame_get_out_samplerate", "lame_set_brate", "lame_get_brate", "lame_set_quality",
+    "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
+    "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
+    "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
+    "lame_close", "get_lame_short_version", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
+    "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
+    "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
+    "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis",
+]
+
+
+def _as_i16(a):
+    a = np.ascontiguousarray(a, dtype=np.int16)
+    return a
+
+
+class Encoder:
+    """One stream through the libmp3lame-compatible entry points (same semantics and error codes)."""
+
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1):
+        self._lib = load_library()
+        self._h = self._lib.lame_init()
+        if not self._h:
+            raise LameGpuError("lame_init failed")
+        L = self._lib
+        L.lame_set_in_samplerate(self._h, samplerate)
+        L.lame_set_num_channels(self._h, channels)
+        if brate:
+            L.lame_set_brate(self._h, brate)
+        if mode != NOT_SET:
+            L.lame_set_mode(self._h, mode)
+        if quality >= 0:
+            L.lame_set_quality(self._h, quality)
+        L.lame_set_bWriteVbrTag(self._h, 0)
+        rc = L.lame_init_params(self._h)
+        if rc < 0:
+            L.lame_close(self._h)
+            self._h = None
+            raise LameGpuError("lame_init_params returned %d (unsupported configuration or no GPU)" % rc)
+        self.channels = channels
+
+    def encode(self, left, right=None):
+        """lame_encode_buffer: int16 PCM in, bytes out (possibly empty)."""
+        l = _as_i16(left)
+        r = _as_i16(right) if right is not None else l
+        n = int(l.shape[0])
+        buf = np.empty(int(1.25 * n) + 7200 + 65536, dtype=np.uint8)
+        rc = self._lib.lame_encode_buffer(self._h, l.ctypes.data, r.ctypes.data, n, buf.ctypes.data, buf.size)
+        if rc < 0:
+            raise LameGpuError("lame_encode_buffer returned %d" % rc)
+        return buf[:rc].tobytes()
+
+    def flush(self):
+        buf = np.empty(65536 + 7200 * 8, dtype=np.uint8)
+        rc = self._lib.lame_encode_flush(self._h, buf.ctypes.data, buf.size)
+        if rc < 0:
+            raise LameGpuError("lame_encode_flush returned %d" % rc)
+        return buf[:rc].tobytes()
+
+    def close(self):
+        if self._h:
+            self._lib.lame_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class BatchEncoder:
+    """`nstreams` independent streams with one configuration, encoded together on one GPU."""
+
+    def __init__(self, nstreams, samplerate=44100, channels=2, brate=128, mode=-1, quality=-1,
+                 frames_per_launch=8, device=0):
+        self._lib = load_library()
+        self.nstreams, self.frames_per_launch = int(nstreams), int(frames_per_launch)
+        self._h = self._lib.lamegpu_batch_open(samplerate, channels, brate, mode, quality, self.nstreams,
+                                               self.frames_per_launch, device)
+        if not self._h:
+            raise LameGpuError("lamegpu_batch_open failed (unsupported configuration, no CUDA device, or out of memory)")
+        self._nbytes = np.zeros(self.nstreams, dtype=np.int32)
+
+    def encode(self, pcm):
+        """pcm: int16 array [nstreams, 2, nsamples].  Returns (frames_encoded, list of bytes per stream)."""
+        pcm = _as_i16(pcm)
+        assert pcm.ndim == 3 and pcm.shape[0] == self.nstreams and pcm.shape[1] == 2
+        n = int(pcm.shape[2])
+        stride = int(1.25 * n) + 7200 + 4096
+        out = np.empty((self.nstreams, stride), dtype=np.uint8)
+        done = self._lib.lamegpu_batch_encode_packed(self._h, pcm.ctypes.data, n, out.ctypes.data, stride,
+                                                     self._nbytes.ctypes.data)
+        if done < 0:
+            raise LameGpuError("lamegpu_batch_encode_packed returned %d" % done)
+        return int(done), [out[s, :self._nbytes[s]].tobytes() for s in range(self.nstreams)]
+
+    def encode_raw(self, pcm, out, nbytes):
+        """Same without Python-side copies: caller owns `out` [nstreams, stride] uint8 and `nbytes` int32."""
+        n = int(pcm.shape[2])
+        return int(self._lib.lamegpu_batch_encode_packed(self._h, pcm.ctypes.data, n, out.ctypes.data,
+                                                         int(out.shape[1]), nbytes.ctypes.data))
+
+    def flush(self):
+        stride = 65536
+        out = np.empty((self.nstreams, stride), dtype=np.uint8)
+        done = self._lib.lamegpu_batch_flush_packed(self._h, out.ctypes.data, stride, self._nbytes.ctypes.data)
+        if done < 0:
+            raise LameGpuError("lamegpu_batch_flush_packed returned %d" % done)
+        return int(done), [out[s, :self._nbytes[s]].tobytes() for s in range(self.nstreams)]
+
+    def flush_raw(self, out, nbytes):
+        return int(self._lib.lamegpu_batch_flush_packed(self._h, out.ctypes.data, int(out.shape[1]), nbytes.ctypes.data))
+
+    # measurement hooks used by bench.py
+    def stage(self, pcm, nframes):
+        rc = self._lib.lamegpu_batch_stage_packed(self._h, _as_i16(pcm).ctypes.data, int(nframes))
+        if rc != 0:
+            raise LameGpuError("lamegpu_batch_stage_packed failed")
+
+    def rerun_device(self, nframes):
+        rc = self._lib.lamegpu_batch_rerun_device(self._h, int(nframes))
+        if rc != 0:
+            raise LameGpuError("lamegpu_batch_rerun_device failed")
+
+    def kernel_ms(self):
+        ms = (ctypes.c_float * 4)()
+        self._lib.lamegpu_batch_kernel_ms(self._h, ms)
+        return [float(x) for x in ms]
+
+    def kernel_launches(self):
+        return int(self._lib.lamegpu_batch_kernel_launches(self._h))
+
+    def set_threads(self, n):
+        self._lib.lamegpu_batch_set_threads(self._h, int(n))
+
+    def close(self):
+        if self._h:
+            self._lib.lamegpu_batch_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -52,7 +52,7 @@ struct lg_engine {
     float *d_sb, *d_xr;
     LgAnalysis *d_ana; LgPsyOut *d_psy; LgFrameCtl *d_frm;
     LgGranuleOut *d_gout; LgFrameOut *d_fout;
-    LgStreamState *d_state;
+    LgStreamState *d_state, *d_state0;   /* d_state0: S copies of the initial state, for one-copy resets */
     int *d_nfr;
     /* pinned host staging */
     int16_t *h_pcm16; float *h_pcmf; int *h_nfr;
@@ -103,7 +103,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     if (!e) return;
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_xr);
     lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout);
-    lg_dev_free(e->d_state); lg_dev_free(e->d_nfr);
+    lg_dev_free(e->d_state); lg_dev_free(e->d_state0); lg_dev_free(e->d_nfr);
     lg_host_free(e->h_pcm16); lg_host_free(e->h_pcmf); lg_host_free(e->h_nfr); lg_host_free(e->h_gout); lg_host_free(e->h_fout);
 #ifndef LG_EMULATE
     for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
@@ -114,15 +114,12 @@ extern "C" void lg_engine_destroy(lg_engine *e)
 
 extern "C" int lg_engine_reset_streams(lg_engine *e, int first, int count)
 {
-    LgStreamState s0;
-    lg_initial_state(&e->hcfg, &s0);
-    for (int i = first; i < first + count && i < e->S; i++) {
+    if (first < 0 || count < 0 || first + count > e->S) return -1;
 #ifdef LG_EMULATE
-        memcpy(e->d_state + i, &s0, sizeof s0);
+    memcpy(e->d_state + first, e->d_state0 + first, (size_t) count * sizeof(LgStreamState));
 #else
-        LG_CHECK(cudaMemcpy(e->d_state + i, &s0, sizeof s0, cudaMemcpyHostToDevice));
+    LG_CHECK(cudaMemcpyAsync(e->d_state + first, e->d_state0 + first, (size_t) count * sizeof(LgStreamState), cudaMemcpyDeviceToDevice, e->stream));
 #endif
-    }
     return 0;
 }
 
@@ -155,6 +152,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     bad |= lg_dev_malloc((void **) &e->d_gout, S * 2 * F * 2 * sizeof(LgGranuleOut));
     bad |= lg_dev_malloc((void **) &e->d_fout, S * F * sizeof(LgFrameOut));
     bad |= lg_dev_malloc((void **) &e->d_state, S * sizeof(LgStreamState));
+    bad |= lg_dev_malloc((void **) &e->d_state0, S * sizeof(LgStreamState));
     bad |= lg_dev_malloc((void **) &e->d_nfr, S * sizeof(int));
     bad |= lg_host_malloc((void **) &e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t));
     bad |= lg_host_malloc((void **) &e->h_nfr, S * sizeof(int));
@@ -170,6 +168,18 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
 #endif
+    {
+        LgStreamState *h0 = (LgStreamState *) malloc(S * sizeof(LgStreamState));
+        if (!h0) { lg_engine_destroy(e); return NULL; }
+        lg_initial_state(&e->hcfg, &h0[0]);
+        for (size_t i = 1; i < S; i++) h0[i] = h0[0];
+#ifdef LG_EMULATE
+        memcpy(e->d_state0, h0, S * sizeof(LgStreamState));
+#else
+        if (cudaMemcpy(e->d_state0, h0, S * sizeof(LgStreamState), cudaMemcpyHostToDevice) != cudaSuccess) { free(h0); lg_engine_destroy(e); return NULL; }
+#endif
+        free(h0);
+    }
     if (lg_engine_reset_streams(e, 0, nstreams) != 0) { lg_engine_destroy(e); return NULL; }
     return e;
 }

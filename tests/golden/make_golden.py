@@ -1,0 +1,55 @@
+"""Generates the committed golden vectors from the UNMODIFIED reference (oracle/_ref, built from
+/root/reference).  Run in the development container only:  python tests/golden/make_golden.py
+
+For every case: the PCM comes from the seeded generators in tests/conftest.py (or testcase.wav shipped by
+the reference, stored once as testcase_pcm.npy), the MP3 bytes come from the reference's own
+lame_init / lame_encode_buffer / lame_encode_flush.  manifest.json records config, sizes and SHA-256.
+"""
+import hashlib
+import json
+import os
+import sys
+import wave
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle  # noqa: E402
+from conftest import make_signal  # noqa: E402
+
+CASES = [
+    # name, signal, frames, samplerate, brate, mode, quality
+    ("testcase_128", "testcase", 21, 44100, 128, -1, -1),
+    ("noise_128", "noise", 24, 44100, 128, -1, -1),
+    ("click_128", "click", 40, 44100, 128, -1, -1),
+    ("gap_128", "gap", 30, 44100, 128, -1, -1),
+    ("sine_320_js", "sine", 24, 44100, 320, 1, -1),
+    ("click_192_stereo_q5", "click", 24, 44100, 192, 0, 5),
+    ("noise_256_48k", "noise", 16, 48000, 256, -1, -1),
+    ("click_160_q7", "click", 16, 44100, 160, -1, 7),
+]
+
+
+def main():
+    assert oracle.build()[1], "reference not available"
+    w = wave.open("/root/reference/testcase.wav", "rb")
+    assert w.getnchannels() == 2 and w.getsampwidth() == 2
+    pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).reshape(-1, 2).T.copy()
+    np.save(os.path.join(HERE, "testcase_pcm.npy"), pcm)
+    manifest = {}
+    for name, sig, frames, sr, brate, mode, q in CASES:
+        x = make_signal(sig, frames * 1152)
+        mp3 = oracle.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q).encode_all(x[0], x[1])
+        with open(os.path.join(HERE, name + ".mp3"), "wb") as f:
+            f.write(mp3)
+        manifest[name] = dict(signal=sig, frames=frames, samplerate=sr, brate=brate, mode=mode, quality=q, nbytes=len(mp3),
+                              pcm_sha256=hashlib.sha256(x.tobytes()).hexdigest(), mp3_sha256=hashlib.sha256(mp3).hexdigest())
+        print(name, len(mp3))
+    with open(os.path.join(HERE, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

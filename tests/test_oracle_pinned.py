@@ -1,0 +1,87 @@
+"""CPU suite: pins the oracle.  (a) oracle/port reproduces every committed golden vector (MP3 bytes produced by the
+unmodified reference, tests/golden/make_golden.py); (b) where the reference build oracle/_ref exists (development
+container and, as a prebuilt .so, the GPU box) the port is compared with the reference itself on more inputs and on
+the init tables / per-frame state through tests/c/port_vs_ref.c."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_signal
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+MANIFEST = json.load(open(os.path.join(GOLD, "manifest.json")))
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_port_reproduces_golden(oracle_mod, name):
+    m = MANIFEST[name]
+    x = make_signal(m["signal"], m["frames"] * 1152)
+    mp3 = oracle_mod.PortEncoder(m["samplerate"], 2, m["brate"], m["mode"], m["quality"]).encode_all(x[0], x[1])
+    want = open(os.path.join(GOLD, name + ".mp3"), "rb").read()
+    assert len(mp3) == m["nbytes"]
+    assert mp3 == want
+
+
+def test_port_chunking_invariance(oracle_mod):
+    """feeding the same PCM in ragged chunks gives the same stream (buffering logic, lame.c:1671)"""
+    x = make_signal("click", 30 * 1152)
+    whole = oracle_mod.PortEncoder().encode_all(x[0], x[1])
+    e = oracle_mod.PortEncoder()
+    out, pos = b"", 0
+    for c in [1, 7, 1151, 1152, 1153, 5000, 333, 10 ** 6]:
+        out += e.encode(x[0][pos:pos + c], x[1][pos:pos + c])
+        pos += c
+        if pos >= x.shape[1]:
+            break
+    out += e.flush()
+    assert out == whole
+
+
+def test_port_rejects_unsupported(oracle_mod):
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=2), dict(samplerate=44100, brate=96)):
+        with pytest.raises(ValueError):
+            oracle_mod.PortEncoder(**kw)
+
+
+@pytest.fixture(scope="module")
+def port_vs_ref_bin(oracle_mod, tmp_path_factory):
+    if not oracle_mod.have_ref() or not os.path.exists(oracle_mod.REFDUMP_SO):
+        pytest.skip("reference build oracle/_ref not present")
+    out = str(tmp_path_factory.mktemp("bin") / "port_vs_ref")
+    subprocess.run(["gcc", "-O2", "-fno-fast-math", "-ffp-contract=off", "-w", os.path.join(ROOT, "tests/c/port_vs_ref.c"), "-o", out,
+                    "-L" + os.path.join(ROOT, "oracle"), "-llameport", oracle_mod.REFDUMP_SO, "-lm",
+                    "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-Wl,-rpath," + os.path.join(ROOT, "oracle", "_ref")], check=True)
+    return out
+
+
+@pytest.mark.parametrize("args", [
+    "noise 128 -1 -1 120", "sine 128 -1 -1 100", "click 128 -1 -1 150", "gap 128 -1 -1 60", "sine 320 1 -1 100",
+    "click 320 1 -1 100", "noise 192 0 -1 60", "click 160 -1 5 80", "click 128 -1 7 60", "sine 128 -1 4 60",
+    "click 256 -1 -1 60 48000", "click 128 -1 -1 60 32000", "silence 128 -1 -1 20", "click 224 0 6 60", "noise 112 -1 9 40",
+])
+def test_port_vs_reference(port_vs_ref_bin, args):
+    """byte-identical MP3 + identical init tables against the real libmp3lame (strict IEEE build)"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
+def test_click_signal_has_short_blocks(oracle_mod):
+    """the transient fixture must really exercise block switching, otherwise short-block parity is vacuous"""
+    x = make_signal("click", 40 * 1152)
+    mp3 = oracle_mod.PortEncoder().encode_all(x[0], x[1])
+    # parse side info: window_switching_flag/block_type of gr0 ch0 in every frame (MPEG-1 stereo, no CRC)
+    pos, types = 0, set()
+    while pos + 40 < len(mp3):
+        assert mp3[pos] == 0xFF and (mp3[pos + 1] & 0xE0) == 0xE0
+        pad = (mp3[pos + 2] >> 1) & 1
+        bits = int.from_bytes(mp3[pos + 4:pos + 36], "big")
+        off = 9 + 3 + 8 + 12 + 9 + 8 + 4          # main_data_begin, private, scfsi, part2_3, big_values, global_gain, sf_compress
+        ws = (bits >> (256 - off - 1)) & 1
+        if ws:
+            types.add((bits >> (256 - off - 3)) & 3)
+        pos += 417 + pad
+    assert 2 in types and 1 in types and 3 in types
