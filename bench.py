@@ -164,7 +164,18 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print("[bench %.1fs] %s" % (time.perf_counter() - T0, msg), file=sys.stderr, flush=True)
+
+
+T0 = time.perf_counter()
+
+
 def main():
+    import faulthandler
+    # a hung run must not eat the GPU lease: dump all stacks and exit after the watchdog period
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -205,10 +216,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    log('engine created')
     # ---------------- value: device pipeline, inputs resident in HBM
     enc.stage(pcm, F)                                        # H2D once + a first (untimed) pass
+    log('staged')
     for _ in range(args.warmup):
         enc.rerun_device(F)
+    log('warm')
     kms = np.zeros(4)
     sampler = ClockSampler(local)
     launches0 = enc.kernel_launches()
@@ -225,6 +239,7 @@ def main():
     barrier()
     clocks = sampler.stop()
     launches = enc.kernel_launches() - launches0
+    log('device timing done: %s' % (kms / args.steps))
     frames_dev, dev_ms_max = reduce_over_ranks(float(S * F * args.steps), dev_ms)
     value = frames_dev / (dev_ms_max * 1e-3)
 
@@ -244,6 +259,7 @@ def main():
         e2e_frames += enc.encode_raw(step_pcm[i % 4], out, nbytes)
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
+    log('e2e done %.1f ms' % e2e_ms)
     total_bytes = int(nbytes.sum())
     e2e_frames_all, e2e_ms_max = reduce_over_ranks(float(e2e_frames), e2e_ms)
     lib = lame_b200.load_library()

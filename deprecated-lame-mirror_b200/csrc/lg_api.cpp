@@ -255,12 +255,16 @@ long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const sho
 long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int *out_cap, int *out_bytes)
 {
     if (!b) return -3;
-    for (int s = 0; s < b->S; s++) b->pad_for_flush(s);
+    std::vector<char> live(b->S);
+    for (int s = 0; s < b->S; s++) {
+        live[s] = b->st[s].mf_samples_to_encode >= 1;         /* lame.c:2067: "was flush already called?" */
+        b->pad_for_flush(s);
+    }
     long const done = b->pump();
     if (done < 0) return done;
     for (int s = 0; s < b->S; s++) {
         Stream &x = b->st[s];
-        if (x.mf_samples_to_encode >= 1) {
+        if (live[s]) {
             x.mf_samples_to_encode = 0;
             lg_pack_flush(&x.bw, &b->cfg, x.last_padding);
             x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
