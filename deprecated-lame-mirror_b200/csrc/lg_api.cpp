@@ -124,7 +124,9 @@ struct lamegpu_batch {
                     for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcm16[c].data(), n * sizeof(int16_t));
                 });
             }
+            if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: launch maxf=%d float=%d\n", maxf, any_float);
             if (lg_engine_encode(eng, maxf, any_float) != 0) return -2;
+            if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: device done, packing\n");
             const LgGranuleOut *go = lg_engine_host_gout(eng);
             const LgFrameOut *fo = lg_engine_host_fout(eng);
             parallel_for(S, nthreads, [&](int s) {
@@ -141,6 +143,7 @@ struct lamegpu_batch {
                 x.drop_consumed();
             });
             for (int s = 0; s < S; s++) done += nfr[s];
+            if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: packed, %ld frames so far\n", done);
         }
         frames_total += done;
         return done;

@@ -101,6 +101,9 @@ static void lg_initial_state(const LgDevCfg *c, LgStreamState *s)
 extern "C" void lg_engine_destroy(lg_engine *e)
 {
     if (!e) return;
+#ifndef LG_EMULATE
+    if (e->stream) cudaStreamSynchronize(e->stream);
+#endif
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_xr);
     lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout);
     lg_dev_free(e->d_state); lg_dev_free(e->d_state0); lg_dev_free(e->d_nfr);
@@ -164,7 +167,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
 #else
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
-    if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+    if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
 #endif
@@ -176,7 +179,10 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
 #ifdef LG_EMULATE
         memcpy(e->d_state0, h0, S * sizeof(LgStreamState));
 #else
-        if (cudaMemcpy(e->d_state0, h0, S * sizeof(LgStreamState), cudaMemcpyHostToDevice) != cudaSuccess) { free(h0); lg_engine_destroy(e); return NULL; }
+        /* cudaMemcpy from pageable memory may return before the DMA has landed, and e->stream is a non-blocking
+         * stream that does not order against the default stream: synchronise the device before anything reads it */
+        if (cudaMemcpy(e->d_state0, h0, S * sizeof(LgStreamState), cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaDeviceSynchronize() != cudaSuccess) { free(h0); lg_engine_destroy(e); return NULL; }
 #endif
         free(h0);
     }
@@ -209,14 +215,17 @@ extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
               e->dcfg, p16, (int) e->pcm_stride, pf, e->d_sb, e->d_ana, e->d_nfr, 2 * F + 1);
 #ifndef LG_EMULATE
     cudaEventRecord(e->ev[1], e->stream);
+    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: analysis done (%s)\n", cudaGetErrorString(r)); }
 #endif
     LG_LAUNCH(lg_kernel_scan, S, 32, sizeof(LgSmemB), e->stream, e->dcfg, e->d_ana, e->d_psy, e->d_frm, e->d_state, e->d_nfr, F);
 #ifndef LG_EMULATE
     cudaEventRecord(e->ev[2], e->stream);
+    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: scan done (%s)\n", cudaGetErrorString(r)); }
 #endif
     LG_LAUNCH(lg_kernel_mdct, S * 2 * F, 64, sizeof(LgSmemC), e->stream, e->dcfg, e->d_sb, e->d_psy, e->d_frm, e->d_xr, e->d_nfr, F);
 #ifndef LG_EMULATE
     cudaEventRecord(e->ev[3], e->stream);
+    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: mdct done (%s)\n", cudaGetErrorString(r)); }
 #endif
     LG_LAUNCH(lg_kernel_quant, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
               e->d_state, e->d_nfr, F);

@@ -684,6 +684,17 @@ __device__ __forceinline__ void lg_copy_f576(float *d, const float *s, int lane)
     __syncwarp();
 }
 
+/* A search loop that runs away means corrupted state (the reference asserts CurrentStep != 0): stop the kernel with
+ * an error instead of hanging the GPU. */
+__device__ __forceinline__ void lg_runaway()
+{
+#ifdef LG_EMULATE
+    abort();
+#else
+    __trap();
+#endif
+}
+
 /* quantize.c:367 bin_search_StepSize */
 __device__ __forceinline__ int lg_bin_search(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int desired_rate,
                                              int *old_value, int *current_step, int lane)
@@ -693,8 +704,9 @@ __device__ __forceinline__ int lg_bin_search(const LgDevCfg *__restrict__ c, LgQ
     int Direction = 0;
     gi.global_gain = start;
     desired_rate -= gi.part2_length;
-    for (;;) {
+    for (int guard = 0;; guard++) {
         int step;
+        if (guard > 600) lg_runaway();
         nBits = lg_count_bits(c, w, gi, qc, nullptr, lane);
         if (CurrentStep == 1 || nBits == desired_rate) break;
         if (nBits > desired_rate) {
@@ -739,9 +751,11 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
     lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
     lg_copy_f576(w->save_xrpow, w->xrpow, lane);
     int age = 0, best_part2_3_length = 9999999, bEndOfSearch = 0, bRefine = 0, best_ggain_pass1 = 0;
+    int guard = 0;
     while (!bEndOfSearch) {
         do {
             LgNoiseRes noise_info;
+            if (++guard > 20000) lg_runaway();
             int const search_limit = 3;
             int maxggain = 255;
             if (c->sfb21_extra) {
