@@ -117,7 +117,7 @@ __device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const LgQWarp *w,
 
 /* ---------------------------------------------------------------- quantiser (takehiro.c:281 quantize_xrpow)
  * Returns the lane's nine (x | y<<16) pairs in px[]. */
-__device__ __forceinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
+__device__ __noinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
                                             const LgPrev &pv, int lane, unsigned px[9])
 {
     int const nsfb = (qc.block_type == LG_SHORT) ? 39 : 22;
@@ -186,7 +186,7 @@ __device__ __forceinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQW
 /* ---------------------------------------------------------------- Huffman table choice for one region, whole warp
  * (takehiro.c:618 choose_table_nonMMX + count_bit_* :449-573).  The lane contributes the pairs it owns
  * that fall in [lo, hi).  Adds the bits to *bits, returns the table. */
-__device__ __forceinline__ int lg_choose_table_warp(const LgDevCfg *__restrict__ c, const unsigned px[9], int lane, int lo, int hi, int *bits)
+__device__ __noinline__ int lg_choose_table_warp(const LgDevCfg *__restrict__ c, const unsigned px[9], int lane, int lo, int hi, int *bits)
 {
     int mx = 0;
 #pragma unroll
@@ -277,7 +277,7 @@ __device__ __forceinline__ int lg_choose_table_warp(const LgDevCfg *__restrict__
 
 /* same decision by ONE lane over ix[lo..hi) in shared memory (used where many ranges are evaluated at
  * once, one per lane: best_huffman_divide) */
-__device__ __forceinline__ int lg_choose_table_serial(const LgDevCfg *__restrict__ c, const int16_t *ix, int lo, int hi, int *bits)
+__device__ __noinline__ int lg_choose_table_serial(const LgDevCfg *__restrict__ c, const int16_t *ix, int lo, int hi, int *bits)
 {
     unsigned mx = 0;
     for (int i = lo; i < hi; i++) { unsigned const v = (unsigned) ix[i]; if (v > mx) mx = v; }
@@ -335,7 +335,7 @@ __device__ __forceinline__ int lg_choose_table_serial(const LgDevCfg *__restrict
 }
 
 /* count1 quadruples [bigv, count1) counted with both count1 books (warp) */
-__device__ __forceinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, const int16_t *ix, int bigv, int count1, int lane, int *a1, int *a2)
+__device__ __noinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, const int16_t *ix, int bigv, int count1, int lane, int *a1, int *a2)
 {
     const uint8_t *t32l = lg_hlen(c, 32), *t33l = lg_hlen(c, 33);
     unsigned s1 = 0, s2 = 0;
@@ -351,7 +351,7 @@ __device__ __forceinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, c
 }
 
 /* takehiro.c:654 noquant_count_bits (use_best_huffman == 2 is not on this path) */
-__device__ __forceinline__ int lg_noquant_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
+__device__ __noinline__ int lg_noquant_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
                                                      LgPrev *pv, const unsigned px[9], int lane)
 {
     int bits = 0, a1, a2;
@@ -412,7 +412,7 @@ __device__ __forceinline__ int lg_noquant_count_bits(const LgDevCfg *__restrict_
 }
 
 /* takehiro.c:767 count_bits; pv == nullptr is the reference's prev_noise == 0 */
-__device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev *pv, int lane)
+__device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev *pv, int lane)
 {
     float const wlim = (LG_IXMAX) / __ldg(&c->ipow20[gi.global_gain]);
     if (gi.xrpow_max > wlim) return LG_LARGE_BITS;
@@ -423,7 +423,7 @@ __device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQ
 }
 
 /* ---------------------------------------------------------------- quantize_pvt.c:815 calc_noise: one lane per band */
-__device__ __forceinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
+__device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
                                               LgNoiseRes *res, LgPrev *pv, int lane)
 {
     int over = 0, ssd = 0;
@@ -494,7 +494,7 @@ __device__ __forceinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, Lg
 }
 
 /* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount */
-__device__ __forceinline__ int lg_scale_bitcount(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int *sf, int lane)
+__device__ __noinline__ int lg_scale_bitcount(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int *sf, int lane)
 {
     const int *tab;
     if (qc.block_type == LG_SHORT) tab = LG_SCALE_SHORT;
@@ -535,7 +535,7 @@ __device__ __forceinline__ int lg_loop_break(const LgQWarp *w, const LgQInfo &gi
 }
 
 /* multiply the lines of the flagged bands (act[sfb] != 0 -> factor in fac[]) and track xrpow_max */
-__device__ __forceinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const float *fac /* shared, per sfb, 0 = untouched */, int lane)
+__device__ __noinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const float *fac /* shared, per sfb, 0 = untouched */, int lane)
 {
     float mx = gi.xrpow_max;
 #pragma unroll
@@ -555,7 +555,7 @@ __device__ __forceinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const fl
 }
 
 /* quantize.c:720 amp_scalefac_bands (noise_shaping_amp 0 and 1; 2/3 belong to quality <= 1) */
-__device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __noinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     float const ifqstep34 = (gi.scalefac_scale == 0) ? (float) 1.29683955465100964055 : (float) 1.68179283050742922612;
     float trigger = 0;
@@ -582,7 +582,7 @@ __device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict
 }
 
 /* quantize.c:808 inc_scalefac_scale */
-__device__ __forceinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __noinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     float const ifqstep34 = (float) 1.29683955465100964055;
     for (int r = 0; r < 2; r++) {
@@ -605,7 +605,7 @@ __device__ __forceinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, c
 }
 
 /* quantize.c:847 inc_subblock_gain (short blocks only; sfb_lmax == 0 because mixed blocks are never used) */
-__device__ __forceinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __noinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     int *scalefac = w->sfw;
     float *fac = reinterpret_cast<float *>(w->act);
@@ -808,7 +808,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
 }
 
 /* ---------------------------------------------------------------- quantize_pvt.c:589 calc_xmin: one lane per band */
-__device__ __forceinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQConst &qc, const LgXmin *en, const LgXmin *thm,
+__device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQConst &qc, const LgXmin *en, const LgXmin *thm,
                                              float ath_adjust_factor, int lane)
 {
     float const eps = (float) 2.2204460492503131e-016;   /* DBL_EPSILON stored in a float */
@@ -899,7 +899,7 @@ __device__ __forceinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQ
 }
 
 /* ---------------------------------------------------------------- takehiro.c:884 best_huffman_divide */
-__device__ __forceinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict__ c, LgQWarp *w, int bigv, int lane)
+__device__ __noinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict__ c, LgQWarp *w, int bigv, int lane)
 {
     const int16_t *ix = w->ixw;
     if (lane < 23) w->r01_bits[lane] = LG_LARGE_BITS;
@@ -931,7 +931,7 @@ __device__ __forceinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict
     __syncwarp();
 }
 /* takehiro.c:847 recalc_divide_sub: g2 is the candidate base, gi the current best */
-__device__ __forceinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &g2, LgQInfo &gi, int lane)
+__device__ __noinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &g2, LgQInfo &gi, int lane)
 {
     int const bigv = g2.big_values;
     /* every lane evaluates one r2 candidate; the sequential scan then replays the reference's order */
@@ -960,7 +960,7 @@ __device__ __forceinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict_
         gi.table_select[2] = tbl;
     }
 }
-__device__ __forceinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __noinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     const int16_t *ix = w->ixw;
     LgQInfo g2 = gi;
@@ -999,7 +999,7 @@ __device__ __forceinline__ void lg_best_huffman_divide(const LgDevCfg *__restric
 }
 
 /* ---------------------------------------------------------------- takehiro.c:1021 best_scalefac_store (+ :964 scfsi_calc) */
-__device__ __forceinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
+__device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
                                                        int gr, const int *sf_gr0, int bt_gr0, uint8_t scfsi[4], int lane)
 {
     int *sf = w->sfw;

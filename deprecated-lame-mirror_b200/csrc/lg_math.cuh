@@ -36,7 +36,7 @@ __constant__ unsigned long long LG_POW_EXPTAB[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull };
 
-__device__ __forceinline__ float lg_powf(float x, float y)
+__device__ __noinline__ float lg_powf(float x, float y)
 {
     unsigned ix = __float_as_uint(x);
     if (ix - 0x00800000u >= 0x7f800000u - 0x00800000u) {
@@ -135,7 +135,7 @@ __device__ __forceinline__ float lg_ns_interp(float x, float y, float r)
 }
 
 /* quantize_pvt.c:554 athAdjust */
-__device__ __forceinline__ float lg_ath_adjust(const LgDevCfg *__restrict__ c, float a, float x, float athFloor, float fixpoint)
+__device__ __noinline__ float lg_ath_adjust(const LgDevCfg *__restrict__ c, float a, float x, float athFloor, float fixpoint)
 {
     float const o = 90.30873362f;
     float const p = (fixpoint < 1.f) ? 94.82444863f : fixpoint;

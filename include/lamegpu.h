@@ -24,42 +24,42 @@ extern "C" {
 
 /* ------------------------------------------------------------------ 1. libmp3lame-compatible face */
 struct lame_global_struct;
-typedef struct lame_global_struct lame_global_flags;          /* include/lame.h:149-150 */
+typedef struct lame_global_struct lame_global_flags;          /* include/lame.h:146-147 */
 typedef lame_global_flags *lame_t;
 
 typedef enum vbr_mode_e { vbr_off = 0, vbr_mt, vbr_rh, vbr_abr, vbr_mtrh, vbr_max_indicator, vbr_default = vbr_mtrh } vbr_mode; /* lame.h:49-57 */
 typedef enum MPEG_mode_e { STEREO = 0, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET, MAX_INDICATOR } MPEG_mode;               /* lame.h:61-68 */
 
 lame_global_flags *lame_init(void);                                                  /* lame.h:168  NULL on OOM */
-int  lame_set_in_samplerate(lame_global_flags *, int);                               /* lame.h:194 */
-int  lame_get_in_samplerate(const lame_global_flags *);                              /* lame.h:195 */
-int  lame_set_num_channels(lame_global_flags *, int);                                /* lame.h:198 */
-int  lame_get_num_channels(const lame_global_flags *);                               /* lame.h:199 */
-int  lame_set_out_samplerate(lame_global_flags *, int);                              /* lame.h:222 */
-int  lame_get_out_samplerate(const lame_global_flags *);                             /* lame.h:223 */
-int  lame_set_brate(lame_global_flags *, int);                                       /* lame.h:330 */
-int  lame_get_brate(const lame_global_flags *);                                      /* lame.h:331 */
-int  lame_set_quality(lame_global_flags *, int);                                     /* lame.h:282 */
-int  lame_get_quality(const lame_global_flags *);                                    /* lame.h:283 */
-int  lame_set_mode(lame_global_flags *, MPEG_mode);                                  /* lame.h:290 */
-MPEG_mode lame_get_mode(const lame_global_flags *);                                  /* lame.h:291 */
-int  lame_set_VBR(lame_global_flags *, vbr_mode);                                    /* lame.h:433  only vbr_off is accepted */
-vbr_mode lame_get_VBR(const lame_global_flags *);                                    /* lame.h:434 */
-int  lame_set_bWriteVbrTag(lame_global_flags *, int);                                /* lame.h:244  the Info tag frame is not produced */
-int  lame_get_bWriteVbrTag(const lame_global_flags *);                               /* lame.h:245 */
+int  lame_set_in_samplerate(lame_global_flags *, int);                               /* lame.h:188 */
+int  lame_get_in_samplerate(const lame_global_flags *);                              /* lame.h:189 */
+int  lame_set_num_channels(lame_global_flags *, int);                                /* lame.h:192 */
+int  lame_get_num_channels(const lame_global_flags *);                               /* lame.h:193 */
+int  lame_set_out_samplerate(lame_global_flags *, int);                              /* lame.h:224 */
+int  lame_get_out_samplerate(const lame_global_flags *);                             /* lame.h:225 */
+int  lame_set_brate(lame_global_flags *, int);                                       /* lame.h:353 */
+int  lame_get_brate(const lame_global_flags *);                                      /* lame.h:354 */
+int  lame_set_quality(lame_global_flags *, int);                                     /* lame.h:263 */
+int  lame_get_quality(const lame_global_flags *);                                    /* lame.h:264 */
+int  lame_set_mode(lame_global_flags *, MPEG_mode);                                  /* lame.h:270 */
+MPEG_mode lame_get_mode(const lame_global_flags *);                                  /* lame.h:271 */
+int  lame_set_VBR(lame_global_flags *, vbr_mode);                                    /* lame.h:432  only vbr_off is accepted */
+vbr_mode lame_get_VBR(const lame_global_flags *);                                    /* lame.h:433 */
+int  lame_set_bWriteVbrTag(lame_global_flags *, int);                                /* lame.h:240  the Info tag frame is not produced */
+int  lame_get_bWriteVbrTag(const lame_global_flags *);                               /* lame.h:241 */
 int  lame_init_params(lame_global_flags *);                                          /* lame.h:636  <0 on error/unsupported */
-int  lame_get_framesize(const lame_global_flags *);                                  /* lame.h:602 */
-int  lame_get_frameNum(const lame_global_flags *);                                   /* lame.h:608 */
-int  lame_get_encoder_delay(const lame_global_flags *);                              /* lame.h:588 */
+int  lame_get_framesize(const lame_global_flags *);                                  /* lame.h:582 */
+int  lame_get_frameNum(const lame_global_flags *);                                   /* lame.h:597 */
+int  lame_get_encoder_delay(const lame_global_flags *);                              /* lame.h:571 */
 int  lame_encode_buffer(lame_global_flags *, const short int pcm_l[], const short int pcm_r[], const int nsamples,
                         unsigned char *mp3buf, const int mp3buf_size);               /* lame.h:715 */
 int  lame_encode_buffer_interleaved(lame_global_flags *, short int pcm[], int num_samples,
                                     unsigned char *mp3buf, int mp3buf_size);         /* lame.h:730 */
 int  lame_encode_buffer_ieee_float(lame_t, const float pcm_l[], const float pcm_r[], const int nsamples,
-                                   unsigned char *mp3buf, const int mp3buf_size);    /* lame.h:760  +/-1.0 full scale */
+                                   unsigned char *mp3buf, const int mp3buf_size);    /* lame.h:758  +/-1.0 full scale */
 int  lame_encode_flush(lame_global_flags *, unsigned char *mp3buf, int size);        /* lame.h:856 */
 int  lame_close(lame_global_flags *);                                                /* lame.h:977 */
-const char *get_lame_short_version(void);                                            /* lame.h:646 */
+const char *get_lame_short_version(void);                                            /* lame.h:645 */
 
 /* ------------------------------------------------------------------ 2. batch face */
 typedef struct lamegpu_batch lamegpu_batch;
