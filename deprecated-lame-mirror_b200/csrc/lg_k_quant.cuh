@@ -33,13 +33,13 @@ struct LgNoiseRes { float max_noise; int over_count, over_SSD, bits; };
 struct LgPrev { int valid, global_gain, sfb_count1; };   /* scalar part of calc_noise_data (quantize_pvt.h:75) */
 
 struct __attribute__((aligned(16))) LgQWarp {
-    float xr[576], xrpow[576], save_xrpow[576];
+    float xr[576], xrpow[576], save_xrpow[576], sq[576];
     int16_t ixw[576], ixb[576];
     float l3_xmin[40], distort[40], pn_noise[40], pn_noise_log[40];
     int   pn_step[40];
     int   sfw[40], sfbst[40];
     int   width[40], window[40], lstart[41];
-    int   act[64];
+    int   act[80];
     int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
     uint8_t line_sfb[576];
@@ -115,15 +115,77 @@ __device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const LgQWarp *w,
          - gi.subblock_gain[w->window[sfb]] * 8;
 }
 
-/* ---------------------------------------------------------------- quantiser (takehiro.c:281 quantize_xrpow)
- * Returns the lane's nine (x | y<<16) pairs in px[]. */
-__device__ __noinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
-                                            const LgPrev &pv, int lane, unsigned px[9])
+/* ---------------------------------------------------------------- Huffman table choice for a region whose largest
+ * magnitude is mx (takehiro.c:618 choose_table_nonMMX): the magnitude class selects a packed length book
+ * (LgDevCfg::huff_pk) and up to three candidate tables; escape classes add linbits per value >= 15. */
+struct LgRegion { int base, t0, t1, t2, lb0, lb1; };
+__device__ __forceinline__ void lg_region_class(const LgDevCfg *__restrict__ c, int mx, LgRegion &r)
 {
+    r.lb0 = r.lb1 = 0;
+    if (mx > 15) {
+        int const m = mx - 15;
+        int choice, choice2;
+        for (choice2 = 24; choice2 < 32; choice2++) if ((int) c->huff_linmax[choice2] >= m) break;
+        for (choice = choice2 - 8; choice < 24; choice++) if ((int) c->huff_linmax[choice] >= m) break;
+        r.base = 6 * 256; r.t0 = choice; r.t1 = r.t2 = choice2;
+        r.lb0 = c->huff_xlen[choice]; r.lb1 = c->huff_xlen[choice2];
+    }
+    else {
+        int const k = (mx <= 1) ? 0 : ((mx <= 3) ? mx - 1 : (mx <= 5 ? 3 : (mx <= 7 ? 4 : 5)));
+        int const t = LG_HUF_NOESC[mx > 0 ? mx - 1 : 0];
+        r.base = k * 256; r.t0 = t;
+        r.t1 = (mx == 1) ? t : t + 1;
+        r.t2 = (mx <= 3) ? r.t1 : t + 2;
+    }
+}
+/* s0/s1/s2 = whole-region bit sums under the three candidates -> chosen table, adds its bits (count_bit_* epilogues) */
+__device__ __forceinline__ int lg_region_pick(const LgRegion &r, unsigned s0, unsigned s1, unsigned s2, unsigned n15, int *bits)
+{
+    s0 += n15 * (unsigned) r.lb0; s1 += n15 * (unsigned) r.lb1; s2 += n15 * (unsigned) r.lb1;
+    int t = r.t0;
+    if (s0 > s1) { s0 = s1; t = r.t1; }
+    if (s0 > s2) { s0 = s2; t = r.t2; }
+    *bits += (int) s0;
+    return t;
+}
+
+/* count1 quadruples [bigv, count1) counted with both count1 books (warp) */
+__device__ __noinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, const int16_t *ix, int bigv, int count1, int lane, int *a1, int *a2)
+{
+    const uint8_t *t32l = lg_hlen(c, 32), *t33l = lg_hlen(c, 33);
+    unsigned s1 = 0, s2 = 0;
+    int const nq = (count1 - bigv) >> 2;
+    for (int k = lane; k < nq; k += 32) {
+        int const i = count1 - 4 * k;
+        int const p = ((ix[i - 4] * 2 + ix[i - 3]) * 2 + ix[i - 2]) * 2 + ix[i - 1];
+        s1 += __ldg(&t32l[p]); s2 += __ldg(&t33l[p]);
+    }
+    unsigned const a = lg_wsum_u(s1 | (s2 << 16));
+    *a1 = (int) (a & 0xffffu);
+    *a2 = (int) (a >> 16);
+}
+
+#ifndef LG_UNROLL_Q
+#define LG_UNROLL_Q 1
+#endif
+#ifndef LG_UNROLL_C
+#define LG_UNROLL_C 1
+#endif
+#define LG_PRAGMA_(x) _Pragma(#x)
+#define LG_UNROLL(n) LG_PRAGMA_(unroll n)
+
+/* ---------------------------------------------------------------- takehiro.c:767 count_bits = quantize_xrpow (:281) +
+ * noquant_count_bits (:654); pv == nullptr is the reference's prev_noise == 0.  The loops over the lane's nine
+ * line pairs are kept rolled on purpose: the whole search loop has to stay inside the 32 KB instruction cache. */
+__device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev *pv, int lane)
+{
+    float const istep = __ldg(&c->ipow20[gi.global_gain]);
+    if (gi.xrpow_max > (LG_IXMAX) / istep) return LG_LARGE_BITS;
     int const nsfb = (qc.block_type == LG_SHORT) ? 39 : 22;
     int const mnz = qc.max_nonzero_coeff;
-    int const prev_data_use = pv.valid && (gi.global_gain == pv.global_gain);
-    float const istep = __ldg(&c->ipow20[gi.global_gain]);
+    int const pv_valid = pv ? pv->valid : 0;
+    int const prev_data_use = pv_valid && (gi.global_gain == pv->global_gain);
+    int const pv_count1 = pv ? pv->sfb_count1 : 0;
     /* per scalefactor band: 0 keep old values, 1 quantise, 2 quantise with the 0/1 shortcut */
     int T = 64;
     for (int r = 0; r < 2; r++) {
@@ -134,7 +196,7 @@ __device__ __noinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp
             if (prev_data_use || qc.block_type == LG_NORM) step = lg_band_step(gi, w, w->sfw, sfb);
             int const skip = prev_data_use && (w->pn_step[sfb] == step);
             int const cross = (w->lstart[sfb] + w->width[sfb]) > mnz;
-            int const is01 = pv.valid && pv.sfb_count1 > 0 && sfb >= pv.sfb_count1 && w->pn_step[sfb] > 0 && step >= w->pn_step[sfb];
+            int const is01 = pv_valid && pv_count1 > 0 && sfb >= pv_count1 && w->pn_step[sfb] > 0 && step >= w->pn_step[sfb];
             w->act[sfb] = skip ? 0 : (is01 ? 2 : 1);
             term = !skip && cross;
         }
@@ -144,19 +206,22 @@ __device__ __noinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp
     __syncwarp();
     float const compareval0 = (1.0f - 0.4054f) / istep;
     const float *adj = c->adj43asm;
-#pragma unroll
+    int ilim = ((mnz + 2) >> 1) << 1;
+    if (ilim > 576) ilim = 576;
+    int hi_nz = -1, hi_big = -1;
+    LG_UNROLL(LG_UNROLL_Q)
     for (int j = 0; j < 9; j++) {
         int const P = lane + 32 * j, i = 2 * P;
         int const sfb = w->line_sfb[i];
         int a0, a1;                       /* action for line i and i+1: 0 keep, 1 quantise, 2 shortcut, 3 zero */
+        a0 = a1 = w->act[sfb];
         if (T < 64) {
             if (i > mnz) a0 = a1 = 3;
             else {
-                a0 = (sfb == T) ? 1 : w->act[sfb];
+                if (sfb == T) a0 = 1;
                 a1 = (i + 1 == mnz) ? ((sfb == T) ? 1 : 3) : a0;
             }
         }
-        else a0 = a1 = w->act[sfb];
         unsigned const old = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
         float2 const xp = *reinterpret_cast<const float2 *>(&w->xrpow[i]);
         int v0 = (int) (old & 0xffffu), v1 = (int) (old >> 16);
@@ -177,102 +242,107 @@ __device__ __noinline__ void lg_quantize(const LgDevCfg *__restrict__ c, LgQWarp
         else if (a1 == 2) v1 = (compareval0 > xp.y) ? 0 : 1;
         else if (a1 == 3) v1 = 0;
         unsigned const nv = (unsigned) v0 | ((unsigned) v1 << 16);
-        px[j] = nv;
         *reinterpret_cast<unsigned *>(&w->ixw[i]) = nv;
+        if (i < ilim) {
+            if (nv != 0u) hi_nz = P;
+            if ((nv & 0xfffefffeu) != 0u) hi_big = P;
+        }
     }
+    /* ---- noquant_count_bits: count1 / big_values split */
+    if (pv) pv->sfb_count1 = 0;
+    hi_nz = lg_wmax_i(hi_nz);                     /* the reductions also order the ix writes above (full-warp barrier) */
+    hi_big = lg_wmax_i(hi_big);
     __syncwarp();
-}
-
-/* ---------------------------------------------------------------- Huffman table choice for one region, whole warp
- * (takehiro.c:618 choose_table_nonMMX + count_bit_* :449-573).  The lane contributes the pairs it owns
- * that fall in [lo, hi).  Adds the bits to *bits, returns the table. */
-__device__ __noinline__ int lg_choose_table_warp(const LgDevCfg *__restrict__ c, const unsigned px[9], int lane, int lo, int hi, int *bits)
-{
-    int mx = 0;
-#pragma unroll
+    int const c1p = hi_nz + 1;
+    gi.count1 = 2 * c1p;
+    int const nquads = (c1p - 1 - hi_big) >> 1;
+    int const bigv = gi.count1 - 4 * nquads;
+    int bits, a1, a2;
+    lg_count1_bits(c, w->ixw, bigv, gi.count1, lane, &a1, &a2);
+    bits = a1;
+    gi.count1table_select = 0;
+    if (a1 > a2) { bits = a2; gi.count1table_select = 1; }
+    gi.count1bits = bits;
+    gi.big_values = bigv;
+    if (bigv == 0) return bits;
+    /* region split: [0,a1) [a1,a2) [a2,bigv) */
+    if (qc.block_type == LG_SHORT) {
+        a1 = 3 * c->sfb_s[3];
+        if (a1 > bigv) a1 = bigv;
+        a2 = bigv;
+    }
+    else if (qc.block_type == LG_NORM) {
+        a1 = gi.region0_count = c->bv_scf[bigv - 2];
+        a2 = gi.region1_count = c->bv_scf[bigv - 1];
+        a2 = c->sfb_l[a1 + a2 + 2];
+        a1 = c->sfb_l[a1 + 1];
+    }
+    else {
+        gi.region0_count = 7;
+        gi.region1_count = LG_SBMAX_L - 1 - 7 - 1;
+        a1 = c->sfb_l[7 + 1];
+        a2 = bigv;
+        if (a1 > a2) a1 = a2;
+    }
+    int const has2 = (qc.block_type == LG_NORM) && a2 < bigv;
+    a1 = a1 < bigv ? a1 : bigv;
+    a2 = a2 < bigv ? a2 : bigv;
+    /* pass 1: largest magnitude per region */
+    int m0 = 0, m1 = 0, m2 = 0;
+    LG_UNROLL(LG_UNROLL_C)
     for (int j = 0; j < 9; j++) {
         int const i = 2 * (lane + 32 * j);
-        if (i >= lo && i < hi) {
-            int const x = (int) (px[j] & 0xffffu), y = (int) (px[j] >> 16);
-            mx = max(mx, max(x, y));
+        unsigned const u = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
+        int const v = max((int) (u & 0xffffu), (int) (u >> 16));
+        if (i < a1) m0 = max(m0, v);
+        else if (i < a2) m1 = max(m1, v);
+        else if (i < bigv) m2 = max(m2, v);
+    }
+    m0 = lg_wmax_i(m0); m1 = lg_wmax_i(m1); m2 = lg_wmax_i(m2);
+    if (max(m0, max(m1, m2)) > LG_IXMAX) {
+        /* cannot happen behind the xrpow_max guard above; the reference's answer is "too many bits" */
+        return LG_LARGE_BITS;
+    }
+    LgRegion R0, R1, R2;
+    lg_region_class(c, m0, R0); lg_region_class(c, m1, R1); lg_region_class(c, m2, R2);
+    /* pass 2: bit sums under the candidate tables, three 10-bit fields per region (a lane adds at most 9 x 31) */
+    unsigned acc0 = 0, acc1 = 0, acc2 = 0, n15 = 0;
+    const uint32_t *pk = c->huff_pk;
+    LG_UNROLL(LG_UNROLL_C)
+    for (int j = 0; j < 9; j++) {
+        int const i = 2 * (lane + 32 * j);
+        if (i < bigv) {
+            unsigned const u = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
+            unsigned x = u & 0xffffu, y = u >> 16;
+            unsigned const over = (x >= 15u) + (y >= 15u);
+            x = x < 15u ? x : 15u; y = y < 15u ? y : 15u;
+            int const reg = (i >= a1) + (i >= a2);
+            int const base = reg == 0 ? R0.base : (reg == 1 ? R1.base : R2.base);
+            unsigned const e = __ldg(&pk[base + (int) ((x << 4) + y)]);
+            if (reg == 0) acc0 += e; else if (reg == 1) acc1 += e; else acc2 += e;
+            n15 += over << (10 * reg);
         }
     }
-    mx = lg_wmax_i(mx);
-    if (mx == 0) return 0;
-    if (mx > 15) {
-        if (mx > LG_IXMAX) { *bits = LG_LARGE_BITS; return -1; }
-        int const m = mx - 15;
-        int choice, choice2;
-        for (choice2 = 24; choice2 < 32; choice2++) if ((int) c->huff_linmax[choice2] >= m) break;
-        for (choice = choice2 - 8; choice < 24; choice++) if ((int) c->huff_linmax[choice] >= m) break;
-        unsigned const linbits = c->huff_xlen[choice] * 65536u + c->huff_xlen[choice2];
-        unsigned sum = 0;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            int const i = 2 * (lane + 32 * j);
-            if (i >= lo && i < hi) {
-                unsigned x = px[j] & 0xffffu, y = px[j] >> 16;
-                if (x >= 15u) { x = 15u; sum += linbits; }
-                if (y >= 15u) { y = 15u; sum += linbits; }
-                sum += __ldg(&c->largetbl[(x << 4) + y]);
-            }
-        }
-        sum = lg_wsum_u(sum);
-        unsigned const sum2 = sum & 0xffffu;
-        sum >>= 16u;
-        if (sum > sum2) { sum = sum2; choice = choice2; }
-        *bits += (int) sum;
-        return choice;
+    n15 = lg_wsum_u(n15);
+    /* the reference adds region 2 first, then 0, then 1 (takehiro.c:719-739); integer sums, so order-free */
+    if (has2) {
+        unsigned const s01 = lg_wsum_u((acc2 & 0x3ffu) | (((acc2 >> 10) & 0x3ffu) << 16)), s2 = lg_wsum_u(acc2 >> 20);
+        gi.table_select[2] = m2 ? lg_region_pick(R2, s01 & 0xffffu, s01 >> 16, s2, n15 >> 20, &bits) : 0;
     }
-    int t1 = LG_HUF_NOESC[mx - 1];
-    unsigned const xlen = c->huff_xlen[t1];
-    if (mx == 1) {
-        const uint8_t *h = lg_hlen(c, 1);
-        unsigned sum = 0;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            int const i = 2 * (lane + 32 * j);
-            if (i >= lo && i < hi) sum += __ldg(&h[2 * (px[j] & 0xffffu) + (px[j] >> 16)]);
-        }
-        *bits += (int) lg_wsum_u(sum);
-        return 1;
+    if (0 < a1) {
+        unsigned const s01 = lg_wsum_u((acc0 & 0x3ffu) | (((acc0 >> 10) & 0x3ffu) << 16)), s2 = lg_wsum_u(acc0 >> 20);
+        gi.table_select[0] = m0 ? lg_region_pick(R0, s01 & 0xffffu, s01 >> 16, s2, n15 & 0x3ffu, &bits) : 0;
     }
-    if (mx <= 3) {
-        const uint32_t *table = (t1 == 2) ? c->table23 : c->table56;
-        unsigned sum = 0;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            int const i = 2 * (lane + 32 * j);
-            if (i >= lo && i < hi) sum += __ldg(&table[(px[j] & 0xffffu) * xlen + (px[j] >> 16)]);
-        }
-        sum = lg_wsum_u(sum);
-        unsigned const sum2 = sum & 0xffffu;
-        sum >>= 16u;
-        if (sum > sum2) { sum = sum2; t1++; }
-        *bits += (int) sum;
-        return t1;
+    if (a1 < a2) {
+        unsigned const s01 = lg_wsum_u((acc1 & 0x3ffu) | (((acc1 >> 10) & 0x3ffu) << 16)), s2 = lg_wsum_u(acc1 >> 20);
+        gi.table_select[1] = m1 ? lg_region_pick(R1, s01 & 0xffffu, s01 >> 16, s2, (n15 >> 10) & 0x3ffu, &bits) : 0;
     }
-    {
-        const uint8_t *h1 = lg_hlen(c, t1), *h2 = lg_hlen(c, t1 + 1), *h3 = lg_hlen(c, t1 + 2);
-        unsigned s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-        for (int j = 0; j < 9; j++) {
-            int const i = 2 * (lane + 32 * j);
-            if (i >= lo && i < hi) {
-                unsigned const x = (px[j] & 0xffffu) * xlen + (px[j] >> 16);
-                s1 += __ldg(&h1[x]); s2 += __ldg(&h2[x]); s3 += __ldg(&h3[x]);
-            }
-        }
-        /* each total < 2^13: two fields per word */
-        unsigned const a = lg_wsum_u(s1 | (s2 << 16));
-        s3 = lg_wsum_u(s3);
-        s1 = a & 0xffffu; s2 = a >> 16;
-        int t = t1;
-        if (s1 > s2) { s1 = s2; t++; }
-        if (s1 > s3) { s1 = s3; t = t1 + 2; }
-        *bits += (int) s1;
-        return t;
+    if (pv && qc.block_type == LG_NORM) {
+        /* first sfb whose start is >= big_values (sfb_l is increasing and ends at 576) */
+        int const below = (lane < 23) && (c->sfb_l[lane] < bigv);
+        pv->sfb_count1 = __popc(__ballot_sync(LG_FULL, below));
     }
+    return bits;
 }
 
 /* same decision by ONE lane over ix[lo..hi) in shared memory (used where many ranges are evaluated at
@@ -334,112 +404,72 @@ __device__ __noinline__ int lg_choose_table_serial(const LgDevCfg *__restrict__ 
     return t;
 }
 
-/* count1 quadruples [bigv, count1) counted with both count1 books (warp) */
-__device__ __noinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, const int16_t *ix, int bigv, int count1, int lane, int *a1, int *a2)
-{
-    const uint8_t *t32l = lg_hlen(c, 32), *t33l = lg_hlen(c, 33);
-    unsigned s1 = 0, s2 = 0;
-    int const nq = (count1 - bigv) >> 2;
-    for (int k = lane; k < nq; k += 32) {
-        int const i = count1 - 4 * k;
-        int const p = ((ix[i - 4] * 2 + ix[i - 3]) * 2 + ix[i - 2]) * 2 + ix[i - 1];
-        s1 += __ldg(&t32l[p]); s2 += __ldg(&t33l[p]);
-    }
-    unsigned const a = lg_wsum_u(s1 | (s2 << 16));
-    *a1 = (int) (a & 0xffffu);
-    *a2 = (int) (a >> 16);
-}
 
-/* takehiro.c:654 noquant_count_bits (use_best_huffman == 2 is not on this path) */
-__device__ __noinline__ int lg_noquant_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
-                                                     LgPrev *pv, const unsigned px[9], int lane)
-{
-    int bits = 0, a1, a2;
-    int i = ((qc.max_nonzero_coeff + 2) >> 1) << 1;
-    if (i > 576) i = 576;
-    if (pv) pv->sfb_count1 = 0;
-    int hi_nz = -1, hi_big = -1;
-#pragma unroll
-    for (int j = 0; j < 9; j++) {
-        int const P = lane + 32 * j;
-        if (2 * P < i) {
-            if (px[j] != 0u) hi_nz = P;
-            if ((px[j] & 0xfffefffeu) != 0u) hi_big = P;
-        }
-    }
-    hi_nz = lg_wmax_i(hi_nz);
-    hi_big = lg_wmax_i(hi_big);
-    int const c1p = hi_nz + 1;
-    gi.count1 = 2 * c1p;
-    int const nquads = (c1p - 1 - hi_big) >> 1;
-    i = gi.count1 - 4 * nquads;
-    lg_count1_bits(c, w->ixw, i, gi.count1, lane, &a1, &a2);
-    bits = a1;
-    gi.count1table_select = 0;
-    if (a1 > a2) { bits = a2; gi.count1table_select = 1; }
-    gi.count1bits = bits;
-    gi.big_values = i;
-    if (i == 0) return bits;
-    if (qc.block_type == LG_SHORT) {
-        a1 = 3 * c->sfb_s[3];
-        if (a1 > gi.big_values) a1 = gi.big_values;
-        a2 = gi.big_values;
-    }
-    else if (qc.block_type == LG_NORM) {
-        a1 = gi.region0_count = c->bv_scf[i - 2];
-        a2 = gi.region1_count = c->bv_scf[i - 1];
-        a2 = c->sfb_l[a1 + a2 + 2];
-        a1 = c->sfb_l[a1 + 1];
-        if (a2 < i) gi.table_select[2] = lg_choose_table_warp(c, px, lane, a2, i, &bits);
-    }
-    else {
-        gi.region0_count = 7;
-        gi.region1_count = LG_SBMAX_L - 1 - 7 - 1;
-        a1 = c->sfb_l[7 + 1];
-        a2 = i;
-        if (a1 > a2) a1 = a2;
-    }
-    a1 = a1 < i ? a1 : i;
-    a2 = a2 < i ? a2 : i;
-    if (0 < a1) gi.table_select[0] = lg_choose_table_warp(c, px, lane, 0, a1, &bits);
-    if (a1 < a2) gi.table_select[1] = lg_choose_table_warp(c, px, lane, a1, a2, &bits);
-    if (pv && qc.block_type == LG_NORM) {
-        int sfb = 0;
-        while (c->sfb_l[sfb] < gi.big_values) sfb++;
-        pv->sfb_count1 = sfb;
-    }
-    return bits;
-}
-
-/* takehiro.c:767 count_bits; pv == nullptr is the reference's prev_noise == 0 */
-__device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev *pv, int lane)
-{
-    float const wlim = (LG_IXMAX) / __ldg(&c->ipow20[gi.global_gain]);
-    if (gi.xrpow_max > wlim) return LG_LARGE_BITS;
-    unsigned px[9];
-    LgPrev none; none.valid = 0; none.global_gain = 0; none.sfb_count1 = 0;
-    lg_quantize(c, w, gi, qc, pv ? *pv : none, lane, px);
-    return lg_noquant_count_bits(c, w, gi, qc, pv, px, lane);
-}
-
-/* ---------------------------------------------------------------- quantize_pvt.c:815 calc_noise: one lane per band */
+/* ---------------------------------------------------------------- quantize_pvt.c:815 calc_noise.
+ * The squared errors of all lines of the bands that need recomputing are formed line-parallel (every lane its nine
+ * pairs) into sq[]; then one lane per band adds them up serially, in the reference's order (calc_noise_core_c :750),
+ * so every float sum is the reference's.  Bands whose step did not change reuse the cached noise (prev_noise). */
 __device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
                                               LgNoiseRes *res, LgPrev *pv, int lane)
 {
+    float *bstep = reinterpret_cast<float *>(w->act);      /* per band: step size, or < 0 = cached */
+    int *breg = w->act + 40;                               /* per band: 0 beyond count1, 1 count1 region, 2 big values */
+    int need = 0;
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        if (sfb < 40) {
+            float st = -1.f;
+            if (sfb < qc.psymax) {
+                int const s = lg_band_step(gi, w, w->sfw, sfb);
+                if (!(pv->valid && w->pn_step[sfb] == s)) {
+                    st = __ldg(&c->pow20[s + LG_QMAX2]);
+                    int const j = w->lstart[sfb];
+                    breg[sfb] = (j > gi.count1) ? 0 : ((j > gi.big_values) ? 1 : 2);
+                    need = 1;
+                }
+            }
+            bstep[sfb] = st;
+        }
+    }
+    need = __any_sync(LG_FULL, need);
+    __syncwarp();
+    if (need) {
+        LG_UNROLL(LG_UNROLL_C)
+        for (int j = 0; j < 9; j++) {
+            int const i = 2 * (lane + 32 * j);
+            int const sfb = w->line_sfb[i];
+            float const step = bstep[sfb];
+            if (step >= 0.f) {
+                float2 const x = *reinterpret_cast<const float2 *>(&w->xr[i]);
+                unsigned const u = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
+                int const reg = breg[sfb];
+                float t0, t1;
+                if (reg == 0) { t0 = x.x; t1 = x.y; }
+                else if (reg == 1) {
+                    t0 = fabsf(x.x) - ((u & 0xffffu) ? step : 0.f);
+                    t1 = fabsf(x.y) - ((u >> 16) ? step : 0.f);
+                }
+                else {
+                    t0 = fabsf(x.x) - __ldg(&c->pow43[u & 0xffffu]) * step;
+                    t1 = fabsf(x.y) - __ldg(&c->pow43[u >> 16]) * step;
+                }
+                { float2 q2; q2.x = t0 * t0; q2.y = t1 * t1; *reinterpret_cast<float2 *>(&w->sq[i]) = q2; }
+            }
+        }
+        __syncwarp();
+    }
     int over = 0, ssd = 0;
     float max_noise = -20.0f;
     for (int r = 0; r < 2; r++) {
         int const sfb = lane + 32 * r;
         if (sfb < qc.psymax) {
-            int const s = lg_band_step(gi, w, w->sfw, sfb);
             float const r_l3_xmin = 1.f / w->l3_xmin[sfb];
             float distort_, noise;
-            if (pv->valid && w->pn_step[sfb] == s) {
+            if (bstep[sfb] < 0.f) {
                 distort_ = r_l3_xmin * w->pn_noise[sfb];
                 noise = w->pn_noise_log[sfb];
             }
             else {
-                float const step = __ldg(&c->pow20[s + LG_QMAX2]);
                 int const width = w->width[sfb];
                 int j = w->lstart[sfb];
                 int l = width >> 1;
@@ -447,30 +477,10 @@ __device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWa
                     int const usefullsize = qc.max_nonzero_coeff - j + 1;
                     l = usefullsize > 0 ? usefullsize >> 1 : 0;
                 }
-                /* quantize_pvt.c:750 calc_noise_core_c */
                 noise = 0;
-                if (j > gi.count1) {
-                    while (l--) {
-                        float t;
-                        t = w->xr[j]; j++; noise += t * t;
-                        t = w->xr[j]; j++; noise += t * t;
-                    }
-                }
-                else if (j > gi.big_values) {
-                    while (l--) {
-                        float t;
-                        t = fabsf(w->xr[j]) - (w->ixw[j] ? step : 0.f); j++; noise += t * t;
-                        t = fabsf(w->xr[j]) - (w->ixw[j] ? step : 0.f); j++; noise += t * t;
-                    }
-                }
-                else {
-                    while (l--) {
-                        float t;
-                        t = fabsf(w->xr[j]) - __ldg(&c->pow43[w->ixw[j]]) * step; j++; noise += t * t;
-                        t = fabsf(w->xr[j]) - __ldg(&c->pow43[w->ixw[j]]) * step; j++; noise += t * t;
-                    }
-                }
-                w->pn_step[sfb] = s;
+                const float2 *q = reinterpret_cast<const float2 *>(&w->sq[j]);
+                for (int k = 0; k < l; k++) { float2 const v = q[k]; noise += v.x; noise += v.y; }
+                w->pn_step[sfb] = lg_band_step(gi, w, w->sfw, sfb);
                 w->pn_noise[sfb] = noise;
                 distort_ = r_l3_xmin * noise;
                 noise = (float) LG_FAST_LOG10_D(c->log_table, (distort_ > 1E-20f ? distort_ : 1E-20f));
@@ -516,12 +526,12 @@ __device__ __noinline__ int lg_scale_bitcount(LgQWarp *w, LgQInfo &gi, const LgQ
     }
     m1 = lg_wmax_i(m1);
     m2 = lg_wmax_i(m2);
+    /* the 16 (slen1, slen2) candidates one per lane; smallest length wins, the lowest index on ties (as the reference's scan) */
+    int key = 0x7fffffff;
+    if (lane < 16 && m1 < LG_SLEN1_N[lane] && m2 < LG_SLEN2_N[lane]) key = tab[lane] * 16 + lane;
+    key = lg_wmin_i(key);
     gi.part2_length = LG_LARGE_BITS;
-    for (int k = 0; k < 16; k++)
-        if (m1 < LG_SLEN1_N[k] && m2 < LG_SLEN2_N[k] && gi.part2_length > tab[k]) {
-            gi.part2_length = tab[k];
-            gi.scalefac_compress = k;
-        }
+    if (key != 0x7fffffff) { gi.part2_length = key >> 4; gi.scalefac_compress = key & 15; }
     return gi.part2_length == LG_LARGE_BITS;
 }
 
@@ -538,7 +548,7 @@ __device__ __forceinline__ int lg_loop_break(const LgQWarp *w, const LgQInfo &gi
 __device__ __noinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const float *fac /* shared, per sfb, 0 = untouched */, int lane)
 {
     float mx = gi.xrpow_max;
-#pragma unroll
+    LG_UNROLL(LG_UNROLL_C)
     for (int j = 0; j < 9; j++) {
         int const i = 2 * (lane + 32 * j);
         float const f = fac[w->line_sfb[i]];
@@ -749,7 +759,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
     best_noise.bits = gi.part2_3_length;
     LgQInfo best = gi;                            /* cod_info_w = *cod_info: from here gi is the work copy */
     lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
-    lg_copy_f576(w->save_xrpow, w->xrpow, lane);
+    if (c->noise_shaping_amp == 3) lg_copy_f576(w->save_xrpow, w->xrpow, lane);
     int age = 0, best_part2_3_length = 9999999, bEndOfSearch = 0, bRefine = 0, best_ggain_pass1 = 0;
     int guard = 0;
     while (!bEndOfSearch) {
@@ -782,7 +792,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
                 best = gi;
                 lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
                 age = 0;
-                lg_copy_f576(w->save_xrpow, w->xrpow, lane);
+                if (c->noise_shaping_amp == 3) lg_copy_f576(w->save_xrpow, w->xrpow, lane);   /* only the refinement pass reads it back */
             }
             else if (c->full_outer_loop == 0) {
                 if (++age > search_limit && best_noise.over_count == 0) break;
@@ -842,7 +852,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
     }
     /* highest non-zero line */
     int k = 0;
-#pragma unroll
+    LG_UNROLL(LG_UNROLL_C)
     for (int j = 0; j < 9; j++) {
         int const i = 2 * (lane + 32 * j);
         if (fabsf(w->xr[i + 1]) > 1e-12f) k = i + 1;
@@ -1223,7 +1233,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                 __syncwarp();
                 /* quantize.c:110 init_xrpow (upper = 575) */
                 float mx = 0.f, amax = 0.f;
-#pragma unroll
+    LG_UNROLL(LG_UNROLL_C)
                 for (int j = 0; j < 9; j++) {
                     int const i = 2 * (lane + 32 * j);
                     float const t0 = fabsf(w->xr[i]), t1 = fabsf(w->xr[i + 1]);
@@ -1261,7 +1271,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                 }
                 /* hand the granule to the bit packer */
                 LgGranuleOut *o = gout + (((size_t) stream * 2 * nframes + gb) * 2 + ch);
-#pragma unroll
+    LG_UNROLL(LG_UNROLL_C)
                 for (int j = 0; j < 9; j++) {
                     int const i = 2 * (lane + 32 * j);
                     int v0 = w->ixw[i], v1 = w->ixw[i + 1];

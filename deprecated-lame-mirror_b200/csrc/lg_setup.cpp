@@ -703,4 +703,23 @@ static void finish_device_tables(LgDevCfg *c)
     memcpy(c->largetbl, LGT_LARGETBL, sizeof LGT_LARGETBL);
     memcpy(c->table23, LGT_TABLE23, sizeof LGT_TABLE23);
     memcpy(c->table56, LGT_TABLE56, sizeof LGT_TABLE56);
+    /* packed per-class books (see lg_types.h): candidates {1} {2,3} {5,6} {7,8,9} {10,11,12} {13,14,15} {16..23, 24..31} */
+    {
+        static const int cand[6][3] = { { 1, 1, 1 }, { 2, 3, 3 }, { 5, 6, 6 }, { 7, 8, 9 }, { 10, 11, 12 }, { 13, 14, 15 } };
+        static const int lim[6] = { 2, 3, 4, 6, 8, 16 };
+        memset(c->huff_pk, 0, sizeof c->huff_pk);
+        for (int k = 0; k < 6; k++) {
+            int const xlen = c->huff_xlen[cand[k][0]];
+            for (int x = 0; x < lim[k]; x++)
+                for (int y = 0; y < lim[k]; y++) {
+                    uint32_t e = 0;
+                    for (int f = 0; f < 3; f++) e |= (uint32_t) c->huff_len[c->huff_off[cand[k][f]] + x * xlen + y] << (10 * f);
+                    c->huff_pk[k * 256 + x * 16 + y] = e;
+                }
+        }
+        for (int i = 0; i < 256; i++) {
+            uint32_t const a = c->largetbl[i] >> 16, b = c->largetbl[i] & 0xffffu;
+            c->huff_pk[6 * 256 + i] = a | (b << 10) | (b << 20);
+        }
+    }
 }

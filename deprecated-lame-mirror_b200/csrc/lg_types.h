@@ -86,6 +86,10 @@ typedef struct {
     uint8_t  huff_xlen[34];
     uint16_t huff_linmax[34];
     uint32_t largetbl[256], table23[9], table56[16];
+    /* one packed length book per magnitude class of a region (max 1 | 2 | 3 | 4-5 | 6-7 | 8-15 | escape): entry
+     * [class][x*16+y] = bits under the class's three candidate tables in 10-bit fields (two-candidate classes repeat
+     * the second), so one code path replaces count_bit_noESC/_from2/_from3/_ESC (takehiro.c:449-573) */
+    uint32_t huff_pk[7 * 256];
 } LgDevCfg;
 
 /* ---- stage A (stateless analysis) -> stage B (ordered scan) */
