@@ -10,11 +10,18 @@
 #include <algorithm>
 #include <functional>
 #include <new>
+#include <chrono>
+#include <mutex>
+#include <condition_variable>
+#include <memory>
 #include "../../include/lamegpu.h"
 #include "lg_engine.h"
 #include "lg_bitstream.h"
 
 namespace {
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+static const bool g_timing = getenv("LAMEGPU_TIMING") != nullptr;
 
 /* One stream = one lame_t of the reference.  The PCM timeline is the reference's zero-prefixed stream:
  * 528 zeros (ENCDELAY - MDCTDELAY, lame.c:2302) then the user's samples; frame k is encodable once the
@@ -70,17 +77,60 @@ struct Stream {
     }
 };
 
-void parallel_for(int n, int nthreads, const std::function<void(int)> &fn)
-{
-    if (nthreads <= 1 || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
-    std::atomic<int> next(0);
-    auto work = [&]() { for (;;) { int const i = next.fetch_add(1); if (i >= n) break; fn(i); } };
-    std::vector<std::thread> th;
-    int const nt = std::min(nthreads, n);
-    for (int t = 1; t < nt; t++) th.emplace_back(work);
-    work();
-    for (auto &t : th) t.join();
-}
+/* Persistent worker pool: the per-call host work (PCM staging, bit packing, output hand-over) is a few hundred
+ * microseconds per thread, so spawning threads per call would cost as much as the work itself. */
+class Pool {
+public:
+    explicit Pool(int nthreads) : n_(std::max(1, nthreads))
+    {
+        for (int t = 1; t < n_; t++) th_.emplace_back([this]() { worker(); });
+    }
+    ~Pool()
+    {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return n_; }
+    void run(int n, const std::function<void(int)> &fn)
+    {
+        if (n_ <= 1 || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+        {
+            std::lock_guard<std::mutex> g(m_);
+            fn_ = &fn; total_ = n; next_.store(0); active_ = (int) th_.size(); gen_++;
+        }
+        cv_.notify_all();
+        drain();
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this]() { return active_ == 0; });
+        fn_ = nullptr;
+    }
+private:
+    void drain() { for (;;) { int const i = next_.fetch_add(1); if (i >= total_) break; (*fn_)(i); } }
+    void worker()
+    {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> g(m_);
+                cv_.wait(g, [&]() { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            drain();
+            { std::lock_guard<std::mutex> g(m_); if (--active_ == 0) done_.notify_one(); }
+        }
+    }
+    int n_;
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int total_ = 0, active_ = 0;
+    unsigned long gen_ = 0;
+    bool stop_ = false;
+};
 
 } // namespace
 
@@ -88,6 +138,13 @@ struct lamegpu_batch {
     LgDevCfg cfg;
     lg_engine *eng = nullptr;
     int S = 0, F = 0, nthreads = 1;
+    std::unique_ptr<Pool> pool;
+    void parallel_for(int n, const std::function<void(int)> &fn)
+    {
+        if (n <= 1 || nthreads <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+        if (!pool || pool->size() != nthreads) pool.reset(new Pool(nthreads));
+        pool->run(n, fn);
+    }
     std::vector<Stream> st;
     long frames_total = 0;
 
@@ -106,10 +163,11 @@ struct lamegpu_batch {
             }
             if (maxf == 0) break;
             size_t const stride = lg_engine_pcm_stride(eng);
+            double const t0 = now_ms();
             if (any_float) {
                 if (lg_engine_need_float_pcm(eng) != 0) return -2;
                 float *hp = lg_engine_host_pcmf(eng);
-                parallel_for(S, nthreads, [&](int s) {
+                parallel_for(S, [&](int s) {
                     if (!nfr[s]) return;
                     st[s].to_float(&cfg);
                     size_t const n = (size_t) nfr[s] * 1152 + LG_PCM_HALO;
@@ -118,18 +176,20 @@ struct lamegpu_batch {
             }
             else {
                 int16_t *hp = lg_engine_host_pcm16(eng);
-                parallel_for(S, nthreads, [&](int s) {
+                parallel_for(S, [&](int s) {
                     if (!nfr[s]) return;
                     size_t const n = (size_t) nfr[s] * 1152 + LG_PCM_HALO;
                     for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcm16[c].data(), n * sizeof(int16_t));
                 });
             }
             if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: launch maxf=%d float=%d\n", maxf, any_float);
+            double const t1 = now_ms();
             if (lg_engine_encode(eng, maxf, any_float) != 0) return -2;
+            double const t2 = now_ms();
             if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: device done, packing\n");
             const LgGranuleOut *go = lg_engine_host_gout(eng);
             const LgFrameOut *fo = lg_engine_host_fout(eng);
-            parallel_for(S, nthreads, [&](int s) {
+            parallel_for(S, [&](int s) {
                 Stream &x = st[s];
                 for (int f = 0; f < nfr[s]; f++) {
                     const LgFrameOut *fr = fo + (size_t) s * F + f;
@@ -143,6 +203,7 @@ struct lamegpu_batch {
                 x.drop_consumed();
             });
             for (int s = 0; s < S; s++) done += nfr[s];
+            if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, device(H2D+kernels+D2H) %.2f ms, pack %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
             if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: packed, %ld frames so far\n", done);
         }
         frames_total += done;
@@ -248,10 +309,10 @@ long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const sho
                           unsigned char *const *out, const int *out_cap, int *out_bytes)
 {
     if (!b) return -3;
-    for (int s = 0; s < b->S; s++) b->feed16(s, pcm_l[s], pcm_r ? pcm_r[s] : NULL, nsamples[s]);
+    b->parallel_for(b->S, [&](int s) { b->feed16(s, pcm_l[s], pcm_r ? pcm_r[s] : NULL, nsamples[s]); });
     long const done = b->pump();
     if (done < 0) return done;
-    for (int s = 0; s < b->S; s++) out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0;
+    b->parallel_for(b->S, [&](int s) { out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0; });
     return done;
 }
 
@@ -281,10 +342,14 @@ long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int 
 long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsamples, unsigned char *out, int out_stride, int *out_bytes)
 {
     if (!b) return -3;
-    for (int s = 0; s < b->S; s++) b->feed16(s, pcm + ((size_t) s * 2) * nsamples, pcm + ((size_t) s * 2 + 1) * nsamples, nsamples);
+    double const t0 = now_ms();
+    b->parallel_for(b->S, [&](int s) { b->feed16(s, pcm + ((size_t) s * 2) * nsamples, pcm + ((size_t) s * 2 + 1) * nsamples, nsamples); });
+    double const t1 = now_ms();
     long const done = b->pump();
     if (done < 0) return done;
-    for (int s = 0; s < b->S; s++) out_bytes[s] = b->take(s, out + (size_t) s * out_stride, out_stride);
+    double const t2 = now_ms();
+    b->parallel_for(b->S, [&](int s) { out_bytes[s] = b->take(s, out + (size_t) s * out_stride, out_stride); });
+    if (g_timing) fprintf(stderr, "lamegpu: feed %.2f ms, pump %.2f ms, take %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
     return done;
 }
 
