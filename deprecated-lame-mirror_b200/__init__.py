@@ -212,7 +212,7 @@ class BatchEncoder:
             raise LameGpuError("lamegpu_batch_rerun_device failed")
 
     def kernel_ms(self):
-        ms = (ctypes.c_float * 4)()
+        ms = (ctypes.c_float * 5)()
         self._lib.lamegpu_batch_kernel_ms(self._h, ms)
         return [float(x) for x in ms]
 

@@ -187,13 +187,14 @@ struct lamegpu_batch {
             if (lg_engine_encode(eng, maxf, any_float) != 0) return -2;
             double const t2 = now_ms();
             if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: device done, packing\n");
-            const LgGranuleOut *go = lg_engine_host_gout(eng);
             const LgFrameOut *fo = lg_engine_host_fout(eng);
+            const unsigned char *pay = lg_engine_host_pay(eng), *hdr = lg_engine_host_hdr(eng);
+            size_t const pay_stride = lg_engine_pay_stride(eng);
             parallel_for(S, [&](int s) {
                 Stream &x = st[s];
                 for (int f = 0; f < nfr[s]; f++) {
                     const LgFrameOut *fr = fo + (size_t) s * F + f;
-                    lg_pack_frame(&x.bw, &cfg, fr, go + ((size_t) s * 2 * F + 2 * f) * 2);
+                    lg_merge_frame(&x.bw, &cfg, fr, hdr + ((size_t) s * F + f) * LG_HDR_STRIDE, pay + (size_t) s * pay_stride + fr->pay_off);
                     x.last_padding = fr->padding;
                 }
                 x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
@@ -203,7 +204,7 @@ struct lamegpu_batch {
                 x.drop_consumed();
             });
             for (int s = 0; s < S; s++) done += nfr[s];
-            if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, device(H2D+kernels+D2H) %.2f ms, pack %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
+            if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, device(H2D+kernels+D2H) %.2f ms, merge %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
             if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: packed, %ld frames so far\n", done);
         }
         frames_total += done;
@@ -389,11 +390,11 @@ int lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes)
     if (lg_engine_run_device(b->eng, nframes, 0) != 0) return -1;
     return lg_engine_sync(b->eng);
 }
-int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[4])
+int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5])
 {
     if (!b) return -1;
     const float *m = lg_engine_last_kernel_ms(b->eng);
-    for (int i = 0; i < 4; i++) ms[i] = m[i];
+    for (int i = 0; i < 5; i++) ms[i] = m[i];
     return 0;
 }
 long lamegpu_batch_kernel_launches(const lamegpu_batch *b) { return b ? lg_engine_launch_count(b->eng) : 0; }

@@ -267,6 +267,39 @@ void lg_pack_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, c
     }
 }
 
+/* The product path: kernel E has already formed the frame's bits.  hdr = header + side info (sideinfo_len bytes),
+ * pay = the frame's payload (ancillary drain + main data, whole bytes).  What is left is what format_bitstream does
+ * with its header ring (bitstream.c:918-960, putheader_bits :130): the payload goes out in order, and each pending
+ * header is spliced in when the stream reaches the position where its frame starts. */
+void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const unsigned char *hdr, const unsigned char *pay)
+{
+    int const sl = cfg->sideinfo_len;
+    memcpy(bw->header[bw->h_ptr].buf, hdr, sl);
+    int const old = bw->h_ptr;
+    bw->h_ptr = (old + 1) & (LG_MAX_HEADER_BUF - 1);
+    bw->header[bw->h_ptr].write_timing = bw->header[old].write_timing + frame_bits(cfg, fo->padding);
+    long n = fo->pay_bytes;
+    while (n > 0) {
+        long const until = bw->header[bw->w_ptr].write_timing - bw->totbit;     /* bits to the next frame start */
+        if (until == 0) {
+            bw->buf.insert(bw->buf.end(), bw->header[bw->w_ptr].buf, bw->header[bw->w_ptr].buf + sl);
+            bw->totbit += 8L * sl;
+            bw->w_ptr = (bw->w_ptr + 1) & (LG_MAX_HEADER_BUF - 1);
+            continue;
+        }
+        long chunk = until / 8;
+        if (until < 0 || chunk > n) chunk = n;
+        bw->buf.insert(bw->buf.end(), pay, pay + chunk);
+        pay += chunk; n -= chunk;
+        bw->totbit += 8 * chunk;
+    }
+    bw->ancillary_flag = fo->anc_post;
+    if (bw->totbit > 1000000000) {
+        for (int i = 0; i < LG_MAX_HEADER_BUF; ++i) bw->header[i].write_timing -= bw->totbit;
+        bw->totbit = 0;
+    }
+}
+
 void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_padding)
 {
     int const first_ptr = bw->w_ptr;

@@ -7,6 +7,7 @@
 #define LG_LAUNCH(kern, grid, block, smem, stream, ...) \
     emu::launch(emu::dim3_t(grid), emu::dim3_t(block), (smem), [=]() { kern(__VA_ARGS__); })
 #define LG_HD
+#define LG_NAMED_BARRIER(id, count) emu::named_barrier((id), (count))
 #else
 #include <cuda_runtime.h>
 #define LG_DYN_SMEM(type, name)                                   \
@@ -14,5 +15,6 @@
     type *name = reinterpret_cast<type *>(lg_smem_raw)
 #define LG_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
 #define LG_HD __host__ __device__
+#define LG_NAMED_BARRIER(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
 #endif
 #define LG_FULL 0xffffffffu

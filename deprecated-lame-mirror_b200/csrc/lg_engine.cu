@@ -1,10 +1,10 @@
 // lg_engine.cu - device side of the batch engine: owns the HBM buffers of one configuration
 // (S streams x up to F frames per launch), the four kernels and the copies.
 //
-//   H2D  pcm (int16 or float, pinned)  ->  A analysis  ->  B scan  ->  C mdct  ->  D quantise  ->  D2H out
+//   H2D  pcm (int16 or float, pinned)  ->  A analysis  ->  B scan  ->  C mdct  ->  D quantise  ->  E pack  ->  D2H bytes
 //
-// All work of one launch goes to one CUDA stream; the host packer (lg_bitstream.cpp) consumes the D2H
-// result.  There is no CPU fallback: without a CUDA device lg_engine_create() fails and says so.
+// All work of one launch goes to one CUDA stream; the host (lg_bitstream.cpp) only interleaves the packed
+// payload bytes with the frame headers.  There is no CPU fallback: without a CUDA device lg_engine_create() fails and says so.
 //
 // This translation unit is also compiled by g++ with -DLG_EMULATE for tests/emu (see lg_compat.h); that
 // build is test infrastructure and is never loaded by the product package.
@@ -18,6 +18,7 @@
 #include "lg_k_scan.cuh"
 #include "lg_k_mdct.cuh"
 #include "lg_k_quant.cuh"
+#include "lg_k_pack.cuh"
 #include "lg_engine.h"
 
 #ifdef LG_EMULATE
@@ -52,16 +53,18 @@ struct lg_engine {
     float *d_sb, *d_xr;
     LgAnalysis *d_ana; LgPsyOut *d_psy; LgFrameCtl *d_frm;
     LgGranuleOut *d_gout; LgFrameOut *d_fout;
+    unsigned char *d_pay, *d_hdr;      /* kernel E: payload bytes [S][pay_stride], header + side info [S][F][LG_HDR_STRIDE] */
+    size_t pay_stride;
     LgStreamState *d_state, *d_state0;   /* d_state0: S copies of the initial state, for one-copy resets */
     int *d_nfr;
     /* pinned host staging */
     int16_t *h_pcm16; float *h_pcmf; int *h_nfr;
-    LgGranuleOut *h_gout; LgFrameOut *h_fout;
+    LgFrameOut *h_fout; unsigned char *h_pay, *h_hdr;
     lgStream_t stream;
 #ifndef LG_EMULATE
-    cudaEvent_t ev[6];
+    cudaEvent_t ev[7];
 #endif
-    float last_ms[5];
+    float last_ms[6];
     long launches;
 };
 
@@ -72,7 +75,9 @@ extern "C" size_t lg_engine_pcm_stride(const lg_engine *e) { return e->pcm_strid
 extern "C" int16_t *lg_engine_host_pcm16(lg_engine *e) { return e->h_pcm16; }
 extern "C" float *lg_engine_host_pcmf(lg_engine *e) { return e->h_pcmf; }
 extern "C" int *lg_engine_host_nfr(lg_engine *e) { return e->h_nfr; }
-extern "C" const LgGranuleOut *lg_engine_host_gout(const lg_engine *e) { return e->h_gout; }
+extern "C" const unsigned char *lg_engine_host_pay(const lg_engine *e) { return e->h_pay; }
+extern "C" const unsigned char *lg_engine_host_hdr(const lg_engine *e) { return e->h_hdr; }
+extern "C" size_t lg_engine_pay_stride(const lg_engine *e) { return e->pay_stride; }
 extern "C" const LgFrameOut *lg_engine_host_fout(const lg_engine *e) { return e->h_fout; }
 extern "C" const float *lg_engine_last_kernel_ms(const lg_engine *e) { return e->last_ms; }
 extern "C" long lg_engine_launch_count(const lg_engine *e) { return e->launches; }
@@ -105,11 +110,11 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
 #endif
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_xr);
-    lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout);
+    lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout); lg_dev_free(e->d_pay); lg_dev_free(e->d_hdr);
     lg_dev_free(e->d_state); lg_dev_free(e->d_state0); lg_dev_free(e->d_nfr);
-    lg_host_free(e->h_pcm16); lg_host_free(e->h_pcmf); lg_host_free(e->h_nfr); lg_host_free(e->h_gout); lg_host_free(e->h_fout);
+    lg_host_free(e->h_pcm16); lg_host_free(e->h_pcmf); lg_host_free(e->h_nfr); lg_host_free(e->h_pay); lg_host_free(e->h_hdr); lg_host_free(e->h_fout);
 #ifndef LG_EMULATE
-    for (int i = 0; i < 6; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 7; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
 #endif
     free(e);
@@ -143,6 +148,10 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     e->hcfg = *cfg;
     e->S = nstreams; e->F = max_frames; e->device = device;
     e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
+    {   /* largest frame (padded) minus its side info, per frame, plus what a full reservoir can add */
+        size_t const frame_bytes = (size_t) (cfg->version + 1) * 72000 * cfg->brate / cfg->samplerate + 1;
+        e->pay_stride = ((size_t) max_frames * (frame_bytes - cfg->sideinfo_len) + LG_PAY_SLACK + 15) & ~(size_t) 15;
+    }
     size_t const S = nstreams, F = max_frames;
     int bad = 0;
     bad |= lg_dev_malloc((void **) &e->dcfg, sizeof(LgDevCfg));
@@ -154,22 +163,26 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     bad |= lg_dev_malloc((void **) &e->d_frm, S * F * sizeof(LgFrameCtl));
     bad |= lg_dev_malloc((void **) &e->d_gout, S * 2 * F * 2 * sizeof(LgGranuleOut));
     bad |= lg_dev_malloc((void **) &e->d_fout, S * F * sizeof(LgFrameOut));
+    bad |= lg_dev_malloc((void **) &e->d_pay, S * e->pay_stride);
+    bad |= lg_dev_malloc((void **) &e->d_hdr, S * F * LG_HDR_STRIDE);
     bad |= lg_dev_malloc((void **) &e->d_state, S * sizeof(LgStreamState));
     bad |= lg_dev_malloc((void **) &e->d_state0, S * sizeof(LgStreamState));
     bad |= lg_dev_malloc((void **) &e->d_nfr, S * sizeof(int));
     bad |= lg_host_malloc((void **) &e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t));
     bad |= lg_host_malloc((void **) &e->h_nfr, S * sizeof(int));
-    bad |= lg_host_malloc((void **) &e->h_gout, S * 2 * F * 2 * sizeof(LgGranuleOut));
+    bad |= lg_host_malloc((void **) &e->h_pay, S * e->pay_stride);
+    bad |= lg_host_malloc((void **) &e->h_hdr, S * F * LG_HDR_STRIDE);
     bad |= lg_host_malloc((void **) &e->h_fout, S * F * sizeof(LgFrameOut));
     if (bad) { fprintf(stderr, "lamegpu: out of memory (S=%d F=%d)\n", nstreams, max_frames); lg_engine_destroy(e); return NULL; }
 #ifdef LG_EMULATE
     memcpy(e->dcfg, cfg, sizeof *cfg);
 #else
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
-    for (int i = 0; i < 6; i++) cudaEventCreate(&e->ev[i]);
+    for (int i = 0; i < 7; i++) cudaEventCreate(&e->ev[i]);
     if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+    cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
 #endif
     {
         LgStreamState *h0 = (LgStreamState *) malloc(S * sizeof(LgStreamState));
@@ -231,9 +244,14 @@ extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
               e->d_state, e->d_nfr, F);
 #ifndef LG_EMULATE
     cudaEventRecord(e->ev[4], e->stream);
+    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: quant done (%s)\n", cudaGetErrorString(r)); }
+#endif
+    LG_LAUNCH(lg_kernel_pack, S * F, 128, sizeof(LgSmemE), e->stream, e->dcfg, e->d_gout, e->d_fout, e->d_pay, (int) e->pay_stride, e->d_hdr, e->d_nfr, F);
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev[5], e->stream);
     LG_CHECK(cudaGetLastError());
 #endif
-    e->launches += 4;
+    e->launches += 5;
     return 0;
 }
 
@@ -241,7 +259,7 @@ extern "C" int lg_engine_sync(lg_engine *e)
 {
 #ifndef LG_EMULATE
     LG_CHECK(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < 4; i++) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->last_ms[i] = ms; }
+    for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->last_ms[i] = ms; }
 #endif
     return 0;
 }
@@ -257,8 +275,9 @@ extern "C" int lg_engine_encode(lg_engine *e, int nframes, int use_float)
     else LG_COPY_H2D(e->d_pcm16, e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t), e->stream);
     LG_COPY_H2D(e->d_nfr, e->h_nfr, S * sizeof(int), e->stream);
     if (lg_engine_run_device(e, nframes, use_float) != 0) return -1;
-    LG_COPY_D2H(e->h_gout, e->d_gout, S * 2 * F * 2 * sizeof(LgGranuleOut), e->stream);
     LG_COPY_D2H(e->h_fout, e->d_fout, S * F * sizeof(LgFrameOut), e->stream);
+    LG_COPY_D2H(e->h_pay, e->d_pay, S * e->pay_stride, e->stream);
+    LG_COPY_D2H(e->h_hdr, e->d_hdr, S * F * LG_HDR_STRIDE, e->stream);
     return lg_engine_sync(e);
 }
 

@@ -22,7 +22,9 @@ size_t lg_engine_pcm_stride(const lg_engine *e);
 int16_t *lg_engine_host_pcm16(lg_engine *e);
 float *lg_engine_host_pcmf(lg_engine *e);
 int *lg_engine_host_nfr(lg_engine *e);
-const LgGranuleOut *lg_engine_host_gout(const lg_engine *e);
+const unsigned char *lg_engine_host_pay(const lg_engine *e);
+const unsigned char *lg_engine_host_hdr(const lg_engine *e);
+size_t lg_engine_pay_stride(const lg_engine *e);
 const LgFrameOut *lg_engine_host_fout(const lg_engine *e);
 const float *lg_engine_last_kernel_ms(const lg_engine *e);
 long lg_engine_launch_count(const lg_engine *e);

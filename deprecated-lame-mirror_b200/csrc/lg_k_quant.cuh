@@ -1145,6 +1145,15 @@ __device__ __forceinline__ void lg_reduce_side(int targ_bits[2], float ms_ener_r
     }
 }
 
+/* bitstream.c:214 drain_into_ancillary: after the bytes "LAME" and the version string, how many bits are written one by one
+ * with the alternating ancillary flag */
+__device__ __forceinline__ int lg_drain_tail_bits(int remainingBits)
+{
+    for (int i = 0; i < 4; i++) if (remainingBits >= 8) remainingBits -= 8;
+    if (remainingBits >= 32) for (int i = 0; i < 6 && remainingBits >= 8; ++i) remainingBits -= 8;
+    return remainingBits;
+}
+
 /* ---------------------------------------------------------------- the kernel */
 __global__ void __launch_bounds__(64)
 lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy,
@@ -1159,6 +1168,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
     LgQWarp *w = &sm->w[ch];
     int resv_size = st->resv_size, main_data_begin = st->main_data_begin;
     int old_value = st->old_value[ch], current_step = st->current_step[ch];
+    int anc_flag = st->ancillary_flag, pay_off = 0;
 
     int const my_frames = nfr[stream];
     for (int frame = 0; frame < my_frames; frame++) {
@@ -1174,6 +1184,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
             if (resv_max < 0 || cfg->disable_reservoir) resv_max = 0;
         }
         uint8_t scfsi[4] = { 0, 0, 0, 0 };
+        int frame_used = 0;
         for (int gr = 0; gr < 2; gr++) {
             int const gb = 2 * frame + gr;
             const LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
@@ -1296,6 +1307,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
             else if (lane == 0) sm->used_bits[ch] = 0;
             __syncthreads();
             resv_size -= sm->used_bits[0] + sm->used_bits[1];        /* reservoir.c:226 ResvAdjust */
+            frame_used += sm->used_bits[0] + sm->used_bits[1];
             __syncthreads();
         }
         /* reservoir.c:239 ResvFrameEnd + the main_data_begin recurrence of format_bitstream (bitstream.c:937) */
@@ -1314,18 +1326,27 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
             resv_size -= stuffingBits;
             main_data_begin = resv_size / 8;                       /* bitstream.c:937-951: mdb*8 == ResvSize */
             LgFrameOut *fo = fout + (size_t) stream * nframes + frame;
+            /* payload of this frame = ancillary drain + main data + ancillary drain: always whole bytes, because
+             * ResvFrameEnd keeps the reservoir a multiple of 8 bits */
+            int const pay_bits = drain_pre + frame_used + drain_post;
+            if (pay_bits & 7) lg_runaway();
+            int const anc_pre = anc_flag;
+            if (!cfg->disable_reservoir) anc_flag ^= (lg_drain_tail_bits(drain_pre) + lg_drain_tail_bits(drain_post)) & 1;
             if (lane == 0) {
                 if (ch == 0) {
                     fo->main_data_begin = mdb_header; fo->drain_pre = drain_pre; fo->drain_post = drain_post;
                     fo->padding = padding; fo->mode_ext = mode_ext; fo->resv_size = resv_size;
+                    fo->pay_off = pay_off; fo->pay_bytes = pay_bits >> 3;
+                    fo->anc_pre = (uint8_t) anc_pre; fo->anc_post = (uint8_t) anc_flag; fo->pad_[0] = fo->pad_[1] = 0; fo->pad2_ = 0;
                 }
                 if (ch < nch) for (int i = 0; i < 4; i++) fo->scfsi[ch][i] = scfsi[i];
                 else for (int i = 0; i < 4; i++) fo->scfsi[ch][i] = 0;
             }
+            pay_off += pay_bits >> 3;
         }
     }
     if (lane == 0) {
-        if (ch == 0) { st->resv_size = resv_size; st->main_data_begin = main_data_begin; }
+        if (ch == 0) { st->resv_size = resv_size; st->main_data_begin = main_data_begin; st->ancillary_flag = anc_flag; }
         st->old_value[ch] = old_value;
         st->current_step[ch] = current_step;
     }

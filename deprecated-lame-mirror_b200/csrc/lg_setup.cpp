@@ -695,6 +695,7 @@ static void finish_device_tables(LgDevCfg *c)
             cnt = (t < 33 ? LGT_HUFF_OFF[t + 1] : (int) sizeof LGT_HUFF_LEN) - LGT_HUFF_OFF[t];
             c->huff_off[t] = n;
             memcpy(c->huff_len + n, LGT_HUFF_LEN + LGT_HUFF_OFF[t], cnt);
+            for (int k = 0; k < cnt; k++) c->huff_code[n + k] = LGT_HUFF_CODE[LGT_HUFF_OFF[t] + k];
             n += cnt;
         }
         c->huff_xlen[t] = LGT_HUFF_XLEN[t];

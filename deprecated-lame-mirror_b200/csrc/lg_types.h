@@ -90,6 +90,7 @@ typedef struct {
      * [class][x*16+y] = bits under the class's three candidate tables in 10-bit fields (two-candidate classes repeat
      * the second), so one code path replaces count_bit_noESC/_from2/_from3/_ESC (takehiro.c:449-573) */
     uint32_t huff_pk[7 * 256];
+    uint16_t huff_code[2048];           /* code words, same layout as huff_len (bit packer, tables.c HB tables) */
 } LgDevCfg;
 
 /* ---- stage A (stateless analysis) -> stage B (ordered scan) */
@@ -137,7 +138,15 @@ typedef struct {
 typedef struct {
     int32_t main_data_begin, drain_pre, drain_post, padding, mode_ext, resv_size;
     uint8_t scfsi[2][4];
+    /* for the device bit packer (kernel E): where this frame's payload (ancillary drain + main data, a whole number
+     * of bytes) sits in the stream's payload buffer of this launch, and the state of the alternating stuffing bit
+     * (bitstream.c:246-256) before and after the frame */
+    int32_t pay_off, pay_bytes;
+    uint8_t anc_pre, anc_post, pad_[2];
+    int32_t pad2_;
 } LgFrameOut;
+#define LG_HDR_STRIDE 40                /* bytes reserved per frame for header + side info (sideinfo_len <= 36) */
+#define LG_PAY_SLACK 1024               /* a launch can drain at most the reservoir (511 bytes) on top of its own frames */
 
 /* ---- per-stream state carried across batches (reference PsyStateVar_t util.h:219, ATH_t :166,
  *      EncStateVar_t :242, QntStateVar_t :318) */
@@ -152,4 +161,5 @@ typedef struct {
     int   resv_size, main_data_begin;
     int   old_value[2], current_step[2];
     int   frames_done;
+    int   ancillary_flag;
 } LgStreamState;

@@ -40,6 +40,8 @@ static void run_block(Block &b, std::vector<char> &stacks)
 {
     g_blk = &b;
     b.bar_count = b.bar_gen = 0;
+    std::memset(b.nbar_count, 0, sizeof b.nbar_count);
+    std::memset(b.nbar_gen, 0, sizeof b.nbar_gen);
     std::memset(b.warps, 0, sizeof b.warps);
     for (int t = 0; t < b.nthreads; t++) {
         Fiber &f = b.fibers[t];

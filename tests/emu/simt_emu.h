@@ -34,6 +34,7 @@ struct Block {
     dim3_t bidx, bdim, gdim;
     unsigned char *smem;
     int bar_count, bar_gen;
+    int nbar_count[16], nbar_gen[16];      /* named barriers (bar.sync id, count) */
     WarpSync warps[32];
     const std::function<void()> *body;
 };
@@ -82,6 +83,14 @@ inline void syncthreads()
     int const g = b->bar_gen;
     if (++b->bar_count == b->nthreads) { b->bar_count = 0; b->bar_gen = g + 1; }
     else while (b->bar_gen == g) yield();
+}
+
+inline void named_barrier(int id, int count)
+{
+    Block *b = g_blk;
+    int const g = b->nbar_gen[id];
+    if (++b->nbar_count[id] == count) { b->nbar_count[id] = 0; b->nbar_gen[id] = g + 1; }
+    else while (b->nbar_gen[id] == g) yield();
 }
 
 } // namespace emu

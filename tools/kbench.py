@@ -17,7 +17,7 @@ enc = lame_b200.BatchEncoder(S, 44100, 2, 128, -1, -1, frames_per_launch=F)
 enc.stage(pcm, F)
 for _ in range(3):
     enc.rerun_device(F)
-k = np.zeros(4)
+k = np.zeros(5)
 for _ in range(reps):
     enc.rerun_device(F)
     k += np.array(enc.kernel_ms())
@@ -34,5 +34,5 @@ for i in range(3):
         h.update(out[s, :nb[s]].tobytes())
 e2e = (time.perf_counter() - t0) / 3
 enc.close()
-print("%-28s S=%d F=%d  A %.3f B %.3f C %.3f D %.3f ms  total %.3f  -> %.0f frames/s  e2e %.1f ms  sha %s" % (
-    os.path.basename(lib), S, F, k[0], k[1], k[2], k[3], k.sum(), S * F / (k.sum() * 1e-3), e2e * 1e3, h.hexdigest()[:12]), flush=True)
+print("%-28s S=%d F=%d  A %.3f B %.3f C %.3f D %.3f E %.3f ms  total %.3f  -> %.0f frames/s  e2e %.1f ms  sha %s" % (
+    os.path.basename(lib), S, F, k[0], k[1], k[2], k[3], k[4], k.sum(), S * F / (k.sum() * 1e-3), e2e * 1e3, h.hexdigest()[:12]), flush=True)
