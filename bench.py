@@ -6,10 +6,10 @@ white noise (uniform int16 in [-12000, 12000], L/R independent), CBR 128 kbps jo
 512 streams x 8 frames per GPU.  With N GPUs every rank encodes its own 512 streams (weak scaling, streams are
 independent: no data-path collective).
 
-  value     frames/s with the PCM already resident in HBM: the four kernels (analysis, scan, mdct, quantise) timed
+  value     frames/s with the PCM already resident in HBM: the five kernels (analysis, scan, mdct, quantise, pack) timed
             with CUDA events on the launching stream, L2 flushed between steps, max over ranks.
   e2e       frames/s through the public C ABI (lamegpu_batch_encode_packed) with HOST buffers: host->device copy of
-            the PCM, kernels, device->host copy of the quantised granules, multi-threaded bit packing to MP3 bytes.
+            the PCM, kernels, device->host copy of the packed frame bytes, header splice to MP3 bytes on the host.
   roofline  dominant kernel (quantise): algorithmic bytes (16 060 B/frame) / its CUDA-event time
             against the measured HBM peak of MEASURED_PEAKS.json.
   cpu_baseline  the unmodified reference libmp3lame (oracle/_ref) single-thread on the host, bounded sample.
@@ -223,7 +223,7 @@ def main():
     for _ in range(args.warmup):
         enc.rerun_device(F)
     log('warm')
-    kms = np.zeros(4)
+    kms = np.zeros(5)
     sampler = ClockSampler(local)
     launches0 = enc.kernel_launches()
     barrier()
@@ -264,7 +264,7 @@ def main():
     e2e_frames_all, e2e_ms_max = reduce_over_ranks(float(e2e_frames), e2e_ms)
     lib = lame_b200.load_library()
     h2d = S * 2 * (F * 1152 + 1328) * 2 + S * 4
-    d2h = S * 2 * F * 2 * int(lib.lamegpu_sizeof_granule_out()) + S * F * 32
+    d2h = int(lib.lamegpu_batch_d2h_bytes(enc._h))
     enc.close()
 
     if rank == 0:
@@ -277,17 +277,18 @@ def main():
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": S, "frames_per_stream_per_step": F,
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-step footprint ~190 MB",
+                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-step footprint ~190 MB > 126 MB L2",
                        "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % world},
             "e2e": {"value": e2e_frames_all / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes_last_step": total_bytes,
-                    "note": "lamegpu_batch_encode_packed: pinned staging + H2D + 4 kernels + D2H + host bit packing (threads=%d)" % (os.cpu_count() or 1)},
+                    "note": "lamegpu_batch_encode_packed: pinned staging + H2D + 5 kernels + D2H of packed bytes + host header splice (threads=%d)" % (os.cpu_count() or 1)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "lg_kernel_quant", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms,
                          "note": "latency/issue-bound integer + table-lookup kernel (SURVEY 8d): HBM fraction is reported, not the binding limit"},
-            "kernels_ms_per_step": {"analysis": kms[0] / args.steps, "scan": kms[1] / args.steps, "mdct": kms[2] / args.steps, "quant": q_ms},
+            "kernels_ms_per_step": {"analysis": kms[0] / args.steps, "scan": kms[1] / args.steps, "mdct": kms[2] / args.steps, "quant": q_ms,
+                                    "pack": kms[4] / args.steps},
             "roofline_mdct_psy": {"bound": "hbm", "kernels": "analysis+scan+mdct", "achieved": ALG_BYTES_ANALYSIS * S * F / (a_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": ALG_BYTES_ANALYSIS * S * F / (a_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,

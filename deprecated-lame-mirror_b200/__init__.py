@@ -74,6 +74,7 @@ def load_library(path=None):
         "lamegpu_batch_set_threads": (c_int, [c_void_p, c_int]),
         "lamegpu_batch_debug_copy": (c_long, [c_void_p, c_int, c_void_p, ctypes.c_size_t]),
         "lamegpu_sizeof_granule_out": (ctypes.c_size_t, []),
+        "lamegpu_batch_d2h_bytes": (c_long, [c_void_p]),
         "lamegpu_sizeof_analysis": (ctypes.c_size_t, []),
     }
     for name, (res, args) in sig.items():
@@ -93,7 +94,7 @@ EXPORTED_SYMBOLS = [
     "lame_close", "get_lame_short_version", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
     "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
-    "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis",
+    "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_batch_d2h_bytes",
 ]
 
 

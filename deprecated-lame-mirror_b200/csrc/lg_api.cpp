@@ -400,6 +400,12 @@ int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5])
 long lamegpu_batch_kernel_launches(const lamegpu_batch *b) { return b ? lg_engine_launch_count(b->eng) : 0; }
 long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap) { return b ? lg_engine_debug_copy(b->eng, what, dst, cap) : -1; }
 size_t lamegpu_sizeof_granule_out(void) { return sizeof(LgGranuleOut); }
+/* bytes one launch copies device -> host: frame records, payload bytes, headers */
+long lamegpu_batch_d2h_bytes(const lamegpu_batch *b)
+{
+    if (!b) return 0;
+    return (long) ((size_t) b->S * b->F * sizeof(LgFrameOut) + (size_t) b->S * lg_engine_pay_stride(b->eng) + (size_t) b->S * b->F * LG_HDR_STRIDE);
+}
 size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }
 
 /* ------------------------------------------------------------------ libmp3lame-compatible face */

@@ -16,6 +16,5 @@ struct LgBitWriter {
     void reset();
 };
 
-void lg_pack_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const LgGranuleOut *g /* [2][2] gr-major */);
 void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const unsigned char *hdr, const unsigned char *pay);
 void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_padding);

@@ -97,6 +97,7 @@ long lamegpu_batch_kernel_launches(const lamegpu_batch *b);
 int  lamegpu_batch_set_threads(lamegpu_batch *b, int nthreads);
 long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap);   /* tests: intermediate device buffers */
 size_t lamegpu_sizeof_granule_out(void);
+long lamegpu_batch_d2h_bytes(const lamegpu_batch *b);              /* device->host bytes per launch */
 size_t lamegpu_sizeof_analysis(void);
 
 #ifdef __cplusplus

@@ -39,7 +39,7 @@ def test_library_contains_sm100a_kernels(lib):
     out = subprocess.run(["cuobjdump", "-lelf", lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", lib.LIB_PATH], capture_output=True, text=True).stdout
-    for k in ("lg_kernel_analysis", "lg_kernel_scan", "lg_kernel_mdct", "lg_kernel_quant"):
+    for k in ("lg_kernel_analysis", "lg_kernel_scan", "lg_kernel_mdct", "lg_kernel_quant", "lg_kernel_pack"):
         assert k in sass
     assert "REDUX" in sass and "SHFL" in sass          # warp reductions of the bit counters / noise maxima
 
