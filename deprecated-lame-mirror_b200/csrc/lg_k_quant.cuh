@@ -23,11 +23,13 @@
 struct LgQInfo {                 /* the scalar part of the reference's gr_info (l3side.h:47), warp-uniform */
     float xrpow_max;
     int part2_3_length, big_values, count1, global_gain, scalefac_compress;
-    int table_select[3], subblock_gain[4];
+    int table_select[3];
+    int sbg;                     /* subblock_gain[0..2] in 4-bit fields (field 3 stays 0: long-block bands use "window 3") */
     int region0_count, region1_count, preflag, scalefac_scale, count1table_select, part2_length, count1bits;
 };
 struct LgQConst {                /* per gr.ch constants set by init_outer_loop / calc_xmin */
     int block_type, sfb_lmax, sfb_smin, psy_lmax, sfbmax, psymax, sfbdivide, max_nonzero_coeff;
+    int jn;                      /* line loops run j < jn: pairs at or above ((max_nonzero_coeff + 2) & ~1) / 2 stay zero */
 };
 struct LgNoiseRes { float max_noise; int over_count, over_SSD, bits; };
 struct LgPrev { int valid, global_gain, sfb_count1; };   /* scalar part of calc_noise_data (quantize_pvt.h:75) */
@@ -40,6 +42,7 @@ struct __attribute__((aligned(16))) LgQWarp {
     int   sfw[40], sfbst[40];
     int   width[40], window[40], lstart[41];
     int   act[80];
+    float tail_max[40];              /* per band: largest xrpow among its lines above max_nonzero_coeff (see lg_scale_bands) */
     int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
     uint8_t line_sfb[576];
@@ -112,7 +115,7 @@ __device__ __forceinline__ const uint8_t *lg_hlen(const LgDevCfg *__restrict__ c
 __device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const LgQWarp *w, const int *sf, int sfb)
 {
     return gi.global_gain - ((sf[sfb] + (gi.preflag ? (int) LG_PRETAB[sfb < 22 ? sfb : 21] : 0)) << (gi.scalefac_scale + 1))
-         - gi.subblock_gain[w->window[sfb]] * 8;
+         - ((gi.sbg >> (4 * w->window[sfb])) & 15) * 8;
 }
 
 /* ---------------------------------------------------------------- Huffman table choice for a region whose largest
@@ -175,28 +178,32 @@ __device__ __noinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, cons
 #define LG_UNROLL(n) LG_PRAGMA_(unroll n)
 
 /* ---------------------------------------------------------------- takehiro.c:767 count_bits = quantize_xrpow (:281) +
- * noquant_count_bits (:654); pv == nullptr is the reference's prev_noise == 0.  The loops over the lane's nine
- * line pairs are kept rolled on purpose: the whole search loop has to stay inside the 32 KB instruction cache. */
-__device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev *pv, int lane)
+ * noquant_count_bits (:654).  pv.valid == 0 is the reference's prev_noise == 0 (step-size search).
+ *
+ * Inlined at its single call site (lg_outer_loop is a state machine around one count_bits and one calc_noise), so the
+ * granule's scalar state lives in registers.  The loops over the lane's line pairs are rolled on purpose (the search
+ * loop has to stay inside the instruction cache) and stop at qc.jn: lines above max_nonzero_coeff are zero when the
+ * granule starts and quantize_xrpow only ever keeps or clears them (takehiro.c:300-330), so they are never touched. */
+__device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev &pv, int lane)
 {
     float const istep = __ldg(&c->ipow20[gi.global_gain]);
     if (gi.xrpow_max > (LG_IXMAX) / istep) return LG_LARGE_BITS;
     int const nsfb = (qc.block_type == LG_SHORT) ? 39 : 22;
     int const mnz = qc.max_nonzero_coeff;
-    int const pv_valid = pv ? pv->valid : 0;
-    int const prev_data_use = pv_valid && (gi.global_gain == pv->global_gain);
-    int const pv_count1 = pv ? pv->sfb_count1 : 0;
+    int const prev_data_use = pv.valid && (gi.global_gain == pv.global_gain);
+    int const pv_count1 = pv.sfb_count1;
     /* per scalefactor band: 0 keep old values, 1 quantise, 2 quantise with the 0/1 shortcut */
     int T = 64;
-    for (int r = 0; r < 2; r++) {
+    for (int r = 0; 32 * r < nsfb; r++) {
         int const sfb = lane + 32 * r;
         int term = 0;
         if (sfb < nsfb) {
             int step = -1;
             if (prev_data_use || qc.block_type == LG_NORM) step = lg_band_step(gi, w, w->sfw, sfb);
-            int const skip = prev_data_use && (w->pn_step[sfb] == step);
+            int const pstep = w->pn_step[sfb];
+            int const skip = prev_data_use && (pstep == step);
             int const cross = (w->lstart[sfb] + w->width[sfb]) > mnz;
-            int const is01 = pv_valid && pv_count1 > 0 && sfb >= pv_count1 && w->pn_step[sfb] > 0 && step >= w->pn_step[sfb];
+            int const is01 = pv.valid && pv_count1 > 0 && sfb >= pv_count1 && pstep > 0 && step >= pstep;
             w->act[sfb] = skip ? 0 : (is01 ? 2 : 1);
             term = !skip && cross;
         }
@@ -206,11 +213,10 @@ __device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWar
     __syncwarp();
     float const compareval0 = (1.0f - 0.4054f) / istep;
     const float *adj = c->adj43asm;
-    int ilim = ((mnz + 2) >> 1) << 1;
-    if (ilim > 576) ilim = 576;
+    int const ilim = (mnz + 2) & ~1;               /* <= 576 because max_nonzero_coeff <= 575 */
     int hi_nz = -1, hi_big = -1;
     LG_UNROLL(LG_UNROLL_Q)
-    for (int j = 0; j < 9; j++) {
+    for (int j = 0; j < qc.jn; j++) {
         int const P = lane + 32 * j, i = 2 * P;
         int const sfb = w->line_sfb[i];
         int a0, a1;                       /* action for line i and i+1: 0 keep, 1 quantise, 2 shortcut, 3 zero */
@@ -249,67 +255,79 @@ __device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWar
         }
     }
     /* ---- noquant_count_bits: count1 / big_values split */
-    if (pv) pv->sfb_count1 = 0;
-    hi_nz = lg_wmax_i(hi_nz);                     /* the reductions also order the ix writes above (full-warp barrier) */
+    pv.sfb_count1 = 0;
+    hi_nz = lg_wmax_i(hi_nz);
     hi_big = lg_wmax_i(hi_big);
-    __syncwarp();
+    __syncwarp();                                  /* the ix written above are read by other lanes below */
     int const c1p = hi_nz + 1;
     gi.count1 = 2 * c1p;
     int const nquads = (c1p - 1 - hi_big) >> 1;
     int const bigv = gi.count1 - 4 * nquads;
-    int bits, a1, a2;
-    lg_count1_bits(c, w->ixw, bigv, gi.count1, lane, &a1, &a2);
-    bits = a1;
-    gi.count1table_select = 0;
-    if (a1 > a2) { bits = a2; gi.count1table_select = 1; }
-    gi.count1bits = bits;
     gi.big_values = bigv;
-    if (bigv == 0) return bits;
-    /* region split: [0,a1) [a1,a2) [a2,bigv) */
-    if (qc.block_type == LG_SHORT) {
-        a1 = 3 * c->sfb_s[3];
-        if (a1 > bigv) a1 = bigv;
-        a2 = bigv;
+    /* region split [0,a1) [a1,a2) [a2,bigv); the count1 quadruples and the regions' largest magnitudes in one go */
+    int a1 = 0, a2 = 0, has2 = 0;
+    if (bigv > 0) {
+        if (qc.block_type == LG_SHORT) {
+            a1 = 3 * c->sfb_s[3];
+            if (a1 > bigv) a1 = bigv;
+            a2 = bigv;
+        }
+        else if (qc.block_type == LG_NORM) {
+            a1 = gi.region0_count = c->bv_scf[bigv - 2];
+            a2 = gi.region1_count = c->bv_scf[bigv - 1];
+            a2 = c->sfb_l[a1 + a2 + 2];
+            a1 = c->sfb_l[a1 + 1];
+            has2 = a2 < bigv;
+        }
+        else {
+            gi.region0_count = 7;
+            gi.region1_count = LG_SBMAX_L - 1 - 7 - 1;
+            a1 = c->sfb_l[7 + 1];
+            a2 = bigv;
+            if (a1 > a2) a1 = a2;
+        }
+        a1 = a1 < bigv ? a1 : bigv;
+        a2 = a2 < bigv ? a2 : bigv;
     }
-    else if (qc.block_type == LG_NORM) {
-        a1 = gi.region0_count = c->bv_scf[bigv - 2];
-        a2 = gi.region1_count = c->bv_scf[bigv - 1];
-        a2 = c->sfb_l[a1 + a2 + 2];
-        a1 = c->sfb_l[a1 + 1];
+    unsigned s1 = 0, s2 = 0;
+    {
+        const uint8_t *t32l = lg_hlen(c, 32), *t33l = lg_hlen(c, 33);
+        const int16_t *ix = w->ixw;
+        for (int k = lane; k < nquads; k += 32) {
+            int const i = gi.count1 - 4 * k;
+            int const p = ((ix[i - 4] * 2 + ix[i - 3]) * 2 + ix[i - 2]) * 2 + ix[i - 1];
+            s1 += __ldg(&t32l[p]); s2 += __ldg(&t33l[p]);
+        }
     }
-    else {
-        gi.region0_count = 7;
-        gi.region1_count = LG_SBMAX_L - 1 - 7 - 1;
-        a1 = c->sfb_l[7 + 1];
-        a2 = bigv;
-        if (a1 > a2) a1 = a2;
-    }
-    int const has2 = (qc.block_type == LG_NORM) && a2 < bigv;
-    a1 = a1 < bigv ? a1 : bigv;
-    a2 = a2 < bigv ? a2 : bigv;
-    /* pass 1: largest magnitude per region */
     int m0 = 0, m1 = 0, m2 = 0;
     LG_UNROLL(LG_UNROLL_C)
-    for (int j = 0; j < 9; j++) {
+    for (int j = 0; j < qc.jn; j++) {
         int const i = 2 * (lane + 32 * j);
-        unsigned const u = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
-        int const v = max((int) (u & 0xffffu), (int) (u >> 16));
-        if (i < a1) m0 = max(m0, v);
-        else if (i < a2) m1 = max(m1, v);
-        else if (i < bigv) m2 = max(m2, v);
+        if (i < bigv) {
+            unsigned const u = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
+            int const v = max((int) (u & 0xffffu), (int) (u >> 16));
+            if (i < a1) m0 = max(m0, v);
+            else if (i < a2) m1 = max(m1, v);
+            else m2 = max(m2, v);
+        }
     }
+    unsigned const cb = lg_wsum_u(s1 | (s2 << 16));          /* two fields, each total < 2^13 */
+    int bits = (int) (cb & 0xffffu);
+    gi.count1table_select = 0;
+    if (bits > (int) (cb >> 16)) { bits = (int) (cb >> 16); gi.count1table_select = 1; }
+    gi.count1bits = bits;
+    if (bigv == 0) return bits;
     m0 = lg_wmax_i(m0); m1 = lg_wmax_i(m1); m2 = lg_wmax_i(m2);
-    if (max(m0, max(m1, m2)) > LG_IXMAX) {
-        /* cannot happen behind the xrpow_max guard above; the reference's answer is "too many bits" */
-        return LG_LARGE_BITS;
-    }
-    LgRegion R0, R1, R2;
-    lg_region_class(c, m0, R0); lg_region_class(c, m1, R1); lg_region_class(c, m2, R2);
-    /* pass 2: bit sums under the candidate tables, three 10-bit fields per region (a lane adds at most 9 x 31) */
+    if (max(m0, max(m1, m2)) > LG_IXMAX) return LG_LARGE_BITS;     /* cannot happen behind the xrpow_max guard above */
+    /* lanes 0..2 classify one region each (choose_table's dispatch on the largest magnitude) */
+    LgRegion R;
+    lg_region_class(c, lane == 0 ? m0 : (lane == 1 ? m1 : m2), R);
+    int const b0 = __shfl_sync(LG_FULL, R.base, 0), b1 = __shfl_sync(LG_FULL, R.base, 1), b2 = __shfl_sync(LG_FULL, R.base, 2);
+    /* bit sums under the candidate tables, three 10-bit fields per region (a lane adds at most 9 x 31) */
     unsigned acc0 = 0, acc1 = 0, acc2 = 0, n15 = 0;
     const uint32_t *pk = c->huff_pk;
     LG_UNROLL(LG_UNROLL_C)
-    for (int j = 0; j < 9; j++) {
+    for (int j = 0; j < qc.jn; j++) {
         int const i = 2 * (lane + 32 * j);
         if (i < bigv) {
             unsigned const u = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
@@ -317,30 +335,34 @@ __device__ __noinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWar
             unsigned const over = (x >= 15u) + (y >= 15u);
             x = x < 15u ? x : 15u; y = y < 15u ? y : 15u;
             int const reg = (i >= a1) + (i >= a2);
-            int const base = reg == 0 ? R0.base : (reg == 1 ? R1.base : R2.base);
+            int const base = reg == 0 ? b0 : (reg == 1 ? b1 : b2);
             unsigned const e = __ldg(&pk[base + (int) ((x << 4) + y)]);
             if (reg == 0) acc0 += e; else if (reg == 1) acc1 += e; else acc2 += e;
             n15 += over << (10 * reg);
         }
     }
     n15 = lg_wsum_u(n15);
-    /* the reference adds region 2 first, then 0, then 1 (takehiro.c:719-739); integer sums, so order-free */
-    if (has2) {
-        unsigned const s01 = lg_wsum_u((acc2 & 0x3ffu) | (((acc2 >> 10) & 0x3ffu) << 16)), s2 = lg_wsum_u(acc2 >> 20);
-        gi.table_select[2] = m2 ? lg_region_pick(R2, s01 & 0xffffu, s01 >> 16, s2, n15 >> 20, &bits) : 0;
+    unsigned const r0 = lg_wsum_u((acc0 & 0x3ffu) | (((acc0 >> 10) & 0x3ffu) << 16)), r1 = lg_wsum_u(acc0 >> 20);
+    unsigned const r2 = lg_wsum_u((acc1 & 0x3ffu) | (((acc1 >> 10) & 0x3ffu) << 16)), r3 = lg_wsum_u(acc1 >> 20);
+    unsigned const r4 = lg_wsum_u((acc2 & 0x3ffu) | (((acc2 >> 10) & 0x3ffu) << 16)), r5 = lg_wsum_u(acc2 >> 20);
+    /* lane r picks region r's table (count_bit_* epilogues); a region the reference does not look at contributes nothing */
+    {
+        unsigned const s01 = lane == 0 ? r0 : (lane == 1 ? r2 : r4), sx = lane == 0 ? r1 : (lane == 1 ? r3 : r5);
+        unsigned const nn = (n15 >> (10 * (lane < 3 ? lane : 0))) & 0x3ffu;
+        int const mreg = lane == 0 ? m0 : (lane == 1 ? m1 : m2);
+        int const used = lane == 0 ? (0 < a1) : (lane == 1 ? (a1 < a2) : (lane == 2 ? has2 : 0));
+        int rb = 0, rt = 0;
+        if (used && mreg) rt = lg_region_pick(R, s01 & 0xffffu, s01 >> 16, sx, nn, &rb);
+        int const t0 = __shfl_sync(LG_FULL, rt, 0), t1 = __shfl_sync(LG_FULL, rt, 1), t2 = __shfl_sync(LG_FULL, rt, 2);
+        bits += __shfl_sync(LG_FULL, rb, 0) + __shfl_sync(LG_FULL, rb, 1) + __shfl_sync(LG_FULL, rb, 2);
+        if (0 < a1) gi.table_select[0] = t0;
+        if (a1 < a2) gi.table_select[1] = t1;
+        if (has2) gi.table_select[2] = t2;
     }
-    if (0 < a1) {
-        unsigned const s01 = lg_wsum_u((acc0 & 0x3ffu) | (((acc0 >> 10) & 0x3ffu) << 16)), s2 = lg_wsum_u(acc0 >> 20);
-        gi.table_select[0] = m0 ? lg_region_pick(R0, s01 & 0xffffu, s01 >> 16, s2, n15 & 0x3ffu, &bits) : 0;
-    }
-    if (a1 < a2) {
-        unsigned const s01 = lg_wsum_u((acc1 & 0x3ffu) | (((acc1 >> 10) & 0x3ffu) << 16)), s2 = lg_wsum_u(acc1 >> 20);
-        gi.table_select[1] = m1 ? lg_region_pick(R1, s01 & 0xffffu, s01 >> 16, s2, (n15 >> 10) & 0x3ffu, &bits) : 0;
-    }
-    if (pv && qc.block_type == LG_NORM) {
+    if (qc.block_type == LG_NORM) {
         /* first sfb whose start is >= big_values (sfb_l is increasing and ends at 576) */
         int const below = (lane < 23) && (c->sfb_l[lane] < bigv);
-        pv->sfb_count1 = __popc(__ballot_sync(LG_FULL, below));
+        pv.sfb_count1 = __popc(__ballot_sync(LG_FULL, below));
     }
     return bits;
 }
@@ -409,8 +431,8 @@ __device__ __noinline__ int lg_choose_table_serial(const LgDevCfg *__restrict__ 
  * The squared errors of all lines of the bands that need recomputing are formed line-parallel (every lane its nine
  * pairs) into sq[]; then one lane per band adds them up serially, in the reference's order (calc_noise_core_c :750),
  * so every float sum is the reference's.  Bands whose step did not change reuse the cached noise (prev_noise). */
-__device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
-                                              LgNoiseRes *res, LgPrev *pv, int lane)
+__device__ __forceinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &gi, const LgQConst &qc,
+                                                 LgNoiseRes *res, LgPrev &pv, int lane)
 {
     float *bstep = reinterpret_cast<float *>(w->act);      /* per band: step size, or < 0 = cached */
     int *breg = w->act + 40;                               /* per band: 0 beyond count1, 1 count1 region, 2 big values */
@@ -421,7 +443,7 @@ __device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWa
             float st = -1.f;
             if (sfb < qc.psymax) {
                 int const s = lg_band_step(gi, w, w->sfw, sfb);
-                if (!(pv->valid && w->pn_step[sfb] == s)) {
+                if (!(pv.valid && w->pn_step[sfb] == s)) {
                     st = __ldg(&c->pow20[s + LG_QMAX2]);
                     int const j = w->lstart[sfb];
                     breg[sfb] = (j > gi.count1) ? 0 : ((j > gi.big_values) ? 1 : 2);
@@ -434,8 +456,9 @@ __device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWa
     need = __any_sync(LG_FULL, need);
     __syncwarp();
     if (need) {
+        /* lines above max_nonzero_coeff never enter a band's sum (see the truncation of l below) */
         LG_UNROLL(LG_UNROLL_C)
-        for (int j = 0; j < 9; j++) {
+        for (int j = 0; j < qc.jn; j++) {
             int const i = 2 * (lane + 32 * j);
             int const sfb = w->line_sfb[i];
             float const step = bstep[sfb];
@@ -496,33 +519,36 @@ __device__ __noinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, LgQWa
             max_noise = max_noise > noise ? max_noise : noise;
         }
     }
-    pv->global_gain = gi.global_gain;
+    pv.global_gain = gi.global_gain;
     res->over_count = (int) lg_wsum_u((unsigned) over);
     res->over_SSD = (int) lg_wsum_u((unsigned) ssd);
     res->max_noise = lg_wmax_f(max_noise);
     __syncwarp();
 }
 
-/* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount */
-__device__ __noinline__ int lg_scale_bitcount(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int *sf, int lane)
+/* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount.
+ * By value (three call sites, and the caller's scalars stay in registers): returns part2_length (LG_LARGE_BITS = does
+ * not fit) | scalefac_compress << 20 | preflag << 24. */
+__device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, int sfbmax, int sfbdivide, int preflag, int compress, int lane)
 {
+    int *sf = w->sfw;
     const int *tab;
-    if (qc.block_type == LG_SHORT) tab = LG_SCALE_SHORT;
+    if (block_type == LG_SHORT) tab = LG_SCALE_SHORT;
     else {
         tab = LG_SCALE_LONG;
-        if (!gi.preflag) {
+        if (!preflag) {
             int bad = 0;
             if (lane >= 11 && lane < LG_SBPSY_L) bad = sf[lane] < (int) LG_PRETAB[lane];
             if (!__any_sync(LG_FULL, bad)) {
-                gi.preflag = 1;
+                preflag = 1;
                 if (lane >= 11 && lane < LG_SBPSY_L) sf[lane] -= LG_PRETAB[lane];
                 __syncwarp();
             }
         }
     }
     int m1 = 0, m2 = 0;
-    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) {
-        if (sfb < qc.sfbdivide) m1 = max(m1, sf[sfb]); else m2 = max(m2, sf[sfb]);
+    for (int sfb = lane; sfb < sfbmax; sfb += 32) {
+        if (sfb < sfbdivide) m1 = max(m1, sf[sfb]); else m2 = max(m2, sf[sfb]);
     }
     m1 = lg_wmax_i(m1);
     m2 = lg_wmax_i(m2);
@@ -530,26 +556,42 @@ __device__ __noinline__ int lg_scale_bitcount(LgQWarp *w, LgQInfo &gi, const LgQ
     int key = 0x7fffffff;
     if (lane < 16 && m1 < LG_SLEN1_N[lane] && m2 < LG_SLEN2_N[lane]) key = tab[lane] * 16 + lane;
     key = lg_wmin_i(key);
-    gi.part2_length = LG_LARGE_BITS;
-    if (key != 0x7fffffff) { gi.part2_length = key >> 4; gi.scalefac_compress = key & 15; }
-    return gi.part2_length == LG_LARGE_BITS;
+    int part2_length = LG_LARGE_BITS;
+    if (key != 0x7fffffff) { part2_length = key >> 4; compress = key & 15; }
+    return (unsigned) part2_length | ((unsigned) compress << 20) | ((unsigned) preflag << 24);
 }
+#define LG_APPLY_SCALE_BITCOUNT(gi, r) do { (gi).part2_length = (int) ((r) & 0xfffffu); (gi).scalefac_compress = (int) (((r) >> 20) & 15u); (gi).preflag = (int) (((r) >> 24) & 1u); } while (0)
 
 /* quantize.c:540 loop_break */
-__device__ __forceinline__ int lg_loop_break(const LgQWarp *w, const LgQInfo &gi, const LgQConst &qc, const int *sf, int lane)
+__device__ __forceinline__ int lg_loop_break(const LgQWarp *w, int sbg, int sfbmax, int lane)
 {
     int unamp = 0;
-    for (int sfb = lane; sfb < qc.sfbmax; sfb += 32)
-        if (sf[sfb] + gi.subblock_gain[w->window[sfb]] == 0) unamp = 1;
+    for (int sfb = lane; sfb < sfbmax; sfb += 32)
+        if (w->sfw[sfb] + ((sbg >> (4 * w->window[sfb])) & 15) == 0) unamp = 1;
     return __any_sync(LG_FULL, unamp) ? 0 : 1;
 }
 
-/* multiply the lines of the flagged bands (act[sfb] != 0 -> factor in fac[]) and track xrpow_max */
-__device__ __noinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const float *fac /* shared, per sfb, 0 = untouched */, int lane)
+/* Multiply the lines of the flagged bands (factor per band in act[] as float, 0 = untouched); returns the new xrpow_max.
+ * Only lines up to max_nonzero_coeff are touched: the quantiser never reads xrpow above it.  The reference scales those
+ * lines too and they take part in its running maximum, so their per-band maximum is carried in tail_max[] and scaled here
+ * (max and a rounded multiply by a positive factor commute): xrpow_max stays exactly the reference's. */
+__device__ __noinline__ float lg_scale_bands(LgQWarp *w, float xrpow_max, int jn, int lane)
 {
-    float mx = gi.xrpow_max;
+    const float *fac = reinterpret_cast<const float *>(w->act);
+    float mx = xrpow_max;
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        if (sfb < 40) {
+            float const f = fac[sfb];
+            if (f != 0.f) {
+                float const tm = w->tail_max[sfb] * f;
+                w->tail_max[sfb] = tm;
+                if (tm > mx) mx = tm;
+            }
+        }
+    }
     LG_UNROLL(LG_UNROLL_C)
-    for (int j = 0; j < 9; j++) {
+    for (int j = 0; j < jn; j++) {
         int const i = 2 * (lane + 32 * j);
         float const f = fac[w->line_sfb[i]];
         if (f != 0.f) {
@@ -560,12 +602,13 @@ __device__ __noinline__ void lg_scale_bands(LgQWarp *w, LgQInfo &gi, const float
             if (v.y > mx) mx = v.y;
         }
     }
-    gi.xrpow_max = lg_wmax_f(mx);
+    mx = lg_wmax_f(mx);
     __syncwarp();
+    return mx;
 }
 
 /* quantize.c:720 amp_scalefac_bands (noise_shaping_amp 0 and 1; 2/3 belong to quality <= 1) */
-__device__ __noinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     float const ifqstep34 = (gi.scalefac_scale == 0) ? (float) 1.29683955465100964055 : (float) 1.68179283050742922612;
     float trigger = 0;
@@ -588,11 +631,11 @@ __device__ __noinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ 
         }
     }
     __syncwarp();
-    lg_scale_bands(w, gi, reinterpret_cast<const float *>(w->act), lane);
+    gi.xrpow_max = lg_scale_bands(w, gi.xrpow_max, qc.jn, lane);
 }
 
 /* quantize.c:808 inc_scalefac_scale */
-__device__ __noinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __forceinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     float const ifqstep34 = (float) 1.29683955465100964055;
     for (int r = 0; r < 2; r++) {
@@ -609,13 +652,13 @@ __device__ __noinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, cons
         }
     }
     __syncwarp();
-    lg_scale_bands(w, gi, reinterpret_cast<const float *>(w->act), lane);
+    gi.xrpow_max = lg_scale_bands(w, gi.xrpow_max, qc.jn, lane);
     gi.preflag = 0;
     gi.scalefac_scale = 1;
 }
 
 /* quantize.c:847 inc_subblock_gain (short blocks only; sfb_lmax == 0 because mixed blocks are never used) */
-__device__ __noinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __forceinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     int *scalefac = w->sfw;
     float *fac = reinterpret_cast<float *>(w->act);
@@ -627,8 +670,8 @@ __device__ __noinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c,
         s1 = lg_wmax_i(s1);
         s2 = lg_wmax_i(s2);
         if (s1 < 16 && s2 < 8) continue;
-        if (gi.subblock_gain[window] >= 7) return 1;
-        gi.subblock_gain[window]++;
+        if (((gi.sbg >> (4 * window)) & 15) >= 7) return 1;
+        gi.sbg += 1 << (4 * window);
         for (int r = 0; r < 2; r++) { int const k = lane + 32 * r; if (k < 40) fac[k] = 0.f; }
         __syncwarp();
         {
@@ -646,26 +689,29 @@ __device__ __noinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__ c,
             if (lane == 0) fac[qc.sfbmax + window] = __ldg(&c->ipow20[202]);
         }
         __syncwarp();
-        lg_scale_bands(w, gi, fac, lane);
+        gi.xrpow_max = lg_scale_bands(w, gi.xrpow_max, qc.jn, lane);
     }
     return 0;
 }
 
-/* quantize.c:940 balance_noise */
+/* quantize.c:940 balance_noise (the two scale_bitcount calls share one site) */
 __device__ __forceinline__ int lg_balance_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     lg_amp_scalefac_bands(c, w, gi, qc, lane);
-    int status = lg_loop_break(w, gi, qc, w->sfw, lane);
-    if (status) return 0;
-    status = lg_scale_bitcount(w, gi, qc, w->sfw, lane);
-    if (!status) return 1;
-    if (c->noise_shaping > 1) {
-        if (!gi.scalefac_scale) { lg_inc_scalefac_scale(w, gi, qc, lane); status = 0; }
-        else if (qc.block_type == LG_SHORT && c->subblock_gain > 0)
-            status = lg_inc_subblock_gain(c, w, gi, qc, lane) || lg_loop_break(w, gi, qc, w->sfw, lane);
+    if (lg_loop_break(w, gi.sbg, qc.sfbmax, lane)) return 0;
+    for (int pass = 0;; pass++) {
+        unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, lane);
+        LG_APPLY_SCALE_BITCOUNT(gi, r);
+        int status = gi.part2_length == LG_LARGE_BITS;
+        if (!status) return 1;
+        if (pass == 1) return 0;
+        if (c->noise_shaping > 1) {
+            if (!gi.scalefac_scale) { lg_inc_scalefac_scale(w, gi, qc, lane); status = 0; }
+            else if (qc.block_type == LG_SHORT && c->subblock_gain > 0)
+                status = lg_inc_subblock_gain(c, w, gi, qc, lane) || lg_loop_break(w, gi.sbg, qc.sfbmax, lane);
+        }
+        if (status) return 0;
     }
-    if (!status) status = lg_scale_bitcount(w, gi, qc, w->sfw, lane);
-    return !status;
 }
 
 /* quantize.c:585 quant_compare, mode 9 (the only one the bitrate presets select) */
@@ -681,16 +727,15 @@ __device__ __forceinline__ int lg_quant_compare(const LgNoiseRes &best, const Lg
     return better;
 }
 
-/* copy work -> best or best -> work (the reference's gr_info struct assignment) */
-__device__ __forceinline__ void lg_copy_ix_sf(int16_t *dix, const int16_t *six, int *dsf, const int *ssf, int lane)
+/* copy work -> best or best -> work (the reference's gr_info struct assignment); lines above max_nonzero_coeff are zero in both */
+__device__ __noinline__ void lg_copy_ix_sf(LgQWarp *w, int to_best, int jn, int lane)
 {
-    for (int i = lane; i < 288; i += 32) reinterpret_cast<unsigned *>(dix)[i] = reinterpret_cast<const unsigned *>(six)[i];
+    unsigned *dix = reinterpret_cast<unsigned *>(to_best ? w->ixb : w->ixw);
+    const unsigned *six = reinterpret_cast<const unsigned *>(to_best ? w->ixw : w->ixb);
+    int *dsf = to_best ? w->sfbst : w->sfw;
+    const int *ssf = to_best ? w->sfw : w->sfbst;
+    for (int i = lane; i < 32 * jn; i += 32) dix[i] = six[i];
     for (int i = lane; i < 40; i += 32) dsf[i] = ssf[i];
-    __syncwarp();
-}
-__device__ __forceinline__ void lg_copy_f576(float *d, const float *s, int lane)
-{
-    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(d)[i] = reinterpret_cast<const float4 *>(s)[i];
     __syncwarp();
 }
 
@@ -705,116 +750,103 @@ __device__ __forceinline__ void lg_runaway()
 #endif
 }
 
-/* quantize.c:367 bin_search_StepSize */
-__device__ __forceinline__ int lg_bin_search(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int desired_rate,
-                                             int *old_value, int *current_step, int lane)
-{
-    int nBits, CurrentStep = *current_step, flag_GoneOver = 0;
-    int const start = *old_value;
-    int Direction = 0;
-    gi.global_gain = start;
-    desired_rate -= gi.part2_length;
-    for (int guard = 0;; guard++) {
-        int step;
-        if (guard > 600) lg_runaway();
-        nBits = lg_count_bits(c, w, gi, qc, nullptr, lane);
-        if (CurrentStep == 1 || nBits == desired_rate) break;
-        if (nBits > desired_rate) {
-            if (Direction == 2) flag_GoneOver = 1;
-            if (flag_GoneOver) CurrentStep /= 2;
-            Direction = 1;
-            step = CurrentStep;
-        }
-        else {
-            if (Direction == 1) flag_GoneOver = 1;
-            if (flag_GoneOver) CurrentStep /= 2;
-            Direction = 2;
-            step = -CurrentStep;
-        }
-        gi.global_gain += step;
-        if (gi.global_gain < 0) { gi.global_gain = 0; flag_GoneOver = 1; }
-        if (gi.global_gain > 255) { gi.global_gain = 255; flag_GoneOver = 1; }
-    }
-    while (nBits > desired_rate && gi.global_gain < 255) {
-        gi.global_gain++;
-        nBits = lg_count_bits(c, w, gi, qc, nullptr, lane);
-    }
-    *current_step = (start - gi.global_gain >= 4) ? 4 : 2;
-    *old_value = gi.global_gain;
-    gi.part2_3_length = nBits;
-    return nBits;
-}
-
-/* quantize.c:1010 outer_loop.  On return the work set (gi, sfw, ixw) holds the chosen quantisation. */
+/* quantize.c:1010 outer_loop with bin_search_StepSize (:367) folded in, written as a state machine around ONE inlined
+ * count_bits and ONE inlined calc_noise, so that the granule's scalar state (gi, best, pv, the search variables) stays in
+ * registers for the whole search.  phase: 0 step-size search, main loop; 1 its "while too many bits" tail; 2 the first
+ * and 3 the second "raise global_gain until it fits" loop of a noise-shaping round (quantize.c:1083-1101).
+ * On return the work set (gi, sfw, ixw) holds the chosen quantisation. */
 __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int targ_bits,
                                               int *old_value, int *current_step, int lane)
 {
-    (void) lg_bin_search(c, w, gi, qc, targ_bits, old_value, current_step, lane);
-    if (!c->noise_shaping) return;
-    LgPrev pv; pv.valid = 1; pv.global_gain = 0; pv.sfb_count1 = 0;
-    for (int i = lane; i < 40; i += 32) { w->pn_step[i] = 0; w->pn_noise[i] = 0; w->pn_noise_log[i] = 0; }
-    __syncwarp();
-    LgNoiseRes best_noise;
-    lg_calc_noise(c, w, gi, qc, &best_noise, &pv, lane);
-    best_noise.bits = gi.part2_3_length;
-    LgQInfo best = gi;                            /* cod_info_w = *cod_info: from here gi is the work copy */
-    lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
-    if (c->noise_shaping_amp == 3) lg_copy_f576(w->save_xrpow, w->xrpow, lane);
-    int age = 0, best_part2_3_length = 9999999, bEndOfSearch = 0, bRefine = 0, best_ggain_pass1 = 0;
-    int guard = 0;
-    while (!bEndOfSearch) {
-        do {
-            LgNoiseRes noise_info;
-            if (++guard > 20000) lg_runaway();
-            int const search_limit = 3;
-            int maxggain = 255;
-            if (c->sfb21_extra) {
-                if (w->distort[qc.sfbmax] > 1.0) break;
-                if (qc.block_type == LG_SHORT && (w->distort[qc.sfbmax + 1] > 1.0 || w->distort[qc.sfbmax + 2] > 1.0)) break;
+    int CurrentStep = *current_step, flag_GoneOver = 0, Direction = 0;
+    int const start = *old_value;
+    gi.global_gain = start;
+    int const desired_rate = targ_bits - gi.part2_length;
+    LgPrev pv; pv.valid = 0; pv.global_gain = 0; pv.sfb_count1 = 0;
+    LgNoiseRes best_noise; best_noise.max_noise = 0.f; best_noise.over_count = 0; best_noise.over_SSD = 0; best_noise.bits = 0;
+    LgQInfo best = gi;
+    int age = 0, best_part2_3_length = 9999999, maxggain = 255, huff_bits = 0, phase = 0;
+    for (int guard = 0;; guard++) {
+        if (guard > 30000) lg_runaway();
+        int const nBits = lg_count_bits(c, w, gi, qc, pv, lane);
+        if (phase == 0) {
+            if (!(CurrentStep == 1 || nBits == desired_rate)) {
+                int step;
+                if (nBits > desired_rate) {
+                    if (Direction == 2) flag_GoneOver = 1;
+                    if (flag_GoneOver) CurrentStep /= 2;
+                    Direction = 1;
+                    step = CurrentStep;
+                }
+                else {
+                    if (Direction == 1) flag_GoneOver = 1;
+                    if (flag_GoneOver) CurrentStep /= 2;
+                    Direction = 2;
+                    step = -CurrentStep;
+                }
+                gi.global_gain += step;
+                if (gi.global_gain < 0) { gi.global_gain = 0; flag_GoneOver = 1; }
+                if (gi.global_gain > 255) { gi.global_gain = 255; flag_GoneOver = 1; }
+                continue;
             }
-            if (lg_balance_noise(c, w, gi, qc, lane) == 0) break;
-            if (gi.scalefac_scale) maxggain = 254;
-            int const huff_bits = targ_bits - gi.part2_length;
-            if (huff_bits <= 0) break;
-            while ((gi.part2_3_length = lg_count_bits(c, w, gi, qc, &pv, lane)) > huff_bits && gi.global_gain <= maxggain)
-                gi.global_gain++;
+            phase = 1;
+        }
+        if (phase == 1) {
+            if (nBits > desired_rate && gi.global_gain < 255) { gi.global_gain++; continue; }
+            *current_step = (start - gi.global_gain >= 4) ? 4 : 2;
+            *old_value = gi.global_gain;
+            gi.part2_3_length = nBits;
+            if (!c->noise_shaping) return;
+            pv.valid = 1; pv.global_gain = 0; pv.sfb_count1 = 0;
+            for (int i = lane; i < 40; i += 32) { w->pn_step[i] = 0; w->pn_noise[i] = 0; w->pn_noise_log[i] = 0; }
+            __syncwarp();
+        }
+        else if (phase == 2) {
+            gi.part2_3_length = nBits;
+            if (nBits > huff_bits && gi.global_gain <= maxggain) { gi.global_gain++; continue; }
             if (gi.global_gain > maxggain) break;
-            if (best_noise.over_count == 0) {
-                while ((gi.part2_3_length = lg_count_bits(c, w, gi, qc, &pv, lane)) > best_part2_3_length && gi.global_gain <= maxggain)
-                    gi.global_gain++;
-                if (gi.global_gain > maxggain) break;
-            }
-            lg_calc_noise(c, w, gi, qc, &noise_info, &pv, lane);
-            noise_info.bits = gi.part2_3_length;
+            if (best_noise.over_count == 0) { phase = 3; continue; }
+        }
+        else {
+            gi.part2_3_length = nBits;
+            if (nBits > best_part2_3_length && gi.global_gain <= maxggain) { gi.global_gain++; continue; }
+            if (gi.global_gain > maxggain) break;
+        }
+        LgNoiseRes noise_info;
+        lg_calc_noise(c, w, gi, qc, &noise_info, pv, lane);
+        noise_info.bits = gi.part2_3_length;
+        if (phase == 1) {
+            best_noise = noise_info;
+            best = gi;                            /* cod_info_w = *cod_info: from here gi is the work copy */
+            lg_copy_ix_sf(w, 1, qc.jn, lane);
+        }
+        else {
             if (lg_quant_compare(best_noise, noise_info)) {
                 best_part2_3_length = best.part2_3_length;
                 best_noise = noise_info;
                 best = gi;
-                lg_copy_ix_sf(w->ixb, w->ixw, w->sfbst, w->sfw, lane);
+                lg_copy_ix_sf(w, 1, qc.jn, lane);
                 age = 0;
-                if (c->noise_shaping_amp == 3) lg_copy_f576(w->save_xrpow, w->xrpow, lane);   /* only the refinement pass reads it back */
             }
             else if (c->full_outer_loop == 0) {
-                if (++age > search_limit && best_noise.over_count == 0) break;
-                if ((c->noise_shaping_amp == 3) && bRefine && age > 30) break;
-                if ((c->noise_shaping_amp == 3) && bRefine && (gi.global_gain - best_ggain_pass1) > 15) break;
+                if (++age > 3 && best_noise.over_count == 0) break;
+                /* the noise_shaping_amp == 3 exits and the second (refinement) pass belong to quality 0/1, which lg_setup rejects */
             }
-        } while ((gi.global_gain + gi.scalefac_scale) < 255);
-        if (c->noise_shaping_amp == 3) {
-            if (!bRefine) {
-                gi = best;
-                lg_copy_ix_sf(w->ixw, w->ixb, w->sfw, w->sfbst, lane);
-                lg_copy_f576(w->xrpow, w->save_xrpow, lane);
-                age = 0;
-                best_ggain_pass1 = gi.global_gain;
-                bRefine = 1;
-            }
-            else bEndOfSearch = 1;
+            if (!((gi.global_gain + gi.scalefac_scale) < 255)) break;
         }
-        else bEndOfSearch = 1;
+        /* top of a noise-shaping round */
+        if (c->sfb21_extra) {
+            if (w->distort[qc.sfbmax] > 1.0) break;
+            if (qc.block_type == LG_SHORT && (w->distort[qc.sfbmax + 1] > 1.0 || w->distort[qc.sfbmax + 2] > 1.0)) break;
+        }
+        if (lg_balance_noise(c, w, gi, qc, lane) == 0) break;
+        maxggain = gi.scalefac_scale ? 254 : 255;
+        huff_bits = targ_bits - gi.part2_length;
+        if (huff_bits <= 0) break;
+        phase = 2;
     }
     gi = best;
-    lg_copy_ix_sf(w->ixw, w->ixb, w->sfw, w->sfbst, lane);
+    lg_copy_ix_sf(w, 0, qc.jn, lane);
 }
 
 /* ---------------------------------------------------------------- quantize_pvt.c:589 calc_xmin: one lane per band */
@@ -866,6 +898,20 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
         if (max_nonzero > limit) max_nonzero = limit;
     }
     qc.max_nonzero_coeff = max_nonzero;
+    {
+        int const ilim = (max_nonzero + 2) & ~1;
+        qc.jn = (ilim + 63) >> 6;
+        /* per band: largest xrpow above max_nonzero_coeff (lg_scale_bands keeps it up to date instead of the lines) */
+        for (int r = 0; r < 2; r++) {
+            int const sfb = lane + 32 * r;
+            if (sfb < 40) {
+                float tm = 0.f;
+                int const j1 = w->lstart[sfb] + w->width[sfb];
+                for (int j = max(w->lstart[sfb], ilim); j < j1; j++) { float const v = w->xrpow[j]; if (v > tm) tm = v; }
+                w->tail_max[sfb] = tm;
+            }
+        }
+    }
     /* short bands: one lane per sfb handles its three windows */
     {
         int const sfb = qc.sfb_smin + lane;
@@ -1070,7 +1116,10 @@ __device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__
     }
     for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (sf[sfb] == -2) sf[sfb] = 0;
     __syncwarp();
-    if (recalc) (void) lg_scale_bitcount(w, gi, qc, sf, lane);
+    if (recalc) {
+        unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, lane);
+        LG_APPLY_SCALE_BITCOUNT(gi, r);
+    }
 }
 
 /* ---------------------------------------------------------------- bit budget (reservoir.c, quantize_pvt.c:428/:492): lane-uniform scalar code */
@@ -1201,7 +1250,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                 /* quantize.c:226 init_outer_loop (the short-block reorder was done by kernel C) */
                 gi.part2_3_length = 0; gi.big_values = 0; gi.count1 = 0; gi.global_gain = 210; gi.scalefac_compress = 0;
                 gi.table_select[0] = gi.table_select[1] = gi.table_select[2] = 0;
-                gi.subblock_gain[0] = gi.subblock_gain[1] = gi.subblock_gain[2] = gi.subblock_gain[3] = 0;
+                gi.sbg = 0;
                 gi.region0_count = 0; gi.region1_count = 0; gi.preflag = 0; gi.scalefac_scale = 0;
                 gi.count1table_select = 0; gi.part2_length = 0; gi.count1bits = 0; gi.xrpow_max = 0;
                 qc.block_type = P->block_type[ch];
@@ -1215,7 +1264,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                     qc.sfbdivide = qc.sfbmax - 18;
                     qc.psy_lmax = 0;
                 }
-                qc.max_nonzero_coeff = 575;
+                qc.max_nonzero_coeff = 575; qc.jn = 9;
                 for (int r = 0; r < 2; r++) {
                     int const k = lane + 32 * r;
                     if (k <= 40) {
@@ -1269,12 +1318,21 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                     nonzero = sum > (float) 1E-20;
                 }
                 if (nonzero) {
-                    lg_calc_xmin(cfg, w, qc, en, thm, F->ath_adjust_factor, lane);
+                    {   /* through a copy: qc and gi must not have their address taken, or they leave the registers */
+                        LgQConst qx = qc;
+                        lg_calc_xmin(cfg, w, qx, en, thm, F->ath_adjust_factor, lane);
+                        qc.max_nonzero_coeff = qx.max_nonzero_coeff; qc.jn = qx.jn;
+                    }
                     lg_outer_loop(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, lane);
                 }
                 /* quantize.c:1213 iteration_finish_one */
-                lg_best_scalefac_store(cfg, w, gi, qc, gr, sm->sf_gr0[ch], sm->bt_gr0[ch], scfsi, lane);
-                if (cfg->use_best_huffman == 1) lg_best_huffman_divide(cfg, w, gi, qc, lane);
+                {
+                    LgQInfo gm = gi;
+                    LgQConst qx = qc;
+                    lg_best_scalefac_store(cfg, w, gm, qx, gr, sm->sf_gr0[ch], sm->bt_gr0[ch], scfsi, lane);
+                    if (cfg->use_best_huffman == 1) lg_best_huffman_divide(cfg, w, gm, qx, lane);
+                    gi = gm;
+                }
                 used = gi.part2_3_length + gi.part2_length;
                 if (gr == 0) {
                     for (int i = lane; i < 40; i += 32) sm->sf_gr0[ch][i] = w->sfw[i];
@@ -1296,7 +1354,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                     o->big_values = (int16_t) gi.big_values; o->count1 = (int16_t) gi.count1;
                     o->global_gain = (uint8_t) gi.global_gain; o->scalefac_compress = (uint8_t) gi.scalefac_compress;
                     o->block_type = (uint8_t) qc.block_type; o->mixed_block_flag = 0;
-                    for (int i = 0; i < 3; i++) { o->table_select[i] = (uint8_t) gi.table_select[i]; o->subblock_gain[i] = (uint8_t) gi.subblock_gain[i]; }
+                    for (int i = 0; i < 3; i++) { o->table_select[i] = (uint8_t) gi.table_select[i]; o->subblock_gain[i] = (uint8_t) ((gi.sbg >> (4 * i)) & 15); }
                     o->region0_count = (uint8_t) gi.region0_count; o->region1_count = (uint8_t) gi.region1_count;
                     o->preflag = (uint8_t) gi.preflag; o->scalefac_scale = (uint8_t) gi.scalefac_scale;
                     o->count1table_select = (uint8_t) gi.count1table_select;

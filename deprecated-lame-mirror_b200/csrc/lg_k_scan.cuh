@@ -11,6 +11,7 @@
 #include "lg_math.cuh"
 
 struct LgSmemB {
+    LgAnalysis A;                     /* first: copied with 8-byte accesses (the dynamic smem base is 16-byte aligned) */
     float eb[4][LG_CBANDS], thr[4][LG_CBANDS];
     float last_thm_s[4][LG_SBMAX_S][3];
     float ssf[4][3];
@@ -21,6 +22,9 @@ struct LgSmemB {
     float frame_tot[2][4];
     int   frame_bt[2][2];
     float bcast[4];
+    /* the stream's carried state and the current granule's analysis record live in shared memory while the warp walks
+     * the stream: the scan is a chain of dependent steps, so every global load would be paid in full latency */
+    LgStreamState st;
 };
 
 /* psymodel.c:350 convert_partition2scalefac, run serially by one lane */
@@ -218,7 +222,13 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
     LG_DYN_SMEM(LgSmemB, sm);
     int const lane = threadIdx.x & 31;
     int const stream = blockIdx.x;
-    LgStreamState *st = state + stream;
+    LgStreamState *st = &sm->st;
+    {
+        const int *src = reinterpret_cast<const int *>(state + stream);
+        int *dst = reinterpret_cast<int *>(st);
+        for (int i = lane; i < (int) (sizeof(LgStreamState) / 4); i += 32) dst[i] = src[i];
+    }
+    __syncwarp();
     const LgBands *gdl = &cfg->l, *gds = &cfg->s;
     int const nch = cfg->channels;
     int const n_chn_psy = (cfg->mode == LG_JOINT) ? 4 : nch;
@@ -226,7 +236,14 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
 
     int const my_frames = nfr[stream];
     for (int gb = 0; gb < 2 * my_frames; gb++) {
-        const LgAnalysis *A = ana + (size_t) stream * 2 * nframes + gb;
+        const LgAnalysis *A = &sm->A;
+        {
+            static_assert(sizeof(LgAnalysis) % 8 == 0, "LgAnalysis is copied in 8-byte words");
+            const float2 *src = reinterpret_cast<const float2 *>(ana + (size_t) stream * 2 * nframes + gb);
+            float2 *dst = reinterpret_cast<float2 *>(&sm->A);
+            for (int i = lane; i < (int) (sizeof(LgAnalysis) / 8); i += 32) dst[i] = __ldg(src + i);
+        }
+        __syncwarp();
         LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
         int const gr = gb & 1;
         float const ath_factor = (cfg->msfix > 0.f) ? (cfg->ath_offset_factor * st->ath_adjust_factor) : 1.f;
@@ -467,5 +484,11 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
             }
             __syncwarp();
         }
+    }
+    __syncwarp();
+    {
+        int *dst = reinterpret_cast<int *>(state + stream);
+        const int *src = reinterpret_cast<const int *>(st);
+        for (int i = lane; i < (int) (sizeof(LgStreamState) / 4); i += 32) dst[i] = src[i];
     }
 }
