@@ -56,6 +56,19 @@ struct LgSmemD {
 };
 
 __constant__ uint8_t LG_PRETAB[22] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0 };
+/* Per-lane table lookups with a different index in every lane are serialised by the constant cache; the small tables of
+ * this kernel are therefore packed into immediates: pretab (2 bits x 22), slen1/slen2 (4 bits x 16), the three
+ * scale_bitcount length tables (8 bits x 16). */
+__device__ __forceinline__ int lg_pretab(int sfb) { return (int) ((0x2FE95400000ull >> (2 * (sfb < 21 ? sfb : 21))) & 3ull); }
+__device__ __forceinline__ int lg_slen1(int k) { return (int) ((0x4433322211130000ull >> (4 * k)) & 15ull); }
+__device__ __forceinline__ int lg_slen2(int k) { return (int) ((0x3232132132103210ull >> (4 * k)) & 15ull); }
+__device__ __forceinline__ int lg_scale_len(int block_type_short, int k)
+{
+    /* LG_SCALE_SHORT / LG_SCALE_LONG, entries 0..7 and 8..15 */
+    unsigned long long const lo = block_type_short ? 0x4836243636241200ull : 0x291F15211E140A00ull;
+    unsigned long long const hi = block_type_short ? 0x7E6C6C5A485A4836ull : 0x4A403F352B342A20ull;
+    return (int) (((k < 8 ? lo : hi) >> (8 * (k & 7))) & 255ull);
+}
 __constant__ int LG_SLEN1_N[16] = { 1, 1, 1, 1, 8, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 16 };
 __constant__ int LG_SLEN2_N[16] = { 1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2, 4, 8, 4, 8 };
 __constant__ int LG_SLEN1_TAB[16] = { 0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4 };
@@ -103,18 +116,37 @@ __device__ __forceinline__ unsigned lg_wor_u(unsigned v)
     return __reduce_or_sync(LG_FULL, v);
 #endif
 }
+/* max of NON-NEGATIVE floats: their bit patterns order like integers, one REDUX instead of five shuffles */
+__device__ __forceinline__ float lg_wmax_fpos(float v)
+{
+#if defined(LG_EMULATE)
+    for (int d = 16; d > 0; d >>= 1) { float o = __shfl_xor_sync(LG_FULL, v, d); v = v > o ? v : o; }
+    return v;
+#else
+    return __int_as_float(__reduce_max_sync(LG_FULL, __float_as_int(v)));
+#endif
+}
 /* float max is exact and order-free */
 __device__ __forceinline__ float lg_wmax_f(float v)
 {
+#if defined(LG_EMULATE)
     for (int d = 16; d > 0; d >>= 1) { float o = __shfl_xor_sync(LG_FULL, v, d); v = v > o ? v : o; }
     return v;
+#else
+    /* order-preserving map float -> int (flip the magnitude bits of negative values), then one integer reduction */
+    int k = __float_as_int(v);
+    k ^= (k >> 31) & 0x7fffffff;
+    k = __reduce_max_sync(LG_FULL, k);
+    k ^= (k >> 31) & 0x7fffffff;
+    return __int_as_float(k);
+#endif
 }
 
 __device__ __forceinline__ const uint8_t *lg_hlen(const LgDevCfg *__restrict__ c, int t) { return c->huff_len + c->huff_off[t]; }
 
 __device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const LgQWarp *w, const int *sf, int sfb)
 {
-    return gi.global_gain - ((sf[sfb] + (gi.preflag ? (int) LG_PRETAB[sfb < 22 ? sfb : 21] : 0)) << (gi.scalefac_scale + 1))
+    return gi.global_gain - ((sf[sfb] + (gi.preflag ? lg_pretab(sfb) : 0)) << (gi.scalefac_scale + 1))
          - ((gi.sbg >> (4 * w->window[sfb])) & 15) * 8;
 }
 
@@ -532,16 +564,13 @@ __device__ __forceinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, Lg
 __device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, int sfbmax, int sfbdivide, int preflag, int compress, int lane)
 {
     int *sf = w->sfw;
-    const int *tab;
-    if (block_type == LG_SHORT) tab = LG_SCALE_SHORT;
-    else {
-        tab = LG_SCALE_LONG;
+    if (block_type != LG_SHORT) {
         if (!preflag) {
             int bad = 0;
-            if (lane >= 11 && lane < LG_SBPSY_L) bad = sf[lane] < (int) LG_PRETAB[lane];
+            if (lane >= 11 && lane < LG_SBPSY_L) bad = sf[lane] < lg_pretab(lane);
             if (!__any_sync(LG_FULL, bad)) {
                 preflag = 1;
-                if (lane >= 11 && lane < LG_SBPSY_L) sf[lane] -= LG_PRETAB[lane];
+                if (lane >= 11 && lane < LG_SBPSY_L) sf[lane] -= lg_pretab(lane);
                 __syncwarp();
             }
         }
@@ -554,7 +583,7 @@ __device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, i
     m2 = lg_wmax_i(m2);
     /* the 16 (slen1, slen2) candidates one per lane; smallest length wins, the lowest index on ties (as the reference's scan) */
     int key = 0x7fffffff;
-    if (lane < 16 && m1 < LG_SLEN1_N[lane] && m2 < LG_SLEN2_N[lane]) key = tab[lane] * 16 + lane;
+    if (lane < 16 && m1 < (1 << lg_slen1(lane)) && m2 < (1 << lg_slen2(lane))) key = lg_scale_len(block_type == LG_SHORT, lane) * 16 + lane;
     key = lg_wmin_i(key);
     int part2_length = LG_LARGE_BITS;
     if (key != 0x7fffffff) { part2_length = key >> 4; compress = key & 15; }
@@ -602,7 +631,7 @@ __device__ __noinline__ float lg_scale_bands(LgQWarp *w, float xrpow_max, int jn
             if (v.y > mx) mx = v.y;
         }
     }
-    mx = lg_wmax_f(mx);
+    mx = lg_wmax_fpos(mx);
     __syncwarp();
     return mx;
 }
@@ -613,7 +642,7 @@ __device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict
     float const ifqstep34 = (gi.scalefac_scale == 0) ? (float) 1.29683955465100964055 : (float) 1.68179283050742922612;
     float trigger = 0;
     for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (trigger < w->distort[sfb]) trigger = w->distort[sfb];
-    trigger = lg_wmax_f(trigger);
+    trigger = lg_wmax_fpos(trigger);
     if (c->noise_shaping_amp == 1) {
         if (trigger > 1.0) trigger = (float) sqrt((double) trigger);      /* pow(trigger, .5), see lg_math.cuh */
         else trigger = (float) (trigger * .95);
@@ -644,7 +673,7 @@ __device__ __forceinline__ void lg_inc_scalefac_scale(LgQWarp *w, LgQInfo &gi, c
             float f = 0.f;
             if (sfb < qc.sfbmax) {
                 int s = w->sfw[sfb];
-                if (gi.preflag) s += LG_PRETAB[sfb < 22 ? sfb : 21];
+                if (gi.preflag) s += lg_pretab(sfb);
                 if (s & 1) { s++; f = ifqstep34; }
                 w->sfw[sfb] = s >> 1;
             }
@@ -1080,9 +1109,9 @@ __device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__
     }
     if (!gi.preflag && qc.block_type != LG_SHORT && c->mode_gr == 2) {
         int bad = 0;
-        if (lane >= 11 && lane < LG_SBPSY_L) bad = (sf[lane] < (int) LG_PRETAB[lane] && sf[lane] != -2);
+        if (lane >= 11 && lane < LG_SBPSY_L) bad = (sf[lane] < lg_pretab(lane) && sf[lane] != -2);
         if (!__any_sync(LG_FULL, bad)) {
-            if (lane >= 11 && lane < LG_SBPSY_L && sf[lane] > 0) sf[lane] -= LG_PRETAB[lane];
+            if (lane >= 11 && lane < LG_SBPSY_L && sf[lane] > 0) sf[lane] -= lg_pretab(lane);
             gi.preflag = recalc = 1;
             __syncwarp();
         }
@@ -1286,9 +1315,8 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                 {   /* line -> band map and the lines themselves */
                     const float *src = xr_in + (((size_t) stream * 2 * nframes + gb) * 2 + ch) * 576;
                     for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(w->xr)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
-                    int const nb = (qc.block_type == LG_SHORT) ? 39 : 22;
-                    for (int b = lane; b < nb; b += 32)
-                        for (int i = w->lstart[b]; i < w->lstart[b] + w->width[b]; i++) w->line_sfb[i] = (uint8_t) b;
+                    const unsigned *map = reinterpret_cast<const unsigned *>(qc.block_type == LG_SHORT ? cfg->line_sfb_s : cfg->line_sfb_l);
+                    for (int i = lane; i < 144; i += 32) reinterpret_cast<unsigned *>(w->line_sfb)[i] = __ldg(map + i);
                 }
                 __syncwarp();
                 /* quantize.c:110 init_xrpow (upper = 575) */
@@ -1306,8 +1334,8 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                     if (t1 > amax) amax = t1;
                     *reinterpret_cast<unsigned *>(&w->ixw[i]) = 0u;
                 }
-                gi.xrpow_max = lg_wmax_f(mx);
-                amax = lg_wmax_f(amax);
+                gi.xrpow_max = lg_wmax_fpos(mx);
+                amax = lg_wmax_fpos(amax);
                 __syncwarp();
                 /* sum > 1e-20 ?  A serial non-negative float sum is >= its largest term, so only a spectrum
                  * whose largest magnitude is itself <= 1e-20 needs the exact serial sum of the reference. */

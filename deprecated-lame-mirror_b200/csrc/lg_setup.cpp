@@ -718,6 +718,12 @@ static void finish_device_tables(LgDevCfg *c)
                     c->huff_pk[k * 256 + x * 16 + y] = e;
                 }
         }
+        for (int b = 0; b < 22; b++) for (int i = c->sfb_l[b]; i < c->sfb_l[b + 1]; i++) c->line_sfb_l[i] = (uint8_t) b;
+        for (int sfb = 0; sfb < 13; sfb++) {
+            int const ws = c->sfb_s[sfb + 1] - c->sfb_s[sfb];
+            for (int wn = 0; wn < 3; wn++)
+                for (int i = 0; i < ws; i++) c->line_sfb_s[3 * c->sfb_s[sfb] + wn * ws + i] = (uint8_t) (3 * sfb + wn);
+        }
         for (int i = 0; i < 256; i++) {
             uint32_t const a = c->largetbl[i] >> 16, b = c->largetbl[i] & 0xffffu;
             c->huff_pk[6 * 256 + i] = a | (b << 10) | (b << 20);

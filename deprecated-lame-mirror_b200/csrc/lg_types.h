@@ -90,6 +90,8 @@ typedef struct {
      * [class][x*16+y] = bits under the class's three candidate tables in 10-bit fields (two-candidate classes repeat
      * the second), so one code path replaces count_bit_noESC/_from2/_from3/_ESC (takehiro.c:449-573) */
     uint32_t huff_pk[7 * 256];
+    /* scalefactor band of every line: long blocks (22 bands) and short blocks after reordering (39 = 13 x 3 windows) */
+    uint8_t line_sfb_l[576], line_sfb_s[576];
     uint16_t huff_code[2048];           /* code words, same layout as huff_len (bit packer, tables.c HB tables) */
 } LgDevCfg;
 
