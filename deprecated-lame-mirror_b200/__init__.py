@@ -60,6 +60,7 @@ def load_library(path=None):
         "lame_encode_buffer_ieee_float": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
         "lame_encode_flush": (c_int, [c_void_p, c_void_p, c_int]),
         "lame_close": (c_int, [c_void_p]),
+        "lame_get_lametag_frame": (ctypes.c_size_t, [c_void_p, c_void_p, ctypes.c_size_t]),
         "get_lame_short_version": (c_char_p, []),
         "lamegpu_batch_open": (c_void_p, [c_int] * 8),
         "lamegpu_batch_close": (None, [c_void_p]),
@@ -91,7 +92,7 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "get_lame_short_version", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
+    "lame_close", "lame_get_lametag_frame", "get_lame_short_version", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
     "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
     "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_batch_d2h_bytes",
@@ -106,7 +107,7 @@ def _as_i16(a):
 class Encoder:
     """One stream through the libmp3lame-compatible entry points (same semantics and error codes)."""
 
-    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1):
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1, write_tag=False):
         self._lib = load_library()
         self._h = self._lib.lame_init()
         if not self._h:
@@ -120,7 +121,7 @@ class Encoder:
             L.lame_set_mode(self._h, mode)
         if quality >= 0:
             L.lame_set_quality(self._h, quality)
-        L.lame_set_bWriteVbrTag(self._h, 0)
+        L.lame_set_bWriteVbrTag(self._h, 1 if write_tag else 0)
         rc = L.lame_init_params(self._h)
         if rc < 0:
             L.lame_close(self._h)
@@ -145,6 +146,12 @@ class Encoder:
         if rc < 0:
             raise LameGpuError("lame_encode_flush returned %d" % rc)
         return buf[:rc].tobytes()
+
+    def lametag_frame(self):
+        """lame_get_lametag_frame: the finished Info tag frame (to be written over the placeholder at offset 0)"""
+        buf = np.empty(2880, dtype=np.uint8)
+        n = self._lib.lame_get_lametag_frame(self._h, buf.ctypes.data, buf.size)
+        return buf[:n].tobytes()
 
     def close(self):
         if self._h:

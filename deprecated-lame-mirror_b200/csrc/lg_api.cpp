@@ -11,6 +11,7 @@
 #include <functional>
 #include <new>
 #include <chrono>
+#include <math.h>
 #include <mutex>
 #include <condition_variable>
 #include <memory>
@@ -36,12 +37,25 @@ struct Stream {
     int  last_padding = 0;
     LgBitWriter bw;
     std::vector<unsigned char> out;    /* packed bytes not yet handed to the caller */
+    /* Info tag bookkeeping of one lame_t (VbrTag.c): the seek table of AddVbrFrame (:196), the byte count and music
+     * CRC of copy_buffer (bitstream.c:1079-1090), what lame_get_lametag_frame (:900) needs at the end */
+    struct Tag {
+        bool on = false;
+        int  frame_size = 0;
+        long nframes = 0, nbytes = 0, sum = 0;
+        int  seen = 0, want = 1, pos = 0;
+        int  bag[400];
+        unsigned short music_crc = 0;
+        long pending = 0;              /* placeholder bytes still in `out`: handed over without CRC (copy_buffer mp3data = 0) */
+        int  mode_ext = 0, enc_padding = 0;
+    } tag;
 
     void init()
     {
         for (int c = 0; c < 2; c++) { pcm16[c].assign(LG_PCM_HIST + 528, 0); pcmf[c].clear(); }
         float_mode = false; tbase = -LG_PCM_HIST; frames_done = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
         bw.reset(); out.clear();
+        tag = Tag();
     }
     long tend() const { return tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()); }
     long frames_ready() const
@@ -76,6 +90,38 @@ struct Stream {
         tbase = keep_from;
     }
 };
+
+/* VbrTag.c:576 CRC_update_lookup: CRC-16, polynomial x^16 + x^15 + x^2 + 1 (reflected 0xA001) */
+static unsigned short crc16_update(unsigned short value, unsigned short crc)
+{
+    static unsigned short table[256];
+    static bool ready = false;
+    if (!ready) {
+        for (int i = 0; i < 256; i++) {
+            unsigned short c = (unsigned short) i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? (unsigned short) ((c >> 1) ^ 0xA001) : (unsigned short) (c >> 1);
+            table[i] = c;
+        }
+        ready = true;
+    }
+    unsigned short const tmp = crc ^ value;
+    return (unsigned short) ((crc >> 8) ^ table[tmp & 0xff]);
+}
+
+/* VbrTag.c:123 addVbr */
+static void tag_add_frame(Stream::Tag &v, int bitrate)
+{
+    v.nframes++;
+    v.sum += bitrate;
+    v.seen++;
+    if (v.seen < v.want) return;
+    if (v.pos < 400) { v.bag[v.pos] = (int) v.sum; v.pos++; v.seen = 0; }
+    if (v.pos == 400) {
+        for (int i = 1; i < 400; i += 2) v.bag[i / 2] = v.bag[i];
+        v.want *= 2;
+        v.pos /= 2;
+    }
+}
 
 /* Persistent worker pool: the per-call host work (PCM staging, bit packing, output hand-over) is a few hundred
  * microseconds per thread, so spawning threads per call would cost as much as the work itself. */
@@ -196,6 +242,7 @@ struct lamegpu_batch {
                     const LgFrameOut *fr = fo + (size_t) s * F + f;
                     lg_merge_frame(&x.bw, &cfg, fr, hdr + ((size_t) s * F + f) * LG_HDR_STRIDE, pay + (size_t) s * pay_stride + fr->pay_off);
                     x.last_padding = fr->padding;
+                    if (x.tag.on) { tag_add_frame(x.tag, cfg.brate); x.tag.mode_ext = fr->mode_ext; }
                 }
                 x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
                 x.bw.buf.clear();
@@ -257,6 +304,7 @@ struct lamegpu_batch {
         long const samples_to_encode = x.mf_samples_to_encode - 1152;
         long end_padding = 1152 - (samples_to_encode % 1152);
         if (end_padding < 576) end_padding += 1152;
+        x.tag.enc_padding = (int) end_padding;                /* lame.c:2091 */
         long const frames_left = (samples_to_encode + end_padding) / 1152;
         long const last = x.frames_done + frames_left - 1;
         long const need = 1152 * last + 1904 - x.tend();
@@ -421,6 +469,39 @@ struct lame_global_struct {
     int initialised;
 };
 
+/* VbrTag.c:255 setLameTagFrameHeader (MPEG-1 branch): the tag frame looks like a frame of the stream itself, without padding */
+static void tag_frame_header(const LgDevCfg *c, int mode_ext, unsigned char *buffer)
+{
+    buffer[0] = 0xff;
+    buffer[1] = (unsigned char) (0xf0 | 0x0a | (c->error_protection ? 0 : 1));
+    buffer[2] = (unsigned char) ((16 * c->bitrate_index) | ((c->samplerate_index << 2) & 0x0c) | (c->extension & 1));
+    buffer[3] = (unsigned char) ((c->mode << 6) | ((mode_ext & 3) << 4) | ((c->copyright & 1) << 3) | ((c->original & 1) << 2) | (c->emphasis & 3));
+}
+
+#define LG_VBRHEADERSIZE (100 + 4 + 4 + 4 + 4 + 4)
+#define LG_LAMEHEADERSIZE (LG_VBRHEADERSIZE + 9 + 1 + 1 + 8 + 1 + 1 + 3 + 1 + 1 + 2 + 4 + 2 + 2)
+
+/* VbrTag.c:492 InitVbrTag for CBR: an all-zero frame (but for its header) goes into the stream ahead of the audio */
+static void tag_init(lamegpu_batch *b)
+{
+    Stream &x = b->st[0];
+    const LgDevCfg *c = &b->cfg;
+    int const total = ((c->version + 1) * 72000 * c->brate) / c->samplerate;
+    if (total < c->sideinfo_len + LG_LAMEHEADERSIZE || total > 2880) return;      /* "disable tag, it wont fit" */
+    x.tag.on = true;
+    x.tag.frame_size = total;
+    std::vector<unsigned char> frame((size_t) total, 0);
+    tag_frame_header(c, 0, frame.data());
+    x.out.insert(x.out.end(), frame.begin(), frame.end());
+    x.tag.pending = total;
+    /* add_dummy_byte (bitstream.c:893): the bytes pass through the bit writer and every header slot moves with them */
+    x.bw.totbit += 8L * total;
+    for (int i = 0; i < LG_MAX_HEADER_BUF; ++i) x.bw.header[i].write_timing += 8L * total;
+}
+
+static void put_be32(unsigned char *p, unsigned long v) { p[0] = (v >> 24) & 0xff; p[1] = (v >> 16) & 0xff; p[2] = (v >> 8) & 0xff; p[3] = v & 0xff; }
+static void put_be16(unsigned char *p, unsigned v) { p[0] = (v >> 8) & 0xff; p[1] = v & 0xff; }
+
 lame_global_flags *lame_init(void)
 {
     lame_global_flags *g = (lame_global_flags *) calloc(1, sizeof *g);
@@ -463,6 +544,7 @@ int lame_init_params(lame_global_flags *g)
     g->quality = g->b->cfg.quality;
     g->mode = (MPEG_mode) g->b->cfg.mode;
     g->initialised = 1;
+    if (g->write_lame_tag) tag_init(g->b);                 /* lame.c:1249 lame_init_bitstream -> InitVbrTag */
     return 0;
 }
 int lame_get_framesize(const lame_global_flags *g) { return ok(g) && g->initialised ? 1152 : 0; }
@@ -474,7 +556,17 @@ static int handle_take(lame_global_flags *g, unsigned char *mp3buf, int mp3buf_s
     Stream &x = g->b->st[0];
     int const have = (int) x.out.size();
     if (mp3buf_size != 0 && have > mp3buf_size) return -1;            /* lame.h:687: mp3buf too small */
-    if (have) { memcpy(mp3buf, x.out.data(), have); x.out.clear(); }
+    if (have) {
+        memcpy(mp3buf, x.out.data(), have);
+        if (x.tag.on) {
+            /* copy_buffer (bitstream.c:1079): audio bytes feed the music CRC and the byte count, the tag placeholder does not */
+            long const skip = std::min<long>(x.tag.pending, have);
+            x.tag.pending -= skip;
+            for (long i = skip; i < have; i++) x.tag.music_crc = crc16_update(x.out[i], x.tag.music_crc);
+            x.tag.nbytes += have - skip;
+        }
+        x.out.clear();
+    }
     return have;
 }
 int lame_encode_buffer(lame_global_flags *g, const short int l[], const short int r[], const int nsamples, unsigned char *mp3buf, const int mp3buf_size)
@@ -516,6 +608,89 @@ int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
     x.bw.buf.clear();
     return handle_take(g, mp3buf, size);
 }
+/* VbrTag.c:900 lame_get_lametag_frame (+ :151 Xing_seek_table, :597 PutLameVBR) for the configurations this library
+ * encodes: CBR ("Info"), MPEG-1, no CRC, no ReplayGain analysis, no nogap. */
+size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer, size_t size)
+{
+    if (!ok(g) || !g->initialised || !g->b) return 0;
+    const Stream &x = g->b->st[0];
+    const LgDevCfg *c = &g->b->cfg;
+    const Stream::Tag &v = x.tag;
+    if (!v.on) return 0;
+    if (v.pos <= 0) return 0;
+    if (size < (size_t) v.frame_size) return (size_t) v.frame_size;
+    if (!buffer) return 0;
+    memset(buffer, 0, (size_t) v.frame_size);
+    tag_frame_header(c, v.mode_ext, buffer);
+    unsigned char toc[100];
+    memset(toc, 0, sizeof toc);
+    for (int i = 1; i < 100; ++i) {
+        float j = i / (float) 100, act, sum;
+        int indx = (int) (floor(j * v.pos));
+        if (indx > v.pos - 1) indx = v.pos - 1;
+        act = (float) v.bag[indx];
+        sum = (float) v.sum;
+        int seek_point = (int) (256. * act / sum);
+        if (seek_point > 255) seek_point = 255;
+        toc[i] = (unsigned char) seek_point;
+    }
+    unsigned n = (unsigned) c->sideinfo_len;
+    memcpy(buffer + n, "Info", 4); n += 4;
+    put_be32(buffer + n, 1 + 2 + 4 + 8); n += 4;            /* FRAMES_FLAG + BYTES_FLAG + TOC_FLAG + VBR_SCALE_FLAG */
+    put_be32(buffer + n, (unsigned long) v.nframes); n += 4;
+    unsigned long const stream_size = (unsigned long) (v.nbytes + v.frame_size);
+    put_be32(buffer + n, stream_size); n += 4;
+    memcpy(buffer + n, toc, sizeof toc); n += sizeof toc;
+    unsigned short crc = 0;
+    for (unsigned i = 0; i < n; i++) crc = crc16_update(buffer[i], crc);
+    /* PutLameVBR */
+    unsigned char *p = buffer + n;
+    int k = 0;
+    int nQuality = 100 - 10 * 4 /* VBR_q default, lame.c:2360 */ - g->quality;
+    if (nQuality < 0) nQuality = 0;
+    double const lp = c->lowpassfreq / 100.0 + .5;
+    unsigned char const nLowpass = (unsigned char) (lp > 255 ? 255 : lp);
+    unsigned char const nFlags = (unsigned char) (c->athtype + (1 << 4) + ((c->use_safe_joint_stereo != 0) << 5));
+    int nStereoMode;
+    switch (c->mode) {
+    case LG_MONO: nStereoMode = 0; break;
+    case LG_STEREO: nStereoMode = 1; break;
+    case LG_DUAL: nStereoMode = 2; break;
+    case LG_JOINT: nStereoMode = c->force_ms ? 4 : 3; break;
+    default: nStereoMode = 7; break;
+    }
+    int nSourceFreq;
+    if (c->samplerate <= 32000) nSourceFreq = 0;
+    else if (c->samplerate == 48000) nSourceFreq = 2;
+    else if (c->samplerate > 48000) nSourceFreq = 3;
+    else nSourceFreq = 1;
+    int const bNonOptimal = (c->short_blocks == 2 /* forced */ || c->short_blocks == 3 /* dispensed */ ||
+                             (c->disable_reservoir && c->brate < 320) || c->athtype == 0 || c->samplerate <= 32000);
+    unsigned char const nMisc = (unsigned char) (c->noise_shaping + (nStereoMode << 2) + (bNonOptimal << 5) + (nSourceFreq << 6));
+    put_be32(p + k, (unsigned long) nQuality); k += 4;
+    memcpy(p + k, "LAME3.99r", 9); k += 9;                  /* get_lame_tag_encoder_short_version(), version.c:148 */
+    p[k++] = 0x01;                                          /* revision 0, vbr_off -> method 1 */
+    p[k++] = nLowpass;
+    put_be32(p + k, 0); k += 4;                             /* peak signal amplitude: no ReplayGain analysis */
+    put_be16(p + k, 0); k += 2;
+    put_be16(p + k, 0); k += 2;
+    p[k++] = nFlags;
+    p[k++] = (unsigned char) (c->brate >= 255 ? 0xFF : c->brate);
+    int const enc_delay = 576, enc_padding = v.enc_padding;
+    p[k] = (unsigned char) (enc_delay >> 4);
+    p[k + 1] = (unsigned char) ((enc_delay << 4) + (enc_padding >> 8));
+    p[k + 2] = (unsigned char) enc_padding;
+    k += 3;
+    p[k++] = nMisc;
+    p[k++] = 0;
+    put_be16(p + k, (unsigned) c->brate); k += 2;           /* cfg->preset: apply_preset(brate) for CBR, presets.c:361 */
+    put_be32(p + k, stream_size); k += 4;
+    put_be16(p + k, v.music_crc); k += 2;
+    for (int i = 0; i < k; i++) crc = crc16_update(p[i], crc);
+    put_be16(p + k, crc);
+    return (size_t) v.frame_size;
+}
+
 int lame_close(lame_global_flags *g)
 {
     if (!ok(g)) return -3;

@@ -58,6 +58,9 @@ int  lame_encode_buffer_interleaved(lame_global_flags *, short int pcm[], int nu
 int  lame_encode_buffer_ieee_float(lame_t, const float pcm_l[], const float pcm_r[], const int nsamples,
                                    unsigned char *mp3buf, const int mp3buf_size);    /* lame.h:758  +/-1.0 full scale */
 int  lame_encode_flush(lame_global_flags *, unsigned char *mp3buf, int size);        /* lame.h:856 */
+/* Info tag (CBR): lame_set_bWriteVbrTag(1) - the reference's default - puts the all-zero placeholder frame ahead of
+ * the audio; after lame_encode_flush this returns the finished tag frame to be written at offset 0 (VbrTag.c:900) */
+size_t lame_get_lametag_frame(const lame_global_flags *, unsigned char *buffer, size_t size); /* lame.h:970 */
 int  lame_close(lame_global_flags *);                                                /* lame.h:977 */
 const char *get_lame_short_version(void);                                            /* lame.h:645 */
 

@@ -74,7 +74,7 @@ class PortEncoder:
 class RefEncoder:
     """The real libmp3lame 3.99.5 through its own public API (include/lame.h)."""
 
-    def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1):
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1, write_tag=False):
         L = self.lib = ctypes.CDLL(REF_SO)
         L.lame_init.restype = ctypes.c_void_p
         for f in ("lame_set_in_samplerate", "lame_set_num_channels", "lame_set_brate", "lame_set_mode", "lame_set_quality",
@@ -93,7 +93,9 @@ class RefEncoder:
             L.lame_set_mode(self.h, mode)
         if quality >= 0:
             L.lame_set_quality(self.h, quality)
-        L.lame_set_bWriteVbrTag(self.h, 0)
+        L.lame_set_bWriteVbrTag(self.h, 1 if write_tag else 0)
+        L.lame_get_lametag_frame.restype = ctypes.c_size_t
+        L.lame_get_lametag_frame.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
         if L.lame_init_params(self.h) < 0:
             raise ValueError("reference: lame_init_params failed")
 
@@ -111,6 +113,11 @@ class RefEncoder:
         buf = np.empty(65536, dtype=np.uint8)
         rc = self.lib.lame_encode_flush(self.h, buf.ctypes.data, buf.size)
         return buf[:rc].tobytes()
+
+    def lametag_frame(self):
+        buf = np.empty(2880, dtype=np.uint8)
+        n = self.lib.lame_get_lametag_frame(self.h, buf.ctypes.data, buf.size)
+        return buf[:n].tobytes()
 
     def close(self):
         if self.h:

@@ -32,6 +32,13 @@ CASES = [
 ]
 
 
+TAG_CASES = [
+    ("tag_noise_128", "noise", 30, 44100, 128, -1, -1),
+    ("tag_click_192_stereo", "click", 45, 44100, 192, 0, -1),
+    ("tag_sine_320_js", "sine", 20, 44100, 320, 1, -1),
+]
+
+
 def main():
     assert oracle.build()[1], "reference not available"
     w = wave.open("/root/reference/testcase.wav", "rb")
@@ -49,6 +56,27 @@ def main():
         print(name, len(mp3))
     with open(os.path.join(HERE, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
+    # Info tag (lame_set_bWriteVbrTag(1), the reference's default): the stream with its placeholder frame, and the
+    # finished tag frame of lame_get_lametag_frame
+    tags = {}
+    for name, sig, frames, sr, brate, mode, q in TAG_CASES:
+        x = make_signal(sig, frames * 1152)
+        r = oracle.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q, write_tag=True)
+        mp3 = b""
+        for pos in range(0, x.shape[1], 4000):
+            mp3 += r.encode(x[0, pos:pos + 4000], x[1, pos:pos + 4000])
+        mp3 += r.flush()
+        tag = r.lametag_frame()
+        r.close()
+        with open(os.path.join(HERE, name + ".mp3"), "wb") as f:
+            f.write(mp3)
+        with open(os.path.join(HERE, name + ".tagframe"), "wb") as f:
+            f.write(tag)
+        tags[name] = dict(signal=sig, frames=frames, samplerate=sr, brate=brate, mode=mode, quality=q, nbytes=len(mp3), tag_nbytes=len(tag),
+                          mp3_sha256=hashlib.sha256(mp3).hexdigest(), tag_sha256=hashlib.sha256(tag).hexdigest())
+        print(name, len(mp3), len(tag))
+    with open(os.path.join(HERE, "manifest_tag.json"), "w") as f:
+        json.dump(tags, f, indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":

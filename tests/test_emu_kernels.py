@@ -26,3 +26,33 @@ def test_emulated_kernels_match_port(emu_bin, args):
     r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "IDENTICAL" in r.stdout
+
+
+TAG_SCRIPT = r"""
+import json, os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import lame_b200
+from conftest import make_signal
+lame_b200._lib = lame_b200.load_library(os.path.join({root!r}, "tests", "emu", "liblamegpu_emu.so"))   # test-only build of the same sources
+gold = os.path.join({root!r}, "tests", "golden")
+for name, m in sorted(json.load(open(os.path.join(gold, "manifest_tag.json"))).items()):
+    x = make_signal(m["signal"], m["frames"] * 1152)
+    e = lame_b200.Encoder(m["samplerate"], 2, m["brate"], m["mode"] if m["mode"] >= 0 else lame_b200.NOT_SET, m["quality"], write_tag=True)
+    mp3 = b""
+    for pos in range(0, x.shape[1], 4000):
+        mp3 += e.encode(x[0, pos:pos + 4000], x[1, pos:pos + 4000])
+    mp3 += e.flush()
+    tag = e.lametag_frame()
+    e.close()
+    assert mp3 == open(os.path.join(gold, name + ".mp3"), "rb").read(), name
+    assert tag == open(os.path.join(gold, name + ".tagframe"), "rb").read(), name
+print("TAG IDENTICAL")
+"""
+
+
+def test_emulated_info_tag_matches_reference_golden(emu_bin):
+    """lame_set_bWriteVbrTag(1) (the reference's default): stream with the placeholder frame + lame_get_lametag_frame,
+    byte for byte against vectors generated from the unmodified reference (tests/golden/make_golden.py)"""
+    import sys
+    r = subprocess.run([sys.executable, "-c", TAG_SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "TAG IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -84,6 +84,32 @@ def test_lame_api_handle_matches_oracle(lib, oracle_mod):
     assert out == oracle_bytes(oracle_mod, x)
 
 
+def test_info_tag_default_settings(lib, oracle_mod):
+    """bWriteVbrTag = 1 is the reference's default: placeholder frame ahead of the audio and the finished Info tag frame
+    (VbrTag.c) - against the committed reference vectors and, where its .so travelled, the reference itself"""
+    tags = json.load(open(os.path.join(GOLD, "manifest_tag.json")))
+    for name, m in sorted(tags.items()):
+        x = make_signal(m["signal"], m["frames"] * 1152)
+        e = lib.Encoder(m["samplerate"], 2, m["brate"], m["mode"] if m["mode"] >= 0 else lib.NOT_SET, m["quality"], write_tag=True)
+        mp3 = b""
+        for pos in range(0, x.shape[1], 4000):
+            mp3 += e.encode(x[0, pos:pos + 4000], x[1, pos:pos + 4000])
+        mp3 += e.flush()
+        tag = e.lametag_frame()
+        e.close()
+        assert mp3 == open(os.path.join(GOLD, name + ".mp3"), "rb").read(), name
+        assert tag == open(os.path.join(GOLD, name + ".tagframe"), "rb").read(), name
+    if oracle_mod.have_ref():
+        x = make_signal("noise", 450 * 1152, seed=77)            # > 400 frames: the seek table is decimated (VbrTag.c:140)
+        e = lib.Encoder(44100, 2, 160, lib.NOT_SET, 5, write_tag=True)
+        r = oracle_mod.RefEncoder(44100, 2, 160, 4, 5, write_tag=True)
+        a = e.encode(x[0], x[1]) + e.flush()
+        b = r.encode(x[0], x[1]) + r.flush()
+        assert a == b and e.lametag_frame() == r.lametag_frame()
+        e.close()
+        r.close()
+
+
 def test_edge_cases(lib, oracle_mod):
     # fewer samples than one frame, then flush: the encoder delay padding still yields complete frames
     for n in (0, 1, 575, 1151, 1376, 1377):
@@ -135,6 +161,36 @@ def test_full_size_config_properties(lib, oracle_mod):
     assert len(sizes) == 1                               # CBR: identical length for every stream
     for s in list(range(0, S, 37)) + [S - 1]:
         assert a[s] + b[s] == oracle_bytes(oracle_mod, pcm[s]), s
+
+
+def test_config2_cbr320_joint_stereo_full_size(lib, oracle_mod):
+    """BASELINE configs[2] at full size: 65 536 frames = 2048 streams x 32 frames of the sine + noise mix, CBR 320 kbps
+    joint stereo (escape Huffman tables, the masking_lower feedback of SURVEY section 7).  Every stream structurally,
+    a sample of streams byte for byte against the oracle."""
+    S, F = 2048, 32
+    n = F * 1152
+    t = np.arange(n) / 44100.0
+    base_l = 8000 * np.sin(2 * np.pi * 440 * t) + 4000 * np.sin(2 * np.pi * 3300 * t)
+    base_r = 8000 * np.sin(2 * np.pi * 554.37 * t) + 3000 * np.sin(2 * np.pi * 7000 * t)
+    rng = np.random.default_rng(2024)
+    noise = rng.integers(-1000, 1001, size=(S, 2, n))
+    pcm = np.rint(noise + np.stack([base_l, base_r])[None]).astype(np.int16)
+    enc = lib.BatchEncoder(S, 44100, 2, 320, 1, -1, frames_per_launch=F)
+    n1, a = enc.encode(pcm)
+    n2, b = enc.flush()
+    enc.close()
+    assert n1 + n2 == S * (F + 1)
+    for s in range(S):
+        mp3 = a[s] + b[s]
+        pos, nfr = 0, 0
+        while pos < len(mp3):
+            assert mp3[pos] == 0xFF and mp3[pos + 1] == 0xFB and (mp3[pos + 2] >> 4) == 14, (s, pos)     # 320 kbps
+            assert (mp3[pos + 3] >> 6) == 1                                                              # joint stereo
+            pos += 1044 + ((mp3[pos + 2] >> 1) & 1)
+            nfr += 1
+        assert pos == len(mp3) and nfr == F + 1, s
+    for s in list(range(0, S, 293)) + [S - 1]:
+        assert a[s] + b[s] == oracle_bytes(oracle_mod, pcm[s], 44100, 320, 1, -1), s
 
 
 def test_c_harness_ragged_streams():
