@@ -60,6 +60,13 @@ def load_library(path=None):
         "lame_encode_buffer_ieee_float": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
         "lame_encode_flush": (c_int, [c_void_p, c_void_p, c_int]),
         "lame_close": (c_int, [c_void_p]),
+        "lame_encode_buffer_float": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_interleaved_ieee_float": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_ieee_double": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_interleaved_ieee_double": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_long": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_long2": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
+        "lame_encode_buffer_int": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
         "lame_get_lametag_frame": (ctypes.c_size_t, [c_void_p, c_void_p, ctypes.c_size_t]),
         "get_lame_short_version": (c_char_p, []),
         "lamegpu_batch_open": (c_void_p, [c_int] * 8),
@@ -92,7 +99,9 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_get_lametag_frame", "get_lame_short_version", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
+    "lame_close", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
+    "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
+    "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
     "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
     "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_batch_d2h_bytes",

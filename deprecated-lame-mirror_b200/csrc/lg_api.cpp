@@ -279,8 +279,10 @@ struct lamegpu_batch {
         if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;     /* lame.c:1735 */
         x.mf_samples_to_encode += n;
     }
-    /* lame.c:1786 lame_copy_inbuffer for non-int16 sample types: s = normalisation factor */
-    void feedf(int s, const float *l, const float *r, int n, float scale)
+    /* lame.c:1786 lame_copy_inbuffer for the sample types other than int16: T = element type, jump = 1 or 2 (interleaved),
+     * scale = the entry point's normalisation factor.  Same operation order as COPY_AND_TRANSFORM: the sample is converted
+     * to float first, the factor is folded into the 2x2 matrix in float. */
+    template <class T> void feedT(int s, const T *l, const T *r, int n, int jump, float scale)
     {
         Stream &x = st[s];
         if (n <= 0) return;
@@ -288,14 +290,17 @@ struct lamegpu_batch {
         x.to_float(&cfg);
         float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
         float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
+        size_t const at = x.pcmf[0].size();
+        x.pcmf[0].resize(at + n); x.pcmf[1].resize(at + n);
         for (int i = 0; i < n; i++) {
-            float const xl = l[i], xr = r[i];
-            x.pcmf[0].push_back(xl * m00 + xr * m01);
-            x.pcmf[1].push_back(xl * m10 + xr * m11);
+            float const xl = (float) l[(size_t) i * jump], xr = (float) r[(size_t) i * jump];
+            x.pcmf[0][at + i] = xl * m00 + xr * m01;
+            x.pcmf[1][at + i] = xl * m10 + xr * m11;
         }
         if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;
         x.mf_samples_to_encode += n;
     }
+    void feedf(int s, const float *l, const float *r, int n, float scale) { feedT<float>(s, l, r, n, 1, scale); }
     /* lame.c:2042 lame_encode_flush: how many zero samples stream s still needs */
     void pad_for_flush(int s)
     {
@@ -586,14 +591,51 @@ int lame_encode_buffer_interleaved(lame_global_flags *g, short int pcm[], int ns
     for (int i = 0; i < nsamples; i++) { l[i] = pcm[2 * i]; r[i] = pcm[2 * i + 1]; }
     return lame_encode_buffer(g, l.data(), r.data(), nsamples, mp3buf, mp3buf_size);
 }
-int lame_encode_buffer_ieee_float(lame_t g, const float l[], const float r[], const int nsamples, unsigned char *mp3buf, const int mp3buf_size)
+/* lame.c:1839 lame_encode_buffer_template for every sample type but int16 */
+extern "C++" {
+template <class T> static int handle_encode_T(lame_global_flags *g, const T *l, const T *r, int nsamples, int jump, float norm, unsigned char *mp3buf, int mp3buf_size)
 {
     if (!ok(g) || !g->initialised) return -3;
     if (nsamples == 0) return 0;
     if (!l || (g->num_channels > 1 && !r)) return 0;
-    g->b->feedf(0, l, g->num_channels > 1 ? r : l, nsamples, 32767.0f);  /* lame.c:1911 */
+    g->b->feedT<T>(0, l, g->num_channels > 1 ? r : l, nsamples, jump, norm);
     if (g->b->pump() < 0) return -2;
     return handle_take(g, mp3buf, mp3buf_size);
+}
+}
+int lame_encode_buffer_float(lame_global_flags *g, const float l[], const float r[], const int n, unsigned char *mp3buf, const int size)
+{
+    return handle_encode_T<float>(g, l, r, n, 1, 1.0f, mp3buf, size);                      /* +/- 32768 full scale, lame.c:1884 */
+}
+int lame_encode_buffer_ieee_float(lame_t g, const float l[], const float r[], const int n, unsigned char *mp3buf, const int size)
+{
+    return handle_encode_T<float>(g, l, r, n, 1, 32767.0f, mp3buf, size);                  /* +/- 1.0 full scale, lame.c:1895 */
+}
+int lame_encode_buffer_interleaved_ieee_float(lame_t g, const float pcm[], const int n, unsigned char *mp3buf, const int size)
+{
+    return handle_encode_T<float>(g, pcm, pcm ? pcm + 1 : pcm, n, 2, 32767.0f, mp3buf, size);
+}
+int lame_encode_buffer_ieee_double(lame_t g, const double l[], const double r[], const int n, unsigned char *mp3buf, const int size)
+{
+    return handle_encode_T<double>(g, l, r, n, 1, 32767.0f, mp3buf, size);
+}
+int lame_encode_buffer_interleaved_ieee_double(lame_t g, const double pcm[], const int n, unsigned char *mp3buf, const int size)
+{
+    return handle_encode_T<double>(g, pcm, pcm ? pcm + 1 : pcm, n, 2, 32767.0f, mp3buf, size);
+}
+int lame_encode_buffer_int(lame_global_flags *g, const int l[], const int r[], const int n, unsigned char *mp3buf, const int size)
+{
+    float const norm = (float) (1.0 / (1L << (8 * sizeof(int) - 16)));                     /* +/- MAX_INT full scale, lame.c:1938 */
+    return handle_encode_T<int>(g, l, r, n, 1, norm, mp3buf, size);
+}
+int lame_encode_buffer_long2(lame_global_flags *g, const long l[], const long r[], const int n, unsigned char *mp3buf, const int size)
+{
+    float const norm = (float) (1.0 / (1L << (8 * sizeof(long) - 16)));                    /* +/- MAX_LONG full scale, lame.c:1949 */
+    return handle_encode_T<long>(g, l, r, n, 1, norm, mp3buf, size);
+}
+int lame_encode_buffer_long(lame_global_flags *g, const long l[], const long r[], const int n, unsigned char *mp3buf, const int size)
+{
+    return handle_encode_T<long>(g, l, r, n, 1, 1.0f, mp3buf, size);                       /* +/- 32768 full scale, lame.c:1960 */
 }
 int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
 {

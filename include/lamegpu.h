@@ -57,6 +57,21 @@ int  lame_encode_buffer_interleaved(lame_global_flags *, short int pcm[], int nu
                                     unsigned char *mp3buf, int mp3buf_size);         /* lame.h:730 */
 int  lame_encode_buffer_ieee_float(lame_t, const float pcm_l[], const float pcm_r[], const int nsamples,
                                    unsigned char *mp3buf, const int mp3buf_size);    /* lame.h:758  +/-1.0 full scale */
+/* the other sample types of the same entry point (lame.c:1839 lame_encode_buffer_template) */
+int  lame_encode_buffer_float(lame_global_flags *, const float pcm_l[], const float pcm_r[], const int nsamples,
+                              unsigned char *mp3buf, const int mp3buf_size);         /* lame.h:746  +/-32768 full scale */
+int  lame_encode_buffer_interleaved_ieee_float(lame_t, const float pcm[], const int nsamples,
+                                   unsigned char *mp3buf, const int mp3buf_size);    /* lame.h:765 */
+int  lame_encode_buffer_ieee_double(lame_t, const double pcm_l[], const double pcm_r[], const int nsamples,
+                                    unsigned char *mp3buf, const int mp3buf_size);   /* lame.h:776 */
+int  lame_encode_buffer_interleaved_ieee_double(lame_t, const double pcm[], const int nsamples,
+                                    unsigned char *mp3buf, const int mp3buf_size);   /* lame.h:783 */
+int  lame_encode_buffer_long(lame_global_flags *, const long pcm_l[], const long pcm_r[], const int nsamples,
+                             unsigned char *mp3buf, const int mp3buf_size);          /* lame.h:799  +/-32768 full scale */
+int  lame_encode_buffer_long2(lame_global_flags *, const long pcm_l[], const long pcm_r[], const int nsamples,
+                              unsigned char *mp3buf, const int mp3buf_size);         /* lame.h:813  +/-MAX_LONG full scale */
+int  lame_encode_buffer_int(lame_global_flags *, const int pcm_l[], const int pcm_r[], const int nsamples,
+                            unsigned char *mp3buf, const int mp3buf_size);           /* lame.h:831  +/-MAX_INT full scale */
 int  lame_encode_flush(lame_global_flags *, unsigned char *mp3buf, int size);        /* lame.h:856 */
 /* Info tag (CBR): lame_set_bWriteVbrTag(1) - the reference's default - puts the all-zero placeholder frame ahead of
  * the audio; after lame_encode_flush this returns the finished tag frame to be written at offset 0 (VbrTag.c:900) */

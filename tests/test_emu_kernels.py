@@ -56,3 +56,13 @@ def test_emulated_info_tag_matches_reference_golden(emu_bin):
     import sys
     r = subprocess.run([sys.executable, "-c", TAG_SCRIPT.format(root=ROOT)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "TAG IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_emulated_sample_type_entry_points(emu_bin, oracle_mod):
+    """lame_encode_buffer_float/_ieee_float/_ieee_double/_int/_long/_long2/_interleaved* against libmp3lame itself"""
+    import sys
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build (oracle/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sample_types_check.py"), os.path.join(ROOT, "tests", "emu", "liblamegpu_emu.so")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "SAMPLE TYPES IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

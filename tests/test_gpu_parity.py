@@ -110,6 +110,15 @@ def test_info_tag_default_settings(lib, oracle_mod):
         r.close()
 
 
+def test_sample_type_entry_points(lib, oracle_mod):
+    """all nine lame_encode_buffer_* variants (lame.h:715-838) against libmp3lame itself"""
+    import sys
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sample_types_check.py"), lib.LIB_PATH], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SAMPLE TYPES IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_edge_cases(lib, oracle_mod):
     # fewer samples than one frame, then flush: the encoder delay padding still yields complete frames
     for n in (0, 1, 575, 1151, 1376, 1377):
