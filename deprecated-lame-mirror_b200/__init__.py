@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblamegpu.so")
 
 STEREO, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET = 0, 1, 2, 3, 4
-VBR_OFF = 0
+VBR_OFF, VBR_ABR = 0, 3            # lame.h:94 vbr_mode
 
 _lib = None
 
@@ -51,6 +51,8 @@ def load_library(path=None):
         "lame_set_quality": (c_int, [c_void_p, c_int]), "lame_get_quality": (c_int, [c_void_p]),
         "lame_set_mode": (c_int, [c_void_p, c_int]), "lame_get_mode": (c_int, [c_void_p]),
         "lame_set_VBR": (c_int, [c_void_p, c_int]), "lame_get_VBR": (c_int, [c_void_p]),
+        "lame_set_VBR_mean_bitrate_kbps": (c_int, [c_void_p, c_int]), "lame_get_VBR_mean_bitrate_kbps": (c_int, [c_void_p]),
+        "lamegpu_batch_open_ex": (c_void_p, [c_int] * 9),
         "lame_set_bWriteVbrTag": (c_int, [c_void_p, c_int]), "lame_get_bWriteVbrTag": (c_int, [c_void_p]),
         "lame_init_params": (c_int, [c_void_p]),
         "lame_get_framesize": (c_int, [c_void_p]), "lame_get_frameNum": (c_int, [c_void_p]),
@@ -99,7 +101,7 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
+    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lamegpu_batch_open_ex", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
@@ -116,7 +118,7 @@ def _as_i16(a):
 class Encoder:
     """One stream through the libmp3lame-compatible entry points (same semantics and error codes)."""
 
-    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1, write_tag=False):
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1, write_tag=False, vbr=VBR_OFF):
         self._lib = load_library()
         self._h = self._lib.lame_init()
         if not self._h:
@@ -124,7 +126,11 @@ class Encoder:
         L = self._lib
         L.lame_set_in_samplerate(self._h, samplerate)
         L.lame_set_num_channels(self._h, channels)
-        if brate:
+        if vbr == VBR_ABR:
+            L.lame_set_VBR(self._h, VBR_ABR)
+            if brate:
+                L.lame_set_VBR_mean_bitrate_kbps(self._h, brate)
+        elif brate:
             L.lame_set_brate(self._h, brate)
         if mode != NOT_SET:
             L.lame_set_mode(self._h, mode)
@@ -178,11 +184,11 @@ class BatchEncoder:
     """`nstreams` independent streams with one configuration, encoded together on one GPU."""
 
     def __init__(self, nstreams, samplerate=44100, channels=2, brate=128, mode=-1, quality=-1,
-                 frames_per_launch=8, device=0):
+                 frames_per_launch=8, device=0, vbr=VBR_OFF):
         self._lib = load_library()
         self.nstreams, self.frames_per_launch = int(nstreams), int(frames_per_launch)
-        self._h = self._lib.lamegpu_batch_open(samplerate, channels, brate, mode, quality, self.nstreams,
-                                               self.frames_per_launch, device)
+        self._h = self._lib.lamegpu_batch_open_ex(samplerate, channels, brate, mode, quality, vbr, self.nstreams,
+                                                  self.frames_per_launch, device)
         if not self._h:
             raise LameGpuError("lamegpu_batch_open failed (unsupported configuration, no CUDA device, or out of memory)")
         self._nbytes = np.zeros(self.nstreams, dtype=np.int32)

@@ -34,7 +34,7 @@ struct Stream {
     long tbase = -LG_PCM_HIST;         /* timeline index of element 0 */
     long frames_done = 0;
     long mf_samples_to_encode = 576 + 1152;   /* ENCDELAY + POSTDELAY, lame.c:2299 */
-    int  last_padding = 0;
+    int  last_padding = 0, last_bitrate_index = 0;
     LgBitWriter bw;
     std::vector<unsigned char> out;    /* packed bytes not yet handed to the caller */
     /* Info tag bookkeeping of one lame_t (VbrTag.c): the seek table of AddVbrFrame (:196), the byte count and music
@@ -242,7 +242,8 @@ struct lamegpu_batch {
                     const LgFrameOut *fr = fo + (size_t) s * F + f;
                     lg_merge_frame(&x.bw, &cfg, fr, hdr + ((size_t) s * F + f) * LG_HDR_STRIDE, pay + (size_t) s * pay_stride + fr->pay_off);
                     x.last_padding = fr->padding;
-                    if (x.tag.on) { tag_add_frame(x.tag, cfg.brate); x.tag.mode_ext = fr->mode_ext; }
+                    x.last_bitrate_index = fr->bitrate_index;
+                    if (x.tag.on) { tag_add_frame(x.tag, cfg.bitrate_kbps[fr->bitrate_index]); x.tag.mode_ext = fr->mode_ext; }
                 }
                 x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
                 x.bw.buf.clear();
@@ -329,13 +330,13 @@ struct lamegpu_batch {
 
 extern "C" {
 
-lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int mode, int quality, int nstreams, int frames_per_launch, int device)
+lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr, int nstreams, int frames_per_launch, int device)
 {
     lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
     if (!b) return NULL;
-    if (lg_setup(&b->cfg, samplerate, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality) != 0) {
-        fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d, channels %d, brate %d, mode %d, quality %d)\n",
-                samplerate, channels, brate, mode, quality);
+    if (lg_setup(&b->cfg, samplerate, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr) != 0) {
+        fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d, channels %d, brate %d, mode %d, quality %d, vbr %d)\n",
+                samplerate, channels, brate, mode, quality, vbr);
         delete b;
         return NULL;
     }
@@ -346,8 +347,13 @@ lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int m
     b->nthreads = (int) std::max(1u, std::min(hw ? hw : 1u, 64u));
     if (const char *e = getenv("LAMEGPU_THREADS")) b->nthreads = std::max(1, atoi(e));
     b->st.resize(nstreams);
-    for (auto &s : b->st) s.init();
+    for (auto &s : b->st) { s.init(); s.last_bitrate_index = b->cfg.bitrate_index; }
     return b;
+}
+
+lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int mode, int quality, int nstreams, int frames_per_launch, int device)
+{
+    return lamegpu_batch_open_ex(samplerate, channels, brate, mode, quality, 0 /* vbr_off */, nstreams, frames_per_launch, device);
 }
 
 void lamegpu_batch_close(lamegpu_batch *b)
@@ -384,7 +390,7 @@ long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int 
         Stream &x = b->st[s];
         if (live[s]) {
             x.mf_samples_to_encode = 0;
-            lg_pack_flush(&x.bw, &b->cfg, x.last_padding);
+            lg_pack_flush(&x.bw, &b->cfg, x.last_bitrate_index, x.last_padding);
             x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
             x.bw.buf.clear();
         }
@@ -466,7 +472,7 @@ size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }
 
 struct lame_global_struct {
     unsigned class_id;
-    int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag;
+    int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag, mean_brate;
     MPEG_mode mode;
     vbr_mode VBR;
     int launch_frames;
@@ -479,7 +485,10 @@ static void tag_frame_header(const LgDevCfg *c, int mode_ext, unsigned char *buf
 {
     buffer[0] = 0xff;
     buffer[1] = (unsigned char) (0xf0 | 0x0a | (c->error_protection ? 0 : 1));
-    buffer[2] = (unsigned char) ((16 * c->bitrate_index) | ((c->samplerate_index << 2) & 0x0c) | (c->extension & 1));
+    /* CBR: the stream's own bitrate; otherwise XING_BITRATE1 = 128 kbps (VbrTag.c:285-306) */
+    int bidx = c->bitrate_index;
+    if (c->vbr != 0) for (bidx = 1; bidx < 15 && c->bitrate_kbps[bidx] != 128; bidx++) { }
+    buffer[2] = (unsigned char) ((16 * bidx) | ((c->samplerate_index << 2) & 0x0c) | (c->extension & 1));
     buffer[3] = (unsigned char) ((c->mode << 6) | ((mode_ext & 3) << 4) | ((c->copyright & 1) << 3) | ((c->original & 1) << 2) | (c->emphasis & 3));
 }
 
@@ -491,7 +500,8 @@ static void tag_init(lamegpu_batch *b)
 {
     Stream &x = b->st[0];
     const LgDevCfg *c = &b->cfg;
-    int const total = ((c->version + 1) * 72000 * c->brate) / c->samplerate;
+    int const kbps_header = (c->vbr == 0) ? c->brate : 128;         /* VbrTag.c:517-529 */
+    int const total = ((c->version + 1) * 72000 * kbps_header) / c->samplerate;
     if (total < c->sideinfo_len + LG_LAMEHEADERSIZE || total > 2880) return;      /* "disable tag, it wont fit" */
     x.tag.on = true;
     x.tag.frame_size = total;
@@ -513,7 +523,7 @@ lame_global_flags *lame_init(void)
     if (!g) return NULL;
     g->class_id = LAME_ID;
     g->num_channels = 2; g->samplerate_in = 44100; g->samplerate_out = 0; g->brate = 0; g->quality = -1;
-    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16;
+    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128;
     if (const char *e = getenv("LAMEGPU_HANDLE_FRAMES")) g->launch_frames = std::max(1, atoi(e));
     return g;
 }
@@ -532,6 +542,8 @@ int lame_set_mode(lame_global_flags *g, MPEG_mode m) { if (!ok(g) || (int) m < 0
 MPEG_mode lame_get_mode(const lame_global_flags *g) { return ok(g) ? g->mode : NOT_SET; }
 int lame_set_VBR(lame_global_flags *g, vbr_mode m) { if (!ok(g) || (int) m < 0 || m >= vbr_max_indicator) return -1; g->VBR = m; return 0; }
 vbr_mode lame_get_VBR(const lame_global_flags *g) { return ok(g) ? g->VBR : vbr_off; }
+int lame_set_VBR_mean_bitrate_kbps(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->mean_brate = v; return 0; }     /* set_get.c:1241 */
+int lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *g) { return ok(g) ? g->mean_brate : 0; }
 int lame_set_bWriteVbrTag(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->write_lame_tag = v; return 0; }
 int lame_get_bWriteVbrTag(const lame_global_flags *g) { return ok(g) ? g->write_lame_tag : 0; }
 const char *get_lame_short_version(void) { return "3.99.5"; }
@@ -539,13 +551,15 @@ const char *get_lame_short_version(void) { return "3.99.5"; }
 int lame_init_params(lame_global_flags *g)
 {
     if (!ok(g)) return -1;
-    if (g->VBR != vbr_off) { fprintf(stderr, "lamegpu: only CBR (vbr_off) is implemented on the GPU path\n"); return -1; }
+    if (g->VBR != vbr_off && g->VBR != vbr_abr) { fprintf(stderr, "lamegpu: only CBR (vbr_off) and ABR (vbr_abr) are implemented on the GPU path\n"); return -1; }
     if (g->samplerate_out && g->samplerate_out != g->samplerate_in) { fprintf(stderr, "lamegpu: resampling is not implemented\n"); return -1; }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
-    g->b = lamegpu_batch_open(g->samplerate_in, g->num_channels, g->brate, g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, 1, g->launch_frames, 0);
+    g->b = lamegpu_batch_open_ex(g->samplerate_in, g->num_channels, g->VBR == vbr_abr ? g->mean_brate : g->brate, g->mode == NOT_SET ? -1 : (int) g->mode, g->quality,
+                                 g->VBR == vbr_abr ? 3 : 0, 1, g->launch_frames, 0);
     if (!g->b) return -1;
     g->samplerate_out = g->samplerate_in;
     g->brate = g->b->cfg.brate;
+    g->mean_brate = g->b->cfg.vbr_mean_kbps;
     g->quality = g->b->cfg.quality;
     g->mode = (MPEG_mode) g->b->cfg.mode;
     g->initialised = 1;
@@ -645,7 +659,7 @@ int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
     g->b->pad_for_flush(0);
     if (g->b->pump() < 0) return -2;
     x.mf_samples_to_encode = 0;
-    lg_pack_flush(&x.bw, &g->b->cfg, x.last_padding);
+    lg_pack_flush(&x.bw, &g->b->cfg, x.last_bitrate_index, x.last_padding);
     x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
     x.bw.buf.clear();
     return handle_take(g, mp3buf, size);
@@ -677,7 +691,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
         toc[i] = (unsigned char) seek_point;
     }
     unsigned n = (unsigned) c->sideinfo_len;
-    memcpy(buffer + n, "Info", 4); n += 4;
+    memcpy(buffer + n, c->vbr == 0 ? "Info" : "Xing", 4); n += 4;
     put_be32(buffer + n, 1 + 2 + 4 + 8); n += 4;            /* FRAMES_FLAG + BYTES_FLAG + TOC_FLAG + VBR_SCALE_FLAG */
     put_be32(buffer + n, (unsigned long) v.nframes); n += 4;
     unsigned long const stream_size = (unsigned long) (v.nbytes + v.frame_size);
@@ -707,17 +721,17 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     else if (c->samplerate > 48000) nSourceFreq = 3;
     else nSourceFreq = 1;
     int const bNonOptimal = (c->short_blocks == 2 /* forced */ || c->short_blocks == 3 /* dispensed */ ||
-                             (c->disable_reservoir && c->brate < 320) || c->athtype == 0 || c->samplerate <= 32000);
+                             (c->disable_reservoir && c->vbr_mean_kbps < 320) || c->athtype == 0 || c->samplerate <= 32000);
     unsigned char const nMisc = (unsigned char) (c->noise_shaping + (nStereoMode << 2) + (bNonOptimal << 5) + (nSourceFreq << 6));
     put_be32(p + k, (unsigned long) nQuality); k += 4;
     memcpy(p + k, "LAME3.99r", 9); k += 9;                  /* get_lame_tag_encoder_short_version(), version.c:148 */
-    p[k++] = 0x01;                                          /* revision 0, vbr_off -> method 1 */
+    p[k++] = (unsigned char) (c->vbr == 3 ? 0x02 : 0x01);   /* revision 0; vbr_type_translator: vbr_off -> 1, vbr_abr -> 2 */
     p[k++] = nLowpass;
     put_be32(p + k, 0); k += 4;                             /* peak signal amplitude: no ReplayGain analysis */
     put_be16(p + k, 0); k += 2;
     put_be16(p + k, 0); k += 2;
     p[k++] = nFlags;
-    p[k++] = (unsigned char) (c->brate >= 255 ? 0xFF : c->brate);
+    p[k++] = (unsigned char) (c->vbr_mean_kbps >= 255 ? 0xFF : c->vbr_mean_kbps);
     int const enc_delay = 576, enc_padding = v.enc_padding;
     p[k] = (unsigned char) (enc_delay >> 4);
     p[k + 1] = (unsigned char) ((enc_delay << 4) + (enc_padding >> 8));
@@ -725,7 +739,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     k += 3;
     p[k++] = nMisc;
     p[k++] = 0;
-    put_be16(p + k, (unsigned) c->brate); k += 2;           /* cfg->preset: apply_preset(brate) for CBR, presets.c:361 */
+    put_be16(p + k, (unsigned) c->vbr_mean_kbps); k += 2;   /* cfg->preset: apply_preset(mean bitrate), presets.c:361 */
     put_be32(p + k, stream_size); k += 4;
     put_be16(p + k, v.music_crc); k += 2;
     for (int i = 0; i < k; i++) crc = crc16_update(p[i], crc);

@@ -63,9 +63,10 @@ static void drain_ancillary(LgBitWriter *bw, const LgDevCfg *cfg, int remainingB
     }
 }
 
-static int frame_bits(const LgDevCfg *c, int padding)
+/* bitstream.c:65 getframebits for a frame's bitrate index */
+static int frame_bits(const LgDevCfg *c, int bitrate_index, int padding)
 {
-    return 8 * ((c->version + 1) * 72000 * c->brate / c->samplerate + padding);
+    return 8 * ((c->version + 1) * 72000 * c->bitrate_kbps[bitrate_index] / c->samplerate + padding);
 }
 
 /* The product path: kernel E has already formed the frame's bits.  hdr = header + side info (sideinfo_len bytes),
@@ -78,7 +79,7 @@ void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, 
     memcpy(bw->header[bw->h_ptr].buf, hdr, sl);
     int const old = bw->h_ptr;
     bw->h_ptr = (old + 1) & (LG_MAX_HEADER_BUF - 1);
-    bw->header[bw->h_ptr].write_timing = bw->header[old].write_timing + frame_bits(cfg, fo->padding);
+    bw->header[bw->h_ptr].write_timing = bw->header[old].write_timing + frame_bits(cfg, fo->bitrate_index, fo->padding);
     long n = fo->pay_bytes;
     while (n > 0) {
         long const until = bw->header[bw->w_ptr].write_timing - bw->totbit;     /* bits to the next frame start */
@@ -101,7 +102,7 @@ void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, 
     }
 }
 
-void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_padding)
+void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding)
 {
     int const first_ptr = bw->w_ptr;
     int last_ptr = bw->h_ptr - 1;
@@ -112,7 +113,7 @@ void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_padding)
         if (last_ptr < first_ptr) remaining_headers = 1 + last_ptr - first_ptr + LG_MAX_HEADER_BUF;
         flushbits -= remaining_headers * 8 * cfg->sideinfo_len;
     }
-    flushbits += frame_bits(cfg, last_padding);
+    flushbits += frame_bits(cfg, last_bitrate_index, last_padding);
     if (flushbits < 0) return;
     drain_ancillary(bw, cfg, (int) flushbits);
 }

@@ -17,4 +17,4 @@ struct LgBitWriter {
 };
 
 void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const unsigned char *hdr, const unsigned char *pay);
-void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_padding);
+void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding);

@@ -149,7 +149,8 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     e->S = nstreams; e->F = max_frames; e->device = device;
     e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
     {   /* largest frame (padded) minus its side info, per frame, plus what a full reservoir can add */
-        size_t const frame_bytes = (size_t) (cfg->version + 1) * 72000 * cfg->brate / cfg->samplerate + 1;
+        int const max_kbps = cfg->vbr ? cfg->bitrate_kbps[cfg->vbr_max_bitrate_index] : cfg->brate;
+        size_t const frame_bytes = (size_t) (cfg->version + 1) * 72000 * max_kbps / cfg->samplerate + 1;
         e->pay_stride = ((size_t) max_frames * (frame_bytes - cfg->sideinfo_len) + LG_PAY_SLACK + 15) & ~(size_t) 15;
     }
     size_t const S = nstreams, F = max_frames;

@@ -7,7 +7,7 @@
 extern "C" {
 #endif
 typedef struct lg_engine lg_engine;
-int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, int mode, int quality);
+int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 vbr_off, 3 vbr_abr */);
 lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device);
 void lg_engine_destroy(lg_engine *e);
 int  lg_engine_reset_streams(lg_engine *e, int first, int count);

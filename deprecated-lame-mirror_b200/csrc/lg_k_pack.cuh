@@ -274,7 +274,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
         lg_put(sm->hdr, so, (unsigned) c->version, 1); so += 1;
         lg_put(sm->hdr, so, 4 - 3, 2); so += 2;
         lg_put(sm->hdr, so, !c->error_protection, 1); so += 1;
-        lg_put(sm->hdr, so, (unsigned) c->bitrate_index, 4); so += 4;
+        lg_put(sm->hdr, so, (unsigned) fo->bitrate_index, 4); so += 4;
         lg_put(sm->hdr, so, (unsigned) c->samplerate_index, 2); so += 2;
         lg_put(sm->hdr, so, (unsigned) fo->padding, 1); so += 1;
         lg_put(sm->hdr, so, (unsigned) c->extension, 1); so += 1;

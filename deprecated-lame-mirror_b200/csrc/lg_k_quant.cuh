@@ -29,6 +29,7 @@ struct LgQInfo {                 /* the scalar part of the reference's gr_info (
 };
 struct LgQConst {                /* per gr.ch constants set by init_outer_loop / calc_xmin */
     int block_type, sfb_lmax, sfb_smin, psy_lmax, sfbmax, psymax, sfbdivide, max_nonzero_coeff;
+    int ath_over;                /* calc_xmin: some band's energy exceeds the ATH (ABR's analog-silence test) */
     int jn;                      /* line loops run j < jn: pairs at or above ((max_nonzero_coeff + 2) & ~1) / 2 stay zero */
 };
 struct LgNoiseRes { float max_noise; int over_count, over_SSD, bits; };
@@ -883,6 +884,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
                                              float ath_adjust_factor, int lane)
 {
     float const eps = (float) 2.2204460492503131e-016;   /* DBL_EPSILON stored in a float */
+    int over = 0;                                        /* ath_over != 0 (quantize_pvt.c:628, :715) */
     /* long bands */
     if (lane < qc.psy_lmax) {
         int const gsfb = lane;
@@ -898,6 +900,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
             en0 += x2;
             rh2 += (x2 < rh1) ? x2 : rh1;
         }
+        if (en0 > xmin) over = 1;
         if (en0 < xmin) rh3 = en0;
         else if (rh2 < xmin) rh3 = xmin;
         else rh3 = rh2;
@@ -960,6 +963,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
                     en0 += x2;
                     rh2 += (x2 < rh1) ? x2 : rh1;
                 }
+                if (en0 > tmpATH) over = 1;
                 if (en0 < tmpATH) rh3 = en0;
                 else if (rh2 < tmpATH) rh3 = tmpATH;
                 else rh3 = rh2;
@@ -980,6 +984,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
             w->l3_xmin[gsfb] = xm[0]; w->l3_xmin[gsfb + 1] = xm[1]; w->l3_xmin[gsfb + 2] = xm[2];
         }
     }
+    qc.ath_over = __any_sync(LG_FULL, over);
     __syncwarp();
 }
 
@@ -1152,9 +1157,25 @@ __device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__
 }
 
 /* ---------------------------------------------------------------- bit budget (reservoir.c, quantize_pvt.c:428/:492): lane-uniform scalar code */
-__device__ __forceinline__ int lg_frame_bits(const LgDevCfg *__restrict__ c, int padding)
+/* bitstream.c:65 getframebits for the frame's bitrate index */
+__device__ __forceinline__ int lg_frame_bits(const LgDevCfg *__restrict__ c, int bitrate_index, int padding)
 {
-    return 8 * ((c->version + 1) * 72000 * c->brate / c->samplerate + padding);
+    return 8 * ((c->version + 1) * 72000 * c->bitrate_kbps[bitrate_index] / c->samplerate + padding);
+}
+/* reservoir.c:83 ResvFrameBegin: returns fullFrameBits */
+__device__ __forceinline__ int lg_resv_frame_begin(const LgDevCfg *__restrict__ c, int bitrate_index, int padding, int resv_size, int *mean_bits, int *resv_max)
+{
+    int const frameLength = lg_frame_bits(c, bitrate_index, padding);
+    int const meanBits = (frameLength - c->sideinfo_len * 8) / c->mode_gr;
+    int const resvLimit = (8 * 256) * c->mode_gr - 8;
+    int rmax = c->buffer_constraint - frameLength;
+    if (rmax > resvLimit) rmax = resvLimit;
+    if (rmax < 0 || c->disable_reservoir) rmax = 0;
+    int full = meanBits * c->mode_gr + (resv_size < rmax ? resv_size : rmax);
+    if (full > c->buffer_constraint) full = c->buffer_constraint;
+    *mean_bits = meanBits;
+    *resv_max = rmax;
+    return full;
 }
 __device__ __forceinline__ void lg_resv_max_bits(const LgDevCfg *__restrict__ c, int resv_size, int resv_max, int mean_bits, int *targ_bits, int *extra_bits, int cbr)
 {
@@ -1232,6 +1253,56 @@ __device__ __forceinline__ int lg_drain_tail_bits(int remainingBits)
     return remainingBits;
 }
 
+/* quantize.c:1768 calc_target_bits (ABR): the four granule.channel targets of a frame from the perceptual entropies,
+ * independent of each other; only the frame's maximum depends on the reservoir */
+__device__ __forceinline__ void lg_calc_target_bits(const LgDevCfg *__restrict__ c, int resv_size, int padding, const float pe[2][2], const int bt[2][2],
+                                                    const float ms_ener_ratio[2], int mode_ext, int targ_bits[2][2], int *analog_silence_bits)
+{
+    int const nch = c->channels;
+    int mean_bits, rmax;
+    int const max_frame_bits = lg_resv_frame_begin(c, c->vbr_max_bitrate_index, padding, resv_size, &mean_bits, &rmax);
+    mean_bits = lg_frame_bits(c, 1, padding) - c->sideinfo_len * 8;
+    *analog_silence_bits = mean_bits / (c->mode_gr * nch);
+    mean_bits = c->vbr_mean_kbps * (576 * c->mode_gr) * 1000;
+    if (c->substep_shaping & 1) mean_bits = (int) (mean_bits * 1.09);
+    mean_bits /= c->samplerate;
+    mean_bits -= c->sideinfo_len * 8;
+    mean_bits /= (c->mode_gr * nch);
+    float res_factor = (float) (.93 + .07 * (11.0 - c->compression_ratio) / (11.0 - 5.5));
+    if (res_factor < .90) res_factor = (float) .90;
+    if (res_factor > 1.00) res_factor = (float) 1.00;
+    for (int gr = 0; gr < c->mode_gr; gr++) {
+        int sum = 0;
+        for (int ch = 0; ch < nch; ch++) {
+            targ_bits[gr][ch] = (int) (res_factor * mean_bits);
+            if (pe[gr][ch] > 700) {
+                int add_bits = (int) ((pe[gr][ch] - 700) / 1.4);
+                if (bt[gr][ch] == LG_SHORT) {
+                    if (add_bits < mean_bits / 2) add_bits = mean_bits / 2;
+                }
+                if (add_bits > mean_bits * 3 / 2) add_bits = mean_bits * 3 / 2;
+                else if (add_bits < 0) add_bits = 0;
+                targ_bits[gr][ch] += add_bits;
+            }
+            if (targ_bits[gr][ch] > LG_MAX_BITS_PER_CHANNEL) targ_bits[gr][ch] = LG_MAX_BITS_PER_CHANNEL;
+            sum += targ_bits[gr][ch];
+        }
+        if (sum > LG_MAX_BITS_PER_GRANULE)
+            for (int ch = 0; ch < nch; ++ch) { targ_bits[gr][ch] *= LG_MAX_BITS_PER_GRANULE; targ_bits[gr][ch] /= sum; }
+    }
+    if (mode_ext == 2)
+        for (int gr = 0; gr < c->mode_gr; gr++) lg_reduce_side(targ_bits[gr], ms_ener_ratio[gr], mean_bits * nch, LG_MAX_BITS_PER_GRANULE);
+    int totbits = 0;
+    for (int gr = 0; gr < c->mode_gr; gr++)
+        for (int ch = 0; ch < nch; ch++) {
+            if (targ_bits[gr][ch] > LG_MAX_BITS_PER_CHANNEL) targ_bits[gr][ch] = LG_MAX_BITS_PER_CHANNEL;
+            totbits += targ_bits[gr][ch];
+        }
+    if (totbits > max_frame_bits && totbits > 0)
+        for (int gr = 0; gr < c->mode_gr; gr++)
+            for (int ch = 0; ch < nch; ch++) { targ_bits[gr][ch] *= max_frame_bits; targ_bits[gr][ch] /= totbits; }
+}
+
 /* ---------------------------------------------------------------- the kernel */
 __global__ void __launch_bounds__(64)
 lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy,
@@ -1252,24 +1323,32 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
     for (int frame = 0; frame < my_frames; frame++) {
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;
-        /* reservoir.c:83 ResvFrameBegin */
-        int const frameLength = lg_frame_bits(cfg, padding);
-        int const mean_bits = (frameLength - cfg->sideinfo_len * 8) / cfg->mode_gr;
-        int resv_max = cfg->buffer_constraint - frameLength;
-        {
-            int const resvLimit = (8 * 256) * cfg->mode_gr - 8;
-            if (resv_max > resvLimit) resv_max = resvLimit;
-            if (resv_max < 0 || cfg->disable_reservoir) resv_max = 0;
+        int const abr = (cfg->vbr == 3);
+        int bitrate_index = cfg->bitrate_index;
+        int mean_bits, resv_max, analog_silence_bits = 0;
+        int targ_abr[2][2] = { { 0, 0 }, { 0, 0 } };
+        if (abr) {
+            /* quantize.c:1900 ABR_iteration_loop: all four targets up front, the frame size is chosen afterwards */
+            const LgPsyOut *P0 = psy + (size_t) stream * 2 * nframes + 2 * frame;
+            float const pe4[2][2] = { { F->pe_use[0][0], F->pe_use[0][1] }, { F->pe_use[1][0], F->pe_use[1][1] } };
+            int const bt4[2][2] = { { P0[0].block_type[0], P0[0].block_type[1] }, { P0[1].block_type[0], P0[1].block_type[1] } };
+            float const mer[2] = { F->ms_ener_ratio[0], F->ms_ener_ratio[1] };
+            lg_calc_target_bits(cfg, resv_size, padding, pe4, bt4, mer, mode_ext, targ_abr, &analog_silence_bits);
+            mean_bits = resv_max = 0;
         }
+        else (void) lg_resv_frame_begin(cfg, bitrate_index, padding, resv_size, &mean_bits, &resv_max);   /* reservoir.c:83 */
         uint8_t scfsi[4] = { 0, 0, 0, 0 };
         int frame_used = 0;
         for (int gr = 0; gr < 2; gr++) {
             int const gb = 2 * frame + gr;
             const LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
             int targ_bits[2];
-            float pe[2] = { F->pe_use[gr][0], F->pe_use[gr][1] };
-            int const max_bits = lg_on_pe(cfg, resv_size, resv_max, pe, targ_bits, mean_bits, gr);
-            if (mode_ext == 2) lg_reduce_side(targ_bits, F->ms_ener_ratio[gr], mean_bits, max_bits);
+            if (abr) { targ_bits[0] = targ_abr[gr][0]; targ_bits[1] = targ_abr[gr][1]; }
+            else {
+                float pe[2] = { F->pe_use[gr][0], F->pe_use[gr][1] };
+                int const max_bits = lg_on_pe(cfg, resv_size, resv_max, pe, targ_bits, mean_bits, gr);
+                if (mode_ext == 2) lg_reduce_side(targ_bits, F->ms_ener_ratio[gr], mean_bits, max_bits);
+            }
             int used = 0;
             if (ch < nch) {
                 LgQInfo gi;
@@ -1350,6 +1429,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                         LgQConst qx = qc;
                         lg_calc_xmin(cfg, w, qx, en, thm, F->ath_adjust_factor, lane);
                         qc.max_nonzero_coeff = qx.max_nonzero_coeff; qc.jn = qx.jn;
+                        if (abr && qx.ath_over == 0) targ_bits[ch] = analog_silence_bits;     /* quantize.c:1951 analog silence */
                     }
                     lg_outer_loop(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, lane);
                 }
@@ -1398,6 +1478,12 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
         }
         /* reservoir.c:239 ResvFrameEnd + the main_data_begin recurrence of format_bitstream (bitstream.c:937) */
         {
+            if (abr) {
+                /* the smallest frame that brings the reservoir back to a non-negative size (quantize.c:1962-1967) */
+                for (bitrate_index = cfg->vbr_min_bitrate_index; bitrate_index <= cfg->vbr_max_bitrate_index; bitrate_index++)
+                    if (lg_resv_frame_begin(cfg, bitrate_index, padding, resv_size, &mean_bits, &resv_max) >= 0) break;
+                if (bitrate_index > cfg->vbr_max_bitrate_index) lg_runaway();
+            }
             int stuffingBits = 0, over_bits, drain_pre = 0, drain_post = 0;
             resv_size += mean_bits * cfg->mode_gr;
             if ((over_bits = resv_size % 8) != 0) stuffingBits += over_bits;
@@ -1423,7 +1509,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                     fo->main_data_begin = mdb_header; fo->drain_pre = drain_pre; fo->drain_post = drain_post;
                     fo->padding = padding; fo->mode_ext = mode_ext; fo->resv_size = resv_size;
                     fo->pay_off = pay_off; fo->pay_bytes = pay_bits >> 3;
-                    fo->anc_pre = (uint8_t) anc_pre; fo->anc_post = (uint8_t) anc_flag; fo->pad_[0] = fo->pad_[1] = 0; fo->pad2_ = 0;
+                    fo->anc_pre = (uint8_t) anc_pre; fo->anc_post = (uint8_t) anc_flag; fo->pad_[0] = fo->pad_[1] = 0; fo->bitrate_index = bitrate_index;
                 }
                 if (ch < nch) for (int i = 0; i < 4; i++) fo->scfsi[ch][i] = scfsi[i];
                 else for (int i = 0; i < 4; i++) fo->scfsi[ch][i] = 0;

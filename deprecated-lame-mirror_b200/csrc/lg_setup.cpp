@@ -515,7 +515,7 @@ static int setup_quality(LgDevCfg *c, int quality)
 
 static void finish_device_tables(LgDevCfg *c);
 
-extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, int mode, int quality)
+extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, int mode, int quality, int vbr)
 {
     /* presets.c:241 abr_switch_map, the columns the CBR path reads */
     static const struct { int kbps, safejoint; float nsmsfix, st_lrm, st_s, scale, masking_adj, ath_lower, ath_curve, interch; int sfscale; }
@@ -544,14 +544,24 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     if (channels == 1) mode = LG_MONO;                                 /* lame.c:597 */
     if (mode == LG_MONO) c->channels = 1;
     c->force_ms = 0;
-    if (brate == 0) {                                                  /* lame.c:623-644 */
-        brate = samplerate * 16 * c->channels / (1.e3 * 11.025f);
+    if (vbr != 0 && vbr != 3) return -1;                              /* vbr_off and vbr_abr only (lame.h:94) */
+    if (vbr == 3) {
+        /* ABR keeps the requested mean bitrate as it is (lame_set_VBR_mean_bitrate_kbps, default 128), clamped for
+         * MPEG-1 rates (lame.c:655-658 and :1088-1093 with the default index range 1..14) */
+        if (brate == 0) brate = 128;
+        if (brate < 32) brate = 32;
+        if (brate > 320) brate = 320;
     }
-    /* util.c:320 FindNearestBitrate on the MPEG-1 row */
-    best = LGT_BITRATE[16 + 1];
-    for (i = 2; i <= 14; i++)
-        if (abs(LGT_BITRATE[16 + i] - brate) < abs(best - brate)) best = LGT_BITRATE[16 + i];
-    brate = best;
+    else {
+        if (brate == 0) {                                              /* lame.c:623-644 */
+            brate = samplerate * 16 * c->channels / (1.e3 * 11.025f);
+        }
+        /* util.c:320 FindNearestBitrate on the MPEG-1 row */
+        best = LGT_BITRATE[16 + 1];
+        for (i = 2; i <= 14; i++)
+            if (abs(LGT_BITRATE[16 + i] - brate) < abs(best - brate)) best = LGT_BITRATE[16 + i];
+        brate = best;
+    }
     /* lame.c:704-762: low-pass from the bitrate */
     lowpass = lowpass_map[nearest_full_index(brate)];
     if (mode == LG_MONO) lowpass *= 1.5;
@@ -582,9 +592,18 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     c->samplerate_index = sr_index;
     c->version = version;
     c->brate = brate;
-    c->bitrate_index = -1;
-    for (i = 0; i <= 14; i++) if (LGT_BITRATE[16 + i] == brate) { c->bitrate_index = i; break; }
-    if (c->bitrate_index <= 0) return -1;
+    c->vbr = vbr;
+    c->vbr_mean_kbps = brate;
+    c->vbr_min_bitrate_index = 1;                                      /* lame.c:1067-1068 */
+    c->vbr_max_bitrate_index = 14;
+    c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * brate);   /* lame.c:778-784 */
+    for (i = 0; i < 16; i++) c->bitrate_kbps[i] = LGT_BITRATE[16 * version + i];
+    if (vbr == 3) c->bitrate_index = 1;                                /* lame.c:921 */
+    else {
+        c->bitrate_index = -1;
+        for (i = 0; i <= 14; i++) if (LGT_BITRATE[16 + i] == brate) { c->bitrate_index = i; break; }
+        if (c->bitrate_index <= 0) return -1;
+    }
     j = sr_index + 3 * version;
     for (i = 0; i < 23; i++) c->sfb_l[i] = LGT_SFB_LONG[j * 23 + i];
     for (i = 0; i < 7; i++) c->psfb21[i] = c->sfb_l[21] + i * ((c->sfb_l[22] - c->sfb_l[21]) / 6);
@@ -643,7 +662,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
         }
         memcpy(c->pcm_transform, m, sizeof m);
     }
-    c->frac_spf = ((version + 1) * 72000L * brate) % samplerate;
+    c->frac_spf = (vbr == 0) ? ((version + 1) * 72000L * brate) % samplerate : 0;      /* lame.c:1245 */
     setup_quantizer_tables(c);
     setup_psy(c, attackthre, attackthre_s, 4, 0.f);
     c->buffer_constraint = 7680 * (version + 1);                       /* bitstream.c:119 MDB_MAXIMUM */

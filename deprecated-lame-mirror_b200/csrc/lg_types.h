@@ -67,6 +67,11 @@ typedef struct {
     float adjust_bass_db, adjust_alto_db, adjust_treble_db, adjust_sfb21_db;
     float ath_aa_sensitivity_p, ath_decay, ath_floor;
     float masking_lower_long, masking_lower_short;  /* (float)pow(10, mask_adjust*0.1), quantize.c:2029 */
+    /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr (lame.h:94).  ABR chooses a frame size per frame: mean bitrate, index range,
+     * the compression ratio calc_target_bits reads (quantize.c:1768) and the bitrate table row of this MPEG version */
+    int   vbr, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
+    float compression_ratio;
+    int   bitrate_kbps[16];
     int   sfb_l[23], sfb_s[14], psfb21[7], psfb12[7];
     float amp_filter[32];
     LgBands l, s, l2s;
@@ -145,7 +150,7 @@ typedef struct {
      * (bitstream.c:246-256) before and after the frame */
     int32_t pay_off, pay_bytes;
     uint8_t anc_pre, anc_post, pad_[2];
-    int32_t pad2_;
+    int32_t bitrate_index;               /* of this frame (constant for CBR, chosen per frame by ABR) */
 } LgFrameOut;
 #define LG_HDR_STRIDE 40                /* bytes reserved per frame for header + side info (sideinfo_len <= 36) */
 #define LG_PAY_SLACK 1024               /* a launch can drain at most the reservoir (511 bytes) on top of its own frames */

@@ -44,7 +44,11 @@ int  lame_get_quality(const lame_global_flags *);                               
 int  lame_set_mode(lame_global_flags *, MPEG_mode);                                  /* lame.h:270 */
 MPEG_mode lame_get_mode(const lame_global_flags *);                                  /* lame.h:271 */
 int  lame_set_VBR(lame_global_flags *, vbr_mode);                                    /* lame.h:432  only vbr_off is accepted */
-vbr_mode lame_get_VBR(const lame_global_flags *);                                    /* lame.h:433 */
+vbr_mode lame_get_VBR(const lame_global_flags *);
+int  lame_set_VBR_mean_bitrate_kbps(lame_global_flags *, int);                       /* lame.h:444  ABR mean bitrate */
+int  lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *);                      /* lame.h:445 */
+int  lame_set_VBR_mean_bitrate_kbps(lame_global_flags *, int);                       /* lame.h:447  ABR mean bitrate */
+int  lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *);                                    /* lame.h:433 */
 int  lame_set_bWriteVbrTag(lame_global_flags *, int);                                /* lame.h:240  the Info tag frame is not produced */
 int  lame_get_bWriteVbrTag(const lame_global_flags *);                               /* lame.h:241 */
 int  lame_init_params(lame_global_flags *);                                          /* lame.h:636  <0 on error/unsupported */
@@ -88,6 +92,10 @@ typedef struct lamegpu_batch lamegpu_batch;
  * GPU or allocation failure (a message goes to stderr). */
 lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int mode /* MPEG_mode or -1 */,
                                   int quality /* 0..9 or -1 */, int nstreams, int frames_per_launch, int device);
+/* same, with the rate mode: vbr = 0 (vbr_off, CBR at `brate`) or 3 (vbr_abr, `brate` is the mean bitrate of
+ * lame_set_VBR_mean_bitrate_kbps; quantize.c:1900 ABR_iteration_loop) */
+lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr,
+                                     int nstreams, int frames_per_launch, int device);
 void lamegpu_batch_close(lamegpu_batch *b);
 
 /* Feed nsamples[i] samples to stream i (pcm_l[i]/pcm_r[i]; pcm_r may be NULL for mono) and encode every

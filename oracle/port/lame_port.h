@@ -1,7 +1,7 @@
 /* oracle/port - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * A plain-C, single-threaded restatement of the LAME 3.99.5 encode hot path (MPEG-1 Layer III,
- * 32/44.1/48 kHz, CBR, stereo / joint stereo / mono, quality 0..9 without substep shaping), written
+ * 32/44.1/48 kHz, CBR and ABR, stereo / joint stereo / mono, quality 0..9 without substep shaping), written
  * from the algorithm's description in the reference sources, each function citing the reference
  * file:line it follows.  Its only job is to be the CPU checker for the CUDA path (tests/, smoke(),
  * bench.py cpu_baseline).  Parity of this port is PINNED: tests/test_port_vs_ref.py compares its MP3
@@ -59,6 +59,10 @@ typedef struct {
     float mask_adjust, mask_adjust_short, pcm_transform[2][2], lowpass1, lowpass2, highpass1, highpass2;
     float adjust_bass_db, adjust_alto_db, adjust_treble_db, adjust_sfb21_db;
     float ath_aa_sensitivity_p, ath_decay, ath_floor;
+    /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr (lame.h:94 vbr_mode); ABR keeps its mean bitrate, the bitrate index range
+     * it may choose a frame size from, and the compression ratio calc_target_bits reads (quantize.c:1768) */
+    int   vbr, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
+    float compression_ratio;
     /* tables */
     int   sfb_l[23], sfb_s[14], psfb21[7], psfb12[7];
     float amp_filter[32];
@@ -109,6 +113,7 @@ typedef struct {
     float sb_sample[2][2][18][32];
     float pefirbuf[19];
     int   slot_lag, padding, mode_ext, frame_number, frame_init_done;
+    int   bitrate_index;                /* of the frame being coded (constant for CBR, chosen per frame for ABR) */
     int   resv_size, resv_max, main_data_begin, drain_pre, drain_post, scfsi[2][4];
     int   old_value[2], current_step[2];
     lp_granule tt[2][2];
@@ -125,12 +130,13 @@ typedef struct {
 
 /* API: mirrors lame_init, lame_set_xxx, lame_init_params, lame_encode_buffer, lame_encode_flush, lame_close */
 lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quality);
+lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 off, 3 abr */);
 int  lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsigned char *out, int cap);
 int  lp_flush(lp_encoder *e, unsigned char *out, int cap);
 void lp_close(lp_encoder *e);
 
 /* internals shared between the port's files */
-int   lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, int quality);
+int   lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, int quality, int vbr);
 float lp_fast_log2(const lp_config *c, float x);
 void  lp_fft_long(const lp_config *c, float x[LP_BLK], const float *buf);
 void  lp_fft_short(const lp_config *c, float x[3][LP_BLK_S], const float *buf);
@@ -138,6 +144,7 @@ int   lp_psycho(lp_encoder *e, const float *const buffer[2], int gr_out, lp_rati
                 lp_ratio masking_ms[2][2], float pe[2], float pe_ms[2], float energy[4], int blocktype_d[2]);
 void  lp_mdct_sub48(lp_encoder *e, const float *w0, const float *w1);
 void  lp_cbr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
+void  lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
 int   lp_getframebits(const lp_encoder *e);
 void  lp_format_bitstream(lp_encoder *e);
 void  lp_flush_bitstream(lp_encoder *e);

@@ -8,10 +8,16 @@
 
 lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quality)
 {
+    return lp_open_ex(samplerate, channels, brate, mode, quality, 0);
+}
+
+lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr)
+{
     lp_encoder *e = calloc(1, sizeof *e);
     int i, j, sb;
     if (!e) return NULL;
-    if (lp_setup(&e->cfg, samplerate, channels, brate, mode, quality) < 0) { free(e); return NULL; }
+    if (lp_setup(&e->cfg, samplerate, channels, brate, mode, quality, vbr) < 0) { free(e); return NULL; }
+    e->bitrate_index = e->cfg.bitrate_index;
     e->buf = calloc(1, LP_BITBUF);
     /* lame.c:2274 lame_init_internal_flags, lame.c:962, psymodel.c:1897-1922/2075 */
     e->old_value[0] = e->old_value[1] = 180;
@@ -156,7 +162,8 @@ static int encode_frame(lp_encoder *e, const float *inbuf_l, const float *inbuf_
     for (gr = 0; gr < cfg->mode_gr; gr++)
         for (ch = 0; ch < cfg->channels; ch++) pe_use[gr][ch] *= f;
     memcpy(e->last_pe, pe_use, sizeof e->last_pe);
-    lp_cbr_iteration_loop(e, pe_use, ms_ener_ratio, masking);
+    if (cfg->vbr == 3) lp_abr_iteration_loop(e, pe_use, ms_ener_ratio, masking);      /* encoder.c:520-538 */
+    else lp_cbr_iteration_loop(e, pe_use, ms_ener_ratio, masking);
     lp_format_bitstream(e);
     mp3count = lp_copy_buffer(e, out, cap);
     ++e->frame_number;

@@ -77,7 +77,7 @@ static void encode_side_info(lp_encoder *e, int bitsPerFrame)
     writeheader(e, cfg->version, 1);
     writeheader(e, 4 - 3, 2);
     writeheader(e, !cfg->error_protection, 1);
-    writeheader(e, cfg->bitrate_index, 4);
+    writeheader(e, e->bitrate_index, 4);
     writeheader(e, cfg->samplerate_index, 2);
     writeheader(e, e->padding, 1);
     writeheader(e, cfg->extension, 1);

@@ -24,7 +24,8 @@ static const uint8_t *hlen_of(int t) { return LGT_HUFF_LEN + LGT_HUFF_OFF[t]; }
 /* bitstream.c:65 getframebits */
 int lp_getframebits(const lp_encoder *e)
 {
-    return 8 * ((e->cfg.version + 1) * 72000 * e->cfg.brate / e->cfg.samplerate + e->padding);
+    /* bit_rate = bitrate_table[version][bitrate_index] of the frame being coded */
+    return 8 * ((e->cfg.version + 1) * 72000 * LGT_BITRATE[16 * e->cfg.version + e->bitrate_index] / e->cfg.samplerate + e->padding);
 }
 /* reservoir.c:83 ResvFrameBegin */
 static int resv_frame_begin(lp_encoder *e, int *mean_bits)
@@ -1123,5 +1124,103 @@ void lp_cbr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ra
             e->resv_size -= gi->part2_3_length + gi->part2_length;       /* reservoir.c:226 ResvAdjust */
         }
     }
+    resv_frame_end(e, mean_bits);
+}
+
+/* quantize.c:1768 calc_target_bits */
+static void calc_target_bits(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], int targ_bits[2][2],
+                             int *analog_silence_bits, int *max_frame_bits)
+{
+    const lp_config *cfg = &e->cfg;
+    float res_factor;
+    int gr, ch, totbits, mean_bits;
+    int const framesize = 576 * cfg->mode_gr;
+    e->bitrate_index = cfg->vbr_max_bitrate_index;
+    *max_frame_bits = resv_frame_begin(e, &mean_bits);
+    e->bitrate_index = 1;
+    mean_bits = lp_getframebits(e) - cfg->sideinfo_len * 8;
+    *analog_silence_bits = mean_bits / (cfg->mode_gr * cfg->channels);
+    mean_bits = cfg->vbr_mean_kbps * framesize * 1000;
+    if (cfg->substep_shaping & 1) mean_bits *= 1.09;
+    mean_bits /= cfg->samplerate;
+    mean_bits -= cfg->sideinfo_len * 8;
+    mean_bits /= (cfg->mode_gr * cfg->channels);
+    res_factor = .93 + .07 * (11.0 - cfg->compression_ratio) / (11.0 - 5.5);     /* double expression stored in a float */
+    if (res_factor < .90) res_factor = .90;
+    if (res_factor > 1.00) res_factor = 1.00;
+    for (gr = 0; gr < cfg->mode_gr; gr++) {
+        int sum = 0;
+        for (ch = 0; ch < cfg->channels; ch++) {
+            targ_bits[gr][ch] = res_factor * mean_bits;
+            if (pe[gr][ch] > 700) {
+                int add_bits = (pe[gr][ch] - 700) / 1.4;
+                targ_bits[gr][ch] = res_factor * mean_bits;
+                if (e->tt[gr][ch].block_type == LP_SHORT) {
+                    if (add_bits < mean_bits / 2) add_bits = mean_bits / 2;
+                }
+                if (add_bits > mean_bits * 3 / 2) add_bits = mean_bits * 3 / 2;
+                else if (add_bits < 0) add_bits = 0;
+                targ_bits[gr][ch] += add_bits;
+            }
+            if (targ_bits[gr][ch] > LP_MAX_BITS_PER_CHANNEL) targ_bits[gr][ch] = LP_MAX_BITS_PER_CHANNEL;
+            sum += targ_bits[gr][ch];
+        }
+        if (sum > LP_MAX_BITS_PER_GRANULE)
+            for (ch = 0; ch < cfg->channels; ++ch) {
+                targ_bits[gr][ch] *= LP_MAX_BITS_PER_GRANULE;
+                targ_bits[gr][ch] /= sum;
+            }
+    }
+    if (e->mode_ext == 2)
+        for (gr = 0; gr < cfg->mode_gr; gr++)
+            reduce_side(targ_bits[gr], ms_ener_ratio[gr], mean_bits * cfg->channels, LP_MAX_BITS_PER_GRANULE);
+    totbits = 0;
+    for (gr = 0; gr < cfg->mode_gr; gr++)
+        for (ch = 0; ch < cfg->channels; ch++) {
+            if (targ_bits[gr][ch] > LP_MAX_BITS_PER_CHANNEL) targ_bits[gr][ch] = LP_MAX_BITS_PER_CHANNEL;
+            totbits += targ_bits[gr][ch];
+        }
+    if (totbits > *max_frame_bits && totbits > 0)
+        for (gr = 0; gr < cfg->mode_gr; gr++)
+            for (ch = 0; ch < cfg->channels; ch++) {
+                targ_bits[gr][ch] *= *max_frame_bits;
+                targ_bits[gr][ch] /= totbits;
+            }
+}
+
+/* quantize.c:1900 ABR_iteration_loop */
+void lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2])
+{
+    const lp_config *cfg = &e->cfg;
+    float l3_xmin[LP_SFBMAX], xrpow[576];
+    int targ_bits[2][2], mean_bits = 0, max_frame_bits, analog_silence_bits, gr, ch, i;
+    calc_target_bits(e, pe, ms_ener_ratio, targ_bits, &analog_silence_bits, &max_frame_bits);
+    for (gr = 0; gr < cfg->mode_gr; gr++) {
+        if (e->mode_ext == 2)
+            for (i = 0; i < 576; ++i) {
+                float l = e->tt[gr][0].xr[i], r = e->tt[gr][1].xr[i];
+                e->tt[gr][0].xr[i] = (l + r) * (float) (SQRT2_D * 0.5);
+                e->tt[gr][1].xr[i] = (l - r) * (float) (SQRT2_D * 0.5);
+            }
+        for (ch = 0; ch < cfg->channels; ch++) {
+            lp_granule *gi = &e->tt[gr][ch];
+            float masking_lower_db;
+            if (gi->block_type != LP_SHORT) masking_lower_db = cfg->mask_adjust - 0;
+            else masking_lower_db = cfg->mask_adjust_short - 0;
+            e->masking_lower = pow(10.0, masking_lower_db * 0.1);
+            init_outer_loop(cfg, gi);
+            if (init_xrpow(gi, xrpow)) {
+                int const ath_over = calc_xmin(e, &ratio[gr][ch], gi, l3_xmin);
+                if (0 == ath_over) targ_bits[gr][ch] = analog_silence_bits;
+                (void) outer_loop(e, gi, l3_xmin, xrpow, ch, targ_bits[gr][ch]);
+            }
+            best_scalefac_store(e, gr, ch);
+            if (cfg->use_best_huffman == 1) best_huffman_divide(cfg, gi);
+            e->resv_size -= gi->part2_3_length + gi->part2_length;
+        }
+    }
+    /* the smallest frame that brings the reservoir back to a non-negative size */
+    for (e->bitrate_index = cfg->vbr_min_bitrate_index; e->bitrate_index <= cfg->vbr_max_bitrate_index; e->bitrate_index++)
+        if (resv_frame_begin(e, &mean_bits) >= 0) break;
     resv_frame_end(e, mean_bits);
 }

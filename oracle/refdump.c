@@ -28,7 +28,8 @@ void *refdump_open(int brate, int mode, int quality, int vbrmode, int vbr_q, int
     h->gfp = gfp;
     lame_set_in_samplerate(gfp, samplerate > 0 ? samplerate : 44100);
     lame_set_num_channels(gfp, nch > 0 ? nch : 2);
-    if (vbrmode > 0) { lame_set_VBR(gfp, (vbr_mode) vbrmode); lame_set_VBR_q(gfp, vbr_q); }
+    if (vbrmode == vbr_abr) { lame_set_VBR(gfp, vbr_abr); if (brate > 0) lame_set_VBR_mean_bitrate_kbps(gfp, brate); }
+    else if (vbrmode > 0) { lame_set_VBR(gfp, (vbr_mode) vbrmode); lame_set_VBR_q(gfp, vbr_q); }
     else if (brate > 0) lame_set_brate(gfp, brate);
     if (mode >= 0) lame_set_mode(gfp, (MPEG_mode) mode);
     if (quality >= 0) lame_set_quality(gfp, quality);

@@ -32,7 +32,8 @@ int main(int argc, char **argv)
           memcpy(t, R[s] + off, (n - off) * 2); memcpy(t + n - off, R[s], off * 2); memcpy(R[s], t, n * 2); free(t); }
         if (s % 4 == 3) { int z = n / 3; memset(L[s], 0, z * 2); memset(R[s], 0, z * 2); }
     }
-    b = lamegpu_batch_open(sr, 2, brate, mode, quality, S, FPL, 0);
+    int const vbr = getenv("LP_VBR") ? atoi(getenv("LP_VBR")) : 0;          /* 0 = CBR, 3 = ABR with mean bitrate `brate` */
+    b = lamegpu_batch_open_ex(sr, 2, brate, mode, quality, vbr, S, FPL, 0);
     if (!b) { printf("batch open failed\n"); return 2; }
     for (i = 0; i < n; i += chunk) {
         int c = n - i < chunk ? n - i : chunk;
@@ -49,7 +50,7 @@ int main(int argc, char **argv)
     { float ms[4]; lamegpu_batch_kernel_ms(b, ms); printf("last launch kernel ms: analysis %.3f scan %.3f mdct %.3f quant %.3f\n", ms[0], ms[1], ms[2], ms[3]); }
     lamegpu_batch_close(b);
     for (s = 0; s < S; s++) {
-        lp_encoder *e = lp_open(sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality);
+        lp_encoder *e = lp_open_ex(sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr);
         int k;
         if (!e) { printf("port open failed\n"); return 2; }
         rlen[s] = lp_encode(e, L[s], R[s], n, ref[s], cap);

@@ -33,9 +33,12 @@ CASES = [
 
 
 TAG_CASES = [
-    ("tag_noise_128", "noise", 30, 44100, 128, -1, -1),
-    ("tag_click_192_stereo", "click", 45, 44100, 192, 0, -1),
-    ("tag_sine_320_js", "sine", 20, 44100, 320, 1, -1),
+    # name, signal, frames, samplerate, brate (CBR bitrate or ABR mean), mode, quality, vbr (0 = vbr_off, 3 = vbr_abr)
+    ("tag_noise_128", "noise", 30, 44100, 128, -1, -1, 0),
+    ("tag_click_192_stereo", "click", 45, 44100, 192, 0, -1, 0),
+    ("tag_sine_320_js", "sine", 20, 44100, 320, 1, -1, 0),
+    ("tag_abr_click_128", "click", 45, 44100, 128, -1, -1, 3),
+    ("tag_abr_gap_150_stereo", "gap", 30, 44100, 150, 0, -1, 3),
 ]
 
 
@@ -59,9 +62,9 @@ def main():
     # Info tag (lame_set_bWriteVbrTag(1), the reference's default): the stream with its placeholder frame, and the
     # finished tag frame of lame_get_lametag_frame
     tags = {}
-    for name, sig, frames, sr, brate, mode, q in TAG_CASES:
+    for name, sig, frames, sr, brate, mode, q, vbr in TAG_CASES:
         x = make_signal(sig, frames * 1152)
-        r = oracle.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q, write_tag=True)
+        r = oracle.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q, write_tag=True, vbr=vbr)
         mp3 = b""
         for pos in range(0, x.shape[1], 4000):
             mp3 += r.encode(x[0, pos:pos + 4000], x[1, pos:pos + 4000])
@@ -72,7 +75,7 @@ def main():
             f.write(mp3)
         with open(os.path.join(HERE, name + ".tagframe"), "wb") as f:
             f.write(tag)
-        tags[name] = dict(signal=sig, frames=frames, samplerate=sr, brate=brate, mode=mode, quality=q, nbytes=len(mp3), tag_nbytes=len(tag),
+        tags[name] = dict(signal=sig, frames=frames, samplerate=sr, brate=brate, mode=mode, quality=q, vbr=vbr, nbytes=len(mp3), tag_nbytes=len(tag),
                           mp3_sha256=hashlib.sha256(mp3).hexdigest(), tag_sha256=hashlib.sha256(tag).hexdigest())
         print(name, len(mp3), len(tag))
     with open(os.path.join(HERE, "manifest_tag.json"), "w") as f:

@@ -28,6 +28,14 @@ def test_emulated_kernels_match_port(emu_bin, args):
     assert "IDENTICAL" in r.stdout
 
 
+@pytest.mark.parametrize("args", ["4 20 8 128 -1 -1 44100 1152", "3 16 5 192 1 -1 44100 3000", "2 12 4 256 -1 7 32000 1152"])
+def test_emulated_kernels_abr_match_port(emu_bin, args):
+    """ABR: per-frame bitrate index chosen on the device, variable frame sizes through kernel E and the host splice"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=600, env=dict(os.environ, LP_VBR="3"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout
+
+
 TAG_SCRIPT = r"""
 import json, os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
@@ -37,7 +45,8 @@ lame_b200._lib = lame_b200.load_library(os.path.join({root!r}, "tests", "emu", "
 gold = os.path.join({root!r}, "tests", "golden")
 for name, m in sorted(json.load(open(os.path.join(gold, "manifest_tag.json"))).items()):
     x = make_signal(m["signal"], m["frames"] * 1152)
-    e = lame_b200.Encoder(m["samplerate"], 2, m["brate"], m["mode"] if m["mode"] >= 0 else lame_b200.NOT_SET, m["quality"], write_tag=True)
+    e = lame_b200.Encoder(m["samplerate"], 2, m["brate"], m["mode"] if m["mode"] >= 0 else lame_b200.NOT_SET, m["quality"], write_tag=True,
+                          vbr=m.get("vbr", 0))
     mp3 = b""
     for pos in range(0, x.shape[1], 4000):
         mp3 += e.encode(x[0, pos:pos + 4000], x[1, pos:pos + 4000])

@@ -70,6 +70,32 @@ def test_batch_matches_oracle(lib, oracle_mod, cfg):
         assert got[s] == oracle_bytes(oracle_mod, pcm[s], sr, brate, mode, q), "stream %d (%s)" % (s, kinds[s % 4])
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(S=16, F=24, fpl=8, brate=128), dict(S=6, F=30, fpl=16, brate=192, mode=1), dict(S=4, F=20, fpl=3, brate=150, mode=0, q=5),
+    dict(S=4, F=16, fpl=8, brate=256, sr=48000), dict(S=3, F=16, fpl=8, brate=112, sr=32000, q=7),
+])
+def test_abr_batch_matches_oracle(lib, oracle_mod, cfg):
+    """ABR (vbr_abr): the device chooses every frame's bitrate index (quantize.c:1962), frames of different sizes go
+    through kernel E and the host splice; byte-identical to the port and to libmp3lame"""
+    S, F = cfg["S"], cfg["F"]
+    sr, brate, mode, q = cfg.get("sr", 44100), cfg["brate"], cfg.get("mode", -1), cfg.get("q", -1)
+    kinds = ("noise", "click", "sine", "gap")
+    pcm = np.stack([make_signal(kinds[s % 4], F * 1152, seed=40 + s) for s in range(S)])
+    enc = lib.BatchEncoder(S, sr, 2, brate, mode, q, frames_per_launch=cfg["fpl"], vbr=lib.VBR_ABR)
+    _, a = enc.encode(pcm)
+    _, b = enc.flush()
+    enc.close()
+    sizes = set()
+    for s in range(S):
+        want = oracle_mod.PortEncoder(sr, 2, brate, mode, q, vbr=3).encode_all(pcm[s, 0], pcm[s, 1])
+        if oracle_mod.have_ref():
+            ref = oracle_mod.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q, vbr=3).encode_all(pcm[s, 0], pcm[s, 1])
+            assert want == ref, "oracle port and reference disagree"
+        assert a[s] + b[s] == want, "stream %d (%s)" % (s, kinds[s % 4])
+        sizes.add(len(want))
+    assert len(sizes) > 1                                  # ABR: stream lengths depend on the signal
+
+
 def test_lame_api_handle_matches_oracle(lib, oracle_mod):
     """the libmp3lame-compatible face: lame_init .. lame_encode_buffer .. lame_encode_flush on one handle"""
     x = make_signal("click", 50 * 1152, seed=3)
@@ -90,7 +116,8 @@ def test_info_tag_default_settings(lib, oracle_mod):
     tags = json.load(open(os.path.join(GOLD, "manifest_tag.json")))
     for name, m in sorted(tags.items()):
         x = make_signal(m["signal"], m["frames"] * 1152)
-        e = lib.Encoder(m["samplerate"], 2, m["brate"], m["mode"] if m["mode"] >= 0 else lib.NOT_SET, m["quality"], write_tag=True)
+        e = lib.Encoder(m["samplerate"], 2, m["brate"], m["mode"] if m["mode"] >= 0 else lib.NOT_SET, m["quality"], write_tag=True,
+                        vbr=m.get("vbr", 0))
         mp3 = b""
         for pos in range(0, x.shape[1], 4000):
             mp3 += e.encode(x[0, pos:pos + 4000], x[1, pos:pos + 4000])

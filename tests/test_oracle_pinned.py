@@ -69,6 +69,17 @@ def test_port_vs_reference(port_vs_ref_bin, args):
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
 
+@pytest.mark.parametrize("args", [
+    "noise 128 -1 -1 80", "click 128 -1 -1 120", "sine 160 -1 -1 60", "gap 192 0 -1 60", "noise 140 -1 5 40", "sine 256 1 -1 40",
+    "silence 128 -1 -1 20", "click 320 -1 -1 40 48000", "click 112 -1 -1 40 32000", "click 200 -1 7 40",
+])
+def test_port_abr_vs_reference(port_vs_ref_bin, args):
+    """ABR (lame_set_VBR(vbr_abr) + mean bitrate; quantize.c:1900): variable frame sizes, byte-identical to libmp3lame"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="3"))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
 def test_click_signal_has_short_blocks(oracle_mod):
     """the transient fixture must really exercise block switching, otherwise short-block parity is vacuous"""
     x = make_signal("click", 40 * 1152)
