@@ -118,6 +118,16 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (profiles/), or None"""
+    try:
+        k = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[kernel]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return sum(float(k[m]["value"]) * scale[k[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 def cpu_baseline(seconds=12.0):
     """unmodified reference (or the port when the reference build is absent), one thread, bounded sample"""
     import oracle
@@ -300,7 +310,8 @@ def main():
                     "note": "lamegpu_batch_encode_packed: pinned staging + H2D + 5 kernels + D2H of packed bytes + host header splice (threads=%d)" % (os.cpu_count() or 1)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "lg_kernel_quant", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": measured_traffic("lg_kernel_quant") if (S, F) == (STREAMS, FRAMES) else None, "peak_source": peak_src,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary.json)",
                          "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms,
                          "note": "latency/issue-bound integer + table-lookup kernel (SURVEY 8d): HBM fraction is reported, not the binding limit"},
             "kernels_ms_per_step": {"analysis": kms[0] / args.steps, "scan": kms[1] / args.steps, "mdct": kms[2] / args.steps, "quant": q_ms,
