@@ -1,7 +1,7 @@
 /* oracle/port - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * A plain-C, single-threaded restatement of the LAME 3.99.5 encode hot path (MPEG-1 Layer III,
- * 32/44.1/48 kHz, CBR and ABR, stereo / joint stereo / mono, quality 0..9 without substep shaping), written
+ * 32/44.1/48 kHz, CBR, ABR and VBR-new (-V0..-V6 at 44.1/48 kHz), stereo / joint stereo / mono), written
  * from the algorithm's description in the reference sources, each function citing the reference
  * file:line it follows.  Its only job is to be the CPU checker for the CUDA path (tests/, smoke(),
  * bench.py cpu_baseline).  Parity of this port is PINNED: tests/test_port_vs_ref.py compares its MP3
@@ -59,9 +59,9 @@ typedef struct {
     float mask_adjust, mask_adjust_short, pcm_transform[2][2], lowpass1, lowpass2, highpass1, highpass2;
     float adjust_bass_db, adjust_alto_db, adjust_treble_db, adjust_sfb21_db;
     float ath_aa_sensitivity_p, ath_decay, ath_floor;
-    /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr (lame.h:94 vbr_mode); ABR keeps its mean bitrate, the bitrate index range
+    /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr, 4 = vbr_mtrh with quality vbr_q (lame.h:94 vbr_mode); ABR keeps its mean bitrate, the bitrate index range
      * it may choose a frame size from, and the compression ratio calc_target_bits reads (quantize.c:1768) */
-    int   vbr, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
+    int   vbr, vbr_q, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
     float compression_ratio;
     /* tables */
     int   sfb_l[23], sfb_s[14], psfb21[7], psfb12[7];
@@ -130,7 +130,7 @@ typedef struct {
 
 /* API: mirrors lame_init, lame_set_xxx, lame_init_params, lame_encode_buffer, lame_encode_flush, lame_close */
 lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quality);
-lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 off, 3 abr */);
+lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 off, 3 abr, 4 mtrh: brate = VBR_q */);
 int  lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsigned char *out, int cap);
 int  lp_flush(lp_encoder *e, unsigned char *out, int cap);
 void lp_close(lp_encoder *e);
@@ -145,6 +145,7 @@ int   lp_psycho(lp_encoder *e, const float *const buffer[2], int gr_out, lp_rati
 void  lp_mdct_sub48(lp_encoder *e, const float *w0, const float *w1);
 void  lp_cbr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
 void  lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
+void  lp_vbr_new_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
 int   lp_getframebits(const lp_encoder *e);
 void  lp_format_bitstream(lp_encoder *e);
 void  lp_flush_bitstream(lp_encoder *e);

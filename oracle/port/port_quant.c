@@ -1224,3 +1224,650 @@ void lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ra
         if (resv_frame_begin(e, &mean_bits) >= 0) break;
     resv_frame_end(e, mean_bits);
 }
+
+/* ================================================================== VBR-new (vbr_mtrh / vbr_mt), vbrquantize.c
+ * One search context per granule.channel: the band-wise scalefactor search works on xr34 = |xr|^(3/4). */
+typedef struct {
+    lp_granule *gi;
+    const float *xr34;
+    int  mingain_l, mingain_s[3];
+    int  is_short, guess_only;
+} vbr_ctx;
+
+static const uint8_t vbr_range_short[LP_SBMAX_S * 3] = {
+    15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
+    7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 0, 0, 0 };
+static const uint8_t vbr_range_long[LP_SBMAX_L] = { 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 0 };
+
+/* vbrquantize.c:170 k_34_4 for n <= 4 values held in double: the 2^23 rounding trick with the adj43asm correction */
+static void vbr_quant4(const lp_config *c, double x[4], int l3[4])
+{
+    int k;
+    union { float f; int i; } fi[4];
+    for (k = 0; k < 4; k++) { x[k] += 8388608.0; fi[k].f = x[k]; }
+    for (k = 0; k < 4; k++) { fi[k].f = x[k] + c->adj43asm[fi[k].i - 0x4b000000]; l3[k] = fi[k].i - 0x4b000000; }
+}
+
+/* vbrquantize.c:218 calc_sfb_noise_x34: quantisation noise of one band at step sf */
+static float vbr_band_noise(const lp_config *c, const float *xr, const float *xr34, unsigned bw, int sf)
+{
+    double x[4];
+    int l3[4];
+    float const sfpow = c->pow20[sf + LP_QMAX2], sfpow34 = c->ipow20[sf];
+    float xfsf = 0;
+    unsigned i = bw >> 2, k;
+    unsigned const remaining = bw & 3u;
+    while (i-- > 0) {
+        for (k = 0; k < 4; k++) x[k] = sfpow34 * xr34[k];
+        vbr_quant4(c, x, l3);
+        for (k = 0; k < 4; k++) x[k] = fabsf(xr[k]) - sfpow * c->pow43[l3[k]];
+        xfsf += (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]);       /* double sum added to the float */
+        xr += 4; xr34 += 4;
+    }
+    if (remaining) {
+        x[0] = x[1] = x[2] = x[3] = 0;
+        for (k = 0; k < remaining; k++) x[k] = sfpow34 * xr34[k];
+        vbr_quant4(c, x, l3);
+        x[0] = x[1] = x[2] = x[3] = 0;
+        for (k = 0; k < remaining; k++) x[k] = fabsf(xr[k]) - sfpow * c->pow43[l3[k]];
+        xfsf += (x[0] * x[0] + x[1] * x[1]) + (x[2] * x[2] + x[3] * x[3]);
+    }
+    return xfsf;
+}
+
+/* vbrquantize.c:148 find_lowest_scalefac: smallest step that keeps the band's largest line within IXMAX_VAL */
+static int vbr_lowest_sf(const lp_config *c, float xr34)
+{
+    int sf_ok = 255, sf = 128, delsf = 64, i;
+    float const ixmax_val = LP_IXMAX;
+    for (i = 0; i < 8; ++i) {
+        float const xfsf = c->ipow20[sf] * xr34;
+        if (xfsf <= ixmax_val) { sf_ok = sf; sf -= delsf; }
+        else sf += delsf;
+        delsf >>= 1;
+    }
+    return sf_ok;
+}
+
+/* vbrquantize.c:278 tri_calc_sfb_noise_x34 without its memo table (the noise is a pure function of sf) */
+static int vbr_too_noisy(const lp_config *c, const float *xr, const float *xr34, float l3_xmin, unsigned bw, int sf)
+{
+    if (l3_xmin < vbr_band_noise(c, xr, xr34, bw, sf)) return 1;
+    if (sf < 255 && l3_xmin < vbr_band_noise(c, xr, xr34, bw, sf + 1)) return 1;
+    if (sf > 0 && l3_xmin < vbr_band_noise(c, xr, xr34, bw, sf - 1)) return 1;
+    return 0;
+}
+
+/* vbrquantize.c:347 find_scalefac_x34 / :324 guess_scalefac_x34 */
+static int vbr_find_sf(const lp_config *c, const float *xr, const float *xr34, float l3_xmin, unsigned bw, int sf_min, int guess_only)
+{
+    int sf = 128, sf_ok = 255, delsf = 128, seen_good_one = 0, i;
+    if (guess_only) {
+        float const cc = 5.799142446;
+        int const guess = 210 + (int) (cc * log10f(l3_xmin / bw) - .5f);
+        if (guess < sf_min) return sf_min;
+        if (guess >= 255) return 255;
+        return guess;
+    }
+    for (i = 0; i < 8; ++i) {
+        delsf >>= 1;
+        if (sf <= sf_min) sf += delsf;
+        else if (vbr_too_noisy(c, xr, xr34, l3_xmin, bw, sf)) sf -= delsf;
+        else { sf_ok = sf; sf += delsf; seen_good_one = 1; }
+        sf &= 255;                                  /* uint8_t arithmetic of the reference */
+    }
+    if (seen_good_one > 0) sf = sf_ok;
+    if (sf <= sf_min) sf = sf_min;
+    return sf;
+}
+
+/* vbrquantize.c:395 block_sf: per band the smallest usable step (vbrsfmin) and the step that just meets l3_xmin (vbrsf) */
+static int vbr_block_sf(const lp_config *c, vbr_ctx *t, const float *l3_xmin, int vbrsf[LP_SFBMAX], int vbrsfmin[LP_SFBMAX])
+{
+    const lp_granule *gi = t->gi;
+    unsigned const max_nonzero_coeff = (unsigned) gi->max_nonzero_coeff;
+    int maxsf = 0, sfb = 0, m_o = -1;
+    unsigned j = 0, i = 0;
+    t->mingain_l = 0;
+    t->mingain_s[0] = t->mingain_s[1] = t->mingain_s[2] = 0;
+    while (j <= max_nonzero_coeff) {
+        unsigned const w = (unsigned) gi->width[sfb], m = max_nonzero_coeff - j + 1;
+        unsigned l = w, k;
+        int m1, m2;
+        float mx = 0;
+        if (l > m) l = m;
+        for (k = 0; k < l; k++) if (mx < t->xr34[j + k]) mx = t->xr34[j + k];      /* vec_max_c */
+        m1 = vbr_lowest_sf(c, mx);
+        vbrsfmin[sfb] = m1;
+        if (t->mingain_l < m1) t->mingain_l = m1;
+        if (t->mingain_s[i] < m1) t->mingain_s[i] = m1;
+        if (++i > 2) i = 0;
+        if (sfb < gi->psymax && w > 2) {
+            if (gi->energy_above_cutoff[sfb]) {
+                m2 = vbr_find_sf(c, &gi->xr[j], &t->xr34[j], l3_xmin[sfb], l, m1, t->guess_only);
+                if (maxsf < m2) maxsf = m2;
+                if (m_o < m2 && m2 < 255) m_o = m2;
+            }
+            else { m2 = 255; maxsf = 255; }
+        }
+        else {
+            if (maxsf < m1) maxsf = m1;
+            m2 = maxsf;
+        }
+        vbrsf[sfb] = m2;
+        ++sfb;
+        j += w;
+    }
+    for (; sfb < LP_SFBMAX; ++sfb) { vbrsf[sfb] = maxsf; vbrsfmin[sfb] = 0; }
+    if (m_o > -1) {
+        maxsf = m_o;
+        for (sfb = 0; sfb < LP_SFBMAX; ++sfb) if (vbrsf[sfb] == 255) vbrsf[sfb] = m_o;
+    }
+    return maxsf;
+}
+
+/* vbrquantize.c:501 quantize_x34 */
+static void vbr_quantize(const lp_config *c, const vbr_ctx *t)
+{
+    lp_granule *gi = t->gi;
+    const float *xr34 = t->xr34;
+    int const ifqstep = (gi->scalefac_scale == 0) ? 2 : 4;
+    int *l3 = gi->l3_enc;
+    unsigned j = 0, sfb = 0;
+    unsigned const max_nonzero_coeff = (unsigned) gi->max_nonzero_coeff;
+    while (j <= max_nonzero_coeff) {
+        int const s = (gi->scalefac[sfb] + (gi->preflag ? lp_pretab[sfb] : 0)) * ifqstep + gi->subblock_gain[gi->window[sfb]] * 8;
+        int const sfac = (gi->global_gain - s) & 255;                       /* (uint8_t) */
+        float const sfpow34 = c->ipow20[sfac];
+        unsigned const w = (unsigned) gi->width[sfb], m = max_nonzero_coeff - j + 1;
+        unsigned n = (w <= m) ? w : m, k;
+        j += w;
+        ++sfb;
+        while (n > 0) {
+            double x[4] = { 0, 0, 0, 0 };
+            int q[4];
+            unsigned const take = n < 4 ? n : 4;
+            for (k = 0; k < take; k++) x[k] = sfpow34 * xr34[k];
+            vbr_quant4(c, x, q);
+            for (k = 0; k < take; k++) l3[k] = q[k];
+            l3 += take; xr34 += take; n -= take;
+        }
+    }
+}
+
+/* vbrquantize.c:596 set_subblock_gain */
+static void vbr_set_subblock_gain(lp_granule *gi, const int mingain_s[3], int sf[])
+{
+    int const maxrange1 = 15, maxrange2 = 7;
+    int const ifqstepShift = (gi->scalefac_scale == 0) ? 1 : 2;
+    int *const sbg = gi->subblock_gain;
+    unsigned const psymax = (unsigned) gi->psymax;
+    unsigned psydiv = 18, sfb, i;
+    int min_sbg = 7;
+    if (psydiv > psymax) psydiv = psymax;
+    for (i = 0; i < 3; ++i) {
+        int maxsf1 = 0, maxsf2 = 0, minsf = 1000;
+        for (sfb = i; sfb < psydiv; sfb += 3) {
+            int const v = -sf[sfb];
+            if (maxsf1 < v) maxsf1 = v;
+            if (minsf > v) minsf = v;
+        }
+        for (; sfb < LP_SFBMAX; sfb += 3) {
+            int const v = -sf[sfb];
+            if (maxsf2 < v) maxsf2 = v;
+            if (minsf > v) minsf = v;
+        }
+        {
+            int const m1 = maxsf1 - (maxrange1 << ifqstepShift), m2 = maxsf2 - (maxrange2 << ifqstepShift);
+            maxsf1 = m1 > m2 ? m1 : m2;
+        }
+        sbg[i] = (minsf > 0) ? (minsf >> 3) : 0;
+        if (maxsf1 > 0) {
+            int const m2 = (maxsf1 + 7) >> 3;
+            if (sbg[i] < m2) sbg[i] = m2;
+        }
+        if (sbg[i] > 0 && mingain_s[i] > (gi->global_gain - sbg[i] * 8)) sbg[i] = (gi->global_gain - mingain_s[i]) >> 3;
+        if (sbg[i] > 7) sbg[i] = 7;
+        if (min_sbg > sbg[i]) min_sbg = sbg[i];
+    }
+    for (sfb = 0; sfb < LP_SFBMAX; sfb += 3) { sf[sfb + 0] += sbg[0] * 8; sf[sfb + 1] += sbg[1] * 8; sf[sfb + 2] += sbg[2] * 8; }
+    if (min_sbg > 0) {
+        for (i = 0; i < 3; ++i) sbg[i] -= min_sbg;
+        gi->global_gain -= min_sbg * 8;
+    }
+}
+
+/* vbrquantize.c:689 set_scalefacs */
+static void vbr_set_scalefacs(lp_granule *gi, const int *vbrsfmin, int sf[], const uint8_t *max_range)
+{
+    int const ifqstep = (gi->scalefac_scale == 0) ? 2 : 4, ifqstepShift = (gi->scalefac_scale == 0) ? 1 : 2;
+    int sfb;
+    if (gi->preflag) for (sfb = 11; sfb < gi->sfbmax; ++sfb) sf[sfb] += lp_pretab[sfb] * ifqstep;
+    for (sfb = 0; sfb < gi->sfbmax; ++sfb) {
+        int const gain = gi->global_gain - (gi->subblock_gain[gi->window[sfb]] * 8) - ((gi->preflag ? lp_pretab[sfb] : 0) * ifqstep);
+        if (sf[sfb] < 0) {
+            int const m = gain - vbrsfmin[sfb];
+            gi->scalefac[sfb] = (ifqstep - 1 - sf[sfb]) >> ifqstepShift;
+            if (gi->scalefac[sfb] > max_range[sfb]) gi->scalefac[sfb] = max_range[sfb];
+            if (gi->scalefac[sfb] > 0 && (gi->scalefac[sfb] << ifqstepShift) > m) gi->scalefac[sfb] = m >> ifqstepShift;
+        }
+        else gi->scalefac[sfb] = 0;
+    }
+    for (; sfb < LP_SFBMAX; ++sfb) gi->scalefac[sfb] = 0;
+}
+
+/* vbrquantize.c:770 short_block_constrain / :848 long_block_constrain: global_gain, scalefac_scale, preflag, subblock gains
+ * and scalefactors that realise the wanted per-band steps as closely as the format allows */
+static void vbr_alloc(const lp_config *c, const vbr_ctx *t, const int vbrsf[LP_SFBMAX], const int vbrsfmin[LP_SFBMAX], int vbrmax)
+{
+    lp_granule *gi = t->gi;
+    int const maxminsfb = t->mingain_l, psymax = gi->psymax;
+    int sf_temp[LP_SFBMAX], sfb, delta = 0, mover, v;
+    if (t->is_short) {
+        int maxover0 = 0, maxover1 = 0;
+        for (sfb = 0; sfb < psymax; ++sfb) {
+            int v0, v1;
+            v = vbrmax - vbrsf[sfb];
+            if (delta < v) delta = v;
+            v0 = v - (4 * 14 + 2 * vbr_range_short[sfb]);
+            v1 = v - (4 * 14 + 4 * vbr_range_short[sfb]);
+            if (maxover0 < v0) maxover0 = v0;
+            if (maxover1 < v1) maxover1 = v1;
+        }
+        if (c->noise_shaping == 2) mover = maxover0 < maxover1 ? maxover0 : maxover1;
+        else mover = maxover0;
+        if (delta > mover) delta = mover;
+        vbrmax -= delta;
+        maxover0 -= mover;
+        maxover1 -= mover;
+        if (maxover0 == 0) gi->scalefac_scale = 0;
+        else if (maxover1 == 0) gi->scalefac_scale = 1;
+        if (vbrmax < maxminsfb) vbrmax = maxminsfb;
+        gi->global_gain = vbrmax;
+        if (gi->global_gain < 0) gi->global_gain = 0;
+        else if (gi->global_gain > 255) gi->global_gain = 255;
+        for (sfb = 0; sfb < LP_SFBMAX; ++sfb) sf_temp[sfb] = vbrsf[sfb] - vbrmax;
+        vbr_set_subblock_gain(gi, t->mingain_s, sf_temp);
+        vbr_set_scalefacs(gi, vbrsfmin, sf_temp, vbr_range_short);
+    }
+    else {
+        const uint8_t *max_rangep = vbr_range_long;            /* mode_gr == 2 */
+        int maxover0 = 0, maxover1 = 0, maxover0p = 0, maxover1p = 0, vm0p = 1, vm1p = 1;
+        for (sfb = 0; sfb < psymax; ++sfb) {
+            int v0, v1, v0p, v1p;
+            v = vbrmax - vbrsf[sfb];
+            if (delta < v) delta = v;
+            v0 = v - 2 * vbr_range_long[sfb];
+            v1 = v - 4 * vbr_range_long[sfb];
+            v0p = v - 2 * (max_rangep[sfb] + lp_pretab[sfb]);
+            v1p = v - 4 * (max_rangep[sfb] + lp_pretab[sfb]);
+            if (maxover0 < v0) maxover0 = v0;
+            if (maxover1 < v1) maxover1 = v1;
+            if (maxover0p < v0p) maxover0p = v0p;
+            if (maxover1p < v1p) maxover1p = v1p;
+        }
+        if (vm0p == 1) {
+            int gain = vbrmax - maxover0p;
+            if (gain < maxminsfb) gain = maxminsfb;
+            for (sfb = 0; sfb < psymax; ++sfb)
+                if ((gain - vbrsfmin[sfb]) - 2 * lp_pretab[sfb] <= 0) { vm0p = 0; vm1p = 0; break; }
+        }
+        if (vm1p == 1) {
+            int gain = vbrmax - maxover1p;
+            if (gain < maxminsfb) gain = maxminsfb;
+            for (sfb = 0; sfb < psymax; ++sfb)
+                if ((gain - vbrsfmin[sfb]) - 4 * lp_pretab[sfb] <= 0) { vm1p = 0; break; }
+        }
+        if (vm0p == 0) maxover0p = maxover0;
+        if (vm1p == 0) maxover1p = maxover1;
+        if (c->noise_shaping != 2) { maxover1 = maxover0; maxover1p = maxover0p; }
+        mover = maxover0 < maxover0p ? maxover0 : maxover0p;
+        mover = mover < maxover1 ? mover : maxover1;
+        mover = mover < maxover1p ? mover : maxover1p;
+        if (delta > mover) delta = mover;
+        vbrmax -= delta;
+        if (vbrmax < maxminsfb) vbrmax = maxminsfb;
+        maxover0 -= mover; maxover0p -= mover; maxover1 -= mover; maxover1p -= mover;
+        if (maxover0 == 0) { gi->scalefac_scale = 0; gi->preflag = 0; }
+        else if (maxover0p == 0) { gi->scalefac_scale = 0; gi->preflag = 1; }
+        else if (maxover1 == 0) { gi->scalefac_scale = 1; gi->preflag = 0; }
+        else if (maxover1p == 0) { gi->scalefac_scale = 1; gi->preflag = 1; }
+        gi->global_gain = vbrmax;
+        if (gi->global_gain < 0) gi->global_gain = 0;
+        else if (gi->global_gain > 255) gi->global_gain = 255;
+        for (sfb = 0; sfb < LP_SFBMAX; ++sfb) sf_temp[sfb] = vbrsf[sfb] - vbrmax;
+        vbr_set_scalefacs(gi, vbrsfmin, sf_temp, max_rangep);
+    }
+}
+
+/* vbrquantize.c:1000 quantizeAndCountBits */
+static int vbr_quantize_and_count(const lp_config *c, const vbr_ctx *t)
+{
+    vbr_quantize(c, t);
+    t->gi->part2_3_length = noquant_count_bits(c, t->gi, 0);
+    return t->gi->part2_3_length;
+}
+
+/* vbrquantize.c:1141 tryThatOne (+ :1012 tryGlobalStepsize when add_part2 == 0) */
+static int vbr_try(const lp_config *c, const vbr_ctx *t, const int sftemp[LP_SFBMAX], const int vbrsfmin[LP_SFBMAX], int vbrmax, int add_part2)
+{
+    float const xrpow_max = t->gi->xrpow_max;
+    int nbits;
+    vbr_alloc(c, t, sftemp, vbrsfmin, vbrmax);
+    (void) scale_bitcount(t->gi);
+    nbits = vbr_quantize_and_count(c, t);
+    if (add_part2) nbits += t->gi->part2_length;
+    t->gi->xrpow_max = xrpow_max;
+    return nbits;
+}
+
+/* vbrquantize.c:1105 flattenDistribution */
+static int vbr_flatten(const int sfwork[LP_SFBMAX], int sf_out[LP_SFBMAX], int dm, int k, int p)
+{
+    int i, x, sfmax = 0;
+    for (i = 0; i < LP_SFBMAX; ++i) {
+        if (dm > 0) {
+            int const di = p - sfwork[i];
+            x = sfwork[i] + (k * di) / dm;
+            if (x < 0) x = 0;
+            else if (x > 255) x = 255;
+        }
+        else x = sfwork[i];
+        sf_out[i] = x;
+        if (sfmax < x) sfmax = x;
+    }
+    return sfmax;
+}
+
+/* vbrquantize.c:1155 outOfBitsStrategy (+ :1041 searchGlobalStepsizeMax) */
+static void vbr_out_of_bits(const lp_config *c, const vbr_ctx *t, const int sfwork[LP_SFBMAX], const int vbrsfmin[LP_SFBMAX], int target)
+{
+    int wrk[LP_SFBMAX], dm = 0, i, part, nbits;
+    int const p = t->gi->global_gain;
+    for (i = 0; i < LP_SFBMAX; ++i) { int const di = 255 - sfwork[i]; if (dm < di) dm = di; }      /* sfDepth */
+    for (part = 0; part < 2; part++) {
+        /* part 0: pull every band towards global_gain by k/dm; part 1: towards a level bi above it */
+        int bi = part == 0 ? dm / 2 : (255 + p) / 2, bi_ok = -1, bu = part == 0 ? 0 : p, bo = part == 0 ? dm : 255;
+        for (;;) {
+            int const sfmax = part == 0 ? vbr_flatten(sfwork, wrk, dm, bi, p) : vbr_flatten(sfwork, wrk, dm, dm, bi);
+            nbits = vbr_try(c, t, wrk, vbrsfmin, sfmax, 1);
+            if (nbits <= target) { bi_ok = bi; bo = bi - 1; }
+            else bu = bi + 1;
+            if (bu <= bo) bi = (bu + bo) / 2;
+            else break;
+        }
+        if (bi_ok >= 0) {
+            if (bi != bi_ok) {
+                int const sfmax = part == 0 ? vbr_flatten(sfwork, wrk, dm, bi_ok, p) : vbr_flatten(sfwork, wrk, dm, dm, bi_ok);
+                (void) vbr_try(c, t, wrk, vbrsfmin, sfmax, 1);
+            }
+            return;
+        }
+    }
+    {   /* searchGlobalStepsizeMax on the last tried distribution */
+        int const gain = t->gi->global_gain;
+        int curr = gain, gain_ok = 1024, l = gain, r = 512;
+        while (l <= r) {
+            int sft[LP_SFBMAX], vbrmax = 0, g;
+            curr = (l + r) >> 1;
+            for (i = 0; i < LP_SFBMAX; ++i) {
+                g = wrk[i] + (curr - gain);
+                if (g < vbrsfmin[i]) g = vbrsfmin[i];
+                if (g > 255) g = 255;
+                if (vbrmax < g) vbrmax = g;
+                sft[i] = g;
+            }
+            nbits = vbr_try(c, t, sft, vbrsfmin, vbrmax, 0);
+            if (nbits == 0 || (nbits + t->gi->part2_length) < target) { r = curr - 1; gain_ok = curr; }
+            else { l = curr + 1; if (gain_ok == 1024) gain_ok = curr; }
+        }
+        if (gain_ok != curr) {
+            int sft[LP_SFBMAX], vbrmax = 0, g;
+            curr = gain_ok;
+            for (i = 0; i < LP_SFBMAX; ++i) {
+                g = wrk[i] + (curr - gain);
+                if (g < vbrsfmin[i]) g = vbrsfmin[i];
+                if (g > 255) g = 255;
+                if (vbrmax < g) vbrmax = g;
+                sft[i] = g;
+            }
+            (void) vbr_try(c, t, sft, vbrsfmin, vbrmax, 0);
+        }
+    }
+}
+
+/* vbrquantize.c:1232 reduce_bit_usage */
+static int vbr_reduce_bits(lp_encoder *e, int gr, int ch)
+{
+    lp_granule *gi = &e->tt[gr][ch];
+    best_scalefac_store(e, gr, ch);
+    if (e->cfg.use_best_huffman == 1) best_huffman_divide(&e->cfg, gi);
+    return gi->part2_3_length + gi->part2_length;
+}
+
+/* vbrquantize.c:1255 VBR_encode_frame */
+static int vbr_encode_frame(lp_encoder *e, float xr34orig[2][2][576], float l3_xmin[2][2][LP_SFBMAX], int max_bits[2][2])
+{
+    const lp_config *c = &e->cfg;
+    int sfwork_[2][2][LP_SFBMAX], vbrsfmin_[2][2][LP_SFBMAX];
+    vbr_ctx that_[2][2];
+    int const ngr = c->mode_gr, nch = c->channels;
+    int max_nbits_ch[2][2] = { { 0, 0 }, { 0, 0 } }, max_nbits_gr[2] = { 0, 0 }, max_nbits_fr = 0;
+    int use_nbits_ch[2][2], use_nbits_gr[2], use_nbits_fr, gr, ch, ok, sum_fr;
+    for (gr = 0; gr < ngr; ++gr) {
+        max_nbits_gr[gr] = 0;
+        for (ch = 0; ch < nch; ++ch) {
+            max_nbits_ch[gr][ch] = max_bits[gr][ch];
+            use_nbits_ch[gr][ch] = 0;
+            max_nbits_gr[gr] += max_bits[gr][ch];
+            max_nbits_fr += max_bits[gr][ch];
+            that_[gr][ch].gi = &e->tt[gr][ch];
+            that_[gr][ch].xr34 = xr34orig[gr][ch];
+            that_[gr][ch].is_short = e->tt[gr][ch].block_type == LP_SHORT;
+            that_[gr][ch].guess_only = c->full_outer_loop < 0;
+        }
+    }
+    for (gr = 0; gr < ngr; ++gr)
+        for (ch = 0; ch < nch; ++ch)
+            if (max_bits[gr][ch] > 0) {
+                vbr_ctx *t = &that_[gr][ch];
+                int const vbrmax = vbr_block_sf(c, t, l3_xmin[gr][ch], sfwork_[gr][ch], vbrsfmin_[gr][ch]);
+                vbr_alloc(c, t, sfwork_[gr][ch], vbrsfmin_[gr][ch], vbrmax);
+                (void) scale_bitcount(t->gi);
+            }
+    use_nbits_fr = 0;
+    for (gr = 0; gr < ngr; ++gr) {
+        use_nbits_gr[gr] = 0;
+        for (ch = 0; ch < nch; ++ch) {
+            if (max_bits[gr][ch] > 0) {
+                memset(&e->tt[gr][ch].l3_enc[0], 0, sizeof e->tt[gr][ch].l3_enc);
+                (void) vbr_quantize_and_count(c, &that_[gr][ch]);
+            }
+            use_nbits_ch[gr][ch] = vbr_reduce_bits(e, gr, ch);
+            use_nbits_gr[gr] += use_nbits_ch[gr][ch];
+        }
+        use_nbits_fr += use_nbits_gr[gr];
+    }
+    if (use_nbits_fr <= max_nbits_fr) {
+        ok = 1;
+        for (gr = 0; gr < ngr; ++gr) {
+            if (use_nbits_gr[gr] > LP_MAX_BITS_PER_GRANULE) ok = 0;
+            for (ch = 0; ch < nch; ++ch) if (use_nbits_ch[gr][ch] > LP_MAX_BITS_PER_CHANNEL) ok = 0;
+        }
+        if (ok) return use_nbits_fr;
+    }
+    /* the frame does not fit: decide how many bits every granule.channel may use (vbrquantize.c:1370-1510) */
+    ok = 1;
+    sum_fr = 0;
+    for (gr = 0; gr < ngr; ++gr) {
+        max_nbits_gr[gr] = 0;
+        for (ch = 0; ch < nch; ++ch) {
+            max_nbits_ch[gr][ch] = use_nbits_ch[gr][ch] > LP_MAX_BITS_PER_CHANNEL ? LP_MAX_BITS_PER_CHANNEL : use_nbits_ch[gr][ch];
+            max_nbits_gr[gr] += max_nbits_ch[gr][ch];
+        }
+        if (max_nbits_gr[gr] > LP_MAX_BITS_PER_GRANULE) {
+            float f[2] = { 0.0f, 0.0f }, s = 0.0f;
+            for (ch = 0; ch < nch; ++ch) {
+                if (max_nbits_ch[gr][ch] > 0) { f[ch] = sqrt(sqrt(max_nbits_ch[gr][ch])); s += f[ch]; }
+                else f[ch] = 0;
+            }
+            for (ch = 0; ch < nch; ++ch) max_nbits_ch[gr][ch] = (s > 0) ? LP_MAX_BITS_PER_GRANULE * f[ch] / s : 0;
+            if (nch > 1) {
+                if (max_nbits_ch[gr][0] > use_nbits_ch[gr][0] + 32) {
+                    max_nbits_ch[gr][1] += max_nbits_ch[gr][0];
+                    max_nbits_ch[gr][1] -= use_nbits_ch[gr][0] + 32;
+                    max_nbits_ch[gr][0] = use_nbits_ch[gr][0] + 32;
+                }
+                if (max_nbits_ch[gr][1] > use_nbits_ch[gr][1] + 32) {
+                    max_nbits_ch[gr][0] += max_nbits_ch[gr][1];
+                    max_nbits_ch[gr][0] -= use_nbits_ch[gr][1] + 32;
+                    max_nbits_ch[gr][1] = use_nbits_ch[gr][1] + 32;
+                }
+                if (max_nbits_ch[gr][0] > LP_MAX_BITS_PER_CHANNEL) max_nbits_ch[gr][0] = LP_MAX_BITS_PER_CHANNEL;
+                if (max_nbits_ch[gr][1] > LP_MAX_BITS_PER_CHANNEL) max_nbits_ch[gr][1] = LP_MAX_BITS_PER_CHANNEL;
+            }
+            max_nbits_gr[gr] = 0;
+            for (ch = 0; ch < nch; ++ch) max_nbits_gr[gr] += max_nbits_ch[gr][ch];
+        }
+        sum_fr += max_nbits_gr[gr];
+    }
+    if (sum_fr > max_nbits_fr) {
+        {
+            float f[2] = { 0.0f, 0.0f }, s = 0.0f;
+            for (gr = 0; gr < ngr; ++gr) {
+                if (max_nbits_gr[gr] > 0) { f[gr] = sqrt(max_nbits_gr[gr]); s += f[gr]; }
+                else f[gr] = 0;
+            }
+            for (gr = 0; gr < ngr; ++gr) max_nbits_gr[gr] = (s > 0) ? max_nbits_fr * f[gr] / s : 0;
+        }
+        if (ngr > 1) {
+            if (max_nbits_gr[0] > use_nbits_gr[0] + 125) {
+                max_nbits_gr[1] += max_nbits_gr[0];
+                max_nbits_gr[1] -= use_nbits_gr[0] + 125;
+                max_nbits_gr[0] = use_nbits_gr[0] + 125;
+            }
+            if (max_nbits_gr[1] > use_nbits_gr[1] + 125) {
+                max_nbits_gr[0] += max_nbits_gr[1];
+                max_nbits_gr[0] -= use_nbits_gr[1] + 125;
+                max_nbits_gr[1] = use_nbits_gr[1] + 125;
+            }
+            for (gr = 0; gr < ngr; ++gr) if (max_nbits_gr[gr] > LP_MAX_BITS_PER_GRANULE) max_nbits_gr[gr] = LP_MAX_BITS_PER_GRANULE;
+        }
+        for (gr = 0; gr < ngr; ++gr) {
+            float f[2] = { 0.0f, 0.0f }, s = 0.0f;
+            for (ch = 0; ch < nch; ++ch) {
+                if (max_nbits_ch[gr][ch] > 0) { f[ch] = sqrt(max_nbits_ch[gr][ch]); s += f[ch]; }
+                else f[ch] = 0;
+            }
+            for (ch = 0; ch < nch; ++ch) max_nbits_ch[gr][ch] = (s > 0) ? max_nbits_gr[gr] * f[ch] / s : 0;
+            if (nch > 1) {
+                if (max_nbits_ch[gr][0] > use_nbits_ch[gr][0] + 32) {
+                    max_nbits_ch[gr][1] += max_nbits_ch[gr][0];
+                    max_nbits_ch[gr][1] -= use_nbits_ch[gr][0] + 32;
+                    max_nbits_ch[gr][0] = use_nbits_ch[gr][0] + 32;
+                }
+                if (max_nbits_ch[gr][1] > use_nbits_ch[gr][1] + 32) {
+                    max_nbits_ch[gr][0] += max_nbits_ch[gr][1];
+                    max_nbits_ch[gr][0] -= use_nbits_ch[gr][1] + 32;
+                    max_nbits_ch[gr][1] = use_nbits_ch[gr][1] + 32;
+                }
+                for (ch = 0; ch < nch; ++ch) if (max_nbits_ch[gr][ch] > LP_MAX_BITS_PER_CHANNEL) max_nbits_ch[gr][ch] = LP_MAX_BITS_PER_CHANNEL;
+            }
+        }
+    }
+    sum_fr = 0;
+    for (gr = 0; gr < ngr; ++gr) {
+        int sum_gr = 0;
+        for (ch = 0; ch < nch; ++ch) {
+            sum_gr += max_nbits_ch[gr][ch];
+            if (max_nbits_ch[gr][ch] > LP_MAX_BITS_PER_CHANNEL) ok = 0;
+        }
+        sum_fr += sum_gr;
+        if (sum_gr > LP_MAX_BITS_PER_GRANULE) ok = 0;
+    }
+    if (sum_fr > max_nbits_fr) ok = 0;
+    if (!ok) for (gr = 0; gr < ngr; ++gr) for (ch = 0; ch < nch; ++ch) max_nbits_ch[gr][ch] = max_bits[gr][ch];
+    /* best_scalefac_store already ran once: reset what it left behind */
+    for (ch = 0; ch < nch; ++ch) e->scfsi[ch][0] = e->scfsi[ch][1] = e->scfsi[ch][2] = e->scfsi[ch][3] = 0;
+    for (gr = 0; gr < ngr; ++gr) for (ch = 0; ch < nch; ++ch) e->tt[gr][ch].scalefac_compress = 0;
+    use_nbits_fr = 0;
+    for (gr = 0; gr < ngr; ++gr) {
+        use_nbits_gr[gr] = 0;
+        for (ch = 0; ch < nch; ++ch) {
+            const vbr_ctx *t = &that_[gr][ch];
+            use_nbits_ch[gr][ch] = 0;
+            if (max_bits[gr][ch] > 0) {
+                int *sfwork = sfwork_[gr][ch], i;
+                int const cut = t->gi->global_gain;
+                for (i = 0; i < LP_SFBMAX; ++i) if (sfwork[i] > cut) sfwork[i] = cut;        /* cutDistribution */
+                vbr_out_of_bits(c, t, sfwork, vbrsfmin_[gr][ch], max_nbits_ch[gr][ch]);
+            }
+            use_nbits_ch[gr][ch] = vbr_reduce_bits(e, gr, ch);
+            use_nbits_gr[gr] += use_nbits_ch[gr][ch];
+        }
+        use_nbits_fr += use_nbits_gr[gr];
+    }
+    return use_nbits_fr;
+}
+
+/* quantize.c:1645 VBR_new_iteration_loop (+ :1582 VBR_new_prepare, :1341 get_framebits) */
+void lp_vbr_new_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2])
+{
+    const lp_config *cfg = &e->cfg;
+    float l3_xmin[2][2][LP_SFBMAX], xrpow[2][2][576];
+    int frameBits[16], max_bits[2][2], used_bits, gr, ch, i, j, analog_silence = 1, avg, bits = 0, maximum_framebits, pad, dummy;
+    (void) ms_ener_ratio;
+    memset(xrpow, 0, sizeof xrpow);
+    /* VBR_new_prepare */
+    e->bitrate_index = cfg->vbr_max_bitrate_index;
+    (void) resv_frame_begin(e, &avg);
+    pad = e->resv_max;
+    for (i = 1; i <= cfg->vbr_max_bitrate_index; i++) {            /* get_framebits */
+        e->bitrate_index = i;
+        frameBits[i] = resv_frame_begin(e, &dummy);
+    }
+    maximum_framebits = frameBits[cfg->vbr_max_bitrate_index];
+    for (gr = 0; gr < cfg->mode_gr; gr++) {
+        (void) on_pe(e, pe, max_bits[gr], avg, gr, 0);
+        if (e->mode_ext == 2)
+            for (i = 0; i < 576; ++i) {
+                float l = e->tt[gr][0].xr[i], r = e->tt[gr][1].xr[i];
+                e->tt[gr][0].xr[i] = (l + r) * (float) (SQRT2_D * 0.5);
+                e->tt[gr][1].xr[i] = (l - r) * (float) (SQRT2_D * 0.5);
+            }
+        for (ch = 0; ch < cfg->channels; ++ch) {
+            lp_granule *gi = &e->tt[gr][ch];
+            e->masking_lower = pow(10.0, cfg->mask_adjust * 0.1);
+            init_outer_loop(cfg, gi);
+            if (0 != calc_xmin(e, &ratio[gr][ch], gi, l3_xmin[gr][ch])) analog_silence = 0;
+            bits += max_bits[gr][ch];
+        }
+    }
+    for (gr = 0; gr < cfg->mode_gr; gr++)
+        for (ch = 0; ch < cfg->channels; ch++)
+            if (bits > maximum_framebits && bits > 0) { max_bits[gr][ch] *= maximum_framebits; max_bits[gr][ch] /= bits; }
+    if (analog_silence) pad = 0;
+    /* the loop itself */
+    for (gr = 0; gr < cfg->mode_gr; gr++)
+        for (ch = 0; ch < cfg->channels; ch++)
+            if (0 == init_xrpow(&e->tt[gr][ch], xrpow[gr][ch])) max_bits[gr][ch] = 0;
+    used_bits = vbr_encode_frame(e, xrpow, l3_xmin, max_bits);
+    i = (analog_silence /* && !enforce_min_bitrate */) ? 1 : cfg->vbr_min_bitrate_index;
+    for (; i < cfg->vbr_max_bitrate_index; i++) if (used_bits <= frameBits[i]) break;
+    if (i > cfg->vbr_max_bitrate_index) i = cfg->vbr_max_bitrate_index;
+    if (pad > 0) {
+        for (j = cfg->vbr_max_bitrate_index; j > i; --j) {
+            int const unused = frameBits[j] - used_bits;
+            if (unused <= pad) break;
+        }
+        e->bitrate_index = j;
+    }
+    else e->bitrate_index = i;
+    {
+        int mean_bits;
+        (void) resv_frame_begin(e, &mean_bits);
+        for (gr = 0; gr < cfg->mode_gr; gr++)
+            for (ch = 0; ch < cfg->channels; ch++) e->resv_size -= e->tt[gr][ch].part2_3_length + e->tt[gr][ch].part2_length;
+        resv_frame_end(e, mean_bits);
+    }
+}

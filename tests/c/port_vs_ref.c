@@ -43,7 +43,7 @@ int main(int argc, char **argv)
     void *h; lp_encoder *e;
     if (siggen(sig, l, r, n, sr, wav) < 0) { printf("bad signal\n"); return 2; }
     int const vbr = getenv("LP_VBR") ? atoi(getenv("LP_VBR")) : 0;          /* 0 = CBR, 3 = ABR with mean bitrate `brate` */
-    h = refdump_open(brate, mode, quality, vbr, 0, sr, 2);
+    h = refdump_open(brate, mode, quality, vbr, vbr == 4 ? brate : 0, sr, 2);   /* vbr 4 (vbr_mtrh): `brate` is VBR_q */
     e = lp_open_ex(sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr);
     if (!h || !e) { printf("open failed ref=%p port=%p\n", h, (void *) e); return (!h && !e) ? 0 : 2; }
     refdump_tables(h, &tab);

@@ -80,6 +80,19 @@ def test_port_abr_vs_reference(port_vs_ref_bin, args):
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
 
+@pytest.mark.parametrize("args", [
+    "noise 2 -1 -1 80", "click 2 -1 -1 150", "sine 2 -1 -1 80", "gap 2 -1 -1 60", "silence 2 -1 -1 20", "click 0 -1 -1 100", "noise 0 -1 -1 40",
+    "sine 4 -1 -1 60", "click 5 -1 -1 80", "noise 6 -1 -1 40", "click 3 0 -1 60", "click 1 1 -1 60", "click 2 -1 5 60", "sine 2 -1 7 60",
+    "click 2 -1 -1 60 48000", "noise 0 -1 -1 40 48000", "click 4 3 -1 60", "click 0 3 -1 100",
+])
+def test_port_vbr_new_vs_reference(port_vs_ref_bin, args):
+    """VBR-new (vbr_mtrh, lame_set_VBR_q = the 2nd argument; vbrquantize.c + quantize.c:1645), including the frames that do not fit
+    and go through outOfBitsStrategy (click at -V0): byte-identical to libmp3lame"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="4"))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
 def test_click_signal_has_short_blocks(oracle_mod):
     """the transient fixture must really exercise block switching, otherwise short-block parity is vacuous"""
     x = make_signal("click", 40 * 1152)
