@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblamegpu.so")
 
 STEREO, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET = 0, 1, 2, 3, 4
-VBR_OFF, VBR_ABR = 0, 3            # lame.h:94 vbr_mode
+VBR_OFF, VBR_ABR, VBR_MTRH = 0, 3, 4            # lame.h:94 vbr_mode (with VBR_MTRH, `brate` is VBR_q)
 
 _lib = None
 
@@ -52,6 +52,7 @@ def load_library(path=None):
         "lame_set_mode": (c_int, [c_void_p, c_int]), "lame_get_mode": (c_int, [c_void_p]),
         "lame_set_VBR": (c_int, [c_void_p, c_int]), "lame_get_VBR": (c_int, [c_void_p]),
         "lame_set_VBR_mean_bitrate_kbps": (c_int, [c_void_p, c_int]), "lame_get_VBR_mean_bitrate_kbps": (c_int, [c_void_p]),
+        "lame_set_VBR_q": (c_int, [c_void_p, c_int]), "lame_get_VBR_q": (c_int, [c_void_p]),
         "lamegpu_batch_open_ex": (c_void_p, [c_int] * 9),
         "lame_set_bWriteVbrTag": (c_int, [c_void_p, c_int]), "lame_get_bWriteVbrTag": (c_int, [c_void_p]),
         "lame_init_params": (c_int, [c_void_p]),
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lamegpu_batch_open_ex", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
+    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
@@ -130,6 +131,9 @@ class Encoder:
             L.lame_set_VBR(self._h, VBR_ABR)
             if brate:
                 L.lame_set_VBR_mean_bitrate_kbps(self._h, brate)
+        elif vbr == VBR_MTRH:
+            L.lame_set_VBR(self._h, VBR_MTRH)
+            L.lame_set_VBR_q(self._h, brate)
         elif brate:
             L.lame_set_brate(self._h, brate)
         if mode != NOT_SET:

@@ -472,7 +472,7 @@ size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }
 
 struct lame_global_struct {
     unsigned class_id;
-    int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag, mean_brate;
+    int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag, mean_brate, vbr_q;
     MPEG_mode mode;
     vbr_mode VBR;
     int launch_frames;
@@ -523,7 +523,7 @@ lame_global_flags *lame_init(void)
     if (!g) return NULL;
     g->class_id = LAME_ID;
     g->num_channels = 2; g->samplerate_in = 44100; g->samplerate_out = 0; g->brate = 0; g->quality = -1;
-    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128;
+    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128; g->vbr_q = 4;
     if (const char *e = getenv("LAMEGPU_HANDLE_FRAMES")) g->launch_frames = std::max(1, atoi(e));
     return g;
 }
@@ -544,6 +544,16 @@ int lame_set_VBR(lame_global_flags *g, vbr_mode m) { if (!ok(g) || (int) m < 0 |
 vbr_mode lame_get_VBR(const lame_global_flags *g) { return ok(g) ? g->VBR : vbr_off; }
 int lame_set_VBR_mean_bitrate_kbps(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->mean_brate = v; return 0; }     /* set_get.c:1241 */
 int lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *g) { return ok(g) ? g->mean_brate : 0; }
+int lame_set_VBR_q(lame_global_flags *g, int v)                     /* set_get.c:1112: clamps to 0..9 and reports -1 */
+{
+    if (!ok(g)) return -1;
+    int ret = 0;
+    if (v < 0) { ret = -1; v = 0; }
+    if (v > 9) { ret = -1; v = 9; }
+    g->vbr_q = v;
+    return ret;
+}
+int lame_get_VBR_q(const lame_global_flags *g) { return ok(g) ? g->vbr_q : 0; }
 int lame_set_bWriteVbrTag(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->write_lame_tag = v; return 0; }
 int lame_get_bWriteVbrTag(const lame_global_flags *g) { return ok(g) ? g->write_lame_tag : 0; }
 const char *get_lame_short_version(void) { return "3.99.5"; }
@@ -551,11 +561,12 @@ const char *get_lame_short_version(void) { return "3.99.5"; }
 int lame_init_params(lame_global_flags *g)
 {
     if (!ok(g)) return -1;
-    if (g->VBR != vbr_off && g->VBR != vbr_abr) { fprintf(stderr, "lamegpu: only CBR (vbr_off) and ABR (vbr_abr) are implemented on the GPU path\n"); return -1; }
+    if (g->VBR == vbr_rh) { fprintf(stderr, "lamegpu: vbr_rh (VBR-old) is not implemented on the GPU path\n"); return -1; }
     if (g->samplerate_out && g->samplerate_out != g->samplerate_in) { fprintf(stderr, "lamegpu: resampling is not implemented\n"); return -1; }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
-    g->b = lamegpu_batch_open_ex(g->samplerate_in, g->num_channels, g->VBR == vbr_abr ? g->mean_brate : g->brate, g->mode == NOT_SET ? -1 : (int) g->mode, g->quality,
-                                 g->VBR == vbr_abr ? 3 : 0, 1, g->launch_frames, 0);
+    int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh);        /* both select VBR_new_iteration_loop, encoder.c:531 */
+    g->b = lamegpu_batch_open_ex(g->samplerate_in, g->num_channels, is_vbr ? g->vbr_q : (g->VBR == vbr_abr ? g->mean_brate : g->brate),
+                                 g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? 4 : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
     if (!g->b) return -1;
     g->samplerate_out = g->samplerate_in;
     g->brate = g->b->cfg.brate;
@@ -702,7 +713,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     /* PutLameVBR */
     unsigned char *p = buffer + n;
     int k = 0;
-    int nQuality = 100 - 10 * 4 /* VBR_q default, lame.c:2360 */ - g->quality;
+    int nQuality = 100 - 10 * g->vbr_q /* default 4, lame.c:2360 */ - g->quality;
     if (nQuality < 0) nQuality = 0;
     double const lp = c->lowpassfreq / 100.0 + .5;
     unsigned char const nLowpass = (unsigned char) (lp > 255 ? 255 : lp);
@@ -725,13 +736,16 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     unsigned char const nMisc = (unsigned char) (c->noise_shaping + (nStereoMode << 2) + (bNonOptimal << 5) + (nSourceFreq << 6));
     put_be32(p + k, (unsigned long) nQuality); k += 4;
     memcpy(p + k, "LAME3.99r", 9); k += 9;                  /* get_lame_tag_encoder_short_version(), version.c:148 */
-    p[k++] = (unsigned char) (c->vbr == 3 ? 0x02 : 0x01);   /* revision 0; vbr_type_translator: vbr_off -> 1, vbr_abr -> 2 */
+    p[k++] = (unsigned char) (c->vbr == 4 ? 0x04 : (c->vbr == 3 ? 0x02 : 0x01));   /* revision 0; vbr_type_translator: off 1, abr 2, mtrh 4 */
     p[k++] = nLowpass;
     put_be32(p + k, 0); k += 4;                             /* peak signal amplitude: no ReplayGain analysis */
     put_be16(p + k, 0); k += 2;
     put_be16(p + k, 0); k += 2;
     p[k++] = nFlags;
-    p[k++] = (unsigned char) (c->vbr_mean_kbps >= 255 ? 0xFF : c->vbr_mean_kbps);
+    {   /* "if ABR, {store bitrate <= 255} else {store -b}": the VBR modes store the minimal bitrate (VbrTag.c:672-686) */
+        int const nABRBitrate = (c->vbr == 4) ? c->bitrate_kbps[c->vbr_min_bitrate_index] : c->vbr_mean_kbps;
+        p[k++] = (unsigned char) (nABRBitrate >= 255 ? 0xFF : nABRBitrate);
+    }
     int const enc_delay = 576, enc_padding = v.enc_padding;
     p[k] = (unsigned char) (enc_delay >> 4);
     p[k + 1] = (unsigned char) ((enc_delay << 4) + (enc_padding >> 8));
@@ -739,7 +753,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     k += 3;
     p[k++] = nMisc;
     p[k++] = 0;
-    put_be16(p + k, (unsigned) c->vbr_mean_kbps); k += 2;   /* cfg->preset: apply_preset(mean bitrate), presets.c:361 */
+    put_be16(p + k, (unsigned) (c->vbr == 4 ? 500 - 10 * c->vbr_q : c->vbr_mean_kbps)); k += 2;   /* cfg->preset: apply_preset(...), presets.c:361 */
     put_be32(p + k, stream_size); k += 4;
     put_be16(p + k, v.music_crc); k += 2;
     for (int i = 0; i < k; i++) crc = crc16_update(p[i], crc);

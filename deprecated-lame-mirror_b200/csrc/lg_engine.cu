@@ -18,6 +18,7 @@
 #include "lg_k_scan.cuh"
 #include "lg_k_mdct.cuh"
 #include "lg_k_quant.cuh"
+#include "lg_k_vbr.cuh"
 #include "lg_k_pack.cuh"
 #include "lg_engine.h"
 
@@ -184,6 +185,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
+    cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
 #endif
     {
         LgStreamState *h0 = (LgStreamState *) malloc(S * sizeof(LgStreamState));
@@ -241,8 +243,12 @@ extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
     cudaEventRecord(e->ev[3], e->stream);
     if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: mdct done (%s)\n", cudaGetErrorString(r)); }
 #endif
-    LG_LAUNCH(lg_kernel_quant, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
-              e->d_state, e->d_nfr, F);
+    if (e->hcfg.vbr == 4)
+        LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F);
+    else
+        LG_LAUNCH(lg_kernel_quant, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F);
 #ifndef LG_EMULATE
     cudaEventRecord(e->ev[4], e->stream);
     if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: quant done (%s)\n", cudaGetErrorString(r)); }

@@ -43,7 +43,8 @@ struct __attribute__((aligned(16))) LgQWarp {
     int   sfw[40], sfbst[40];
     int   width[40], window[40], lstart[41];
     int   act[80];
-    float tail_max[40];              /* per band: largest xrpow among its lines above max_nonzero_coeff (see lg_scale_bands) */
+    float tail_max[40];
+    int   eac[40];                   /* calc_xmin: energy_above_cutoff per band (quantize_pvt.c:643), read by the VBR search */              /* per band: largest xrpow among its lines above max_nonzero_coeff (see lg_scale_bands) */
     int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
     uint8_t line_sfb[576];
@@ -217,6 +218,8 @@ __device__ __noinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, cons
  * granule's scalar state lives in registers.  The loops over the lane's line pairs are rolled on purpose (the search
  * loop has to stay inside the instruction cache) and stop at qc.jn: lines above max_nonzero_coeff are zero when the
  * granule starts and quantize_xrpow only ever keeps or clears them (takehiro.c:300-330), so they are never touched. */
+__device__ __forceinline__ int lg_noquant_tail(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev &pv,
+                                               int hi_nz, int hi_big, int lane);
 __device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev &pv, int lane)
 {
     float const istep = __ldg(&c->ipow20[gi.global_gain]);
@@ -287,6 +290,14 @@ __device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQ
             if ((nv & 0xfffefffeu) != 0u) hi_big = P;
         }
     }
+    return lg_noquant_tail(c, w, gi, qc, pv, hi_nz, hi_big, lane);
+}
+
+/* takehiro.c:654 noquant_count_bits on the ix in w->ixw; hi_nz / hi_big = the lane's highest pair (below the limit of
+ * max_nonzero_coeff) that is non-zero / holds a value > 1 */
+__device__ __forceinline__ int lg_noquant_tail(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev &pv,
+                                               int hi_nz, int hi_big, int lane)
+{
     /* ---- noquant_count_bits: count1 / big_values split */
     pv.sfb_count1 = 0;
     hi_nz = lg_wmax_i(hi_nz);
@@ -913,6 +924,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
         }
         xmin = ((double) xmin > 2.2204460492503131e-016) ? xmin : eps;
         w->l3_xmin[gsfb] = xmin;
+        w->eac[gsfb] = (en0 > xmin + 1e-14f) ? 1 : 0;
     }
     /* highest non-zero line */
     int k = 0;
@@ -976,6 +988,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
                 }
                 xmin = ((double) xmin > 2.2204460492503131e-016) ? xmin : eps;
                 xm[b] = xmin;
+                w->eac[gsfb + b] = (en0 > xmin + 1e-14f) ? 1 : 0;
             }
             if (c->use_temporal) {
                 if (xm[0] > xm[1]) xm[1] += (xm[0] - xm[1]) * c->decay;

@@ -478,7 +478,7 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                 F->ms_ener_ratio[1] = ms_ener_ratio[1];
                 F->ath_adjust_factor = st->ath_adjust_factor;
                 /* quantize.c:2019-2029: masking_lower left behind by the last gr/ch of this frame */
-                st->masking_lower = (sm->frame_bt[1][nch - 1] != LG_SHORT) ? cfg->masking_lower_long : cfg->masking_lower_short;
+                st->masking_lower = (cfg->vbr == 4 || sm->frame_bt[1][nch - 1] != LG_SHORT) ? cfg->masking_lower_long : cfg->masking_lower_short;   /* VBR-new: mask_adjust for every block type, quantize.c:1613 */
                 F->masking_lower = st->masking_lower;
                 st->frames_done++;
             }

@@ -477,6 +477,14 @@ static void setup_psy(LgDevCfg *c, float attackthre, float attackthre_s, int vbr
 /* lame.c:363 lame_init_qval */
 static int setup_quality(LgDevCfg *c, int quality)
 {
+    if (c->vbr == 4 && quality == 0) {
+        /* lame.c:458-470 case 0; substep_shaping = 2 only matters to the CBR/ABR loops */
+        if (c->noise_shaping == 0) c->noise_shaping = 1;
+        c->noise_shaping_amp = 2; c->noise_shaping_stop = 1;
+        if (c->subblock_gain == -1) c->subblock_gain = 1;
+        c->use_best_huffman = 1; c->full_outer_loop = 1;
+        return 0;
+    }
     switch (quality) {
     default:
     case 9:
@@ -487,6 +495,7 @@ static int setup_quality(LgDevCfg *c, int quality)
     case 7:
         c->noise_shaping = 0; c->noise_shaping_amp = 0; c->noise_shaping_stop = 0;
         c->use_best_huffman = 0; c->full_outer_loop = 0;
+        if (c->vbr == 4) c->full_outer_loop = -1;          /* lame.c:389-391 */
         break;
     case 6:
     case 5:
@@ -531,7 +540,18 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
         {320, 1, 0.90, 5.20, 125, 1.00, -10, 12.0, 0, 0, 0} };
     static const int lowpass_map[17] = { 2000, 3700, 3900, 5500, 7000, 7500, 10000, 11000, 13500, 15100,
         15600, 17000, 17500, 18600, 19400, 19700, 20500 };
-    int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, suggested;
+    /* presets.c:99 vbr_mt_psy_switch_map: st_lrm, st_s, masking_adj (long, short), ath_lower, ath_curve, ath_sensitivity,
+     * interch, safejoint, sfb21mod, msfix, minval, ath_fixpoint; expY = (q >= 3) */
+    static const struct { float st_lrm, st_s, madj, madj_s, ath_lower, ath_curve, ath_sens, interch; int safejoint, sfb21mod; float msfix, minval, ath_fixpoint; }
+    vm[10] = {
+        {4.20, 25.0, -6.8, -6.8, 7.1, 1, 0, 0, 2, 31, 1.000, 5, 100}, {4.20, 25.0, -4.8, -4.8, 5.4, 1.4, -1, 0, 2, 27, 1.122, 5, 98},
+        {4.20, 25.0, -2.6, -2.6, 3.7, 2.0, -3, 0, 2, 23, 1.288, 5, 97}, {4.20, 25.0, -1.6, -1.6, 2.0, 2.0, -5, 0, 2, 18, 1.479, 5, 96},
+        {4.20, 25.0, -0.0, -0.0, 0.0, 2.0, -8, 0, 2, 12, 1.698, 5, 95}, {4.20, 25.0, 1.3, 1.3, -6, 3.5, -11, 0, 2, 8, 1.950, 5, 94.2},
+        {4.50, 100.0, 2.2, 2.3, -12.0, 6.0, -14, 0, 2, 4, 2.239, 3, 93.9}, {4.80, 200.0, 2.7, 2.7, -18.0, 9.0, -17, 0, 2, 0, 2.570, 1, 93.6},
+        {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} };
+    static const int vbr_lowpass[11] = { 24000, 19500, 18500, 18000, 17500, 17000, 16500, 15600, 15200, 7230, 3950 };
+    int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, suggested, vbr_q = 0;
+    float athaa_sensitivity = 0;
     float scale = 1, maskingadjust, maskingadjust_short, ath_lower_db, attackthre, attackthre_s;
     double lowpass;
 
@@ -544,8 +564,17 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     if (channels == 1) mode = LG_MONO;                                 /* lame.c:597 */
     if (mode == LG_MONO) c->channels = 1;
     c->force_ms = 0;
-    if (vbr != 0 && vbr != 3) return -1;                              /* vbr_off and vbr_abr only (lame.h:94) */
-    if (vbr == 3) {
+    if (vbr != 0 && vbr != 3 && vbr != 4) return -1;                  /* vbr_off, vbr_abr, vbr_mtrh (lame.h:94) */
+    if (vbr == 4) {
+        /* `brate` carries VBR_q.  Levels 7..9 make lame_init_params pick a lower output rate at these input rates
+         * (lame.c:661-698), which needs the resampler; at 32 kHz it rescales VBR_q to a fractional level (:679-686) */
+        vbr_q = brate;
+        if (vbr_q < 0 || vbr_q > 6) return -1;
+        if (samplerate == 32000) return -1;
+        brate = 128;                                                   /* gfp->brate stays unused; keeps the arithmetic below defined */
+    }
+    if (vbr == 4) { }
+    else if (vbr == 3) {
         /* ABR keeps the requested mean bitrate as it is (lame_set_VBR_mean_bitrate_kbps, default 128), clamped for
          * MPEG-1 rates (lame.c:655-658 and :1088-1093 with the default index range 1..14) */
         if (brate == 0) brate = 128;
@@ -564,7 +593,8 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     }
     /* lame.c:704-762: low-pass from the bitrate */
     lowpass = lowpass_map[nearest_full_index(brate)];
-    if (mode == LG_MONO) lowpass *= 1.5;
+    if (vbr == 4) lowpass = vbr_lowpass[vbr_q];                        /* lame.c:730-741, VBR_q_frac = 0 */
+    else if (mode == LG_MONO) lowpass *= 1.5;
     c->lowpassfreq = lowpass;
     if (2 * c->lowpassfreq > samplerate) c->lowpassfreq = samplerate / 2;
     /* lame.c:245 optimum_samplefreq: we only accept the cases where no resampling results */
@@ -574,7 +604,8 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     if (c->lowpassfreq <= 11220) suggested = 24000;
     if (samplerate < suggested) suggested = samplerate;               /* lame.c:304-334 maps up to the input rate */
     if (suggested != samplerate) return -1;
-    c->lowpassfreq = c->lowpassfreq < 20500 ? c->lowpassfreq : 20500;
+    if (vbr == 4) c->lowpassfreq = c->lowpassfreq < 24000 ? c->lowpassfreq : 24000;     /* lame.c:770-775 */
+    else c->lowpassfreq = c->lowpassfreq < 20500 ? c->lowpassfreq : 20500;
     c->lowpassfreq = samplerate / 2 < c->lowpassfreq ? samplerate / 2 : c->lowpassfreq;
     c->mode_gr = 2;
     if (mode == LG_MODE_NOT_SET || mode < 0) mode = LG_JOINT;
@@ -598,7 +629,8 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     c->vbr_max_bitrate_index = 14;
     c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * brate);   /* lame.c:778-784 */
     for (i = 0; i < 16; i++) c->bitrate_kbps[i] = LGT_BITRATE[16 * version + i];
-    if (vbr == 3) c->bitrate_index = 1;                                /* lame.c:921 */
+    c->vbr_q = vbr_q;
+    if (vbr != 0) c->bitrate_index = 1;                                /* lame.c:921 */
     else {
         c->bitrate_index = -1;
         for (i = 0; i <= 14; i++) if (LGT_BITRATE[16 + i] == brate) { c->bitrate_index = i; break; }
@@ -614,6 +646,31 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     c->sideinfo_len = (c->channels == 1) ? 4 + 17 : 4 + 32;
     c->original = 1;
 
+    if (vbr == 4) {
+        /* lame.c:975-1003 + presets.c:143 apply_vbr_preset(VBR_q) with every option still at its default */
+        c->noise_shaping = 0;
+        c->quant_comp = 9;
+        c->quant_comp_short = 9;
+        attackthre = vm[vbr_q].st_lrm;
+        attackthre_s = vm[vbr_q].st_s;
+        maskingadjust = vm[vbr_q].madj + 0.0f;                          /* LERP with VBR_q_frac = 0 turns the table's -0.0 into +0.0 */
+        maskingadjust_short = vm[vbr_q].madj_s + 0.0f;
+        ath_lower_db = vm[vbr_q].ath_lower;
+        c->athcurve = vm[vbr_q].ath_curve;
+        athaa_sensitivity = vm[vbr_q].ath_sens;
+        c->interch = vm[vbr_q].interch > 0 ? vm[vbr_q].interch : 0;
+        if (vm[vbr_q].safejoint > 0) exp_nspsytune |= 2;
+        if (vm[vbr_q].sfb21mod > 0) exp_nspsytune |= vm[vbr_q].sfb21mod << 20;
+        c->msfix = vm[vbr_q].msfix;
+        c->minval = vm[vbr_q].minval;
+        c->athfixpoint = vm[vbr_q].ath_fixpoint;
+        if (quality < 0) quality = 3;
+        if (quality < 5) quality = 0;
+        if (quality > 7) quality = 7;
+        if (quality == 7) return -1;      /* guess_scalefac_x34 (vbrquantize.c:317) calls log10f at run time: not restated on the device */
+        c->sfb21_extra = (vbr_q >= 3) ? 0 : (samplerate > 44000);     /* experimentalY from the preset, lame.c:996-999 */
+        goto presets_done;
+    }
     /* presets.c:216 apply_abr_preset(brate) with every option still at its default */
     r = nearest_full_index(brate);
     if (pm[r].safejoint > 0) exp_nspsytune |= 2;
@@ -633,6 +690,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     c->minval = 5. * (pm[r].kbps / 320.);
 
     c->sfb21_extra = 0;
+presets_done:
     c->mask_adjust = maskingadjust;
     c->mask_adjust_short = maskingadjust_short;
     c->substep_shaping = 0;
@@ -644,14 +702,18 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     c->quality = quality;
     if (setup_quality(c, quality) < 0) return -1;
     c->ath_use_adjust = 3;
-    c->ath_aa_sensitivity_p = pow(10.0, 0.0 / -10.0);
+    c->ath_aa_sensitivity_p = pow(10.0, athaa_sensitivity / -10.0);
     c->short_blocks = (c->mode == LG_JOINT || c->mode == LG_STEREO) ? 1 /* coupled */ : 0 /* allowed */;
-    c->athtype = 4;
-    c->use_temporal = 1;
+    c->athtype = (vbr == 4) ? 5 : 4;                                    /* presets.c:170 */
+    c->use_temporal = (vbr == 4) ? 0 : 1;                               /* lame.c:979-981 */
     c->ath_offset_db = 0 - ath_lower_db;
     c->ath_offset_factor = powf(10.f, c->ath_offset_db * 0.1f);
     c->use_safe_joint_stereo = exp_nspsytune & 2;
-    c->adjust_bass_db = c->adjust_alto_db = c->adjust_treble_db = c->adjust_sfb21_db = 0;
+    c->adjust_bass_db = c->adjust_alto_db = c->adjust_treble_db = 0;
+    c->adjust_sfb21_db = (exp_nspsytune >> 20) & 63;                    /* lame.c:1186-1190 */
+    if (c->adjust_sfb21_db >= 32.f) c->adjust_sfb21_db -= 64.f;
+    c->adjust_sfb21_db *= 0.25f;
+    c->adjust_sfb21_db += c->adjust_treble_db;
     {
         float m[2][2] = { {1.0f, 0.0f}, {0.0f, 1.0f} };
         m[0][0] *= scale; m[0][1] *= scale; m[1][0] *= scale; m[1][1] *= scale;
@@ -664,7 +726,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, in
     }
     c->frac_spf = (vbr == 0) ? ((version + 1) * 72000L * brate) % samplerate : 0;      /* lame.c:1245 */
     setup_quantizer_tables(c);
-    setup_psy(c, attackthre, attackthre_s, 4, 0.f);
+    setup_psy(c, attackthre, attackthre_s, vbr == 4 ? vbr_q : 4, 0.f);
     c->buffer_constraint = 7680 * (version + 1);                       /* bitstream.c:119 MDB_MAXIMUM */
     finish_device_tables(c);
     return 0;

@@ -67,9 +67,9 @@ typedef struct {
     float adjust_bass_db, adjust_alto_db, adjust_treble_db, adjust_sfb21_db;
     float ath_aa_sensitivity_p, ath_decay, ath_floor;
     float masking_lower_long, masking_lower_short;  /* (float)pow(10, mask_adjust*0.1), quantize.c:2029 */
-    /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr (lame.h:94).  ABR chooses a frame size per frame: mean bitrate, index range,
+    /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr, 4 = vbr_mtrh at quality vbr_q (lame.h:94).  ABR chooses a frame size per frame: mean bitrate, index range,
      * the compression ratio calc_target_bits reads (quantize.c:1768) and the bitrate table row of this MPEG version */
-    int   vbr, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
+    int   vbr, vbr_q, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
     float compression_ratio;
     int   bitrate_kbps[16];
     int   sfb_l[23], sfb_s[14], psfb21[7], psfb12[7];

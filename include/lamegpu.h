@@ -47,6 +47,8 @@ int  lame_set_VBR(lame_global_flags *, vbr_mode);                               
 vbr_mode lame_get_VBR(const lame_global_flags *);
 int  lame_set_VBR_mean_bitrate_kbps(lame_global_flags *, int);                       /* lame.h:444  ABR mean bitrate */
 int  lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *);                      /* lame.h:445 */
+int  lame_set_VBR_q(lame_global_flags *, int);                                       /* lame.h:436  VBR quality 0..9 (vbr_mtrh: 0..6 here) */
+int  lame_get_VBR_q(const lame_global_flags *);                                      /* lame.h:437 */
 int  lame_set_VBR_mean_bitrate_kbps(lame_global_flags *, int);                       /* lame.h:447  ABR mean bitrate */
 int  lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *);                                    /* lame.h:433 */
 int  lame_set_bWriteVbrTag(lame_global_flags *, int);                                /* lame.h:240  the Info tag frame is not produced */
@@ -93,7 +95,8 @@ typedef struct lamegpu_batch lamegpu_batch;
 lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int mode /* MPEG_mode or -1 */,
                                   int quality /* 0..9 or -1 */, int nstreams, int frames_per_launch, int device);
 /* same, with the rate mode: vbr = 0 (vbr_off, CBR at `brate`) or 3 (vbr_abr, `brate` is the mean bitrate of
- * lame_set_VBR_mean_bitrate_kbps; quantize.c:1900 ABR_iteration_loop) */
+ * lame_set_VBR_mean_bitrate_kbps; quantize.c:1900 ABR_iteration_loop) or 4 (vbr_mtrh, `brate` is VBR_q 0..6;
+ * quantize.c:1645 VBR_new_iteration_loop + vbrquantize.c) */
 lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr,
                                      int nstreams, int frames_per_launch, int device);
 void lamegpu_batch_close(lamegpu_batch *b);

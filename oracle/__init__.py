@@ -93,6 +93,11 @@ class RefEncoder:
             L.lame_set_VBR(self.h, 3)
             if brate:
                 L.lame_set_VBR_mean_bitrate_kbps(self.h, brate)
+        elif vbr == 4:                                        # vbr_mtrh: brate is VBR_q
+            L.lame_set_VBR.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            L.lame_set_VBR_q.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            L.lame_set_VBR(self.h, 4)
+            L.lame_set_VBR_q(self.h, brate)
         elif brate:
             L.lame_set_brate(self.h, brate)
         if 0 <= mode < 4:

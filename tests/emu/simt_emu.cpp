@@ -95,6 +95,8 @@ void launch(dim3_t grid, dim3_t block, size_t smem_bytes, const std::function<vo
             b.gdim = grid;
             b.bidx = dim3_t(i % grid.x, (i / grid.x) % grid.y, i / (grid.x * grid.y));
             b.smem = (unsigned char *) (((uintptr_t) smem.data() + 63) & ~(uintptr_t) 63);
+            /* shared memory is NOT zeroed on a GPU: poison it so that reads of never-written words show up here too */
+            std::memset(smem.data(), std::getenv("LG_EMU_SMEM_FILL") ? std::atoi(std::getenv("LG_EMU_SMEM_FILL")) : 0xCD, smem.size());
             b.body = &body;
             run_block(b, stacks);
         }

@@ -33,12 +33,16 @@ CASES = [
 
 
 TAG_CASES = [
-    # name, signal, frames, samplerate, brate (CBR bitrate or ABR mean), mode, quality, vbr (0 = vbr_off, 3 = vbr_abr)
+    # name, signal, frames, samplerate, brate (CBR bitrate, ABR mean or VBR_q), mode, quality, vbr (0 = vbr_off, 3 = vbr_abr, 4 = vbr_mtrh)
     ("tag_noise_128", "noise", 30, 44100, 128, -1, -1, 0),
     ("tag_click_192_stereo", "click", 45, 44100, 192, 0, -1, 0),
     ("tag_sine_320_js", "sine", 20, 44100, 320, 1, -1, 0),
     ("tag_abr_click_128", "click", 45, 44100, 128, -1, -1, 3),
     ("tag_abr_gap_150_stereo", "gap", 30, 44100, 150, 0, -1, 3),
+    # vbr 4 = vbr_mtrh: "brate" is VBR_q (-V2, -V0)
+    ("tag_vbr_v2_noise", "noise", 30, 44100, 2, -1, -1, 4),
+    ("tag_vbr_v0_click", "click", 45, 44100, 0, -1, -1, 4),
+    ("tag_vbr_v4_sine_stereo", "sine", 24, 44100, 4, 0, -1, 4),
 ]
 
 

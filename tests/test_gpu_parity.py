@@ -96,6 +96,60 @@ def test_abr_batch_matches_oracle(lib, oracle_mod, cfg):
     assert len(sizes) > 1                                  # ABR: stream lengths depend on the signal
 
 
+@pytest.mark.parametrize("cfg", [
+    dict(S=16, F=24, fpl=8, q=2), dict(S=8, F=30, fpl=16, q=0), dict(S=4, F=20, fpl=3, q=4, mode=0, quality=5),
+    dict(S=4, F=16, fpl=8, q=0, sr=48000), dict(S=3, F=16, fpl=8, q=5, mode=3), dict(S=4, F=20, fpl=20, q=6, quality=6),
+])
+def test_vbr_batch_matches_oracle(lib, oracle_mod, cfg):
+    """VBR-new (vbr_mtrh, -V q): lg_kernel_vbr - per-band step search, fitting, and for the frames that do not
+    fit (click at -V0) the out-of-bits strategy; byte-identical to the port and to libmp3lame"""
+    S, F = cfg["S"], cfg["F"]
+    sr, q, mode, quality = cfg.get("sr", 44100), cfg["q"], cfg.get("mode", -1), cfg.get("quality", -1)
+    kinds = ("noise", "click", "sine", "gap")
+    pcm = np.stack([make_signal(kinds[s % 4], F * 1152, seed=60 + s) for s in range(S)])
+    enc = lib.BatchEncoder(S, sr, 2, q, mode, quality, frames_per_launch=cfg["fpl"], vbr=lib.VBR_MTRH)
+    _, a = enc.encode(pcm)
+    _, b = enc.flush()
+    enc.close()
+    for s in range(S):
+        want = oracle_mod.PortEncoder(sr, 2, q, mode, quality, vbr=4).encode_all(pcm[s, 0], pcm[s, 1])
+        if oracle_mod.have_ref():
+            ref = oracle_mod.RefEncoder(sr, 2, q, mode if mode >= 0 else 4, quality, vbr=4).encode_all(pcm[s, 0], pcm[s, 1])
+            assert want == ref, "oracle port and reference disagree"
+        assert a[s] + b[s] == want, "stream %d (%s)" % (s, kinds[s % 4])
+
+
+def test_config4_vbr_v2_full_size(lib, oracle_mod):
+    """BASELINE configs[3]: VBR -V2 (vbr_mtrh) on the sine + noise mix at 2048 streams x 16 frames; every stream structurally
+    (frame sync, frame length from its own bitrate index), a sample of streams byte for byte against the oracle - exact,
+    not tolerance-matched."""
+    S, F = 2048, 16
+    n = F * 1152
+    t = np.arange(n) / 44100.0
+    base = np.stack([8000 * np.sin(2 * np.pi * 440 * t) + 4000 * np.sin(2 * np.pi * 3300 * t),
+                     8000 * np.sin(2 * np.pi * 554.37 * t) + 3000 * np.sin(2 * np.pi * 7000 * t)])
+    rng = np.random.default_rng(2025)
+    pcm = np.rint(rng.integers(-1000, 1001, size=(S, 2, n)) + base[None]).astype(np.int16)
+    enc = lib.BatchEncoder(S, 44100, 2, 2, -1, -1, frames_per_launch=F, vbr=lib.VBR_MTRH)
+    n1, a = enc.encode(pcm)
+    n2, b = enc.flush()
+    enc.close()
+    assert n1 + n2 == S * (F + 1)
+    kbps = [0, 32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 320]
+    for s in range(S):
+        mp3 = a[s] + b[s]
+        pos, nfr = 0, 0
+        while pos < len(mp3):
+            assert mp3[pos] == 0xFF and mp3[pos + 1] == 0xFB, (s, pos)
+            idx = mp3[pos + 2] >> 4
+            assert 1 <= idx <= 14 and ((mp3[pos + 2] >> 1) & 1) == 0             # no padding in VBR
+            pos += 144000 * kbps[idx] // 44100
+            nfr += 1
+        assert pos == len(mp3) and nfr == F + 1, s
+    for s in list(range(0, S, 293)) + [S - 1]:
+        assert a[s] + b[s] == oracle_mod.PortEncoder(44100, 2, 2, -1, -1, vbr=4).encode_all(pcm[s, 0], pcm[s, 1]), s
+
+
 def test_lame_api_handle_matches_oracle(lib, oracle_mod):
     """the libmp3lame-compatible face: lame_init .. lame_encode_buffer .. lame_encode_flush on one handle"""
     x = make_signal("click", 50 * 1152, seed=3)
@@ -167,7 +221,7 @@ def test_unsupported_configurations_fail_loudly(lib):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()
     h = L.lame_init()
-    L.lame_set_VBR(h, 4)
+    L.lame_set_VBR(h, 2)                     # vbr_rh (VBR-old) is not implemented
     assert L.lame_init_params(h) == -1
     L.lame_close(h)
 
