@@ -259,10 +259,6 @@ __device__ __forceinline__ void lg_vset_scalefacs(LgVWarp *v, const LgQInfo &gi,
                     if (sc > 0 && (sc << ifqstepShift) > m) sc = m >> ifqstepShift;
                 }
             }
-#ifdef LG_VBR_DEBUG
-            if (blockIdx.x == 1 && (threadIdx.x >> 5) == 1 && sfb < 39 && qc.block_type == LG_SHORT)
-                printf("DBGS sfb %d sftmp %d gg %d sbg %x win %d min %d sc %d scale %d\n", sfb, v->sftmp[sfb], gi.global_gain, gi.sbg, w->window[sfb], v->vbrsfmin[sfb], sc, gi.scalefac_scale);
-#endif
             w->sfw[sfb] = sc;
         }
     }
@@ -304,7 +300,9 @@ __device__ __noinline__ void lg_valloc(const LgDevCfg *__restrict__ c, LgVWarp *
             int const ifqstepShift = (gi.scalefac_scale == 0) ? 1 : 2;
             int const psydiv = psymax < 18 ? psymax : 18;
             int maxsf1 = 0, maxsf2 = 0, minsf = 1000;
-            /* the window's bands below psydiv (part 1) and from psydiv on (part 2), vbrquantize.c:613-632 */
+            /* the window's bands below psydiv (part 1) and from psydiv on (part 2), vbrquantize.c:613-632.
+             * One signed loop on purpose: two back-to-back loops with an unsigned band counter came out of
+             * nvcc 12.9 with a wrong minimum on sm_100a (the emulator build of the same source was right). */
             for (int sfb = lane; sfb < LG_SFBMAX; sfb += 3) {
                 int const t = -v->sftmp[sfb];
                 if (sfb < psydiv) maxsf1 = max(maxsf1, t); else maxsf2 = max(maxsf2, t);
@@ -316,10 +314,6 @@ __device__ __noinline__ void lg_valloc(const LgDevCfg *__restrict__ c, LgVWarp *
             if (maxsf1 > 0) sbgv = max(sbgv, (maxsf1 + 7) >> 3);
             if (sbgv > 0 && ctx.mingain_s[lane] > (gi.global_gain - sbgv * 8)) sbgv = (gi.global_gain - ctx.mingain_s[lane]) >> 3;
             if (sbgv > 7) sbgv = 7;
-#ifdef LG_VBR_DEBUG
-            if (blockIdx.x == 1 && (threadIdx.x >> 5) == 1)
-                printf("DBGG lane %d maxsf1 %d maxsf2 %d minsf %d sbgv %d gg %d mg %d shift %d psydiv %u s1 %d s4 %d\n", lane, maxsf1, maxsf2, minsf, sbgv, gi.global_gain, ctx.mingain_s[lane], ifqstepShift, (unsigned) psydiv, v->sftmp[1], v->sftmp[4]);
-#endif
         }
         int const s0 = __shfl_sync(LG_FULL, sbgv, 0), s1 = __shfl_sync(LG_FULL, sbgv, 1), s2 = __shfl_sync(LG_FULL, sbgv, 2);
         int const min_sbg = min(7, min(s0, min(s1, s2)));
@@ -652,20 +646,9 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
         int const my_max = active ? mb[gr][ch] : 0;
         if (active && my_max > 0) {
             int const vbrmax = lg_vblock_sf(c, v, qc, ctx, lane);
-#ifdef LG_VBR_DEBUG
-            if (stream == 1 && frame == 0 && warp == 1 && lane == 0) {
-                printf("DBG vbrmax %d mnz %d bt %d mingain %d %d %d %d xrpow_max %.9g\n", vbrmax, qc.max_nonzero_coeff, qc.block_type, ctx.mingain_l, ctx.mingain_s[0], ctx.mingain_s[1], ctx.mingain_s[2], (double) gi.xrpow_max);
-                for (int i = 0; i < 39; i++) printf("DBG b%d sf %d min %d xmin %.9g eac %d len %d\n", i, v->vbrsf[i], v->vbrsfmin[i], (double) w->l3_xmin[i], w->eac[i], v->blen[i]);
-            }
-#endif
             lg_valloc(c, v, gi, qc, ctx, v->vbrsf, vbrmax, lane);
             lg_vbitcount(v, gi, qc, lane);
             (void) lg_vquantize_count(c, v, gi, qc, lane);
-#ifdef LG_VBR_DEBUG
-            if (stream == 1 && frame == 0 && warp == 1 && lane == 0)
-                printf("DBGQ gg %d sbg %x scale %d pre %d p2 %d p23 %d bv %d c1 %d ts %d %d %d c1t %d\n", gi.global_gain, gi.sbg, gi.scalefac_scale, gi.preflag, gi.part2_length, gi.part2_3_length,
-                       gi.big_values, gi.count1, gi.table_select[0], gi.table_select[1], gi.table_select[2], gi.count1table_select);
-#endif
         }
         /* reduce_bit_usage: granule 1 reads granule 0's scalefactors (scfsi), so the two granules take turns */
         uint8_t scfsi[4] = { 0, 0, 0, 0 };
@@ -694,11 +677,6 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
                 for (int k = 0; k < nch; k++) if (use_ch[g][k] > LG_MAX_BITS_PER_CHANNEL) fits = 0;
             }
         }
-#ifdef LG_VBR_DEBUG
-        if (stream == 1 && threadIdx.x == 0)
-            printf("DBGF frame %d use %d %d %d %d mb %d %d %d %d use_fr %d max_fr %d fits %d resv %d avg %d rmax %d maxfb %d pe %.9g %.9g %.9g %.9g\n", frame, use_ch[0][0], use_ch[0][1], use_ch[1][0], use_ch[1][1],
-                   mb[0][0], mb[0][1], mb[1][0], mb[1][1], use_fr, max_fr, fits, resv_size, avg, resv_max_m, maximum_framebits, (double) F->pe_use[0][0], (double) F->pe_use[0][1], (double) F->pe_use[1][0], (double) F->pe_use[1][1]);
-#endif
         if (!fits) {
             int max_ch[2][2] = { { 0, 0 }, { 0, 0 } }, max_gr[2] = { 0, 0 }, ok = 1, sum_fr = 0;
             for (int g = 0; g < 2; g++) {
