@@ -58,7 +58,28 @@ def reduce_over_ranks(frames, ms, device="cuda"):
 
 def noise_pcm(nstreams, nsamples, seed):
     rng = np.random.default_rng(seed)
+    if SIGNAL == "sine":      # two tones per channel + U[-1000,1000], every stream at its own start time
+        out = np.empty((nstreams, 2, nsamples), dtype=np.int16)
+        for s0 in range(0, nstreams, 128):
+            n = min(128, nstreams - s0)
+            t = (np.arange(nsamples)[None, :] + rng.integers(0, 44100, size=(n, 1))) / 44100.0
+            out[s0:s0 + n, 0] = np.rint(8000 * np.sin(2 * np.pi * 440 * t) + 4000 * np.sin(2 * np.pi * 3300 * t) + rng.integers(-1000, 1001, size=t.shape))
+            out[s0:s0 + n, 1] = np.rint(8000 * np.sin(2 * np.pi * 554.37 * t) + 3000 * np.sin(2 * np.pi * 7000 * t) + rng.integers(-1000, 1001, size=t.shape))
+        return out
     return rng.integers(-12000, 12001, size=(nstreams, 2, nsamples), dtype=np.int16)
+
+
+SIGNAL, BRATE, VBR = "noise", 128, 0       # configs[1]; --signal/--brate/--vbr select the other BASELINE configs
+
+
+def set_workload(args):
+    """configs[1] by default; `--signal sine --brate 320` = configs[2], `--signal sine --vbr 4 --brate 2` = configs[3] (VBR -V2)"""
+    global SIGNAL, BRATE, VBR, STREAMS, FRAMES, WORKLOAD
+    SIGNAL, BRATE, VBR, STREAMS, FRAMES = args.signal, args.brate, args.vbr, args.streams, args.frames
+    if (SIGNAL, BRATE, VBR, STREAMS, FRAMES) != ("noise", 128, 0, 512, 8):
+        rate = {0: "CBR %d kbps" % BRATE, 3: "ABR %d kbps" % BRATE, 4: "VBR-new -V%d" % BRATE}[VBR]
+        sig = "white noise U[-12000,12000]" if SIGNAL == "noise" else "two tones per channel + U[-1000,1000]"
+        WORKLOAD = "%d frames/GPU = %d streams x %d frames, 44.1 kHz stereo %s, %s joint stereo q3" % (STREAMS * FRAMES, STREAMS, FRAMES, sig, rate)
 
 
 class ClockSampler:
@@ -135,7 +156,7 @@ def cpu_baseline(seconds=12.0):
     kind = "reference" if oracle.have_ref() else "port"
     Enc = oracle.RefEncoder if kind == "reference" else oracle.PortEncoder
     pcm = noise_pcm(1, 1152 * 256, 777)[0]
-    enc = Enc(44100, 2, 128, 4, -1)
+    enc = Enc(44100, 2, BRATE, 4, -1, vbr=VBR)
     frames, t0 = 0, time.perf_counter()
     while True:
         enc.encode(pcm[0], pcm[1])
@@ -145,7 +166,7 @@ def cpu_baseline(seconds=12.0):
             break
     enc.close()
     return {"value": frames / dt, "unit": "frames/s", "cores": 1, "kind": kind,
-            "sample": "%d frames of the same white-noise CBR-128 workload, one stream, one host thread, %.1f s" % (frames, dt)}
+            "sample": "%d frames of the same workload, one stream, one host thread, %.1f s" % (frames, dt)}
 
 
 def run_reference_arm(args):
@@ -161,7 +182,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     nsamp = FRAMES * 1152
     pcm = noise_pcm(STREAMS, nsamp, 4242)
-    encs = [Enc(44100, 2, 128, 4, -1) for _ in range(STREAMS)]
+    encs = [Enc(44100, 2, BRATE, 4, -1, vbr=VBR) for _ in range(STREAMS)]
     pool = ThreadPoolExecutor(max_workers=cores)
 
     def step():
@@ -181,7 +202,7 @@ def run_reference_arm(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams": STREAMS, "frames_per_stream_per_step": FRAMES},
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
-                             "sample": "the full step (512 persistent streams x 8 frames) on %d host threads" % cores},
+                             "sample": "the full step (%d persistent streams x %d frames) on %d host threads" % (STREAMS, FRAMES, cores)},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -205,8 +226,12 @@ def main():
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--frames", type=int, default=FRAMES)
+    ap.add_argument("--brate", type=int, default=128, help="kbps (CBR/ABR) or the -V level with --vbr 4")
+    ap.add_argument("--vbr", type=int, default=0, choices=(0, 3, 4), help="0 CBR, 3 ABR, 4 VBR-new (vbr_mtrh)")
+    ap.add_argument("--signal", default="noise", choices=("noise", "sine"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    set_workload(args)
     if args.impl == "reference":
         run_reference_arm(args)
         return
@@ -229,7 +254,7 @@ def main():
     # the global job is world*S independent streams; this rank owns a contiguous shard of them
     lo, hi = shard_range(world * S, rank, world)
     assert hi - lo == S
-    enc = lame_b200.BatchEncoder(S, 44100, 2, 128, -1, -1, frames_per_launch=F, device=local)
+    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, -1, frames_per_launch=F, device=local, vbr=VBR)
     pcm = noise_pcm(S, nsamp + 224, 1000 + rank)            # +224: the first launch needs 1152*F + 224 user samples
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -271,9 +296,9 @@ def main():
 
     # ---------------- e2e: public API, host buffers in, MP3 bytes out
     enc.close()
-    enc = lame_b200.BatchEncoder(S, 44100, 2, 128, -1, -1, frames_per_launch=F, device=local)
+    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, -1, frames_per_launch=F, device=local, vbr=VBR)
     step_pcm = [noise_pcm(S, nsamp, 5000 + 17 * i + rank) for i in range(4)]
-    out = np.empty((S, int(1.25 * nsamp) + 7200 + 4096), dtype=np.uint8)
+    out = np.empty((S, int(1.25 * nsamp) + 7200 + 4096 + 1440 * F), dtype=np.uint8)
     nbytes = np.zeros(S, dtype=np.int32)
     enc.encode_raw(pcm, out, nbytes)                          # primes the 528+... encoder delay: afterwards every call yields F frames
     for i in range(args.warmup):
@@ -296,6 +321,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         q_ms = kms[3] / args.steps
+        qname = "lg_kernel_vbr" if VBR == 4 else "lg_kernel_quant"
         achieved = ALG_BYTES_QUANT * S * F / (q_ms * 1e-3) / 1e9
         a_ms = (kms[0] + kms[1] + kms[2]) / args.steps
         line = {
@@ -309,8 +335,8 @@ def main():
                     "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes_last_step": total_bytes,
                     "note": "lamegpu_batch_encode_packed: pinned staging + H2D + 5 kernels + D2H of packed bytes + host header splice (threads=%d)" % (os.cpu_count() or 1)},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "lg_kernel_quant", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic("lg_kernel_quant") if (S, F) == (STREAMS, FRAMES) else None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": qname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": measured_traffic(qname) if (S, F, SIGNAL, BRATE, VBR) == (512, 8, "noise", 128, 0) else None, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary.json)",
                          "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms,
                          "note": "latency/issue-bound integer + table-lookup kernel (SURVEY 8d): HBM fraction is reported, not the binding limit"},
