@@ -1,4 +1,4 @@
-"""B200 batched MP3 (MPEG-1 Layer III, CBR) encoder behind the libmp3lame API - Python host side.
+"""B200 batched MP3 (MPEG-1 Layer III; CBR, ABR, VBR-new) encoder behind the libmp3lame API - Python host side.
 
 The product is the C-ABI library ``liblamegpu.so`` (``csrc/``, declared in ``include/lamegpu.h``): hand-written
 sm_100a CUDA kernels for the encode hot path plus the thin host code the reference keeps serial (PCM
@@ -54,6 +54,7 @@ def load_library(path=None):
         "lame_set_VBR_mean_bitrate_kbps": (c_int, [c_void_p, c_int]), "lame_get_VBR_mean_bitrate_kbps": (c_int, [c_void_p]),
         "lame_set_VBR_q": (c_int, [c_void_p, c_int]), "lame_get_VBR_q": (c_int, [c_void_p]),
         "lamegpu_batch_open_ex": (c_void_p, [c_int] * 9),
+        "lamegpu_batch_open_rs": (c_void_p, [c_int] * 10),
         "lame_set_bWriteVbrTag": (c_int, [c_void_p, c_int]), "lame_get_bWriteVbrTag": (c_int, [c_void_p]),
         "lame_init_params": (c_int, [c_void_p]),
         "lame_get_framesize": (c_int, [c_void_p]), "lame_get_frameNum": (c_int, [c_void_p]),
@@ -102,7 +103,7 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
+    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lamegpu_batch_open_rs", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
@@ -119,7 +120,7 @@ def _as_i16(a):
 class Encoder:
     """One stream through the libmp3lame-compatible entry points (same semantics and error codes)."""
 
-    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1, write_tag=False, vbr=VBR_OFF):
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=NOT_SET, quality=-1, write_tag=False, vbr=VBR_OFF, out_samplerate=0):
         self._lib = load_library()
         self._h = self._lib.lame_init()
         if not self._h:
@@ -127,6 +128,8 @@ class Encoder:
         L = self._lib
         L.lame_set_in_samplerate(self._h, samplerate)
         L.lame_set_num_channels(self._h, channels)
+        if out_samplerate:
+            L.lame_set_out_samplerate(self._h, out_samplerate)     # else chosen by lame_init_params; resampled on the device when it differs
         if vbr == VBR_ABR:
             L.lame_set_VBR(self._h, VBR_ABR)
             if brate:
@@ -188,10 +191,10 @@ class BatchEncoder:
     """`nstreams` independent streams with one configuration, encoded together on one GPU."""
 
     def __init__(self, nstreams, samplerate=44100, channels=2, brate=128, mode=-1, quality=-1,
-                 frames_per_launch=8, device=0, vbr=VBR_OFF):
+                 frames_per_launch=8, device=0, vbr=VBR_OFF, out_samplerate=0):
         self._lib = load_library()
         self.nstreams, self.frames_per_launch = int(nstreams), int(frames_per_launch)
-        self._h = self._lib.lamegpu_batch_open_ex(samplerate, channels, brate, mode, quality, vbr, self.nstreams,
+        self._h = self._lib.lamegpu_batch_open_rs(samplerate, out_samplerate, channels, brate, mode, quality, vbr, self.nstreams,
                                                   self.frames_per_launch, device)
         if not self._h:
             raise LameGpuError("lamegpu_batch_open failed (unsupported configuration, no CUDA device, or out of memory)")

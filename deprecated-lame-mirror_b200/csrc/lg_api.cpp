@@ -21,6 +21,8 @@
 
 namespace {
 
+enum { LG_RS_HIST = 48 };      /* input samples kept before a chunk's first one: the filter reaches filter_l/2 + 1 <= 17 back */
+
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 static const bool g_timing = getenv("LAMEGPU_TIMING") != nullptr;
 
@@ -31,6 +33,16 @@ struct Stream {
     std::vector<int16_t> pcm16[2];     /* timeline samples from index tbase on */
     std::vector<float> pcmf[2];        /* same, already through pcm_transform, once a float entry point was used */
     bool float_mode = false;
+    /* input-rate conversion (util.c:531): the stream's input samples (through pcm_transform) from absolute index
+     * raw_base on, the reference's per-call bookkeeping replayed as a list of chunks, the input clock, and the end
+     * of the timeline the chunks cover.  The samples themselves are made on the device (kernel R). */
+    struct Chunk { double itime; long in_base, out_pos; int count; };
+    bool rs_mode = false;
+    std::vector<float> raw[2];
+    long raw_base = -LG_RS_HIST;
+    std::vector<Chunk> chunks;
+    double rs_itime = 0;
+    long rs_tend = 528;
     long tbase = -LG_PCM_HIST;         /* timeline index of element 0 */
     long frames_done = 0;
     long mf_samples_to_encode = 576 + 1152;   /* ENCDELAY + POSTDELAY, lame.c:2299 */
@@ -54,10 +66,12 @@ struct Stream {
     {
         for (int c = 0; c < 2; c++) { pcm16[c].assign(LG_PCM_HIST + 528, 0); pcmf[c].clear(); }
         float_mode = false; tbase = -LG_PCM_HIST; frames_done = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
+        for (int c = 0; c < 2; c++) raw[c].assign(LG_RS_HIST, 0.f);
+        raw_base = -LG_RS_HIST; chunks.clear(); rs_itime = 0; rs_tend = 528;
         bw.reset(); out.clear();
         tag = Tag();
     }
-    long tend() const { return tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()); }
+    long tend() const { return rs_mode ? rs_tend : tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()); }
     long frames_ready() const
     {
         long const have = tend();
@@ -83,6 +97,18 @@ struct Stream {
     void drop_consumed()
     {
         long const keep_from = 1152 * frames_done - LG_PCM_HIST;
+        if (rs_mode) {
+            /* chunks that end before the next window, and the input samples only they needed */
+            size_t n = 0;
+            while (n < chunks.size() && chunks[n].out_pos + chunks[n].count <= keep_from) n++;
+            chunks.erase(chunks.begin(), chunks.begin() + n);
+            long const from = (chunks.empty() ? raw_base + (long) raw[0].size() : chunks[0].in_base) - LG_RS_HIST;
+            if (from > raw_base) {
+                for (int c = 0; c < 2; c++) raw[c].erase(raw[c].begin(), raw[c].begin() + (from - raw_base));
+                raw_base = from;
+            }
+            return;
+        }
         long const d = keep_from - tbase;
         if (d <= 0) return;
         if (float_mode) for (int c = 0; c < 2; c++) pcmf[c].erase(pcmf[c].begin(), pcmf[c].begin() + d);
@@ -210,7 +236,50 @@ struct lamegpu_batch {
             if (maxf == 0) break;
             size_t const stride = lg_engine_pcm_stride(eng);
             double const t0 = now_ms();
-            if (any_float) {
+            if (cfg.resample) {
+                /* kernel R makes the window: stage the input samples and the chunks that overlap it */
+                int const reach = cfg.rs_filter_l - cfg.rs_filter_l / 2;
+                std::atomic<int> most(0), bad(0);
+                auto window = [&](int s, long &t0, long &t1, size_t &nck) {
+                    const Stream &x = st[s];
+                    t0 = 1152 * x.frames_done - LG_PCM_HIST; t1 = t0 + (long) nfr[s] * 1152 + LG_PCM_HALO;
+                    nck = 0;
+                    while (nck < x.chunks.size() && x.chunks[nck].out_pos < t1) nck++;
+                };
+                for (int s = 0; s < S; s++) {
+                    if (!nfr[s]) continue;
+                    long t0, t1; size_t nck;
+                    window(s, t0, t1, nck);
+                    if ((int) nck > most.load()) most.store((int) nck);
+                }
+                if (lg_engine_reserve_chunks(eng, most.load()) != 0) return -2;
+                size_t const raw_stride = lg_engine_raw_stride(eng);
+                int const cap = lg_engine_chunk_cap(eng);
+                float *hr = lg_engine_host_raw(eng);
+                LgRsChunk *hc = lg_engine_host_chunks(eng);
+                int *hn = lg_engine_host_rs_counts(eng);
+                parallel_for(S, [&](int s) {
+                    hn[2 * s] = hn[2 * s + 1] = 0;
+                    if (!nfr[s]) return;
+                    const Stream &x = st[s];
+                    long t0, t1; size_t nck;
+                    window(s, t0, t1, nck);
+                    long hi = 0;
+                    for (size_t i = 0; i < nck; i++) {
+                        const Stream::Chunk &c = x.chunks[i];
+                        LgRsChunk &o = hc[(size_t) s * cap + i];
+                        o.itime = c.itime; o.in_base = c.in_base - x.raw_base; o.out_pos = (int32_t) (c.out_pos - t0); o.count = c.count;
+                        long const klast = std::min<long>(c.count, t1 - c.out_pos) - 1;
+                        hi = std::max(hi, c.in_base + (long) floor((double) klast * cfg.rs_ratio - c.itime) + reach + 1 - x.raw_base);
+                    }
+                    if (hi > (long) raw_stride || hi > (long) x.raw[0].size()) { bad.store(1); return; }
+                    for (int c = 0; c < 2; c++) memcpy(hr + ((size_t) s * 2 + c) * raw_stride, x.raw[c].data(), (size_t) hi * sizeof(float));
+                    hn[2 * s] = (int) nck; hn[2 * s + 1] = (int) (t1 - t0);
+                });
+                if (bad.load()) { fprintf(stderr, "lamegpu: resampler staging overflow\n"); return -2; }
+                any_float = 1;
+            }
+            else if (any_float) {
                 if (lg_engine_need_float_pcm(eng) != 0) return -2;
                 float *hp = lg_engine_host_pcmf(eng);
                 parallel_for(S, [&](int s) {
@@ -259,11 +328,54 @@ struct lamegpu_batch {
         return done;
     }
 
+    /* util.c:531 fill_buffer_resample as lame_encode_buffer_sample_t (lame.c:1671) drives it, bookkeeping only: the `n`
+     * input samples of one call are consumed in chunks of at most 1152 output samples.  Output sample k of a chunk
+     * sits at input time k*ratio - itime and needs the inputs up to floor(that) + filter_l - filter_l/2, so a chunk
+     * ends at the first k whose window passes the end of the call's data (found by bisection: that index grows with k). */
+    void rs_schedule(Stream &x, int n)
+    {
+        double const ratio = cfg.rs_ratio;
+        int const filter_l = cfg.rs_filter_l, reach = filter_l - filter_l / 2;
+        long in_ptr = x.raw_base + (long) x.raw[0].size() - n;
+        int remaining = n;
+        while (remaining > 0) {
+            double const itime = x.rs_itime;
+            auto jof = [&](int k) { return (int) floor((double) k * ratio - itime); };
+            int lo = 0, hi = 1152;                         /* first k in [0, 1152) with reach + j(k) >= remaining, else 1152 */
+            while (lo < hi) {
+                int const mid = (lo + hi) >> 1;
+                if (reach + jof(mid) >= remaining) hi = mid; else lo = mid + 1;
+            }
+            int const count = lo;
+            int const j = jof(count < 1152 ? count : 1151);
+            int const used = std::min(remaining, reach + j);
+            if (count > 0) x.chunks.push_back(Stream::Chunk{ itime, in_ptr, x.rs_tend, count });
+            x.rs_itime += (double) used - (double) count * ratio;
+            in_ptr += used; remaining -= used;
+            x.rs_tend += count;
+            if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;     /* lame.c:1735 */
+            x.mf_samples_to_encode += count;
+        }
+    }
+    template <class T> void feed_rs(Stream &x, const T *l, const T *r, int n, int jump, float scale)
+    {
+        float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
+        float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
+        size_t const at = x.raw[0].size();
+        x.raw[0].resize(at + n); x.raw[1].resize(at + n);
+        for (int i = 0; i < n; i++) {
+            float const xl = (float) l[(size_t) i * jump], xr = (float) r[(size_t) i * jump];
+            x.raw[0][at + i] = xl * m00 + xr * m01;
+            x.raw[1][at + i] = xl * m10 + xr * m11;
+        }
+        rs_schedule(x, n);
+    }
     void feed16(int s, const short *l, const short *r, int n)
     {
         Stream &x = st[s];
         if (n <= 0) return;
         if (!r) r = l;
+        if (x.rs_mode) { feed_rs<short>(x, l, r, n, 1, 1.0f); return; }
         if (x.float_mode) {
             float const m00 = cfg.pcm_transform[0][0], m01 = cfg.pcm_transform[0][1];
             float const m10 = cfg.pcm_transform[1][0], m11 = cfg.pcm_transform[1][1];
@@ -288,6 +400,7 @@ struct lamegpu_batch {
         Stream &x = st[s];
         if (n <= 0) return;
         if (!r) r = l;
+        if (x.rs_mode) { feed_rs<T>(x, l, r, n, jump, scale); return; }
         x.to_float(&cfg);
         float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
         float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
@@ -307,6 +420,30 @@ struct lamegpu_batch {
     {
         Stream &x = st[s];
         if (x.mf_samples_to_encode < 1) return;
+        if (x.rs_mode) {
+            /* lame.c:2077-2117 with resampling: zero samples go in, in bunches sized from the fill of the frame buffer,
+             * until the frames counted at the start have come out.  Every frame that is ready has been encoded
+             * (pump() runs after each feed), so the buffer fill is what the timeline holds beyond them. */
+            int samples_to_encode = (int) (x.mf_samples_to_encode - 1152);
+            samples_to_encode += 16. / cfg.rs_ratio;
+            int end_padding = 1152 - (samples_to_encode % 1152);
+            if (end_padding < 576) end_padding += 1152;
+            x.tag.enc_padding = end_padding;
+            int frames_left = (samples_to_encode + end_padding) / 1152;
+            long virt_done = x.frames_done;                 /* frames the reference would have encoded so far */
+            while (frames_left > 0) {
+                int bunch = (int) (1904 - (x.rs_tend - 1152 * virt_done));
+                bunch *= cfg.rs_ratio;
+                if (bunch > 1152) bunch = 1152;
+                if (bunch < 1) bunch = 1;
+                for (int c = 0; c < 2; c++) x.raw[c].insert(x.raw[c].end(), (size_t) bunch, 0.f);
+                rs_schedule(x, bunch);
+                long const ready = x.rs_tend >= 1152 * virt_done + 1904 ? (x.rs_tend - 1904 - 1152 * virt_done) / 1152 + 1 : 0;
+                if (ready > 0) frames_left -= 1;
+                virt_done += ready;
+            }
+            return;
+        }
         long const samples_to_encode = x.mf_samples_to_encode - 1152;
         long end_padding = 1152 - (samples_to_encode % 1152);
         if (end_padding < 576) end_padding += 1152;
@@ -332,11 +469,17 @@ extern "C" {
 
 lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr, int nstreams, int frames_per_launch, int device)
 {
+    return lamegpu_batch_open_rs(samplerate, 0, channels, brate, mode, quality, vbr, nstreams, frames_per_launch, device);
+}
+
+lamegpu_batch *lamegpu_batch_open_rs(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, int nstreams,
+                                     int frames_per_launch, int device)
+{
     lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
     if (!b) return NULL;
-    if (lg_setup(&b->cfg, samplerate, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr) != 0) {
-        fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d, channels %d, brate %d, mode %d, quality %d, vbr %d)\n",
-                samplerate, channels, brate, mode, quality, vbr);
+    if (lg_setup(&b->cfg, samplerate_in, samplerate_out, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr) != 0) {
+        fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d -> %d, channels %d, brate %d, mode %d, quality %d, vbr %d)\n",
+                samplerate_in, samplerate_out, channels, brate, mode, quality, vbr);
         delete b;
         return NULL;
     }
@@ -347,7 +490,7 @@ lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, in
     b->nthreads = (int) std::max(1u, std::min(hw ? hw : 1u, 64u));
     if (const char *e = getenv("LAMEGPU_THREADS")) b->nthreads = std::max(1, atoi(e));
     b->st.resize(nstreams);
-    for (auto &s : b->st) { s.init(); s.last_bitrate_index = b->cfg.bitrate_index; }
+    for (auto &s : b->st) { s.rs_mode = b->cfg.resample != 0; s.init(); s.last_bitrate_index = b->cfg.bitrate_index; }
     return b;
 }
 
@@ -562,13 +705,12 @@ int lame_init_params(lame_global_flags *g)
 {
     if (!ok(g)) return -1;
     if (g->VBR == vbr_rh) { fprintf(stderr, "lamegpu: vbr_rh (VBR-old) is not implemented on the GPU path\n"); return -1; }
-    if (g->samplerate_out && g->samplerate_out != g->samplerate_in) { fprintf(stderr, "lamegpu: resampling is not implemented\n"); return -1; }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
     int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh);        /* both select VBR_new_iteration_loop, encoder.c:531 */
-    g->b = lamegpu_batch_open_ex(g->samplerate_in, g->num_channels, is_vbr ? g->vbr_q : (g->VBR == vbr_abr ? g->mean_brate : g->brate),
+    g->b = lamegpu_batch_open_rs(g->samplerate_in, g->samplerate_out, g->num_channels, is_vbr ? g->vbr_q : (g->VBR == vbr_abr ? g->mean_brate : g->brate),
                                  g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? 4 : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
     if (!g->b) return -1;
-    g->samplerate_out = g->samplerate_in;
+    g->samplerate_out = g->b->cfg.samplerate;
     g->brate = g->b->cfg.brate;
     g->mean_brate = g->b->cfg.vbr_mean_kbps;
     g->quality = g->b->cfg.quality;
@@ -727,12 +869,12 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     default: nStereoMode = 7; break;
     }
     int nSourceFreq;
-    if (c->samplerate <= 32000) nSourceFreq = 0;
-    else if (c->samplerate == 48000) nSourceFreq = 2;
-    else if (c->samplerate > 48000) nSourceFreq = 3;
+    if (c->samplerate_in <= 32000) nSourceFreq = 0;
+    else if (c->samplerate_in == 48000) nSourceFreq = 2;
+    else if (c->samplerate_in > 48000) nSourceFreq = 3;
     else nSourceFreq = 1;
     int const bNonOptimal = (c->short_blocks == 2 /* forced */ || c->short_blocks == 3 /* dispensed */ ||
-                             (c->disable_reservoir && c->vbr_mean_kbps < 320) || c->athtype == 0 || c->samplerate <= 32000);
+                             (c->disable_reservoir && c->vbr_mean_kbps < 320) || c->athtype == 0 || c->samplerate_in <= 32000);
     unsigned char const nMisc = (unsigned char) (c->noise_shaping + (nStereoMode << 2) + (bNonOptimal << 5) + (nSourceFreq << 6));
     put_be32(p + k, (unsigned long) nQuality); k += 4;
     memcpy(p + k, "LAME3.99r", 9); k += 9;                  /* get_lame_tag_encoder_short_version(), version.c:148 */

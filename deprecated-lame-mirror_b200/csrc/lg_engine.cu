@@ -1,7 +1,7 @@
 // lg_engine.cu - device side of the batch engine: owns the HBM buffers of one configuration
 // (S streams x up to F frames per launch), the four kernels and the copies.
 //
-//   H2D  pcm (int16 or float, pinned)  ->  A analysis  ->  B scan  ->  C mdct  ->  D quantise  ->  E pack  ->  D2H bytes
+//   H2D  pcm (int16 or float, pinned)  [->  R resample, when the input rate differs]  ->  A analysis  ->  B scan  ->  C mdct  ->  D quantise  ->  E pack  ->  D2H bytes
 //
 // All work of one launch goes to one CUDA stream; the host (lg_bitstream.cpp) only interleaves the packed
 // payload bytes with the frame headers.  There is no CPU fallback: without a CUDA device lg_engine_create() fails and says so.
@@ -11,9 +11,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <new>
 #include "lg_compat.h"
 #include "lg_types.h"
+#include "lg_k_resample.cuh"
 #include "lg_k_analysis.cuh"
 #include "lg_k_scan.cuh"
 #include "lg_k_mdct.cuh"
@@ -61,9 +63,12 @@ struct lg_engine {
     /* pinned host staging */
     int16_t *h_pcm16; float *h_pcmf; int *h_nfr;
     LgFrameOut *h_fout; unsigned char *h_pay, *h_hdr;
+    /* kernel R (input-rate conversion): raw input samples, the chunk list and the per-stream header, device + pinned */
+    size_t raw_stride; int chunk_cap;
+    float *d_raw, *h_raw; LgRsChunk *d_rsc, *h_rsc; LgRsStream *d_rss, *h_rss;
     lgStream_t stream;
 #ifndef LG_EMULATE
-    cudaEvent_t ev[7];
+    cudaEvent_t ev[8];
 #endif
     float last_ms[6];
     long launches;
@@ -83,6 +88,11 @@ extern "C" const LgFrameOut *lg_engine_host_fout(const lg_engine *e) { return e-
 extern "C" const float *lg_engine_last_kernel_ms(const lg_engine *e) { return e->last_ms; }
 extern "C" long lg_engine_launch_count(const lg_engine *e) { return e->launches; }
 extern "C" void *lg_engine_device_pcm16(lg_engine *e) { return e->d_pcm16; }
+extern "C" size_t lg_engine_raw_stride(const lg_engine *e) { return e->raw_stride; }
+extern "C" float *lg_engine_host_raw(lg_engine *e) { return e->h_raw; }
+extern "C" LgRsChunk *lg_engine_host_chunks(lg_engine *e) { return e->h_rsc; }
+extern "C" int *lg_engine_host_rs_counts(lg_engine *e) { return (int *) e->h_rss; }
+extern "C" int lg_engine_chunk_cap(const lg_engine *e) { return e->chunk_cap; }
 
 /* initial per-stream state: lame.c:2274 lame_init_internal_flags, lame.c:962, psymodel.c:1897-1922 and :2075 */
 static void lg_initial_state(const LgDevCfg *c, LgStreamState *s)
@@ -113,9 +123,10 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_xr);
     lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout); lg_dev_free(e->d_pay); lg_dev_free(e->d_hdr);
     lg_dev_free(e->d_state); lg_dev_free(e->d_state0); lg_dev_free(e->d_nfr);
+    lg_dev_free(e->d_raw); lg_dev_free(e->d_rsc); lg_dev_free(e->d_rss); lg_host_free(e->h_raw); lg_host_free(e->h_rsc); lg_host_free(e->h_rss);
     lg_host_free(e->h_pcm16); lg_host_free(e->h_pcmf); lg_host_free(e->h_nfr); lg_host_free(e->h_pay); lg_host_free(e->h_hdr); lg_host_free(e->h_fout);
 #ifndef LG_EMULATE
-    for (int i = 0; i < 7; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 8; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
 #endif
     free(e);
@@ -175,12 +186,24 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     bad |= lg_host_malloc((void **) &e->h_pay, S * e->pay_stride);
     bad |= lg_host_malloc((void **) &e->h_hdr, S * F * LG_HDR_STRIDE);
     bad |= lg_host_malloc((void **) &e->h_fout, S * F * sizeof(LgFrameOut));
+    if (cfg->resample) {
+        /* inputs behind one window: its own samples, one more reference call (<= 1152 outputs) before it, the filter taps */
+        e->raw_stride = (size_t) ceil((double) (e->pcm_stride + 1152) * cfg->rs_ratio) + 128;
+        e->chunk_cap = 2 * max_frames + 16;
+        bad |= lg_dev_malloc((void **) &e->d_raw, S * 2 * e->raw_stride * sizeof(float));
+        bad |= lg_host_malloc((void **) &e->h_raw, S * 2 * e->raw_stride * sizeof(float));
+        bad |= lg_dev_malloc((void **) &e->d_rsc, S * e->chunk_cap * sizeof(LgRsChunk));
+        bad |= lg_host_malloc((void **) &e->h_rsc, S * e->chunk_cap * sizeof(LgRsChunk));
+        bad |= lg_dev_malloc((void **) &e->d_rss, S * sizeof(LgRsStream));
+        bad |= lg_host_malloc((void **) &e->h_rss, S * sizeof(LgRsStream));
+        bad |= lg_dev_malloc((void **) &e->d_pcmf, S * 2 * e->pcm_stride * sizeof(float));
+    }
     if (bad) { fprintf(stderr, "lamegpu: out of memory (S=%d F=%d)\n", nstreams, max_frames); lg_engine_destroy(e); return NULL; }
 #ifdef LG_EMULATE
     memcpy(e->dcfg, cfg, sizeof *cfg);
 #else
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
-    for (int i = 0; i < 7; i++) cudaEventCreate(&e->ev[i]);
+    for (int i = 0; i < 8; i++) cudaEventCreate(&e->ev[i]);
     if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
@@ -211,7 +234,27 @@ extern "C" int lg_engine_need_float_pcm(lg_engine *e)
 {
     if (e->h_pcmf) return 0;
     size_t const n = (size_t) e->S * 2 * e->pcm_stride * sizeof(float);
-    if (lg_host_malloc((void **) &e->h_pcmf, n) || lg_dev_malloc((void **) &e->d_pcmf, n)) return -1;
+    if (lg_host_malloc((void **) &e->h_pcmf, n)) return -1;
+    if (!e->d_pcmf && lg_dev_malloc((void **) &e->d_pcmf, n)) return -1;
+    return 0;
+}
+
+/* a launch whose streams were fed in many small calls has more chunks than usual: grow the chunk list (contents are
+ * restaged by the caller afterwards) */
+extern "C" int lg_engine_reserve_chunks(lg_engine *e, int per_stream)
+{
+    if (per_stream <= e->chunk_cap) return 0;
+#ifndef LG_EMULATE
+    LG_CHECK(cudaStreamSynchronize(e->stream));       /* nothing in flight may still read the old list */
+#endif
+    int const cap = per_stream + per_stream / 2;
+    LgRsChunk *d = NULL, *h = NULL;
+    if (lg_dev_malloc((void **) &d, (size_t) e->S * cap * sizeof(LgRsChunk)) || lg_host_malloc((void **) &h, (size_t) e->S * cap * sizeof(LgRsChunk))) {
+        lg_dev_free(d); lg_host_free(h);
+        return -1;
+    }
+    lg_dev_free(e->d_rsc); lg_host_free(e->h_rsc);
+    e->d_rsc = d; e->h_rsc = h; e->chunk_cap = cap;
     return 0;
 }
 
@@ -275,7 +318,24 @@ extern "C" int lg_engine_sync(lg_engine *e)
 extern "C" int lg_engine_encode(lg_engine *e, int nframes, int use_float)
 {
     size_t const S = e->S, F = e->F;
-    if (use_float) {
+    if (e->hcfg.resample) {
+        /* kernel R turns the staged input samples + chunk lists into the float PCM window */
+        int const tiles = (int) ((e->pcm_stride + 255) / 256);
+        LG_COPY_H2D(e->d_raw, e->h_raw, S * 2 * e->raw_stride * sizeof(float), e->stream);
+        LG_COPY_H2D(e->d_rsc, e->h_rsc, S * e->chunk_cap * sizeof(LgRsChunk), e->stream);
+        LG_COPY_H2D(e->d_rss, e->h_rss, S * sizeof(LgRsStream), e->stream);
+#ifndef LG_EMULATE
+        cudaEventRecord(e->ev[6], e->stream);
+#endif
+        LG_LAUNCH(lg_kernel_resample, (int) S * tiles, 256, 0, e->stream, e->dcfg, e->d_raw, (int) e->raw_stride, e->d_rsc, e->chunk_cap, e->d_rss,
+                  e->d_pcmf, (int) e->pcm_stride, tiles);
+#ifndef LG_EMULATE
+        cudaEventRecord(e->ev[7], e->stream);
+#endif
+        e->launches += 1;
+        use_float = 1;
+    }
+    else if (use_float) {
         if (!e->h_pcmf) return -1;
         LG_COPY_H2D(e->d_pcmf, e->h_pcmf, S * 2 * e->pcm_stride * sizeof(float), e->stream);
     }
@@ -285,7 +345,11 @@ extern "C" int lg_engine_encode(lg_engine *e, int nframes, int use_float)
     LG_COPY_D2H(e->h_fout, e->d_fout, S * F * sizeof(LgFrameOut), e->stream);
     LG_COPY_D2H(e->h_pay, e->d_pay, S * e->pay_stride, e->stream);
     LG_COPY_D2H(e->h_hdr, e->d_hdr, S * F * LG_HDR_STRIDE, e->stream);
-    return lg_engine_sync(e);
+    if (lg_engine_sync(e) != 0) return -1;
+#ifndef LG_EMULATE
+    if (e->hcfg.resample) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]); e->last_ms[5] = ms; }
+#endif
+    return 0;
 }
 
 /* test/debug hook: copy an intermediate device buffer to the host.

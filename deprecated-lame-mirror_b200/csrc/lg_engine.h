@@ -7,11 +7,18 @@
 extern "C" {
 #endif
 typedef struct lg_engine lg_engine;
-int lg_setup(LgDevCfg *c, int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 vbr_off, 3 vbr_abr */);
+int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out /* 0 = as lame_init_params picks it */, int channels, int brate, int mode, int quality,
+             int vbr /* 0 vbr_off, 3 vbr_abr, 4 vbr_mtrh (brate = VBR_q) */);
 lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device);
 void lg_engine_destroy(lg_engine *e);
 int  lg_engine_reset_streams(lg_engine *e, int first, int count);
 int  lg_engine_need_float_pcm(lg_engine *e);
+int  lg_engine_reserve_chunks(lg_engine *e, int per_stream);
+size_t lg_engine_raw_stride(const lg_engine *e);
+float *lg_engine_host_raw(lg_engine *e);
+LgRsChunk *lg_engine_host_chunks(lg_engine *e);
+int *lg_engine_host_rs_counts(lg_engine *e);          /* per stream: { nchunks, win_n } */
+int  lg_engine_chunk_cap(const lg_engine *e);
 int  lg_engine_encode(lg_engine *e, int nframes, int use_float);
 int  lg_engine_run_device(lg_engine *e, int nframes, int use_float);
 int  lg_engine_sync(lg_engine *e);

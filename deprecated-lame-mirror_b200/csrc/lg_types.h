@@ -37,6 +37,8 @@
 #define LG_MAX_BITS_PER_GRANULE 7680
 #define LG_PCM_HIST 576                 /* samples kept before the first frame of a batch */
 #define LG_PCM_HALO 1328                /* HIST + 752 look-ahead (encoder.c:254-299) */
+#define LG_RS_BPC 320                   /* util.h BPC: fractional-offset filters each side of the resampler */
+#define LG_RS_TAPS 33                   /* filter_l + 1 <= 33 taps */
 #define LG_GR_SPAN 1328                 /* samples one granule's analysis touches: [576g+576, 576g+1904) */
 
 enum { LG_NORM = 0, LG_START = 1, LG_SHORT = 2, LG_STOP = 3 };
@@ -98,7 +100,19 @@ typedef struct {
     /* scalefactor band of every line: long blocks (22 bands) and short blocks after reordering (39 = 13 x 3 windows) */
     uint8_t line_sfb_l[576], line_sfb_s[576];
     uint16_t huff_code[2048];           /* code words, same layout as huff_len (bit packer, tables.c HB tables) */
+    /* input-rate conversion (util.c:531 fill_buffer_resample); `samplerate` above is the OUTPUT rate */
+    int   samplerate_in, resample, rs_filter_l, rs_bpc;
+    double rs_ratio;
+    float rs_filt[(2 * LG_RS_BPC + 1) * LG_RS_TAPS];
 } LgDevCfg;
+
+/* one call of the reference's resampler = one chunk: `count` output samples starting at timeline index `out_pos`,
+ * made from the stream's input samples from absolute index `in_base` on, with the input clock at `itime` */
+typedef struct {
+    double  itime;
+    int64_t in_base;
+    int32_t out_pos, count;
+} LgRsChunk;
 
 /* ---- stage A (stateless analysis) -> stage B (ordered scan) */
 typedef struct {

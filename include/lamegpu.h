@@ -99,6 +99,12 @@ lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int m
  * quantize.c:1645 VBR_new_iteration_loop + vbrquantize.c) */
 lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr,
                                      int nstreams, int frames_per_launch, int device);
+/* same, with the input rate apart from the MPEG output rate (lame_set_in_samplerate / lame_set_out_samplerate,
+ * lame.h:184,196).  samplerate_out = 0 picks the output rate the way lame_init_params does (lame.c:764-769
+ * optimum_samplefreq); it must come out as 32000, 44100 or 48000.  When the two differ the streams' samples go
+ * through the reference's polyphase resampler (util.c:531 fill_buffer_resample) on the device. */
+lamegpu_batch *lamegpu_batch_open_rs(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality,
+                                     int vbr, int nstreams, int frames_per_launch, int device);
 void lamegpu_batch_close(lamegpu_batch *b);
 
 /* Feed nsamples[i] samples to stream i (pcm_l[i]/pcm_r[i]; pcm_r may be NULL for mono) and encode every

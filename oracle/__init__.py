@@ -34,14 +34,14 @@ def have_ref():
 
 
 class PortEncoder:
-    def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1, vbr=0):
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1, vbr=0, out_samplerate=0):
         self.lib = ctypes.CDLL(PORT_SO)
-        self.lib.lp_open_ex.restype = ctypes.c_void_p
-        self.lib.lp_open_ex.argtypes = [ctypes.c_int] * 6
+        self.lib.lp_open_rs.restype = ctypes.c_void_p
+        self.lib.lp_open_rs.argtypes = [ctypes.c_int] * 7
         self.lib.lp_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         self.lib.lp_flush.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         self.lib.lp_close.argtypes = [ctypes.c_void_p]
-        self.h = self.lib.lp_open_ex(samplerate, channels, brate, 4 if mode < 0 else mode, quality, vbr)
+        self.h = self.lib.lp_open_rs(samplerate, out_samplerate, channels, brate, 4 if mode < 0 else mode, quality, vbr)
         if not self.h:
             raise ValueError("port: unsupported configuration")
 
@@ -74,10 +74,10 @@ class PortEncoder:
 class RefEncoder:
     """The real libmp3lame 3.99.5 through its own public API (include/lame.h)."""
 
-    def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1, write_tag=False, vbr=0):
+    def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1, write_tag=False, vbr=0, out_samplerate=0):
         L = self.lib = ctypes.CDLL(REF_SO)
         L.lame_init.restype = ctypes.c_void_p
-        for f in ("lame_set_in_samplerate", "lame_set_num_channels", "lame_set_brate", "lame_set_mode", "lame_set_quality",
+        for f in ("lame_set_in_samplerate", "lame_set_out_samplerate", "lame_set_num_channels", "lame_set_brate", "lame_set_mode", "lame_set_quality",
                   "lame_set_bWriteVbrTag"):
             getattr(L, f).argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.lame_init_params.argtypes = [ctypes.c_void_p]
@@ -87,6 +87,8 @@ class RefEncoder:
         self.h = L.lame_init()
         L.lame_set_in_samplerate(self.h, samplerate)
         L.lame_set_num_channels(self.h, channels)
+        if out_samplerate:
+            L.lame_set_out_samplerate(self.h, out_samplerate)
         if vbr == 3:                                          # vbr_abr: brate is the mean bitrate
             L.lame_set_VBR.argtypes = [ctypes.c_void_p, ctypes.c_int]
             L.lame_set_VBR_mean_bitrate_kbps.argtypes = [ctypes.c_void_p, ctypes.c_int]

@@ -1,7 +1,7 @@
 /* oracle/port - TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
  * A plain-C, single-threaded restatement of the LAME 3.99.5 encode hot path (MPEG-1 Layer III,
- * 32/44.1/48 kHz, CBR, ABR and VBR-new (-V0..-V6 at 44.1/48 kHz), stereo / joint stereo / mono), written
+ * 32/44.1/48 kHz output from any input rate, CBR, ABR and VBR-new (-V0..-V6), stereo / joint stereo / mono), written
  * from the algorithm's description in the reference sources, each function citing the reference
  * file:line it follows.  Its only job is to be the CPU checker for the CUDA path (tests/, smoke(),
  * bench.py cpu_baseline).  Parity of this port is PINNED: tests/test_port_vs_ref.py compares its MP3
@@ -33,6 +33,8 @@
 #define LP_LARGE_BITS 100000
 #define LP_MAX_BITS_PER_CHANNEL 4095
 #define LP_MAX_BITS_PER_GRANULE 7680
+#define LP_RS_BPC 320               /* util.h BPC: at most this many fractional-offset filters each side */
+#define LP_RS_TAPS 33               /* filter_l + 1 <= 33 */
 
 enum { LP_NORM = 0, LP_START = 1, LP_SHORT = 2, LP_STOP = 3 };
 enum { LP_STEREO = 0, LP_JOINT = 1, LP_DUAL = 2, LP_MONO = 3, LP_MODE_NOT_SET = 4 };
@@ -63,6 +65,9 @@ typedef struct {
      * it may choose a frame size from, and the compression ratio calc_target_bits reads (quantize.c:1768) */
     int   vbr, vbr_q, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
     float compression_ratio;
+    /* input-rate conversion (util.c:531 fill_buffer_resample): samplerate is the OUTPUT rate */
+    int   samplerate_in, resample, rs_filter_l, rs_bpc;
+    double rs_ratio;
     /* tables */
     int   sfb_l[23], sfb_s[14], psfb21[7], psfb12[7];
     float amp_filter[32];
@@ -75,6 +80,7 @@ typedef struct {
     float pow43[LP_PRECALC], adj43asm[LP_PRECALC], ipow20[LP_QMAX], pow20[LP_QMAX + LP_QMAX2 + 1];
     float log_table[513];
     float ma_max_i1, ma_max_i2;
+    float rs_filt[(2 * LP_RS_BPC + 1) * LP_RS_TAPS];
 } lp_config;
 
 /* one granule/channel of coded data (reference gr_info, l3side.h:47) */
@@ -119,6 +125,8 @@ typedef struct {
     lp_granule tt[2][2];
     float mfbuf[2][LP_MFSIZE];
     int   mf_size, mf_samples_to_encode;
+    float rs_old[2][LP_RS_TAPS];        /* resampler: the last filter_l + 1 input samples, and the input time of the next chunk */
+    double rs_itime[2];
     /* bit writer (reference Bit_stream_struc + header ring, util.h:272) */
     unsigned char *buf;
     int   totbit, buf_byte_idx, buf_bit_idx;
@@ -131,12 +139,13 @@ typedef struct {
 /* API: mirrors lame_init, lame_set_xxx, lame_init_params, lame_encode_buffer, lame_encode_flush, lame_close */
 lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quality);
 lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 off, 3 abr, 4 mtrh: brate = VBR_q */);
+lp_encoder *lp_open_rs(int samplerate_in, int samplerate_out /* 0 = as lame_init_params picks it */, int channels, int brate, int mode, int quality, int vbr);
 int  lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsigned char *out, int cap);
 int  lp_flush(lp_encoder *e, unsigned char *out, int cap);
 void lp_close(lp_encoder *e);
 
 /* internals shared between the port's files */
-int   lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, int quality, int vbr);
+int   lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr);
 float lp_fast_log2(const lp_config *c, float x);
 void  lp_fft_long(const lp_config *c, float x[LP_BLK], const float *buf);
 void  lp_fft_short(const lp_config *c, float x[3][LP_BLK_S], const float *buf);

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 #include "lame_port.h"
 
 lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quality)
@@ -13,10 +14,15 @@ lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quali
 
 lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr)
 {
+    return lp_open_rs(samplerate, 0, channels, brate, mode, quality, vbr);
+}
+
+lp_encoder *lp_open_rs(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr)
+{
     lp_encoder *e = calloc(1, sizeof *e);
     int i, j, sb;
     if (!e) return NULL;
-    if (lp_setup(&e->cfg, samplerate, channels, brate, mode, quality, vbr) < 0) { free(e); return NULL; }
+    if (lp_setup(&e->cfg, samplerate_in, samplerate_out, channels, brate, mode, quality, vbr) < 0) { free(e); return NULL; }
     e->bitrate_index = e->cfg.bitrate_index;
     e->buf = calloc(1, LP_BITBUF);
     /* lame.c:2274 lame_init_internal_flags, lame.c:962, psymodel.c:1897-1922/2075 */
@@ -171,35 +177,83 @@ static int encode_frame(lp_encoder *e, const float *inbuf_l, const float *inbuf_
     return mp3count;
 }
 
-/* lame.c:1786 lame_copy_inbuffer + lame.c:1671 lame_encode_buffer_sample_t (no resampling) */
+/* util.c:531 fill_buffer_resample: up to `desired` output samples from `len` input samples of one channel.
+ * Output sample k sits at input time k*ratio - itime; the filter for its fractional position is the nearest of
+ * the 2*bpc + 1 precomputed ones.  Returns the samples made, *used = the input samples consumed. */
+static int resample_chunk(lp_encoder *e, float *outbuf, int desired, const float *inbuf, int len, int *used, int ch)
+{
+    const lp_config *cfg = &e->cfg;
+    int const filter_l = cfg->rs_filter_l, taps = filter_l + 1, bpc = cfg->rs_bpc;
+    double const ratio = cfg->rs_ratio;
+    float *old = e->rs_old[ch];
+    int i, j = 0, k;
+    for (k = 0; k < desired; k++) {
+        double const time0 = k * ratio;
+        float offset, xvalue = 0.;
+        const float *f;
+        int joff;
+        j = floor(time0 - e->rs_itime[ch]);
+        if ((filter_l + j - filter_l / 2) >= len) break;
+        offset = (time0 - e->rs_itime[ch] - (j + .5 * (filter_l % 2)));
+        joff = floor((offset * 2 * bpc) + bpc + .5);
+        f = cfg->rs_filt + joff * LP_RS_TAPS;
+        for (i = 0; i <= filter_l; ++i) {
+            int const j2 = i + j - filter_l / 2;
+            float const y = (j2 < 0) ? old[taps + j2] : inbuf[j2];
+            xvalue += y * f[i];
+        }
+        outbuf[k] = xvalue;
+    }
+    *used = len < filter_l + j - filter_l / 2 ? len : filter_l + j - filter_l / 2;
+    e->rs_itime[ch] += *used - k * ratio;
+    if (*used >= taps) for (i = 0; i < taps; i++) old[i] = inbuf[*used + i - taps];
+    else {
+        int const shift = taps - *used;
+        for (i = 0; i < shift; ++i) old[i] = old[i + *used];
+        for (j = 0; i < taps; ++i, ++j) old[i] = inbuf[j];
+    }
+    return k;
+}
+
+/* lame.c:1786 lame_copy_inbuffer + lame.c:1671 lame_encode_buffer_sample_t + util.c:665 fill_buffer */
 int lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsigned char *out, int cap)
 {
     const lp_config *cfg = &e->cfg;
     int mp3size = 0, ret, i, ch;
     int const mf_needed = 1024 + 1152 - (224 + 48);        /* lame.c:1627 calcNeeded: max(1904, 1632) */
     float m[2][2];
+    float *in[2] = { NULL, NULL };
+    const float *inp[2];
     if (nsamples == 0) return 0;
     if (cfg->channels < 2 && r == NULL) r = l;
     m[0][0] = 1.0f * cfg->pcm_transform[0][0]; m[0][1] = 1.0f * cfg->pcm_transform[0][1];
     m[1][0] = 1.0f * cfg->pcm_transform[1][0]; m[1][1] = 1.0f * cfg->pcm_transform[1][1];
+    in[0] = malloc(sizeof(float) * nsamples); in[1] = malloc(sizeof(float) * nsamples);
+    for (i = 0; i < nsamples; i++) {
+        float const xl = l[i], xr = r[i];
+        in[0][i] = xl * m[0][0] + xr * m[0][1];
+        in[1][i] = xl * m[1][0] + xr * m[1][1];
+    }
+    inp[0] = in[0]; inp[1] = in[1];
     while (nsamples > 0) {
-        int const n = nsamples < 1152 ? nsamples : 1152;
-        for (i = 0; i < n; i++) {
-            float const xl = l[i], xr = r[i];
-            float const u = xl * m[0][0] + xr * m[0][1];
-            float const v = xl * m[1][0] + xr * m[1][1];
-            e->mfbuf[0][e->mf_size + i] = u;
-            if (cfg->channels == 2) e->mfbuf[1][e->mf_size + i] = v;
+        int n_in = 0, n_out = 0;
+        if (cfg->resample) {
+            for (ch = 0; ch < cfg->channels; ch++)
+                n_out = resample_chunk(e, &e->mfbuf[ch][e->mf_size], 1152, inp[ch], nsamples, &n_in, ch);
         }
-        nsamples -= n; l += n; r += n;
-        e->mf_size += n;
+        else {
+            n_in = n_out = nsamples < 1152 ? nsamples : 1152;
+            for (ch = 0; ch < cfg->channels; ch++) memcpy(&e->mfbuf[ch][e->mf_size], inp[ch], n_out * sizeof(float));
+        }
+        nsamples -= n_in; inp[0] += n_in; inp[1] += n_in;
+        e->mf_size += n_out;
         if (e->mf_samples_to_encode < 1) e->mf_samples_to_encode = 576 + 1152;
-        e->mf_samples_to_encode += n;
+        e->mf_samples_to_encode += n_out;
         if (e->mf_size >= mf_needed) {
             int buf_size = cap - mp3size;
             if (cap == 0) buf_size = 0;
             ret = encode_frame(e, e->mfbuf[0], e->mfbuf[1], out, buf_size);
-            if (ret < 0) return ret;
+            if (ret < 0) { mp3size = ret; break; }
             out += ret;
             mp3size += ret;
             e->mf_size -= 1152;
@@ -208,6 +262,7 @@ int lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsig
                 for (i = 0; i < e->mf_size; i++) e->mfbuf[ch][i] = e->mfbuf[ch][i + 1152];
         }
     }
+    free(in[0]); free(in[1]);
     return mp3size;
 }
 
@@ -219,6 +274,7 @@ int lp_flush(lp_encoder *e, unsigned char *out, int cap)
     int const mf_needed = 1904;
     if (e->mf_samples_to_encode < 1) return 0;
     samples_to_encode = e->mf_samples_to_encode - 1152;
+    if (e->cfg.resample) samples_to_encode += 16. / e->cfg.rs_ratio;       /* lame.c:2083-2087 the resampler's delay */
     memset(buffer, 0, sizeof buffer);
     end_padding = 1152 - (samples_to_encode % 1152);
     if (end_padding < 576) end_padding += 1152;
@@ -226,6 +282,7 @@ int lp_flush(lp_encoder *e, unsigned char *out, int cap)
     while (frames_left > 0 && imp3 >= 0) {
         int const frame_num = e->frame_number;
         int bunch = mf_needed - e->mf_size;
+        if (e->cfg.resample) bunch *= e->cfg.rs_ratio;                         /* int *= double: truncated */
         if (bunch > 1152) bunch = 1152;
         if (bunch < 1) bunch = 1;
         remaining = cap - mp3count;

@@ -6,6 +6,7 @@
  * (util.c:959).  Only the CBR / MPEG-1 corner of the configuration space is implemented; anything
  * else makes lp_setup() fail.  All libm calls are the host's, as in the reference. */
 #include <math.h>
+#include <float.h>
 #include <string.h>
 #include "lame_port.h"
 #include "port_tables.inc"
@@ -523,7 +524,75 @@ static int setup_quality(lp_config *c, int quality)
     return 0;
 }
 
-int lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, int quality, int vbr)
+/* util.c:393 map2MP3Frequency */
+static int map_to_mp3_frequency(int freq)
+{
+    static const int f[8] = { 8000, 11025, 12000, 16000, 22050, 24000, 32000, 44100 };
+    int i;
+    for (i = 0; i < 8; i++) if (freq <= f[i]) return f[i];
+    return 48000;
+}
+
+/* lame.c:274 optimum_samplefreq: the MPEG rate that suits the low-pass, never far below the input rate */
+static int optimum_samplefreq(int lowpassfreq, int in)
+{
+    static const int rate[9] = { 48000, 44100, 32000, 24000, 22050, 16000, 12000, 11025, 8000 };
+    static const int cut[8] = { 15960, 15250, 11220, 9970, 7230, 5420, 4510, 3970 };    /* low-pass at or below cut[i] -> rate[i + 1] */
+    int i, suggested = 44100;
+    for (i = 0; i < 9; i++) if (in >= rate[i]) { suggested = rate[i]; break; }
+    if (lowpassfreq == -1) return suggested;
+    for (i = 0; i < 8; i++) if (lowpassfreq <= cut[i]) suggested = rate[i + 1];
+    if (in < suggested) {
+        for (i = 1; i < 9; i++) if (in > rate[i]) return rate[i - 1];
+        return 8000;
+    }
+    return suggested;
+}
+
+/* util.c:490 blackman + the table part of util.c:531 fill_buffer_resample: (2*bpc + 1) windowed-sinc filters of
+ * filter_l + 1 taps, one per fractional offset, each normalised to unit sum */
+static float rs_blackman(float x, float fcn, int l)
+{
+    float bkwn, x2;
+    float const wcn = (M_PI * fcn);
+    x /= l;
+    if (x < 0) x = 0;
+    if (x > 1) x = 1;
+    x2 = x - .5;
+    bkwn = 0.42 - 0.5 * cos(2 * x * M_PI) + 0.08 * cos(4 * x * M_PI);
+    if (fabs((double) x2) < 1e-9) return wcn / M_PI;
+    return (bkwn * sin((double) (l * wcn * x2)) / (M_PI * l * x2));
+}
+
+static int rs_gcd(int i, int j) { return j ? rs_gcd(j, i % j) : i; }
+
+static int setup_resampler(lp_config *c)
+{
+    int const lo = c->samplerate * 0.9995f, hi = c->samplerate * 1.0005f;      /* util.c:654 isResamplingNecessary */
+    int i, j, bpc;
+    double ratio;
+    float fcn;
+    c->resample = (c->samplerate_in < lo) || (hi < c->samplerate_in) ? 1 : 0;
+    if (!c->resample) return 0;
+    ratio = (double) c->samplerate_in / (double) c->samplerate;
+    bpc = c->samplerate / rs_gcd(c->samplerate, c->samplerate_in);
+    if (bpc > LP_RS_BPC) bpc = LP_RS_BPC;
+    fcn = 1.00 / ratio;
+    if (fcn > 1.00) fcn = 1.00;
+    c->rs_filter_l = 31 + (fabs(ratio - floor(.5 + ratio)) < FLT_EPSILON ? 1 : 0);
+    c->rs_bpc = bpc;
+    c->rs_ratio = ratio;
+    for (j = 0; j <= 2 * bpc; j++) {
+        float sum = 0.;
+        float const offset = (j - bpc) / (2. * bpc);
+        float *f = c->rs_filt + j * LP_RS_TAPS;
+        for (i = 0; i <= c->rs_filter_l; i++) sum += f[i] = rs_blackman(i - offset, fcn, c->rs_filter_l);
+        for (i = 0; i <= c->rs_filter_l; i++) f[i] /= sum;
+    }
+    return 0;
+}
+
+int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr)
 {
     /* presets.c:241 abr_switch_map, the columns the CBR path reads */
     static const struct { int kbps, safejoint; float nsmsfix, st_lrm, st_s, scale, masking_adj, ath_lower, ath_curve, interch; int sfscale; }
@@ -549,16 +618,15 @@ int lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, in
         {4.50, 100.0, 2.2, 2.3, -12.0, 6.0, -14, 0, 2, 4, 2.239, 3, 93.9}, {4.80, 200.0, 2.7, 2.7, -18.0, 9.0, -17, 0, 2, 0, 2.570, 1, 93.6},
         {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} };
     static const int vbr_lowpass[11] = { 24000, 19500, 18500, 18000, 17500, 17000, 16500, 15600, 15200, 7230, 3950 };
-    int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, suggested, vbr_q = 0;
+    int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, vbr_q = 0;
+    int samplerate = samplerate_out;                                   /* 0 = chosen below the way lame_init_params does */
     float athaa_sensitivity = 0;
     float scale = 1, maskingadjust, maskingadjust_short, ath_lower_db, attackthre, attackthre_s;
     double lowpass;
 
     memset(c, 0, sizeof *c);
     if (channels != 1 && channels != 2) return -1;
-    if (samplerate == 44100) sr_index = 0; else if (samplerate == 48000) sr_index = 1;
-    else if (samplerate == 32000) sr_index = 2; else return -1;       /* util.c:433 SmpFrqIndex, MPEG-1 only */
-    c->samplerate = samplerate;
+    if (samplerate_in < 1) return -1;
     c->channels = channels;
     if (channels == 1) mode = LP_MONO;                                 /* lame.c:597 */
     if (mode == LP_MONO) c->channels = 1;
@@ -569,7 +637,7 @@ int lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, in
          * (lame.c:661-698), which needs the resampler */
         vbr_q = brate;
         if (vbr_q < 0 || vbr_q > 6) return -1;
-        if (samplerate == 32000) return -1;                            /* lame.c:679-686 rescales VBR_q to a fractional level at 32 kHz */
+        if (samplerate == 0 && samplerate_in == 32000) return -1;      /* lame.c:679-686 rescales VBR_q to a fractional level at 32 kHz */
         brate = 128;                                                   /* gfp->brate stays unused; keeps the arithmetic below defined */
     }
     if (vbr == 4) { }
@@ -582,6 +650,7 @@ int lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, in
     }
     else {
         if (brate == 0) {                                              /* lame.c:623-644 */
+            if (samplerate == 0) samplerate = map_to_mp3_frequency((int) (0.97 * samplerate_in));
             brate = samplerate * 16 * c->channels / (1.e3 * 11.025f);
         }
         /* util.c:320 FindNearestBitrate on the MPEG-1 row */
@@ -595,14 +664,15 @@ int lp_setup(lp_config *c, int samplerate, int channels, int brate, int mode, in
     if (vbr == 4) lowpass = vbr_lowpass[vbr_q];                        /* lame.c:730-741, VBR_q_frac = 0 */
     else if (mode == LP_MONO) lowpass *= 1.5;
     c->lowpassfreq = lowpass;
-    if (2 * c->lowpassfreq > samplerate) c->lowpassfreq = samplerate / 2;
-    /* lame.c:245 optimum_samplefreq: we only accept the cases where no resampling results */
-    suggested = samplerate;
-    if (c->lowpassfreq <= 15960) suggested = 44100;
-    if (c->lowpassfreq <= 15250) suggested = 32000;
-    if (c->lowpassfreq <= 11220) suggested = 24000;
-    if (samplerate < suggested) suggested = samplerate;               /* lame.c:304-334 maps up to the input rate */
-    if (suggested != samplerate) return -1;
+    if (samplerate == 0) {                                             /* lame.c:764-769 */
+        if (2 * c->lowpassfreq > samplerate_in) c->lowpassfreq = samplerate_in / 2;
+        samplerate = optimum_samplefreq(c->lowpassfreq, samplerate_in);
+    }
+    if (samplerate == 44100) sr_index = 0; else if (samplerate == 48000) sr_index = 1;
+    else if (samplerate == 32000) sr_index = 2; else return -1;       /* util.c:433 SmpFrqIndex, MPEG-1 only */
+    c->samplerate = samplerate;
+    c->samplerate_in = samplerate_in;
+    if (setup_resampler(c) != 0) return -1;
     if (vbr == 4) c->lowpassfreq = c->lowpassfreq < 24000 ? c->lowpassfreq : 24000;     /* lame.c:770-775 */
     else c->lowpassfreq = c->lowpassfreq < 20500 ? c->lowpassfreq : 20500;
     c->lowpassfreq = samplerate / 2 < c->lowpassfreq ? samplerate / 2 : c->lowpassfreq;

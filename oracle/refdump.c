@@ -23,11 +23,17 @@ struct refdump_handle { lame_global_flags *gfp; };
 
 void *refdump_open(int brate, int mode, int quality, int vbrmode, int vbr_q, int samplerate, int nch)
 {
+    return refdump_open_rs(brate, mode, quality, vbrmode, vbr_q, samplerate, 0, nch);
+}
+
+void *refdump_open_rs(int brate, int mode, int quality, int vbrmode, int vbr_q, int samplerate, int out_samplerate, int nch)
+{
     struct refdump_handle *h = calloc(1, sizeof *h);
     lame_global_flags *gfp = lame_init();
     h->gfp = gfp;
     lame_set_in_samplerate(gfp, samplerate > 0 ? samplerate : 44100);
     lame_set_num_channels(gfp, nch > 0 ? nch : 2);
+    if (out_samplerate > 0) lame_set_out_samplerate(gfp, out_samplerate);
     if (vbrmode == vbr_abr) { lame_set_VBR(gfp, vbr_abr); if (brate > 0) lame_set_VBR_mean_bitrate_kbps(gfp, brate); }
     else if (vbrmode > 0) { lame_set_VBR(gfp, (vbr_mode) vbrmode); lame_set_VBR_q(gfp, vbr_q); }
     else if (brate > 0) lame_set_brate(gfp, brate);

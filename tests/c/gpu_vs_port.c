@@ -33,7 +33,8 @@ int main(int argc, char **argv)
         if (s % 4 == 3) { int z = n / 3; memset(L[s], 0, z * 2); memset(R[s], 0, z * 2); }
     }
     int const vbr = getenv("LP_VBR") ? atoi(getenv("LP_VBR")) : 0;          /* 0 = CBR, 3 = ABR with mean bitrate `brate` */
-    b = lamegpu_batch_open_ex(sr, 2, brate, mode, quality, vbr, S, FPL, 0);
+    int const out_sr = getenv("LP_OUT_SR") ? atoi(getenv("LP_OUT_SR")) : 0; /* explicit output rate, 0 = automatic (resampling when it differs from sr) */
+    b = lamegpu_batch_open_rs(sr, out_sr, 2, brate, mode, quality, vbr, S, FPL, 0);
     if (!b) { printf("batch open failed\n"); return 2; }
     for (i = 0; i < n; i += chunk) {
         int c = n - i < chunk ? n - i : chunk;
@@ -50,10 +51,11 @@ int main(int argc, char **argv)
     { float ms[4]; lamegpu_batch_kernel_ms(b, ms); printf("last launch kernel ms: analysis %.3f scan %.3f mdct %.3f quant %.3f\n", ms[0], ms[1], ms[2], ms[3]); }
     lamegpu_batch_close(b);
     for (s = 0; s < S; s++) {
-        lp_encoder *e = lp_open_ex(sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr);
+        lp_encoder *e = lp_open_rs(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr);
         int k;
         if (!e) { printf("port open failed\n"); return 2; }
-        rlen[s] = lp_encode(e, L[s], R[s], n, ref[s], cap);
+        /* same call pattern as above: with resampling the reference's state depends on where the calls end */
+        for (i = 0; i < n; i += chunk) rlen[s] += lp_encode(e, L[s] + i, R[s] + i, n - i < chunk ? n - i : chunk, ref[s] + rlen[s], cap - rlen[s]);
         rlen[s] += lp_flush(e, ref[s] + rlen[s], cap - rlen[s]);
         lp_close(e);
         if (olen[s] != rlen[s] || memcmp(out[s], ref[s], rlen[s])) {

@@ -43,8 +43,10 @@ int main(int argc, char **argv)
     void *h; lp_encoder *e;
     if (siggen(sig, l, r, n, sr, wav) < 0) { printf("bad signal\n"); return 2; }
     int const vbr = getenv("LP_VBR") ? atoi(getenv("LP_VBR")) : 0;          /* 0 = CBR, 3 = ABR with mean bitrate `brate` */
-    h = refdump_open(brate, mode, quality, vbr, vbr == 4 ? brate : 0, sr, 2);   /* vbr 4 (vbr_mtrh): `brate` is VBR_q */
-    e = lp_open_ex(sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr);
+    int const out_sr = getenv("LP_OUT_SR") ? atoi(getenv("LP_OUT_SR")) : 0; /* explicit output rate (lame_set_out_samplerate), 0 = automatic */
+    int const chunk = getenv("LP_CHUNK") ? atoi(getenv("LP_CHUNK")) : 1152;  /* samples per encode call: the resampler's state depends on it */
+    h = refdump_open_rs(brate, mode, quality, vbr, vbr == 4 ? brate : 0, sr, out_sr, 2);   /* vbr 4 (vbr_mtrh): `brate` is VBR_q */
+    e = lp_open_rs(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr);
     if (!h || !e) { printf("open failed ref=%p port=%p\n", h, (void *) e); return (!h && !e) ? 0 : 2; }
     refdump_tables(h, &tab);
     {
@@ -72,11 +74,13 @@ int main(int argc, char **argv)
         CMPI("sfb21_extra", (&tab.sfb21_extra), (&c->sfb21_extra), 1); CMPI("quant_comp", (&tab.quant_comp), (&c->quant_comp), 1);
         printf("setup tables: %s\n", nbad ? "MISMATCH" : "identical");
     }
-    for (f = 0; f <= nframes; f++) {
+    int const ncalls = (n + chunk - 1) / chunk;
+    for (f = 0; f <= ncalls; f++) {
         int nr, np, gr, ch;
-        if (f < nframes) {
-            nr = refdump_encode(h, l + f * 1152, r + f * 1152, 1152, ob_ref, sizeof ob_ref);
-            np = lp_encode(e, l + f * 1152, r + f * 1152, 1152, ob_port, sizeof ob_port);
+        if (f < ncalls) {
+            int const cn = (f + 1) * chunk <= n ? chunk : n - f * chunk;
+            nr = refdump_encode(h, l + f * chunk, r + f * chunk, cn, ob_ref, sizeof ob_ref);
+            np = lp_encode(e, l + f * chunk, r + f * chunk, cn, ob_port, sizeof ob_port);
         }
         else {
             nr = refdump_flush(h, ob_ref, sizeof ob_ref);

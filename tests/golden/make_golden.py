@@ -29,6 +29,12 @@ CASES = [
     ("click_192_stereo_q5", "click", 24, 44100, 192, 0, 5),
     ("noise_256_48k", "noise", 16, 48000, 256, -1, -1),
     ("click_160_q7", "click", 16, 44100, 160, -1, 7),
+    # input rate != MPEG output rate: the reference's polyphase resampler (util.c:531) in front; an 8th field is an explicit
+    # lame_set_out_samplerate, otherwise lame_init_params picks the rate (96 kbps at 44.1 kHz -> 32 kHz, 112 kbps at 48 kHz -> 44.1 kHz)
+    ("click_128_48k_to_44k", "click", 20, 48000, 128, -1, -1, 44100),
+    ("sine_96_44k_auto32k", "sine", 20, 44100, 96, -1, -1),
+    ("noise_112_48k_auto44k", "noise", 16, 48000, 112, -1, -1),
+    ("gap_160_37800_to_48k", "gap", 16, 37800, 160, -1, -1, 48000),
 ]
 
 
@@ -53,12 +59,13 @@ def main():
     pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16).reshape(-1, 2).T.copy()
     np.save(os.path.join(HERE, "testcase_pcm.npy"), pcm)
     manifest = {}
-    for name, sig, frames, sr, brate, mode, q in CASES:
+    for name, sig, frames, sr, brate, mode, q, *rest in CASES:
+        out_sr = rest[0] if rest else 0
         x = make_signal(sig, frames * 1152)
-        mp3 = oracle.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q).encode_all(x[0], x[1])
+        mp3 = oracle.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q, out_samplerate=out_sr).encode_all(x[0], x[1])
         with open(os.path.join(HERE, name + ".mp3"), "wb") as f:
             f.write(mp3)
-        manifest[name] = dict(signal=sig, frames=frames, samplerate=sr, brate=brate, mode=mode, quality=q, nbytes=len(mp3),
+        manifest[name] = dict(signal=sig, frames=frames, samplerate=sr, out_samplerate=out_sr, brate=brate, mode=mode, quality=q, nbytes=len(mp3),
                               pcm_sha256=hashlib.sha256(x.tobytes()).hexdigest(), mp3_sha256=hashlib.sha256(mp3).hexdigest())
         print(name, len(mp3))
     with open(os.path.join(HERE, "manifest.json"), "w") as f:

@@ -44,6 +44,19 @@ def test_emulated_kernels_vbr_match_port(emu_bin, args):
     assert "IDENTICAL" in r.stdout
 
 
+@pytest.mark.parametrize("args,env", [
+    ("3 10 4 128 -1 -1 48000 777", dict(LP_OUT_SR="44100")), ("2 8 8 192 -1 -1 44100 3000", dict(LP_OUT_SR="48000")),
+    ("2 8 3 96 -1 -1 44100 100", {}), ("2 4 4 128 -1 -1 8000 50", dict(LP_OUT_SR="44100")), ("2 16 4 128 -1 -1 96000 1152", {}),
+    ("2 8 4 2 -1 -1 44100 1152", dict(LP_VBR="4", LP_OUT_SR="32000")), ("2 4 4 128 -1 -1 48000 7", dict(LP_OUT_SR="44100")),
+])
+def test_emulated_resampler_matches_port(emu_bin, args, env):
+    """kernel R (lg_kernel_resample) + the host's replay of the reference's per-call resampler bookkeeping (chunks, input
+    clock, flush bunches), incl. calls of 7 samples (chunk list growth) and 8 kHz -> 44.1 kHz upsampling"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout
+
+
 TAG_SCRIPT = r"""
 import json, os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))

@@ -35,7 +35,7 @@ def test_golden_vectors(lib, name):
     """the reference's own output, committed as fixtures, reproduced by the GPU"""
     m = MANIFEST[name]
     x = make_signal(m["signal"], m["frames"] * 1152)
-    enc = lib.BatchEncoder(1, m["samplerate"], 2, m["brate"], m["mode"], m["quality"], frames_per_launch=8)
+    enc = lib.BatchEncoder(1, m["samplerate"], 2, m["brate"], m["mode"], m["quality"], frames_per_launch=8, out_samplerate=m.get("out_samplerate", 0))
     _, a = enc.encode(x[None])
     _, b = enc.flush()
     enc.close()
@@ -117,6 +117,62 @@ def test_vbr_batch_matches_oracle(lib, oracle_mod, cfg):
             ref = oracle_mod.RefEncoder(sr, 2, q, mode if mode >= 0 else 4, quality, vbr=4).encode_all(pcm[s, 0], pcm[s, 1])
             assert want == ref, "oracle port and reference disagree"
         assert a[s] + b[s] == want, "stream %d (%s)" % (s, kinds[s % 4])
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(S=8, F=20, fpl=8, sr=48000, out=44100, brate=128, chunk=4000), dict(S=4, F=16, fpl=4, sr=44100, out=48000, brate=192, chunk=1152),
+    dict(S=4, F=16, fpl=8, sr=44100, out=0, brate=96, chunk=777), dict(S=4, F=6, fpl=4, sr=8000, out=44100, brate=128, chunk=100),
+    dict(S=3, F=40, fpl=4, sr=192000, out=32000, brate=128, chunk=50000), dict(S=3, F=24, fpl=8, sr=96000, out=0, brate=160, chunk=10 ** 9),
+    dict(S=4, F=16, fpl=8, sr=44100, out=32000, brate=2, vbr=4, chunk=3000), dict(S=4, F=16, fpl=8, sr=48000, out=0, brate=112, vbr=3, chunk=5000),
+    dict(S=3, F=12, fpl=4, sr=44100, out=0, brate=64, mode=3, chunk=2000), dict(S=2, F=3, fpl=4, sr=48000, out=44100, brate=128, chunk=7),
+])
+def test_resampled_batch_matches_oracle(lib, oracle_mod, cfg):
+    """input rate != MPEG output rate.  lg_kernel_resample makes the PCM window on the device from the reference's
+    per-call chunk schedule (util.c:531), so the streams are fed to the oracle in the same call sizes; byte-identical to
+    the port and to libmp3lame, incl. the low bitrates that imply a 32 kHz output and calls of 7 samples"""
+    S, F, sr, out, brate, chunk = cfg["S"], cfg["F"], cfg["sr"], cfg["out"], cfg["brate"], cfg["chunk"]
+    mode, vbr = cfg.get("mode", -1), cfg.get("vbr", 0)
+    kinds = ("noise", "click", "sine", "gap")
+    pcm = np.stack([make_signal(kinds[s % 4], F * 1152, seed=80 + s) for s in range(S)])
+    enc = lib.BatchEncoder(S, sr, 2, brate, mode, -1, frames_per_launch=cfg["fpl"], vbr=vbr, out_samplerate=out)
+    got = [b""] * S
+    for pos in range(0, F * 1152, chunk):
+        _, o = enc.encode(pcm[:, :, pos:pos + chunk])
+        got = [g + x for g, x in zip(got, o)]
+    _, o = enc.flush()
+    got = [g + x for g, x in zip(got, o)]
+    enc.close()
+    for s in range(S):
+        encs = [oracle_mod.PortEncoder(sr, 2, brate, mode, -1, vbr=vbr, out_samplerate=out)]
+        if oracle_mod.have_ref():
+            encs.append(oracle_mod.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, -1, vbr=vbr, out_samplerate=out))
+        for e in encs:
+            want = b""
+            for pos in range(0, F * 1152, chunk):
+                want += e.encode(pcm[s, 0, pos:pos + chunk], pcm[s, 1, pos:pos + chunk])
+            want += e.flush()
+            e.close()
+            assert got[s] == want, "stream %d (%s) vs %s" % (s, kinds[s % 4], type(e).__name__)
+
+
+def test_resampled_lame_api_with_tag(lib, oracle_mod):
+    """the lame.h face with lame_set_out_samplerate, float input and the Info tag: source-rate field and encoder padding of the
+    tag come from the resampling path (VbrTag.c:775, lame.c:2083-2091)"""
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build")
+    x = make_signal("click", 30 * 1152, seed=5)
+    e = lib.Encoder(48000, 2, 128, write_tag=True, out_samplerate=44100)
+    r = oracle_mod.RefEncoder(48000, 2, 128, write_tag=True, out_samplerate=44100)
+    a = b_ = b""
+    for pos in range(0, x.shape[1], 5000):
+        a += e.encode(x[0, pos:pos + 5000], x[1, pos:pos + 5000])
+        b_ += r.encode(x[0, pos:pos + 5000], x[1, pos:pos + 5000])
+    a += e.flush()
+    b_ += r.flush()
+    assert a == b_
+    assert e.lametag_frame() == r.lametag_frame()
+    e.close()
+    r.close()
 
 
 def test_config4_vbr_v2_full_size(lib, oracle_mod):
@@ -216,7 +272,7 @@ def test_edge_cases(lib, oracle_mod):
 
 
 def test_unsupported_configurations_fail_loudly(lib):
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=1)):
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=1), dict(out_samplerate=24000), dict(brate=7, vbr=4)):
         with pytest.raises(lib.LameGpuError):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()

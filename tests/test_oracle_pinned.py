@@ -19,7 +19,7 @@ MANIFEST = json.load(open(os.path.join(GOLD, "manifest.json")))
 def test_port_reproduces_golden(oracle_mod, name):
     m = MANIFEST[name]
     x = make_signal(m["signal"], m["frames"] * 1152)
-    mp3 = oracle_mod.PortEncoder(m["samplerate"], 2, m["brate"], m["mode"], m["quality"]).encode_all(x[0], x[1])
+    mp3 = oracle_mod.PortEncoder(m["samplerate"], 2, m["brate"], m["mode"], m["quality"], out_samplerate=m.get("out_samplerate", 0)).encode_all(x[0], x[1])
     want = open(os.path.join(GOLD, name + ".mp3"), "rb").read()
     assert len(mp3) == m["nbytes"]
     assert mp3 == want
@@ -41,7 +41,8 @@ def test_port_chunking_invariance(oracle_mod):
 
 
 def test_port_rejects_unsupported(oracle_mod):
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=2), dict(samplerate=44100, brate=96)):
+    # MPEG-2 output rates (22.05 kHz input; 64 kbps makes lame_init_params pick 24 kHz), quality 0-2, VBR -V7 (fractional VBR_q at 32 kHz)
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=2), dict(brate=7, vbr=4), dict(out_samplerate=22050)):
         with pytest.raises(ValueError):
             oracle_mod.PortEncoder(**kw)
 
@@ -89,6 +90,24 @@ def test_port_vbr_new_vs_reference(port_vs_ref_bin, args):
     """VBR-new (vbr_mtrh, lame_set_VBR_q = the 2nd argument; vbrquantize.c + quantize.c:1645), including the frames that do not fit
     and go through outOfBitsStrategy (click at -V0): byte-identical to libmp3lame"""
     r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="4"))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
+@pytest.mark.parametrize("args,env", [
+    ("click 128 -1 -1 60 48000", dict(LP_OUT_SR="44100")), ("click 192 -1 -1 60 44100", dict(LP_OUT_SR="48000")),
+    ("sine 128 -1 -1 60 44100", dict(LP_OUT_SR="32000", LP_CHUNK="777")), ("noise 128 -1 -1 30 8000", dict(LP_OUT_SR="44100", LP_CHUNK="100")),
+    ("click 128 -1 -1 60 192000", dict(LP_OUT_SR="32000", LP_CHUNK="5000")), ("sine 128 -1 -1 60 96000", {}), ("click 112 -1 -1 60 48000", {}),
+    ("click 96 -1 -1 60 44100", {}), ("noise 80 -1 -1 60 44100", {}), ("click 64 3 -1 60 44100", {}), ("click 160 -1 -1 40 37800", {}),
+    ("click 48 -1 -1 40 44100", dict(LP_OUT_SR="32000")), ("click 2 -1 -1 60 44100", dict(LP_VBR="4", LP_OUT_SR="32000")),
+    ("click 2 -1 -1 60 88200", dict(LP_VBR="4")), ("click 112 -1 -1 60 48000", dict(LP_VBR="3", LP_CHUNK="4000")),
+    ("noise 128 -1 -1 8 48000", dict(LP_OUT_SR="44100", LP_CHUNK="7")),
+])
+def test_port_resampler_vs_reference(port_vs_ref_bin, args, env):
+    """input rate != output rate (explicit lame_set_out_samplerate = LP_OUT_SR, or the rate lame_init_params picks): the
+    polyphase resampler util.c:531, its per-call state (LP_CHUNK = samples per encode call) and the flush padding rule
+    lame.c:2083-2100; also the low bitrates that only exist through it (96 kbps at 44.1 kHz -> 32 kHz).  Byte-identical."""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **env))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
