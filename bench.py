@@ -69,17 +69,17 @@ def noise_pcm(nstreams, nsamples, seed):
     return rng.integers(-12000, 12001, size=(nstreams, 2, nsamples), dtype=np.int16)
 
 
-SIGNAL, BRATE, VBR = "noise", 128, 0       # configs[1]; --signal/--brate/--vbr select the other BASELINE configs
+SIGNAL, BRATE, VBR, QUALITY = "noise", 128, 0, -1       # configs[1]; --signal/--brate/--vbr select the other BASELINE configs
 
 
 def set_workload(args):
     """configs[1] by default; `--signal sine --brate 320` = configs[2], `--signal sine --vbr 4 --brate 2` = configs[3] (VBR -V2)"""
-    global SIGNAL, BRATE, VBR, STREAMS, FRAMES, WORKLOAD
-    SIGNAL, BRATE, VBR, STREAMS, FRAMES = args.signal, args.brate, args.vbr, args.streams, args.frames
-    if (SIGNAL, BRATE, VBR, STREAMS, FRAMES) != ("noise", 128, 0, 512, 8):
+    global SIGNAL, BRATE, VBR, STREAMS, FRAMES, WORKLOAD, QUALITY
+    SIGNAL, BRATE, VBR, STREAMS, FRAMES, QUALITY = args.signal, args.brate, args.vbr, args.streams, args.frames, args.quality
+    if (SIGNAL, BRATE, VBR, STREAMS, FRAMES, QUALITY) != ("noise", 128, 0, 512, 8, -1):
         rate = {0: "CBR %d kbps" % BRATE, 3: "ABR %d kbps" % BRATE, 4: "VBR-new -V%d" % BRATE}[VBR]
         sig = "white noise U[-12000,12000]" if SIGNAL == "noise" else "two tones per channel + U[-1000,1000]"
-        WORKLOAD = "%d frames/GPU = %d streams x %d frames, 44.1 kHz stereo %s, %s joint stereo q3" % (STREAMS * FRAMES, STREAMS, FRAMES, sig, rate)
+        WORKLOAD = "%d frames/GPU = %d streams x %d frames, 44.1 kHz stereo %s, %s joint stereo q%d" % (STREAMS * FRAMES, STREAMS, FRAMES, sig, rate, 3 if QUALITY < 0 else QUALITY)
 
 
 class ClockSampler:
@@ -156,7 +156,7 @@ def cpu_baseline(seconds=12.0):
     kind = "reference" if oracle.have_ref() else "port"
     Enc = oracle.RefEncoder if kind == "reference" else oracle.PortEncoder
     pcm = noise_pcm(1, 1152 * 256, 777)[0]
-    enc = Enc(44100, 2, BRATE, 4, -1, vbr=VBR)
+    enc = Enc(44100, 2, BRATE, 4, QUALITY, vbr=VBR)
     frames, t0 = 0, time.perf_counter()
     while True:
         enc.encode(pcm[0], pcm[1])
@@ -182,7 +182,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     nsamp = FRAMES * 1152
     pcm = noise_pcm(STREAMS, nsamp, 4242)
-    encs = [Enc(44100, 2, BRATE, 4, -1, vbr=VBR) for _ in range(STREAMS)]
+    encs = [Enc(44100, 2, BRATE, 4, QUALITY, vbr=VBR) for _ in range(STREAMS)]
     pool = ThreadPoolExecutor(max_workers=cores)
 
     def step():
@@ -229,6 +229,7 @@ def main():
     ap.add_argument("--brate", type=int, default=128, help="kbps (CBR/ABR) or the -V level with --vbr 4")
     ap.add_argument("--vbr", type=int, default=0, choices=(0, 3, 4), help="0 CBR, 3 ABR, 4 VBR-new (vbr_mtrh)")
     ap.add_argument("--signal", default="noise", choices=("noise", "sine"))
+    ap.add_argument("--quality", type=int, default=-1, help="lame_set_quality 0..9, -1 = default (3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     set_workload(args)
@@ -254,7 +255,7 @@ def main():
     # the global job is world*S independent streams; this rank owns a contiguous shard of them
     lo, hi = shard_range(world * S, rank, world)
     assert hi - lo == S
-    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, -1, frames_per_launch=F, device=local, vbr=VBR)
+    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=local, vbr=VBR)
     pcm = noise_pcm(S, nsamp + 224, 1000 + rank)            # +224: the first launch needs 1152*F + 224 user samples
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -296,7 +297,7 @@ def main():
 
     # ---------------- e2e: public API, host buffers in, MP3 bytes out
     enc.close()
-    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, -1, frames_per_launch=F, device=local, vbr=VBR)
+    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=local, vbr=VBR)
     step_pcm = [noise_pcm(S, nsamp, 5000 + 17 * i + rank) for i in range(4)]
     out = np.empty((S, int(1.25 * nsamp) + 7200 + 4096 + 1440 * F), dtype=np.uint8)
     nbytes = np.zeros(S, dtype=np.int32)
@@ -336,7 +337,7 @@ def main():
                     "note": "lamegpu_batch_encode_packed: pinned staging + H2D + 5 kernels + D2H of packed bytes + host header splice (threads=%d)" % (os.cpu_count() or 1)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": qname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(qname) if (S, F, SIGNAL, BRATE, VBR) == (512, 8, "noise", 128, 0) else None, "peak_source": peak_src,
+                         "traffic": measured_traffic(qname) if (S, F, SIGNAL, BRATE, VBR, QUALITY) == (512, 8, "noise", 128, 0, -1) else None, "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary.json)",
                          "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms,
                          "note": "latency/issue-bound integer + table-lookup kernel (SURVEY 8d): HBM fraction is reported, not the binding limit"},

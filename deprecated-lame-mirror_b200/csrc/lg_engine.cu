@@ -206,7 +206,8 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     for (int i = 0; i < 8; i++) cudaEventCreate(&e->ev[i]);
     if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
-    cudaFuncSetAttribute(lg_kernel_quant, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+    cudaFuncSetAttribute(lg_kernel_quant<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+    cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
     cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
 #endif
@@ -289,8 +290,11 @@ extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
     if (e->hcfg.vbr == 4)
         LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
+    else if (e->hcfg.substep_shaping & 2)
+        LG_LAUNCH(lg_kernel_quant<1>, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F);
     else
-        LG_LAUNCH(lg_kernel_quant, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+        LG_LAUNCH(lg_kernel_quant<0>, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
 #ifndef LG_EMULATE
     cudaEventRecord(e->ev[4], e->stream);

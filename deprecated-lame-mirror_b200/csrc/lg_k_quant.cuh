@@ -48,6 +48,7 @@ struct __attribute__((aligned(16))) LgQWarp {
     int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
     uint8_t line_sfb[576];
+    unsigned ph[2];                  /* QntStateVar_t.pseudohalf as a bit per band: substep shaping (quality 0-2) has the band in its half step */
 };
 struct LgSmemD {
     LgQWarp w[2];
@@ -220,6 +221,33 @@ __device__ __noinline__ void lg_count1_bits(const LgDevCfg *__restrict__ c, cons
  * granule starts and quantize_xrpow only ever keeps or clears them (takehiro.c:300-330), so they are never touched. */
 __device__ __forceinline__ int lg_noquant_tail(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev &pv,
                                                int hi_nz, int hi_big, int lane);
+/* takehiro.c:781-797, quality 0-2 only: in the bands that are in their half step, values whose xrpow is below
+ * 0.6345 / IPOW20(gain) - the ones that only just rounded up to 1 - are dropped.  Runs over the quantised pairs again and
+ * recomputes the lane's highest non-zero / big pair, so the main loop stays as it is for the other quality levels. */
+__device__ __noinline__ unsigned lg_substep_zero(const LgDevCfg *__restrict__ c, LgQWarp *w, int gain, int sfbmax, int jn, int ilim, int lane)
+{
+    float const roundfac = (float) (0.634521682242439 / (double) __ldg(&c->ipow20[gain]));
+    unsigned const ph0 = w->ph[0], ph1 = w->ph[1];
+    int nz = -1, big = -1;
+    for (int j = 0; j < jn; j++) {
+        int const P = lane + 32 * j, i = 2 * P;
+        int const sfb = w->line_sfb[i];
+        unsigned nv = *reinterpret_cast<const unsigned *>(&w->ixw[i]);
+        if (sfb < sfbmax && (((sfb < 32 ? ph0 : ph1) >> (sfb & 31)) & 1u)) {
+            float2 const xp = *reinterpret_cast<const float2 *>(&w->xrpow[i]);
+            if (!(xp.x >= roundfac)) nv &= 0xffff0000u;
+            if (!(xp.y >= roundfac)) nv &= 0x0000ffffu;
+            *reinterpret_cast<unsigned *>(&w->ixw[i]) = nv;
+        }
+        if (i < ilim) {
+            if (nv != 0u) nz = P;
+            if ((nv & 0xfffefffeu) != 0u) big = P;
+        }
+    }
+    return (unsigned) (nz + 1) | ((unsigned) (big + 1) << 16);     /* both are < 288 */
+}
+
+template <int SUB>
 __device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, LgPrev &pv, int lane)
 {
     float const istep = __ldg(&c->ipow20[gi.global_gain]);
@@ -289,6 +317,10 @@ __device__ __forceinline__ int lg_count_bits(const LgDevCfg *__restrict__ c, LgQ
             if (nv != 0u) hi_nz = P;
             if ((nv & 0xfffefffeu) != 0u) hi_big = P;
         }
+    }
+    if (SUB) {
+        unsigned const r = lg_substep_zero(c, w, gi.global_gain + gi.scalefac_scale, qc.sfbmax, qc.jn, ilim, lane);
+        hi_nz = (int) (r & 0xffffu) - 1; hi_big = (int) (r >> 16) - 1;
     }
     return lg_noquant_tail(c, w, gi, qc, pv, hi_nz, hi_big, lane);
 }
@@ -648,13 +680,40 @@ __device__ __noinline__ float lg_scale_bands(LgQWarp *w, float xrpow_max, int jn
     return mx;
 }
 
-/* quantize.c:720 amp_scalefac_bands (noise_shaping_amp 0 and 1; 2/3 belong to quality <= 1) */
+/* quantize.c:720 amp_scalefac_bands with noise_shaping_amp == 2 (quality 0/1): exactly one band, the first whose
+ * distortion is the maximum; with substep shaping every other visit of a band is its half step - the band's flag flips
+ * off and nothing is amplified (quantize.c:781-785).  Returns the new xrpow_max.  Out of line: the other quality levels
+ * never come here and the search loop has to stay small. */
+__device__ __noinline__ float lg_amp_one_band(LgQWarp *w, float trigger, float ifqstep34, float xrpow_max, int sfbmax, int jn, int substep, int lane)
+{
+    int first = 64;
+    for (int r = 1; r >= 0; r--) { int const sfb = lane + 32 * r; if (sfb < sfbmax && !(w->distort[sfb] < trigger)) first = sfb; }
+    first = lg_wmin_i(first);
+    if (first >= sfbmax) return xrpow_max;
+    if (substep) {
+        unsigned const bit = 1u << (first & 31);
+        unsigned const now = w->ph[first >> 5] ^ bit;
+        __syncwarp();
+        if (lane == 0) w->ph[first >> 5] = now;
+        __syncwarp();
+        if (!(now & bit)) return xrpow_max;
+    }
+    for (int r = 0; r < 2; r++) { int const sfb = lane + 32 * r; if (sfb < 40) reinterpret_cast<float *>(w->act)[sfb] = (sfb == first) ? ifqstep34 : 0.f; }
+    if (lane == 0) w->sfw[first]++;
+    __syncwarp();
+    return lg_scale_bands(w, xrpow_max, jn, lane);
+}
+
+/* quantize.c:720 amp_scalefac_bands (noise_shaping_amp 0, 1 and 2; 3 is not selected by any quality level) */
+template <int SUB>
 __device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     float const ifqstep34 = (gi.scalefac_scale == 0) ? (float) 1.29683955465100964055 : (float) 1.68179283050742922612;
     float trigger = 0;
     for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (trigger < w->distort[sfb]) trigger = w->distort[sfb];
     trigger = lg_wmax_fpos(trigger);
+    int const substep = SUB;
+    if (SUB && c->noise_shaping_amp == 2) { gi.xrpow_max = lg_amp_one_band(w, trigger, ifqstep34, gi.xrpow_max, qc.sfbmax, qc.jn, substep, lane); return; }
     if (c->noise_shaping_amp == 1) {
         if (trigger > 1.0) trigger = (float) sqrt((double) trigger);      /* pow(trigger, .5), see lg_math.cuh */
         else trigger = (float) (trigger * .95);
@@ -665,10 +724,12 @@ __device__ __forceinline__ void lg_amp_scalefac_bands(const LgDevCfg *__restrict
     }
     for (int r = 0; r < 2; r++) {
         int const sfb = lane + 32 * r;
-        if (sfb < 40) {
-            float f = 0.f;
-            if (sfb < qc.sfbmax && !(w->distort[sfb] < trigger)) { w->sfw[sfb]++; f = ifqstep34; }
-            reinterpret_cast<float *>(w->act)[sfb] = f;
+        float f = 0.f;
+        if (sfb < qc.sfbmax && !(w->distort[sfb] < trigger)) { w->sfw[sfb]++; f = ifqstep34; }
+        if (sfb < 40) reinterpret_cast<float *>(w->act)[sfb] = f;
+        if (substep) {                             /* every amplified band flips its half-step flag (quantize.c:781) */
+            unsigned const m = __ballot_sync(LG_FULL, f != 0.f);
+            if (lane == 0) w->ph[r] ^= m;
         }
     }
     __syncwarp();
@@ -736,9 +797,10 @@ __device__ __forceinline__ int lg_inc_subblock_gain(const LgDevCfg *__restrict__
 }
 
 /* quantize.c:940 balance_noise (the two scale_bitcount calls share one site) */
+template <int SUB>
 __device__ __forceinline__ int lg_balance_noise(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
-    lg_amp_scalefac_bands(c, w, gi, qc, lane);
+    lg_amp_scalefac_bands<SUB>(c, w, gi, qc, lane);
     if (lg_loop_break(w, gi.sbg, qc.sfbmax, lane)) return 0;
     for (int pass = 0;; pass++) {
         unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, lane);
@@ -747,6 +809,10 @@ __device__ __forceinline__ int lg_balance_noise(const LgDevCfg *__restrict__ c, 
         if (!status) return 1;
         if (pass == 1) return 0;
         if (c->noise_shaping > 1) {
+            if (SUB) {                                           /* quantize.c:971 */
+                if (lane == 0) { w->ph[0] = 0; w->ph[1] = 0; }
+                __syncwarp();
+            }
             if (!gi.scalefac_scale) { lg_inc_scalefac_scale(w, gi, qc, lane); status = 0; }
             else if (qc.block_type == LG_SHORT && c->subblock_gain > 0)
                 status = lg_inc_subblock_gain(c, w, gi, qc, lane) || lg_loop_break(w, gi.sbg, qc.sfbmax, lane);
@@ -796,6 +862,7 @@ __device__ __forceinline__ void lg_runaway()
  * registers for the whole search.  phase: 0 step-size search, main loop; 1 its "while too many bits" tail; 2 the first
  * and 3 the second "raise global_gain until it fits" loop of a noise-shaping round (quantize.c:1083-1101).
  * On return the work set (gi, sfw, ixw) holds the chosen quantisation. */
+template <int SUB>
 __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int targ_bits,
                                               int *old_value, int *current_step, int lane)
 {
@@ -809,7 +876,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
     int age = 0, best_part2_3_length = 9999999, maxggain = 255, huff_bits = 0, phase = 0;
     for (int guard = 0;; guard++) {
         if (guard > 30000) lg_runaway();
-        int const nBits = lg_count_bits(c, w, gi, qc, pv, lane);
+        int const nBits = lg_count_bits<SUB>(c, w, gi, qc, pv, lane);
         if (phase == 0) {
             if (!(CurrentStep == 1 || nBits == desired_rate)) {
                 int step;
@@ -870,8 +937,8 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
                 age = 0;
             }
             else if (c->full_outer_loop == 0) {
-                if (++age > 3 && best_noise.over_count == 0) break;
-                /* the noise_shaping_amp == 3 exits and the second (refinement) pass belong to quality 0/1, which lg_setup rejects */
+                if (++age > (SUB ? 20 : 3) && best_noise.over_count == 0) break;     /* quantize.c:1061-1066 */
+                /* the noise_shaping_amp == 3 exits and the second (refinement) pass are not selected by any quality level */
             }
             if (!((gi.global_gain + gi.scalefac_scale) < 255)) break;
         }
@@ -880,7 +947,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
             if (w->distort[qc.sfbmax] > 1.0) break;
             if (qc.block_type == LG_SHORT && (w->distort[qc.sfbmax + 1] > 1.0 || w->distort[qc.sfbmax + 2] > 1.0)) break;
         }
-        if (lg_balance_noise(c, w, gi, qc, lane) == 0) break;
+        if (lg_balance_noise<SUB>(c, w, gi, qc, lane) == 0) break;
         maxggain = gi.scalefac_scale ? 254 : 255;
         huff_bits = targ_bits - gi.part2_length;
         if (huff_bits <= 0) break;
@@ -1317,6 +1384,9 @@ __device__ __forceinline__ void lg_calc_target_bits(const LgDevCfg *__restrict__
 }
 
 /* ---------------------------------------------------------------- the kernel */
+/* SUB = 1: the build of the kernel with substep shaping and one-band amplification (quality 0-2; cfg->substep_shaping & 2).
+ * The other quality levels run SUB = 0, whose search loop does not carry that code. */
+template <int SUB>
 __global__ void __launch_bounds__(64)
 lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy,
                 const LgFrameCtl *__restrict__ frm, LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout,
@@ -1444,7 +1514,11 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                         qc.max_nonzero_coeff = qx.max_nonzero_coeff; qc.jn = qx.jn;
                         if (abr && qx.ath_over == 0) targ_bits[ch] = analog_silence_bits;     /* quantize.c:1951 analog silence */
                     }
-                    lg_outer_loop(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, lane);
+                    if (SUB) {                                    /* quantize.c:131-137 */
+                        if (lane == 0) w->ph[0] = w->ph[1] = ~0u;
+                        __syncwarp();
+                    }
+                    lg_outer_loop<SUB>(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, lane);
                 }
                 /* quantize.c:1213 iteration_finish_one */
                 {

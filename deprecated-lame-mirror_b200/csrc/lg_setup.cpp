@@ -517,8 +517,21 @@ static int setup_quality(LgDevCfg *c, int quality)
         if (c->subblock_gain == -1) c->subblock_gain = 1;
         c->use_best_huffman = 1; c->full_outer_loop = 0;
         break;
-    case 2: case 1: case 0:
-        return -1; /* substep shaping (qsort path) is outside the restated path */
+    case 2:
+        if (c->noise_shaping == 0) c->noise_shaping = 1;
+        if (c->substep_shaping == 0) c->substep_shaping = 2;
+        c->noise_shaping_amp = 1; c->noise_shaping_stop = 1;
+        if (c->subblock_gain == -1) c->subblock_gain = 1;
+        c->use_best_huffman = 1; c->full_outer_loop = 0;
+        break;
+    case 1:
+    case 0:
+        if (c->noise_shaping == 0) c->noise_shaping = 1;
+        if (c->substep_shaping == 0) c->substep_shaping = 2;
+        c->noise_shaping_amp = 2; c->noise_shaping_stop = 1;
+        if (c->subblock_gain == -1) c->subblock_gain = 1;
+        c->use_best_huffman = 1; c->full_outer_loop = (quality == 0);
+        break;
     }
     return 0;
 }

@@ -563,12 +563,31 @@ static int noquant_count_bits(const lp_config *c, lp_granule *gi, noise_cache *p
     return bits;
 }
 
+/* QntStateVar_t.pseudohalf (util.h:318): per scalefactor band, whether the "half step" of substep shaping (quality 0-2)
+ * is on.  One array per encoder in the reference; init_xrpow resets every band a gr.ch uses before it is read, so a
+ * per-thread array is equivalent. */
+static __thread int pseudohalf[LP_SFBMAX];
+
 /* takehiro.c:767 count_bits */
 static int count_bits(const lp_config *c, const float *xr, lp_granule *gi, noise_cache *prev)
 {
     float const w = (LP_IXMAX) / c->ipow20[gi->global_gain];
     if (gi->xrpow_max > w) return LP_LARGE_BITS;
     quantize_xrpow(c, xr, gi->l3_enc, c->ipow20[gi->global_gain], gi, prev);
+    if (c->substep_shaping & 2) {
+        /* bands in their half step drop the values that only just rounded up to 1 (takehiro.c:781-797) */
+        int sfb, j = 0;
+        int const gain = gi->global_gain + gi->scalefac_scale;
+        const float roundfac = 0.634521682242439 / c->ipow20[gain];
+        for (sfb = 0; sfb < gi->sfbmax; sfb++) {
+            int const width = gi->width[sfb];
+            if (!pseudohalf[sfb]) j += width;
+            else {
+                int k;
+                for (k = j, j += width; k < j; ++k) gi->l3_enc[k] = (xr[k] >= roundfac) ? gi->l3_enc[k] : 0;
+            }
+        }
+    }
     return noquant_count_bits(c, gi, prev);
 }
 
@@ -815,7 +834,7 @@ static void init_outer_loop(const lp_config *c, lp_granule *gi)
 }
 
 /* quantize.c:110 init_xrpow with :72 init_xrpow_core_c */
-static int init_xrpow(lp_granule *gi, float xrpow[576])
+static int init_xrpow(const lp_config *c, lp_granule *gi, float xrpow[576])
 {
     float sum = 0;
     int i;
@@ -828,7 +847,11 @@ static int init_xrpow(lp_granule *gi, float xrpow[576])
         xrpow[i] = sqrt(tmp * sqrt(tmp));       /* double sqrt of the float, float product, double sqrt */
         if (xrpow[i] > gi->xrpow_max) gi->xrpow_max = xrpow[i];
     }
-    if (sum > (float) 1E-20) return 1;
+    if (sum > (float) 1E-20) {
+        int const j = (c->substep_shaping & 2) ? 1 : 0;
+        for (i = 0; i < gi->psymax; i++) pseudohalf[i] = j;
+        return 1;
+    }
     memset(&gi->l3_enc[0], 0, sizeof(int) * 576);
     return 0;
 }
@@ -925,6 +948,10 @@ static void amp_scalefac_bands(const lp_config *c, lp_granule *gi, const float *
         int l;
         j += width;
         if (distort[sfb] < trigger) continue;
+        if (c->substep_shaping & 2) {
+            pseudohalf[sfb] = !pseudohalf[sfb];
+            if (!pseudohalf[sfb] && c->noise_shaping_amp == 2) return;
+        }
         gi->scalefac[sfb]++;
         for (l = -width; l < 0; l++) {
             xrpow[j + l] *= ifqstep34;
@@ -1010,6 +1037,7 @@ static int balance_noise(const lp_config *c, lp_granule *gi, const float *distor
     status = scale_bitcount(gi);
     if (!status) return 1;
     if (c->noise_shaping > 1) {
+        memset(pseudohalf, 0, sizeof pseudohalf);
         if (!gi->scalefac_scale) { inc_scalefac_scale(gi, xrpow); status = 0; }
         else if (gi->block_type == LP_SHORT && c->subblock_gain > 0)
             status = inc_subblock_gain(c, gi, xrpow) || loop_break(gi);
@@ -1022,7 +1050,7 @@ static int balance_noise(const lp_config *c, lp_granule *gi, const float *distor
 static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float xrpow[576], int ch, int targ_bits)
 {
     const lp_config *cfg = &e->cfg;
-    static lp_granule gi_w;
+    static __thread lp_granule gi_w;
     float save_xrpow[576], distort[LP_SFBMAX];
     noise_result best_noise_info;
     int huff_bits, better, age;
@@ -1040,7 +1068,8 @@ static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float
     while (!bEndOfSearch) {
         do {
             noise_result noise_info;
-            int search_limit = 3, maxggain = 255;
+            int const search_limit = (cfg->substep_shaping & 2) ? 20 : 3;
+            int maxggain = 255;
             if (cfg->sfb21_extra) {
                 if (distort[gi_w.sfbmax] > 1.0) break;
                 if (gi_w.block_type == LP_SHORT && (distort[gi_w.sfbmax + 1] > 1.0 || distort[gi_w.sfbmax + 2] > 1.0)) break;
@@ -1115,7 +1144,7 @@ void lp_cbr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ra
             else masking_lower_db = cfg->mask_adjust_short - 0;
             e->masking_lower = pow(10.0, masking_lower_db * 0.1);
             init_outer_loop(cfg, gi);
-            if (init_xrpow(gi, xrpow)) {
+            if (init_xrpow(cfg, gi, xrpow)) {
                 (void) calc_xmin(e, &ratio[gr][ch], gi, l3_xmin);
                 (void) outer_loop(e, gi, l3_xmin, xrpow, ch, targ_bits[ch]);
             }
@@ -1209,7 +1238,7 @@ void lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ra
             else masking_lower_db = cfg->mask_adjust_short - 0;
             e->masking_lower = pow(10.0, masking_lower_db * 0.1);
             init_outer_loop(cfg, gi);
-            if (init_xrpow(gi, xrpow)) {
+            if (init_xrpow(cfg, gi, xrpow)) {
                 int const ath_over = calc_xmin(e, &ratio[gr][ch], gi, l3_xmin);
                 if (0 == ath_over) targ_bits[gr][ch] = analog_silence_bits;
                 (void) outer_loop(e, gi, l3_xmin, xrpow, ch, targ_bits[gr][ch]);
@@ -1850,7 +1879,7 @@ void lp_vbr_new_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ene
     /* the loop itself */
     for (gr = 0; gr < cfg->mode_gr; gr++)
         for (ch = 0; ch < cfg->channels; ch++)
-            if (0 == init_xrpow(&e->tt[gr][ch], xrpow[gr][ch])) max_bits[gr][ch] = 0;
+            if (0 == init_xrpow(cfg, &e->tt[gr][ch], xrpow[gr][ch])) max_bits[gr][ch] = 0;
     used_bits = vbr_encode_frame(e, xrpow, l3_xmin, max_bits);
     i = (analog_silence /* && !enforce_min_bitrate */) ? 1 : cfg->vbr_min_bitrate_index;
     for (; i < cfg->vbr_max_bitrate_index; i++) if (used_bits <= frameBits[i]) break;

@@ -57,6 +57,18 @@ def test_emulated_resampler_matches_port(emu_bin, args, env):
     assert "IDENTICAL" in r.stdout
 
 
+@pytest.mark.parametrize("args,env", [
+    ("4 12 4 128 -1 2 44100 1152", {}), ("3 12 4 128 -1 1 44100 1152", {}), ("3 12 8 320 1 0 44100 3000", {}), ("3 12 4 192 0 1 48000 777", {}),
+    ("3 12 8 128 -1 0 44100 1152", dict(LP_VBR="3")),
+])
+def test_emulated_quality_0_to_2_matches_port(emu_bin, args, env):
+    """kernel D with substep shaping (half-step flags as a bit mask, the post-quantisation drop in lg_substep_zero), one-band
+    amplification and the full outer loop"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout
+
+
 TAG_SCRIPT = r"""
 import json, os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))

@@ -46,6 +46,9 @@ def test_golden_vectors(lib, name):
     dict(S=16, F=24, fpl=8, brate=128), dict(S=7, F=30, fpl=16, brate=320, mode=1), dict(S=5, F=20, fpl=3, brate=192, mode=0, q=5),
     dict(S=4, F=16, fpl=8, brate=256, sr=48000), dict(S=4, F=16, fpl=8, brate=128, sr=32000), dict(S=3, F=12, fpl=4, brate=160, q=7),
     dict(S=3, F=12, fpl=4, brate=112, q=9), dict(S=2, F=40, fpl=40, brate=224, q=4),
+    # quality 2 / 1 / 0: substep shaping, one-band amplification, full outer loop
+    dict(S=8, F=24, fpl=8, brate=128, q=2), dict(S=8, F=24, fpl=8, brate=128, q=1), dict(S=8, F=24, fpl=8, brate=128, q=0),
+    dict(S=4, F=20, fpl=4, brate=320, mode=1, q=0), dict(S=4, F=16, fpl=8, brate=192, mode=0, q=1, sr=48000), dict(S=4, F=16, fpl=8, brate=112, q=2, sr=32000),
 ])
 def test_batch_matches_oracle(lib, oracle_mod, cfg):
     S, F = cfg["S"], cfg["F"]
@@ -73,6 +76,7 @@ def test_batch_matches_oracle(lib, oracle_mod, cfg):
 @pytest.mark.parametrize("cfg", [
     dict(S=16, F=24, fpl=8, brate=128), dict(S=6, F=30, fpl=16, brate=192, mode=1), dict(S=4, F=20, fpl=3, brate=150, mode=0, q=5),
     dict(S=4, F=16, fpl=8, brate=256, sr=48000), dict(S=3, F=16, fpl=8, brate=112, sr=32000, q=7),
+    dict(S=4, F=20, fpl=8, brate=128, q=0), dict(S=4, F=20, fpl=8, brate=160, q=2),
 ])
 def test_abr_batch_matches_oracle(lib, oracle_mod, cfg):
     """ABR (vbr_abr): the device chooses every frame's bitrate index (quantize.c:1962), frames of different sizes go
@@ -272,7 +276,7 @@ def test_edge_cases(lib, oracle_mod):
 
 
 def test_unsupported_configurations_fail_loudly(lib):
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=1), dict(out_samplerate=24000), dict(brate=7, vbr=4)):
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(out_samplerate=24000), dict(brate=7, vbr=4)):
         with pytest.raises(lib.LameGpuError):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()

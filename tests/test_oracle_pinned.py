@@ -41,8 +41,8 @@ def test_port_chunking_invariance(oracle_mod):
 
 
 def test_port_rejects_unsupported(oracle_mod):
-    # MPEG-2 output rates (22.05 kHz input; 64 kbps makes lame_init_params pick 24 kHz), quality 0-2, VBR -V7 (fractional VBR_q at 32 kHz)
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(quality=2), dict(brate=7, vbr=4), dict(out_samplerate=22050)):
+    # MPEG-2 output rates (22.05 kHz input; 64 kbps makes lame_init_params pick 24 kHz), VBR -V7 (fractional VBR_q at 32 kHz)
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(brate=7, vbr=4), dict(out_samplerate=22050)):
         with pytest.raises(ValueError):
             oracle_mod.PortEncoder(**kw)
 
@@ -107,6 +107,19 @@ def test_port_resampler_vs_reference(port_vs_ref_bin, args, env):
     """input rate != output rate (explicit lame_set_out_samplerate = LP_OUT_SR, or the rate lame_init_params picks): the
     polyphase resampler util.c:531, its per-call state (LP_CHUNK = samples per encode call) and the flush padding rule
     lame.c:2083-2100; also the low bitrates that only exist through it (96 kbps at 44.1 kHz -> 32 kHz).  Byte-identical."""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
+@pytest.mark.parametrize("args,env", [
+    ("noise 128 -1 2 60", {}), ("click 128 -1 2 100", {}), ("sine 128 -1 1 60", {}), ("click 128 -1 1 100", {}), ("click 128 -1 0 100", {}),
+    ("noise 128 -1 0 40", {}), ("gap 192 0 0 60", {}), ("click 320 1 1 60", {}), ("click 160 -1 2 60 48000", {}), ("sine 112 -1 0 40 32000", {}),
+    ("click 128 -1 0 60", dict(LP_VBR="3")), ("noise 160 -1 2 40", dict(LP_VBR="3")),
+])
+def test_port_quality_0_to_2_vs_reference(port_vs_ref_bin, args, env):
+    """quality 2 / 1 / 0 (the 4th argument): substep shaping with the per-band half-step flags (quantize.c:131,781, takehiro.c:781),
+    one-band-at-a-time amplification (noise_shaping_amp 2) and the full outer loop; CBR and ABR, byte-identical to libmp3lame"""
     r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **env))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
