@@ -73,6 +73,9 @@ def load_library(path=None):
         "lame_encode_buffer_int": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int]),
         "lame_get_lametag_frame": (ctypes.c_size_t, [c_void_p, c_void_p, ctypes.c_size_t]),
         "get_lame_short_version": (c_char_p, []),
+        "lame_bitrate_kbps": (None, [c_void_p, c_void_p]), "lame_bitrate_hist": (None, [c_void_p, c_void_p]),
+        "lame_stereo_mode_hist": (None, [c_void_p, c_void_p]), "lame_bitrate_stereo_mode_hist": (None, [c_void_p, c_void_p]),
+        "lame_block_type_hist": (None, [c_void_p, c_void_p]), "lame_bitrate_block_type_hist": (None, [c_void_p, c_void_p]),
         "lamegpu_batch_open": (c_void_p, [c_int] * 8),
         "lamegpu_batch_close": (None, [c_void_p]),
         "lamegpu_batch_encode": (c_long, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -103,7 +106,8 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lamegpu_batch_open_rs", "lame_get_lametag_frame", "get_lame_short_version", "lame_encode_buffer_float",
+    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lamegpu_batch_open_rs", "lame_get_lametag_frame", "get_lame_short_version", "lame_bitrate_kbps", "lame_bitrate_hist", "lame_stereo_mode_hist",
+    "lame_bitrate_stereo_mode_hist", "lame_block_type_hist", "lame_bitrate_block_type_hist", "lame_encode_buffer_float",
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
@@ -115,6 +119,19 @@ EXPORTED_SYMBOLS = [
 def _as_i16(a):
     a = np.ascontiguousarray(a, dtype=np.int16)
     return a
+
+
+def _histograms(L, h):
+    """the six statistics calls of lame.h:909-929 on handle `h` of library `L` (ours or the reference's)"""
+    out = {}
+    for name, shape in (("lame_bitrate_kbps", (14,)), ("lame_bitrate_hist", (14,)), ("lame_stereo_mode_hist", (4,)),
+                        ("lame_bitrate_stereo_mode_hist", (14, 4)), ("lame_block_type_hist", (6,)), ("lame_bitrate_block_type_hist", (14, 6))):
+        a = np.zeros(shape, dtype=np.int32)
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = None, [ctypes.c_void_p, ctypes.c_void_p]
+        fn(h, a.ctypes.data)
+        out[name] = a
+    return out
 
 
 class Encoder:
@@ -174,6 +191,10 @@ class Encoder:
         buf = np.empty(2880, dtype=np.uint8)
         n = self._lib.lame_get_lametag_frame(self._h, buf.ctypes.data, buf.size)
         return buf[:n].tobytes()
+
+    def histograms(self):
+        """lame_bitrate_kbps / _hist / _stereo_mode_hist / _block_type_hist and the per-bitrate tables (lame.h:909-929)"""
+        return _histograms(self._lib, self._h)
 
     def close(self):
         if self._h:

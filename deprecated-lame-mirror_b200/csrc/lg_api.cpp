@@ -48,6 +48,9 @@ struct Stream {
     long mf_samples_to_encode = 576 + 1152;   /* ENCDELAY + POSTDELAY, lame.c:2299 */
     int  last_padding = 0, last_bitrate_index = 0;
     LgBitWriter bw;
+    /* encoder.c:156 updateStats: frames per bitrate index x mode extension (column 4 = all), gr.ch per bitrate index x block
+     * type (4 = mixed, column 5 = all); row 15 = totals */
+    int  hist_mode[16][5], hist_block[16][6];
     std::vector<unsigned char> out;    /* packed bytes not yet handed to the caller */
     /* Info tag bookkeeping of one lame_t (VbrTag.c): the seek table of AddVbrFrame (:196), the byte count and music
      * CRC of copy_buffer (bitstream.c:1079-1090), what lame_get_lametag_frame (:900) needs at the end */
@@ -69,6 +72,7 @@ struct Stream {
         for (int c = 0; c < 2; c++) raw[c].assign(LG_RS_HIST, 0.f);
         raw_base = -LG_RS_HIST; chunks.clear(); rs_itime = 0; rs_tend = 528;
         bw.reset(); out.clear();
+        memset(hist_mode, 0, sizeof hist_mode); memset(hist_block, 0, sizeof hist_block);
         tag = Tag();
     }
     long tend() const { return rs_mode ? rs_tend : tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()); }
@@ -312,6 +316,14 @@ struct lamegpu_batch {
                     lg_merge_frame(&x.bw, &cfg, fr, hdr + ((size_t) s * F + f) * LG_HDR_STRIDE, pay + (size_t) s * pay_stride + fr->pay_off);
                     x.last_padding = fr->padding;
                     x.last_bitrate_index = fr->bitrate_index;
+                    {
+                        int const bi = fr->bitrate_index & 15;
+                        const unsigned char *bt = hdr + ((size_t) s * F + f) * LG_HDR_STRIDE + 36;
+                        x.hist_mode[bi][4]++; x.hist_mode[15][4]++;
+                        if (cfg.channels == 2) { x.hist_mode[bi][fr->mode_ext & 3]++; x.hist_mode[15][fr->mode_ext & 3]++; }
+                        for (int k = 0; k < 4; k++)
+                            if (bt[k] < 5) { x.hist_block[bi][bt[k]]++; x.hist_block[bi][5]++; x.hist_block[15][bt[k]]++; x.hist_block[15][5]++; }
+                    }
                     if (x.tag.on) { tag_add_frame(x.tag, cfg.bitrate_kbps[fr->bitrate_index]); x.tag.mode_ext = fr->mode_ext; }
                 }
                 x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
@@ -816,6 +828,38 @@ int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
     x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
     x.bw.buf.clear();
     return handle_take(g, mp3buf, size);
+}
+/* lame.c:2462-2606: the statistics of the frames encoded so far (bitrates of this MPEG version, frames per bitrate and
+ * stereo mode, gr.ch per bitrate and block type) */
+void lame_bitrate_kbps(const lame_global_flags *g, int bitrate_kbps[14])
+{
+    if (!ok(g) || !g->b) return;
+    for (int i = 0; i < 14; i++) bitrate_kbps[i] = g->b->cfg.bitrate_kbps[i + 1];
+}
+void lame_bitrate_hist(const lame_global_flags *g, int bitrate_count[14])
+{
+    if (!ok(g) || !g->b) return;
+    for (int i = 0; i < 14; i++) bitrate_count[i] = g->b->st[0].hist_mode[i + 1][4];
+}
+void lame_stereo_mode_hist(const lame_global_flags *g, int stmode_count[4])
+{
+    if (!ok(g) || !g->b) return;
+    for (int i = 0; i < 4; i++) stmode_count[i] = g->b->st[0].hist_mode[15][i];
+}
+void lame_bitrate_stereo_mode_hist(const lame_global_flags *g, int bitrate_stmode_count[14][4])
+{
+    if (!ok(g) || !g->b) return;
+    for (int j = 0; j < 14; j++) for (int i = 0; i < 4; i++) bitrate_stmode_count[j][i] = g->b->st[0].hist_mode[j + 1][i];
+}
+void lame_block_type_hist(const lame_global_flags *g, int btype_count[6])
+{
+    if (!ok(g) || !g->b) return;
+    for (int i = 0; i < 6; i++) btype_count[i] = g->b->st[0].hist_block[15][i];
+}
+void lame_bitrate_block_type_hist(const lame_global_flags *g, int bitrate_btype_count[14][6])
+{
+    if (!ok(g) || !g->b) return;
+    for (int j = 0; j < 14; j++) for (int i = 0; i < 6; i++) bitrate_btype_count[j][i] = g->b->st[0].hist_block[j + 1][i];
 }
 /* VbrTag.c:900 lame_get_lametag_frame (+ :151 Xing_seek_table, :597 PutLameVBR) for the configurations this library
  * encodes: CBR ("Info"), MPEG-1, no CRC, no ReplayGain analysis, no nogap. */

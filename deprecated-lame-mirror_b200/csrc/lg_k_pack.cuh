@@ -255,6 +255,9 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
             lg_put(sm->hdr, so, gi->count1table_select, 1);
         }
     }
+    /* bytes 36..39 of the record, behind the longest side info: the four block types (4 = mixed, 0xff = no such channel) for
+     * the host's statistics (encoder.c:156 updateStats) */
+    if (lane == 0) lg_put(sm->hdr, 288 + 8 * warp, ch < nch ? (g4[warp].mixed_block_flag ? 4u : (unsigned) g4[warp].block_type) : 0xffu, 8);
     /* ---- ancillary drains and the frame header (warps 2 and 3 are the lighter ones in joint stereo) */
     if (warp == 3) lg_put_drain(sm->img, 0, fo->drain_pre, fo->anc_pre, !c->disable_reservoir, lane);
     if (warp == 2) {

@@ -82,6 +82,13 @@ int  lame_encode_flush(lame_global_flags *, unsigned char *mp3buf, int size);   
 /* Info tag (CBR): lame_set_bWriteVbrTag(1) - the reference's default - puts the all-zero placeholder frame ahead of
  * the audio; after lame_encode_flush this returns the finished tag frame to be written at offset 0 (VbrTag.c:900) */
 size_t lame_get_lametag_frame(const lame_global_flags *, unsigned char *buffer, size_t size); /* lame.h:970 */
+/* statistics of the frames encoded so far (encoder.c:156 updateStats), same layouts as the reference */
+void lame_bitrate_kbps(const lame_global_flags *, int bitrate_kbps[14]);                         /* lame.h:912 */
+void lame_bitrate_hist(const lame_global_flags *, int bitrate_count[14]);                        /* lame.h:909 */
+void lame_stereo_mode_hist(const lame_global_flags *, int stereo_mode_count[4]);                 /* lame.h:915 */
+void lame_bitrate_stereo_mode_hist(const lame_global_flags *, int bitrate_stmode_count[14][4]);  /* lame.h:919 */
+void lame_block_type_hist(const lame_global_flags *, int btype_count[6]);                        /* lame.h:923 */
+void lame_bitrate_block_type_hist(const lame_global_flags *, int bitrate_btype_count[14][6]);    /* lame.h:927 */
 int  lame_close(lame_global_flags *);                                                /* lame.h:977 */
 const char *get_lame_short_version(void);                                            /* lame.h:645 */
 

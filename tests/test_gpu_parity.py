@@ -179,6 +179,27 @@ def test_resampled_lame_api_with_tag(lib, oracle_mod):
     r.close()
 
 
+@pytest.mark.parametrize("kw", [dict(brate=128), dict(brate=2, vbr=4), dict(brate=150, vbr=3), dict(brate=192, mode=0), dict(brate=96, mode=3)])
+def test_statistics_match_reference(lib, oracle_mod, kw):
+    """lame_bitrate_hist / lame_stereo_mode_hist / lame_block_type_hist and the per-bitrate tables (lame.h:909-929, encoder.c:156):
+    the host keeps them from what the device reports per frame; equal to the reference's after the same stream"""
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build")
+    x = make_signal("click", 40 * 1152, seed=9)
+    mode = kw.get("mode", -1)
+    e = lib.Encoder(44100, 2, kw["brate"], mode if mode >= 0 else lib.NOT_SET, -1, vbr=kw.get("vbr", 0))
+    r = oracle_mod.RefEncoder(44100, 2, kw["brate"], mode if mode >= 0 else 4, -1, vbr=kw.get("vbr", 0))
+    a = e.encode(x[0], x[1]) + e.flush()
+    b = r.encode(x[0], x[1]) + r.flush()
+    assert a == b
+    ours, ref = e.histograms(), lib._histograms(r.lib, r.h)
+    for k in ref:
+        assert (ours[k] == ref[k]).all(), k
+    assert ours["lame_block_type_hist"][2] > 0        # the click stream has short blocks
+    e.close()
+    r.close()
+
+
 def test_config4_vbr_v2_full_size(lib, oracle_mod):
     """BASELINE configs[3]: VBR -V2 (vbr_mtrh) on the sine + noise mix at 2048 streams x 16 frames; every stream structurally
     (frame sync, frame length from its own bitrate index), a sample of streams byte for byte against the oracle - exact,
