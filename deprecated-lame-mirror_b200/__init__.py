@@ -55,6 +55,8 @@ def load_library(path=None):
         "lame_set_VBR_q": (c_int, [c_void_p, c_int]), "lame_get_VBR_q": (c_int, [c_void_p]),
         "lamegpu_batch_open_ex": (c_void_p, [c_int] * 9),
         "lamegpu_batch_open_rs": (c_void_p, [c_int] * 10),
+        "lamegpu_batch_open_vq": (c_void_p, [c_int, c_int, c_int, ctypes.c_float] + [c_int] * 6),
+        "lame_set_VBR_quality": (c_int, [c_void_p, ctypes.c_float]), "lame_get_VBR_quality": (ctypes.c_float, [c_void_p]),
         "lame_set_bWriteVbrTag": (c_int, [c_void_p, c_int]), "lame_get_bWriteVbrTag": (c_int, [c_void_p]),
         "lame_init_params": (c_int, [c_void_p]),
         "lame_get_framesize": (c_int, [c_void_p]), "lame_get_frameNum": (c_int, [c_void_p]),
@@ -106,7 +108,7 @@ EXPORTED_SYMBOLS = [
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
     "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
     "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lamegpu_batch_open_rs", "lame_get_lametag_frame", "get_lame_short_version", "lame_bitrate_kbps", "lame_bitrate_hist", "lame_stereo_mode_hist",
+    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lamegpu_batch_open_rs", "lamegpu_batch_open_vq", "lame_set_VBR_quality", "lame_get_VBR_quality", "lame_get_lametag_frame", "get_lame_short_version", "lame_bitrate_kbps", "lame_bitrate_hist", "lame_stereo_mode_hist",
     "lame_bitrate_stereo_mode_hist", "lame_block_type_hist", "lame_bitrate_block_type_hist", "lame_encode_buffer_float",
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
@@ -153,7 +155,10 @@ class Encoder:
                 L.lame_set_VBR_mean_bitrate_kbps(self._h, brate)
         elif vbr == VBR_MTRH:
             L.lame_set_VBR(self._h, VBR_MTRH)
-            L.lame_set_VBR_q(self._h, brate)
+            if float(brate) == int(brate):
+                L.lame_set_VBR_q(self._h, int(brate))
+            else:
+                L.lame_set_VBR_quality(self._h, float(brate))   # fractional level
         elif brate:
             L.lame_set_brate(self._h, brate)
         if mode != NOT_SET:
@@ -215,7 +220,7 @@ class BatchEncoder:
                  frames_per_launch=8, device=0, vbr=VBR_OFF, out_samplerate=0):
         self._lib = load_library()
         self.nstreams, self.frames_per_launch = int(nstreams), int(frames_per_launch)
-        self._h = self._lib.lamegpu_batch_open_rs(samplerate, out_samplerate, channels, brate, mode, quality, vbr, self.nstreams,
+        self._h = self._lib.lamegpu_batch_open_vq(samplerate, out_samplerate, channels, float(brate), mode, quality, vbr, self.nstreams,
                                                   self.frames_per_launch, device)
         if not self._h:
             raise LameGpuError("lamegpu_batch_open failed (unsupported configuration, no CUDA device, or out of memory)")

@@ -487,9 +487,17 @@ lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, in
 lamegpu_batch *lamegpu_batch_open_rs(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, int nstreams,
                                      int frames_per_launch, int device)
 {
+    return lamegpu_batch_open_vq(samplerate_in, samplerate_out, channels, (float) brate, mode, quality, vbr, nstreams, frames_per_launch, device);
+}
+
+lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int channels, float rate, int mode, int quality, int vbr, int nstreams,
+                                     int frames_per_launch, int device)
+{
+    int const brate = (int) rate;
+    float const vbr_q_frac = (vbr == 4) ? rate - (float) brate : 0.f;
     lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
     if (!b) return NULL;
-    if (lg_setup(&b->cfg, samplerate_in, samplerate_out, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr) != 0) {
+    if (lg_setup(&b->cfg, samplerate_in, samplerate_out, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr, vbr_q_frac) != 0) {
         fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d -> %d, channels %d, brate %d, mode %d, quality %d, vbr %d)\n",
                 samplerate_in, samplerate_out, channels, brate, mode, quality, vbr);
         delete b;
@@ -628,6 +636,7 @@ size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }
 struct lame_global_struct {
     unsigned class_id;
     int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag, mean_brate, vbr_q;
+    float vbr_q_frac;
     MPEG_mode mode;
     vbr_mode VBR;
     int launch_frames;
@@ -678,7 +687,7 @@ lame_global_flags *lame_init(void)
     if (!g) return NULL;
     g->class_id = LAME_ID;
     g->num_channels = 2; g->samplerate_in = 44100; g->samplerate_out = 0; g->brate = 0; g->quality = -1;
-    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128; g->vbr_q = 4;
+    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128; g->vbr_q = 4; g->vbr_q_frac = 0;
     if (const char *e = getenv("LAMEGPU_HANDLE_FRAMES")) g->launch_frames = std::max(1, atoi(e));
     return g;
 }
@@ -706,8 +715,20 @@ int lame_set_VBR_q(lame_global_flags *g, int v)                     /* set_get.c
     if (v < 0) { ret = -1; v = 0; }
     if (v > 9) { ret = -1; v = 9; }
     g->vbr_q = v;
+    g->vbr_q_frac = 0;
     return ret;
 }
+int lame_set_VBR_quality(lame_global_flags *g, float v)            /* set_get.c:1152: 0 .. 9.999, integer level + fraction */
+{
+    if (!ok(g)) return -1;
+    int ret = 0;
+    if (0 > v) { ret = -1; v = 0; }
+    if (9.999 < v) { ret = -1; v = 9.999; }
+    g->vbr_q = (int) v;
+    g->vbr_q_frac = v - g->vbr_q;
+    return ret;
+}
+float lame_get_VBR_quality(const lame_global_flags *g) { return ok(g) ? g->vbr_q + g->vbr_q_frac : 0; }
 int lame_get_VBR_q(const lame_global_flags *g) { return ok(g) ? g->vbr_q : 0; }
 int lame_set_bWriteVbrTag(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->write_lame_tag = v; return 0; }
 int lame_get_bWriteVbrTag(const lame_global_flags *g) { return ok(g) ? g->write_lame_tag : 0; }
@@ -719,13 +740,15 @@ int lame_init_params(lame_global_flags *g)
     if (g->VBR == vbr_rh) { fprintf(stderr, "lamegpu: vbr_rh (VBR-old) is not implemented on the GPU path\n"); return -1; }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
     int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh);        /* both select VBR_new_iteration_loop, encoder.c:531 */
-    g->b = lamegpu_batch_open_rs(g->samplerate_in, g->samplerate_out, g->num_channels, is_vbr ? g->vbr_q : (g->VBR == vbr_abr ? g->mean_brate : g->brate),
+    g->b = lamegpu_batch_open_vq(g->samplerate_in, g->samplerate_out, g->num_channels,
+                                 is_vbr ? g->vbr_q + g->vbr_q_frac : (float) (g->VBR == vbr_abr ? g->mean_brate : g->brate),
                                  g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? 4 : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
     if (!g->b) return -1;
     g->samplerate_out = g->b->cfg.samplerate;
     g->brate = g->b->cfg.brate;
     g->mean_brate = g->b->cfg.vbr_mean_kbps;
     g->quality = g->b->cfg.quality;
+    if (is_vbr) { g->vbr_q = g->b->cfg.vbr_q; g->vbr_q_frac = g->b->cfg.vbr_q_frac; }      /* presets.c:203-206 */
     g->mode = (MPEG_mode) g->b->cfg.mode;
     g->initialised = 1;
     if (g->write_lame_tag) tag_init(g->b);                 /* lame.c:1249 lame_init_bitstream -> InitVbrTag */

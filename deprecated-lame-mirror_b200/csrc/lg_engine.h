@@ -8,7 +8,7 @@ extern "C" {
 #endif
 typedef struct lg_engine lg_engine;
 int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out /* 0 = as lame_init_params picks it */, int channels, int brate, int mode, int quality,
-             int vbr /* 0 vbr_off, 3 vbr_abr, 4 vbr_mtrh (brate = VBR_q) */);
+             int vbr /* 0 vbr_off, 3 vbr_abr, 4 vbr_mtrh (brate = VBR_q) */, float vbr_q_frac /* VBR quality = VBR_q + this */);
 lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device);
 void lg_engine_destroy(lg_engine *e);
 int  lg_engine_reset_streams(lg_engine *e, int first, int count);

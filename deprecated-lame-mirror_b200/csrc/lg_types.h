@@ -72,7 +72,7 @@ typedef struct {
     /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr, 4 = vbr_mtrh at quality vbr_q (lame.h:94).  ABR chooses a frame size per frame: mean bitrate, index range,
      * the compression ratio calc_target_bits reads (quantize.c:1768) and the bitrate table row of this MPEG version */
     int   vbr, vbr_q, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
-    float compression_ratio;
+    float compression_ratio, vbr_q_frac;     /* VBR quality = vbr_q + vbr_q_frac, after the mapping of lame.c:661-698 */
     int   bitrate_kbps[16];
     int   sfb_l[23], sfb_s[14], psfb21[7], psfb12[7];
     float amp_filter[32];

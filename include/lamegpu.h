@@ -49,6 +49,8 @@ int  lame_set_VBR_mean_bitrate_kbps(lame_global_flags *, int);                  
 int  lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *);                      /* lame.h:445 */
 int  lame_set_VBR_q(lame_global_flags *, int);                                       /* lame.h:436  VBR quality 0..9 (vbr_mtrh: 0..6 here) */
 int  lame_get_VBR_q(const lame_global_flags *);                                      /* lame.h:437 */
+int  lame_set_VBR_quality(lame_global_flags *, float);                               /* lame.h:438  fractional level 0 .. 9.999 */
+float lame_get_VBR_quality(const lame_global_flags *);                               /* lame.h:439 */
 int  lame_set_VBR_mean_bitrate_kbps(lame_global_flags *, int);                       /* lame.h:447  ABR mean bitrate */
 int  lame_get_VBR_mean_bitrate_kbps(const lame_global_flags *);                                    /* lame.h:433 */
 int  lame_set_bWriteVbrTag(lame_global_flags *, int);                                /* lame.h:240  the Info tag frame is not produced */
@@ -111,6 +113,11 @@ lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, in
  * optimum_samplefreq); it must come out as 32000, 44100 or 48000.  When the two differ the streams' samples go
  * through the reference's polyphase resampler (util.c:531 fill_buffer_resample) on the device. */
 lamegpu_batch *lamegpu_batch_open_rs(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality,
+                                     int vbr, int nstreams, int frames_per_launch, int device);
+/* same with a fractional rate argument: for vbr = 4 `rate` is the VBR quality 0 .. 9.999 of lame_set_VBR_quality (lame.h:447),
+ * otherwise the bitrate as above.  Without an explicit output rate the level is mapped as lame_init_params does it
+ * (lame.c:661-698): e.g. 7.0 at 44.1 kHz encodes at 32 kHz with internal quality 5.63. */
+lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int channels, float rate, int mode, int quality,
                                      int vbr, int nstreams, int frames_per_launch, int device);
 void lamegpu_batch_close(lamegpu_batch *b);
 

@@ -36,12 +36,13 @@ def have_ref():
 class PortEncoder:
     def __init__(self, samplerate=44100, channels=2, brate=128, mode=4, quality=-1, vbr=0, out_samplerate=0):
         self.lib = ctypes.CDLL(PORT_SO)
-        self.lib.lp_open_rs.restype = ctypes.c_void_p
-        self.lib.lp_open_rs.argtypes = [ctypes.c_int] * 7
+        self.lib.lp_open_vq.restype = ctypes.c_void_p
+        self.lib.lp_open_vq.argtypes = [ctypes.c_int] * 7 + [ctypes.c_float]
         self.lib.lp_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         self.lib.lp_flush.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         self.lib.lp_close.argtypes = [ctypes.c_void_p]
-        self.h = self.lib.lp_open_rs(samplerate, out_samplerate, channels, brate, 4 if mode < 0 else mode, quality, vbr)
+        frac = np.float32(brate) - np.float32(int(brate)) if vbr == 4 else 0.0      # VBR quality = integer level + fraction
+        self.h = self.lib.lp_open_vq(samplerate, out_samplerate, channels, int(brate), 4 if mode < 0 else mode, quality, vbr, float(frac))
         if not self.h:
             raise ValueError("port: unsupported configuration")
 
@@ -98,8 +99,12 @@ class RefEncoder:
         elif vbr == 4:                                        # vbr_mtrh: brate is VBR_q
             L.lame_set_VBR.argtypes = [ctypes.c_void_p, ctypes.c_int]
             L.lame_set_VBR_q.argtypes = [ctypes.c_void_p, ctypes.c_int]
+            L.lame_set_VBR_quality.argtypes = [ctypes.c_void_p, ctypes.c_float]
             L.lame_set_VBR(self.h, 4)
-            L.lame_set_VBR_q(self.h, brate)
+            if float(brate) == int(brate):
+                L.lame_set_VBR_q(self.h, int(brate))
+            else:
+                L.lame_set_VBR_quality(self.h, float(brate))
         elif brate:
             L.lame_set_brate(self.h, brate)
         if 0 <= mode < 4:

@@ -64,7 +64,7 @@ typedef struct {
     /* vbr: 0 = vbr_off (CBR), 3 = vbr_abr, 4 = vbr_mtrh with quality vbr_q (lame.h:94 vbr_mode); ABR keeps its mean bitrate, the bitrate index range
      * it may choose a frame size from, and the compression ratio calc_target_bits reads (quantize.c:1768) */
     int   vbr, vbr_q, vbr_mean_kbps, vbr_min_bitrate_index, vbr_max_bitrate_index;
-    float compression_ratio;
+    float compression_ratio, vbr_q_frac;
     /* input-rate conversion (util.c:531 fill_buffer_resample): samplerate is the OUTPUT rate */
     int   samplerate_in, resample, rs_filter_l, rs_bpc;
     double rs_ratio;
@@ -140,12 +140,14 @@ typedef struct {
 lp_encoder *lp_open(int samplerate, int channels, int brate, int mode, int quality);
 lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr /* 0 off, 3 abr, 4 mtrh: brate = VBR_q */);
 lp_encoder *lp_open_rs(int samplerate_in, int samplerate_out /* 0 = as lame_init_params picks it */, int channels, int brate, int mode, int quality, int vbr);
+/* vbr 4 with a fractional level: VBR quality = brate + vbr_q_frac (lame_set_VBR_quality, set_get.c:1152) */
+lp_encoder *lp_open_vq(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac);
 int  lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsigned char *out, int cap);
 int  lp_flush(lp_encoder *e, unsigned char *out, int cap);
 void lp_close(lp_encoder *e);
 
 /* internals shared between the port's files */
-int   lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr);
+int   lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac);
 float lp_fast_log2(const lp_config *c, float x);
 void  lp_fft_long(const lp_config *c, float x[LP_BLK], const float *buf);
 void  lp_fft_short(const lp_config *c, float x[3][LP_BLK_S], const float *buf);

@@ -19,10 +19,15 @@ lp_encoder *lp_open_ex(int samplerate, int channels, int brate, int mode, int qu
 
 lp_encoder *lp_open_rs(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr)
 {
+    return lp_open_vq(samplerate_in, samplerate_out, channels, brate, mode, quality, vbr, 0.f);
+}
+
+lp_encoder *lp_open_vq(int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac)
+{
     lp_encoder *e = calloc(1, sizeof *e);
     int i, j, sb;
     if (!e) return NULL;
-    if (lp_setup(&e->cfg, samplerate_in, samplerate_out, channels, brate, mode, quality, vbr) < 0) { free(e); return NULL; }
+    if (lp_setup(&e->cfg, samplerate_in, samplerate_out, channels, brate, mode, quality, vbr, vbr_q_frac) < 0) { free(e); return NULL; }
     e->bitrate_index = e->cfg.bitrate_index;
     e->buf = calloc(1, LP_BITBUF);
     /* lame.c:2274 lame_init_internal_flags, lame.c:962, psymodel.c:1897-1922/2075 */

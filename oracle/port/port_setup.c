@@ -605,7 +605,7 @@ static int setup_resampler(lp_config *c)
     return 0;
 }
 
-int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr)
+int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac)
 {
     /* presets.c:241 abr_switch_map, the columns the CBR path reads */
     static const struct { int kbps, safejoint; float nsmsfix, st_lrm, st_s, scale, masking_adj, ath_lower, ath_curve, interch; int sfscale; }
@@ -632,6 +632,7 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} };
     static const int vbr_lowpass[11] = { 24000, 19500, 18500, 18000, 17500, 17000, 16500, 15600, 15200, 7230, 3950 };
     int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, vbr_q = 0;
+    int vbr_no_lowpass = 0;
     int samplerate = samplerate_out;                                   /* 0 = chosen below the way lame_init_params does */
     float athaa_sensitivity = 0;
     float scale = 1, maskingadjust, maskingadjust_short, ath_lower_db, attackthre, attackthre_s;
@@ -649,8 +650,34 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         /* `brate` carries VBR_q.  Levels 7..9 make lame_init_params pick a lower output rate at these input rates
          * (lame.c:661-698), which needs the resampler */
         vbr_q = brate;
-        if (vbr_q < 0 || vbr_q > 6) return -1;
-        if (samplerate == 0 && samplerate_in == 32000) return -1;      /* lame.c:679-686 rescales VBR_q to a fractional level at 32 kHz */
+        if (vbr_q < 0 || vbr_q > 9 || !(vbr_q_frac >= 0.f && vbr_q_frac < 1.f)) return -1;
+        if (samplerate == 0) {
+            /* lame.c:661-698: the -V scale is mapped to the internal quality scale of the output rate it implies; e.g. -V7 at
+             * 44.1 kHz becomes quality 5.63 at 32 kHz, and at 32 kHz input the levels below 6.5 shrink to 0..5.2 */
+            static const struct { int sr_a; float qa, qb, ta, tb; } qm[9] = {
+                {48000, 0.0, 6.5, 0.0, 6.5}, {44100, 0.0, 6.5, 0.0, 6.5}, {32000, 6.5, 8.0, 5.2, 6.5}, {24000, 8.0, 8.5, 5.2, 6.0},
+                {22050, 8.5, 9.01, 5.2, 6.5}, {16000, 9.01, 9.4, 4.9, 6.5}, {12000, 9.4, 9.6, 4.5, 6.0}, {11025, 9.6, 9.9, 5.1, 6.5},
+                {8000, 9.9, 10., 4.9, 6.5} };
+            float const qval = vbr_q + vbr_q_frac;
+            for (i = 2; i < 9; ++i) {
+                if (samplerate_in == qm[i].sr_a && qval < qm[i].qa) {
+                    double d = qval / qm[i].qa;
+                    d = d * qm[i].ta;
+                    vbr_q = (int) d;
+                    vbr_q_frac = d - vbr_q;
+                }
+                if (samplerate_in >= qm[i].sr_a && qm[i].qa <= qval && qval < qm[i].qb) {
+                    float const q_ = qm[i].qb - qm[i].qa;
+                    float const t_ = qm[i].tb - qm[i].ta;
+                    double d = qm[i].ta + t_ * (qval - qm[i].qa) / q_;
+                    vbr_q = (int) d;
+                    vbr_q_frac = d - vbr_q;
+                    samplerate = qm[i].sr_a;
+                    vbr_no_lowpass = 1;                                /* gfp->lowpassfreq = -1 */
+                    break;
+                }
+            }
+        }
         brate = 128;                                                   /* gfp->brate stays unused; keeps the arithmetic below defined */
     }
     if (vbr == 4) { }
@@ -674,7 +701,11 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     }
     /* lame.c:704-762: low-pass from the bitrate */
     lowpass = lowpass_map[nearest_full_index(brate)];
-    if (vbr == 4) lowpass = vbr_lowpass[vbr_q];                        /* lame.c:730-741, VBR_q_frac = 0 */
+    if (vbr == 4) {                                                    /* lame.c:730-741 */
+        double const a = vbr_lowpass[vbr_q], b = vbr_lowpass[vbr_q + 1], m = vbr_q_frac;
+        lowpass = a + m * (b - a);
+        if (vbr_no_lowpass) lowpass = -1;
+    }
     else if (mode == LP_MONO) lowpass *= 1.5;
     c->lowpassfreq = lowpass;
     if (samplerate == 0) {                                             /* lame.c:764-769 */
@@ -711,6 +742,7 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     c->vbr_max_bitrate_index = 14;
     c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * brate);   /* lame.c:778-784 */
     c->vbr_q = vbr_q;
+    c->vbr_q_frac = (vbr == 4) ? vbr_q_frac : 0.f;
     if (vbr != 0) c->bitrate_index = 1;                                /* lame.c:921 */
     else {
         c->bitrate_index = -1;
@@ -732,19 +764,29 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         c->noise_shaping = 0;
         c->quant_comp = 9;
         c->quant_comp_short = 9;
-        attackthre = vm[vbr_q].st_lrm;
-        attackthre_s = vm[vbr_q].st_s;
-        maskingadjust = vm[vbr_q].madj + 0.0f;                          /* LERP with VBR_q_frac = 0 turns the table's -0.0 into +0.0 */
-        maskingadjust_short = vm[vbr_q].madj_s + 0.0f;
-        ath_lower_db = vm[vbr_q].ath_lower;
-        c->athcurve = vm[vbr_q].ath_curve;
-        athaa_sensitivity = vm[vbr_q].ath_sens;
-        c->interch = vm[vbr_q].interch > 0 ? vm[vbr_q].interch : 0;
-        if (vm[vbr_q].safejoint > 0) exp_nspsytune |= 2;
-        if (vm[vbr_q].sfb21mod > 0) exp_nspsytune |= vm[vbr_q].sfb21mod << 20;
-        c->msfix = vm[vbr_q].msfix;
-        c->minval = vm[vbr_q].minval;
-        c->athfixpoint = vm[vbr_q].ath_fixpoint;
+        {   /* presets.c:143-161: every float column moves towards the next level by VBR_q_frac, sfb21mod does so as an int */
+            float const x = vbr_q_frac;
+            int const n = vbr_q + 1;
+            int sfb21mod = vm[vbr_q].sfb21mod;
+            if (vbr_q > 8) return -1;                                   /* the table row of level 10 is not carried here */
+#define VLERP(f) (vm[vbr_q].f + x * (vm[n].f - vm[vbr_q].f))
+            attackthre = VLERP(st_lrm);
+            attackthre_s = VLERP(st_s);
+            maskingadjust = VLERP(madj);
+            maskingadjust_short = VLERP(madj_s);
+            ath_lower_db = VLERP(ath_lower);
+            c->athcurve = VLERP(ath_curve);
+            athaa_sensitivity = VLERP(ath_sens);
+            c->interch = VLERP(interch);
+            if (!(c->interch > 0)) c->interch = 0;
+            sfb21mod = sfb21mod + x * (vm[n].sfb21mod - sfb21mod);
+            c->msfix = VLERP(msfix);
+            c->minval = VLERP(minval);
+            c->athfixpoint = VLERP(ath_fixpoint);
+#undef VLERP
+            if (vm[vbr_q].safejoint > 0) exp_nspsytune |= 2;
+            if (sfb21mod > 0) exp_nspsytune |= sfb21mod << 20;
+        }
         if (quality < 0) quality = 3;
         if (quality < 5) quality = 0;
         if (quality > 7) quality = 7;
@@ -806,7 +848,7 @@ presets_done:
     }
     c->frac_spf = (vbr == 0) ? ((version + 1) * 72000L * brate) % samplerate : 0;      /* lame.c:1245 */
     setup_quantizer_tables(c);
-    setup_psy(c, attackthre, attackthre_s, vbr == 4 ? vbr_q : 4, 0.f);
+    setup_psy(c, attackthre, attackthre_s, vbr == 4 ? vbr_q : 4, vbr == 4 ? vbr_q_frac : 0.f);
     c->buffer_constraint = 7680 * (version + 1);                       /* bitstream.c:119 MDB_MAXIMUM */
     return 0;
 }

@@ -28,6 +28,11 @@ void *refdump_open(int brate, int mode, int quality, int vbrmode, int vbr_q, int
 
 void *refdump_open_rs(int brate, int mode, int quality, int vbrmode, int vbr_q, int samplerate, int out_samplerate, int nch)
 {
+    return refdump_open_vq(brate, mode, quality, vbrmode, vbr_q, 0.f, samplerate, out_samplerate, nch);
+}
+
+void *refdump_open_vq(int brate, int mode, int quality, int vbrmode, int vbr_q, float vbr_q_frac, int samplerate, int out_samplerate, int nch)
+{
     struct refdump_handle *h = calloc(1, sizeof *h);
     lame_global_flags *gfp = lame_init();
     h->gfp = gfp;
@@ -35,7 +40,7 @@ void *refdump_open_rs(int brate, int mode, int quality, int vbrmode, int vbr_q, 
     lame_set_num_channels(gfp, nch > 0 ? nch : 2);
     if (out_samplerate > 0) lame_set_out_samplerate(gfp, out_samplerate);
     if (vbrmode == vbr_abr) { lame_set_VBR(gfp, vbr_abr); if (brate > 0) lame_set_VBR_mean_bitrate_kbps(gfp, brate); }
-    else if (vbrmode > 0) { lame_set_VBR(gfp, (vbr_mode) vbrmode); lame_set_VBR_q(gfp, vbr_q); }
+    else if (vbrmode > 0) { lame_set_VBR(gfp, (vbr_mode) vbrmode); if (vbr_q_frac > 0) lame_set_VBR_quality(gfp, vbr_q + vbr_q_frac); else lame_set_VBR_q(gfp, vbr_q); }
     else if (brate > 0) lame_set_brate(gfp, brate);
     if (mode >= 0) lame_set_mode(gfp, (MPEG_mode) mode);
     if (quality >= 0) lame_set_quality(gfp, quality);

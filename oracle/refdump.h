@@ -65,6 +65,7 @@ typedef struct {
 } refdump_tab;
 
 void *refdump_open(int brate, int mode, int quality, int vbrmode, int vbr_q, int samplerate, int nch);
+void *refdump_open_vq(int brate, int mode, int quality, int vbrmode, int vbr_q, float vbr_q_frac, int samplerate, int out_samplerate, int nch);
 void *refdump_open_rs(int brate, int mode, int quality, int vbrmode, int vbr_q, int samplerate, int out_samplerate /* 0 = automatic */, int nch);
 int   refdump_encode(void *h, const short *l, const short *r, int n, unsigned char *out, int cap);
 int   refdump_flush(void *h, unsigned char *out, int cap);

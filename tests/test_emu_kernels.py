@@ -48,6 +48,8 @@ def test_emulated_kernels_vbr_match_port(emu_bin, args):
     ("3 10 4 128 -1 -1 48000 777", dict(LP_OUT_SR="44100")), ("2 8 8 192 -1 -1 44100 3000", dict(LP_OUT_SR="48000")),
     ("2 8 3 96 -1 -1 44100 100", {}), ("2 4 4 128 -1 -1 8000 50", dict(LP_OUT_SR="44100")), ("2 16 4 128 -1 -1 96000 1152", {}),
     ("2 8 4 2 -1 -1 44100 1152", dict(LP_VBR="4", LP_OUT_SR="32000")), ("2 4 4 128 -1 -1 48000 7", dict(LP_OUT_SR="44100")),
+    # -V7 at 44.1 kHz (32 kHz output, quality 5.63) and a level between the presets
+    ("3 8 4 7 -1 -1 44100 1152", dict(LP_VBR="4")), ("3 8 4 5 -1 -1 48000 1152", dict(LP_VBR="4", LP_VBRQ_FRAC="0.3")),
 ])
 def test_emulated_resampler_matches_port(emu_bin, args, env):
     """kernel R (lg_kernel_resample) + the host's replay of the reference's per-call resampler bookkeeping (chunks, input

@@ -103,6 +103,8 @@ def test_abr_batch_matches_oracle(lib, oracle_mod, cfg):
 @pytest.mark.parametrize("cfg", [
     dict(S=16, F=24, fpl=8, q=2), dict(S=8, F=30, fpl=16, q=0), dict(S=4, F=20, fpl=3, q=4, mode=0, quality=5),
     dict(S=4, F=16, fpl=8, q=0, sr=48000), dict(S=3, F=16, fpl=8, q=5, mode=3), dict(S=4, F=20, fpl=20, q=6, quality=6),
+    # levels between the presets (lame_set_VBR_quality), -V7 (32 kHz output through the resampler), VBR at 32 kHz input
+    dict(S=4, F=20, fpl=8, q=2.5), dict(S=4, F=16, fpl=8, q=5.3, sr=48000), dict(S=4, F=20, fpl=8, q=7), dict(S=4, F=16, fpl=4, q=3, sr=32000),
 ])
 def test_vbr_batch_matches_oracle(lib, oracle_mod, cfg):
     """VBR-new (vbr_mtrh, -V q): lg_kernel_vbr - per-band step search, fitting, and for the frames that do not
@@ -159,14 +161,16 @@ def test_resampled_batch_matches_oracle(lib, oracle_mod, cfg):
             assert got[s] == want, "stream %d (%s) vs %s" % (s, kinds[s % 4], type(e).__name__)
 
 
-def test_resampled_lame_api_with_tag(lib, oracle_mod):
-    """the lame.h face with lame_set_out_samplerate, float input and the Info tag: source-rate field and encoder padding of the
-    tag come from the resampling path (VbrTag.c:775, lame.c:2083-2091)"""
+@pytest.mark.parametrize("kw", [dict(samplerate=48000, brate=128, out_samplerate=44100), dict(samplerate=44100, brate=7, vbr=4),
+                                dict(samplerate=44100, brate=4.6, vbr=4), dict(samplerate=44100, brate=96, quality=1)])
+def test_resampled_lame_api_with_tag(lib, oracle_mod, kw):
+    """the lame.h face with lame_set_out_samplerate / -V7 / a fractional level / quality 1, and the Info tag: source-rate field,
+    encoder padding, quality and preset fields of the tag (VbrTag.c:775, lame.c:2083-2091)"""
     if not oracle_mod.have_ref():
         pytest.skip("needs the reference build")
     x = make_signal("click", 30 * 1152, seed=5)
-    e = lib.Encoder(48000, 2, 128, write_tag=True, out_samplerate=44100)
-    r = oracle_mod.RefEncoder(48000, 2, 128, write_tag=True, out_samplerate=44100)
+    e = lib.Encoder(channels=2, write_tag=True, **kw)
+    r = oracle_mod.RefEncoder(channels=2, write_tag=True, **kw)
     a = b_ = b""
     for pos in range(0, x.shape[1], 5000):
         a += e.encode(x[0, pos:pos + 5000], x[1, pos:pos + 5000])
@@ -297,7 +301,7 @@ def test_edge_cases(lib, oracle_mod):
 
 
 def test_unsupported_configurations_fail_loudly(lib):
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(out_samplerate=24000), dict(brate=7, vbr=4)):
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(out_samplerate=24000), dict(brate=8, vbr=4)):
         with pytest.raises(lib.LameGpuError):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()

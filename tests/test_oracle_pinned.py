@@ -41,8 +41,8 @@ def test_port_chunking_invariance(oracle_mod):
 
 
 def test_port_rejects_unsupported(oracle_mod):
-    # MPEG-2 output rates (22.05 kHz input; 64 kbps makes lame_init_params pick 24 kHz), VBR -V7 (fractional VBR_q at 32 kHz)
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(brate=7, vbr=4), dict(out_samplerate=22050)):
+    # MPEG-2 output rates: 22.05 kHz input, 64 kbps (lame_init_params picks 24 kHz), VBR -V8 (24 kHz), explicit 22.05 kHz
+    for kw in (dict(samplerate=22050), dict(brate=64), dict(brate=8, vbr=4), dict(out_samplerate=22050)):
         with pytest.raises(ValueError):
             oracle_mod.PortEncoder(**kw)
 
@@ -121,6 +121,21 @@ def test_port_quality_0_to_2_vs_reference(port_vs_ref_bin, args, env):
     """quality 2 / 1 / 0 (the 4th argument): substep shaping with the per-band half-step flags (quantize.c:131,781, takehiro.c:781),
     one-band-at-a-time amplification (noise_shaping_amp 2) and the full outer loop; CBR and ABR, byte-identical to libmp3lame"""
     r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
+@pytest.mark.parametrize("args,env", [
+    ("click 7 -1 -1 60 44100", {}), ("noise 2 -1 -1 40 32000", {}), ("click 5 -1 -1 60 32000", {}), ("click 2 -1 -1 60 44100", dict(LP_VBRQ_FRAC="0.5")),
+    ("sine 5 -1 -1 60 48000", dict(LP_VBRQ_FRAC="0.3")), ("click 6 -1 -1 60 44100", dict(LP_VBRQ_FRAC="0.9")), ("gap 0 -1 -1 60 44100", dict(LP_VBRQ_FRAC="0.77")),
+    ("click 3 0 -1 60 32000", dict(LP_VBRQ_FRAC="0.4")), ("click 7 -1 -1 60 96000", dict(LP_VBRQ_FRAC="0.999")),
+    ("click 6 -1 -1 40 44100", dict(LP_VBRQ_FRAC="0.25", LP_OUT_SR="44100")),
+])
+def test_port_fractional_vbr_quality_vs_reference(port_vs_ref_bin, args, env):
+    """VBR levels between the presets (lame_set_VBR_quality = 2nd argument + LP_VBRQ_FRAC; presets.c:143 interpolation) and the
+    mapping of the -V scale to the output rate it implies (lame.c:661-698): -V7 at 44.1 kHz = quality 5.63 at 32 kHz through the
+    resampler, levels at 32 kHz input shrunk to 0..5.2"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="4", **env))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
