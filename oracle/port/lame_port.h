@@ -93,6 +93,8 @@ typedef struct {
           mixed_block_flag, table_select[3], subblock_gain[4], region0_count, region1_count, preflag,
           scalefac_scale, count1table_select, part2_length, sfb_lmax, sfb_smin, psy_lmax, sfbmax,
           psymax, sfbdivide, width[LP_SFBMAX], window[LP_SFBMAX], count1bits, max_nonzero_coeff;
+    int   slen[4];                      /* MPEG-2/2.5 (LSF) scalefactor coding: bits per partition and the partition sizes (takehiro.c:1218) */
+    const int *sfb_partition_table;
     char  energy_above_cutoff[LP_SFBMAX];
 } lp_granule;
 

@@ -225,7 +225,8 @@ int lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsig
 {
     const lp_config *cfg = &e->cfg;
     int mp3size = 0, ret, i, ch;
-    int const mf_needed = 1024 + 1152 - (224 + 48);        /* lame.c:1627 calcNeeded: max(1904, 1632) */
+    int const fs = 576 * cfg->mode_gr;                     /* samples per frame: 1152 (MPEG-1) or 576 (MPEG-2/2.5) */
+    int const mf_needed = 1024 + fs - (224 + 48);          /* lame.c:1627 calcNeeded: max(BLKSIZE + fs - FFTOFFSET, 512 + fs - 32) */
     float m[2][2];
     float *in[2] = { NULL, NULL };
     const float *inp[2];
@@ -244,10 +245,10 @@ int lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsig
         int n_in = 0, n_out = 0;
         if (cfg->resample) {
             for (ch = 0; ch < cfg->channels; ch++)
-                n_out = resample_chunk(e, &e->mfbuf[ch][e->mf_size], 1152, inp[ch], nsamples, &n_in, ch);
+                n_out = resample_chunk(e, &e->mfbuf[ch][e->mf_size], fs, inp[ch], nsamples, &n_in, ch);
         }
         else {
-            n_in = n_out = nsamples < 1152 ? nsamples : 1152;
+            n_in = n_out = nsamples < fs ? nsamples : fs;
             for (ch = 0; ch < cfg->channels; ch++) memcpy(&e->mfbuf[ch][e->mf_size], inp[ch], n_out * sizeof(float));
         }
         nsamples -= n_in; inp[0] += n_in; inp[1] += n_in;
@@ -261,10 +262,10 @@ int lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsig
             if (ret < 0) { mp3size = ret; break; }
             out += ret;
             mp3size += ret;
-            e->mf_size -= 1152;
-            e->mf_samples_to_encode -= 1152;
+            e->mf_size -= fs;
+            e->mf_samples_to_encode -= fs;
             for (ch = 0; ch < cfg->channels; ch++)
-                for (i = 0; i < e->mf_size; i++) e->mfbuf[ch][i] = e->mfbuf[ch][i + 1152];
+                for (i = 0; i < e->mf_size; i++) e->mfbuf[ch][i] = e->mfbuf[ch][i + fs];
         }
     }
     free(in[0]); free(in[1]);
@@ -276,14 +277,15 @@ int lp_flush(lp_encoder *e, unsigned char *out, int cap)
 {
     short buffer[2][1152];
     int imp3 = 0, mp3count = 0, remaining, end_padding, frames_left, samples_to_encode;
-    int const mf_needed = 1904;
+    int const fs = 576 * e->cfg.mode_gr;
+    int const mf_needed = 1024 + fs - (224 + 48);
     if (e->mf_samples_to_encode < 1) return 0;
     samples_to_encode = e->mf_samples_to_encode - 1152;
     if (e->cfg.resample) samples_to_encode += 16. / e->cfg.rs_ratio;       /* lame.c:2083-2087 the resampler's delay */
     memset(buffer, 0, sizeof buffer);
-    end_padding = 1152 - (samples_to_encode % 1152);
-    if (end_padding < 576) end_padding += 1152;
-    frames_left = (samples_to_encode + end_padding) / 1152;
+    end_padding = fs - (samples_to_encode % fs);
+    if (end_padding < 576) end_padding += fs;
+    frames_left = (samples_to_encode + end_padding) / fs;
     while (frames_left > 0 && imp3 >= 0) {
         int const frame_num = e->frame_number;
         int bunch = mf_needed - e->mf_size;

@@ -66,14 +66,15 @@ static void writeheader(lp_encoder *e, int val, int j)
     }
     e->header[e->h_ptr].ptr = ptr;
 }
-/* bitstream.c:321 encodeSideInfo2 (MPEG-1 branch) */
+/* bitstream.c:321 encodeSideInfo2 */
 static void encode_side_info(lp_encoder *e, int bitsPerFrame)
 {
     const lp_config *cfg = &e->cfg;
     int gr, ch, band, old;
     e->header[e->h_ptr].ptr = 0;
     memset(e->header[e->h_ptr].buf, 0, cfg->sideinfo_len);
-    writeheader(e, 0xfff, 12);
+    if (cfg->samplerate < 16000) writeheader(e, 0xffe, 12);           /* MPEG-2.5 */
+    else writeheader(e, 0xfff, 12);
     writeheader(e, cfg->version, 1);
     writeheader(e, 4 - 3, 2);
     writeheader(e, !cfg->error_protection, 1);
@@ -86,6 +87,45 @@ static void encode_side_info(lp_encoder *e, int bitsPerFrame)
     writeheader(e, cfg->copyright, 1);
     writeheader(e, cfg->original, 1);
     writeheader(e, cfg->emphasis, 2);
+    if (cfg->version != 1) {
+        /* MPEG-2/2.5: one granule, 8-bit main_data_begin, 9-bit scalefac_compress, no scfsi, no preflag bit */
+        writeheader(e, e->main_data_begin, 8);
+        writeheader(e, 0, cfg->channels);
+        for (ch = 0; ch < cfg->channels; ch++) {
+            lp_granule *gi = &e->tt[0][ch];
+            writeheader(e, gi->part2_3_length + gi->part2_length, 12);
+            writeheader(e, gi->big_values / 2, 9);
+            writeheader(e, gi->global_gain, 8);
+            writeheader(e, gi->scalefac_compress, 9);
+            if (gi->table_select[0] == 14) gi->table_select[0] = 16;
+            if (gi->table_select[1] == 14) gi->table_select[1] = 16;
+            if (gi->block_type != LP_NORM) {
+                writeheader(e, 1, 1);
+                writeheader(e, gi->block_type, 2);
+                writeheader(e, gi->mixed_block_flag, 1);
+                writeheader(e, gi->table_select[0], 5);
+                writeheader(e, gi->table_select[1], 5);
+                writeheader(e, gi->subblock_gain[0], 3);
+                writeheader(e, gi->subblock_gain[1], 3);
+                writeheader(e, gi->subblock_gain[2], 3);
+            }
+            else {
+                writeheader(e, 0, 1);
+                writeheader(e, gi->table_select[0], 5);
+                writeheader(e, gi->table_select[1], 5);
+                if (gi->table_select[2] == 14) gi->table_select[2] = 16;
+                writeheader(e, gi->table_select[2], 5);
+                writeheader(e, gi->region0_count, 4);
+                writeheader(e, gi->region1_count, 3);
+            }
+            writeheader(e, gi->scalefac_scale, 1);
+            writeheader(e, gi->count1table_select, 1);
+        }
+        old = e->h_ptr;
+        e->h_ptr = (old + 1) & (LP_MAX_HEADER_BUF - 1);
+        e->header[e->h_ptr].write_timing = e->header[old].write_timing + bitsPerFrame;
+        return;
+    }
     writeheader(e, e->main_data_begin, 9);
     writeheader(e, 0, cfg->channels == 2 ? 3 : 5);
     for (ch = 0; ch < cfg->channels; ch++)
@@ -198,16 +238,31 @@ static int huffman_count1(lp_encoder *e, const lp_granule *gi)
     }
     return bits;
 }
-/* bitstream.c:686 writeMainData (MPEG-1 branch) with Short/LongHuffmancodebits (:633/:650) */
+/* bitstream.c:686 writeMainData with Short/LongHuffmancodebits (:633/:650) */
 static int write_main_data(lp_encoder *e)
 {
     const lp_config *cfg = &e->cfg;
     int gr, ch, sfb, data_bits, tot_bits = 0;
-    for (gr = 0; gr < 2; gr++)
+    for (gr = 0; gr < cfg->mode_gr; gr++)
         for (ch = 0; ch < cfg->channels; ch++) {
             const lp_granule *gi = &e->tt[gr][ch];
-            int const slen1 = slen1_tab[gi->scalefac_compress], slen2 = slen2_tab[gi->scalefac_compress];
             data_bits = 0;
+            if (cfg->version != 1) {
+                /* MPEG-2/2.5: every band of a partition with the partition's width, bands past the last partition not at all */
+                int part, i, w, nwin = (gi->block_type == LP_SHORT) ? 3 : 1;
+                sfb = 0;
+                for (part = 0; part < 4; part++) {
+                    int const sfbs = gi->sfb_partition_table[part] / nwin, slen = gi->slen[part];
+                    for (i = 0; i < sfbs; i++, sfb++)
+                        for (w = 0; w < nwin; w++) {
+                            int const v = gi->scalefac[sfb * nwin + w];
+                            putbits(e, v > 0 ? v : 0, slen);
+                            data_bits += slen;
+                        }
+                }
+            }
+            else {
+            int const slen1 = slen1_tab[gi->scalefac_compress], slen2 = slen2_tab[gi->scalefac_compress];
             for (sfb = 0; sfb < gi->sfbdivide; sfb++) {
                 if (gi->scalefac[sfb] == -1) continue;
                 putbits(e, gi->scalefac[sfb], slen1);
@@ -217,6 +272,7 @@ static int write_main_data(lp_encoder *e)
                 if (gi->scalefac[sfb] == -1) continue;
                 putbits(e, gi->scalefac[sfb], slen2);
                 data_bits += slen2;
+            }
             }
             if (gi->block_type == LP_SHORT) {
                 int region1Start = 3 * cfg->sfb_s[3];

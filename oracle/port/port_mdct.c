@@ -256,5 +256,6 @@ void lp_mdct_sub48(lp_encoder *e, const float *w0, const float *w1)
             }
         }
         wk = w1 + 286;
+        if (cfg->mode_gr == 1) memcpy(e->sb_sample[ch][0], e->sb_sample[ch][1], 576 * sizeof(float));    /* newmdct.c:1037 */
     }
 }

@@ -207,8 +207,8 @@ static int calc_xmin(lp_encoder *e, const lp_ratio *ratio, lp_granule *gi, float
     else { max_nonzero /= 6; max_nonzero *= 6; max_nonzero += 5; }
     if (cfg->sfb21_extra == 0 && cfg->samplerate < 44000) {
         int limit;
-        if (gi->block_type != LP_SHORT) limit = cfg->sfb_l[21] - 1;
-        else limit = 3 * cfg->sfb_s[12] - 1;
+        if (gi->block_type != LP_SHORT) limit = cfg->sfb_l[cfg->samplerate <= 8000 ? 17 : 21] - 1;
+        else limit = 3 * cfg->sfb_s[cfg->samplerate <= 8000 ? 9 : 12] - 1;
         if (max_nonzero > limit) max_nonzero = limit;
     }
     gi->max_nonzero_coeff = max_nonzero;
@@ -641,9 +641,10 @@ static void best_huffman_divide(const lp_config *c, lp_granule *gi)
 {
     const uint8_t *t32l = hlen_of(32), *t33l = hlen_of(33);
     int i, a1, a2;
-    static lp_granule gi2;
+    static __thread lp_granule gi2;
     const int *ix = gi->l3_enc;
     int r01_bits[7 + 15 + 1], r01_div[7 + 15 + 1], r0_tbl[7 + 15 + 1], r1_tbl[7 + 15 + 1];
+    if (gi->block_type == LP_SHORT && c->mode_gr == 1) return;        /* takehiro.c:899: not for short blocks of MPEG-2 */
     memcpy(&gi2, gi, sizeof(lp_granule));
     if (gi->block_type == LP_NORM) {
         recalc_divide_init(c, gi, ix, r01_bits, r01_div, r0_tbl, r1_tbl);
@@ -681,7 +682,41 @@ static const int slen1_n[16] = { 1, 1, 1, 1, 8, 2, 2, 2, 4, 4, 4, 8, 8, 8, 16, 1
 static const int slen2_n[16] = { 1, 2, 4, 8, 1, 2, 4, 8, 2, 4, 8, 2, 4, 8, 4, 8 };
 static const int slen1_tab[16] = { 0, 0, 0, 0, 3, 1, 1, 1, 2, 2, 2, 3, 3, 3, 4, 4 };
 static const int slen2_tab[16] = { 0, 1, 2, 3, 0, 1, 2, 3, 1, 2, 3, 1, 2, 3, 2, 3 };
-static int scale_bitcount(lp_granule *gi)
+/* takehiro.c:1218 mpeg2_scale_bitcount: MPEG-2/2.5 code the scalefactors in four partitions whose sizes come from
+ * nr_of_sfb_block (tables.c) and whose widths slen[] are the bit lengths of the partitions' maxima.  When a maximum is out
+ * of range nothing is written (part2_length keeps its value) and 1 comes back. */
+static const int nr_of_sfb_block[6][3][4] = {
+    { {6, 5, 5, 5}, {9, 9, 9, 9}, {6, 9, 9, 9} }, { {6, 5, 7, 3}, {9, 9, 12, 6}, {6, 9, 12, 6} }, { {11, 10, 0, 0}, {18, 18, 0, 0}, {15, 18, 0, 0} },
+    { {7, 7, 7, 0}, {12, 12, 12, 0}, {6, 15, 12, 0} }, { {6, 6, 6, 3}, {12, 9, 9, 6}, {6, 12, 9, 6} }, { {8, 8, 5, 0}, {15, 12, 9, 0}, {6, 18, 9, 0} } };
+static int scale_bitcount_lsf(lp_granule *gi)
+{
+    static const int max_range[6][4] = { {15, 15, 7, 7}, {15, 15, 7, 0}, {7, 3, 0, 0}, {15, 31, 31, 0}, {7, 7, 7, 0}, {3, 3, 0, 0} };
+    static const int log2tab[16] = { 0, 1, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4 };
+    int const table_number = gi->preflag ? 2 : 0, row = (gi->block_type == LP_SHORT) ? 1 : 0;
+    const int *ptab = nr_of_sfb_block[table_number][row];
+    const int *scalefac = gi->scalefac;
+    int max_sfac[4] = { 0, 0, 0, 0 }, partition, sfb = 0, i, window, over = 0;
+    for (partition = 0; partition < 4; partition++) {
+        if (row) {
+            for (i = 0; i < ptab[partition] / 3; i++, sfb++)
+                for (window = 0; window < 3; window++)
+                    if (scalefac[sfb * 3 + window] > max_sfac[partition]) max_sfac[partition] = scalefac[sfb * 3 + window];
+        }
+        else for (i = 0; i < ptab[partition]; i++, sfb++) if (scalefac[sfb] > max_sfac[partition]) max_sfac[partition] = scalefac[sfb];
+    }
+    for (partition = 0; partition < 4; partition++) if (max_sfac[partition] > max_range[table_number][partition]) over++;
+    if (!over) {
+        gi->sfb_partition_table = ptab;
+        for (partition = 0; partition < 4; partition++) gi->slen[partition] = log2tab[max_sfac[partition]];
+        if (table_number == 0) gi->scalefac_compress = (((gi->slen[0] * 5) + gi->slen[1]) << 4) + (gi->slen[2] << 2) + gi->slen[3];
+        else gi->scalefac_compress = 500 + (gi->slen[0] * 3) + gi->slen[1];
+        gi->part2_length = 0;
+        for (partition = 0; partition < 4; partition++) gi->part2_length += gi->slen[partition] * ptab[partition];
+    }
+    return over;
+}
+
+static int scale_bitcount(const lp_config *c, lp_granule *gi)
 {
     static const int scale_short[16] = { 0, 18, 36, 54, 54, 36, 54, 72, 54, 72, 90, 72, 90, 108, 108, 126 };
     static const int scale_mixed[16] = { 0, 18, 36, 54, 51, 35, 53, 71, 52, 70, 88, 69, 87, 105, 104, 122 };
@@ -689,6 +724,7 @@ static int scale_bitcount(lp_granule *gi)
     int k, sfb, max_slen1 = 0, max_slen2 = 0;
     const int *tab;
     int *scalefac = gi->scalefac;
+    if (c->mode_gr == 1) return scale_bitcount_lsf(gi);               /* takehiro.c:1318 */
     if (gi->block_type == LP_SHORT) {
         tab = scale_short;
         if (gi->mixed_block_flag) tab = scale_mixed;
@@ -781,7 +817,7 @@ static void best_scalefac_store(lp_encoder *e, int gr, int ch)
         recalc = 0;
     }
     for (sfb = 0; sfb < gi->sfbmax; sfb++) if (gi->scalefac[sfb] == -2) gi->scalefac[sfb] = 0;
-    if (recalc) (void) scale_bitcount(gi);
+    if (recalc) (void) scale_bitcount(&e->cfg, gi);
 }
 
 /* ------------------------------------------------------------------ noise shaping loop (quantize.c) */
@@ -794,8 +830,11 @@ static void init_outer_loop(const lp_config *c, lp_granule *gi)
     gi->subblock_gain[0] = gi->subblock_gain[1] = gi->subblock_gain[2] = gi->subblock_gain[3] = 0;
     gi->region0_count = 0; gi->region1_count = 0; gi->preflag = 0; gi->scalefac_scale = 0;
     gi->count1table_select = 0; gi->part2_length = 0;
+    gi->sfb_partition_table = nr_of_sfb_block[0][0];                  /* quantize.c:331-335 */
+    gi->slen[0] = gi->slen[1] = gi->slen[2] = gi->slen[3] = 0;
     gi->sfb_lmax = LP_SBPSY_L; gi->sfb_smin = LP_SBPSY_S;
     gi->psy_lmax = c->sfb21_extra ? LP_SBMAX_L : LP_SBPSY_L;
+    if (c->samplerate <= 8000) { gi->sfb_lmax = 17; gi->sfb_smin = 9; gi->psy_lmax = 17; }       /* quantize.c:252-256 */
     gi->psymax = gi->psy_lmax;
     gi->sfbmax = gi->sfb_lmax;
     gi->sfbdivide = 11;
@@ -811,6 +850,7 @@ static void init_outer_loop(const lp_config *c, lp_granule *gi)
         if (gi->mixed_block_flag) { gi->sfb_smin = 3; gi->sfb_lmax = c->mode_gr * 2 + 4; }
         gi->psymax = gi->sfb_lmax + 3 * ((c->sfb21_extra ? LP_SBMAX_S : LP_SBPSY_S) - gi->sfb_smin);
         gi->sfbmax = gi->sfb_lmax + 3 * (LP_SBPSY_S - gi->sfb_smin);
+        if (c->samplerate <= 8000) gi->psymax = gi->sfbmax = gi->sfb_lmax + 3 * (9 - gi->sfb_smin);     /* quantize.c:284-289 */
         gi->sfbdivide = gi->sfbmax - 18;
         gi->psy_lmax = gi->sfb_lmax;
         ix = &gi->xr[c->sfb_l[gi->sfb_lmax]];
@@ -1034,7 +1074,7 @@ static int balance_noise(const lp_config *c, lp_granule *gi, const float *distor
     amp_scalefac_bands(c, gi, distort, xrpow, bRefine);
     status = loop_break(gi);
     if (status) return 0;
-    status = scale_bitcount(gi);
+    status = scale_bitcount(c, gi);
     if (!status) return 1;
     if (c->noise_shaping > 1) {
         memset(pseudohalf, 0, sizeof pseudohalf);
@@ -1042,7 +1082,7 @@ static int balance_noise(const lp_config *c, lp_granule *gi, const float *distor
         else if (gi->block_type == LP_SHORT && c->subblock_gain > 0)
             status = inc_subblock_gain(c, gi, xrpow) || loop_break(gi);
     }
-    if (!status) status = scale_bitcount(gi);
+    if (!status) status = scale_bitcount(c, gi);
     return !status;
 }
 
@@ -1520,7 +1560,8 @@ static void vbr_alloc(const lp_config *c, const vbr_ctx *t, const int vbrsf[LP_S
         vbr_set_scalefacs(gi, vbrsfmin, sf_temp, vbr_range_short);
     }
     else {
-        const uint8_t *max_rangep = vbr_range_long;            /* mode_gr == 2 */
+        static const uint8_t range_long_lsf_pretab[LP_SBMAX_L] = { 7, 7, 7, 7, 7, 7, 3, 3, 3, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+        const uint8_t *max_rangep = c->mode_gr == 2 ? vbr_range_long : range_long_lsf_pretab;      /* vbrquantize.c:861 */
         int maxover0 = 0, maxover1 = 0, maxover0p = 0, maxover1p = 0, vm0p = 1, vm1p = 1;
         for (sfb = 0; sfb < psymax; ++sfb) {
             int v0, v1, v0p, v1p;
@@ -1557,9 +1598,9 @@ static void vbr_alloc(const lp_config *c, const vbr_ctx *t, const int vbrsf[LP_S
         vbrmax -= delta;
         if (vbrmax < maxminsfb) vbrmax = maxminsfb;
         maxover0 -= mover; maxover0p -= mover; maxover1 -= mover; maxover1p -= mover;
-        if (maxover0 == 0) { gi->scalefac_scale = 0; gi->preflag = 0; }
+        if (maxover0 == 0) { gi->scalefac_scale = 0; gi->preflag = 0; max_rangep = vbr_range_long; }
         else if (maxover0p == 0) { gi->scalefac_scale = 0; gi->preflag = 1; }
-        else if (maxover1 == 0) { gi->scalefac_scale = 1; gi->preflag = 0; }
+        else if (maxover1 == 0) { gi->scalefac_scale = 1; gi->preflag = 0; max_rangep = vbr_range_long; }
         else if (maxover1p == 0) { gi->scalefac_scale = 1; gi->preflag = 1; }
         gi->global_gain = vbrmax;
         if (gi->global_gain < 0) gi->global_gain = 0;
@@ -1583,7 +1624,7 @@ static int vbr_try(const lp_config *c, const vbr_ctx *t, const int sftemp[LP_SFB
     float const xrpow_max = t->gi->xrpow_max;
     int nbits;
     vbr_alloc(c, t, sftemp, vbrsfmin, vbrmax);
-    (void) scale_bitcount(t->gi);
+    (void) scale_bitcount(c, t->gi);
     nbits = vbr_quantize_and_count(c, t);
     if (add_part2) nbits += t->gi->part2_length;
     t->gi->xrpow_max = xrpow_max;
@@ -1702,7 +1743,7 @@ static int vbr_encode_frame(lp_encoder *e, float xr34orig[2][2][576], float l3_x
                 vbr_ctx *t = &that_[gr][ch];
                 int const vbrmax = vbr_block_sf(c, t, l3_xmin[gr][ch], sfwork_[gr][ch], vbrsfmin_[gr][ch]);
                 vbr_alloc(c, t, sfwork_[gr][ch], vbrsfmin_[gr][ch], vbrmax);
-                (void) scale_bitcount(t->gi);
+                (void) scale_bitcount(c, t->gi);
             }
     use_nbits_fr = 0;
     for (gr = 0; gr < ngr; ++gr) {

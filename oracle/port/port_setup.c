@@ -631,7 +631,7 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         {4.50, 100.0, 2.2, 2.3, -12.0, 6.0, -14, 0, 2, 4, 2.239, 3, 93.9}, {4.80, 200.0, 2.7, 2.7, -18.0, 9.0, -17, 0, 2, 0, 2.570, 1, 93.6},
         {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} };
     static const int vbr_lowpass[11] = { 24000, 19500, 18500, 18000, 17500, 17000, 16500, 15600, 15200, 7230, 3950 };
-    int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, vbr_q = 0;
+    int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, vbr_q = 0, brow = 1;
     int vbr_no_lowpass = 0;
     int samplerate = samplerate_out;                                   /* 0 = chosen below the way lame_init_params does */
     float athaa_sensitivity = 0;
@@ -685,19 +685,17 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         /* ABR keeps the requested mean bitrate as it is (lame_set_VBR_mean_bitrate_kbps, default 128), clamped for
          * MPEG-1 rates (lame.c:655-658 and :1088-1093 with the default index range 1..14) */
         if (brate == 0) brate = 128;
-        if (brate < 32) brate = 32;
-        if (brate > 320) brate = 320;
+        if (samplerate) {                                              /* lame.c:645-658: only with an explicit output rate */
+            int const lo = samplerate < 32000 ? 8 : 32, hi = samplerate < 16000 ? 64 : (samplerate < 32000 ? 160 : 320);
+            if (brate < lo) brate = lo;
+            if (brate > hi) brate = hi;
+        }
     }
     else {
         if (brate == 0) {                                              /* lame.c:623-644 */
             if (samplerate == 0) samplerate = map_to_mp3_frequency((int) (0.97 * samplerate_in));
             brate = samplerate * 16 * c->channels / (1.e3 * 11.025f);
         }
-        /* util.c:320 FindNearestBitrate on the MPEG-1 row */
-        best = LGT_BITRATE[16 + 1];
-        for (i = 2; i <= 14; i++)
-            if (abs(LGT_BITRATE[16 + i] - brate) < abs(best - brate)) best = LGT_BITRATE[16 + i];
-        brate = best;
     }
     /* lame.c:704-762: low-pass from the bitrate */
     lowpass = lowpass_map[nearest_full_index(brate)];
@@ -712,15 +710,30 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         if (2 * c->lowpassfreq > samplerate_in) c->lowpassfreq = samplerate_in / 2;
         samplerate = optimum_samplefreq(c->lowpassfreq, samplerate_in);
     }
-    if (samplerate == 44100) sr_index = 0; else if (samplerate == 48000) sr_index = 1;
-    else if (samplerate == 32000) sr_index = 2; else return -1;       /* util.c:433 SmpFrqIndex, MPEG-1 only */
+    /* util.c:433 SmpFrqIndex: MPEG-1 (32/44.1/48 kHz), MPEG-2 (16/22.05/24 kHz) and MPEG-2.5 (8/11.025/12 kHz, also version 0) */
+    sr_index = -1;
+    for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) if (samplerate == LGT_SAMPLERATE[4 * i + j]) { sr_index = j; version = (i == 1) ? 1 : 0; }
+    if (sr_index < 0) return -1;
+    brow = (version == 1) ? 1 : (samplerate < 16000 ? 2 : 0);          /* row of bitrate_table: MPEG-2, MPEG-1, MPEG-2.5 */
+    if (vbr == 0) {
+        /* util.c:320 FindNearestBitrate on that row (lame.c:905-915) */
+        best = LGT_BITRATE[16 * brow + 1];
+        for (i = 1; i <= 14; i++)
+            if (LGT_BITRATE[16 * brow + i] > 0 && abs(LGT_BITRATE[16 * brow + i] - brate) < abs(best - brate)) best = LGT_BITRATE[16 * brow + i];
+        brate = best;
+    }
+    if (vbr == 3) {                                                    /* lame.c:1088-1093: into the range of this MPEG version */
+        int const hi = LGT_BITRATE[16 * version + (samplerate < 16000 ? 8 : 14)], lo = LGT_BITRATE[16 * version + 1];
+        if (brate > hi) brate = hi;
+        if (brate < lo) brate = lo;
+    }
     c->samplerate = samplerate;
     c->samplerate_in = samplerate_in;
     if (setup_resampler(c) != 0) return -1;
     if (vbr == 4) c->lowpassfreq = c->lowpassfreq < 24000 ? c->lowpassfreq : 24000;     /* lame.c:770-775 */
     else c->lowpassfreq = c->lowpassfreq < 20500 ? c->lowpassfreq : 20500;
     c->lowpassfreq = samplerate / 2 < c->lowpassfreq ? samplerate / 2 : c->lowpassfreq;
-    c->mode_gr = 2;
+    c->mode_gr = samplerate <= 24000 ? 1 : 2;                          /* lame.c:797 */
     if (mode == LP_MODE_NOT_SET || mode < 0) mode = LP_JOINT;
     if (mode == LP_DUAL) return -1;
     c->mode = mode;
@@ -739,24 +752,25 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     c->vbr = vbr;
     c->vbr_mean_kbps = brate;
     c->vbr_min_bitrate_index = 1;                                      /* lame.c:1067-1068 */
-    c->vbr_max_bitrate_index = 14;
+    c->vbr_max_bitrate_index = samplerate < 16000 ? 8 : 14;            /* 64 kbps with MPEG-2.5 */
     c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * brate);   /* lame.c:778-784 */
     c->vbr_q = vbr_q;
     c->vbr_q_frac = (vbr == 4) ? vbr_q_frac : 0.f;
     if (vbr != 0) c->bitrate_index = 1;                                /* lame.c:921 */
     else {
         c->bitrate_index = -1;
-        for (i = 0; i <= 14; i++) if (LGT_BITRATE[16 + i] == brate) { c->bitrate_index = i; break; }
+        for (i = 0; i <= 14; i++) if (LGT_BITRATE[16 * brow + i] == brate) { c->bitrate_index = i; break; }
         if (c->bitrate_index <= 0) return -1;
     }
-    j = sr_index + 3 * version;
+    j = sr_index + 3 * version + 6 * (samplerate < 16000);             /* lame.c:927 */
     for (i = 0; i < 23; i++) c->sfb_l[i] = LGT_SFB_LONG[j * 23 + i];
     for (i = 0; i < 7; i++) c->psfb21[i] = c->sfb_l[21] + i * ((c->sfb_l[22] - c->sfb_l[21]) / 6);
     c->psfb21[6] = 576;
     for (i = 0; i < 14; i++) c->sfb_s[i] = LGT_SFB_SHORT[j * 14 + i];
     for (i = 0; i < 7; i++) c->psfb12[i] = c->sfb_s[12] + i * ((c->sfb_s[13] - c->sfb_s[12]) / 6);
     c->psfb12[6] = 192;
-    c->sideinfo_len = (c->channels == 1) ? 4 + 17 : 4 + 32;
+    if (version == 1) c->sideinfo_len = (c->channels == 1) ? 4 + 17 : 4 + 32;     /* lame.c:1228-1235 */
+    else c->sideinfo_len = (c->channels == 1) ? 4 + 9 : 4 + 17;
     c->original = 1;
 
     if (vbr == 4) {

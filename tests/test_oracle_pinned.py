@@ -41,8 +41,8 @@ def test_port_chunking_invariance(oracle_mod):
 
 
 def test_port_rejects_unsupported(oracle_mod):
-    # MPEG-2 output rates: 22.05 kHz input, 64 kbps (lame_init_params picks 24 kHz), VBR -V8 (24 kHz), explicit 22.05 kHz
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(brate=8, vbr=4), dict(out_samplerate=22050)):
+    # not an MPEG rate, dual channel, VBR level out of range, VBR-new with quality 7+ is fine but vbr_rh is not a mode of the port
+    for kw in (dict(out_samplerate=20000), dict(mode=2), dict(brate=10, vbr=4), dict(vbr=2)):
         with pytest.raises(ValueError):
             oracle_mod.PortEncoder(**kw)
 
@@ -136,6 +136,23 @@ def test_port_fractional_vbr_quality_vs_reference(port_vs_ref_bin, args, env):
     mapping of the -V scale to the output rate it implies (lame.c:661-698): -V7 at 44.1 kHz = quality 5.63 at 32 kHz through the
     resampler, levels at 32 kHz input shrunk to 0..5.2"""
     r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="4", **env))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
+@pytest.mark.parametrize("args,env", [
+    ("noise 64 -1 -1 40 24000", {}), ("click 64 -1 -1 80 22050", {}), ("sine 96 0 -1 40 24000", {}), ("click 32 -1 -1 40 16000", {}), ("click 160 -1 -1 40 24000", {}),
+    ("click 24 -1 -1 40 8000", {}), ("noise 32 3 -1 40 11025", {}), ("gap 8 3 -1 40 12000", {}), ("click 40 -1 -1 60 12000", {}), ("sine 16 -1 5 40 8000", {}),
+    ("click 80 1 2 40 22050", {}), ("sine 56 -1 0 40 16000", {}), ("click 64 -1 -1 60 44100", {}), ("sine 32 -1 -1 60 44100", {}), ("click 8 3 -1 60 44100", {}),
+    ("click 48 -1 -1 60 44100", dict(LP_OUT_SR="16000", LP_CHUNK="777")), ("click 64 -1 -1 60 22050", dict(LP_VBR="3")), ("noise 24 -1 -1 40 8000", dict(LP_VBR="3")),
+    ("click 8 -1 -1 60 44100", dict(LP_VBR="4")), ("click 9 -1 -1 60 44100", dict(LP_VBR="4")), ("click 4 -1 -1 60 22050", dict(LP_VBR="4")),
+    ("noise 2 -1 -1 60 16000", dict(LP_VBR="4")), ("click 5 -1 -1 60 8000", dict(LP_VBR="4")), ("click 9 -1 -1 60 48000", dict(LP_VBR="4", LP_VBRQ_FRAC="0.5")),
+])
+def test_port_mpeg2_and_mpeg25_vs_reference(port_vs_ref_bin, args, env):
+    """MPEG-2 (16/22.05/24 kHz) and MPEG-2.5 (8/11.025/12 kHz) output: one granule per frame, LSF scalefactor partitions
+    (takehiro.c:1218), 8-bit main_data_begin side info, the 8 kHz band limits; CBR, ABR, VBR (-V8/-V9 through the resampler),
+    byte-identical to libmp3lame"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **env))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
