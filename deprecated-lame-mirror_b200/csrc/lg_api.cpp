@@ -33,6 +33,7 @@ struct Stream {
     std::vector<int16_t> pcm16[2];     /* timeline samples from index tbase on */
     std::vector<float> pcmf[2];        /* same, already through pcm_transform, once a float entry point was used */
     bool float_mode = false;
+    int  fs = 1152, need = 1904;       /* samples per frame (576 per granule) and what a frame needs in the buffer (calcNeeded, lame.c:1627) */
     /* input-rate conversion (util.c:531): the stream's input samples (through pcm_transform) from absolute index
      * raw_base on, the reference's per-call bookkeeping replayed as a list of chunks, the input clock, and the end
      * of the timeline the chunks cover.  The samples themselves are made on the device (kernel R). */
@@ -80,8 +81,8 @@ struct Stream {
     {
         long const have = tend();
         long const k = frames_done;
-        if (have < 1152 * k + 1904) return 0;
-        return (have - 1904 - 1152 * k) / 1152 + 1;
+        if (have < (long) fs * k + need) return 0;
+        return (have - need - (long) fs * k) / fs + 1;
     }
     void to_float(const LgDevCfg *cfg)
     {
@@ -100,7 +101,7 @@ struct Stream {
     }
     void drop_consumed()
     {
-        long const keep_from = 1152 * frames_done - LG_PCM_HIST;
+        long const keep_from = (long) fs * frames_done - LG_PCM_HIST;
         if (rs_mode) {
             /* chunks that end before the next window, and the input samples only they needed */
             size_t n = 0;
@@ -246,7 +247,7 @@ struct lamegpu_batch {
                 std::atomic<int> most(0), bad(0);
                 auto window = [&](int s, long &t0, long &t1, size_t &nck) {
                     const Stream &x = st[s];
-                    t0 = 1152 * x.frames_done - LG_PCM_HIST; t1 = t0 + (long) nfr[s] * 1152 + LG_PCM_HALO;
+                    t0 = (long) x.fs * x.frames_done - LG_PCM_HIST; t1 = t0 + (long) nfr[s] * x.fs + LG_PCM_HALO;
                     nck = 0;
                     while (nck < x.chunks.size() && x.chunks[nck].out_pos < t1) nck++;
                 };
@@ -289,7 +290,7 @@ struct lamegpu_batch {
                 parallel_for(S, [&](int s) {
                     if (!nfr[s]) return;
                     st[s].to_float(&cfg);
-                    size_t const n = (size_t) nfr[s] * 1152 + LG_PCM_HALO;
+                    size_t const n = (size_t) nfr[s] * st[s].fs + LG_PCM_HALO;
                     for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcmf[c].data(), n * sizeof(float));
                 });
             }
@@ -297,7 +298,7 @@ struct lamegpu_batch {
                 int16_t *hp = lg_engine_host_pcm16(eng);
                 parallel_for(S, [&](int s) {
                     if (!nfr[s]) return;
-                    size_t const n = (size_t) nfr[s] * 1152 + LG_PCM_HALO;
+                    size_t const n = (size_t) nfr[s] * st[s].fs + LG_PCM_HALO;
                     for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcm16[c].data(), n * sizeof(int16_t));
                 });
             }
@@ -329,7 +330,7 @@ struct lamegpu_batch {
                 x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
                 x.bw.buf.clear();
                 x.frames_done += nfr[s];
-                x.mf_samples_to_encode -= 1152L * nfr[s];
+                x.mf_samples_to_encode -= (long) x.fs * nfr[s];
                 x.drop_consumed();
             });
             for (int s = 0; s < S; s++) done += nfr[s];
@@ -353,13 +354,14 @@ struct lamegpu_batch {
         while (remaining > 0) {
             double const itime = x.rs_itime;
             auto jof = [&](int k) { return (int) floor((double) k * ratio - itime); };
-            int lo = 0, hi = 1152;                         /* first k in [0, 1152) with reach + j(k) >= remaining, else 1152 */
+            int const fs = x.fs;                           /* a chunk is at most one frame of output */
+            int lo = 0, hi = fs;                           /* first k in [0, fs) with reach + j(k) >= remaining, else fs */
             while (lo < hi) {
                 int const mid = (lo + hi) >> 1;
                 if (reach + jof(mid) >= remaining) hi = mid; else lo = mid + 1;
             }
             int const count = lo;
-            int const j = jof(count < 1152 ? count : 1151);
+            int const j = jof(count < fs ? count : fs - 1);
             int const used = std::min(remaining, reach + j);
             if (count > 0) x.chunks.push_back(Stream::Chunk{ itime, in_ptr, x.rs_tend, count });
             x.rs_itime += (double) used - (double) count * ratio;
@@ -438,31 +440,33 @@ struct lamegpu_batch {
              * (pump() runs after each feed), so the buffer fill is what the timeline holds beyond them. */
             int samples_to_encode = (int) (x.mf_samples_to_encode - 1152);
             samples_to_encode += 16. / cfg.rs_ratio;
-            int end_padding = 1152 - (samples_to_encode % 1152);
-            if (end_padding < 576) end_padding += 1152;
+            int const fs = x.fs;
+            int end_padding = fs - (samples_to_encode % fs);
+            if (end_padding < 576) end_padding += fs;
             x.tag.enc_padding = end_padding;
-            int frames_left = (samples_to_encode + end_padding) / 1152;
+            int frames_left = (samples_to_encode + end_padding) / fs;
             long virt_done = x.frames_done;                 /* frames the reference would have encoded so far */
             while (frames_left > 0) {
-                int bunch = (int) (1904 - (x.rs_tend - 1152 * virt_done));
+                int bunch = (int) (x.need - (x.rs_tend - (long) fs * virt_done));
                 bunch *= cfg.rs_ratio;
                 if (bunch > 1152) bunch = 1152;
                 if (bunch < 1) bunch = 1;
                 for (int c = 0; c < 2; c++) x.raw[c].insert(x.raw[c].end(), (size_t) bunch, 0.f);
                 rs_schedule(x, bunch);
-                long const ready = x.rs_tend >= 1152 * virt_done + 1904 ? (x.rs_tend - 1904 - 1152 * virt_done) / 1152 + 1 : 0;
+                long const ready = x.rs_tend >= (long) fs * virt_done + x.need ? (x.rs_tend - x.need - (long) fs * virt_done) / fs + 1 : 0;
                 if (ready > 0) frames_left -= 1;
                 virt_done += ready;
             }
             return;
         }
         long const samples_to_encode = x.mf_samples_to_encode - 1152;
-        long end_padding = 1152 - (samples_to_encode % 1152);
-        if (end_padding < 576) end_padding += 1152;
+        long const fs = x.fs;
+        long end_padding = fs - (samples_to_encode % fs);
+        if (end_padding < 576) end_padding += fs;
         x.tag.enc_padding = (int) end_padding;                /* lame.c:2091 */
-        long const frames_left = (samples_to_encode + end_padding) / 1152;
+        long const frames_left = (samples_to_encode + end_padding) / fs;
         long const last = x.frames_done + frames_left - 1;
-        long const need = 1152 * last + 1904 - x.tend();
+        long const need = fs * last + x.need - x.tend();
         if (need > 0) {
             if (x.float_mode) for (int c = 0; c < 2; c++) x.pcmf[c].insert(x.pcmf[c].end(), (size_t) need, 0.f);
             else for (int c = 0; c < 2; c++) x.pcm16[c].insert(x.pcm16[c].end(), (size_t) need, (int16_t) 0);
@@ -510,7 +514,10 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
     b->nthreads = (int) std::max(1u, std::min(hw ? hw : 1u, 64u));
     if (const char *e = getenv("LAMEGPU_THREADS")) b->nthreads = std::max(1, atoi(e));
     b->st.resize(nstreams);
-    for (auto &s : b->st) { s.rs_mode = b->cfg.resample != 0; s.init(); s.last_bitrate_index = b->cfg.bitrate_index; }
+    for (auto &s : b->st) {
+        s.rs_mode = b->cfg.resample != 0; s.fs = 576 * b->cfg.mode_gr; s.need = 1024 + s.fs - 272;
+        s.init(); s.last_bitrate_index = b->cfg.bitrate_index;
+    }
     return b;
 }
 
@@ -594,7 +601,7 @@ int lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes)
     size_t const stride = lg_engine_pcm_stride(b->eng);
     int16_t *hp = lg_engine_host_pcm16(b->eng);
     int *nfr = lg_engine_host_nfr(b->eng);
-    size_t const nsamp = (size_t) nframes * 1152 + LG_PCM_HALO - LG_PCM_HIST - 528;   /* user samples consumed */
+    size_t const nsamp = (size_t) nframes * b->st[0].fs + LG_PCM_HALO - LG_PCM_HIST - 528;   /* user samples consumed */
     for (int s = 0; s < b->S; s++) {
         nfr[s] = nframes;
         for (int c = 0; c < 2; c++) {
@@ -645,13 +652,17 @@ struct lame_global_struct {
 };
 
 /* VbrTag.c:255 setLameTagFrameHeader (MPEG-1 branch): the tag frame looks like a frame of the stream itself, without padding */
+static int tag_xing_kbps(const LgDevCfg *c) { return c->version == 1 ? 128 : (c->samplerate < 16000 ? 32 : 64); }
+
 static void tag_frame_header(const LgDevCfg *c, int mode_ext, unsigned char *buffer)
 {
     buffer[0] = 0xff;
-    buffer[1] = (unsigned char) (0xf0 | 0x0a | (c->error_protection ? 0 : 1));
-    /* CBR: the stream's own bitrate; otherwise XING_BITRATE1 = 128 kbps (VbrTag.c:285-306) */
+    /* sync (MPEG-2.5 clears its last bit), version bit, layer III, protection (VbrTag.c:262-267, :308-322) */
+    buffer[1] = (unsigned char) ((c->samplerate < 16000 ? 0xe0 : 0xf0) | (c->version == 1 ? 0x0a : 0x02) | (c->error_protection ? 0 : 1));
+    /* CBR: the stream's own bitrate; otherwise XING_BITRATE1 / 2 / 25 = 128 / 64 / 32 kbps (VbrTag.c:285-306) */
     int bidx = c->bitrate_index;
-    if (c->vbr != 0) for (bidx = 1; bidx < 15 && c->bitrate_kbps[bidx] != 128; bidx++) { }
+    int const xing_kbps = tag_xing_kbps(c);
+    if (c->vbr != 0) for (bidx = 1; bidx < 15 && c->bitrate_kbps[bidx] != xing_kbps; bidx++) { }
     buffer[2] = (unsigned char) ((16 * bidx) | ((c->samplerate_index << 2) & 0x0c) | (c->extension & 1));
     buffer[3] = (unsigned char) ((c->mode << 6) | ((mode_ext & 3) << 4) | ((c->copyright & 1) << 3) | ((c->original & 1) << 2) | (c->emphasis & 3));
 }
@@ -664,7 +675,7 @@ static void tag_init(lamegpu_batch *b)
 {
     Stream &x = b->st[0];
     const LgDevCfg *c = &b->cfg;
-    int const kbps_header = (c->vbr == 0) ? c->brate : 128;         /* VbrTag.c:517-529 */
+    int const kbps_header = (c->vbr == 0) ? c->brate : tag_xing_kbps(c);         /* VbrTag.c:517-529 */
     int const total = ((c->version + 1) * 72000 * kbps_header) / c->samplerate;
     if (total < c->sideinfo_len + LG_LAMEHEADERSIZE || total > 2880) return;      /* "disable tag, it wont fit" */
     x.tag.on = true;
@@ -754,7 +765,7 @@ int lame_init_params(lame_global_flags *g)
     if (g->write_lame_tag) tag_init(g->b);                 /* lame.c:1249 lame_init_bitstream -> InitVbrTag */
     return 0;
 }
-int lame_get_framesize(const lame_global_flags *g) { return ok(g) && g->initialised ? 1152 : 0; }
+int lame_get_framesize(const lame_global_flags *g) { return ok(g) && g->initialised ? 576 * g->b->cfg.mode_gr : 0; }
 int lame_get_frameNum(const lame_global_flags *g) { return ok(g) && g->b ? (int) g->b->st[0].frames_done : 0; }
 int lame_get_encoder_delay(const lame_global_flags *g) { return ok(g) ? 576 : 0; }
 

@@ -319,7 +319,7 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int const stream = blockIdx.x / nslots, slot = blockIdx.x % nslots;
     int const nch = cfg->channels;
-    if (slot > 2 * nfr[stream]) return;                      /* this stream has fewer frames in this launch */
+    if (slot > cfg->mode_gr * nfr[stream]) return;           /* this stream has fewer frames (of mode_gr granules) in this launch */
 
     /* phase 1: lame.c:1786 lame_copy_inbuffer (u = xl*m00 + xr*m01, v = xl*m10 + xr*m11) */
     {

@@ -98,9 +98,9 @@ lg_kernel_mdct(const LgDevCfg *__restrict__ cfg, const float *__restrict__ sb, c
     int const ngr = 2 * nframes;
     int const stream = blockIdx.x / ngr, gb = blockIdx.x % ngr;
     int const nch = cfg->channels;
-    if (gb >= 2 * nfr[stream]) return;
+    if (gb >= cfg->mode_gr * nfr[stream]) return;
     const LgPsyOut *P = psy + (size_t) stream * ngr + gb;
-    const LgFrameCtl *F = frm + (size_t) stream * nframes + (gb >> 1);
+    const LgFrameCtl *F = frm + (size_t) stream * nframes + (gb / cfg->mode_gr);
     int const type = (ch < nch) ? P->block_type[ch] : LG_NORM;
     const float *win = cfg->mdctwin;
     const float *tantab_l = win + 2 * 36 + 3, *cx = win + 2 * 36 + 12, *ca = win + 2 * 36 + 20, *cs = win + 2 * 36 + 28;

@@ -108,7 +108,8 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const nch = c->channels;
     const LgFrameOut *fo = fout + (size_t) stream * nframes + frame;
-    const LgGranuleOut *g4 = gout + ((size_t) stream * 2 * nframes + 2 * frame) * 2;
+    int const mgr = c->mode_gr;                   /* MPEG-2/2.5: one granule per frame, warps 2 and 3 only help with the drains */
+    const LgGranuleOut *g4 = gout + ((size_t) stream * 2 * nframes + mgr * frame) * 2;
     int const pay_bytes = fo->pay_bytes;
     int const nwords = (pay_bytes + 3) >> 2;
     for (int i = threadIdx.x; i <= nwords && i < LG_PACK_WORDS; i += 128) sm->img[i] = 0u;
@@ -117,16 +118,32 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
         int o = fo->drain_pre;
         for (int k = 0; k < 4; k++) {
             sm->gstart[k] = o;
-            if ((k & 1) < nch) o += g4[k].part2_3_length + g4[k].part2_length;
+            if ((k & 1) < nch && (k >> 1) < mgr) o += g4[k].part2_3_length + g4[k].part2_length;
         }
     }
     __syncthreads();
     int const gr = warp >> 1, ch = warp & 1;
-    if (ch < nch) {
+    if (ch < nch && gr < mgr) {
         const LgGranuleOut *gi = &g4[warp];
         int pos = sm->gstart[warp];
-        /* ---- scale factors (writeMainData bitstream.c:700-718) */
-        {
+        /* ---- scale factors (writeMainData bitstream.c:700-718; MPEG-2/2.5 :747-775: every band of a partition with the partition's
+         * width, which scalefac_compress encodes (takehiro.c:1281-1297)) */
+        if (mgr == 1) {
+            int const sfc = gi->scalefac_compress | (gi->scalefac_compress_hi << 8), sh = gi->block_type == LG_SHORT;
+            int slen[5] = { 0, 0, 0, 0, 0 };
+            if (gi->preflag) { slen[0] = (sfc - 500) / 3; slen[1] = (sfc - 500) % 3; }
+            else { slen[0] = (sfc >> 4) / 5; slen[1] = (sfc >> 4) % 5; slen[2] = (sfc >> 2) & 3; slen[3] = sfc & 3; }
+            for (int r = 0; r < 2; r++) {
+                int const sfb = lane + 32 * r;
+                int n = 0, v = 0;
+                if (sfb < 39) { n = slen[lg_lsf_partition(sh, gi->preflag, sfb)]; v = gi->scalefac[sfb] > 0 ? gi->scalefac[sfb] : 0; }
+                int tot;
+                int const off = lg_warp_excl_scan(n, lane, &tot);
+                lg_put(sm->img, pos + off, (unsigned) v, n);
+                pos += tot;
+            }
+        }
+        else {
             int const slen1 = LG_SLEN1_TAB[gi->scalefac_compress], slen2 = LG_SLEN2_TAB[gi->scalefac_compress];
             for (int r = 0; r < 2; r++) {
                 int const sfb = lane + 32 * r;
@@ -222,7 +239,39 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
 #endif
         }
         /* ---- this granule.channel's 59 bits of side info (encodeSideInfo2 bitstream.c:409-460) */
-        if (lane == 0) {
+        if (lane == 0 && mgr == 1) {
+            /* bitstream.c:415-466: MPEG-2/2.5 side info of one gr.ch = 63 bits behind the 8-bit main_data_begin and the private bits */
+            int so = 32 + 8 + nch + 63 * ch;
+            int a0 = t0, a1 = t1, a2 = t2;
+            if (a0 == 14) a0 = 16;
+            if (a1 == 14) a1 = 16;
+            if (a2 == 14) a2 = 16;
+            lg_put(sm->hdr, so, (unsigned) (gi->part2_3_length + gi->part2_length), 12); so += 12;
+            lg_put(sm->hdr, so, (unsigned) (bigv / 2), 9); so += 9;
+            lg_put(sm->hdr, so, gi->global_gain, 8); so += 8;
+            lg_put(sm->hdr, so, (unsigned) (gi->scalefac_compress | (gi->scalefac_compress_hi << 8)), 9); so += 9;
+            if (gi->block_type != LG_NORM) {
+                lg_put(sm->hdr, so, 1u, 1); so += 1;
+                lg_put(sm->hdr, so, gi->block_type, 2); so += 2;
+                lg_put(sm->hdr, so, gi->mixed_block_flag, 1); so += 1;
+                lg_put(sm->hdr, so, (unsigned) a0, 5); so += 5;
+                lg_put(sm->hdr, so, (unsigned) a1, 5); so += 5;
+                lg_put(sm->hdr, so, gi->subblock_gain[0], 3); so += 3;
+                lg_put(sm->hdr, so, gi->subblock_gain[1], 3); so += 3;
+                lg_put(sm->hdr, so, gi->subblock_gain[2], 3); so += 3;
+            }
+            else {
+                so += 1;
+                lg_put(sm->hdr, so, (unsigned) a0, 5); so += 5;
+                lg_put(sm->hdr, so, (unsigned) a1, 5); so += 5;
+                lg_put(sm->hdr, so, (unsigned) a2, 5); so += 5;
+                lg_put(sm->hdr, so, gi->region0_count, 4); so += 4;
+                lg_put(sm->hdr, so, gi->region1_count, 3); so += 3;
+            }
+            lg_put(sm->hdr, so, gi->scalefac_scale, 1); so += 1;
+            lg_put(sm->hdr, so, gi->count1table_select, 1);
+        }
+        else if (lane == 0) {
             int so = 32 + 9 + (nch == 2 ? 3 : 5) + 4 * nch + 59 * (gr * nch + ch);
             int a0 = t0, a1 = t1, a2 = t2;
             if (a0 == 14) a0 = 16;
@@ -257,7 +306,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
     }
     /* bytes 36..39 of the record, behind the longest side info: the four block types (4 = mixed, 0xff = no such channel) for
      * the host's statistics (encoder.c:156 updateStats) */
-    if (lane == 0) lg_put(sm->hdr, 288 + 8 * warp, ch < nch ? (g4[warp].mixed_block_flag ? 4u : (unsigned) g4[warp].block_type) : 0xffu, 8);
+    if (lane == 0) lg_put(sm->hdr, 288 + 8 * warp, (ch < nch && gr < mgr) ? (g4[warp].mixed_block_flag ? 4u : (unsigned) g4[warp].block_type) : 0xffu, 8);
     /* ---- ancillary drains and the frame header (warps 2 and 3 are the lighter ones in joint stereo) */
     if (warp == 3) lg_put_drain(sm->img, 0, fo->drain_pre, fo->anc_pre, !c->disable_reservoir, lane);
     if (warp == 2) {
@@ -273,7 +322,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
     if (threadIdx.x == 33) {
         /* bitstream.c:330-372: header, main_data_begin, private bits, scfsi */
         int so = 0;
-        lg_put(sm->hdr, so, 0xfffu, 12); so += 12;
+        lg_put(sm->hdr, so, c->samplerate < 16000 ? 0xffeu : 0xfffu, 12); so += 12;     /* MPEG-2.5 clears the last sync bit */
         lg_put(sm->hdr, so, (unsigned) c->version, 1); so += 1;
         lg_put(sm->hdr, so, 4 - 3, 2); so += 2;
         lg_put(sm->hdr, so, !c->error_protection, 1); so += 1;
@@ -286,10 +335,13 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
         lg_put(sm->hdr, so, (unsigned) c->copyright, 1); so += 1;
         lg_put(sm->hdr, so, (unsigned) c->original, 1); so += 1;
         lg_put(sm->hdr, so, (unsigned) c->emphasis, 2); so += 2;
-        lg_put(sm->hdr, so, (unsigned) fo->main_data_begin, 9); so += 9;
-        so += (nch == 2 ? 3 : 5);
-        for (int k = 0; k < nch; k++)
-            for (int band = 0; band < 4; band++) { lg_put(sm->hdr, so, fo->scfsi[k][band], 1); so += 1; }
+        if (mgr == 1) lg_put(sm->hdr, so, (unsigned) fo->main_data_begin, 8);          /* then nch private bits (0), no scfsi */
+        else {
+            lg_put(sm->hdr, so, (unsigned) fo->main_data_begin, 9); so += 9;
+            so += (nch == 2 ? 3 : 5);
+            for (int k = 0; k < nch; k++)
+                for (int band = 0; band < 4; band++) { lg_put(sm->hdr, so, fo->scfsi[k][band], 1); so += 1; }
+        }
     }
     __syncthreads();
     /* ---- image -> HBM (big-endian bit order = byte-swapped words) */

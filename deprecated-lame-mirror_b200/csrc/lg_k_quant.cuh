@@ -602,11 +602,54 @@ __device__ __forceinline__ void lg_calc_noise(const LgDevCfg *__restrict__ c, Lg
     __syncwarp();
 }
 
-/* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount.
- * By value (three call sites, and the caller's scalars stay in registers): returns part2_length (LG_LARGE_BITS = does
- * not fit) | scalefac_compress << 20 | preflag << 24. */
-__device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, int sfbmax, int sfbdivide, int preflag, int compress, int lane)
+/* takehiro.c:1218 mpeg2_scale_bitcount (MPEG-2/2.5): four partitions of bands (nr_of_sfb_block, quantize_pvt.c:51; table 0 without,
+ * table 2 with preflag; the row for short blocks counts the three windows), each coded with the bit length of its largest
+ * scalefactor.  A partition's maximum out of range = "over": part2_length and scalefac_compress keep their values. */
+__device__ __forceinline__ int lg_lsf_partition(int short_block, int preflag, int sfb)
 {
+    /* first band of partitions 1..3 (bands of a short block counted per window: sfb / 3) */
+    int const b = short_block ? sfb / 3 : sfb;
+    if (preflag) return short_block ? (b >= 12 ? 4 : (b >= 6)) : (b >= 21 ? 4 : (b >= 11));
+    if (short_block) return b >= 12 ? 4 : b / 3;
+    return b >= 21 ? 4 : (b < 6 ? 0 : 1 + (b - 6) / 5);
+}
+__device__ __forceinline__ int lg_lsf_partition_bands(int short_block, int preflag, int part)
+{
+    if (preflag) return part < 2 ? (short_block ? 18 : (part ? 10 : 11)) : 0;
+    return short_block ? 9 : (part ? 5 : 6);
+}
+__device__ __noinline__ unsigned lg_scale_bitcount_lsf(LgQWarp *w, int block_type, int preflag, int compress, int part2_length, int lane)
+{
+    const int *sf = w->sfw;
+    int const sh = block_type == LG_SHORT;
+    int m[4] = { 0, 0, 0, 0 };
+    for (int r = 0; r < 2; r++) {
+        int const sfb = lane + 32 * r;
+        int const part = sfb < 39 ? lg_lsf_partition(sh, preflag, sfb) : 4;
+        int const v = part < 4 ? sf[sfb] : 0;
+        for (int p = 0; p < 4; p++) if (part == p && v > m[p]) m[p] = v;
+    }
+    int over = 0, bits = 0, slen[4];
+    for (int p = 0; p < 4; p++) {
+        m[p] = lg_wmax_i(m[p]);
+        int const range = preflag ? (p == 0 ? 7 : (p == 1 ? 3 : 0)) : (p < 2 ? 15 : 7);      /* max_range_sfac_tab rows 2 and 0 */
+        over += m[p] > range;
+        slen[p] = m[p] == 0 ? 0 : 32 - __clz(m[p]);                                     /* log2tab: bits of the maximum (<= 15) */
+        bits += slen[p] * lg_lsf_partition_bands(sh, preflag, p);
+    }
+    if (!over) {
+        part2_length = bits;
+        compress = preflag ? 500 + slen[0] * 3 + slen[1] : (((slen[0] * 5) + slen[1]) << 4) + (slen[2] << 2) + slen[3];
+    }
+    return (unsigned) part2_length | ((unsigned) compress << 20) | ((unsigned) preflag << 29) | ((unsigned) (over != 0) << 30);
+}
+
+/* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount (and :1318 the dispatch to the
+ * MPEG-2 form).  By value (three call sites, and the caller's scalars stay in registers): returns part2_length (LG_LARGE_BITS
+ * = does not fit) | scalefac_compress << 20 | preflag << 29 | does-not-fit << 30. */
+__device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, int sfbmax, int sfbdivide, int preflag, int compress, int lsf_part2, int lane)
+{
+    if (lsf_part2 >= 0) return lg_scale_bitcount_lsf(w, block_type, preflag, compress, lsf_part2, lane);
     int *sf = w->sfw;
     if (block_type != LG_SHORT) {
         if (!preflag) {
@@ -631,9 +674,11 @@ __device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, i
     key = lg_wmin_i(key);
     int part2_length = LG_LARGE_BITS;
     if (key != 0x7fffffff) { part2_length = key >> 4; compress = key & 15; }
-    return (unsigned) part2_length | ((unsigned) compress << 20) | ((unsigned) preflag << 24);
+    return (unsigned) part2_length | ((unsigned) compress << 20) | ((unsigned) preflag << 29) | ((unsigned) (part2_length == LG_LARGE_BITS) << 30);
 }
-#define LG_APPLY_SCALE_BITCOUNT(gi, r) do { (gi).part2_length = (int) ((r) & 0xfffffu); (gi).scalefac_compress = (int) (((r) >> 20) & 15u); (gi).preflag = (int) (((r) >> 24) & 1u); } while (0)
+#define LG_APPLY_SCALE_BITCOUNT(gi, r) do { (gi).part2_length = (int) ((r) & 0xfffffu); (gi).scalefac_compress = (int) (((r) >> 20) & 511u); (gi).preflag = (int) (((r) >> 29) & 1u); } while (0)
+/* the last argument of lg_scale_bitcount: -1 for MPEG-1, else the current part2_length (kept when the MPEG-2 form does not fit) */
+#define LG_LSF_ARG(c, gi) ((c)->mode_gr == 1 ? (gi).part2_length : -1)
 
 /* quantize.c:540 loop_break */
 __device__ __forceinline__ int lg_loop_break(const LgQWarp *w, int sbg, int sfbmax, int lane)
@@ -803,9 +848,9 @@ __device__ __forceinline__ int lg_balance_noise(const LgDevCfg *__restrict__ c, 
     lg_amp_scalefac_bands<SUB>(c, w, gi, qc, lane);
     if (lg_loop_break(w, gi.sbg, qc.sfbmax, lane)) return 0;
     for (int pass = 0;; pass++) {
-        unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, lane);
+        unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, LG_LSF_ARG(c, gi), lane);
         LG_APPLY_SCALE_BITCOUNT(gi, r);
-        int status = gi.part2_length == LG_LARGE_BITS;
+        int status = (int) (r >> 30) & 1;
         if (!status) return 1;
         if (pass == 1) return 0;
         if (c->noise_shaping > 1) {
@@ -1005,7 +1050,7 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
     if (qc.block_type != LG_SHORT) max_nonzero |= 1;
     else { max_nonzero /= 6; max_nonzero *= 6; max_nonzero += 5; }
     if (c->sfb21_extra == 0 && c->samplerate < 44000) {
-        int const limit = (qc.block_type != LG_SHORT) ? c->sfb_l[21] - 1 : 3 * c->sfb_s[12] - 1;
+        int const limit = (qc.block_type != LG_SHORT) ? c->sfb_l[c->samplerate <= 8000 ? 17 : 21] - 1 : 3 * c->sfb_s[c->samplerate <= 8000 ? 9 : 12] - 1;
         if (max_nonzero > limit) max_nonzero = limit;
     }
     qc.max_nonzero_coeff = max_nonzero;
@@ -1133,6 +1178,7 @@ __device__ __noinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c
 __device__ __noinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
 {
     const int16_t *ix = w->ixw;
+    if (qc.block_type == LG_SHORT && c->mode_gr == 1) return;          /* takehiro.c:899: not for short blocks of MPEG-2 */
     LgQInfo g2 = gi;
     if (qc.block_type == LG_NORM) {
         lg_recalc_divide_init(c, w, gi.big_values, lane);
@@ -1231,7 +1277,7 @@ __device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__
     for (int sfb = lane; sfb < qc.sfbmax; sfb += 32) if (sf[sfb] == -2) sf[sfb] = 0;
     __syncwarp();
     if (recalc) {
-        unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, lane);
+        unsigned const r = lg_scale_bitcount(w, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, LG_LSF_ARG(c, gi), lane);
         LG_APPLY_SCALE_BITCOUNT(gi, r);
     }
 }
@@ -1403,6 +1449,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
     int anc_flag = st->ancillary_flag, pay_off = 0;
 
     int const my_frames = nfr[stream];
+    int const mgr = cfg->mode_gr;                      /* granules per frame: 2 (MPEG-1) or 1 (MPEG-2/2.5) */
     for (int frame = 0; frame < my_frames; frame++) {
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;
@@ -1412,9 +1459,9 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
         int targ_abr[2][2] = { { 0, 0 }, { 0, 0 } };
         if (abr) {
             /* quantize.c:1900 ABR_iteration_loop: all four targets up front, the frame size is chosen afterwards */
-            const LgPsyOut *P0 = psy + (size_t) stream * 2 * nframes + 2 * frame;
+            const LgPsyOut *P0 = psy + (size_t) stream * 2 * nframes + mgr * frame;
             float const pe4[2][2] = { { F->pe_use[0][0], F->pe_use[0][1] }, { F->pe_use[1][0], F->pe_use[1][1] } };
-            int const bt4[2][2] = { { P0[0].block_type[0], P0[0].block_type[1] }, { P0[1].block_type[0], P0[1].block_type[1] } };
+            int const bt4[2][2] = { { P0[0].block_type[0], P0[0].block_type[1] }, { P0[mgr - 1].block_type[0], P0[mgr - 1].block_type[1] } };
             float const mer[2] = { F->ms_ener_ratio[0], F->ms_ener_ratio[1] };
             lg_calc_target_bits(cfg, resv_size, padding, pe4, bt4, mer, mode_ext, targ_abr, &analog_silence_bits);
             mean_bits = resv_max = 0;
@@ -1422,8 +1469,8 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
         else (void) lg_resv_frame_begin(cfg, bitrate_index, padding, resv_size, &mean_bits, &resv_max);   /* reservoir.c:83 */
         uint8_t scfsi[4] = { 0, 0, 0, 0 };
         int frame_used = 0;
-        for (int gr = 0; gr < 2; gr++) {
-            int const gb = 2 * frame + gr;
+        for (int gr = 0; gr < mgr; gr++) {
+            int const gb = mgr * frame + gr;
             const LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
             int targ_bits[2];
             if (abr) { targ_bits[0] = targ_abr[gr][0]; targ_bits[1] = targ_abr[gr][1]; }
@@ -1447,11 +1494,13 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                 qc.block_type = P->block_type[ch];
                 qc.sfb_lmax = LG_SBPSY_L; qc.sfb_smin = LG_SBPSY_S;
                 qc.psy_lmax = cfg->sfb21_extra ? LG_SBMAX_L : LG_SBPSY_L;
+                if (cfg->samplerate <= 8000) { qc.sfb_lmax = 17; qc.sfb_smin = 9; qc.psy_lmax = 17; }      /* quantize.c:252-256 */
                 qc.psymax = qc.psy_lmax; qc.sfbmax = qc.sfb_lmax; qc.sfbdivide = 11;
                 if (qc.block_type == LG_SHORT) {
                     qc.sfb_smin = 0; qc.sfb_lmax = 0;
                     qc.psymax = 3 * (cfg->sfb21_extra ? LG_SBMAX_S : LG_SBPSY_S);
                     qc.sfbmax = 3 * LG_SBPSY_S;
+                    if (cfg->samplerate <= 8000) qc.psymax = qc.sfbmax = 3 * 9;                           /* quantize.c:284-289 */
                     qc.sfbdivide = qc.sfbmax - 18;
                     qc.psy_lmax = 0;
                 }
@@ -1548,12 +1597,13 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                     o->part2_3_length = (int16_t) gi.part2_3_length; o->part2_length = (int16_t) gi.part2_length;
                     o->big_values = (int16_t) gi.big_values; o->count1 = (int16_t) gi.count1;
                     o->global_gain = (uint8_t) gi.global_gain; o->scalefac_compress = (uint8_t) gi.scalefac_compress;
+                    o->scalefac_compress_hi = (uint8_t) (gi.scalefac_compress >> 8);
                     o->block_type = (uint8_t) qc.block_type; o->mixed_block_flag = 0;
                     for (int i = 0; i < 3; i++) { o->table_select[i] = (uint8_t) gi.table_select[i]; o->subblock_gain[i] = (uint8_t) ((gi.sbg >> (4 * i)) & 15); }
                     o->region0_count = (uint8_t) gi.region0_count; o->region1_count = (uint8_t) gi.region1_count;
                     o->preflag = (uint8_t) gi.preflag; o->scalefac_scale = (uint8_t) gi.scalefac_scale;
                     o->count1table_select = (uint8_t) gi.count1table_select;
-                    o->sfbmax = (uint8_t) qc.sfbmax; o->sfbdivide = (uint8_t) qc.sfbdivide; o->pad_ = 0;
+                    o->sfbmax = (uint8_t) qc.sfbmax; o->sfbdivide = (uint8_t) qc.sfbdivide;
                     sm->used_bits[ch] = used;
                 }
             }

@@ -235,7 +235,8 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
     float const pcfact = 0.6f;
 
     int const my_frames = nfr[stream];
-    for (int gb = 0; gb < 2 * my_frames; gb++) {
+    int const mgr = cfg->mode_gr;                 /* granules per frame: 2 (MPEG-1) or 1 (MPEG-2/2.5) */
+    for (int gb = 0; gb < mgr * my_frames; gb++) {
         const LgAnalysis *A = &sm->A;
         {
             static_assert(sizeof(LgAnalysis) % 8 == 0, "LgAnalysis is copied in 8-byte words");
@@ -245,7 +246,7 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
         }
         __syncwarp();
         LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
-        int const gr = gb & 1;
+        int const gr = gb % mgr;
         float const ath_factor = (cfg->msfix > 0.f) ? (cfg->ath_offset_factor * st->ath_adjust_factor) : 1.f;
         float const qml = st->masking_lower;
 
@@ -433,11 +434,11 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
         __syncwarp();
 
         /* ---- frame-level decisions once both granules are known (encoder.c:380-518) */
-        if (gr == 1) {
-            int const frame = gb >> 1;
+        if (gr == mgr - 1) {
+            int const frame = gb / mgr;
             LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
             if (lane == 0) {
-                const LgPsyOut *P0 = P - 1;
+                const LgPsyOut *P0 = P - (mgr - 1);
                 float loud[2][2] = { { P0->loudness_sq[0], P0->loudness_sq[1] }, { P->loudness_sq[0], P->loudness_sq[1] } };
                 float ms_ener_ratio[2] = { .5f, .5f };
                 int mode_ext = 0;
@@ -445,7 +446,7 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                 int padding = 0;
                 if ((st->slot_lag -= cfg->frac_spf) < 0) { st->slot_lag += cfg->samplerate; padding = 1; }
                 if (cfg->mode == LG_JOINT)
-                    for (int g = 0; g < 2; g++) {
+                    for (int g = 0; g < mgr; g++) {
                         ms_ener_ratio[g] = sm->frame_tot[g][2] + sm->frame_tot[g][3];
                         if (ms_ener_ratio[g] > 0) ms_ener_ratio[g] = sm->frame_tot[g][3] / ms_ener_ratio[g];
                     }
@@ -453,10 +454,10 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                 if (cfg->force_ms) mode_ext = 2;
                 else if (cfg->mode == LG_JOINT) {
                     float sum_pe_MS = 0, sum_pe_LR = 0;
-                    for (int g = 0; g < 2; g++)
+                    for (int g = 0; g < mgr; g++)
                         for (int ch = 0; ch < nch; ch++) { sum_pe_MS += sm->frame_pe[g][2 + ch]; sum_pe_LR += sm->frame_pe[g][ch]; }
                     if (sum_pe_MS <= 1.00 * sum_pe_LR) {
-                        if (sm->frame_bt[0][0] == sm->frame_bt[0][1] && sm->frame_bt[1][0] == sm->frame_bt[1][1]) mode_ext = 2;
+                        if (sm->frame_bt[0][0] == sm->frame_bt[0][1] && sm->frame_bt[mgr - 1][0] == sm->frame_bt[mgr - 1][1]) mode_ext = 2;
                     }
                 }
                 int const off = (mode_ext == 2) ? 2 : 0;
@@ -464,21 +465,21 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                     7.79609e-18 * 5, 0.0467745 * 5, 0.10091 * 5, 0.151365 * 5, 0.187098 * 5 };
                 for (int i = 0; i < 18; i++) st->pefirbuf[i] = st->pefirbuf[i + 1];
                 float f = 0.0f;
-                for (int g = 0; g < 2; g++)
+                for (int g = 0; g < mgr; g++)
                     for (int ch = 0; ch < nch; ch++) f += sm->frame_pe[g][off + ch];
                 st->pefirbuf[18] = f;
                 f = st->pefirbuf[9];
                 for (int i = 0; i < 9; i++) f += (st->pefirbuf[i] + st->pefirbuf[18 - i]) * fircoef[i];
                 f = (670 * 5 * cfg->mode_gr * nch) / f;
                 for (int g = 0; g < 2; g++)
-                    for (int ch = 0; ch < 2; ch++) F->pe_use[g][ch] = (ch < nch) ? sm->frame_pe[g][off + ch] * f : 0.f;
+                    for (int ch = 0; ch < 2; ch++) F->pe_use[g][ch] = (ch < nch && g < mgr) ? sm->frame_pe[g][off + ch] * f : 0.f;
                 F->mode_ext = mode_ext;
                 F->padding = padding;
                 F->ms_ener_ratio[0] = ms_ener_ratio[0];
                 F->ms_ener_ratio[1] = ms_ener_ratio[1];
                 F->ath_adjust_factor = st->ath_adjust_factor;
                 /* quantize.c:2019-2029: masking_lower left behind by the last gr/ch of this frame */
-                st->masking_lower = (cfg->vbr == 4 || sm->frame_bt[1][nch - 1] != LG_SHORT) ? cfg->masking_lower_long : cfg->masking_lower_short;   /* VBR-new: mask_adjust for every block type, quantize.c:1613 */
+                st->masking_lower = (cfg->vbr == 4 || sm->frame_bt[mgr - 1][nch - 1] != LG_SHORT) ? cfg->masking_lower_long : cfg->masking_lower_short;   /* VBR-new: mask_adjust for every block type, quantize.c:1613 */
                 F->masking_lower = st->masking_lower;
                 st->frames_done++;
             }

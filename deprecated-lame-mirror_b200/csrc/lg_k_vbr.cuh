@@ -43,6 +43,9 @@ struct LgVCtx { int mingain_l, mingain_s[3], is_short, guess_only; };
 
 __constant__ uint8_t LG_VRANGE_SHORT[40] = { 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15,
     7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 0, 0, 0, 0 };
+/* vbrquantize.c:579 max_range_long_lsf_pretab: MPEG-2/2.5 with preflag (scalefactor partition table 2) */
+__constant__ uint8_t LG_VRANGE_LONG_LSF[40] = { 7, 7, 7, 7, 7, 7, 3, 3, 3, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 __constant__ uint8_t LG_VRANGE_LONG[40] = { 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 15, 7, 7, 7, 7, 7, 7, 7, 7, 7, 7, 0,
     0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 
@@ -331,11 +334,12 @@ __device__ __noinline__ void lg_valloc(const LgDevCfg *__restrict__ c, LgVWarp *
         for (int sfb = lane; sfb < psymax; sfb += 32) {
             int const d = vbrmax - sfin[sfb];
             int const rng = LG_VRANGE_LONG[sfb], pre = lg_pretab(sfb);
+            int const rngp = (c->mode_gr == 2) ? rng : (int) LG_VRANGE_LONG_LSF[sfb];      /* vbrquantize.c:861 */
             delta = max(delta, d);
             maxover0 = max(maxover0, d - 2 * rng);
             maxover1 = max(maxover1, d - 4 * rng);
-            maxover0p = max(maxover0p, d - 2 * (rng + pre));
-            maxover1p = max(maxover1p, d - 4 * (rng + pre));
+            maxover0p = max(maxover0p, d - 2 * (rngp + pre));
+            maxover1p = max(maxover1p, d - 4 * (rngp + pre));
         }
         delta = lg_wmax_i(delta); maxover0 = lg_wmax_i(maxover0); maxover1 = lg_wmax_i(maxover1);
         maxover0p = lg_wmax_i(maxover0p); maxover1p = lg_wmax_i(maxover1p);
@@ -371,7 +375,7 @@ __device__ __noinline__ void lg_valloc(const LgDevCfg *__restrict__ c, LgVWarp *
         else if (gi.global_gain > 255) gi.global_gain = 255;
         for (int sfb = lane; sfb < 40; sfb += 32) v->sftmp[sfb] = (sfb < LG_SFBMAX) ? sfin[sfb] - vbrmax : 0;
         __syncwarp();
-        lg_vset_scalefacs(v, gi, qc, LG_VRANGE_LONG, lane);
+        lg_vset_scalefacs(v, gi, qc, (c->mode_gr == 2 || !gi.preflag) ? LG_VRANGE_LONG : LG_VRANGE_LONG_LSF, lane);
     }
 }
 
@@ -415,11 +419,11 @@ __device__ __noinline__ int lg_vquantize_count(const LgDevCfg *__restrict__ c, L
 }
 
 /* bitcount (vbrquantize.c:985): scale_bitcount must succeed for scalefactors chosen this way */
-__device__ __forceinline__ void lg_vbitcount(LgVWarp *v, LgQInfo &gi, const LgQConst &qc, int lane)
+__device__ __forceinline__ void lg_vbitcount(const LgDevCfg *__restrict__ c, LgVWarp *v, LgQInfo &gi, const LgQConst &qc, int lane)
 {
-    unsigned const r = lg_scale_bitcount(&v->q, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, lane);
+    unsigned const r = lg_scale_bitcount(&v->q, qc.block_type, qc.sfbmax, qc.sfbdivide, gi.preflag, gi.scalefac_compress, LG_LSF_ARG(c, gi), lane);
     LG_APPLY_SCALE_BITCOUNT(gi, r);
-    if (gi.part2_length == LG_LARGE_BITS) lg_runaway();
+    if ((r >> 30) & 1u) lg_runaway();
 }
 
 /* vbrquantize.c:1141 tryThatOne / :1012 tryGlobalStepsize */
@@ -427,7 +431,7 @@ __device__ __noinline__ int lg_vtry(const LgDevCfg *__restrict__ c, LgVWarp *v, 
                                       const int *sft, int vbrmax, int add_part2, int lane)
 {
     lg_valloc(c, v, gi, qc, ctx, sft, vbrmax, lane);
-    lg_vbitcount(v, gi, qc, lane);
+    lg_vbitcount(c, v, gi, qc, lane);
     int nbits = lg_vquantize_count(c, v, gi, qc, lane);
     if (add_part2) nbits += gi.part2_length;
     return nbits;
@@ -527,12 +531,13 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
     LgQWarp *w = &v->q;
     int resv_size = st->resv_size, main_data_begin = st->main_data_begin;
     int anc_flag = st->ancillary_flag, pay_off = 0;
-    int const active = ch < nch;
+    int const mgr = cfg->mode_gr;                 /* MPEG-2/2.5: one granule per frame, warps 2 and 3 stay idle */
+    int const active = ch < nch && gr < mgr;
     int const my_frames = nfr[stream];
     for (int frame = 0; frame < my_frames; frame++) {
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;
-        int const gb = 2 * frame + gr;
+        int const gb = mgr * frame + (active ? gr : 0);
         const LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
         /* ---- VBR_new_prepare (quantize.c:1582): frame sizes of every bitrate index, bit budget, allowed noise */
         int frameBits[16], avg, resv_max_m, dummy;
@@ -541,7 +546,8 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
         for (int i = 1; i <= c->vbr_max_bitrate_index; i++) frameBits[i] = lg_resv_frame_begin(c, i, padding, resv_size, &dummy, &dummy);
         int const maximum_framebits = frameBits[c->vbr_max_bitrate_index];
         int mb[2][2];
-        for (int g = 0; g < 2; g++) {
+        mb[1][0] = mb[1][1] = 0;
+        for (int g = 0; g < mgr; g++) {
             float pe[2] = { F->pe_use[g][0], F->pe_use[g][1] };
             int tb[2];
             (void) lg_on_pe(c, resv_size, resv_max_m, pe, tb, avg, 0);
@@ -562,11 +568,13 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
             /* quantize.c:226 init_outer_loop */
             qc.block_type = P->block_type[ch];
             qc.psy_lmax = c->sfb21_extra ? LG_SBMAX_L : LG_SBPSY_L;
+            if (c->samplerate <= 8000) { qc.sfb_lmax = 17; qc.sfb_smin = 9; qc.psy_lmax = 17; qc.sfbmax = 17; }       /* quantize.c:252-256 */
             qc.psymax = qc.psy_lmax;
             if (qc.block_type == LG_SHORT) {
                 qc.sfb_smin = 0; qc.sfb_lmax = 0;
                 qc.psymax = 3 * (c->sfb21_extra ? LG_SBMAX_S : LG_SBPSY_S);
                 qc.sfbmax = 3 * LG_SBPSY_S;
+                if (c->samplerate <= 8000) qc.psymax = qc.sfbmax = 3 * 9;                                          /* quantize.c:284-289 */
                 qc.sfbdivide = qc.sfbmax - 18;
                 qc.psy_lmax = 0;
             }
@@ -635,11 +643,11 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
         int analog_silence = 1;
         {
             int bits = 0;
-            for (int g = 0; g < 2; g++) for (int k = 0; k < nch; k++) { bits += mb[g][k]; if (sm->ath_over[g * 2 + k]) analog_silence = 0; }
-            for (int g = 0; g < 2; g++)
+            for (int g = 0; g < mgr; g++) for (int k = 0; k < nch; k++) { bits += mb[g][k]; if (sm->ath_over[g * 2 + k]) analog_silence = 0; }
+            for (int g = 0; g < mgr; g++)
                 for (int k = 0; k < nch; k++)
                     if (bits > maximum_framebits && bits > 0) { mb[g][k] *= maximum_framebits; mb[g][k] /= bits; }
-            for (int g = 0; g < 2; g++) for (int k = 0; k < nch; k++) if (!sm->nonzero[g * 2 + k]) mb[g][k] = 0;
+            for (int g = 0; g < mgr; g++) for (int k = 0; k < nch; k++) if (!sm->nonzero[g * 2 + k]) mb[g][k] = 0;
         }
         if (analog_silence) pad = 0;
         /* ---- VBR_encode_frame (vbrquantize.c:1255): search, fit, quantise "as is" */
@@ -647,7 +655,7 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
         if (active && my_max > 0) {
             int const vbrmax = lg_vblock_sf(c, v, qc, ctx, lane);
             lg_valloc(c, v, gi, qc, ctx, v->vbrsf, vbrmax, lane);
-            lg_vbitcount(v, gi, qc, lane);
+            lg_vbitcount(c, v, gi, qc, lane);
             (void) lg_vquantize_count(c, v, gi, qc, lane);
         }
         /* reduce_bit_usage: granule 1 reads granule 0's scalefactors (scfsi), so the two granules take turns */
@@ -667,19 +675,19 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
         }
         /* ---- the frame's bit budget (vbrquantize.c:1341-1530), computed by every thread alike */
         int use_ch[2][2], use_gr[2] = { 0, 0 }, use_fr = 0, max_fr = 0;
-        for (int g = 0; g < 2; g++) for (int k = 0; k < 2; k++) { use_ch[g][k] = k < nch ? sm->use_bits[g * 2 + k] : 0; use_gr[g] += use_ch[g][k]; if (k < nch) max_fr += mb[g][k]; }
+        for (int g = 0; g < mgr; g++) for (int k = 0; k < 2; k++) { use_ch[g][k] = k < nch ? sm->use_bits[g * 2 + k] : 0; use_gr[g] += use_ch[g][k]; if (k < nch) max_fr += mb[g][k]; }
         use_fr = use_gr[0] + use_gr[1];
         int fits = 0;
         if (use_fr <= max_fr) {
             fits = 1;
-            for (int g = 0; g < 2; g++) {
+            for (int g = 0; g < mgr; g++) {
                 if (use_gr[g] > LG_MAX_BITS_PER_GRANULE) fits = 0;
                 for (int k = 0; k < nch; k++) if (use_ch[g][k] > LG_MAX_BITS_PER_CHANNEL) fits = 0;
             }
         }
         if (!fits) {
             int max_ch[2][2] = { { 0, 0 }, { 0, 0 } }, max_gr[2] = { 0, 0 }, ok = 1, sum_fr = 0;
-            for (int g = 0; g < 2; g++) {
+            for (int g = 0; g < mgr; g++) {
                 max_gr[g] = 0;
                 for (int k = 0; k < nch; k++) {
                     max_ch[g][k] = use_ch[g][k] > LG_MAX_BITS_PER_CHANNEL ? LG_MAX_BITS_PER_CHANNEL : use_ch[g][k];
@@ -706,16 +714,18 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
             if (sum_fr > max_fr) {
                 {
                     float f[2] = { 0.0f, 0.0f }, s = 0.0f;
-                    for (int g = 0; g < 2; g++) {
+                    for (int g = 0; g < mgr; g++) {
                         if (max_gr[g] > 0) { f[g] = (float) sqrt((double) max_gr[g]); s += f[g]; }
                         else f[g] = 0;
                     }
-                    for (int g = 0; g < 2; g++) max_gr[g] = (s > 0) ? (int) (max_fr * f[g] / s) : 0;
+                    for (int g = 0; g < mgr; g++) max_gr[g] = (s > 0) ? (int) (max_fr * f[g] / s) : 0;
                 }
+                if (mgr > 1) {
                 if (max_gr[0] > use_gr[0] + 125) { max_gr[1] += max_gr[0]; max_gr[1] -= use_gr[0] + 125; max_gr[0] = use_gr[0] + 125; }
                 if (max_gr[1] > use_gr[1] + 125) { max_gr[0] += max_gr[1]; max_gr[0] -= use_gr[1] + 125; max_gr[1] = use_gr[1] + 125; }
-                for (int g = 0; g < 2; g++) if (max_gr[g] > LG_MAX_BITS_PER_GRANULE) max_gr[g] = LG_MAX_BITS_PER_GRANULE;
-                for (int g = 0; g < 2; g++) {
+                for (int g = 0; g < mgr; g++) if (max_gr[g] > LG_MAX_BITS_PER_GRANULE) max_gr[g] = LG_MAX_BITS_PER_GRANULE;
+                }
+                for (int g = 0; g < mgr; g++) {
                     float f[2] = { 0.0f, 0.0f }, s = 0.0f;
                     for (int k = 0; k < nch; k++) {
                         if (max_ch[g][k] > 0) { f[k] = (float) sqrt((double) max_ch[g][k]); s += f[k]; }
@@ -730,14 +740,14 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
                 }
             }
             sum_fr = 0;
-            for (int g = 0; g < 2; g++) {
+            for (int g = 0; g < mgr; g++) {
                 int sum_gr = 0;
                 for (int k = 0; k < nch; k++) { sum_gr += max_ch[g][k]; if (max_ch[g][k] > LG_MAX_BITS_PER_CHANNEL) ok = 0; }
                 sum_fr += sum_gr;
                 if (sum_gr > LG_MAX_BITS_PER_GRANULE) ok = 0;
             }
             if (sum_fr > max_fr) ok = 0;
-            if (!ok) for (int g = 0; g < 2; g++) for (int k = 0; k < nch; k++) max_ch[g][k] = mb[g][k];
+            if (!ok) for (int g = 0; g < mgr; g++) for (int k = 0; k < nch; k++) max_ch[g][k] = mb[g][k];
             /* best_scalefac_store already ran once: reset what it left behind, then re-quantise until it fits */
             for (int i = 0; i < 4; i++) scfsi[i] = 0;
             gi.scalefac_compress = 0;
@@ -761,7 +771,7 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
                 __syncthreads();
             }
             use_fr = 0;
-            for (int g = 0; g < 2; g++) for (int k = 0; k < nch; k++) use_fr += sm->use_bits[g * 2 + k];
+            for (int g = 0; g < mgr; g++) for (int k = 0; k < nch; k++) use_fr += sm->use_bits[g * 2 + k];
         }
         int const used_bits = use_fr;
         /* ---- hand the granule to the bit packer */
@@ -779,12 +789,13 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
                 o->part2_3_length = (int16_t) gi.part2_3_length; o->part2_length = (int16_t) gi.part2_length;
                 o->big_values = (int16_t) gi.big_values; o->count1 = (int16_t) gi.count1;
                 o->global_gain = (uint8_t) gi.global_gain; o->scalefac_compress = (uint8_t) gi.scalefac_compress;
+                o->scalefac_compress_hi = (uint8_t) (gi.scalefac_compress >> 8);
                 o->block_type = (uint8_t) qc.block_type; o->mixed_block_flag = 0;
                 for (int i = 0; i < 3; i++) { o->table_select[i] = (uint8_t) gi.table_select[i]; o->subblock_gain[i] = (uint8_t) ((gi.sbg >> (4 * i)) & 15); }
                 o->region0_count = (uint8_t) gi.region0_count; o->region1_count = (uint8_t) gi.region1_count;
                 o->preflag = (uint8_t) gi.preflag; o->scalefac_scale = (uint8_t) gi.scalefac_scale;
                 o->count1table_select = (uint8_t) gi.count1table_select;
-                o->sfbmax = (uint8_t) qc.sfbmax; o->sfbdivide = (uint8_t) qc.sfbdivide; o->pad_ = 0;
+                o->sfbmax = (uint8_t) qc.sfbmax; o->sfbdivide = (uint8_t) qc.sfbdivide;
             }
             if (lane == 0 && gr == 1) for (int i = 0; i < 4; i++) sm->scfsi[ch][i] = scfsi[i];
         }

@@ -717,7 +717,6 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
     for (i = 0; i < 3; i++) for (j = 0; j < 3; j++) if (samplerate == LGT_SAMPLERATE[4 * i + j]) { sr_index = j; version = (i == 1) ? 1 : 0; }
     if (sr_index < 0) return -1;
     brow = (version == 1) ? 1 : (samplerate < 16000 ? 2 : 0);          /* row of bitrate_table: MPEG-2, MPEG-1, MPEG-2.5 */
-    if (version != 1 && !getenv("LAMEGPU_LSF")) return -1;            /* MPEG-2/2.5 device path: work in progress */
     if (vbr == 0) {
         /* util.c:320 FindNearestBitrate on that row (lame.c:905-915) */
         best = LGT_BITRATE[16 * brow + 1];

@@ -153,7 +153,8 @@ typedef struct {
     int16_t part2_3_length, part2_length, big_values, count1;
     uint8_t global_gain, scalefac_compress, block_type, mixed_block_flag;
     uint8_t table_select[3], subblock_gain[3];
-    uint8_t region0_count, region1_count, preflag, scalefac_scale, count1table_select, sfbmax, sfbdivide, pad_;
+    uint8_t region0_count, region1_count, preflag, scalefac_scale, count1table_select, sfbmax, sfbdivide;
+    uint8_t scalefac_compress_hi;        /* MPEG-2/2.5: scalefac_compress has 9 bits (takehiro.c:1281) */
 } __attribute__((aligned(16))) LgGranuleOut;
 
 typedef struct {

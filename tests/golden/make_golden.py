@@ -35,6 +35,10 @@ CASES = [
     ("sine_96_44k_auto32k", "sine", 20, 44100, 96, -1, -1),
     ("noise_112_48k_auto44k", "noise", 16, 48000, 112, -1, -1),
     ("gap_160_37800_to_48k", "gap", 16, 37800, 160, -1, -1, 48000),
+    # MPEG-2 (22.05 kHz input; 64 kbps at 44.1 kHz -> 24 kHz) and MPEG-2.5 (8 kHz, mono): one granule per frame, LSF scalefactors
+    ("click_64_22k", "click", 20, 22050, 64, -1, -1),
+    ("sine_64_44k_auto24k", "sine", 20, 44100, 64, -1, -1),
+    ("noise_16_8k_mono", "noise", 12, 8000, 16, 3, -1),
 ]
 
 

@@ -71,6 +71,19 @@ def test_emulated_quality_0_to_2_matches_port(emu_bin, args, env):
     assert "IDENTICAL" in r.stdout
 
 
+@pytest.mark.parametrize("args,env", [
+    ("3 10 4 64 -1 -1 22050 1152", {}), ("3 12 4 32 -1 -1 16000 777", {}), ("3 12 4 24 -1 -1 8000 1152", {}), ("3 12 4 32 3 -1 11025 1152", {}),
+    ("3 12 4 64 -1 -1 44100 1152", {}), ("3 12 4 80 1 2 22050 1152", {}), ("3 12 4 64 -1 -1 22050 1152", dict(LP_VBR="3")),
+    ("3 10 4 4 -1 -1 22050 1152", dict(LP_VBR="4")), ("3 10 4 9 -1 -1 44100 777", dict(LP_VBR="4")), ("3 10 4 5 -1 -1 8000 1152", dict(LP_VBR="4")),
+])
+def test_emulated_mpeg2_matches_port(emu_bin, args, env):
+    """MPEG-2 / MPEG-2.5 output through all kernels: one granule per frame in B, D, D', E; LSF scalefactor partitions
+    (lg_scale_bitcount_lsf), LSF side info and scalefactor packing in kernel E, the 8 kHz band limits; CBR, ABR, VBR"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout
+
+
 TAG_SCRIPT = r"""
 import json, os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))

@@ -162,7 +162,9 @@ def test_resampled_batch_matches_oracle(lib, oracle_mod, cfg):
 
 
 @pytest.mark.parametrize("kw", [dict(samplerate=48000, brate=128, out_samplerate=44100), dict(samplerate=44100, brate=7, vbr=4),
-                                dict(samplerate=44100, brate=4.6, vbr=4), dict(samplerate=44100, brate=96, quality=1)])
+                                dict(samplerate=44100, brate=4.6, vbr=4), dict(samplerate=44100, brate=96, quality=1),
+                                dict(samplerate=22050, brate=64), dict(samplerate=44100, brate=9, vbr=4), dict(samplerate=8000, brate=16, mode=3),
+                                dict(samplerate=24000, brate=80, vbr=3)])
 def test_resampled_lame_api_with_tag(lib, oracle_mod, kw):
     """the lame.h face with lame_set_out_samplerate / -V7 / a fractional level / quality 1, and the Info tag: source-rate field,
     encoder padding, quality and preset fields of the tag (VbrTag.c:775, lame.c:2083-2091)"""
@@ -183,7 +185,8 @@ def test_resampled_lame_api_with_tag(lib, oracle_mod, kw):
     r.close()
 
 
-@pytest.mark.parametrize("kw", [dict(brate=128), dict(brate=2, vbr=4), dict(brate=150, vbr=3), dict(brate=192, mode=0), dict(brate=96, mode=3)])
+@pytest.mark.parametrize("kw", [dict(brate=128), dict(brate=2, vbr=4), dict(brate=150, vbr=3), dict(brate=192, mode=0), dict(brate=96, mode=3),
+                                dict(brate=64), dict(brate=9, vbr=4)])
 def test_statistics_match_reference(lib, oracle_mod, kw):
     """lame_bitrate_hist / lame_stereo_mode_hist / lame_block_type_hist and the per-bitrate tables (lame.h:909-929, encoder.c:156):
     the host keeps them from what the device reports per frame; equal to the reference's after the same stream"""
@@ -202,6 +205,44 @@ def test_statistics_match_reference(lib, oracle_mod, kw):
     assert ours["lame_block_type_hist"][2] > 0        # the click stream has short blocks
     e.close()
     r.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(S=8, F=24, fpl=8, sr=22050, brate=64), dict(S=4, F=24, fpl=4, sr=16000, brate=32, chunk=777), dict(S=4, F=24, fpl=8, sr=24000, brate=160, mode=0),
+    dict(S=4, F=24, fpl=4, sr=8000, brate=24), dict(S=4, F=24, fpl=4, sr=11025, brate=32, mode=3), dict(S=4, F=24, fpl=4, sr=12000, brate=8, mode=3, chunk=500),
+    dict(S=8, F=20, fpl=8, sr=44100, brate=64), dict(S=4, F=20, fpl=4, sr=22050, brate=80, mode=1, q=2), dict(S=4, F=20, fpl=4, sr=16000, brate=56, q=0),
+    dict(S=4, F=20, fpl=8, sr=22050, brate=64, vbr=3), dict(S=4, F=20, fpl=4, sr=8000, brate=24, vbr=3),
+    dict(S=8, F=20, fpl=8, sr=22050, brate=4, vbr=4), dict(S=4, F=20, fpl=4, sr=44100, brate=8, vbr=4), dict(S=4, F=20, fpl=4, sr=44100, brate=9, vbr=4, chunk=777),
+    dict(S=4, F=20, fpl=4, sr=16000, brate=2, vbr=4), dict(S=4, F=20, fpl=4, sr=8000, brate=5, vbr=4), dict(S=4, F=20, fpl=4, sr=48000, brate=9.5, vbr=4),
+    dict(S=4, F=20, fpl=4, sr=44100, brate=48, out=16000, chunk=3000),
+])
+def test_mpeg2_batch_matches_oracle(lib, oracle_mod, cfg):
+    """MPEG-2 (16 / 22.05 / 24 kHz) and MPEG-2.5 (8 / 11.025 / 12 kHz) output, native or through the resampler (64 kbps at
+    44.1 kHz -> 24 kHz, -V8, -V9): one granule per frame, LSF scalefactor partitions and side info; CBR, ABR, VBR, quality 0 and 2;
+    byte-identical to the port and to libmp3lame"""
+    S, F, sr, brate, chunk = cfg["S"], cfg["F"], cfg["sr"], cfg["brate"], cfg.get("chunk", 1152 * 4)
+    mode, vbr, q, out = cfg.get("mode", -1), cfg.get("vbr", 0), cfg.get("q", -1), cfg.get("out", 0)
+    kinds = ("noise", "click", "sine", "gap")
+    pcm = np.stack([make_signal(kinds[s % 4], F * 1152, seed=120 + s) for s in range(S)])
+    enc = lib.BatchEncoder(S, sr, 2, brate, mode, q, frames_per_launch=cfg["fpl"], vbr=vbr, out_samplerate=out)
+    got = [b""] * S
+    for pos in range(0, F * 1152, chunk):
+        _, o = enc.encode(pcm[:, :, pos:pos + chunk])
+        got = [g + x for g, x in zip(got, o)]
+    _, o = enc.flush()
+    got = [g + x for g, x in zip(got, o)]
+    enc.close()
+    for s in range(S):
+        encs = [oracle_mod.PortEncoder(sr, 2, brate, mode, q, vbr=vbr, out_samplerate=out)]
+        if oracle_mod.have_ref():
+            encs.append(oracle_mod.RefEncoder(sr, 2, brate, mode if mode >= 0 else 4, q, vbr=vbr, out_samplerate=out))
+        for e in encs:
+            want = b""
+            for pos in range(0, F * 1152, chunk):
+                want += e.encode(pcm[s, 0, pos:pos + chunk], pcm[s, 1, pos:pos + chunk])
+            want += e.flush()
+            e.close()
+            assert got[s] == want, "stream %d (%s) vs %s" % (s, kinds[s % 4], type(e).__name__)
 
 
 def test_config4_vbr_v2_full_size(lib, oracle_mod):
@@ -301,7 +342,7 @@ def test_edge_cases(lib, oracle_mod):
 
 
 def test_unsupported_configurations_fail_loudly(lib):
-    for kw in (dict(samplerate=22050), dict(brate=64), dict(out_samplerate=24000), dict(brate=8, vbr=4)):
+    for kw in (dict(out_samplerate=20000), dict(mode=2), dict(brate=10, vbr=4), dict(samplerate=0)):
         with pytest.raises(lib.LameGpuError):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()
