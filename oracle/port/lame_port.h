@@ -158,6 +158,7 @@ int   lp_psycho(lp_encoder *e, const float *const buffer[2], int gr_out, lp_rati
 void  lp_mdct_sub48(lp_encoder *e, const float *w0, const float *w1);
 void  lp_cbr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
 void  lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
+void  lp_vbr_old_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
 void  lp_vbr_new_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2]);
 int   lp_getframebits(const lp_encoder *e);
 void  lp_format_bitstream(lp_encoder *e);

@@ -175,6 +175,7 @@ static int encode_frame(lp_encoder *e, const float *inbuf_l, const float *inbuf_
     memcpy(e->last_pe, pe_use, sizeof e->last_pe);
     if (cfg->vbr == 3) lp_abr_iteration_loop(e, pe_use, ms_ener_ratio, masking);      /* encoder.c:520-538 */
     else if (cfg->vbr == 4) lp_vbr_new_iteration_loop(e, pe_use, ms_ener_ratio, masking);
+    else if (cfg->vbr == 2) lp_vbr_old_iteration_loop(e, pe_use, ms_ener_ratio, masking);
     else lp_cbr_iteration_loop(e, pe_use, ms_ener_ratio, masking);
     lp_format_bitstream(e);
     mp3count = lp_copy_buffer(e, out, cap);

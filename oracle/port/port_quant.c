@@ -1086,6 +1086,9 @@ static int balance_noise(const lp_config *c, lp_granule *gi, const float *distor
     return !status;
 }
 
+/* VBR-old switches sfb21_extra off for the tries near the bit limit (quantize.c:1265-1268): -1 = the configuration's value */
+static __thread int sfb21_now = -1;
+
 /* quantize.c:1010 outer_loop */
 static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float xrpow[576], int ch, int targ_bits)
 {
@@ -1110,7 +1113,7 @@ static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float
             noise_result noise_info;
             int const search_limit = (cfg->substep_shaping & 2) ? 20 : 3;
             int maxggain = 255;
-            if (cfg->sfb21_extra) {
+            if (sfb21_now >= 0 ? sfb21_now : cfg->sfb21_extra) {
                 if (distort[gi_w.sfbmax] > 1.0) break;
                 if (gi_w.block_type == LP_SHORT && (distort[gi_w.sfbmax + 1] > 1.0 || distort[gi_w.sfbmax + 2] > 1.0)) break;
             }
@@ -1157,6 +1160,7 @@ static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float
         }
         else bEndOfSearch = 1;
     }
+    if (cfg->vbr == 2) memcpy(xrpow, save_xrpow, sizeof(float) * 576);     /* quantize.c:1188: restore for the next try */
     return best_noise_info.over_count;
 }
 
@@ -1291,6 +1295,162 @@ void lp_abr_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ra
     /* the smallest frame that brings the reservoir back to a non-negative size */
     for (e->bitrate_index = cfg->vbr_min_bitrate_index; e->bitrate_index <= cfg->vbr_max_bitrate_index; e->bitrate_index++)
         if (resv_frame_begin(e, &mean_bits) >= 0) break;
+    resv_frame_end(e, mean_bits);
+}
+
+/* quantize.c:160 psfb21_analogsilence (vbr_rh only, the tail of init_outer_loop :342): from the top of the spectrum down, lines
+ * of the six sub-bands of sfb21 (sfb12 of every window for short blocks) below the ATH become zero, until one is not */
+static void psfb21_analog_silence(const lp_encoder *e, lp_granule *gi)
+{
+    const lp_config *cfg = &e->cfg;
+    float *xr = gi->xr;
+    int gsfb, j, block, stop = 0;
+    if (gi->block_type != LP_SHORT) {
+        for (gsfb = 6 - 1; gsfb >= 0 && !stop; gsfb--) {
+            int const start = cfg->psfb21[gsfb], end = cfg->psfb21[gsfb + 1];
+            float ath21 = ath_adjust(cfg, e->ath_adjust_factor, cfg->ath_psfb21[gsfb], cfg->ath_floor, 0);
+            if (cfg->longfact[21] > 1e-12f) ath21 *= cfg->longfact[21];
+            for (j = end - 1; j >= start; j--) {
+                if (fabs(xr[j]) < ath21) xr[j] = 0;
+                else { stop = 1; break; }
+            }
+        }
+        return;
+    }
+    for (block = 0; block < 3; block++) {
+        stop = 0;
+        for (gsfb = 6 - 1; gsfb >= 0 && !stop; gsfb--) {
+            int const start = cfg->sfb_s[12] * 3 + (cfg->sfb_s[13] - cfg->sfb_s[12]) * block + (cfg->psfb12[gsfb] - cfg->psfb12[0]);
+            int const end = start + (cfg->psfb12[gsfb + 1] - cfg->psfb12[gsfb]);
+            float ath12 = ath_adjust(cfg, e->ath_adjust_factor, cfg->ath_psfb12[gsfb], cfg->ath_floor, 0);
+            if (cfg->shortfact[12] > 1e-12f) ath12 *= cfg->shortfact[12];
+            for (j = end - 1; j >= start; j--) {
+                if (fabs(xr[j]) < ath12) xr[j] = 0;
+                else { stop = 1; break; }
+            }
+        }
+    }
+}
+
+/* quantize.c:1246 VBR_encode_granule: bisection on the bit budget of one gr.ch - the smallest number of bits (within 32)
+ * at which outer_loop leaves no band distorted */
+static void vbr_old_encode_granule(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float xrpow[576], int ch, int min_bits, int max_bits)
+{
+    static __thread lp_granule bst;
+    float bst_xrpow[576];
+    int const Max_bits = max_bits;
+    int real_bits = max_bits + 1, this_bits = (max_bits + min_bits) / 2, dbits, over, found = 0;
+    memset(bst.l3_enc, 0, sizeof bst.l3_enc);
+    do {
+        sfb21_now = (this_bits > Max_bits - 42) ? 0 : e->cfg.sfb21_extra;
+        over = outer_loop(e, gi, l3_xmin, xrpow, ch, this_bits);
+        if (over <= 0) {
+            found = 1;
+            real_bits = gi->part2_3_length;
+            bst = *gi;
+            memcpy(bst_xrpow, xrpow, sizeof(float) * 576);
+            max_bits = real_bits - 32;
+            dbits = max_bits - min_bits;
+            this_bits = (max_bits + min_bits) / 2;
+        }
+        else {
+            min_bits = this_bits + 32;
+            dbits = max_bits - min_bits;
+            this_bits = (max_bits + min_bits) / 2;
+            if (found) {
+                found = 2;
+                *gi = bst;
+                memcpy(xrpow, bst_xrpow, sizeof(float) * 576);
+            }
+        }
+    } while (dbits > 12);
+    sfb21_now = -1;
+    if (found == 2) memcpy(gi->l3_enc, bst.l3_enc, sizeof(int) * 576);
+}
+
+/* quantize.c:1491 VBR_old_iteration_loop (+ :1370 VBR_old_prepare, :1326 get_framebits, :1455 bitpressure_strategy) */
+void lp_vbr_old_iteration_loop(lp_encoder *e, float pe[2][2], const float ms_ener_ratio[2], lp_ratio ratio[2][2])
+{
+    const lp_config *cfg = &e->cfg;
+    float l3_xmin[2][2][LP_SFBMAX], xrpow[576], adjust, masking_lower_db;
+    int frameBits[16], min_bits[2][2], max_bits[2][2], bands[2][2], used_bits, bits = 0, mean_bits, gr, ch, i, sfb, analog_silence = 1, avg, mxb, dummy;
+    /* prepare */
+    e->bitrate_index = cfg->vbr_max_bitrate_index;
+    avg = resv_frame_begin(e, &avg) / cfg->mode_gr;
+    for (i = 1; i <= cfg->vbr_max_bitrate_index; i++) { e->bitrate_index = i; frameBits[i] = resv_frame_begin(e, &dummy); }
+    for (gr = 0; gr < cfg->mode_gr; gr++) {
+        mxb = on_pe(e, pe, max_bits[gr], avg, gr, 0);
+        if (e->mode_ext == 2) {
+            for (i = 0; i < 576; ++i) {
+                float l = e->tt[gr][0].xr[i], r = e->tt[gr][1].xr[i];
+                e->tt[gr][0].xr[i] = (l + r) * (float) (SQRT2_D * 0.5);
+                e->tt[gr][1].xr[i] = (l - r) * (float) (SQRT2_D * 0.5);
+            }
+            reduce_side(max_bits[gr], ms_ener_ratio[gr], avg, mxb);
+        }
+        for (ch = 0; ch < cfg->channels; ++ch) {
+            lp_granule *gi = &e->tt[gr][ch];
+            if (gi->block_type != LP_SHORT) {
+                adjust = 1.28 / (1 + exp(3.5 - pe[gr][ch] / 300.)) - 0.05;
+                masking_lower_db = cfg->mask_adjust - adjust;
+            }
+            else {
+                adjust = 2.56 / (1 + exp(3.5 - pe[gr][ch] / 300.)) - 0.14;
+                masking_lower_db = cfg->mask_adjust_short - adjust;
+            }
+            e->masking_lower = pow(10.0, masking_lower_db * 0.1);
+            init_outer_loop(cfg, gi);
+            psfb21_analog_silence(e, gi);
+            bands[gr][ch] = calc_xmin(e, &ratio[gr][ch], gi, l3_xmin[gr][ch]);
+            if (bands[gr][ch]) analog_silence = 0;
+            min_bits[gr][ch] = 126;
+            bits += max_bits[gr][ch];
+        }
+    }
+    for (gr = 0; gr < cfg->mode_gr; gr++)
+        for (ch = 0; ch < cfg->channels; ch++) {
+            if (bits > frameBits[cfg->vbr_max_bitrate_index] && bits > 0) {
+                max_bits[gr][ch] *= frameBits[cfg->vbr_max_bitrate_index];
+                max_bits[gr][ch] /= bits;
+            }
+            if (min_bits[gr][ch] > max_bits[gr][ch]) min_bits[gr][ch] = max_bits[gr][ch];
+        }
+    for (;;) {
+        used_bits = 0;
+        for (gr = 0; gr < cfg->mode_gr; gr++)
+            for (ch = 0; ch < cfg->channels; ch++) {
+                lp_granule *gi = &e->tt[gr][ch];
+                int const ret = init_xrpow(cfg, gi, xrpow);
+                if (ret == 0 || max_bits[gr][ch] == 0) continue;
+                vbr_old_encode_granule(e, gi, l3_xmin[gr][ch], xrpow, ch, min_bits[gr][ch], max_bits[gr][ch]);
+                used_bits += gi->part2_3_length + gi->part2_length;
+            }
+        e->bitrate_index = analog_silence ? 1 : cfg->vbr_min_bitrate_index;
+        for (; e->bitrate_index < cfg->vbr_max_bitrate_index; e->bitrate_index++) if (used_bits <= frameBits[e->bitrate_index]) break;
+        bits = resv_frame_begin(e, &mean_bits);
+        if (used_bits <= bits) break;
+        /* bitpressure_strategy: allow more noise towards the high bands and shrink the budgets */
+        for (gr = 0; gr < cfg->mode_gr; gr++)
+            for (ch = 0; ch < cfg->channels; ch++) {
+                const lp_granule *gi = &e->tt[gr][ch];
+                float *pxmin = l3_xmin[gr][ch];
+                for (sfb = 0; sfb < gi->psy_lmax; sfb++) *pxmin++ *= 1. + .029 * sfb * sfb / LP_SBMAX_L / LP_SBMAX_L;
+                if (gi->block_type == LP_SHORT)
+                    for (sfb = gi->sfb_smin; sfb < LP_SBMAX_S; sfb++) {
+                        *pxmin++ *= 1. + .029 * sfb * sfb / LP_SBMAX_S / LP_SBMAX_S;
+                        *pxmin++ *= 1. + .029 * sfb * sfb / LP_SBMAX_S / LP_SBMAX_S;
+                        *pxmin++ *= 1. + .029 * sfb * sfb / LP_SBMAX_S / LP_SBMAX_S;
+                    }
+                max_bits[gr][ch] = min_bits[gr][ch] > 0.9 * max_bits[gr][ch] ? min_bits[gr][ch] : 0.9 * max_bits[gr][ch];
+            }
+    }
+    for (gr = 0; gr < cfg->mode_gr; gr++)
+        for (ch = 0; ch < cfg->channels; ch++) {
+            lp_granule *gi = &e->tt[gr][ch];
+            best_scalefac_store(e, gr, ch);
+            if (cfg->use_best_huffman == 1) best_huffman_divide(cfg, gi);
+            e->resv_size -= gi->part2_3_length + gi->part2_length;
+        }
     resv_frame_end(e, mean_bits);
 }
 

@@ -629,7 +629,16 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         {4.20, 25.0, -2.6, -2.6, 3.7, 2.0, -3, 0, 2, 23, 1.288, 5, 97}, {4.20, 25.0, -1.6, -1.6, 2.0, 2.0, -5, 0, 2, 18, 1.479, 5, 96},
         {4.20, 25.0, -0.0, -0.0, 0.0, 2.0, -8, 0, 2, 12, 1.698, 5, 95}, {4.20, 25.0, 1.3, 1.3, -6, 3.5, -11, 0, 2, 8, 1.950, 5, 94.2},
         {4.50, 100.0, 2.2, 2.3, -12.0, 6.0, -14, 0, 2, 4, 2.239, 3, 93.9}, {4.80, 200.0, 2.7, 2.7, -18.0, 9.0, -17, 0, 2, 0, 2.570, 1, 93.6},
-        {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} };
+        {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} },
+    /* presets.c:88 vbr_old_switch_map (vbr_rh), same columns, levels 0..10 */
+    vo[11] = {
+        {5.20, 125.0, -4.2, -6.3, 4.8, 1, 0, 0, 2, 21, 0.97, 5, 100}, {5.30, 125.0, -3.6, -5.6, 4.5, 1.5, 0, 0, 2, 21, 1.35, 5, 100},
+        {5.60, 125.0, -2.2, -3.5, 2.8, 2, 0, 0, 2, 21, 1.49, 5, 100}, {5.80, 130.0, -1.8, -2.8, 2.6, 3, -4, 0, 2, 20, 1.64, 5, 100},
+        {6.00, 135.0, -0.7, -1.1, 1.1, 3.5, -8, 0, 2, 0, 1.79, 5, 100}, {6.40, 140.0, 0.5, 0.4, -7.5, 4, -12, 0.0002, 0, 0, 1.95, 5, 100},
+        {6.60, 145.0, 0.67, 0.65, -14.7, 6.5, -19, 0.0004, 0, 0, 2.30, 5, 100}, {6.60, 145.0, 0.8, 0.75, -19.7, 8, -22, 0.0006, 0, 0, 2.70, 5, 100},
+        {6.60, 145.0, 1.2, 1.15, -27.5, 10, -23, 0.0007, 0, 0, 0, 5, 100}, {6.60, 145.0, 1.6, 1.6, -36, 11, -25, 0.0008, 0, 0, 0, 5, 100},
+        {6.60, 145.0, 2.0, 2.0, -36, 12, -25, 0.0008, 0, 0, 0, 5, 100} };
+    static const int vbr_old_lowpass[11] = { 19500, 19000, 18600, 18000, 17500, 16000, 15600, 14900, 12500, 10000, 3950 };
     static const int vbr_lowpass[11] = { 24000, 19500, 18500, 18000, 17500, 17000, 16500, 15600, 15200, 7230, 3950 };
     int i, j, r, exp_nspsytune = 0, version = 1, best, sr_index, vbr_q = 0, brow = 1;
     int vbr_no_lowpass = 0;
@@ -645,7 +654,12 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     if (channels == 1) mode = LP_MONO;                                 /* lame.c:597 */
     if (mode == LP_MONO) c->channels = 1;
     c->force_ms = 0;
-    if (vbr != 0 && vbr != 3 && vbr != 4) return -1;                  /* vbr_off, vbr_abr, vbr_mtrh */
+    if (vbr != 0 && vbr != 2 && vbr != 3 && vbr != 4) return -1;                  /* vbr_off, vbr_abr, vbr_mtrh */
+    if (vbr == 2) {                                                    /* vbr_rh: `brate` carries VBR_q, no mapping to other rates */
+        vbr_q = brate;
+        if (vbr_q < 0 || vbr_q > 9 || !(vbr_q_frac >= 0.f && vbr_q_frac < 1.f)) return -1;
+        brate = 128;
+    }
     if (vbr == 4) {
         /* `brate` carries VBR_q.  Levels 7..9 make lame_init_params pick a lower output rate at these input rates
          * (lame.c:661-698), which needs the resampler */
@@ -680,7 +694,7 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         }
         brate = 128;                                                   /* gfp->brate stays unused; keeps the arithmetic below defined */
     }
-    if (vbr == 4) { }
+    if (vbr == 4 || vbr == 2) { }
     else if (vbr == 3) {
         /* ABR keeps the requested mean bitrate as it is (lame_set_VBR_mean_bitrate_kbps, default 128), clamped for
          * MPEG-1 rates (lame.c:655-658 and :1088-1093 with the default index range 1..14) */
@@ -703,6 +717,10 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
         double const a = vbr_lowpass[vbr_q], b = vbr_lowpass[vbr_q + 1], m = vbr_q_frac;
         lowpass = a + m * (b - a);
         if (vbr_no_lowpass) lowpass = -1;
+    }
+    else if (vbr == 2) {                                               /* lame.c:717-728 */
+        double const a = vbr_old_lowpass[vbr_q], b = vbr_old_lowpass[vbr_q + 1], m = vbr_q_frac;
+        lowpass = a + m * (b - a);
     }
     else if (mode == LP_MONO) lowpass *= 1.5;
     c->lowpassfreq = lowpass;
@@ -755,7 +773,7 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     c->vbr_max_bitrate_index = samplerate < 16000 ? 8 : 14;            /* 64 kbps with MPEG-2.5 */
     c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * brate);   /* lame.c:778-784 */
     c->vbr_q = vbr_q;
-    c->vbr_q_frac = (vbr == 4) ? vbr_q_frac : 0.f;
+    c->vbr_q_frac = (vbr == 4 || vbr == 2) ? vbr_q_frac : 0.f;
     if (vbr != 0) c->bitrate_index = 1;                                /* lame.c:921 */
     else {
         c->bitrate_index = -1;
@@ -773,17 +791,18 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     else c->sideinfo_len = (c->channels == 1) ? 4 + 9 : 4 + 17;
     c->original = 1;
 
-    if (vbr == 4) {
-        /* lame.c:975-1003 + presets.c:143 apply_vbr_preset(VBR_q) with every option still at its default */
+    if (vbr == 4 || vbr == 2) {
+        /* lame.c:975-1029 + presets.c:143 apply_vbr_preset(VBR_q) with every option still at its default */
         c->noise_shaping = 0;
         c->quant_comp = 9;
         c->quant_comp_short = 9;
         {   /* presets.c:143-161: every float column moves towards the next level by VBR_q_frac, sfb21mod does so as an int */
             float const x = vbr_q_frac;
             int const n = vbr_q + 1;
-            int sfb21mod = vm[vbr_q].sfb21mod;
-            if (vbr_q > 8) return -1;                                   /* the table row of level 10 is not carried here */
-#define VLERP(f) (vm[vbr_q].f + x * (vm[n].f - vm[vbr_q].f))
+#define VP(i) (vbr == 4 ? vm[i] : vo[i])
+            int sfb21mod = VP(vbr_q).sfb21mod;
+            if (vbr == 4 && vbr_q > 8) return -1;                       /* the table row of level 10 is not carried for vbr_mtrh (never reached: -V9 is remapped) */
+#define VLERP(f) (VP(vbr_q).f + x * (VP(n).f - VP(vbr_q).f))
             attackthre = VLERP(st_lrm);
             attackthre_s = VLERP(st_s);
             maskingadjust = VLERP(madj);
@@ -793,17 +812,24 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
             athaa_sensitivity = VLERP(ath_sens);
             c->interch = VLERP(interch);
             if (!(c->interch > 0)) c->interch = 0;
-            sfb21mod = sfb21mod + x * (vm[n].sfb21mod - sfb21mod);
+            sfb21mod = sfb21mod + x * (VP(n).sfb21mod - sfb21mod);
             c->msfix = VLERP(msfix);
             c->minval = VLERP(minval);
             c->athfixpoint = VLERP(ath_fixpoint);
 #undef VLERP
-            if (vm[vbr_q].safejoint > 0) exp_nspsytune |= 2;
+            if (VP(vbr_q).safejoint > 0) exp_nspsytune |= 2;
+#undef VP
             if (sfb21mod > 0) exp_nspsytune |= sfb21mod << 20;
         }
+        if (vbr == 2) {                                                 /* lame.c:1006-1029: at least level 6 */
+            if (quality > 6) quality = 6;
+            if (quality < 0) quality = 3;
+        }
+        else {
         if (quality < 0) quality = 3;
         if (quality < 5) quality = 0;
         if (quality > 7) quality = 7;
+        }
         c->sfb21_extra = (vbr_q >= 3) ? 0 : (samplerate > 44000);     /* experimentalY from the preset, lame.c:996-999 */
         goto presets_done;
     }
@@ -862,7 +888,7 @@ presets_done:
     }
     c->frac_spf = (vbr == 0) ? ((version + 1) * 72000L * brate) % samplerate : 0;      /* lame.c:1245 */
     setup_quantizer_tables(c);
-    setup_psy(c, attackthre, attackthre_s, vbr == 4 ? vbr_q : 4, vbr == 4 ? vbr_q_frac : 0.f);
+    setup_psy(c, attackthre, attackthre_s, (vbr == 4 || vbr == 2) ? vbr_q : 4, (vbr == 4 || vbr == 2) ? vbr_q_frac : 0.f);
     c->buffer_constraint = 7680 * (version + 1);                       /* bitstream.c:119 MDB_MAXIMUM */
     return 0;
 }

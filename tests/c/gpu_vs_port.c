@@ -52,7 +52,7 @@ int main(int argc, char **argv)
     { float ms[4]; lamegpu_batch_kernel_ms(b, ms); printf("last launch kernel ms: analysis %.3f scan %.3f mdct %.3f quant %.3f\n", ms[0], ms[1], ms[2], ms[3]); }
     lamegpu_batch_close(b);
     for (s = 0; s < S; s++) {
-        lp_encoder *e = lp_open_vq(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr, vbr == 4 ? ((float) brate + qfrac) - (float) brate : 0.f);
+        lp_encoder *e = lp_open_vq(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr, (vbr == 4 || vbr == 2) ? ((float) brate + qfrac) - (float) brate : 0.f);
         int k;
         if (!e) { printf("port open failed\n"); return 2; }
         /* same call pattern as above: with resampling the reference's state depends on where the calls end */

@@ -46,9 +46,9 @@ int main(int argc, char **argv)
     int const out_sr = getenv("LP_OUT_SR") ? atoi(getenv("LP_OUT_SR")) : 0; /* explicit output rate (lame_set_out_samplerate), 0 = automatic */
     int const chunk = getenv("LP_CHUNK") ? atoi(getenv("LP_CHUNK")) : 1152;  /* samples per encode call: the resampler's state depends on it */
     float const qfrac = getenv("LP_VBRQ_FRAC") ? (float) atof(getenv("LP_VBRQ_FRAC")) : 0.f;  /* VBR quality = brate + this (lame_set_VBR_quality) */
-    h = refdump_open_vq(brate, mode, quality, vbr, vbr == 4 ? brate : 0, qfrac, sr, out_sr, 2);   /* vbr 4 (vbr_mtrh): `brate` is VBR_q */
+    h = refdump_open_vq(brate, mode, quality, vbr, (vbr == 4 || vbr == 2) ? brate : 0, qfrac, sr, out_sr, 2);   /* vbr 4 (vbr_mtrh): `brate` is VBR_q */
     /* the same split of the float level as lame_set_VBR_quality (set_get.c:1169) */
-    e = lp_open_vq(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr, vbr == 4 ? ((float) brate + qfrac) - (float) brate : 0.f);
+    e = lp_open_vq(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr, (vbr == 4 || vbr == 2) ? ((float) brate + qfrac) - (float) brate : 0.f);
     if (!h || !e) { printf("open failed ref=%p port=%p\n", h, (void *) e); return (!h && !e) ? 0 : 2; }
     refdump_tables(h, &tab);
     {

@@ -41,8 +41,8 @@ def test_port_chunking_invariance(oracle_mod):
 
 
 def test_port_rejects_unsupported(oracle_mod):
-    # not an MPEG rate, dual channel, VBR level out of range, VBR-new with quality 7+ is fine but vbr_rh is not a mode of the port
-    for kw in (dict(out_samplerate=20000), dict(mode=2), dict(brate=10, vbr=4), dict(vbr=2)):
+    # not an MPEG rate, dual channel, VBR level out of range, not a vbr_mode
+    for kw in (dict(out_samplerate=20000), dict(mode=2), dict(brate=10, vbr=4), dict(vbr=5)):
         with pytest.raises(ValueError):
             oracle_mod.PortEncoder(**kw)
 
@@ -153,6 +153,19 @@ def test_port_mpeg2_and_mpeg25_vs_reference(port_vs_ref_bin, args, env):
     (takehiro.c:1218), 8-bit main_data_begin side info, the 8 kHz band limits; CBR, ABR, VBR (-V8/-V9 through the resampler),
     byte-identical to libmp3lame"""
     r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
+@pytest.mark.parametrize("args,env", [
+    ("noise 2 -1 -1 60", {}), ("click 2 -1 -1 100", {}), ("sine 4 -1 -1 60", {}), ("click 0 -1 -1 80", {}), ("gap 6 -1 -1 60", {}), ("click 2 0 -1 60 48000", {}),
+    ("click 5 3 -1 60", {}), ("noise 9 -1 -1 40", {}), ("click 3 -1 5 60 32000", {}), ("click 4 -1 -1 60 22050", {}), ("click 2 -1 0 40", {}),
+    ("click 7 -1 -1 60 8000", {}), ("click 2 -1 -1 60", dict(LP_VBRQ_FRAC="0.5")),
+])
+def test_port_vbr_old_vs_reference(port_vs_ref_bin, args, env):
+    """VBR-old (vbr_rh, quantize.c:1491): per gr.ch bisection of the bit budget over outer_loop, masking lowered by the perceptual
+    entropy, the sfb21 analog-silence cut, bit-pressure rounds; all MPEG versions, quality 0, a fractional level"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="2", **env))
     assert r.returncode == 0, r.stdout[-2000:]
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
