@@ -21,7 +21,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblamegpu.so")
 
 STEREO, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET = 0, 1, 2, 3, 4
-VBR_OFF, VBR_ABR, VBR_MTRH = 0, 3, 4            # lame.h:94 vbr_mode (with VBR_MTRH, `brate` is VBR_q)
+VBR_OFF, VBR_MT, VBR_RH, VBR_ABR, VBR_MTRH = 0, 1, 2, 3, 4     # lame.h:94 vbr_mode (with the VBR modes, `brate` is VBR_q)
 
 _lib = None
 
@@ -153,8 +153,8 @@ class Encoder:
             L.lame_set_VBR(self._h, VBR_ABR)
             if brate:
                 L.lame_set_VBR_mean_bitrate_kbps(self._h, brate)
-        elif vbr == VBR_MTRH:
-            L.lame_set_VBR(self._h, VBR_MTRH)
+        elif vbr in (VBR_MTRH, VBR_RH, VBR_MT):
+            L.lame_set_VBR(self._h, vbr)
             if float(brate) == int(brate):
                 L.lame_set_VBR_q(self._h, int(brate))
             else:

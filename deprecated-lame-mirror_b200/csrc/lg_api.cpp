@@ -498,7 +498,7 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
                                      int frames_per_launch, int device)
 {
     int const brate = (int) rate;
-    float const vbr_q_frac = (vbr == 4) ? rate - (float) brate : 0.f;
+    float const vbr_q_frac = (vbr == 4 || vbr == 2) ? rate - (float) brate : 0.f;
     lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
     if (!b) return NULL;
     if (lg_setup(&b->cfg, samplerate_in, samplerate_out, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr, vbr_q_frac) != 0) {
@@ -748,12 +748,11 @@ const char *get_lame_short_version(void) { return "3.99.5"; }
 int lame_init_params(lame_global_flags *g)
 {
     if (!ok(g)) return -1;
-    if (g->VBR == vbr_rh) { fprintf(stderr, "lamegpu: vbr_rh (VBR-old) is not implemented on the GPU path\n"); return -1; }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
-    int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh);        /* both select VBR_new_iteration_loop, encoder.c:531 */
+    int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh || g->VBR == vbr_rh);   /* vbr_mt and vbr_mtrh both select VBR_new_iteration_loop, encoder.c:531 */
     g->b = lamegpu_batch_open_vq(g->samplerate_in, g->samplerate_out, g->num_channels,
                                  is_vbr ? g->vbr_q + g->vbr_q_frac : (float) (g->VBR == vbr_abr ? g->mean_brate : g->brate),
-                                 g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? 4 : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
+                                 g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? (g->VBR == vbr_rh ? 2 : 4) : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
     if (!g->b) return -1;
     g->samplerate_out = g->b->cfg.samplerate;
     g->brate = g->b->cfg.brate;
@@ -956,14 +955,17 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     unsigned char const nMisc = (unsigned char) (c->noise_shaping + (nStereoMode << 2) + (bNonOptimal << 5) + (nSourceFreq << 6));
     put_be32(p + k, (unsigned long) nQuality); k += 4;
     memcpy(p + k, "LAME3.99r", 9); k += 9;                  /* get_lame_tag_encoder_short_version(), version.c:148 */
-    p[k++] = (unsigned char) (c->vbr == 4 ? 0x04 : (c->vbr == 3 ? 0x02 : 0x01));   /* revision 0; vbr_type_translator: off 1, abr 2, mtrh 4 */
+    {   /* revision 0 + the method: vbr_mode numbered the Lame tag's way (VbrTag.c:646) */
+        static const unsigned char vbr_type_translator[7] = { 1, 5, 3, 2, 4, 0, 3 };
+        p[k++] = (unsigned) g->VBR < 7u ? vbr_type_translator[g->VBR] : 0;
+    }
     p[k++] = nLowpass;
     put_be32(p + k, 0); k += 4;                             /* peak signal amplitude: no ReplayGain analysis */
     put_be16(p + k, 0); k += 2;
     put_be16(p + k, 0); k += 2;
     p[k++] = nFlags;
     {   /* "if ABR, {store bitrate <= 255} else {store -b}": the VBR modes store the minimal bitrate (VbrTag.c:672-686) */
-        int const nABRBitrate = (c->vbr == 4) ? c->bitrate_kbps[c->vbr_min_bitrate_index] : c->vbr_mean_kbps;
+        int const nABRBitrate = (c->vbr == 4 || c->vbr == 2) ? c->bitrate_kbps[c->vbr_min_bitrate_index] : c->vbr_mean_kbps;
         p[k++] = (unsigned char) (nABRBitrate >= 255 ? 0xFF : nABRBitrate);
     }
     int const enc_delay = 576, enc_padding = v.enc_padding;
@@ -973,7 +975,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     k += 3;
     p[k++] = nMisc;
     p[k++] = 0;
-    put_be16(p + k, (unsigned) (c->vbr == 4 ? 500 - 10 * c->vbr_q : c->vbr_mean_kbps)); k += 2;   /* cfg->preset: apply_preset(...), presets.c:361 */
+    put_be16(p + k, (unsigned) ((c->vbr == 4 || c->vbr == 2) ? 500 - 10 * c->vbr_q : c->vbr_mean_kbps)); k += 2;   /* cfg->preset: apply_preset(...), presets.c:361 */
     put_be32(p + k, stream_size); k += 4;
     put_be16(p + k, v.music_crc); k += 2;
     for (int i = 0; i < k; i++) crc = crc16_update(p[i], crc);

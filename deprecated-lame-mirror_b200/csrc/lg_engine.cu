@@ -21,6 +21,7 @@
 #include "lg_k_mdct.cuh"
 #include "lg_k_quant.cuh"
 #include "lg_k_vbr.cuh"
+#include "lg_k_vbrold.cuh"
 #include "lg_k_pack.cuh"
 #include "lg_engine.h"
 
@@ -210,6 +211,8 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
     cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
+    cudaFuncSetAttribute(lg_kernel_vbrold<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
+    cudaFuncSetAttribute(lg_kernel_vbrold<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
 #endif
     {
         LgStreamState *h0 = (LgStreamState *) malloc(S * sizeof(LgStreamState));
@@ -289,6 +292,12 @@ extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
 #endif
     if (e->hcfg.vbr == 4)
         LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F);
+    else if (e->hcfg.vbr == 2 && (e->hcfg.substep_shaping & 2))
+        LG_LAUNCH(lg_kernel_vbrold<1>, S, 64, sizeof(LgSmemO), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F);
+    else if (e->hcfg.vbr == 2)
+        LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
     else if (e->hcfg.substep_shaping & 2)
         LG_LAUNCH(lg_kernel_quant<1>, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,

@@ -44,6 +44,7 @@ struct __attribute__((aligned(16))) LgQWarp {
     int   width[40], window[40], lstart[41];
     int   act[80];
     float tail_max[40];
+    float tail_save[40];             /* tail_max as of save_xrpow (VBR-old keeps xrpow across outer_loop calls) */
     int   eac[40];                   /* calc_xmin: energy_above_cutoff per band (quantize_pvt.c:643), read by the VBR search */              /* per band: largest xrpow among its lines above max_nonzero_coeff (see lg_scale_bands) */
     int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
@@ -891,6 +892,16 @@ __device__ __noinline__ void lg_copy_ix_sf(LgQWarp *w, int to_best, int jn, int 
     __syncwarp();
 }
 
+/* xrpow (and the maxima of its lines above max_nonzero_coeff) -> save_xrpow or back: quantize.c:1144 / :1188, VBR-old only */
+__device__ __noinline__ void lg_copy_xrpow(LgQWarp *w, int to_save, int jn, int lane)
+{
+    float2 *d = reinterpret_cast<float2 *>(to_save ? w->save_xrpow : w->xrpow);
+    const float2 *s = reinterpret_cast<const float2 *>(to_save ? w->xrpow : w->save_xrpow);
+    for (int i = lane; i < 32 * jn; i += 32) d[i] = s[i];
+    for (int i = lane; i < 40; i += 32) { if (to_save) w->tail_save[i] = w->tail_max[i]; else w->tail_max[i] = w->tail_save[i]; }
+    __syncwarp();
+}
+
 /* A search loop that runs away means corrupted state (the reference asserts CurrentStep != 0): stop the kernel with
  * an error instead of hanging the GPU. */
 __device__ __forceinline__ void lg_runaway()
@@ -906,11 +917,14 @@ __device__ __forceinline__ void lg_runaway()
  * count_bits and ONE inlined calc_noise, so that the granule's scalar state (gi, best, pv, the search variables) stays in
  * registers for the whole search.  phase: 0 step-size search, main loop; 1 its "while too many bits" tail; 2 the first
  * and 3 the second "raise global_gain until it fits" loop of a noise-shaping round (quantize.c:1083-1101).
- * On return the work set (gi, sfw, ixw) holds the chosen quantisation. */
-template <int SUB>
-__device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int targ_bits,
-                                              int *old_value, int *current_step, int lane)
+ * On return the work set (gi, sfw, ixw) holds the chosen quantisation; the value is the number of distorted bands of it.
+ * FL bit 0: substep shaping (quality 0-2).  FL bit 1: VBR-old - the caller runs several searches on one gr.ch, so xrpow is kept as of
+ * the chosen quantisation (save_xrpow, quantize.c:1144/:1188) and sfb21_extra is the caller's (it switches it off near the bit limit). */
+template <int FL>
+__device__ __forceinline__ int lg_outer_loop(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int targ_bits,
+                                             int *old_value, int *current_step, int sfb21_vbro, int lane)
 {
+    constexpr int SUB = FL & 1, VBRO = (FL >> 1) & 1;
     int CurrentStep = *current_step, flag_GoneOver = 0, Direction = 0;
     int const start = *old_value;
     gi.global_gain = start;
@@ -949,7 +963,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
             *current_step = (start - gi.global_gain >= 4) ? 4 : 2;
             *old_value = gi.global_gain;
             gi.part2_3_length = nBits;
-            if (!c->noise_shaping) return;
+            if (!c->noise_shaping) return 100;
             pv.valid = 1; pv.global_gain = 0; pv.sfb_count1 = 0;
             for (int i = lane; i < 40; i += 32) { w->pn_step[i] = 0; w->pn_noise[i] = 0; w->pn_noise_log[i] = 0; }
             __syncwarp();
@@ -972,6 +986,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
             best_noise = noise_info;
             best = gi;                            /* cod_info_w = *cod_info: from here gi is the work copy */
             lg_copy_ix_sf(w, 1, qc.jn, lane);
+            if (VBRO) lg_copy_xrpow(w, 1, qc.jn, lane);
         }
         else {
             if (lg_quant_compare(best_noise, noise_info)) {
@@ -979,6 +994,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
                 best_noise = noise_info;
                 best = gi;
                 lg_copy_ix_sf(w, 1, qc.jn, lane);
+                if (VBRO) lg_copy_xrpow(w, 1, qc.jn, lane);
                 age = 0;
             }
             else if (c->full_outer_loop == 0) {
@@ -988,7 +1004,7 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
             if (!((gi.global_gain + gi.scalefac_scale) < 255)) break;
         }
         /* top of a noise-shaping round */
-        if (c->sfb21_extra) {
+        if (VBRO ? sfb21_vbro : c->sfb21_extra) {
             if (w->distort[qc.sfbmax] > 1.0) break;
             if (qc.block_type == LG_SHORT && (w->distort[qc.sfbmax + 1] > 1.0 || w->distort[qc.sfbmax + 2] > 1.0)) break;
         }
@@ -1000,6 +1016,8 @@ __device__ __forceinline__ void lg_outer_loop(const LgDevCfg *__restrict__ c, Lg
     }
     gi = best;
     lg_copy_ix_sf(w, 0, qc.jn, lane);
+    if (VBRO) lg_copy_xrpow(w, 0, qc.jn, lane);
+    return best_noise.over_count;
 }
 
 /* ---------------------------------------------------------------- quantize_pvt.c:589 calc_xmin: one lane per band */
@@ -1567,7 +1585,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                         if (lane == 0) w->ph[0] = w->ph[1] = ~0u;
                         __syncwarp();
                     }
-                    lg_outer_loop<SUB>(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, lane);
+                    (void) lg_outer_loop<SUB>(cfg, w, gi, qc, targ_bits[ch], &old_value, &current_step, 0, lane);
                 }
                 /* quantize.c:1213 iteration_finish_one */
                 {

@@ -656,8 +656,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
     if (channels == 1) mode = LG_MONO;                                 /* lame.c:597 */
     if (mode == LG_MONO) c->channels = 1;
     c->force_ms = 0;
-    if (vbr != 0 && vbr != 2 && vbr != 3 && vbr != 4) return -1;
-    if (vbr == 2 && !getenv("LAMEGPU_VBR_OLD")) return -1;            /* vbr_rh device path: work in progress */                  /* vbr_off, vbr_abr, vbr_mtrh (lame.h:94) */
+    if (vbr != 0 && vbr != 2 && vbr != 3 && vbr != 4) return -1;                  /* vbr_off, vbr_abr, vbr_mtrh (lame.h:94) */
     if (vbr == 2) {                                                    /* vbr_rh: `brate` carries VBR_q, no mapping to other rates */
         vbr_q = brate;
         if (vbr_q < 0 || vbr_q > 9 || !(vbr_q_frac >= 0.f && vbr_q_frac < 1.f)) return -1;

@@ -41,7 +41,7 @@ class PortEncoder:
         self.lib.lp_encode.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
         self.lib.lp_flush.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
         self.lib.lp_close.argtypes = [ctypes.c_void_p]
-        frac = np.float32(brate) - np.float32(int(brate)) if vbr == 4 else 0.0      # VBR quality = integer level + fraction
+        frac = np.float32(brate) - np.float32(int(brate)) if vbr in (2, 4) else 0.0      # VBR quality = integer level + fraction
         self.h = self.lib.lp_open_vq(samplerate, out_samplerate, channels, int(brate), 4 if mode < 0 else mode, quality, vbr, float(frac))
         if not self.h:
             raise ValueError("port: unsupported configuration")
@@ -96,11 +96,11 @@ class RefEncoder:
             L.lame_set_VBR(self.h, 3)
             if brate:
                 L.lame_set_VBR_mean_bitrate_kbps(self.h, brate)
-        elif vbr == 4:                                        # vbr_mtrh: brate is VBR_q
+        elif vbr in (1, 2, 4):                                # vbr_mt / vbr_rh / vbr_mtrh: brate is VBR_q
             L.lame_set_VBR.argtypes = [ctypes.c_void_p, ctypes.c_int]
             L.lame_set_VBR_q.argtypes = [ctypes.c_void_p, ctypes.c_int]
             L.lame_set_VBR_quality.argtypes = [ctypes.c_void_p, ctypes.c_float]
-            L.lame_set_VBR(self.h, 4)
+            L.lame_set_VBR(self.h, vbr)
             if float(brate) == int(brate):
                 L.lame_set_VBR_q(self.h, int(brate))
             else:

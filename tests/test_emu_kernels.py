@@ -84,6 +84,18 @@ def test_emulated_mpeg2_matches_port(emu_bin, args, env):
     assert "IDENTICAL" in r.stdout
 
 
+@pytest.mark.parametrize("args,env", [
+    ("3 8 4 2 -1 -1 44100 1152", {}), ("3 10 4 0 -1 -1 44100 1152", {}), ("3 10 8 4 0 -1 48000 777", {}), ("3 10 4 4 -1 -1 22050 1152", {}),
+    ("3 10 4 2 -1 0 44100 1152", {}), ("3 10 4 2 -1 -1 44100 1152", dict(LP_VBRQ_FRAC="0.5")),
+])
+def test_emulated_vbr_old_matches_port(emu_bin, args, env):
+    """VBR-old (vbr_rh): lg_kernel_vbrold - bisection of the bit budget over kernel D's outer_loop with xrpow kept between runs, the
+    sfb21 analog-silence cut, bit-pressure rounds, the entropy-driven masking feedback in the scan kernel"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=1200, env=dict(os.environ, LP_VBR="2", **env))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout
+
+
 TAG_SCRIPT = r"""
 import json, os, sys
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))

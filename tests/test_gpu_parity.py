@@ -164,7 +164,8 @@ def test_resampled_batch_matches_oracle(lib, oracle_mod, cfg):
 @pytest.mark.parametrize("kw", [dict(samplerate=48000, brate=128, out_samplerate=44100), dict(samplerate=44100, brate=7, vbr=4),
                                 dict(samplerate=44100, brate=4.6, vbr=4), dict(samplerate=44100, brate=96, quality=1),
                                 dict(samplerate=22050, brate=64), dict(samplerate=44100, brate=9, vbr=4), dict(samplerate=8000, brate=16, mode=3),
-                                dict(samplerate=24000, brate=80, vbr=3)])
+                                dict(samplerate=24000, brate=80, vbr=3), dict(samplerate=44100, brate=2, vbr=2), dict(samplerate=44100, brate=4, vbr=1),
+                                dict(samplerate=22050, brate=5, vbr=2)])
 def test_resampled_lame_api_with_tag(lib, oracle_mod, kw):
     """the lame.h face with lame_set_out_samplerate / -V7 / a fractional level / quality 1, and the Info tag: source-rate field,
     encoder padding, quality and preset fields of the tag (VbrTag.c:775, lame.c:2083-2091)"""
@@ -243,6 +244,30 @@ def test_mpeg2_batch_matches_oracle(lib, oracle_mod, cfg):
             want += e.flush()
             e.close()
             assert got[s] == want, "stream %d (%s) vs %s" % (s, kinds[s % 4], type(e).__name__)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(S=8, F=20, fpl=8, q=2), dict(S=4, F=20, fpl=4, q=0), dict(S=4, F=16, fpl=8, q=4, mode=0, sr=48000), dict(S=4, F=16, fpl=4, q=5, mode=3),
+    dict(S=4, F=16, fpl=4, q=9), dict(S=4, F=16, fpl=4, q=3, quality=5, sr=32000), dict(S=4, F=16, fpl=4, q=4, sr=22050), dict(S=4, F=16, fpl=4, q=2, quality=0),
+    dict(S=4, F=16, fpl=4, q=7, sr=8000), dict(S=4, F=16, fpl=4, q=2.5),
+])
+def test_vbr_old_batch_matches_oracle(lib, oracle_mod, cfg):
+    """VBR-old (vbr_rh, quantize.c:1491) on lg_kernel_vbrold; the masking feedback evaluates exp/pow in double on the device
+    (rounded to float, equal to the host's unless a double lands within an ulp of a float rounding boundary)"""
+    S, F = cfg["S"], cfg["F"]
+    sr, q, mode, quality = cfg.get("sr", 44100), cfg["q"], cfg.get("mode", -1), cfg.get("quality", -1)
+    kinds = ("noise", "click", "sine", "gap")
+    pcm = np.stack([make_signal(kinds[s % 4], F * 1152, seed=140 + s) for s in range(S)])
+    enc = lib.BatchEncoder(S, sr, 2, q, mode, quality, frames_per_launch=cfg["fpl"], vbr=lib.VBR_RH)
+    _, a = enc.encode(pcm)
+    _, b = enc.flush()
+    enc.close()
+    for s in range(S):
+        want = oracle_mod.PortEncoder(sr, 2, q, mode, quality, vbr=2).encode_all(pcm[s, 0], pcm[s, 1])
+        if oracle_mod.have_ref():
+            ref = oracle_mod.RefEncoder(sr, 2, q, mode if mode >= 0 else 4, quality, vbr=2).encode_all(pcm[s, 0], pcm[s, 1])
+            assert want == ref, "oracle port and reference disagree"
+        assert a[s] + b[s] == want, "stream %d (%s)" % (s, kinds[s % 4])
 
 
 def test_config4_vbr_v2_full_size(lib, oracle_mod):
@@ -347,7 +372,7 @@ def test_unsupported_configurations_fail_loudly(lib):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()
     h = L.lame_init()
-    L.lame_set_VBR(h, 2)                     # vbr_rh (VBR-old) is not implemented
+    L.lame_set_mode(h, 2)                    # dual channel is not implemented
     assert L.lame_init_params(h) == -1
     L.lame_close(h)
 
