@@ -77,7 +77,7 @@ def set_workload(args):
     global SIGNAL, BRATE, VBR, STREAMS, FRAMES, WORKLOAD, QUALITY
     SIGNAL, BRATE, VBR, STREAMS, FRAMES, QUALITY = args.signal, args.brate, args.vbr, args.streams, args.frames, args.quality
     if (SIGNAL, BRATE, VBR, STREAMS, FRAMES, QUALITY) != ("noise", 128, 0, 512, 8, -1):
-        rate = {0: "CBR %d kbps" % BRATE, 3: "ABR %d kbps" % BRATE, 4: "VBR-new -V%d" % BRATE}[VBR]
+        rate = {0: "CBR %d kbps" % BRATE, 2: "VBR-old -V%d" % BRATE, 3: "ABR %d kbps" % BRATE, 4: "VBR-new -V%d" % BRATE}[VBR]
         sig = "white noise U[-12000,12000]" if SIGNAL == "noise" else "two tones per channel + U[-1000,1000]"
         WORKLOAD = "%d frames/GPU = %d streams x %d frames, 44.1 kHz stereo %s, %s joint stereo q%d" % (STREAMS * FRAMES, STREAMS, FRAMES, sig, rate, 3 if QUALITY < 0 else QUALITY)
 
@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--streams", type=int, default=STREAMS)
     ap.add_argument("--frames", type=int, default=FRAMES)
     ap.add_argument("--brate", type=int, default=128, help="kbps (CBR/ABR) or the -V level with --vbr 4")
-    ap.add_argument("--vbr", type=int, default=0, choices=(0, 3, 4), help="0 CBR, 3 ABR, 4 VBR-new (vbr_mtrh)")
+    ap.add_argument("--vbr", type=int, default=0, choices=(0, 2, 3, 4), help="0 CBR, 2 VBR-old (vbr_rh), 3 ABR, 4 VBR-new (vbr_mtrh)")
     ap.add_argument("--signal", default="noise", choices=("noise", "sine"))
     ap.add_argument("--quality", type=int, default=-1, help="lame_set_quality 0..9, -1 = default (3)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -322,7 +322,7 @@ def main():
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         q_ms = kms[3] / args.steps
-        qname = "lg_kernel_vbr" if VBR == 4 else "lg_kernel_quant"
+        qname = {4: "lg_kernel_vbr", 2: "lg_kernel_vbrold"}.get(VBR, "lg_kernel_quant")
         achieved = ALG_BYTES_QUANT * S * F / (q_ms * 1e-3) / 1e9
         a_ms = (kms[0] + kms[1] + kms[2]) / args.steps
         line = {

@@ -3,7 +3,7 @@ usage: python tools/ncu_by_line.py <rep.ncu-rep> <lib.so> <kernel-substring> [to
 import csv, io, os, re, subprocess, sys, tempfile
 rep, lib, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 60
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern.split("ILi")[0]], capture_output=True, text=True).stdout
 lines = txt.splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
 rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))

@@ -15,7 +15,7 @@ for rep in sys.argv[2:]:
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
         d = dict(zip(hdr, r)); u = dict(zip(hdr, units))
-        name = d["Kernel Name"].split("(")[0].split("<")[0]
+        name = d["Kernel Name"].split("(")[0].split("<")[0].replace("void ", "").strip()
         k = {m: {"unit": u[m], "value": d[m]} for m in WANT if m in d}
         k["stall_cycles_per_issue"] = {m: d[m] for m in hdr if "issue_stalled" in m and m.endswith("per_issue_active.ratio") and float(d[m] or 0) >= 0.05}
         k["source"] = rep.split("/")[-1]
