@@ -102,7 +102,17 @@ def load_library(path=None):
     return lib
 
 
-EXPORTED_SYMBOLS = [
+def _option_symbols():
+    """lame_set_X / lame_get_X pairs carried for link compatibility (include/lamegpu_options.h, generated)"""
+    import re
+    h = os.path.join(os.path.dirname(_HERE), "include", "lamegpu_options.h")
+    return re.findall(r"\b(lame_[sg]et_\w+)\s*\(", open(h).read()) if os.path.exists(h) else []
+
+
+EXPORTED_SYMBOLS = _option_symbols() + [
+    "get_lame_version", "get_lame_very_short_version", "get_psy_version", "get_lame_url", "get_lame_os_bitness", "lame_get_version",
+    "lame_get_encoder_padding", "lame_get_mf_samples_to_encode", "lame_get_totalframes", "lame_print_config", "lame_print_internals",
+    "lame_mp3_tags_fid", "lame_encode_finish",
     "lame_init", "lame_set_in_samplerate", "lame_get_in_samplerate", "lame_set_num_channels", "lame_get_num_channels",
     "lame_set_out_samplerate", "lame_get_out_samplerate", "lame_set_brate", "lame_get_brate", "lame_set_quality",
     "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",

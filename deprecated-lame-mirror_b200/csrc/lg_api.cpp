@@ -481,6 +481,8 @@ struct lamegpu_batch {
     }
 };
 
+static thread_local const int *g_header_bits = nullptr;     /* set by lame_init_params around its lamegpu_batch_open_vq call */
+
 extern "C" {
 
 lamegpu_batch *lamegpu_batch_open_ex(int samplerate, int channels, int brate, int mode, int quality, int vbr, int nstreams, int frames_per_launch, int device)
@@ -506,6 +508,9 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
                 samplerate_in, samplerate_out, channels, brate, mode, quality, vbr);
         delete b;
         return NULL;
+    }
+    if (g_header_bits) {             /* lame_init_params: copyright / original / emphasis / extension of the handle */
+        b->cfg.copyright = g_header_bits[0]; b->cfg.original = g_header_bits[1]; b->cfg.emphasis = g_header_bits[2]; b->cfg.extension = g_header_bits[3];
     }
     b->eng = lg_engine_create(&b->cfg, nstreams, frames_per_launch, device);
     if (!b->eng) { delete b; return NULL; }
@@ -640,8 +645,24 @@ size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }
 /* ------------------------------------------------------------------ libmp3lame-compatible face */
 #define LAME_ID 0xFFF88E3B      /* lame_global_flags.h / lame.c class_id check */
 
+/* libmp3lame options this library only carries (include/lamegpu_options.h, generated from the reference's lame.h):
+ * name, C type, default before and after lame_init_params, honoured */
+enum {
+#define LG_OPT(n, t, d, d2, h) LG_OPTI_##n,
+#include "lg_api_options.inc"
+#undef LG_OPT
+    LG_NOPT
+};
+static const struct { const char *name; double def, def2; int honoured; } g_opts[LG_NOPT] = {
+#define LG_OPT(n, t, d, d2, h) { #n, (double) d, (double) d2, h },
+#include "lg_api_options.inc"
+#undef LG_OPT
+};
+
 struct lame_global_struct {
     unsigned class_id;
+    double opt[LG_NOPT];
+    unsigned char opt_set[LG_NOPT];
     int num_channels, samplerate_in, samplerate_out, brate, quality, write_lame_tag, mean_brate, vbr_q;
     float vbr_q_frac;
     MPEG_mode mode;
@@ -697,6 +718,7 @@ lame_global_flags *lame_init(void)
     lame_global_flags *g = (lame_global_flags *) calloc(1, sizeof *g);
     if (!g) return NULL;
     g->class_id = LAME_ID;
+    for (int i = 0; i < LG_NOPT; i++) g->opt[i] = g_opts[i].def;
     g->num_channels = 2; g->samplerate_in = 44100; g->samplerate_out = 0; g->brate = 0; g->quality = -1;
     g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128; g->vbr_q = 4; g->vbr_q_frac = 0;
     if (const char *e = getenv("LAMEGPU_HANDLE_FRAMES")) g->launch_frames = std::max(1, atoi(e));
@@ -748,11 +770,20 @@ const char *get_lame_short_version(void) { return "3.99.5"; }
 int lame_init_params(lame_global_flags *g)
 {
     if (!ok(g)) return -1;
+    for (int i = 0; i < LG_NOPT; i++)
+        if (g->opt_set[i] && !g_opts[i].honoured && g->opt[i] != g_opts[i].def && g->opt[i] != g_opts[i].def2) {
+            fprintf(stderr, "lamegpu: lame_set_%s(%g) is not supported (only the default %g)\n", g_opts[i].name, g->opt[i], g_opts[i].def);
+            return -1;
+        }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
     int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh || g->VBR == vbr_rh);   /* vbr_mt and vbr_mtrh both select VBR_new_iteration_loop, encoder.c:531 */
+    int const header_bits[4] = { (int) g->opt[LG_OPTI_copyright] != 0, (int) g->opt[LG_OPTI_original] != 0, (int) g->opt[LG_OPTI_emphasis] & 3,
+                                 (int) g->opt[LG_OPTI_extension] != 0 };
+    g_header_bits = header_bits;
     g->b = lamegpu_batch_open_vq(g->samplerate_in, g->samplerate_out, g->num_channels,
                                  is_vbr ? g->vbr_q + g->vbr_q_frac : (float) (g->VBR == vbr_abr ? g->mean_brate : g->brate),
                                  g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? (g->VBR == vbr_rh ? 2 : 4) : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
+    g_header_bits = nullptr;
     if (!g->b) return -1;
     g->samplerate_out = g->b->cfg.samplerate;
     g->brate = g->b->cfg.brate;
@@ -862,6 +893,61 @@ int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
     x.bw.buf.clear();
     return handle_take(g, mp3buf, size);
 }
+/* the carried options: setter stores, getter returns what was stored (or the reference's default) */
+#define LG_OPT(n, t, d, d2, h) \
+    int lame_set_##n(lame_global_flags *g, t v) { if (!ok(g)) return -1; g->opt[LG_OPTI_##n] = (double) v; g->opt_set[LG_OPTI_##n] = 1; return 0; } \
+    t lame_get_##n(const lame_global_flags *g) { return ok(g) ? (t) g->opt[LG_OPTI_##n] : (t) 0; }
+#include "lg_api_options.inc"
+#undef LG_OPT
+
+/* version.c:55-260, set_get.c and lame.c read-only queries */
+const char *get_lame_version(void) { return "3.99.5"; }
+const char *get_lame_very_short_version(void) { return "LAME3.99r5"; }
+const char *get_psy_version(void) { return "1.0"; }
+const char *get_lame_url(void) { return "http://lame.sf.net"; }
+const char *get_lame_os_bitness(void) { return sizeof(void *) == 8 ? "64bits" : "32bits"; }
+int lame_get_version(const lame_global_flags *g) { return ok(g) && g->b ? g->b->cfg.version : 0; }            /* 1 = MPEG-1, 0 = MPEG-2/2.5 */
+int lame_get_encoder_padding(const lame_global_flags *g) { return ok(g) && g->b ? g->b->st[0].tag.enc_padding : 0; }
+int lame_get_mf_samples_to_encode(const lame_global_flags *g) { return ok(g) && g->b ? (int) g->b->st[0].mf_samples_to_encode : 0; }
+int lame_get_totalframes(const lame_global_flags *g)                                                          /* set_get.c:2121 */
+{
+    if (!ok(g) || !g->b) return 0;
+    unsigned long const fs = 576ul * g->b->cfg.mode_gr;
+    unsigned long n = (unsigned long) g->opt[LG_OPTI_num_samples];
+    if (n == (0ul - 1ul) || n == 4294967295ul) return 0;
+    if (g->samplerate_in != g->samplerate_out && g->samplerate_in > 0) n *= (double) g->samplerate_out / g->samplerate_in;
+    n += 576;
+    unsigned long end_padding = fs - (n % fs);
+    if (end_padding < 576) end_padding += fs;
+    return (int) ((n + end_padding) / fs);
+}
+void lame_print_config(const lame_global_flags *g)
+{
+    if (!ok(g) || !g->b) return;
+    const LgDevCfg *c = &g->b->cfg;
+    fprintf(stderr, "lamegpu %s: %d Hz -> %d Hz%s, MPEG-%s Layer III, %s, quality %d, lowpass %d Hz\n", get_lame_version(), c->samplerate_in, c->samplerate,
+            c->resample ? " (resampled on the device)" : "", c->version == 1 ? "1" : (c->samplerate < 16000 ? "2.5" : "2"),
+            c->vbr == 0 ? "CBR" : (c->vbr == 3 ? "ABR" : (c->vbr == 2 ? "VBR (rh)" : "VBR (mtrh)")), c->quality, c->lowpassfreq);
+}
+void lame_print_internals(const lame_global_flags *g) { lame_print_config(g); }
+/* lame.c:2234 lame_mp3_tags_fid: the finished Info tag over the placeholder frame at the start of the file (no ID3v2 to skip) */
+void lame_mp3_tags_fid(lame_global_flags *g, FILE *f)
+{
+    if (!ok(g) || !g->b || !f || !g->b->st[0].tag.on) return;
+    unsigned char buf[2880];
+    size_t const n = lame_get_lametag_frame(g, buf, sizeof buf);
+    if (n == 0 || n > sizeof buf) return;
+    if (fseek(f, 0, SEEK_SET) != 0) { fprintf(stderr, "lamegpu: could not update LAME tag, file not seekable.\n"); return; }
+    if (fwrite(buf, 1, n, f) != n) fprintf(stderr, "lamegpu: could not update LAME tag.\n");
+}
+/* lame.c:2145 lame_encode_finish = lame_encode_flush + lame_close */
+int lame_encode_finish(lame_global_flags *g, unsigned char *mp3buf, int size)
+{
+    int const ret = lame_encode_flush(g, mp3buf, size);
+    (void) lame_close(g);
+    return ret;
+}
+
 /* lame.c:2462-2606: the statistics of the frames encoded so far (bitrates of this MPEG version, frames per bitrate and
  * stereo mode, gr.ch per bitrate and block type) */
 void lame_bitrate_kbps(const lame_global_flags *g, int bitrate_kbps[14])

@@ -18,6 +18,7 @@
 #ifndef LAMEGPU_H
 #define LAMEGPU_H
 #include <stddef.h>
+#include <stdio.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -29,6 +30,7 @@ typedef lame_global_flags *lame_t;
 
 typedef enum vbr_mode_e { vbr_off = 0, vbr_mt, vbr_rh, vbr_abr, vbr_mtrh, vbr_max_indicator, vbr_default = vbr_mtrh } vbr_mode; /* lame.h:49-57 */
 typedef enum MPEG_mode_e { STEREO = 0, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET, MAX_INDICATOR } MPEG_mode;               /* lame.h:61-68 */
+typedef enum Padding_type_e { PAD_NO = 0, PAD_ALL, PAD_ADJUST, PAD_MAX_INDICATOR } Padding_type;                             /* lame.h:72-77 */
 
 lame_global_flags *lame_init(void);                                                  /* lame.h:168  NULL on OOM */
 int  lame_set_in_samplerate(lame_global_flags *, int);                               /* lame.h:188 */
@@ -93,6 +95,20 @@ void lame_block_type_hist(const lame_global_flags *, int btype_count[6]);       
 void lame_bitrate_block_type_hist(const lame_global_flags *, int bitrate_btype_count[14][6]);    /* lame.h:927 */
 int  lame_close(lame_global_flags *);                                                /* lame.h:977 */
 const char *get_lame_short_version(void);                                            /* lame.h:645 */
+const char *get_lame_version(void);                                                  /* lame.h:644 */
+const char *get_lame_very_short_version(void);                                       /* lame.h:646 */
+const char *get_psy_version(void);                                                   /* lame.h:647 */
+const char *get_lame_url(void);                                                      /* lame.h:648 */
+const char *get_lame_os_bitness(void);                                               /* lame.h:649 */
+int  lame_get_version(const lame_global_flags *);                                    /* lame.h:568  1 = MPEG-1, 0 = MPEG-2/2.5 */
+int  lame_get_encoder_padding(const lame_global_flags *);                            /* lame.h:579 */
+int  lame_get_mf_samples_to_encode(const lame_global_flags *);                       /* lame.h:585 */
+int  lame_get_totalframes(const lame_global_flags *);                                /* lame.h:603 */
+void lame_print_config(const lame_global_flags *);                                   /* lame.h:678 */
+void lame_print_internals(const lame_global_flags *);                                /* lame.h:680 */
+void lame_mp3_tags_fid(lame_global_flags *, FILE *fid);                              /* lame.h:950 */
+int  lame_encode_finish(lame_global_flags *, unsigned char *mp3buf, int size);       /* lame.h:988 */
+#include "lamegpu_options.h"                                                         /* the remaining lame_set_X / lame_get_X pairs */
 
 /* ------------------------------------------------------------------ 2. batch face */
 typedef struct lamegpu_batch lamegpu_batch;

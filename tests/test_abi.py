@@ -18,10 +18,10 @@ def lib():
 
 
 def declared_functions():
-    src = open(os.path.join(ROOT, "include", "lamegpu.h")).read()
+    src = open(os.path.join(ROOT, "include", "lamegpu.h")).read() + open(os.path.join(ROOT, "include", "lamegpu_options.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src)
-    return sorted({n for n in names if n.startswith(("lame_", "lamegpu_", "get_lame"))})
+    return sorted({n for n in names if n.startswith(("lame_", "lamegpu_", "get_lame", "get_psy"))})
 
 
 def test_header_symbols_are_exported(lib):
@@ -42,6 +42,26 @@ def test_library_contains_sm100a_kernels(lib):
     for k in ("lg_kernel_analysis", "lg_kernel_scan", "lg_kernel_mdct", "lg_kernel_quant", "lg_kernel_pack"):
         assert k in sass
     assert "REDUX" in sass and "SHFL" in sass          # warp reductions of the bit counters / noise maxima
+
+
+def test_carried_options_accept_defaults_only(lib):
+    """the lame_set_X / lame_get_X pairs of libmp3lame that this library does not act on: the value is stored and read back, and
+    lame_init_params refuses it when it is not the reference's default (checked before any GPU work)"""
+    import ctypes
+    L = lib.load_library()
+    for fn, res, arg in (("lame_set_lowpassfreq", None, ctypes.c_int), ("lame_get_lowpassfreq", ctypes.c_int, None), ("lame_set_scale", None, ctypes.c_float),
+                         ("lame_get_scale", ctypes.c_float, None), ("lame_set_disable_reservoir", None, ctypes.c_int), ("lame_set_copyright", None, ctypes.c_int),
+                         ("lame_get_copyright", ctypes.c_int, None), ("lame_get_original", ctypes.c_int, None)):
+        f = getattr(L, fn)
+        f.restype = res if res else ctypes.c_int
+        f.argtypes = [ctypes.c_void_p] + ([arg] if arg else [])
+    h = L.lame_init()
+    assert L.lame_get_lowpassfreq(h) == 0 and L.lame_get_scale(h) == 1.0 and L.lame_get_original(h) == 1
+    assert L.lame_set_disable_reservoir(h, 0) == 0 and L.lame_set_scale(h, 1.0) == 0 and L.lame_set_copyright(h, 1) == 0
+    assert L.lame_get_copyright(h) == 1
+    assert L.lame_set_lowpassfreq(h, 12345) == 0 and L.lame_get_lowpassfreq(h) == 12345
+    assert L.lame_init_params(h) == -1           # a low-pass other than the default is not implemented: refused, loudly
+    L.lame_close(h)
 
 
 def test_signatures_bind(lib):

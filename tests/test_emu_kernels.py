@@ -127,6 +127,16 @@ def test_emulated_info_tag_matches_reference_golden(emu_bin):
     assert r.returncode == 0 and "TAG IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_emulated_header_bits_and_tag_file(emu_bin, oracle_mod):
+    """lame_set_copyright / _original / _emphasis / _extension reach the frame headers and the Info tag; lame_mp3_tags_fid"""
+    import sys
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build (oracle/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "header_bits_check.py"), os.path.join(ROOT, "tests", "emu", "liblamegpu_emu.so")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "HEADER BITS IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_emulated_sample_type_entry_points(emu_bin, oracle_mod):
     """lame_encode_buffer_float/_ieee_float/_ieee_double/_int/_long/_long2/_interleaved* against libmp3lame itself"""
     import sys

@@ -351,6 +351,15 @@ def test_sample_type_entry_points(lib, oracle_mod):
     assert r.returncode == 0 and "SAMPLE TYPES IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_header_bits_and_tag_file(lib, oracle_mod):
+    """the header bits a caller may set (copyright, original, emphasis, extension) and lame_mp3_tags_fid, against libmp3lame"""
+    import sys
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the prebuilt reference (oracle/_ref)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "header_bits_check.py"), lib.LIB_PATH], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "HEADER BITS IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 def test_edge_cases(lib, oracle_mod):
     # fewer samples than one frame, then flush: the encoder delay padding still yields complete frames
     for n in (0, 1, 575, 1151, 1376, 1377):
