@@ -753,7 +753,7 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     c->lowpassfreq = samplerate / 2 < c->lowpassfreq ? samplerate / 2 : c->lowpassfreq;
     c->mode_gr = samplerate <= 24000 ? 1 : 2;                          /* lame.c:797 */
     if (mode == LP_MODE_NOT_SET || mode < 0) mode = LP_JOINT;
-    if (mode == LP_DUAL) return -1;
+    /* dual channel (mode 2): two independent channels - no M/S, block types not coupled, its own header code */
     c->mode = mode;
     c->highpass1 = c->highpass2 = 0;
     c->lowpass1 = c->lowpass2 = 0;

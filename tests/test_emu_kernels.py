@@ -21,7 +21,7 @@ def emu_bin(oracle_mod, tmp_path_factory):
 
 # nstreams frames_per_stream frames_per_launch brate mode quality samplerate chunk
 @pytest.mark.parametrize("args", ["4 24 8 128 -1 -1 44100 1152", "3 20 5 320 1 -1 44100 3000", "3 16 16 192 0 5 48000 777",
-                                  "2 12 4 160 -1 7 32000 1152"])
+                                  "2 12 4 160 -1 7 32000 1152", "3 10 4 128 2 -1 44100 1152"])
 def test_emulated_kernels_match_port(emu_bin, args):
     r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

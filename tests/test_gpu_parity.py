@@ -45,7 +45,7 @@ def test_golden_vectors(lib, name):
 @pytest.mark.parametrize("cfg", [
     dict(S=16, F=24, fpl=8, brate=128), dict(S=7, F=30, fpl=16, brate=320, mode=1), dict(S=5, F=20, fpl=3, brate=192, mode=0, q=5),
     dict(S=4, F=16, fpl=8, brate=256, sr=48000), dict(S=4, F=16, fpl=8, brate=128, sr=32000), dict(S=3, F=12, fpl=4, brate=160, q=7),
-    dict(S=3, F=12, fpl=4, brate=112, q=9), dict(S=2, F=40, fpl=40, brate=224, q=4),
+    dict(S=3, F=12, fpl=4, brate=112, q=9), dict(S=2, F=40, fpl=40, brate=224, q=4), dict(S=4, F=20, fpl=8, brate=160, mode=2),
     # quality 2 / 1 / 0: substep shaping, one-band amplification, full outer loop
     dict(S=8, F=24, fpl=8, brate=128, q=2), dict(S=8, F=24, fpl=8, brate=128, q=1), dict(S=8, F=24, fpl=8, brate=128, q=0),
     dict(S=4, F=20, fpl=4, brate=320, mode=1, q=0), dict(S=4, F=16, fpl=8, brate=192, mode=0, q=1, sr=48000), dict(S=4, F=16, fpl=8, brate=112, q=2, sr=32000),
@@ -376,12 +376,14 @@ def test_edge_cases(lib, oracle_mod):
 
 
 def test_unsupported_configurations_fail_loudly(lib):
-    for kw in (dict(out_samplerate=20000), dict(mode=2), dict(brate=10, vbr=4), dict(samplerate=0)):
+    for kw in (dict(out_samplerate=20000), dict(channels=3), dict(brate=10, vbr=4), dict(samplerate=0)):
         with pytest.raises(lib.LameGpuError):
             lib.BatchEncoder(2, **kw)
     L = lib.load_library()
     h = L.lame_init()
-    L.lame_set_mode(h, 2)                    # dual channel is not implemented
+    import ctypes
+    L.lame_set_free_format.argtypes, L.lame_set_free_format.restype = [ctypes.c_void_p, ctypes.c_int], ctypes.c_int
+    assert L.lame_set_free_format(h, 1) == 0   # free format is not implemented: the option is carried, a non-default value refused
     assert L.lame_init_params(h) == -1
     L.lame_close(h)
 

@@ -41,8 +41,8 @@ def test_port_chunking_invariance(oracle_mod):
 
 
 def test_port_rejects_unsupported(oracle_mod):
-    # not an MPEG rate, dual channel, VBR level out of range, not a vbr_mode
-    for kw in (dict(out_samplerate=20000), dict(mode=2), dict(brate=10, vbr=4), dict(vbr=5)):
+    # not an MPEG rate, three channels, VBR level out of range, not a vbr_mode
+    for kw in (dict(out_samplerate=20000), dict(channels=3), dict(brate=10, vbr=4), dict(vbr=5)):
         with pytest.raises(ValueError):
             oracle_mod.PortEncoder(**kw)
 
@@ -62,6 +62,7 @@ def port_vs_ref_bin(oracle_mod, tmp_path_factory):
     "noise 128 -1 -1 120", "sine 128 -1 -1 100", "click 128 -1 -1 150", "gap 128 -1 -1 60", "sine 320 1 -1 100",
     "click 320 1 -1 100", "noise 192 0 -1 60", "click 160 -1 5 80", "click 128 -1 7 60", "sine 128 -1 4 60",
     "click 256 -1 -1 60 48000", "click 128 -1 -1 60 32000", "silence 128 -1 -1 20", "click 224 0 6 60", "noise 112 -1 9 40",
+    "click 128 2 -1 80", "click 192 2 5 60 48000", "click 64 2 -1 60 22050",        # dual channel (mode 2)
 ])
 def test_port_vs_reference(port_vs_ref_bin, args):
     """byte-identical MP3 + identical init tables against the real libmp3lame (strict IEEE build)"""
