@@ -319,7 +319,7 @@ struct lamegpu_batch {
                     x.last_bitrate_index = fr->bitrate_index;
                     {
                         int const bi = fr->bitrate_index & 15;
-                        const unsigned char *bt = hdr + ((size_t) s * F + f) * LG_HDR_STRIDE + 36;
+                        const unsigned char *bt = hdr + ((size_t) s * F + f) * LG_HDR_STRIDE + 40;
                         x.hist_mode[bi][4]++; x.hist_mode[15][4]++;
                         if (cfg.channels == 2) { x.hist_mode[bi][fr->mode_ext & 3]++; x.hist_mode[15][fr->mode_ext & 3]++; }
                         for (int k = 0; k < 4; k++)
@@ -509,8 +509,9 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
         delete b;
         return NULL;
     }
-    if (g_header_bits) {             /* lame_init_params: copyright / original / emphasis / extension of the handle */
+    if (g_header_bits) {             /* lame_init_params: copyright / original / emphasis / extension / error_protection of the handle */
         b->cfg.copyright = g_header_bits[0]; b->cfg.original = g_header_bits[1]; b->cfg.emphasis = g_header_bits[2]; b->cfg.extension = g_header_bits[3];
+        if (g_header_bits[4]) { b->cfg.error_protection = 1; b->cfg.sideinfo_len += 2; }       /* lame.c:954 */
     }
     b->eng = lg_engine_create(&b->cfg, nstreams, frames_per_launch, device);
     if (!b->eng) { delete b; return NULL; }
@@ -777,8 +778,8 @@ int lame_init_params(lame_global_flags *g)
         }
     if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
     int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh || g->VBR == vbr_rh);   /* vbr_mt and vbr_mtrh both select VBR_new_iteration_loop, encoder.c:531 */
-    int const header_bits[4] = { (int) g->opt[LG_OPTI_copyright] != 0, (int) g->opt[LG_OPTI_original] != 0, (int) g->opt[LG_OPTI_emphasis] & 3,
-                                 (int) g->opt[LG_OPTI_extension] != 0 };
+    int const header_bits[5] = { (int) g->opt[LG_OPTI_copyright] != 0, (int) g->opt[LG_OPTI_original] != 0, (int) g->opt[LG_OPTI_emphasis] & 3,
+                                 (int) g->opt[LG_OPTI_extension] != 0, (int) g->opt[LG_OPTI_error_protection] != 0 };
     g_header_bits = header_bits;
     g->b = lamegpu_batch_open_vq(g->samplerate_in, g->samplerate_out, g->num_channels,
                                  is_vbr ? g->vbr_q + g->vbr_q_frac : (float) (g->VBR == vbr_abr ? g->mean_brate : g->brate),
@@ -1007,12 +1008,14 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
         toc[i] = (unsigned char) seek_point;
     }
     unsigned n = (unsigned) c->sideinfo_len;
+    if (c->error_protection) n -= 2;                        /* VbrTag.c:955-961: the Xing data keeps its offset */
     memcpy(buffer + n, c->vbr == 0 ? "Info" : "Xing", 4); n += 4;
     put_be32(buffer + n, 1 + 2 + 4 + 8); n += 4;            /* FRAMES_FLAG + BYTES_FLAG + TOC_FLAG + VBR_SCALE_FLAG */
     put_be32(buffer + n, (unsigned long) v.nframes); n += 4;
     unsigned long const stream_size = (unsigned long) (v.nbytes + v.frame_size);
     put_be32(buffer + n, stream_size); n += 4;
     memcpy(buffer + n, toc, sizeof toc); n += sizeof toc;
+    if (c->error_protection) lg_header_crc(buffer, c->sideinfo_len);     /* VbrTag.c:996 */
     unsigned short crc = 0;
     for (unsigned i = 0; i < n; i++) crc = crc16_update(buffer[i], crc);
     /* PutLameVBR */

@@ -73,10 +73,29 @@ static int frame_bits(const LgDevCfg *c, int bitrate_index, int padding)
  * pay = the frame's payload (ancillary drain + main data, whole bytes).  What is left is what format_bitstream does
  * with its header ring (bitstream.c:918-960, putheader_bits :130): the payload goes out in order, and each pending
  * header is spliced in when the stream reaches the position where its frame starts. */
+/* bitstream.c:287 CRC_update + :304 CRC_writeheader: CRC-16 (x^16 + x^15 + x^2 + 1, MSB first, start 0xffff) over header bytes 2-3 and the
+ * side info, stored in bytes 4-5 (error_protection) */
+void lg_header_crc(unsigned char *header, int sideinfo_len)
+{
+    int crc = 0xffff;
+    for (int i = 2; i < sideinfo_len; i++) {
+        if (i == 4 || i == 5) continue;
+        int value = header[i] << 8;
+        for (int k = 0; k < 8; k++) {
+            value <<= 1;
+            crc <<= 1;
+            if ((crc ^ value) & 0x10000) crc ^= 0x8005;
+        }
+    }
+    header[4] = (unsigned char) (crc >> 8);
+    header[5] = (unsigned char) (crc & 255);
+}
+
 void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const unsigned char *hdr, const unsigned char *pay)
 {
     int const sl = cfg->sideinfo_len;
     memcpy(bw->header[bw->h_ptr].buf, hdr, sl);
+    if (cfg->error_protection) lg_header_crc(bw->header[bw->h_ptr].buf, sl);
     int const old = bw->h_ptr;
     bw->h_ptr = (old + 1) & (LG_MAX_HEADER_BUF - 1);
     bw->header[bw->h_ptr].write_timing = bw->header[old].write_timing + frame_bits(cfg, fo->bitrate_index, fo->padding);

@@ -16,5 +16,6 @@ struct LgBitWriter {
     void reset();
 };
 
+void lg_header_crc(unsigned char *header, int sideinfo_len);
 void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const unsigned char *hdr, const unsigned char *pay);
 void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding);

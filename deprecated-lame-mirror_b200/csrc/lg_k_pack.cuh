@@ -108,6 +108,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const nch = c->channels;
     const LgFrameOut *fo = fout + (size_t) stream * nframes + frame;
+    int const crc = c->error_protection ? 16 : 0;   /* bits left free behind the header for the CRC the host fills in (bitstream.c:348) */
     int const mgr = c->mode_gr;                   /* MPEG-2/2.5: one granule per frame, warps 2 and 3 only help with the drains */
     const LgGranuleOut *g4 = gout + ((size_t) stream * 2 * nframes + mgr * frame) * 2;
     int const pay_bytes = fo->pay_bytes;
@@ -241,7 +242,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
         /* ---- this granule.channel's 59 bits of side info (encodeSideInfo2 bitstream.c:409-460) */
         if (lane == 0 && mgr == 1) {
             /* bitstream.c:415-466: MPEG-2/2.5 side info of one gr.ch = 63 bits behind the 8-bit main_data_begin and the private bits */
-            int so = 32 + 8 + nch + 63 * ch;
+            int so = 32 + crc + 8 + nch + 63 * ch;
             int a0 = t0, a1 = t1, a2 = t2;
             if (a0 == 14) a0 = 16;
             if (a1 == 14) a1 = 16;
@@ -272,7 +273,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
             lg_put(sm->hdr, so, gi->count1table_select, 1);
         }
         else if (lane == 0) {
-            int so = 32 + 9 + (nch == 2 ? 3 : 5) + 4 * nch + 59 * (gr * nch + ch);
+            int so = 32 + crc + 9 + (nch == 2 ? 3 : 5) + 4 * nch + 59 * (gr * nch + ch);
             int a0 = t0, a1 = t1, a2 = t2;
             if (a0 == 14) a0 = 16;
             if (a1 == 14) a1 = 16;
@@ -304,9 +305,9 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
             lg_put(sm->hdr, so, gi->count1table_select, 1);
         }
     }
-    /* bytes 36..39 of the record, behind the longest side info: the four block types (4 = mixed, 0xff = no such channel) for
+    /* bytes 40..43 of the record, behind the longest side info: the four block types (4 = mixed, 0xff = no such channel) for
      * the host's statistics (encoder.c:156 updateStats) */
-    if (lane == 0) lg_put(sm->hdr, 288 + 8 * warp, (ch < nch && gr < mgr) ? (g4[warp].mixed_block_flag ? 4u : (unsigned) g4[warp].block_type) : 0xffu, 8);
+    if (lane == 0) lg_put(sm->hdr, 320 + 8 * warp, (ch < nch && gr < mgr) ? (g4[warp].mixed_block_flag ? 4u : (unsigned) g4[warp].block_type) : 0xffu, 8);
     /* ---- ancillary drains and the frame header (warps 2 and 3 are the lighter ones in joint stereo) */
     if (warp == 3) lg_put_drain(sm->img, 0, fo->drain_pre, fo->anc_pre, !c->disable_reservoir, lane);
     if (warp == 2) {
@@ -335,6 +336,7 @@ lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ 
         lg_put(sm->hdr, so, (unsigned) c->copyright, 1); so += 1;
         lg_put(sm->hdr, so, (unsigned) c->original, 1); so += 1;
         lg_put(sm->hdr, so, (unsigned) c->emphasis, 2); so += 2;
+        so += crc;
         if (mgr == 1) lg_put(sm->hdr, so, (unsigned) fo->main_data_begin, 8);          /* then nch private bits (0), no scfsi */
         else {
             lg_put(sm->hdr, so, (unsigned) fo->main_data_begin, 9); so += 9;

@@ -167,7 +167,7 @@ typedef struct {
     uint8_t anc_pre, anc_post, pad_[2];
     int32_t bitrate_index;               /* of this frame (constant for CBR, chosen per frame by ABR) */
 } LgFrameOut;
-#define LG_HDR_STRIDE 40                /* bytes reserved per frame for header + side info (sideinfo_len <= 36) */
+#define LG_HDR_STRIDE 44                /* bytes per frame record: header + side info (sideinfo_len <= 38 with CRC), block types at 40..43 */
 #define LG_PAY_SLACK 1024               /* a launch can drain at most the reservoir (511 bytes) on top of its own frames */
 
 /* ---- per-stream state carried across batches (reference PsyStateVar_t util.h:219, ATH_t :166,

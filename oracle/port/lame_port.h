@@ -132,7 +132,7 @@ typedef struct {
     /* bit writer (reference Bit_stream_struc + header ring, util.h:272) */
     unsigned char *buf;
     int   totbit, buf_byte_idx, buf_bit_idx;
-    struct { int write_timing, ptr; unsigned char buf[40]; } header[LP_MAX_HEADER_BUF];
+    struct { int write_timing, ptr; unsigned char buf[40]; } header[LP_MAX_HEADER_BUF];   /* sideinfo_len <= 38 */
     int   h_ptr, w_ptr, ancillary_flag;
     /* last frame's psy products kept for tests */
     float last_pe[2][2];
@@ -147,6 +147,7 @@ lp_encoder *lp_open_vq(int samplerate_in, int samplerate_out, int channels, int 
 int  lp_encode(lp_encoder *e, const short *l, const short *r, int nsamples, unsigned char *out, int cap);
 int  lp_flush(lp_encoder *e, unsigned char *out, int cap);
 void lp_close(lp_encoder *e);
+void lp_set_error_protection(lp_encoder *e);   /* before the first lp_encode */
 
 /* internals shared between the port's files */
 int   lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac);

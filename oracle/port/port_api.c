@@ -51,6 +51,12 @@ lp_encoder *lp_open_vq(int samplerate_in, int samplerate_out, int channels, int 
     return e;
 }
 
+/* lame_set_error_protection(1), lame.c:954: a CRC-16 behind every frame header, two more bytes of side info */
+void lp_set_error_protection(lp_encoder *e)
+{
+    if (!e->cfg.error_protection) { e->cfg.error_protection = 1; e->cfg.sideinfo_len += 2; }
+}
+
 void lp_close(lp_encoder *e)
 {
     if (!e) return;

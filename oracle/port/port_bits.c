@@ -66,6 +66,25 @@ static void writeheader(lp_encoder *e, int val, int j)
     }
     e->header[e->h_ptr].ptr = ptr;
 }
+/* bitstream.c:287 CRC_update + :304 CRC_writeheader: CRC-16 (x^16 + x^15 + x^2 + 1, MSB first, start 0xffff) over header bytes 2-3 and the
+ * side info, stored behind the header */
+static void crc_writeheader(const lp_config *cfg, unsigned char *header)
+{
+    int crc = 0xffff, i, k;
+    for (i = 2; i < cfg->sideinfo_len; i++) {
+        int value;
+        if (i == 4 || i == 5) continue;
+        value = header[i] << 8;
+        for (k = 0; k < 8; k++) {
+            value <<= 1;
+            crc <<= 1;
+            if ((crc ^ value) & 0x10000) crc ^= 0x8005;
+        }
+    }
+    header[4] = crc >> 8;
+    header[5] = crc & 255;
+}
+
 /* bitstream.c:321 encodeSideInfo2 */
 static void encode_side_info(lp_encoder *e, int bitsPerFrame)
 {
@@ -87,6 +106,7 @@ static void encode_side_info(lp_encoder *e, int bitsPerFrame)
     writeheader(e, cfg->copyright, 1);
     writeheader(e, cfg->original, 1);
     writeheader(e, cfg->emphasis, 2);
+    if (cfg->error_protection) writeheader(e, 0, 16);                 /* room for the CRC */
     if (cfg->version != 1) {
         /* MPEG-2/2.5: one granule, 8-bit main_data_begin, 9-bit scalefac_compress, no scfsi, no preflag bit */
         writeheader(e, e->main_data_begin, 8);
@@ -121,6 +141,7 @@ static void encode_side_info(lp_encoder *e, int bitsPerFrame)
             writeheader(e, gi->scalefac_scale, 1);
             writeheader(e, gi->count1table_select, 1);
         }
+        if (cfg->error_protection) crc_writeheader(cfg, e->header[e->h_ptr].buf);
         old = e->h_ptr;
         e->h_ptr = (old + 1) & (LP_MAX_HEADER_BUF - 1);
         e->header[e->h_ptr].write_timing = e->header[old].write_timing + bitsPerFrame;
@@ -164,6 +185,7 @@ static void encode_side_info(lp_encoder *e, int bitsPerFrame)
             writeheader(e, gi->scalefac_scale, 1);
             writeheader(e, gi->count1table_select, 1);
         }
+    if (cfg->error_protection) crc_writeheader(cfg, e->header[e->h_ptr].buf);
     old = e->h_ptr;
     e->h_ptr = (old + 1) & (LP_MAX_HEADER_BUF - 1);
     e->header[e->h_ptr].write_timing = e->header[old].write_timing + bitsPerFrame;

@@ -39,6 +39,7 @@ void *refdump_open_vq(int brate, int mode, int quality, int vbrmode, int vbr_q, 
     lame_set_in_samplerate(gfp, samplerate > 0 ? samplerate : 44100);
     lame_set_num_channels(gfp, nch > 0 ? nch : 2);
     if (out_samplerate > 0) lame_set_out_samplerate(gfp, out_samplerate);
+    if (getenv("LP_CRC")) lame_set_error_protection(gfp, 1);
     if (vbrmode == vbr_abr) { lame_set_VBR(gfp, vbr_abr); if (brate > 0) lame_set_VBR_mean_bitrate_kbps(gfp, brate); }
     else if (vbrmode > 0) { lame_set_VBR(gfp, (vbr_mode) vbrmode); if (vbr_q_frac > 0) lame_set_VBR_quality(gfp, vbr_q + vbr_q_frac); else lame_set_VBR_q(gfp, vbr_q); }
     else if (brate > 0) lame_set_brate(gfp, brate);

@@ -49,6 +49,7 @@ int main(int argc, char **argv)
     h = refdump_open_vq(brate, mode, quality, vbr, (vbr == 4 || vbr == 2) ? brate : 0, qfrac, sr, out_sr, 2);   /* vbr 4 (vbr_mtrh): `brate` is VBR_q */
     /* the same split of the float level as lame_set_VBR_quality (set_get.c:1169) */
     e = lp_open_vq(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr, (vbr == 4 || vbr == 2) ? ((float) brate + qfrac) - (float) brate : 0.f);
+    if (e && getenv("LP_CRC")) lp_set_error_protection(e);            /* refdump_open reads the same variable */
     if (!h || !e) { printf("open failed ref=%p port=%p\n", h, (void *) e); return (!h && !e) ? 0 : 2; }
     refdump_tables(h, &tab);
     {

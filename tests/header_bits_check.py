@@ -15,11 +15,12 @@ import oracle  # noqa: E402
 from conftest import make_signal  # noqa: E402
 
 
-def run(lib, x):
+def run(lib, x, sr=44100, brate=128, crc=0, vbr=0):
     lib.lame_init.restype = ctypes.c_void_p
     h = ctypes.c_void_p(lib.lame_init())
-    for f, v in (("lame_set_in_samplerate", 44100), ("lame_set_num_channels", 2), ("lame_set_brate", 128), ("lame_set_copyright", 1),
-                 ("lame_set_original", 0), ("lame_set_emphasis", 1), ("lame_set_extension", 1), ("lame_set_bWriteVbrTag", 1)):
+    for f, v in (("lame_set_in_samplerate", sr), ("lame_set_num_channels", 2), ("lame_set_brate", brate), ("lame_set_copyright", 1),
+                 ("lame_set_original", 0), ("lame_set_emphasis", 1), ("lame_set_extension", 1), ("lame_set_bWriteVbrTag", 1),
+                 ("lame_set_error_protection", crc), ("lame_set_VBR", vbr), ("lame_set_VBR_q", 3)):
         fn = getattr(lib, f)
         fn.argtypes, fn.restype = [ctypes.c_void_p, ctypes.c_int], ctypes.c_int
         assert fn(h, v) == 0, f
@@ -43,6 +44,12 @@ def main():
     ours = ctypes.CDLL(sys.argv[1])
     ref = ctypes.CDLL(oracle.REF_SO)
     x = make_signal("click", 12 * 1152, seed=3)
+    # error_protection (lame.h:312): CRC-16 behind every header, MPEG-1 and MPEG-2, CBR and VBR
+    for kw in (dict(crc=1), dict(crc=1, sr=22050, brate=64), dict(crc=1, vbr=4), dict(crc=1, vbr=2, sr=48000)):
+        _, a, ta = run(ours, x, **kw)
+        _, b, tb = run(ref, x, **kw)
+        assert a == b, "stream differs with %r" % kw
+        assert ta == tb, "tag frame differs with %r" % kw
     h, a, ta = run(ours, x)
     _, b, tb = run(ref, x)
     assert a == b, "stream differs"

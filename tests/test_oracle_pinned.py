@@ -171,6 +171,14 @@ def test_port_vbr_old_vs_reference(port_vs_ref_bin, args, env):
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
 
+@pytest.mark.parametrize("args,env", [("click 128 -1 -1 60", {}), ("noise 128 3 -1 40", {}), ("click 64 -1 -1 60 22050", {}), ("click 2 -1 -1 60", dict(LP_VBR="4"))])
+def test_port_crc_vs_reference(port_vs_ref_bin, args, env):
+    """error_protection: the CRC-16 behind every frame header (bitstream.c:304), two more bytes of side info in every budget"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_CRC="1", **env))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
 def test_click_signal_has_short_blocks(oracle_mod):
     """the transient fixture must really exercise block switching, otherwise short-block parity is vacuous"""
     x = make_signal("click", 40 * 1152)
