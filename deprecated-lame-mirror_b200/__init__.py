@@ -87,6 +87,7 @@ def load_library(path=None):
         "lamegpu_batch_rerun_device": (c_int, [c_void_p, c_int]),
         "lamegpu_batch_stage_packed": (c_int, [c_void_p, c_void_p, c_int]),
         "lamegpu_batch_kernel_ms": (c_int, [c_void_p, P(ctypes.c_float)]),
+        "lamegpu_batch_step_ms": (ctypes.c_float, [c_void_p]),
         "lamegpu_batch_kernel_launches": (c_long, [c_void_p]),
         "lamegpu_batch_set_threads": (c_int, [c_void_p, c_int]),
         "lamegpu_batch_debug_copy": (c_long, [c_void_p, c_int, c_void_p, ctypes.c_size_t]),
@@ -123,7 +124,7 @@ EXPORTED_SYMBOLS = _option_symbols() + [
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
-    "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
+    "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_step_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
     "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_batch_d2h_bytes",
 ]
 
@@ -281,6 +282,10 @@ class BatchEncoder:
         ms = (ctypes.c_float * 5)()
         self._lib.lamegpu_batch_kernel_ms(self._h, ms)
         return [float(x) for x in ms]
+
+    def step_ms(self):
+        """device time of the last launch, first kernel start to last kernel end (CUDA events)"""
+        return float(self._lib.lamegpu_batch_step_ms(self._h))
 
     def kernel_launches(self):
         return int(self._lib.lamegpu_batch_kernel_launches(self._h))

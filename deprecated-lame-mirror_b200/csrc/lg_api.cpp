@@ -632,6 +632,8 @@ int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5])
     for (int i = 0; i < 5; i++) ms[i] = m[i];
     return 0;
 }
+/* device time of the last launch from the start of its first kernel to the end of its last (the pieces' kernels overlap) */
+float lamegpu_batch_step_ms(const lamegpu_batch *b) { return b ? lg_engine_last_kernel_ms(b->eng)[7] : 0.f; }
 long lamegpu_batch_kernel_launches(const lamegpu_batch *b) { return b ? lg_engine_launch_count(b->eng) : 0; }
 long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap) { return b ? lg_engine_debug_copy(b->eng, what, dst, cap) : -1; }
 size_t lamegpu_sizeof_granule_out(void) { return sizeof(LgGranuleOut); }

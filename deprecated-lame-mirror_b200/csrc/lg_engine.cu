@@ -48,6 +48,8 @@ static void lg_host_free(void *p) { if (p) cudaFreeHost(p); }
 #define LG_MEMSET(dst, v, n, st) cudaMemsetAsync(dst, v, n, st)
 #endif
 
+#define LG_MAX_PIECES 8
+
 struct lg_engine {
     LgDevCfg hcfg;
     LgDevCfg *dcfg;
@@ -67,11 +69,19 @@ struct lg_engine {
     /* kernel R (input-rate conversion): raw input samples, the chunk list and the per-stream header, device + pinned */
     size_t raw_stride; int chunk_cap;
     float *d_raw, *h_raw; LgRsChunk *d_rsc, *h_rsc; LgRsStream *d_rss, *h_rss;
-    lgStream_t stream;
+    /* two CUDA streams: `stream` carries the copies and the stateless/scan kernels (A, B, C) of the batch piece by piece, `stream2` the
+     * quantiser and the packer (D, E), each piece as soon as its A-B-C is done - kernel D is latency-bound and leaves most issue
+     * slots free, so the next piece's A-B-C (and its share of the H2D copy) run underneath it */
+    lgStream_t stream, stream2;
+    int pieces;                       /* how many pieces a launch is cut into along the frame axis (1 = no overlap) */
+    int *d_ready;                     /* one flag per piece: raised on stream 1 behind the piece's kernel C, awaited by kernel D on stream 2 */
 #ifndef LG_EMULATE
-    cudaEvent_t ev[8];
+    cudaEvent_t ev[8];                /* 6, 7: around kernel R */
+    cudaEvent_t pev[LG_MAX_PIECES][8];/* per piece: stream 1 before A, after A, after B, after C; stream 2 before D, after D, after E */
+    cudaEvent_t ev_begin, ev_end;
+    int pieces_used;
 #endif
-    float last_ms[6];
+    float last_ms[8];                 /* A, B, C, D, E summed over the pieces, R, -, 7: begin of the first kernel to end of the last */
     long launches;
 };
 
@@ -120,15 +130,20 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     if (!e) return;
 #ifndef LG_EMULATE
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->stream2) cudaStreamSynchronize(e->stream2);
 #endif
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_xr);
     lg_dev_free(e->d_ana); lg_dev_free(e->d_psy); lg_dev_free(e->d_frm); lg_dev_free(e->d_gout); lg_dev_free(e->d_fout); lg_dev_free(e->d_pay); lg_dev_free(e->d_hdr);
-    lg_dev_free(e->d_state); lg_dev_free(e->d_state0); lg_dev_free(e->d_nfr);
+    lg_dev_free(e->d_state); lg_dev_free(e->d_state0); lg_dev_free(e->d_nfr); lg_dev_free(e->d_ready);
     lg_dev_free(e->d_raw); lg_dev_free(e->d_rsc); lg_dev_free(e->d_rss); lg_host_free(e->h_raw); lg_host_free(e->h_rsc); lg_host_free(e->h_rss);
     lg_host_free(e->h_pcm16); lg_host_free(e->h_pcmf); lg_host_free(e->h_nfr); lg_host_free(e->h_pay); lg_host_free(e->h_hdr); lg_host_free(e->h_fout);
 #ifndef LG_EMULATE
     for (int i = 0; i < 8; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int p = 0; p < LG_MAX_PIECES; p++) for (int i = 0; i < 8; i++) if (e->pev[p][i]) cudaEventDestroy(e->pev[p][i]);
+    if (e->ev_begin) cudaEventDestroy(e->ev_begin);
+    if (e->ev_end) cudaEventDestroy(e->ev_end);
     if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->stream2) cudaStreamDestroy(e->stream2);
 #endif
     free(e);
 }
@@ -160,6 +175,21 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     if (!e) return NULL;
     e->hcfg = *cfg;
     e->S = nstreams; e->F = max_frames; e->device = device;
+    /* VBR kernels settle a frame's size over all its granules at once and run as one piece; CBR/ABR: up to 4 pieces */
+    e->pieces = (cfg->vbr == 0 || cfg->vbr == 3) ? 4 : 1;
+    if (const char *pe = getenv("LAMEGPU_PIECES")) e->pieces = atoi(pe);
+    if (e->pieces < 1) e->pieces = 1;
+    if (e->pieces > LG_MAX_PIECES) e->pieces = LG_MAX_PIECES;
+    if (cfg->vbr == 4 || cfg->vbr == 2) e->pieces = 1;
+#ifndef LG_EMULATE
+    {   /* kernel D waits inside the kernel for the later pieces, whose kernels A-B-C need room on the SMs next to it: up to 7 of D's CTAs
+         * fit on an SM (31 KB shared memory each), so with more than ~5 streams per SM the device could fill up with waiting CTAs.  Then
+         * the batch runs as one piece.  (The wait is bounded in any case: lg_wait_piece traps after ~2 s.) */
+        int nsm = 0;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+        if (nsm < 1 || nstreams > 5 * nsm) e->pieces = 1;
+    }
+#endif
     e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
     {   /* largest frame (padded) minus its side info, per frame, plus what a full reservoir can add */
         int const max_kbps = cfg->vbr ? cfg->bitrate_kbps[cfg->vbr_max_bitrate_index] : cfg->brate;
@@ -182,6 +212,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     bad |= lg_dev_malloc((void **) &e->d_state, S * sizeof(LgStreamState));
     bad |= lg_dev_malloc((void **) &e->d_state0, S * sizeof(LgStreamState));
     bad |= lg_dev_malloc((void **) &e->d_nfr, S * sizeof(int));
+    bad |= lg_dev_malloc((void **) &e->d_ready, LG_MAX_PIECES * sizeof(int));
     bad |= lg_host_malloc((void **) &e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t));
     bad |= lg_host_malloc((void **) &e->h_nfr, S * sizeof(int));
     bad |= lg_host_malloc((void **) &e->h_pay, S * e->pay_stride);
@@ -204,7 +235,10 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     memcpy(e->dcfg, cfg, sizeof *cfg);
 #else
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+    if (cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     for (int i = 0; i < 8; i++) cudaEventCreate(&e->ev[i]);
+    for (int p = 0; p < LG_MAX_PIECES; p++) for (int i = 0; i < 8; i++) cudaEventCreate(&e->pev[p][i]);
+    cudaEventCreate(&e->ev_begin); cudaEventCreate(&e->ev_end);
     if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
@@ -262,75 +296,123 @@ extern "C" int lg_engine_reserve_chunks(lg_engine *e, int per_stream)
     return 0;
 }
 
-/* Launch the four kernels on what is already in device memory (bench "value": inputs resident in HBM).
- * nframes = max over streams of d_nfr[]. */
-extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float)
+/* Launch the kernels on what is already in device memory (bench "value": inputs resident in HBM).  nframes = max over streams of
+ * d_nfr[].  The batch is cut into `pieces` along the frame axis: A, B, C of piece i on stream 1, D and E of piece i on stream 2 behind an
+ * event, so that A-B-C of piece i+1 run under kernel D of piece i.  When h2d_pcm is set, each piece's share of the staged PCM is copied in
+ * front of its kernel A (the 1328-sample halo travels with the first piece). */
+/* kernels D (or D', D'') and E over the whole batch on stream 2; D waits for the pieces' flags as it reaches their frames */
+static void lg_launch_quant_pack(lg_engine *e, int nframes, int P)
 {
     int const S = e->S, F = e->F;
-    if (nframes < 1 || nframes > F) return -1;
-    (void) nframes;
-    const int16_t *p16 = use_float ? NULL : e->d_pcm16;
-    const float *pf = use_float ? e->d_pcmf : NULL;
 #ifndef LG_EMULATE
-    cudaEventRecord(e->ev[0], e->stream);
-#endif
-    LG_LAUNCH(lg_kernel_analysis, S * (2 * F + 1), 128, sizeof(LgSmemA), e->stream,
-              e->dcfg, p16, (int) e->pcm_stride, pf, e->d_sb, e->d_ana, e->d_nfr, 2 * F + 1);
-#ifndef LG_EMULATE
-    cudaEventRecord(e->ev[1], e->stream);
-    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: analysis done (%s)\n", cudaGetErrorString(r)); }
-#endif
-    LG_LAUNCH(lg_kernel_scan, S, 32, sizeof(LgSmemB), e->stream, e->dcfg, e->d_ana, e->d_psy, e->d_frm, e->d_state, e->d_nfr, F);
-#ifndef LG_EMULATE
-    cudaEventRecord(e->ev[2], e->stream);
-    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: scan done (%s)\n", cudaGetErrorString(r)); }
-#endif
-    LG_LAUNCH(lg_kernel_mdct, S * 2 * F, 64, sizeof(LgSmemC), e->stream, e->dcfg, e->d_sb, e->d_psy, e->d_frm, e->d_xr, e->d_nfr, F);
-#ifndef LG_EMULATE
-    cudaEventRecord(e->ev[3], e->stream);
-    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: mdct done (%s)\n", cudaGetErrorString(r)); }
+    cudaEventRecord(e->pev[0][4], e->stream2);
 #endif
     if (e->hcfg.vbr == 4)
-        LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+        LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
     else if (e->hcfg.vbr == 2 && (e->hcfg.substep_shaping & 2))
-        LG_LAUNCH(lg_kernel_vbrold<1>, S, 64, sizeof(LgSmemO), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+        LG_LAUNCH(lg_kernel_vbrold<1>, S, 64, sizeof(LgSmemO), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
     else if (e->hcfg.vbr == 2)
-        LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+        LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
     else if (e->hcfg.substep_shaping & 2)
-        LG_LAUNCH(lg_kernel_quant<1>, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
-                  e->d_state, e->d_nfr, F);
+        LG_LAUNCH(lg_kernel_quant<1>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F, 0, F, e->d_ready, P, nframes);
     else
-        LG_LAUNCH(lg_kernel_quant<0>, S, 64, sizeof(LgSmemD), e->stream, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
-                  e->d_state, e->d_nfr, F);
+        LG_LAUNCH(lg_kernel_quant<0>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
+                  e->d_state, e->d_nfr, F, 0, F, e->d_ready, P, nframes);
 #ifndef LG_EMULATE
-    cudaEventRecord(e->ev[4], e->stream);
-    if (getenv("LAMEGPU_DEBUG_SYNC")) { cudaError_t r = cudaStreamSynchronize(e->stream); fprintf(stderr, "lamegpu: quant done (%s)\n", cudaGetErrorString(r)); }
+    cudaEventRecord(e->pev[0][5], e->stream2);
 #endif
-    LG_LAUNCH(lg_kernel_pack, S * F, 128, sizeof(LgSmemE), e->stream, e->dcfg, e->d_gout, e->d_fout, e->d_pay, (int) e->pay_stride, e->d_hdr, e->d_nfr, F);
+    LG_LAUNCH(lg_kernel_pack, S * F, 128, sizeof(LgSmemE), e->stream2, e->dcfg, e->d_gout, e->d_fout, e->d_pay, (int) e->pay_stride, e->d_hdr,
+              e->d_nfr, F, 0, F);
 #ifndef LG_EMULATE
-    cudaEventRecord(e->ev[5], e->stream);
-    LG_CHECK(cudaGetLastError());
+    cudaEventRecord(e->pev[0][6], e->stream2);
 #endif
-    e->launches += 5;
+    e->launches += 2;
+}
+
+static int lg_run_pieces(lg_engine *e, int nframes, int use_float, int h2d_pcm)
+{
+    int const S = e->S, F = e->F, mgr = e->hcfg.mode_gr;
+    if (nframes < 1 || nframes > F) return -1;
+    const int16_t *p16 = use_float ? NULL : e->d_pcm16;
+    const float *pf = use_float ? e->d_pcmf : NULL;
+    int P = e->pieces;
+    if (P > nframes) P = nframes;
+#ifndef LG_EMULATE
+    e->pieces_used = P;
+    if (P > 1) LG_CHECK(cudaMemsetAsync(e->d_ready, 0, LG_MAX_PIECES * sizeof(int), e->stream));
+    cudaEventRecord(e->ev_begin, e->stream);
+#endif
+    for (int p = 0; p < P; p++) {
+        int const f0 = (int) ((long) nframes * p / P), f1 = (int) ((long) nframes * (p + 1) / P);
+        if (h2d_pcm) {
+            /* samples [576*mgr*f0 (+ the halo, for the first piece: from 0), 576*mgr*f1 + halo) of every channel row */
+            size_t const a = (p == 0) ? 0 : (size_t) 576 * mgr * f0 + LG_PCM_HALO, b = (size_t) 576 * mgr * f1 + LG_PCM_HALO;
+            size_t const esz = use_float ? sizeof(float) : sizeof(int16_t);
+            char *dst = use_float ? (char *) e->d_pcmf : (char *) e->d_pcm16;
+            const char *src = use_float ? (const char *) e->h_pcmf : (const char *) e->h_pcm16;
+#ifdef LG_EMULATE
+            for (size_t r = 0; r < (size_t) S * 2; r++) memcpy(dst + (r * e->pcm_stride + a) * esz, src + (r * e->pcm_stride + a) * esz, (b - a) * esz);
+#else
+            LG_CHECK(cudaMemcpy2DAsync(dst + a * esz, e->pcm_stride * esz, src + a * esz, e->pcm_stride * esz, (b - a) * esz, (size_t) S * 2,
+                                       cudaMemcpyHostToDevice, e->stream));
+#endif
+        }
+        int const slot0 = (f0 == 0) ? 0 : mgr * f0 + 1, nslot = mgr * f1 - slot0 + 1;
+#ifndef LG_EMULATE
+        cudaEventRecord(e->pev[p][0], e->stream);
+#endif
+        LG_LAUNCH(lg_kernel_analysis, S * nslot, 128, sizeof(LgSmemA), e->stream,
+                  e->dcfg, p16, (int) e->pcm_stride, pf, e->d_sb, e->d_ana, e->d_nfr, 2 * F + 1, slot0, nslot);
+#ifndef LG_EMULATE
+        cudaEventRecord(e->pev[p][1], e->stream);
+#endif
+        LG_LAUNCH(lg_kernel_scan, S, 32, sizeof(LgSmemB), e->stream, e->dcfg, e->d_ana, e->d_psy, e->d_frm, e->d_state, e->d_nfr, F, f0, f1);
+#ifndef LG_EMULATE
+        cudaEventRecord(e->pev[p][2], e->stream);
+#endif
+        LG_LAUNCH(lg_kernel_mdct, S * mgr * (f1 - f0), 64, sizeof(LgSmemC), e->stream, e->dcfg, e->d_sb, e->d_psy, e->d_frm, e->d_xr, e->d_nfr, F,
+                  mgr * f0, mgr * (f1 - f0));
+#ifndef LG_EMULATE
+        cudaEventRecord(e->pev[p][3], e->stream);
+        if (P > 1) { lg_kernel_piece_ready<<<1, 1, 0, e->stream>>>(e->d_ready, p); e->launches += 1; }
+        if (p == 0) { cudaStreamWaitEvent(e->stream2, e->pev[0][3], 0); lg_launch_quant_pack(e, nframes, P); }
+#endif
+        e->launches += 3;
+    }
+#ifdef LG_EMULATE
+    lg_launch_quant_pack(e, nframes, P);          /* the emulator runs launches one after the other: quantise when everything is there */
+#endif
+#ifndef LG_EMULATE
+    cudaEventRecord(e->ev_end, e->stream2);
+#endif
     return 0;
 }
+
+extern "C" int lg_engine_run_device(lg_engine *e, int nframes, int use_float) { return lg_run_pieces(e, nframes, use_float, 0); }
 
 extern "C" int lg_engine_sync(lg_engine *e)
 {
 #ifndef LG_EMULATE
     LG_CHECK(cudaStreamSynchronize(e->stream));
-    for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]); e->last_ms[i] = ms; }
+    LG_CHECK(cudaStreamSynchronize(e->stream2));
+    for (int i = 0; i < 5; i++) e->last_ms[i] = 0.f;
+    static const int first[5] = { 0, 1, 2, 4, 5 };
+    for (int p = 0; p < e->pieces_used; p++)
+        for (int i = 0; i < (p == 0 ? 5 : 3); i++) { float ms = 0; cudaEventElapsedTime(&ms, e->pev[p][first[i]], e->pev[p][first[i] + 1]); e->last_ms[i] += ms; }
+    { float ms = 0; cudaEventElapsedTime(&ms, e->ev_begin, e->ev_end); e->last_ms[7] = ms; }
 #endif
     return 0;
 }
 
-/* Full step: H2D of the staged PCM + frame counts, kernels, D2H of the quantised frames, sync. */
+/* Full step: H2D of the staged PCM + frame counts, kernels, D2H of the packed frames, sync. */
 extern "C" int lg_engine_encode(lg_engine *e, int nframes, int use_float)
 {
     size_t const S = e->S, F = e->F;
+    int h2d_pcm = 1;
     if (e->hcfg.resample) {
         /* kernel R turns the staged input samples + chunk lists into the float PCM window */
         int const tiles = (int) ((e->pcm_stride + 255) / 256);
@@ -347,17 +429,14 @@ extern "C" int lg_engine_encode(lg_engine *e, int nframes, int use_float)
 #endif
         e->launches += 1;
         use_float = 1;
+        h2d_pcm = 0;
     }
-    else if (use_float) {
-        if (!e->h_pcmf) return -1;
-        LG_COPY_H2D(e->d_pcmf, e->h_pcmf, S * 2 * e->pcm_stride * sizeof(float), e->stream);
-    }
-    else LG_COPY_H2D(e->d_pcm16, e->h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t), e->stream);
+    else if (use_float && !e->h_pcmf) return -1;
     LG_COPY_H2D(e->d_nfr, e->h_nfr, S * sizeof(int), e->stream);
-    if (lg_engine_run_device(e, nframes, use_float) != 0) return -1;
-    LG_COPY_D2H(e->h_fout, e->d_fout, S * F * sizeof(LgFrameOut), e->stream);
-    LG_COPY_D2H(e->h_pay, e->d_pay, S * e->pay_stride, e->stream);
-    LG_COPY_D2H(e->h_hdr, e->d_hdr, S * F * LG_HDR_STRIDE, e->stream);
+    if (lg_run_pieces(e, nframes, use_float, h2d_pcm) != 0) return -1;
+    LG_COPY_D2H(e->h_fout, e->d_fout, S * F * sizeof(LgFrameOut), e->stream2);
+    LG_COPY_D2H(e->h_pay, e->d_pay, S * e->pay_stride, e->stream2);
+    LG_COPY_D2H(e->h_hdr, e->d_hdr, S * F * LG_HDR_STRIDE, e->stream2);
     if (lg_engine_sync(e) != 0) return -1;
 #ifndef LG_EMULATE
     if (e->hcfg.resample) { float ms = 0; cudaEventElapsedTime(&ms, e->ev[6], e->ev[7]); e->last_ms[5] = ms; }

@@ -313,11 +313,11 @@ __device__ __forceinline__ void lg_partition_and_spread(const LgDevCfg *__restri
 __global__ void __launch_bounds__(128)
 lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__ pcm, int pcm_stride /* samples per channel */,
                    const float *__restrict__ pcmf, float *__restrict__ sb, LgAnalysis *__restrict__ ana,
-                   const int *__restrict__ nfr, int nslots /* 2F+1, F = frames per launch */)
+                   const int *__restrict__ nfr, int nslots /* 2F+1, F = frames per launch */, int slot0, int cnt /* this launch: slots slot0 .. slot0+cnt-1 */)
 {
     LG_DYN_SMEM(LgSmemA, sm);
     int const tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int const stream = blockIdx.x / nslots, slot = blockIdx.x % nslots;
+    int const stream = blockIdx.x / cnt, slot = slot0 + blockIdx.x % cnt;
     int const nch = cfg->channels;
     if (slot > cfg->mode_gr * nfr[stream]) return;           /* this stream has fewer frames (of mode_gr granules) in this launch */
 

@@ -91,12 +91,12 @@ __device__ __forceinline__ void lg_mdct_short(float *io, const float *__restrict
 __global__ void __launch_bounds__(64)
 lg_kernel_mdct(const LgDevCfg *__restrict__ cfg, const float *__restrict__ sb, const LgPsyOut *__restrict__ psy,
                const LgFrameCtl *__restrict__ frm, float *__restrict__ xr_out,
-               const int *__restrict__ nfr, int nframes)
+               const int *__restrict__ nfr, int nframes, int g0, int cnt /* this launch: granules g0 .. g0+cnt-1 */)
 {
     LG_DYN_SMEM(LgSmemC, sm);
     int const lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
     int const ngr = 2 * nframes;
-    int const stream = blockIdx.x / ngr, gb = blockIdx.x % ngr;
+    int const stream = blockIdx.x / cnt, gb = g0 + blockIdx.x % cnt;
     int const nch = cfg->channels;
     if (gb >= cfg->mode_gr * nfr[stream]) return;
     const LgPsyOut *P = psy + (size_t) stream * ngr + gb;

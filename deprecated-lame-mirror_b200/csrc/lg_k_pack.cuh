@@ -100,10 +100,10 @@ __device__ __forceinline__ int lg_pair_code(const LgDevCfg *__restrict__ c, int 
 __global__ void __launch_bounds__(128)
 lg_kernel_pack(const LgDevCfg *__restrict__ c, const LgGranuleOut *__restrict__ gout, const LgFrameOut *__restrict__ fout,
                unsigned char *__restrict__ pay, int pay_stride, unsigned char *__restrict__ hdr_out,
-               const int *__restrict__ nfr, int nframes)
+               const int *__restrict__ nfr, int nframes, int f0, int cnt /* this launch: frames f0 .. f0+cnt-1 */)
 {
     LG_DYN_SMEM(LgSmemE, sm);
-    int const stream = blockIdx.x / nframes, frame = blockIdx.x % nframes;
+    int const stream = blockIdx.x / cnt, frame = f0 + blockIdx.x % cnt;
     if (frame >= nfr[stream]) return;
     int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int const nch = c->channels;

@@ -1447,14 +1447,42 @@ __device__ __forceinline__ void lg_calc_target_bits(const LgDevCfg *__restrict__
             for (int ch = 0; ch < nch; ch++) { targ_bits[gr][ch] *= max_frame_bits; targ_bits[gr][ch] /= totbits; }
 }
 
+/* Wait until piece `p` of the batch has been produced (its flag is raised by lg_kernel_piece_ready on the other stream, behind that
+ * piece's kernel C).  A flag that never comes would hang the GPU, so the wait is bounded and ends in a trap. */
+__device__ __forceinline__ void lg_wait_piece(const int *ready, int p)
+{
+#ifndef LG_EMULATE
+    const volatile int *flag = ready + p;
+    if (*flag == 0) {
+        long spins = 0;
+        while (*flag == 0) {
+            __nanosleep(500);
+            if (++spins > 4000000) lg_runaway();          /* ~2 s */
+        }
+    }
+    __threadfence();
+#else
+    (void) ready; (void) p;
+#endif
+}
+#ifndef LG_EMULATE
+__global__ void lg_kernel_piece_ready(int *ready, int p)
+{
+    __threadfence();
+    ready[p] = 1;
+}
+#endif
+
 /* ---------------------------------------------------------------- the kernel */
 /* SUB = 1: the build of the kernel with substep shaping and one-band amplification (quality 0-2; cfg->substep_shaping & 2).
  * The other quality levels run SUB = 0, whose search loop does not carry that code. */
 template <int SUB>
 __global__ void __launch_bounds__(64)
-lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy,
-                const LgFrameCtl *__restrict__ frm, LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout,
-                LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes)
+lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *xr_in, const LgPsyOut *psy, const LgFrameCtl *frm /* written by kernels of the other
+                stream while this one runs (later pieces): plain coherent loads, no __restrict__ / __ldg on them */,
+                LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout,
+                LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes, int f0, int f1 /* this launch: frames f0 .. f1-1 */,
+                const int *ready, int npieces, int batch_frames /* piece p = frames [batch_frames*p/npieces, batch_frames*(p+1)/npieces) is usable once ready[p] != 0 */)
 {
     LG_DYN_SMEM(LgSmemD, sm);
     int const lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
@@ -1466,9 +1494,20 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
     int old_value = st->old_value[ch], current_step = st->current_step[ch];
     int anc_flag = st->ancillary_flag, pay_off = 0;
 
-    int const my_frames = nfr[stream];
+    int const my_frames = min(nfr[stream], f1);
     int const mgr = cfg->mode_gr;                      /* granules per frame: 2 (MPEG-1) or 1 (MPEG-2/2.5) */
-    for (int frame = 0; frame < my_frames; frame++) {
+    if (f0 > 0 && f0 < my_frames) {                     /* a later piece of the batch: the payload continues behind the previous frame's */
+        const LgFrameOut *pf = fout + (size_t) stream * nframes + (f0 - 1);
+        pay_off = pf->pay_off + pf->pay_bytes;
+    }
+    int piece = 0;
+    for (int frame = f0; frame < my_frames; frame++) {
+        /* the batch arrives in pieces: kernels A-B-C of the later pieces run while this kernel works on the earlier ones, a one-thread
+         * kernel behind each piece's kernel C raises its flag */
+        if (npieces > 1) {
+            while (piece + 1 < npieces && frame >= (int) ((long) batch_frames * (piece + 1) / npieces)) piece++;
+            lg_wait_piece(ready, piece);
+        }
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;
         int const abr = (cfg->vbr == 3);
@@ -1543,7 +1582,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_i
                 __syncwarp();
                 {   /* line -> band map and the lines themselves */
                     const float *src = xr_in + (((size_t) stream * 2 * nframes + gb) * 2 + ch) * 576;
-                    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(w->xr)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+                    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(w->xr)[i] = reinterpret_cast<const float4 *>(src)[i];
                     const unsigned *map = reinterpret_cast<const unsigned *>(qc.block_type == LG_SHORT ? cfg->line_sfb_s : cfg->line_sfb_l);
                     for (int i = lane; i < 144; i += 32) reinterpret_cast<unsigned *>(w->line_sfb)[i] = __ldg(map + i);
                 }

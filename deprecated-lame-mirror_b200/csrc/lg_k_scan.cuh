@@ -8,6 +8,7 @@
 // Reference: L3psycho_anal_vbr psymodel.c:1397 (minus the stateless parts done by kernel A),
 // lame_encode_mp3_frame encoder.c:305 stages 1 and 3, adjust_ATH encoder.c:56.
 #pragma once
+#include <stddef.h>
 #include "lg_math.cuh"
 
 struct LgSmemB {
@@ -217,7 +218,7 @@ __device__ __forceinline__ void lg_adjust_ath(const LgDevCfg *__restrict__ cfg, 
 __global__ void __launch_bounds__(32)
 lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ ana, LgPsyOut *__restrict__ psy,
                LgFrameCtl *__restrict__ frm, LgStreamState *__restrict__ state,
-               const int *__restrict__ nfr, int nframes)
+               const int *__restrict__ nfr, int nframes, int f0, int f1 /* this launch: frames f0 .. f1-1 of the batch */)
 {
     LG_DYN_SMEM(LgSmemB, sm);
     int const lane = threadIdx.x & 31;
@@ -234,9 +235,9 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
     int const n_chn_psy = (cfg->mode == LG_JOINT) ? 4 : nch;
     float const pcfact = 0.6f;
 
-    int const my_frames = nfr[stream];
+    int const my_frames = min(nfr[stream], f1);
     int const mgr = cfg->mode_gr;                 /* granules per frame: 2 (MPEG-1) or 1 (MPEG-2/2.5) */
-    for (int gb = 0; gb < mgr * my_frames; gb++) {
+    for (int gb = mgr * f0; gb < mgr * my_frames; gb++) {
         const LgAnalysis *A = &sm->A;
         {
             static_assert(sizeof(LgAnalysis) % 8 == 0, "LgAnalysis is copied in 8-byte words");
@@ -497,8 +498,12 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
     }
     __syncwarp();
     {
+        /* write back what this kernel owns: the quantiser's fields of the state (reservoir, step-size memory, ancillary flag) may be
+         * written by kernel D of an earlier piece of the batch at the same time */
         int *dst = reinterpret_cast<int *>(state + stream);
         const int *src = reinterpret_cast<const int *>(st);
-        for (int i = lane; i < (int) (sizeof(LgStreamState) / 4); i += 32) dst[i] = src[i];
+        int const q0 = (int) (offsetof(LgStreamState, resv_size) / 4), q1 = (int) (offsetof(LgStreamState, frames_done) / 4);
+        int const qa = (int) (offsetof(LgStreamState, ancillary_flag) / 4);
+        for (int i = lane; i < (int) (sizeof(LgStreamState) / 4); i += 32) if (!((i >= q0 && i < q1) || i == qa)) dst[i] = src[i];
     }
 }

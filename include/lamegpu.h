@@ -157,7 +157,8 @@ long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_st
  * without copies or packing; per-kernel CUDA-event times of the last launch in ms [analysis, scan, mdct, quant] */
 int  lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes);
 int  lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes);
-int  lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5]);   /* analysis, scan, mdct, quantise, pack */
+int  lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5]);   /* analysis, scan, mdct, quantise, pack: summed over the launch's pieces */
+float lamegpu_batch_step_ms(const lamegpu_batch *b);                  /* first kernel start to last kernel end of the last launch */
 long lamegpu_batch_kernel_launches(const lamegpu_batch *b);
 int  lamegpu_batch_set_threads(lamegpu_batch *b, int nthreads);
 long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap);   /* tests: intermediate device buffers */
