@@ -181,13 +181,15 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     if (e->pieces < 1) e->pieces = 1;
     if (e->pieces > LG_MAX_PIECES) e->pieces = LG_MAX_PIECES;
     if (cfg->vbr == 4 || cfg->vbr == 2) e->pieces = 1;
+    /* a profiler that serialises kernels (ncu replays each launch alone) would leave kernel D waiting for flags nobody can raise */
+    if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("COMPUTE_SANITIZER_INJECTION")) e->pieces = 1;
 #ifndef LG_EMULATE
     {   /* kernel D waits inside the kernel for the later pieces, whose kernels A-B-C need room on the SMs next to it: up to 7 of D's CTAs
-         * fit on an SM (31 KB shared memory each), so with more than ~5 streams per SM the device could fill up with waiting CTAs.  Then
-         * the batch runs as one piece.  (The wait is bounded in any case: lg_wait_piece traps after ~2 s.) */
+         * fit on an SM (31 KB shared memory each), so with too many streams per SM the device fills up with waiting CTAs: measured on a B200, 640
+         * streams (4.3 per SM) run, 740 (5 per SM) do not.  Above 4 per SM the batch runs as one piece.  (The wait is bounded in any case: lg_wait_piece traps after ~2 s.) */
         int nsm = 0;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-        if (nsm < 1 || nstreams > 5 * nsm) e->pieces = 1;
+        if (nsm < 1 || nstreams > 4 * nsm) e->pieces = 1;
     }
 #endif
     e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
@@ -250,6 +252,15 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
     cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
+    /* kernels of the two streams share SMs (A-B-C of a later piece next to the resident kernel D): every kernel asks for the same, largest
+     * shared-memory carve-out, so that placing one next to the other never needs an SM to be reconfigured (which would wait for it to drain) */
+    cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lg_kernel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lg_kernel_mdct, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lg_kernel_quant<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lg_kernel_piece_ready, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(lg_kernel_vbrold<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
     cudaFuncSetAttribute(lg_kernel_vbrold<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
 #endif

@@ -41,14 +41,16 @@ struct __attribute__((aligned(16))) LgQWarp {
     float l3_xmin[40], distort[40], pn_noise[40], pn_noise_log[40];
     int   pn_step[40];
     int   sfw[40], sfbst[40];
-    int   width[40], window[40], lstart[41];
+    int   width[40], lstart[41];
     int   act[80];
     float tail_max[40];
     float tail_save[40];             /* tail_max as of save_xrpow (VBR-old keeps xrpow across outer_loop calls) */
-    int   eac[40];                   /* calc_xmin: energy_above_cutoff per band (quantize_pvt.c:643), read by the VBR search */              /* per band: largest xrpow among its lines above max_nonzero_coeff (see lg_scale_bands) */
     int   r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int   comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
     uint8_t line_sfb[576];
+    /* bytes, not ints: sizeof(LgSmemD) has to stay below 32 329 B or only six instead of seven CTAs fit an SM (it matters from 889 streams on) */
+    uint8_t window[40];              /* window 0..2 of a short-block band, 3 for long-block bands */
+    uint8_t eac[40];                 /* calc_xmin: energy_above_cutoff per band (quantize_pvt.c:643), read by the VBR search */
     unsigned ph[2];                  /* QntStateVar_t.pseudohalf as a bit per band: substep shaping (quality 0-2) has the band in its half step */
 };
 struct LgSmemD {
@@ -58,6 +60,7 @@ struct LgSmemD {
     int sf_gr0[2][40];           /* granule-0 scalefactors for scfsi (takehiro.c:964) */
     int bt_gr0[2];
 };
+static_assert(sizeof(LgSmemD) + 1024 <= 233472 / 7, "kernel D: seven CTAs per SM need at most 32 329 B of dynamic shared memory each");
 
 __constant__ uint8_t LG_PRETAB[22] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 3, 3, 3, 2, 0 };
 /* Per-lane table lookups with a different index in every lane are serialised by the constant cache; the small tables of
