@@ -73,6 +73,7 @@ struct lg_engine {
      * quantiser and the packer (D, E), each piece as soon as its A-B-C is done - kernel D is latency-bound and leaves most issue
      * slots free, so the next piece's A-B-C (and its share of the H2D copy) run underneath it */
     lgStream_t stream, stream2;
+    int dense;                        /* more than six streams per SM: kernel D in its seven-CTAs-per-SM build */
     int pieces;                       /* how many pieces a launch is cut into along the frame axis (1 = no overlap) */
     int *d_ready;                     /* one flag per piece: raised on stream 1 behind the piece's kernel C, awaited by kernel D on stream 2 */
 #ifndef LG_EMULATE
@@ -159,6 +160,25 @@ extern "C" int lg_engine_reset_streams(lg_engine *e, int first, int count)
     return 0;
 }
 
+/* Kernels of the two streams share SMs when a launch runs in pieces (A-B-C of a later piece next to the resident kernel D): then every
+ * kernel asks for the same, largest shared-memory carve-out, so that placing one next to the other never needs an SM to be reconfigured
+ * (which would wait for it to drain).  Without pieces the driver's own choice is better: it leaves more L1 for the tables. */
+static void lg_set_carveout(int max_shared)
+{
+#ifndef LG_EMULATE
+    int const v = max_shared ? (int) cudaSharedmemCarveoutMaxShared : (int) cudaSharedmemCarveoutDefault;
+    cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(lg_kernel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(lg_kernel_mdct, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(lg_kernel_quant<0>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+    cudaFuncSetAttribute(lg_kernel_piece_ready, cudaFuncAttributePreferredSharedMemoryCarveout, v);
+#else
+    (void) max_shared;
+#endif
+}
+
 extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device)
 {
     if (nstreams < 1 || max_frames < 1) return NULL;
@@ -190,6 +210,10 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
         int nsm = 0;
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
         if (nsm < 1 || nstreams > 4 * nsm) e->pieces = 1;
+        /* without pieces and with more than four streams per SM: kernel D in its seven-CTAs-per-SM build (measured 700..888 streams x 8
+         * frames: 7.4-7.7 ms against 11.1-11.7 ms; at 592 streams the two are equal) */
+        e->dense = nsm > 0 && nstreams > 4 * nsm;
+        if (const char *de = getenv("LAMEGPU_DENSE")) e->dense = atoi(de);
     }
 #endif
     e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
@@ -250,17 +274,17 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
     cudaFuncSetAttribute(lg_kernel_quant<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+    cudaFuncSetAttribute(lg_kernel_quant<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+    cudaFuncSetAttribute(lg_kernel_quant<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
     cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
-    /* kernels of the two streams share SMs (A-B-C of a later piece next to the resident kernel D): every kernel asks for the same, largest
-     * shared-memory carve-out, so that placing one next to the other never needs an SM to be reconfigured (which would wait for it to drain) */
-    cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lg_kernel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lg_kernel_mdct, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lg_kernel_quant<0>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(lg_kernel_piece_ready, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (getenv("LAMEGPU_DEBUG_OCC")) {
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lg_kernel_quant<0>, 64, sizeof(LgSmemD));
+        fprintf(stderr, "lamegpu: kernel D %zu B smem, %d CTAs per SM\n", sizeof(LgSmemD), nb);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lg_kernel_analysis, 128, sizeof(LgSmemA));
+        fprintf(stderr, "lamegpu: kernel A %zu B smem, %d CTAs per SM\n", sizeof(LgSmemA), nb);
+    }
     cudaFuncSetAttribute(lg_kernel_vbrold<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
     cudaFuncSetAttribute(lg_kernel_vbrold<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
 #endif
@@ -279,6 +303,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
 #endif
         free(h0);
     }
+    lg_set_carveout(e->pieces > 1);
     if (lg_engine_reset_streams(e, 0, nstreams) != 0) { lg_engine_destroy(e); return NULL; }
     return e;
 }
@@ -332,12 +357,13 @@ static void lg_launch_quant_pack(lg_engine *e, int nframes, int P)
     else if (e->hcfg.vbr == 2)
         LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
-    else if (e->hcfg.substep_shaping & 2)
-        LG_LAUNCH(lg_kernel_quant<1>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
-                  e->d_state, e->d_nfr, F, 0, F, e->d_ready, P, nframes);
-    else
-        LG_LAUNCH(lg_kernel_quant<0>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
-                  e->d_state, e->d_nfr, F, 0, F, e->d_ready, P, nframes);
+    else {
+        int const fl = ((e->hcfg.substep_shaping & 2) ? 1 : 0) | (e->dense ? 4 : 0);
+#define LG_LAUNCH_D(FLV) LG_LAUNCH(lg_kernel_quant<FLV>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout, \
+                                   e->d_state, e->d_nfr, F, 0, F, e->d_ready, P, nframes)
+        if (fl == 0) LG_LAUNCH_D(0); else if (fl == 1) LG_LAUNCH_D(1); else if (fl == 4) LG_LAUNCH_D(4); else LG_LAUNCH_D(5);
+#undef LG_LAUNCH_D
+    }
 #ifndef LG_EMULATE
     cudaEventRecord(e->pev[0][5], e->stream2);
 #endif

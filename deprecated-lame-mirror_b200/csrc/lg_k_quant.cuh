@@ -1479,14 +1479,25 @@ __global__ void lg_kernel_piece_ready(int *ready, int p)
 /* ---------------------------------------------------------------- the kernel */
 /* SUB = 1: the build of the kernel with substep shaping and one-band amplification (quality 0-2; cfg->substep_shaping & 2).
  * The other quality levels run SUB = 0, whose search loop does not carry that code. */
-template <int SUB>
-__global__ void __launch_bounds__(64)
-lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *xr_in, const LgPsyOut *psy, const LgFrameCtl *frm /* written by kernels of the other
+#ifdef LG_D_RESTRICT
+#define LG_XR __restrict__
+#define LG_XLD(p) __ldg(p)
+#else
+#define LG_XR
+#define LG_XLD(p) (*(p))
+#endif
+/* FL bit 2 ("dense"): for batches with more than six streams per SM.  Left alone the compiler takes 149 registers, which is best for the
+ * latency of one warp but allows six CTAs per SM; shared memory allows seven, and with the registers kept within that (120) a 4096-stream
+ * batch runs 9 % faster (33.4 -> 30.5 ms for 8 frames) while the 512-stream one would lose 2 % (6.47 -> 6.61 ms). */
+template <int FL>
+__global__ void __launch_bounds__(64, (FL & 4) ? 7 : 1)
+lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *LG_XR xr_in, const LgPsyOut *LG_XR psy, const LgFrameCtl *LG_XR frm /* written by kernels of the other
                 stream while this one runs (later pieces): plain coherent loads, no __restrict__ / __ldg on them */,
                 LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout,
                 LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes, int f0, int f1 /* this launch: frames f0 .. f1-1 */,
                 const int *ready, int npieces, int batch_frames /* piece p = frames [batch_frames*p/npieces, batch_frames*(p+1)/npieces) is usable once ready[p] != 0 */)
 {
+    constexpr int SUB = FL & 1;
     LG_DYN_SMEM(LgSmemD, sm);
     int const lane = threadIdx.x & 31, ch = threadIdx.x >> 5;
     int const stream = blockIdx.x;
@@ -1585,7 +1596,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *xr_in, const LgPs
                 __syncwarp();
                 {   /* line -> band map and the lines themselves */
                     const float *src = xr_in + (((size_t) stream * 2 * nframes + gb) * 2 + ch) * 576;
-                    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(w->xr)[i] = reinterpret_cast<const float4 *>(src)[i];
+                    for (int i = lane; i < 144; i += 32) reinterpret_cast<float4 *>(w->xr)[i] = LG_XLD(reinterpret_cast<const float4 *>(src) + i);
                     const unsigned *map = reinterpret_cast<const unsigned *>(qc.block_type == LG_SHORT ? cfg->line_sfb_s : cfg->line_sfb_l);
                     for (int i = lane; i < 144; i += 32) reinterpret_cast<unsigned *>(w->line_sfb)[i] = __ldg(map + i);
                 }
