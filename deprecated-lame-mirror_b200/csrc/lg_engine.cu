@@ -201,6 +201,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     if (e->pieces < 1) e->pieces = 1;
     if (e->pieces > LG_MAX_PIECES) e->pieces = LG_MAX_PIECES;
     if (cfg->vbr == 4 || cfg->vbr == 2) e->pieces = 1;
+    if (cfg->noise_shaping == 0) e->pieces = 1;      /* quality 7-9: kernel D is too short to hide anything under (1.70e6 frames/s as one piece, 1.28e6 in pieces) */
     /* a profiler that serialises kernels (ncu replays each launch alone) would leave kernel D waiting for flags nobody can raise */
     if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("COMPUTE_SANITIZER_INJECTION")) e->pieces = 1;
 #ifndef LG_EMULATE
