@@ -147,7 +147,7 @@ __device__ __noinline__ int lg_vblock_sf(const LgDevCfg *__restrict__ c, LgVWarp
             int const sfb = lane + 32 * r;
             if (srch[r]) {
                 float const cc = 5.799142446f;
-                int const guess = 210 + (int) (cc * log10f(w->l3_xmin[sfb] / v->blen[sfb]) - .5f);
+                int const guess = 210 + (int) (cc * lg_log10f(w->l3_xmin[sfb] / v->blen[sfb]) - .5f);
                 int const sf_min = v->vbrsfmin[sfb];
                 sfc[r] = guess < sf_min ? sf_min : (guess >= 255 ? 255 : guess);
             }

@@ -8,6 +8,7 @@
 // this path produces.  tests/test_powf.py checks it against the host's powf over 2e8 arguments.
 // pow(x, .5) rounded to float equals (float)sqrt((double)x) for every float x (a 24-bit x cannot have a
 // square root within 2^-50 of a 25-bit rounding boundary), so the device uses the IEEE sqrt.
+// lg_log10f() likewise restates glibc 2.39's log10f (e_log10f.c over e_logf.c) for calc_scalefac (vbrquantize.c:317).
 // Everything here is compiled with -fmad=false: no contraction, same operations as the host build.
 #pragma once
 #include "lg_compat.h"
@@ -82,6 +83,60 @@ __device__ __noinline__ float lg_powf(float x, float y)
     yy = zz * r2 + yy;
     yy = yy * s;
     return (float) yy;
+}
+
+/* glibc 2.39 logf_data (sysdeps/ieee754/flt-32/e_logf_data.c): 16 x { 1/c, log(c) } */
+__constant__ double LG_LOGF_TAB[16][2] = {
+    { 0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2 }, { 0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2 },
+    { 0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2 },  { 0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3 },
+    { 0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3 }, { 0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3 },
+    { 0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4 }, { 0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4 },
+    { 0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5 }, { 0x1p+0, 0x0p+0 },
+    { 0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5 },  { 0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4 },
+    { 0x1.b2036576afce6p-1, 0x1.526e57720db08p-3 },  { 0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3 },
+    { 0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2 },  { 0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2 } };
+
+/* glibc 2.39 log10f = the fdlibm wrapper of sysdeps/ieee754/flt-32/e_log10f.c (x = 2^k * m, log10 = k*log10(2) in two
+ * floats + ivln10 * logf(m), all in binary32) around the table-driven logf of e_logf.c (binary64 inside, one rounding).
+ * The one run-time caller on this path is calc_scalefac (vbrquantize.c:317, the quality-7 step guess of VBR-new);
+ * its argument l3_xmin / width is a positive float, possibly subnormal, inf when the threshold overflowed.
+ * tests/test_powf.py checks it against the host's log10f on every positive float. */
+__device__ __noinline__ float lg_log10f(float x)
+{
+    int hx = __float_as_int(x), k = 0;
+    if (hx < 0x00800000) {
+        if ((hx & 0x7fffffff) == 0) return __uint_as_float(0xff800000u);          /* log10(+-0) = -inf */
+        if (hx < 0) return __uint_as_float(0x7fc00000u);                          /* log10(-#) = NaN   */
+        k -= 25;
+        x *= 3.3554432000e+07f;                                                   /* subnormal: scale by 2^25 */
+        hx = __float_as_int(x);
+    }
+    if (hx >= 0x7f800000) return x + x;
+    k += (hx >> 23) - 127;
+    int const i = (int) (((unsigned) k & 0x80000000u) >> 31);
+    hx = (hx & 0x007fffff) | ((0x7f - i) << 23);
+    float const y = (float) (k + i);
+    /* e_logf.c on m = 2^-i * 1.f, which is a normal number in [0.5, 2) */
+    float lf;
+    unsigned const ix = (unsigned) hx;
+    if (ix == 0x3f800000u) lf = 0.f;
+    else {
+        unsigned const tmp = ix - 0x3f330000u;
+        int const ti = (int) ((tmp >> 19) & 15u);
+        int const tk = (int) tmp >> 23;
+        unsigned const iz = ix - (tmp & (0x1ffu << 23));
+        double const invc = LG_LOGF_TAB[ti][0], logc = LG_LOGF_TAB[ti][1];
+        double const z = (double) __uint_as_float(iz);
+        double const r = z * invc - 1;
+        double const y0 = logc + (double) tk * 0x1.62e42fefa39efp-1;
+        double const r2 = r * r;
+        double yy = 0x1.5575b0be00b6ap-2 * r + -0x1.ffffef20a4123p-2;
+        yy = -0x1.00ea348b88334p-2 * r2 + yy;
+        yy = yy * r2 + (y0 + r);
+        lf = (float) yy;
+    }
+    float const z = y * 7.9034151668e-07f + 4.3429449201e-01f * lf;
+    return z + y * 3.0102920532e-01f;
 }
 
 /* util.c:977 fast_log2 (513-entry table + linear interpolation) */

@@ -833,7 +833,6 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
         if (quality < 5) quality = 0;
         if (quality > 7) quality = 7;
         }
-        if (quality == 7) return -1;      /* guess_scalefac_x34 (vbrquantize.c:317) calls log10f at run time: not restated on the device */
         c->sfb21_extra = (vbr_q >= 3) ? 0 : (samplerate > 44000);     /* experimentalY from the preset, lame.c:996-999 */
         goto presets_done;
     }

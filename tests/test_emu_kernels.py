@@ -36,7 +36,9 @@ def test_emulated_kernels_abr_match_port(emu_bin, args):
     assert "IDENTICAL" in r.stdout
 
 
-@pytest.mark.parametrize("args", ["4 12 4 2 -1 -1 44100 1152", "4 16 8 0 -1 -1 44100 1152", "3 16 16 4 0 5 48000 777", "2 12 4 5 3 -1 44100 1152"])
+@pytest.mark.parametrize("args", ["4 12 4 2 -1 -1 44100 1152", "4 16 8 0 -1 -1 44100 1152", "3 16 16 4 0 5 48000 777", "2 12 4 5 3 -1 44100 1152",
+                                  # quality 7-9: guess_scalefac_x34 (vbrquantize.c:324) through lg_log10f
+                                  "4 12 4 2 -1 7 44100 1152", "3 12 8 4 0 8 48000 777", "4 10 4 0 -1 9 44100 1152", "3 10 4 4 -1 7 22050 1152"])
 def test_emulated_kernels_vbr_match_port(emu_bin, args):
     """VBR-new (vbr_mtrh; the 4th argument is VBR_q): lg_kernel_vbr incl. the out-of-bits path (click streams at -V0)"""
     r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, LP_VBR="4"))

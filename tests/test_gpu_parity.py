@@ -105,6 +105,9 @@ def test_abr_batch_matches_oracle(lib, oracle_mod, cfg):
     dict(S=4, F=16, fpl=8, q=0, sr=48000), dict(S=3, F=16, fpl=8, q=5, mode=3), dict(S=4, F=20, fpl=20, q=6, quality=6),
     # levels between the presets (lame_set_VBR_quality), -V7 (32 kHz output through the resampler), VBR at 32 kHz input
     dict(S=4, F=20, fpl=8, q=2.5), dict(S=4, F=16, fpl=8, q=5.3, sr=48000), dict(S=4, F=20, fpl=8, q=7), dict(S=4, F=16, fpl=4, q=3, sr=32000),
+    # quality 7-9: the step guess of vbrquantize.c:324 (log10f restated on the device as lg_log10f)
+    dict(S=8, F=20, fpl=8, q=2, quality=7), dict(S=4, F=16, fpl=16, q=4, quality=9, sr=48000), dict(S=4, F=16, fpl=4, q=0, mode=0, quality=8),
+    dict(S=4, F=16, fpl=8, q=5, quality=7, sr=22050),
 ])
 def test_vbr_batch_matches_oracle(lib, oracle_mod, cfg):
     """VBR-new (vbr_mtrh, -V q): lg_kernel_vbr - per-band step search, fitting, and for the frames that do not

@@ -126,6 +126,16 @@ def test_port_quality_0_to_2_vs_reference(port_vs_ref_bin, args, env):
     assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
 
 
+@pytest.mark.parametrize("args", ["click 2 -1 7 60 44100", "noise 4 -1 8 40 44100", "sine 0 -1 9 40 48000", "gap 5 3 7 40 32000",
+                                  "click 6 0 7 60 44100", "click 4 -1 7 40 22050"])
+def test_port_vbr_new_quality_7_to_9_vs_reference(port_vs_ref_bin, args):
+    """VBR-new with quality 7-9 (the 4th argument): guess_scalefac_x34 (vbrquantize.c:324) instead of the per-band step search -
+    one log10f per band, the host's libm here as in the reference"""
+    r = subprocess.run([port_vs_ref_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, env=dict(os.environ, LP_VBR="4"))
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "setup tables: identical" in r.stdout and "IDENTICAL" in r.stdout.splitlines()[-1]
+
+
 @pytest.mark.parametrize("args,env", [
     ("click 7 -1 -1 60 44100", {}), ("noise 2 -1 -1 40 32000", {}), ("click 5 -1 -1 60 32000", {}), ("click 2 -1 -1 60 44100", dict(LP_VBRQ_FRAC="0.5")),
     ("sine 5 -1 -1 60 48000", dict(LP_VBRQ_FRAC="0.3")), ("click 6 -1 -1 60 44100", dict(LP_VBRQ_FRAC="0.9")), ("gap 0 -1 -1 60 44100", dict(LP_VBRQ_FRAC="0.77")),

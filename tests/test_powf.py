@@ -1,6 +1,7 @@
 """CPU suite: lg_powf (csrc/lg_math.cuh), the device's restatement of glibc's powf, against the host's powf bit for bit.
 The kernels call it where the reference calls libm at run time (athAdjust quantize_pvt.c:572, NS_INTERP psymodel.c:452); the
-source is compiled for the host through the emulator shims (tests/c/powf_check.cpp)."""
+source is compiled for the host through the emulator shims (tests/c/powf_check.cpp).  Likewise lg_log10f against the host's log10f
+(calc_scalefac vbrquantize.c:317, the quality-7 step guess of VBR-new) on every non-negative float (tests/c/log10f_check.cpp)."""
 import os
 import subprocess
 
@@ -12,4 +13,12 @@ def test_lg_powf_matches_host_powf(tmp_path):
     subprocess.run(["g++", "-O2", "-fno-fast-math", "-ffp-contract=off", "-std=c++17", "-DLG_EMULATE", "-I" + os.path.join(ROOT, "tests/emu"),
                     "-I" + os.path.join(ROOT, "deprecated-lame-mirror_b200/csrc"), "-w", os.path.join(ROOT, "tests/c/powf_check.cpp"), "-o", exe, "-lm"], check=True)
     r = subprocess.run([exe, "200"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:]
+
+
+def test_lg_log10f_matches_host_log10f_exhaustively(tmp_path):
+    exe = str(tmp_path / "log10f_check")
+    subprocess.run(["g++", "-O2", "-fno-fast-math", "-ffp-contract=off", "-std=c++17", "-DLG_EMULATE", "-I" + os.path.join(ROOT, "tests/emu"),
+                    "-I" + os.path.join(ROOT, "deprecated-lame-mirror_b200/csrc"), "-w", os.path.join(ROOT, "tests/c/log10f_check.cpp"), "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)         # stride 1: all 2 139 095 041 floats in [+0, +inf]
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:]
