@@ -125,7 +125,7 @@ EXPORTED_SYMBOLS = _option_symbols() + [
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
     "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_step_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
-    "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_batch_d2h_bytes",
+    "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_math_selftest", "lamegpu_batch_d2h_bytes",
 ]
 
 

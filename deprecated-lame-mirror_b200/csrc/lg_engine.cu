@@ -512,3 +512,34 @@ extern "C" long lg_engine_debug_copy(lg_engine *e, int what, void *dst, size_t c
 #endif
     return (long) n;
 }
+
+#ifndef LG_EMULATE
+/* Test hook (tests/test_gpu_parity.py): the restated libm functions of lg_math.cuh evaluated on the device, so that the GPU suite can
+ * compare them with the host's libm argument by argument.  fn: 0 lg_powf(x, y), 1 lg_log10f(x), 2 lg_exp(x), 3 lg_pow(x, y); the
+ * binary32 ones take and return their floats widened to double (exact). */
+__global__ void lg_kernel_math_selftest(int fn, const double *__restrict__ x, const double *__restrict__ y, double *__restrict__ out, int n)
+{
+    int const i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    switch (fn) {
+    case 0: out[i] = (double) lg_powf((float) x[i], (float) y[i]); break;
+    case 1: out[i] = (double) lg_log10f((float) x[i]); break;
+    case 2: out[i] = lg_exp(x[i]); break;
+    default: out[i] = lg_pow(x[i], y[i]); break;
+    }
+}
+extern "C" int lamegpu_math_selftest(int fn, const double *x, const double *y, double *out, int n)
+{
+    if (fn < 0 || fn > 3 || n <= 0 || !x || !y || !out) return -1;
+    double *d = nullptr;
+    size_t const bytes = (size_t) n * sizeof(double);
+    if (cudaMalloc(&d, 3 * bytes) != cudaSuccess) { fprintf(stderr, "lamegpu: no CUDA device for the math self-test\n"); return -1; }
+    cudaMemcpy(d, x, bytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(d + n, y, bytes, cudaMemcpyHostToDevice);
+    lg_kernel_math_selftest<<<(n + 255) / 256, 256>>>(fn, d, d + n, d + 2 * (size_t) n, n);
+    cudaError_t const err = cudaMemcpy(out, d + 2 * (size_t) n, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (err != cudaSuccess) { fprintf(stderr, "lamegpu: math self-test: %s\n", cudaGetErrorString(err)); return -1; }
+    return 0;
+}
+#endif

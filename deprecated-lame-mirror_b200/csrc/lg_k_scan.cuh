@@ -486,9 +486,9 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                      * value is what the next frame's psycho-acoustics sees.  exp and pow in double, rounded to float as the reference's. */
                     float const pe_last = sm->frame_pe[mgr - 1][off + nch - 1] * f;
                     float adjust, db;
-                    if (sm->frame_bt[mgr - 1][nch - 1] != LG_SHORT) { adjust = (float) (1.28 / (1 + exp(3.5 - pe_last / 300.)) - 0.05); db = cfg->mask_adjust - adjust; }
-                    else { adjust = (float) (2.56 / (1 + exp(3.5 - pe_last / 300.)) - 0.14); db = cfg->mask_adjust_short - adjust; }
-                    st->masking_lower = (float) pow(10.0, db * 0.1);
+                    if (sm->frame_bt[mgr - 1][nch - 1] != LG_SHORT) { adjust = (float) (1.28 / (1 + lg_exp(3.5 - pe_last / 300.)) - 0.05); db = cfg->mask_adjust - adjust; }
+                    else { adjust = (float) (2.56 / (1 + lg_exp(3.5 - pe_last / 300.)) - 0.14); db = cfg->mask_adjust_short - adjust; }
+                    st->masking_lower = (float) lg_pow(10.0, db * 0.1);
                 }
                 F->masking_lower = st->masking_lower;
                 st->frames_done++;

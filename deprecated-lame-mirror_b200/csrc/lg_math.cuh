@@ -1,6 +1,7 @@
 // lg_math.cuh - scalar device helpers whose results must match the host's bit for bit.
 //
-// The reference calls libm at run time in three places on this path: powf() in athAdjust
+// The reference calls libm at run time in a few places on this path (VBR-new adds log10f, VBR-old exp and pow: see lg_log10f, lg_exp,
+// lg_pow below); for CBR/ABR in three: powf() in athAdjust
 // (quantize_pvt.c:572) and NS_INTERP (psymodel.c:452), and pow(x, .5) in amp_scalefac_bands
 // (quantize.c:758).  The GPU cannot call glibc, so lg_powf() restates glibc 2.39's powf
 // (sysdeps/ieee754/flt-32/e_powf.c: 16-entry log2 table + degree-5 polynomial, 32-entry exp2 table +
@@ -137,6 +138,80 @@ __device__ __noinline__ float lg_log10f(float x)
     }
     float const z = y * 7.9034151668e-07f + 4.3429449201e-01f * lf;
     return z + y * 3.0102920532e-01f;
+}
+
+#include "lg_libm_tab.inc"
+
+/* glibc 2.39 exp (sysdeps/ieee754/dbl-64/e_exp.c): x = k ln2/128 + r, 2^(k/128) from a 128-entry table with a tail, degree-5 polynomial.
+ * On x86-64 glibc dispatches to the copy of that file built with -mfma (sysdeps/x86_64/fpu/multiarch/e_exp-fma.c, picked on every CPU
+ * with AVX2 + FMA), in which the compiler contracted each a*b + c of the source into one fused operation; the fma() calls below are that
+ * build's operations in its order (read off its machine code), so the result is the host libm's bit for bit - the reference's own result
+ * is that of the libm it runs on.  The one run-time caller on this path is the masking feedback of VBR-old (quantize.c:1419-1426):
+ * exp(3.5 - pe/300), |x| < 512.  Outside [2^-54, 512) glibc runs its special cases (1 + x, overflow, subnormal results): CUDA's exp
+ * stands in there, unreachable for a finite perceptual entropy below 1.5e5.  tests/test_powf.py checks both against the host's libm. */
+__device__ __forceinline__ double lg_exp_core(double x, double xtail, bool has_tail)
+{
+    double kd = fma(x, 0x1.71547652b82fep+7, 0x1.8p+52);
+    unsigned long long const ki = (unsigned long long) __double_as_longlong(kd);
+    kd -= 0x1.8p+52;
+    double r = fma(kd, -0x1.cf79abc9e3b3ap-47, fma(kd, -0x1.62e42fefa0000p-8, x));
+    if (has_tail) r = xtail + r;
+    unsigned const idx = 2u * (unsigned) (ki & 127u);
+    unsigned long long const top = ki << (52 - 7);
+    double const tail = __longlong_as_double((long long) LG_EXP_TAB[idx]);
+    unsigned long long const sbits = LG_EXP_TAB[idx + 1] + top;
+    double const r2 = r * r;
+    double const lo = fma(r, 0x1.555555555543cp-3, 0x1.ffffffffffdbdp-2);
+    double const hi = fma(r, 0x1.1111167a4d017p-7, 0x1.55555cf172b91p-5);
+    double const tmp = fma(hi, r2 * r2, fma(lo, r2, r + tail));
+    double const scale = __longlong_as_double((long long) sbits);
+    return fma(tmp, scale, scale);
+}
+__device__ __noinline__ double lg_exp(double x)
+{
+    unsigned const abstop = (unsigned) ((unsigned long long) __double_as_longlong(x) >> 52) & 0x7ffu;
+    if (abstop - 0x3c9u >= 0x408u - 0x3c9u) return exp(x);
+    return lg_exp_core(x, 0.0, false);
+}
+
+/* glibc 2.39 pow (sysdeps/ieee754/dbl-64/e_pow.c, its -mfma build as above) for a positive normal base and an exponent whose result is a
+ * normal number: log(x) as hi + lo from a 128-entry table and a degree-7 polynomial, y log(x) as ehi + elo, then the exp above with the
+ * tail.  Caller: pow(10.0, masking_lower_db * 0.1) of VBR-old (quantize.c:1426), |y| < 4; glibc's special cases (y = 0 among them) go to
+ * CUDA's pow, exact there. */
+__device__ __noinline__ double lg_pow(double x, double y)
+{
+    unsigned long long const ix = (unsigned long long) __double_as_longlong(x), iy = (unsigned long long) __double_as_longlong(y);
+    unsigned const topx = (unsigned) (ix >> 52), topy = (unsigned) (iy >> 52) & 0x7ffu;
+    if (topx - 0x001u >= 0x7ffu - 0x001u || topy - 0x3beu >= 0x43eu - 0x3beu) return pow(x, y);
+    unsigned long long const tmp = ix - 0x3fe6955500000000ull;
+    int const i = (int) ((tmp >> (52 - 7)) & 127u);
+    int const k = (int) ((long long) tmp >> 52);
+    unsigned long long const iz = ix - (tmp & (0xfffull << 52));
+    double const z = __longlong_as_double((long long) iz), kd = (double) k;
+    double const invc = LG_POWLOG_TAB[i][0], logc = LG_POWLOG_TAB[i][1], logctail = LG_POWLOG_TAB[i][2];
+    double const t1 = fma(kd, 0x1.62e42fefa3800p-1, logc);
+    double const lo1 = fma(kd, 0x1.ef35793c76730p-45, logctail);
+    double const r = fma(z, invc, -1.0);
+    double const ar = r * -0x1p-1;
+    double const q12 = fma(r, 0x1.0000000000006p-1, -0x1.555555555556p-1);
+    double const q34 = fma(r, -0x1.555555529a47ap-1, 0x1.999999959554ep-1);
+    double const t2 = r + t1;
+    double const lo2 = (t1 - t2) + r;
+    double const ar2 = r * ar;
+    double const ar3 = r * ar2;
+    double const lo3 = fma(ar, r, -ar2);
+    double const hi = t2 + ar2;
+    double const q56 = fma(r, 0x1.0002b8b263fc3p+0, -0x1.2495b9b4845e9p+0);
+    double const lo4 = (t2 - hi) + ar2;
+    double const q = fma(ar2, fma(q56, ar2, q34), q12);
+    double const lo = fma(ar3, q, ((lo1 + lo2) + lo3) + lo4);
+    double const lhi = hi + lo;
+    double const ltail = (hi - lhi) + lo;
+    double const ehi = y * lhi;
+    double const elo = fma(y, ltail, fma(lhi, y, -ehi));
+    unsigned const abstop = (unsigned) ((unsigned long long) __double_as_longlong(ehi) >> 52) & 0x7ffu;
+    if (abstop - 0x3c9u >= 0x408u - 0x3c9u) return pow(x, y);
+    return lg_exp_core(ehi, elo, true);
 }
 
 /* util.c:977 fast_log2 (513-entry table + linear interpolation) */

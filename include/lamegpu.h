@@ -165,6 +165,9 @@ long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap)
 size_t lamegpu_sizeof_granule_out(void);
 long lamegpu_batch_d2h_bytes(const lamegpu_batch *b);              /* device->host bytes per launch */
 size_t lamegpu_sizeof_analysis(void);
+/* tests: the device restatements of the reference's run-time libm calls (csrc/lg_math.cuh) on n arguments;
+ * fn 0 powf(x, y), 1 log10f(x), 2 exp(x), 3 pow(x, y); floats travel widened to double.  0 = ok, -1 = no CUDA device */
+int  lamegpu_math_selftest(int fn, const double *x, const double *y, double *out, int n);
 
 #ifdef __cplusplus
 }

@@ -456,3 +456,45 @@ def test_c_harness_ragged_streams():
         ge.build_test_binaries()
     r = subprocess.run([exe, "24", "20", "6", "128", "-1", "-1", "44100", "2500"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_device_libm_restatements_match_host_libm(lib):
+    """lg_powf / lg_log10f / lg_exp / lg_pow (csrc/lg_math.cuh) evaluated ON THE DEVICE against this host's glibc, argument by argument:
+    powf in athAdjust / NS_INTERP, log10f in calc_scalefac (vbrquantize.c:317), exp and pow in the masking feedback of VBR-old
+    (quantize.c:1419-1426).  The CPU suite checks the same sources compiled for the host on 2e8 .. 2e9 arguments (tests/test_powf.py)."""
+    import ctypes
+    import math
+    L = lib.load_library()
+    dp = ctypes.POINTER(ctypes.c_double)
+    L.lamegpu_math_selftest.argtypes, L.lamegpu_math_selftest.restype = [ctypes.c_int, dp, dp, dp, ctypes.c_int], ctypes.c_int
+    libm = ctypes.CDLL("libm.so.6")
+    libm.powf.argtypes, libm.powf.restype = [ctypes.c_float, ctypes.c_float], ctypes.c_float
+    libm.log10f.argtypes, libm.log10f.restype = [ctypes.c_float], ctypes.c_float
+    rng = np.random.default_rng(5)
+    n = 20000
+
+    def device(fn, x, y):
+        x, y, out = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64), np.empty(len(x), np.float64)
+        assert L.lamegpu_math_selftest(fn, x.ctypes.data_as(dp), y.ctypes.data_as(dp), out.ctypes.data_as(dp), len(x)) == 0
+        return out
+
+    # powf: base 10 with athAdjust's exponents, and ratios over the float range with exponents in (0, 1)
+    x = np.concatenate([np.full(n // 2, 10.0, np.float32), rng.integers(1, 0x7f800000, n // 2).astype(np.uint32).view(np.float32)])
+    y = np.concatenate([(rng.uniform(-40, 40, n // 2).astype(np.float32) * np.float32(0.1)), rng.uniform(0, 1, n // 2).astype(np.float32)])
+    want = np.array([libm.powf(float(a), float(b)) for a, b in zip(x, y)], np.float32)
+    assert np.array_equal(device(0, x, y).astype(np.float32).view(np.uint32), want.view(np.uint32))
+    # log10f: positive floats of every exponent, subnormals included
+    x = rng.integers(1, 0x7f800000, n).astype(np.uint32).view(np.float32)
+    want = np.array([libm.log10f(float(a)) for a in x], np.float32)
+    assert np.array_equal(device(1, x, x).astype(np.float32).view(np.uint32), want.view(np.uint32))
+    # exp(3.5 - pe / 300.) and pow(10, db * 0.1) as VBR-old forms them, plus a wider range
+    pe = rng.uniform(0, 6000, n).astype(np.float32)
+    x = np.concatenate([3.5 - pe.astype(np.float64) / 300., rng.uniform(-500, 500, n)])
+    want = np.array([math.exp(a) for a in x], np.float64)
+    assert np.array_equal(device(2, x, x).view(np.uint64), want.view(np.uint64))
+    db = rng.uniform(-12, 12, n).astype(np.float32)
+    y = np.concatenate([db.astype(np.float64) * 0.1, rng.uniform(-100, 100, n)])
+    x = np.concatenate([np.full(n, 10.0), rng.uniform(0.001, 1000, n)])
+    want = np.array([math.pow(a, b) for a, b in zip(x, y)], np.float64)
+    assert np.array_equal(device(3, x, y).view(np.uint64), want.view(np.uint64))

@@ -22,3 +22,17 @@ def test_lg_log10f_matches_host_log10f_exhaustively(tmp_path):
                     "-I" + os.path.join(ROOT, "deprecated-lame-mirror_b200/csrc"), "-w", os.path.join(ROOT, "tests/c/log10f_check.cpp"), "-o", exe, "-lm"], check=True)
     r = subprocess.run([exe, "1"], capture_output=True, text=True, timeout=600)         # stride 1: all 2 139 095 041 floats in [+0, +inf]
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:]
+
+
+def test_lg_exp_and_lg_pow_match_host_libm(tmp_path):
+    """the masking feedback of VBR-old (quantize.c:1419-1426) calls exp and pow in binary64 once per frame: lg_exp / lg_pow restate the
+    host glibc's (x86-64 FMA build) operations; 4e7 arguments each over and beyond what the feedback can produce"""
+    import platform
+    if platform.machine() != "x86_64" or "fma" not in open("/proc/cpuinfo").read():
+        import pytest
+        pytest.skip("the restated build of glibc's exp/pow is the one x86-64 hosts with FMA run")
+    exe = str(tmp_path / "exppow_check")
+    subprocess.run(["g++", "-O2", "-fno-fast-math", "-ffp-contract=off", "-mfma", "-std=c++17", "-DLG_EMULATE", "-I" + os.path.join(ROOT, "tests/emu"),
+                    "-I" + os.path.join(ROOT, "deprecated-lame-mirror_b200/csrc"), "-w", os.path.join(ROOT, "tests/c/exppow_check.cpp"), "-o", exe, "-lm"], check=True)
+    r = subprocess.run([exe, "40"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:]
