@@ -147,9 +147,9 @@ __device__ __noinline__ float lg_log10f(float x)
  * with AVX2 + FMA), in which the compiler contracted each a*b + c of the source into one fused operation; the fma() calls below are that
  * build's operations in its order (read off its machine code), so the result is the host libm's bit for bit - the reference's own result
  * is that of the libm it runs on.  The one run-time caller on this path is the masking feedback of VBR-old (quantize.c:1419-1426):
- * exp(3.5 - pe/300), |x| < 512.  Outside [2^-54, 512) glibc runs its special cases (1 + x, overflow, subnormal results): CUDA's exp
- * stands in there, unreachable for a finite perceptual entropy below 1.5e5.  tests/test_powf.py checks both against the host's libm. */
-__device__ __forceinline__ double lg_exp_core(double x, double xtail, bool has_tail)
+ * exp(3.5 - pe/300).  Where glibc's result is 1 + x (|x| < 2^-54), inf, 0 or a subnormal number (x < -708.39) CUDA's exp stands in: the
+ * first three are the same values, the last is unreachable for a perceptual entropy below 2e5.  tests/test_powf.py checks both against the host's libm. */
+__device__ __forceinline__ double lg_exp_core(double x, double xtail, bool has_tail, bool large, bool *subnormal)
 {
     double kd = fma(x, 0x1.71547652b82fep+7, 0x1.8p+52);
     unsigned long long const ki = (unsigned long long) __double_as_longlong(kd);
@@ -164,14 +164,27 @@ __device__ __forceinline__ double lg_exp_core(double x, double xtail, bool has_t
     double const lo = fma(r, 0x1.555555555543cp-3, 0x1.ffffffffffdbdp-2);
     double const hi = fma(r, 0x1.1111167a4d017p-7, 0x1.55555cf172b91p-5);
     double const tmp = fma(hi, r2 * r2, fma(lo, r2, r + tail));
+    if (large) {
+        /* e_exp.c specialcase(), 512 <= |x| < 1024: the scale 2^(k/128) alone would over- or underflow */
+        if ((ki & 0x80000000ull) == 0) {
+            double const scale = __longlong_as_double((long long) (sbits - (1009ull << 52)));
+            return 0x1p1009 * fma(scale, tmp, scale);
+        }
+        double const scale = __longlong_as_double((long long) (sbits + (1022ull << 52)));
+        double const yy = scale + scale * tmp;                                  /* not fused in the host's build */
+        if (fabs(yy) < 1.0) { *subnormal = true; return 0.0; }                  /* subnormal result: the caller falls back */
+        return 0x1p-1022 * yy;
+    }
     double const scale = __longlong_as_double((long long) sbits);
     return fma(tmp, scale, scale);
 }
 __device__ __noinline__ double lg_exp(double x)
 {
     unsigned const abstop = (unsigned) ((unsigned long long) __double_as_longlong(x) >> 52) & 0x7ffu;
-    if (abstop - 0x3c9u >= 0x408u - 0x3c9u) return exp(x);
-    return lg_exp_core(x, 0.0, false);
+    if (abstop - 0x3c9u >= 0x409u - 0x3c9u) return exp(x);                      /* |x| < 2^-54: 1 + x; |x| >= 1024: inf or 0 */
+    bool sub = false;
+    double const v = lg_exp_core(x, 0.0, false, abstop == 0x408u, &sub);
+    return sub ? exp(x) : v;
 }
 
 /* glibc 2.39 pow (sysdeps/ieee754/dbl-64/e_pow.c, its -mfma build as above) for a positive normal base and an exponent whose result is a
@@ -210,8 +223,10 @@ __device__ __noinline__ double lg_pow(double x, double y)
     double const ehi = y * lhi;
     double const elo = fma(y, ltail, fma(lhi, y, -ehi));
     unsigned const abstop = (unsigned) ((unsigned long long) __double_as_longlong(ehi) >> 52) & 0x7ffu;
-    if (abstop - 0x3c9u >= 0x408u - 0x3c9u) return pow(x, y);
-    return lg_exp_core(ehi, elo, true);
+    if (abstop - 0x3c9u >= 0x409u - 0x3c9u) return pow(x, y);                    /* result 1, inf or 0 */
+    bool sub = false;
+    double const v = lg_exp_core(ehi, elo, true, abstop == 0x408u, &sub);
+    return sub ? pow(x, y) : v;
 }
 
 /* util.c:977 fast_log2 (513-entry table + linear interpolation) */

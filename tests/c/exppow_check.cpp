@@ -25,8 +25,8 @@ int main(int argc, char **argv)
         switch (k & 3) {
         case 0: { float const pe = (float) (unit() * 6000.0); xe = 3.5 - pe / 300.; float const db = (float) (unit() * 24.0 - 12.0); yp = db * 0.1; break; }
         case 1: { float const pe = (float) (unit() * 1.0e5); xe = 3.5 - pe / 300.; float const db = (float) (unit() * 2.0 - 1.0); yp = db * 0.1; break; }
-        case 2: xe = unit() * 1000.0 - 500.0; yp = unit() * 8.0 - 4.0; break;
-        default: xe = (unit() - 0.5) * 1e-3; yp = unit() * 200.0 - 100.0; xb = 0.001 + unit() * 1000.0; break;
+        case 2: xe = unit() * 1416.0 - 707.0; yp = unit() * 8.0 - 4.0; break;       /* exp: the whole range of normal results */
+        default: xe = (unit() - 0.5) * 1e-3; yp = unit() * 200.0 - 100.0; xb = 0.001 + unit() * 1000.0; break;   /* |y log x| up to 691 */
         }
         if (!same(lg_exp(xe), exp(xe))) { if (bad_e < 5) printf("exp(%a): %a vs %a\n", xe, lg_exp(xe), exp(xe)); bad_e++; }
         if (!same(lg_pow(xb, yp), pow(xb, yp))) { if (bad_p < 5) printf("pow(%a, %a): %a vs %a\n", xb, yp, lg_pow(xb, yp), pow(xb, yp)); bad_p++; }
