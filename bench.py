@@ -298,6 +298,14 @@ def main():
     # ---------------- e2e: public API, host buffers in, MP3 bytes out
     enc.close()
     enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=local, vbr=VBR)
+    # host worker pool (staging, header splice): all cores for up to four ranks of a box, half of them per rank at eight
+    # (measured on 32 cores at N=8: 32 / 16 / 4 threads per rank -> 3.23e6 / 3.41e6 / 2.87e6 frames/s end to end, profiles/README.md)
+    cores = min(64, os.cpu_count() or 1)
+    host_threads = cores
+    if world > 1 and "LAMEGPU_THREADS" not in os.environ:
+        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+        host_threads = min(cores, max(8, 4 * cores // local_world))
+        enc.set_threads(host_threads)
     step_pcm = [noise_pcm(S, nsamp, 5000 + 17 * i + rank) for i in range(4)]
     out = np.empty((S, int(1.25 * nsamp) + 7200 + 4096 + 1440 * F), dtype=np.uint8)
     nbytes = np.zeros(S, dtype=np.int32)
@@ -334,7 +342,7 @@ def main():
                        "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % world},
             "e2e": {"value": e2e_frames_all / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes_last_step": total_bytes,
-                    "note": "lamegpu_batch_encode_packed: pinned staging + piecewise H2D + kernels + D2H of packed bytes + host header splice (threads=%d)" % (os.cpu_count() or 1)},
+                    "note": "lamegpu_batch_encode_packed: pinned staging + piecewise H2D + kernels + D2H of packed bytes + host header splice (threads=%s per rank)" % os.environ.get("LAMEGPU_THREADS", host_threads)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": qname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(qname) if (S, F, SIGNAL, BRATE, VBR, QUALITY) == (512, 8, "noise", 128, 0, -1) else None, "peak_source": peak_src,
