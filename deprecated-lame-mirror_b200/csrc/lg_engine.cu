@@ -20,6 +20,7 @@
 #include "lg_k_scan.cuh"
 #include "lg_k_mdct.cuh"
 #include "lg_k_quant.cuh"
+#include "lg_k_quantg.cuh"
 #include "lg_k_vbr.cuh"
 #include "lg_k_vbrold.cuh"
 #include "lg_k_pack.cuh"
@@ -74,6 +75,7 @@ struct lg_engine {
      * slots free, so the next piece's A-B-C (and its share of the H2D copy) run underneath it */
     lgStream_t stream, stream2;
     int dense;                        /* more than six streams per SM: kernel D in its seven-CTAs-per-SM build */
+    int group_nw;                     /* > 0: kernel D in its group form (lg_k_quantg.cuh) with this many warps per granule.channel */
     int pieces;                       /* how many pieces a launch is cut into along the frame axis (1 = no overlap) */
     int *d_ready;                     /* one flag per piece: raised on stream 1 behind the piece's kernel C, awaited by kernel D on stream 2 */
 #ifndef LG_EMULATE
@@ -201,7 +203,12 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     if (e->pieces < 1) e->pieces = 1;
     if (e->pieces > LG_MAX_PIECES) e->pieces = LG_MAX_PIECES;
     if (cfg->vbr == 4 || cfg->vbr == 2) e->pieces = 1;
-    if (cfg->noise_shaping == 0) e->pieces = 1;      /* quality 7-9: kernel D is too short to hide anything under (1.70e6 frames/s as one piece, 1.28e6 in pieces) */
+    if (cfg->noise_shaping == 0) e->pieces = 1;
+    /* CBR/ABR at quality >= 3: kernel D in its group form (three warps per granule.channel, lines in registers); it runs behind A-B-C as one piece */
+    e->group_nw = ((cfg->vbr == 0 || cfg->vbr == 3) && !(cfg->substep_shaping & 2)) ? 3 : 0;
+    if (const char *ge = getenv("LAMEGPU_GROUP_NW")) e->group_nw = ((cfg->vbr == 0 || cfg->vbr == 3) && !(cfg->substep_shaping & 2)) ? atoi(ge) : 0;
+    if (e->group_nw < 0 || e->group_nw > 3) e->group_nw = 3;
+    if (e->group_nw > 0) e->pieces = 1;      /* quality 7-9: kernel D is too short to hide anything under (1.70e6 frames/s as one piece, 1.28e6 in pieces) */
     /* a profiler that serialises kernels (ncu replays each launch alone) would leave kernel D waiting for flags nobody can raise */
     if (getenv("CUDA_INJECTION64_PATH") || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("COMPUTE_SANITIZER_INJECTION")) e->pieces = 1;
 #ifndef LG_EMULATE
@@ -277,6 +284,9 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_quant<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_quant<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
     cudaFuncSetAttribute(lg_kernel_quant<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemD));
+    cudaFuncSetAttribute(lg_kernel_quantg<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemG<1>));
+    cudaFuncSetAttribute(lg_kernel_quantg<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemG<2>));
+    cudaFuncSetAttribute(lg_kernel_quantg<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemG<3>));
     cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemE));
     cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
     if (getenv("LAMEGPU_DEBUG_OCC")) {
@@ -358,6 +368,12 @@ static void lg_launch_quant_pack(lg_engine *e, int nframes, int P)
     else if (e->hcfg.vbr == 2)
         LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout,
                   e->d_state, e->d_nfr, F);
+    else if (e->group_nw > 0) {
+#define LG_LAUNCH_G(NWV) LG_LAUNCH(lg_kernel_quantg<NWV>, S, 64 * NWV, sizeof(LgSmemG<NWV>), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout, \
+                                   e->d_state, e->d_nfr, F)
+        if (e->group_nw == 1) LG_LAUNCH_G(1); else if (e->group_nw == 2) LG_LAUNCH_G(2); else LG_LAUNCH_G(3);
+#undef LG_LAUNCH_G
+    }
     else {
         int const fl = ((e->hcfg.substep_shaping & 2) ? 1 : 0) | (e->dense ? 4 : 0);
 #define LG_LAUNCH_D(FLV) LG_LAUNCH(lg_kernel_quant<FLV>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, e->d_xr, e->d_psy, e->d_frm, e->d_gout, e->d_fout, \

@@ -151,7 +151,8 @@ __device__ __forceinline__ float lg_wmax_f(float v)
 
 __device__ __forceinline__ const uint8_t *lg_hlen(const LgDevCfg *__restrict__ c, int t) { return c->huff_len + c->huff_off[t]; }
 
-__device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const LgQWarp *w, const int *sf, int sfb)
+template <class W>
+__device__ __forceinline__ int lg_band_step(const LgQInfo &gi, const W *w, const int *sf, int sfb)
 {
     return gi.global_gain - ((sf[sfb] + (gi.preflag ? lg_pretab(sfb) : 0)) << (gi.scalefac_scale + 1))
          - ((gi.sbg >> (4 * w->window[sfb])) & 15) * 8;
@@ -622,7 +623,8 @@ __device__ __forceinline__ int lg_lsf_partition_bands(int short_block, int prefl
     if (preflag) return part < 2 ? (short_block ? 18 : (part ? 10 : 11)) : 0;
     return short_block ? 9 : (part ? 5 : 6);
 }
-__device__ __noinline__ unsigned lg_scale_bitcount_lsf(LgQWarp *w, int block_type, int preflag, int compress, int part2_length, int lane)
+template <class W>
+__device__ __noinline__ unsigned lg_scale_bitcount_lsf(W *w, int block_type, int preflag, int compress, int part2_length, int lane)
 {
     const int *sf = w->sfw;
     int const sh = block_type == LG_SHORT;
@@ -651,7 +653,8 @@ __device__ __noinline__ unsigned lg_scale_bitcount_lsf(LgQWarp *w, int block_typ
 /* ---------------------------------------------------------------- takehiro.c:1135 mpeg1_scale_bitcount (and :1318 the dispatch to the
  * MPEG-2 form).  By value (three call sites, and the caller's scalars stay in registers): returns part2_length (LG_LARGE_BITS
  * = does not fit) | scalefac_compress << 20 | preflag << 29 | does-not-fit << 30. */
-__device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, int sfbmax, int sfbdivide, int preflag, int compress, int lsf_part2, int lane)
+template <class W>
+__device__ __noinline__ unsigned lg_scale_bitcount(W *w, int block_type, int sfbmax, int sfbdivide, int preflag, int compress, int lsf_part2, int lane)
 {
     if (lsf_part2 >= 0) return lg_scale_bitcount_lsf(w, block_type, preflag, compress, lsf_part2, lane);
     int *sf = w->sfw;
@@ -685,7 +688,8 @@ __device__ __noinline__ unsigned lg_scale_bitcount(LgQWarp *w, int block_type, i
 #define LG_LSF_ARG(c, gi) ((c)->mode_gr == 1 ? (gi).part2_length : -1)
 
 /* quantize.c:540 loop_break */
-__device__ __forceinline__ int lg_loop_break(const LgQWarp *w, int sbg, int sfbmax, int lane)
+template <class W>
+__device__ __forceinline__ int lg_loop_break(const W *w, int sbg, int sfbmax, int lane)
 {
     int unamp = 0;
     for (int sfb = lane; sfb < sfbmax; sfb += 32)
@@ -1135,24 +1139,32 @@ __device__ __noinline__ void lg_calc_xmin(const LgDevCfg *__restrict__ c, LgQWar
 }
 
 /* ---------------------------------------------------------------- takehiro.c:884 best_huffman_divide */
-__device__ __noinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict__ c, LgQWarp *w, int bigv, int lane)
+/* the candidates: region 0 = [0, sfb_l[r0+1]) for r0 < 16 and region 1 = [sfb_l[r0+1], sfb_l[r0+r1+2]) for the 16 x 8 pairs, each with its best table; thread t of nt */
+template <class W>
+__device__ __noinline__ void lg_recalc_divide_cand(const LgDevCfg *__restrict__ c, W *w, int bigv, int t, int nt)
 {
     const int16_t *ix = w->ixw;
-    if (lane < 23) w->r01_bits[lane] = LG_LARGE_BITS;
-    if (lane < 16) {
-        int const a1 = c->sfb_l[lane + 1];
-        int bits = 0, t = 0;
-        if (a1 < bigv) t = lg_choose_table_serial(c, ix, 0, a1, &bits);
-        w->r0b[lane] = bits; w->r0t[lane] = t;
+    for (int q = t; q < 144; q += nt) {
+        if (q >= 128) {
+            int const r0 = q - 128;
+            int const a1 = c->sfb_l[r0 + 1];
+            int bits = 0, tb = 0;
+            if (a1 < bigv) tb = lg_choose_table_serial(c, ix, 0, a1, &bits);
+            w->r0b[r0] = bits; w->r0t[r0] = tb;
+        }
+        else {
+            int const r0 = q >> 3, r1 = q & 7;
+            int const a1 = c->sfb_l[r0 + 1], a2 = c->sfb_l[r0 + r1 + 2];
+            int bits = LG_LARGE_BITS, tb = 0;
+            if (a1 < bigv && a2 < bigv) { bits = 0; tb = lg_choose_table_serial(c, ix, a1, a2, &bits); }
+            w->comb_bits[q] = bits; w->comb_tbl[q] = tb;
+        }
     }
-    for (int q = lane; q < 128; q += 32) {
-        int const r0 = q >> 3, r1 = q & 7;
-        int const a1 = c->sfb_l[r0 + 1], a2 = c->sfb_l[r0 + r1 + 2];
-        int bits = LG_LARGE_BITS, t = 0;
-        if (a1 < bigv && a2 < bigv) { bits = 0; t = lg_choose_table_serial(c, ix, a1, a2, &bits); }
-        w->comb_bits[q] = bits; w->comb_tbl[q] = t;
-    }
-    __syncwarp();
+}
+/* per r0 + r1 (0..22) the best split */
+template <class W>
+__device__ __noinline__ void lg_recalc_divide_comb(W *w, int lane)
+{
     if (lane < 23) {
         int best = LG_LARGE_BITS, div = 0, t0 = 0, t1 = 0;
         for (int r0 = 0; r0 < 16; r0++) {
@@ -1166,8 +1178,16 @@ __device__ __noinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict__ 
     }
     __syncwarp();
 }
+template <class W>
+__device__ __forceinline__ void lg_recalc_divide_init(const LgDevCfg *__restrict__ c, W *w, int bigv, int lane)
+{
+    lg_recalc_divide_cand(c, w, bigv, lane, 32);
+    __syncwarp();
+    lg_recalc_divide_comb(w, lane);
+}
 /* takehiro.c:847 recalc_divide_sub: g2 is the candidate base, gi the current best */
-__device__ __noinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c, LgQWarp *w, const LgQInfo &g2, LgQInfo &gi, int lane)
+template <class W>
+__device__ __noinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c, W *w, const LgQInfo &g2, LgQInfo &gi, int lane)
 {
     int const bigv = g2.big_values;
     /* every lane evaluates one r2 candidate; the sequential scan then replays the reference's order */
@@ -1196,13 +1216,15 @@ __device__ __noinline__ void lg_recalc_divide_sub(const LgDevCfg *__restrict__ c
         gi.table_select[2] = tbl;
     }
 }
-__device__ __noinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc, int lane)
+template <class W>
+__device__ __noinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__ c, W *w, LgQInfo &gi, const LgQConst &qc, int lane, int have_cand = 0)
 {
     const int16_t *ix = w->ixw;
     if (qc.block_type == LG_SHORT && c->mode_gr == 1) return;          /* takehiro.c:899: not for short blocks of MPEG-2 */
     LgQInfo g2 = gi;
     if (qc.block_type == LG_NORM) {
-        lg_recalc_divide_init(c, w, gi.big_values, lane);
+        if (have_cand) lg_recalc_divide_comb(w, lane);       /* the group form evaluates the candidates on all its warps beforehand */
+        else lg_recalc_divide_init(c, w, gi.big_values, lane);
         lg_recalc_divide_sub(c, w, g2, gi, lane);
     }
     int i = g2.big_values;
@@ -1236,7 +1258,8 @@ __device__ __noinline__ void lg_best_huffman_divide(const LgDevCfg *__restrict__
 }
 
 /* ---------------------------------------------------------------- takehiro.c:1021 best_scalefac_store (+ :964 scfsi_calc) */
-__device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__ c, LgQWarp *w, LgQInfo &gi, const LgQConst &qc,
+template <class W>
+__device__ __noinline__ void lg_best_scalefac_store(const LgDevCfg *__restrict__ c, W *w, LgQInfo &gi, const LgQConst &qc,
                                                        int gr, const int *sf_gr0, int bt_gr0, uint8_t scfsi[4], int lane)
 {
     int *sf = w->sfw;
