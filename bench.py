@@ -6,13 +6,13 @@ white noise (uniform int16 in [-12000, 12000], L/R independent), CBR 128 kbps jo
 512 streams x 8 frames per GPU.  With N GPUs every rank encodes its own 512 streams (weak scaling, streams are
 independent: no data-path collective).
 
-  value     frames/s with the PCM already resident in HBM: the device step (analysis, scan, mdct, quantise, pack; the batch runs in
-            pieces whose kernels overlap on two streams) timed with CUDA events from the first kernel's start to the last one's end,
-            L2 flushed between steps, max over ranks.
-  e2e       frames/s through the public C ABI (lamegpu_batch_encode_packed) with HOST buffers: host->device copy of
+  value     frames/s with the PCM already resident in HBM: K device steps (analysis, scan, mdct, quantise, pack) back to back on
+            PERSISTENT streams (no reset between steps), consecutive steps overlapping on the engine's two CUDA streams as in
+            production, timed with CUDA events from the first kernel's start to the last one's end, max over ranks.
+  e2e       frames/s through the public C ABI (lamegpu_batch_encode_packed, pipelined) with HOST buffers: host->device copy of
             the PCM, kernels, device->host copy of the packed frame bytes, header splice to MP3 bytes on the host.
-  roofline  dominant kernel (quantise): algorithmic bytes (16 060 B/frame) / its CUDA-event time
-            against the measured HBM peak of MEASURED_PEAKS.json.
+  roofline  dominant kernel (quantise): issued warp instructions per second against 592 schedulers x SM clock (the limit that
+            binds: SURVEY 8d); roofline_hbm: algorithmic bytes (16 060 B/frame) / its CUDA-event time against the measured HBM peak.
   cpu_baseline  the unmodified reference libmp3lame (oracle/_ref) single-thread on the host, bounded sample.
 
 `--impl reference` times the reference's own CPU implementation on all host threads for the same workload.
@@ -140,14 +140,25 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this workload (profiles/), or None"""
-    try:
-        k = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_summary.json")))[kernel]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        return sum(float(k[m]["value"]) * scale[k[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    except Exception:
-        return None
+def ncu_profile(kernel):
+    """per-launch figures of `kernel` from the committed `ncu --set full` capture of the headline workload (profiles/): DRAM bytes,
+    executed warp instructions, issue-active %; newest round first"""
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for name in ("r2_ncu_summary.json", "r1_ncu_summary.json"):
+        try:
+            k = json.load(open(os.path.join(ROOT, "profiles", name)))[kernel]
+            return {"file": "profiles/" + name,
+                    "traffic": sum(float(k[m]["value"]) * scale[k[m]["unit"]] for m in ("dram__bytes_read.sum", "dram__bytes_write.sum")),
+                    "inst": float(k["smsp__inst_executed.sum"]["value"]),
+                    "issue_active": float(k["smsp__issue_active.avg.pct_of_peak_sustained_active"]["value"])}
+        except Exception:
+            continue
+    return None
+
+
+def bench_config(S, F):
+    """the `config` object, identical in both arms"""
+    return {"workload": WORKLOAD, "streams_per_gpu": S, "frames_per_stream_per_step": F}
 
 
 def cpu_baseline(seconds=12.0):
@@ -201,7 +212,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "mp3_frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams": STREAMS, "frames_per_stream_per_step": FRAMES},
+            "config": bench_config(STREAMS, FRAMES),
             "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": kind,
                              "sample": "the full step (%d persistent streams x %d frames) on %d host threads" % (STREAMS, FRAMES, cores)},
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -266,27 +277,22 @@ def main():
         torch.cuda.synchronize()
 
     log('engine created')
-    # ---------------- value: device pipeline, inputs resident in HBM
-    enc.stage(pcm, F)                                        # H2D once + a first (untimed) pass
+    # ---------------- value: device pipeline, inputs resident in HBM, persistent streams, steps back to back
+    enc.stage(pcm, F)                                        # H2D once + one (untimed) full step per buffer set
     log('staged')
     sampler = ClockSampler(local)
     sampler.start()
-    for _ in range(args.warmup):
-        enc.rerun_device(F)
-    for _ in range(40):                                      # untimed load so that the clock samples around a short timed region are under load
-        enc.rerun_device(F)
+    enc.run_device_steps(F, args.warmup)
+    enc.run_device_steps(F, 40)                              # untimed load so that the clock samples around a short timed region are under load
     log('warm')
-    kms = np.zeros(5)
     launches0 = enc.kernel_launches()
     barrier()
     sampler.mark_begin()
-    dev_ms = 0.0
-    for _ in range(args.steps):
-        flush_buf.zero_()                                    # evict inputs/intermediates from L2 between timed steps
-        torch.cuda.synchronize()
-        enc.rerun_device(F)                                  # CUDA events on the engine's streams: per kernel, and first start to last end
-        kms += np.array(enc.kernel_ms())
-        dev_ms += enc.step_ms()                              # the kernels of consecutive pieces overlap: the step is not their sum
+    # K steps on the same streams (reservoir, psycho-acoustic state and step-size memory carried from step to step); CUDA events on the
+    # engine's streams from the first kernel's start to the last one's end.  Step i+1's analysis kernels run under step i's quantiser, as in
+    # production; every step touches ~215 MB on alternating buffer sets, more than the 126 MB L2, so no step finds its inputs cached.
+    dev_ms = enc.run_device_steps(F, args.steps) * args.steps
+    kms = np.array(enc.kernel_ms()) * args.steps             # per-kernel CUDA-event times, mean over exactly these steps
     barrier()
     sampler.mark_end()
     clocks = sampler.stop()
@@ -298,29 +304,35 @@ def main():
     # ---------------- e2e: public API, host buffers in, MP3 bytes out
     enc.close()
     enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=local, vbr=VBR)
-    # host worker pool (staging, header splice): all cores for up to four ranks of a box, half of them per rank at eight
-    # (measured on 32 cores at N=8: 32 / 16 / 4 threads per rank -> 3.23e6 / 3.41e6 / 2.87e6 frames/s end to end, profiles/README.md)
-    cores = min(64, os.cpu_count() or 1)
-    host_threads = cores
-    if world > 1 and "LAMEGPU_THREADS" not in os.environ:
-        local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
-        host_threads = min(cores, max(8, 4 * cores // local_world))
-        enc.set_threads(host_threads)
+    # The batch is pipelined: a call stages its PCM from the caller's buffers into pinned memory and submits the step; while the device
+    # encodes it, the previous step's bytes are spliced and handed over.  That host work is memcpy-class and hidden under the device
+    # step, so a few host threads per rank do (round 1 needed 16 and lost 15 % at eight ranks on 32 cores).
+    cores = os.cpu_count() or 1
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    host_threads = int(os.environ.get("LAMEGPU_THREADS", max(2, min(4, cores // local_world))))
+    enc.set_threads(host_threads)
+    enc.set_pipelined(True)
     step_pcm = [noise_pcm(S, nsamp, 5000 + 17 * i + rank) for i in range(4)]
     out = np.empty((S, int(1.25 * nsamp) + 7200 + 4096 + 1440 * F), dtype=np.uint8)
     nbytes = np.zeros(S, dtype=np.int32)
+    empty = np.empty((S, 2, 0), dtype=np.int16)
     enc.encode_raw(pcm, out, nbytes)                          # primes the 528+... encoder delay: afterwards every call yields F frames
     for i in range(args.warmup):
         enc.encode_raw(step_pcm[i % 4], out, nbytes)
+    enc.set_pipelined(False); enc.encode_raw(empty, out, nbytes); enc.set_pipelined(True)     # nothing in flight when the clock starts
     barrier()
     t0 = time.perf_counter()
     e2e_frames = 0
+    total_bytes = 0
     for i in range(args.steps):
-        e2e_frames += enc.encode_raw(step_pcm[i % 4], out, nbytes)
+        e2e_frames += enc.encode_raw(step_pcm[i % 4], out, nbytes)    # H2D of this step's PCM; the bytes of step i-1 land in `out`
+        total_bytes += int(nbytes.sum())
+    enc.set_pipelined(False)                                  # the last step: wait for its D2H, splice
+    enc.encode_raw(empty, out, nbytes)                        # ... and take its bytes: all K steps are in host memory inside the timed region
+    total_bytes += int(nbytes.sum())
     torch.cuda.synchronize()
     e2e_ms = 1e3 * (time.perf_counter() - t0)
     log('e2e done %.1f ms' % e2e_ms)
-    total_bytes = int(nbytes.sum())
     e2e_frames_all, e2e_ms_max = reduce_over_ranks(float(e2e_frames), e2e_ms)
     lib = lame_b200.load_library()
     h2d = S * 2 * (F * 1152 + 1328) * 2 + S * 4
@@ -330,28 +342,43 @@ def main():
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         q_ms = kms[3] / args.steps
-        qname = {4: "lg_kernel_vbr", 2: "lg_kernel_vbrold"}.get(VBR, "lg_kernel_quant")
+        qname = {4: "lg_kernel_vbr", 2: "lg_kernel_vbrold"}.get(VBR, "lg_kernel_quantg" if (QUALITY < 0 or 3 <= QUALITY <= 6) and S <= 592 else "lg_kernel_quant")
+        headline = (S, F, SIGNAL, BRATE, VBR, QUALITY) == (512, 8, "noise", 128, 0, -1)
         achieved = ALG_BYTES_QUANT * S * F / (q_ms * 1e-3) / 1e9
         a_ms = (kms[0] + kms[1] + kms[2]) / args.steps
+        prof = ncu_profile(qname) if headline else None
+        sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
+        issue_peak = 148 * 4 * sm_hz                          # one warp instruction per scheduler per cycle
+        issue = None
+        if prof and prof.get("inst"):
+            issue = {"bound": "issue", "kernel": qname, "achieved": prof["inst"] / (q_ms * 1e-3), "peak": issue_peak, "unit": "warp-inst/s",
+                     "frac": prof["inst"] / (q_ms * 1e-3) / issue_peak, "traffic": prof.get("traffic"),
+                     "warp_instructions_per_launch": prof["inst"], "avg_launch_ms": q_ms, "issue_active_pct_ncu": prof.get("issue_active"),
+                     "peak_source": "148 SMs x 4 schedulers x SM clock under load (%.0f MHz)" % (sm_hz / 1e6),
+                     "source": "smsp__inst_executed.sum of one launch from the committed ncu --set full capture (%s); duration live, CUDA events over the timed region" % prof["file"],
+                     "note": "the path is latency/issue-bound integer + table-lookup work (SURVEY 8d): the binding roofline is the issue rate; the HBM fraction is in roofline_hbm"}
+        hbm = {"bound": "hbm", "kernel": qname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+               "traffic": prof.get("traffic") if prof else None, "peak_source": peak_src,
+               "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/)",
+               "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms}
         line = {
             "metric": "mp3_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "frames_per_stream_per_step": F,
-                       "l2": "256 MiB buffer written between timed steps (L2 flush); per-step footprint ~190 MB > 126 MB L2",
-                       "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % world},
+            "config": bench_config(S, F),
+            "notes": {"l2": "no explicit flush: steps run back to back on persistent streams; a step touches ~215 MB (two alternating buffer sets) > 126 MB L2",
+                      "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % world,
+                      "value": "K pipelined steps on persistent streams, first kernel start to last kernel end (CUDA events) / K"},
             "e2e": {"value": e2e_frames_all / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes_last_step": total_bytes,
-                    "note": "lamegpu_batch_encode_packed: pinned staging + piecewise H2D + kernels + D2H of packed bytes + host header splice (threads=%s per rank)" % os.environ.get("LAMEGPU_THREADS", host_threads)},
+                    "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes": total_bytes,
+                    "note": "lamegpu_batch_encode_packed, pipelined (lamegpu_batch_set_pipelined): caller's PCM -> pinned staging -> H2D -> kernels -> D2H of packed "
+                            "bytes -> host header splice -> caller's buffer; all K steps' bytes received inside the timed region (host threads per rank: %d)" % host_threads},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": qname, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": measured_traffic(qname) if (S, F, SIGNAL, BRATE, VBR, QUALITY) == (512, 8, "noise", 128, 0, -1) else None, "peak_source": peak_src,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r1_ncu_summary.json)",
-                         "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms,
-                         "note": "latency/issue-bound integer + table-lookup kernel (SURVEY 8d): HBM fraction is reported, not the binding limit"},
+            "roofline": issue if issue else hbm,
+            "roofline_hbm": hbm,
             "kernels_ms_per_step": {"analysis": kms[0] / args.steps, "scan": kms[1] / args.steps, "mdct": kms[2] / args.steps, "quant": q_ms,
                                     "pack": kms[4] / args.steps,
-                                    "note": "summed over the pieces of a step; A-B-C of piece i+1 run under kernel D of piece i, so ms_per_step is less than their sum"},
+                                    "note": "CUDA events around each kernel; analysis/scan/mdct of step i+1 run under the quantiser of step i, so ms_per_step is less than their sum"},
             "roofline_mdct_psy": {"bound": "hbm", "kernels": "analysis+scan+mdct", "achieved": ALG_BYTES_ANALYSIS * S * F / (a_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": ALG_BYTES_ANALYSIS * S * F / (a_ms * 1e-3) / 1e9 / peak},
             "clocks": clocks,

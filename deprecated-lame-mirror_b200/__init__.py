@@ -85,6 +85,8 @@ def load_library(path=None):
         "lamegpu_batch_encode_packed": (c_long, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
         "lamegpu_batch_flush_packed": (c_long, [c_void_p, c_void_p, c_int, c_void_p]),
         "lamegpu_batch_rerun_device": (c_int, [c_void_p, c_int]),
+        "lamegpu_batch_run_device_steps": (ctypes.c_float, [c_void_p, c_int, c_int]),
+        "lamegpu_batch_set_pipelined": (c_int, [c_void_p, c_int]),
         "lamegpu_batch_stage_packed": (c_int, [c_void_p, c_void_p, c_int]),
         "lamegpu_batch_kernel_ms": (c_int, [c_void_p, P(ctypes.c_float)]),
         "lamegpu_batch_step_ms": (ctypes.c_float, [c_void_p]),
@@ -124,6 +126,7 @@ EXPORTED_SYMBOLS = _option_symbols() + [
     "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
     "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
     "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
+    "lamegpu_batch_run_device_steps", "lamegpu_batch_set_pipelined",
     "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_step_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
     "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_math_selftest", "lamegpu_batch_d2h_bytes",
 ]
@@ -277,6 +280,18 @@ class BatchEncoder:
         rc = self._lib.lamegpu_batch_rerun_device(self._h, int(nframes))
         if rc != 0:
             raise LameGpuError("lamegpu_batch_rerun_device failed")
+
+    def run_device_steps(self, nframes, steps):
+        """`steps` device-only steps back to back on persistent streams; device ms per step (CUDA events)"""
+        ms = float(self._lib.lamegpu_batch_run_device_steps(self._h, int(nframes), int(steps)))
+        if ms < 0:
+            raise LameGpuError("lamegpu_batch_run_device_steps failed")
+        return ms
+
+    def set_pipelined(self, on=True):
+        """leave the newest step in flight between calls: bytes come out one call later, host work overlaps the device"""
+        if self._lib.lamegpu_batch_set_pipelined(self._h, 1 if on else 0) != 0:
+            raise LameGpuError("lamegpu_batch_set_pipelined failed")
 
     def kernel_ms(self):
         ms = (ctypes.c_float * 5)()

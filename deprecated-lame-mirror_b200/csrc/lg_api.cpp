@@ -45,7 +45,12 @@ struct Stream {
     double rs_itime = 0;
     long rs_tend = 528;
     long tbase = -LG_PCM_HIST;         /* timeline index of element 0 */
-    long frames_done = 0;
+    /* int16 input of the call in progress that has not been copied yet: the caller's buffers cover the timeline from the end of
+     * pcm16[] on; frames are staged straight from them and only what later frames still need is kept (unborrow) */
+    const short *bl = nullptr, *br = nullptr;
+    long bn = 0;
+    long frames_done = 0;              /* frames handed to the device */
+    long frames_out = 0;               /* frames whose bytes have been spliced into `out` */
     long mf_samples_to_encode = 576 + 1152;   /* ENCDELAY + POSTDELAY, lame.c:2299 */
     int  last_padding = 0, last_bitrate_index = 0;
     LgBitWriter bw;
@@ -69,14 +74,29 @@ struct Stream {
     void init()
     {
         for (int c = 0; c < 2; c++) { pcm16[c].assign(LG_PCM_HIST + 528, 0); pcmf[c].clear(); }
-        float_mode = false; tbase = -LG_PCM_HIST; frames_done = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
+        float_mode = false; tbase = -LG_PCM_HIST; frames_done = 0; frames_out = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
+        bl = br = nullptr; bn = 0;
         for (int c = 0; c < 2; c++) raw[c].assign(LG_RS_HIST, 0.f);
         raw_base = -LG_RS_HIST; chunks.clear(); rs_itime = 0; rs_tend = 528;
         bw.reset(); out.clear();
         memset(hist_mode, 0, sizeof hist_mode); memset(hist_block, 0, sizeof hist_block);
         tag = Tag();
     }
-    long tend() const { return rs_mode ? rs_tend : tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()); }
+    long tend() const { return rs_mode ? rs_tend : tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()) + bn; }
+    /* timeline samples [from, from + n) of channel c as int16 into dst: from the kept samples, then from the borrowed input */
+    void copy16(int c, long from, size_t n, int16_t *dst) const
+    {
+        long const have = (long) pcm16[c].size(), off = from - tbase;
+        size_t k = 0;
+        if (off < have) { k = std::min<size_t>(n, (size_t) (have - off)); memcpy(dst, pcm16[c].data() + off, k * sizeof(int16_t)); }
+        if (k < n) memcpy(dst + k, (c ? br : bl) + (off + (long) k - have), (n - k) * sizeof(int16_t));
+    }
+    void unborrow()
+    {
+        if (!bn) return;
+        for (int c = 0; c < 2; c++) pcm16[c].insert(pcm16[c].end(), c ? br : bl, (c ? br : bl) + bn);
+        bl = br = nullptr; bn = 0;
+    }
     long frames_ready() const
     {
         long const have = tend();
@@ -87,6 +107,7 @@ struct Stream {
     void to_float(const LgDevCfg *cfg)
     {
         if (float_mode) return;
+        unborrow();
         size_t const n = pcm16[0].size();
         float const m00 = cfg->pcm_transform[0][0], m01 = cfg->pcm_transform[0][1];
         float const m10 = cfg->pcm_transform[1][0], m11 = cfg->pcm_transform[1][1];
@@ -117,7 +138,15 @@ struct Stream {
         long const d = keep_from - tbase;
         if (d <= 0) return;
         if (float_mode) for (int c = 0; c < 2; c++) pcmf[c].erase(pcmf[c].begin(), pcmf[c].begin() + d);
-        else for (int c = 0; c < 2; c++) pcm16[c].erase(pcm16[c].begin(), pcm16[c].begin() + d);
+        else {
+            long const have = (long) pcm16[0].size();
+            if (d <= have) for (int c = 0; c < 2; c++) pcm16[c].erase(pcm16[c].begin(), pcm16[c].begin() + d);
+            else {                               /* the kept samples are used up: the rest of the consumed range lies in the borrowed input */
+                long const skip = std::min<long>(d - have, bn);
+                for (int c = 0; c < 2; c++) pcm16[c].clear();
+                bl += skip; br += skip; bn -= skip;
+            }
+        }
         tbase = keep_from;
     }
 };
@@ -225,20 +254,78 @@ struct lamegpu_batch {
     std::vector<Stream> st;
     long frames_total = 0;
 
-    /* encode every complete frame of every stream; returns frames encoded */
+    /* ---- the step pipeline.  A step = the frames of all streams that are complete, at most F per stream: staged into one of the
+     * engine's two slots, submitted (asynchronous), completed later (wait + splice of the packed frames into the streams' output).
+     * Synchronous mode completes a step right away.  Pipelined mode (lamegpu_batch_set_pipelined) leaves the newest step in flight
+     * when a call returns: its bytes come out of the next call (or the flush), and the host work of a call - staging the next step,
+     * splicing the previous one - runs while the device works. */
+    int next_slot = 0;
+    bool pipelined = false;
+    double acc_ms[5] = { 0, 0, 0, 0, 0 };   /* per-kernel device times summed over the steps of the last lamegpu_batch_run_device_steps */
+    int acc_n = 0;
+    bool in_flight[2] = { false, false };
+    std::vector<int> flight_nfr[2];
+
+    /* wait for slot k's step and splice its frames into the streams */
+    int complete(int k)
+    {
+        if (!in_flight[k]) return 0;
+        double const t0 = now_ms();
+        if (lg_engine_wait(eng, k) != 0) return -2;
+        double const t1 = now_ms();
+        in_flight[k] = false;
+        const int *nfr = flight_nfr[k].data();
+        const LgFrameOut *fo = lg_engine_host_fout(eng, k);
+        const unsigned char *pay = lg_engine_host_pay(eng, k), *hdr = lg_engine_host_hdr(eng, k);
+        size_t const pay_stride = lg_engine_pay_stride(eng);
+        parallel_for(S, [&](int s) {
+            if (!nfr[s]) return;
+            Stream &x = st[s];
+            for (int f = 0; f < nfr[s]; f++) {
+                const LgFrameOut *fr = fo + (size_t) s * F + f;
+                lg_merge_frame(&x.bw, &cfg, fr, hdr + ((size_t) s * F + f) * LG_HDR_STRIDE, pay + (size_t) s * pay_stride + fr->pay_off);
+                x.last_padding = fr->padding;
+                x.last_bitrate_index = fr->bitrate_index;
+                {
+                    int const bi = fr->bitrate_index & 15;
+                    const unsigned char *bt = hdr + ((size_t) s * F + f) * LG_HDR_STRIDE + 40;
+                    x.hist_mode[bi][4]++; x.hist_mode[15][4]++;
+                    if (cfg.channels == 2) { x.hist_mode[bi][fr->mode_ext & 3]++; x.hist_mode[15][fr->mode_ext & 3]++; }
+                    for (int q = 0; q < 4; q++)
+                        if (bt[q] < 5) { x.hist_block[bi][bt[q]]++; x.hist_block[bi][5]++; x.hist_block[15][bt[q]]++; x.hist_block[15][5]++; }
+                }
+                if (x.tag.on) { tag_add_frame(x.tag, cfg.bitrate_kbps[fr->bitrate_index]); x.tag.mode_ext = fr->mode_ext; }
+            }
+            x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
+            x.bw.buf.clear();
+            x.frames_out += nfr[s];
+        });
+        if (g_timing) fprintf(stderr, "lamegpu: slot %d: waited %.2f ms for the device, splice %.2f ms\n", k, t1 - t0, now_ms() - t1);
+        return 0;
+    }
+    /* complete whatever is in flight, oldest first */
+    int drain()
+    {
+        if (complete(next_slot) != 0) return -2;
+        return complete(next_slot ^ 1);
+    }
+
+    /* stage and submit every complete frame of every stream; returns frames submitted (their bytes are in the streams' `out` on return
+     * unless the batch is pipelined) */
     long pump()
     {
         long done = 0;
         for (;;) {
-            int *nfr = lg_engine_host_nfr(eng);
+            int const k = next_slot;
             int maxf = 0, any_float = 0;
             for (int s = 0; s < S; s++) {
                 long const r = st[s].frames_ready();
-                nfr[s] = (int) std::min<long>(r, F);
-                maxf = std::max(maxf, nfr[s]);
-                if (nfr[s] > 0 && st[s].float_mode) any_float = 1;
+                if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode) any_float = 1; }
             }
             if (maxf == 0) break;
+            if (complete(k) != 0) return -2;                 /* the slot's previous step (two steps back) */
+            int *nfr = lg_engine_host_nfr(eng, k);
+            for (int s = 0; s < S; s++) nfr[s] = (int) std::min<long>(st[s].frames_ready(), F);
             size_t const stride = lg_engine_pcm_stride(eng);
             double const t0 = now_ms();
             if (cfg.resample) {
@@ -257,12 +344,12 @@ struct lamegpu_batch {
                     window(s, t0, t1, nck);
                     if ((int) nck > most.load()) most.store((int) nck);
                 }
-                if (lg_engine_reserve_chunks(eng, most.load()) != 0) return -2;
+                if (lg_engine_reserve_chunks(eng, k, most.load()) != 0) return -2;
                 size_t const raw_stride = lg_engine_raw_stride(eng);
-                int const cap = lg_engine_chunk_cap(eng);
-                float *hr = lg_engine_host_raw(eng);
-                LgRsChunk *hc = lg_engine_host_chunks(eng);
-                int *hn = lg_engine_host_rs_counts(eng);
+                int const cap = lg_engine_chunk_cap(eng, k);
+                float *hr = lg_engine_host_raw(eng, k);
+                LgRsChunk *hc = lg_engine_host_chunks(eng, k);
+                int *hn = lg_engine_host_rs_counts(eng, k);
                 parallel_for(S, [&](int s) {
                     hn[2 * s] = hn[2 * s + 1] = 0;
                     if (!nfr[s]) return;
@@ -286,7 +373,7 @@ struct lamegpu_batch {
             }
             else if (any_float) {
                 if (lg_engine_need_float_pcm(eng) != 0) return -2;
-                float *hp = lg_engine_host_pcmf(eng);
+                float *hp = lg_engine_host_pcmf(eng, k);
                 parallel_for(S, [&](int s) {
                     if (!nfr[s]) return;
                     st[s].to_float(&cfg);
@@ -295,47 +382,32 @@ struct lamegpu_batch {
                 });
             }
             else {
-                int16_t *hp = lg_engine_host_pcm16(eng);
+                int16_t *hp = lg_engine_host_pcm16(eng, k);
                 parallel_for(S, [&](int s) {
                     if (!nfr[s]) return;
-                    size_t const n = (size_t) nfr[s] * st[s].fs + LG_PCM_HALO;
-                    for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcm16[c].data(), n * sizeof(int16_t));
+                    const Stream &x = st[s];
+                    size_t const n = (size_t) nfr[s] * x.fs + LG_PCM_HALO;
+                    for (int c = 0; c < 2; c++) x.copy16(c, x.tbase, n, hp + ((size_t) s * 2 + c) * stride);
                 });
             }
-            if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: launch maxf=%d float=%d\n", maxf, any_float);
             double const t1 = now_ms();
-            if (lg_engine_encode(eng, maxf, any_float) != 0) return -2;
-            double const t2 = now_ms();
-            if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: device done, packing\n");
-            const LgFrameOut *fo = lg_engine_host_fout(eng);
-            const unsigned char *pay = lg_engine_host_pay(eng), *hdr = lg_engine_host_hdr(eng);
-            size_t const pay_stride = lg_engine_pay_stride(eng);
+            if (lg_engine_submit(eng, k, maxf, any_float) != 0) return -2;
+            in_flight[k] = true;
+            flight_nfr[k].assign(nfr, nfr + S);
+            next_slot = k ^ 1;
+            /* the streams move on at submission: the next step can be staged while this one runs */
             parallel_for(S, [&](int s) {
+                if (!nfr[s]) return;
                 Stream &x = st[s];
-                for (int f = 0; f < nfr[s]; f++) {
-                    const LgFrameOut *fr = fo + (size_t) s * F + f;
-                    lg_merge_frame(&x.bw, &cfg, fr, hdr + ((size_t) s * F + f) * LG_HDR_STRIDE, pay + (size_t) s * pay_stride + fr->pay_off);
-                    x.last_padding = fr->padding;
-                    x.last_bitrate_index = fr->bitrate_index;
-                    {
-                        int const bi = fr->bitrate_index & 15;
-                        const unsigned char *bt = hdr + ((size_t) s * F + f) * LG_HDR_STRIDE + 40;
-                        x.hist_mode[bi][4]++; x.hist_mode[15][4]++;
-                        if (cfg.channels == 2) { x.hist_mode[bi][fr->mode_ext & 3]++; x.hist_mode[15][fr->mode_ext & 3]++; }
-                        for (int k = 0; k < 4; k++)
-                            if (bt[k] < 5) { x.hist_block[bi][bt[k]]++; x.hist_block[bi][5]++; x.hist_block[15][bt[k]]++; x.hist_block[15][5]++; }
-                    }
-                    if (x.tag.on) { tag_add_frame(x.tag, cfg.bitrate_kbps[fr->bitrate_index]); x.tag.mode_ext = fr->mode_ext; }
-                }
-                x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
-                x.bw.buf.clear();
                 x.frames_done += nfr[s];
                 x.mf_samples_to_encode -= (long) x.fs * nfr[s];
                 x.drop_consumed();
             });
             for (int s = 0; s < S; s++) done += nfr[s];
-            if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, device(H2D+kernels+D2H) %.2f ms, merge %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
-            if (getenv("LAMEGPU_DEBUG")) fprintf(stderr, "lamegpu: packed, %ld frames so far\n", done);
+            double const t2 = now_ms();
+            if (complete(k ^ 1) != 0) return -2;             /* the step before this one, while this one runs */
+            if (!pipelined && complete(k) != 0) return -2;
+            if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, submit %.2f ms, completion %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
         }
         frames_total += done;
         return done;
@@ -400,12 +472,15 @@ struct lamegpu_batch {
             }
         }
         else {
-            x.pcm16[0].insert(x.pcm16[0].end(), l, l + n);
-            x.pcm16[1].insert(x.pcm16[1].end(), r, r + n);
+            /* not copied here: pump() stages the frames this input completes straight from the caller's buffers, end_call() keeps the rest */
+            x.unborrow();
+            x.bl = l; x.br = r; x.bn = n;
         }
         if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;     /* lame.c:1735 */
         x.mf_samples_to_encode += n;
     }
+    /* before an API call returns: the caller's buffers are theirs again */
+    void end_call() { parallel_for(S, [&](int s) { st[s].unborrow(); }); }
     /* lame.c:1786 lame_copy_inbuffer for the sample types other than int16: T = element type, jump = 1 or 2 (interleaved),
      * scale = the entry point's normalisation factor.  Same operation order as COPY_AND_TRANSFORM: the sample is converted
      * to float first, the factor is folded into the 2x2 matrix in float. */
@@ -472,6 +547,23 @@ struct lamegpu_batch {
             else for (int c = 0; c < 2; c++) x.pcm16[c].insert(x.pcm16[c].end(), (size_t) need, (int16_t) 0);
         }
     }
+    /* lame.c:2134 flush_bitstream for the streams marked in live[] (all their frames have been spliced): the rest of the last frame
+     * goes out as ancillary data, and the bit reservoir ends there - ResvSize = 0, main_data_begin = 0 (bitstream.c:886-889), on the
+     * device too, so that a stream that is fed again after a flush continues as the reference does */
+    int finish_streams(const char *live)
+    {
+        std::vector<int> idx, anc;
+        for (int s = 0; s < S; s++) {
+            if (!live[s]) continue;
+            Stream &x = st[s];
+            x.mf_samples_to_encode = 0;
+            if (lg_pack_flush(&x.bw, &cfg, x.last_bitrate_index, x.last_padding)) { idx.push_back(s); anc.push_back(x.bw.ancillary_flag); }
+            x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
+            x.bw.buf.clear();
+        }
+        if (idx.empty()) return 0;
+        return lg_engine_end_reservoir(eng, idx.data(), anc.data(), (int) idx.size());
+    }
     int take(int s, unsigned char *out, int cap)
     {
         Stream &x = st[s];
@@ -516,8 +608,9 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
     b->eng = lg_engine_create(&b->cfg, nstreams, frames_per_launch, device);
     if (!b->eng) { delete b; return NULL; }
     b->S = nstreams; b->F = frames_per_launch;
+    /* host worker pool for staging and splice: memcpy-class work that overlaps the device when the batch is pipelined - a few threads do */
     unsigned const hw = std::thread::hardware_concurrency();
-    b->nthreads = (int) std::max(1u, std::min(hw ? hw : 1u, 64u));
+    b->nthreads = (int) std::max(1u, std::min(hw ? hw : 1u, 8u));
     if (const char *e = getenv("LAMEGPU_THREADS")) b->nthreads = std::max(1, atoi(e));
     b->st.resize(nstreams);
     for (auto &s : b->st) {
@@ -547,6 +640,7 @@ long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const sho
     if (!b) return -3;
     b->parallel_for(b->S, [&](int s) { b->feed16(s, pcm_l[s], pcm_r ? pcm_r[s] : NULL, nsamples[s]); });
     long const done = b->pump();
+    b->end_call();
     if (done < 0) return done;
     b->parallel_for(b->S, [&](int s) { out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0; });
     return done;
@@ -562,16 +656,9 @@ long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int 
     }
     long const done = b->pump();
     if (done < 0) return done;
-    for (int s = 0; s < b->S; s++) {
-        Stream &x = b->st[s];
-        if (live[s]) {
-            x.mf_samples_to_encode = 0;
-            lg_pack_flush(&x.bw, &b->cfg, x.last_bitrate_index, x.last_padding);
-            x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
-            x.bw.buf.clear();
-        }
-        out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0;
-    }
+    if (b->drain() != 0) return -2;
+    if (b->finish_streams(live.data()) != 0) return -2;
+    for (int s = 0; s < b->S; s++) out_bytes[s] = out ? b->take(s, out[s], out_cap[s]) : 0;
     return done;
 }
 
@@ -582,6 +669,7 @@ long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsample
     b->parallel_for(b->S, [&](int s) { b->feed16(s, pcm + ((size_t) s * 2) * nsamples, pcm + ((size_t) s * 2 + 1) * nsamples, nsamples); });
     double const t1 = now_ms();
     long const done = b->pump();
+    b->end_call();
     if (done < 0) return done;
     double const t2 = now_ms();
     b->parallel_for(b->S, [&](int s) { out_bytes[s] = b->take(s, out + (size_t) s * out_stride, out_stride); });
@@ -598,36 +686,79 @@ long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_st
     return lamegpu_batch_flush(b, po.data(), cap.data(), out_bytes);
 }
 
+int lamegpu_batch_set_pipelined(lamegpu_batch *b, int on)
+{
+    if (!b) return -1;
+    if (!on && b->drain() != 0) return -2;
+    b->pipelined = on != 0;
+    return 0;
+}
+
 /* bench hooks */
 int lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes)
 {
-    /* lay `nframes` frames of every stream (from a fresh stream start) into the pinned staging buffer and the
-     * device buffer; used to measure the device pipeline with inputs resident in HBM */
+    /* lay `nframes` frames of every stream (from a fresh stream start) into both slots' pinned staging buffers and run one full step
+     * on each, so that the device buffers hold inputs; used to measure the device pipeline with inputs resident in HBM */
     if (!b || nframes < 1 || nframes > b->F) return -1;
+    if (b->drain() != 0) return -1;
     size_t const stride = lg_engine_pcm_stride(b->eng);
-    int16_t *hp = lg_engine_host_pcm16(b->eng);
-    int *nfr = lg_engine_host_nfr(b->eng);
     size_t const nsamp = (size_t) nframes * b->st[0].fs + LG_PCM_HALO - LG_PCM_HIST - 528;   /* user samples consumed */
-    for (int s = 0; s < b->S; s++) {
-        nfr[s] = nframes;
-        for (int c = 0; c < 2; c++) {
-            int16_t *d = hp + ((size_t) s * 2 + c) * stride;
-            memset(d, 0, (LG_PCM_HIST + 528) * sizeof(int16_t));
-            memcpy(d + LG_PCM_HIST + 528, pcm + ((size_t) s * 2 + c) * nsamp, nsamp * sizeof(int16_t));
+    for (int k = 0; k < lg_engine_slots(b->eng); k++) {
+        int16_t *hp = lg_engine_host_pcm16(b->eng, k);
+        int *nfr = lg_engine_host_nfr(b->eng, k);
+        for (int s = 0; s < b->S; s++) {
+            nfr[s] = nframes;
+            for (int c = 0; c < 2; c++) {
+                int16_t *d = hp + ((size_t) s * 2 + c) * stride;
+                memset(d, 0, (LG_PCM_HIST + 528) * sizeof(int16_t));
+                memcpy(d + LG_PCM_HIST + 528, pcm + ((size_t) s * 2 + c) * nsamp, nsamp * sizeof(int16_t));
+            }
         }
+        if (lg_engine_submit(b->eng, k, nframes, 0) != 0 || lg_engine_wait(b->eng, k) != 0) return -1;
     }
-    return lg_engine_encode(b->eng, nframes, 0);
+    return lg_engine_reset_streams(b->eng, 0, b->S);
+}
+/* `steps` device-only steps on the staged input, back to back on alternating slots, the streams' state carried from step to step
+ * (persistent streams: no reset in between).  Returns the device time per step in ms: first kernel's start to last kernel's end over
+ * all steps, so that consecutive steps overlap as they do in production. */
+float lamegpu_batch_run_device_steps(lamegpu_batch *b, int nframes, int steps)
+{
+    if (!b || steps < 1) return -1.f;
+    if (b->drain() != 0) return -1.f;
+    for (int i = 0; i < 5; i++) b->acc_ms[i] = 0;
+    b->acc_n = 0;
+    auto collect = [&](int k) {
+        if (!lg_engine_in_flight(b->eng, k)) return 0;
+        if (lg_engine_wait(b->eng, k) != 0) return -1;
+        const float *m = lg_engine_last_kernel_ms(b->eng);
+        for (int i = 0; i < 5; i++) b->acc_ms[i] += m[i];
+        b->acc_n++;
+        return 0;
+    };
+    int k = 0;
+    if (lg_engine_mark(b->eng, 0) != 0) return -1.f;
+    for (int i = 0; i < steps; i++, k ^= 1) {
+        if (collect(k) != 0) return -1.f;                     /* step i-2 (its events are about to be reused); step i-1 keeps the device busy */
+        if (lg_engine_run_device(b->eng, k, nframes, 0) != 0) return -1.f;
+    }
+    if (lg_engine_mark(b->eng, 1) != 0) return -1.f;
+    if (collect(k) != 0 || collect(k ^ 1) != 0) return -1.f;
+    float const ms = lg_engine_marked_ms(b->eng);
+    return ms < 0.f ? ms : ms / (float) steps;
 }
 int lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes)
 {
     if (!b) return -1;
+    if (b->drain() != 0) return -1;
     if (lg_engine_reset_streams(b->eng, 0, b->S) != 0) return -1;
-    if (lg_engine_run_device(b->eng, nframes, 0) != 0) return -1;
-    return lg_engine_sync(b->eng);
+    if (lg_engine_run_device(b->eng, 0, nframes, 0) != 0) return -1;
+    b->acc_n = 0;
+    return lg_engine_wait(b->eng, 0);
 }
 int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5])
 {
     if (!b) return -1;
+    if (b->acc_n > 0) { for (int i = 0; i < 5; i++) ms[i] = (float) (b->acc_ms[i] / b->acc_n); return 0; }   /* mean over the last run of device steps */
     const float *m = lg_engine_last_kernel_ms(b->eng);
     for (int i = 0; i < 5; i++) ms[i] = m[i];
     return 0;
@@ -826,7 +957,9 @@ int lame_encode_buffer(lame_global_flags *g, const short int l[], const short in
     if (nsamples == 0) return 0;
     if (!l || (g->num_channels > 1 && !r)) return 0;                  /* lame.c:1856-1864 */
     g->b->feed16(0, l, g->num_channels > 1 ? r : l, nsamples);
-    if (g->b->pump() < 0) return -2;
+    long const done = g->b->pump();
+    g->b->end_call();
+    if (done < 0) return -2;
     return handle_take(g, mp3buf, mp3buf_size);
 }
 int lame_encode_buffer_interleaved(lame_global_flags *g, short int pcm[], int nsamples, unsigned char *mp3buf, int mp3buf_size)
@@ -889,11 +1022,9 @@ int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
     Stream &x = g->b->st[0];
     if (x.mf_samples_to_encode < 1) return 0;
     g->b->pad_for_flush(0);
-    if (g->b->pump() < 0) return -2;
-    x.mf_samples_to_encode = 0;
-    lg_pack_flush(&x.bw, &g->b->cfg, x.last_bitrate_index, x.last_padding);
-    x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
-    x.bw.buf.clear();
+    if (g->b->pump() < 0 || g->b->drain() != 0) return -2;
+    char const live = 1;
+    if (g->b->finish_streams(&live) != 0) return -2;
     return handle_take(g, mp3buf, size);
 }
 /* the carried options: setter stores, getter returns what was stored (or the reference's default) */

@@ -121,7 +121,8 @@ void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, 
     }
 }
 
-void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding)
+/* returns 1 when the stream was drained (the reference then ends the bit reservoir), 0 when there was nothing to flush */
+int lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding)
 {
     int const first_ptr = bw->w_ptr;
     int last_ptr = bw->h_ptr - 1;
@@ -133,6 +134,7 @@ void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index,
         flushbits -= remaining_headers * 8 * cfg->sideinfo_len;
     }
     flushbits += frame_bits(cfg, last_bitrate_index, last_padding);
-    if (flushbits < 0) return;
+    if (flushbits < 0) return 0;
     drain_ancillary(bw, cfg, (int) flushbits);
+    return 1;
 }

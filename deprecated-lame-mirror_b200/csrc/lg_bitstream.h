@@ -18,4 +18,4 @@ struct LgBitWriter {
 
 void lg_header_crc(unsigned char *header, int sideinfo_len);
 void lg_merge_frame(LgBitWriter *bw, const LgDevCfg *cfg, const LgFrameOut *fo, const unsigned char *hdr, const unsigned char *pay);
-void lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding);
+int  lg_pack_flush(LgBitWriter *bw, const LgDevCfg *cfg, int last_bitrate_index, int last_padding);

@@ -1473,32 +1473,6 @@ __device__ __forceinline__ void lg_calc_target_bits(const LgDevCfg *__restrict__
             for (int ch = 0; ch < nch; ch++) { targ_bits[gr][ch] *= max_frame_bits; targ_bits[gr][ch] /= totbits; }
 }
 
-/* Wait until piece `p` of the batch has been produced (its flag is raised by lg_kernel_piece_ready on the other stream, behind that
- * piece's kernel C).  A flag that never comes would hang the GPU, so the wait is bounded and ends in a trap. */
-__device__ __forceinline__ void lg_wait_piece(const int *ready, int p)
-{
-#ifndef LG_EMULATE
-    const volatile int *flag = ready + p;
-    if (*flag == 0) {
-        long spins = 0;
-        while (*flag == 0) {
-            __nanosleep(500);
-            if (++spins > 4000000) lg_runaway();          /* ~2 s */
-        }
-    }
-    __threadfence();
-#else
-    (void) ready; (void) p;
-#endif
-}
-#ifndef LG_EMULATE
-__global__ void lg_kernel_piece_ready(int *ready, int p)
-{
-    __threadfence();
-    ready[p] = 1;
-}
-#endif
-
 /* ---------------------------------------------------------------- the kernel */
 /* SUB = 1: the build of the kernel with substep shaping and one-band amplification (quality 0-2; cfg->substep_shaping & 2).
  * The other quality levels run SUB = 0, whose search loop does not carry that code. */
@@ -1514,11 +1488,9 @@ __global__ void lg_kernel_piece_ready(int *ready, int p)
  * batch runs 9 % faster (33.4 -> 30.5 ms for 8 frames) while the 512-stream one would lose 2 % (6.47 -> 6.61 ms). */
 template <int FL>
 __global__ void __launch_bounds__(64, (FL & 4) ? 7 : 1)
-lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *LG_XR xr_in, const LgPsyOut *LG_XR psy, const LgFrameCtl *LG_XR frm /* written by kernels of the other
-                stream while this one runs (later pieces): plain coherent loads, no __restrict__ / __ldg on them */,
+lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *LG_XR xr_in, const LgPsyOut *LG_XR psy, const LgFrameCtl *LG_XR frm,
                 LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout,
-                LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes, int f0, int f1 /* this launch: frames f0 .. f1-1 */,
-                const int *ready, int npieces, int batch_frames /* piece p = frames [batch_frames*p/npieces, batch_frames*(p+1)/npieces) is usable once ready[p] != 0 */)
+                LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes, int f0, int f1 /* this launch: frames f0 .. f1-1 */)
 {
     constexpr int SUB = FL & 1;
     LG_DYN_SMEM(LgSmemD, sm);
@@ -1537,14 +1509,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *LG_XR xr_in, cons
         const LgFrameOut *pf = fout + (size_t) stream * nframes + (f0 - 1);
         pay_off = pf->pay_off + pf->pay_bytes;
     }
-    int piece = 0;
     for (int frame = f0; frame < my_frames; frame++) {
-        /* the batch arrives in pieces: kernels A-B-C of the later pieces run while this kernel works on the earlier ones, a one-thread
-         * kernel behind each piece's kernel C raises its flag */
-        if (npieces > 1) {
-            while (piece + 1 < npieces && frame >= (int) ((long) batch_frames * (piece + 1) / npieces)) piece++;
-            lg_wait_piece(ready, piece);
-        }
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;
         int const abr = (cfg->vbr == 3);

@@ -27,8 +27,25 @@ struct __attribute__((aligned(16))) LgGBand {            /* band-level work set:
     uint8_t window[40];
     LgQInfo best;                 /* outer_loop's best quantisation so far (the reference's cod_info copy), scalar part */
 };
+#ifndef LG_G_LINES_SMEM
+#define LG_G_LINES_SMEM 1
+#endif
+#if LG_G_LINES_SMEM
+/* experiment: the own lines stay in shared memory (every thread its own elements, no extra barriers) and the loops over them are
+ * rolled - smaller code (the search loop has to fit the 32 KB instruction cache) and fewer registers against less ILP */
+#define LG_G_UNROLL _Pragma("unroll 1")
+template <class T, int NT> struct LgGOwn { T *base; int g; __device__ __forceinline__ T &operator[](int j) const { return base[g + NT * j]; } };
+template <int NT> struct LgGOwnSfb { const uint8_t *base; int g; __device__ __forceinline__ int operator[](int j) const { return base[g + NT * j]; } };
+#else
+#define LG_G_UNROLL _Pragma("unroll")
+#endif
 template <int NW> struct __attribute__((aligned(16))) LgGChan : LgGBand {      /* the base is warp 0's replica */
     float xr[576], sq[576];
+#if LG_G_LINES_SMEM
+    float xrpow[576];
+    int16_t ixb[576];
+    uint8_t pair_sfb[320];
+#endif
     int16_t ixw[576];
     int r01_bits[24], r01_div[24], r0_tbl[24], r1_tbl[24];
     int comb_bits[128], comb_tbl[128], r0b[16], r0t[16];
@@ -49,6 +66,11 @@ template <int NW> struct LgSmemG {
     int sfb_l[24];
     uint8_t bv_scf[576];
 };
+#if LG_G_LINES_SMEM
+#define LG_G_XRPOW0(cs) (cs)->xrpow
+#else
+#define LG_G_XRPOW0(cs) (cs)->sq
+#endif
 template <int NW> struct LgGT {
     static constexpr int NT = 32 * NW;
     static constexpr int NP = (288 + NT - 1) / NT;
@@ -80,9 +102,9 @@ __device__ __forceinline__ void lg_g_exchange(LgGChan<NW> *cs, int &ring, const 
 }
 
 /* ---------------------------------------------------------------- count_bits (takehiro.c:767) for a group */
-template <int NW>
+template <int NW, class XP, class IV, class SF>
 __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, LgSmemG<NW> *sm, LgGChan<NW> *cs, LgGBand *w, LgQInfo &gi, const LgQConst &qc,
-                                               LgPrev &pv, const float2 (&xp)[LgGT<NW>::NP], unsigned (&iv)[LgGT<NW>::NP], const int (&sfbp)[LgGT<NW>::NP],
+                                               LgPrev &pv, const XP &xp, IV &iv, const SF &sfbp,
                                                float xm_warp, int &ring, const LgGId &id)
 {
     constexpr int NT = LgGT<NW>::NT, NP = LgGT<NW>::NP;
@@ -119,7 +141,7 @@ __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, L
         __syncwarp();
         float const compareval0 = (1.0f - 0.4054f) / istep;
         const float *adj = c->adj43asm;
-#pragma unroll
+LG_G_UNROLL
         for (int j = 0; j < NP; j++) {
             int const P = id.g + NT * j, i = 2 * P;
             if (P < plim) {
@@ -153,7 +175,9 @@ __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, L
                 else if (a1 == 3) v1 = 0;
                 unsigned const nv = (unsigned) v0 | ((unsigned) v1 << 16);
                 iv[j] = nv;
+#if !LG_G_LINES_SMEM
                 reinterpret_cast<unsigned *>(cs->ixw)[P] = nv;
+#endif
                 if (i < ilim) {
                     if (nv != 0u) hi_nz = P;
                     if ((nv & 0xfffefffeu) != 0u) hi_big = P;
@@ -215,7 +239,7 @@ __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, L
         }
     }
     int m0 = 0, m1 = 0, m2 = 0;
-#pragma unroll
+LG_G_UNROLL
     for (int j = 0; j < NP; j++) {
         int const i = 2 * (id.g + NT * j);
         if (i < bigv) {
@@ -246,7 +270,7 @@ __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, L
     int const b0 = __shfl_sync(LG_FULL, R.base, 0), b1 = __shfl_sync(LG_FULL, R.base, 1), b2 = __shfl_sync(LG_FULL, R.base, 2);
     unsigned acc0 = 0, acc1 = 0, acc2 = 0, n15 = 0;
     const uint32_t *pk = c->huff_pk;
-#pragma unroll
+LG_G_UNROLL
     for (int j = 0; j < NP; j++) {
         int const i = 2 * (id.g + NT * j);
         if (i < bigv) {
@@ -296,9 +320,9 @@ __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, L
 }
 
 /* ---------------------------------------------------------------- calc_noise (quantize_pvt.c:815) for a group */
-template <int NW>
+template <int NW, class IV, class SF>
 __device__ __forceinline__ void lg_g_calc_noise(const LgDevCfg *__restrict__ c, LgGChan<NW> *cs, LgGBand *w, const LgQInfo &gi, const LgQConst &qc,
-                                                LgNoiseRes *res, LgPrev &pv, const unsigned (&iv)[LgGT<NW>::NP], const int (&sfbp)[LgGT<NW>::NP], const LgGId &id)
+                                                LgNoiseRes *res, LgPrev &pv, const IV &iv, const SF &sfbp, const LgGId &id)
 {
     constexpr int NT = LgGT<NW>::NT, NP = LgGT<NW>::NP;
     int const lane = id.lane;
@@ -325,7 +349,7 @@ __device__ __forceinline__ void lg_g_calc_noise(const LgDevCfg *__restrict__ c, 
     __syncwarp();
     if (need) {
         int const plim = 32 * qc.jn;
-#pragma unroll
+LG_G_UNROLL
         for (int j = 0; j < NP; j++) {
             int const P = id.g + NT * j, i = 2 * P;
             if (P < plim) {
@@ -397,8 +421,8 @@ __device__ __forceinline__ void lg_g_calc_noise(const LgDevCfg *__restrict__ c, 
 }
 
 /* multiply the own lines of the flagged bands (factor per band in act[] as float, 0 = untouched); returns the warp's new maximum */
-template <int NW>
-__device__ __forceinline__ float lg_g_scale_bands(LgGBand *w, float xm_warp, int jn, float2 (&xp)[LgGT<NW>::NP], const int (&sfbp)[LgGT<NW>::NP], const LgGId &id)
+template <int NW, class XP, class SF>
+__device__ __forceinline__ float lg_g_scale_bands(LgGBand *w, float xm_warp, int jn, XP &xp, const SF &sfbp, const LgGId &id)
 {
     constexpr int NT = LgGT<NW>::NT, NP = LgGT<NW>::NP;
     const float *fac = reinterpret_cast<const float *>(w->act);
@@ -415,7 +439,7 @@ __device__ __forceinline__ float lg_g_scale_bands(LgGBand *w, float xm_warp, int
         }
     }
     int const plim = 32 * jn;
-#pragma unroll
+LG_G_UNROLL
     for (int j = 0; j < NP; j++) {
         if (id.g + NT * j < plim) {
             float const f = fac[sfbp[j]];
@@ -432,9 +456,9 @@ __device__ __forceinline__ float lg_g_scale_bands(LgGBand *w, float xm_warp, int
 }
 
 /* quantize.c:720 amp_scalefac_bands, noise_shaping_amp 0 and 1 (2 belongs to quality 0/1: one-warp kernel) */
-template <int NW>
+template <int NW, class XP, class SF>
 __device__ __forceinline__ float lg_g_amp_scalefac_bands(const LgDevCfg *__restrict__ c, LgGBand *w, const LgQInfo &gi, const LgQConst &qc, float xm_warp,
-                                                         float2 (&xp)[LgGT<NW>::NP], const int (&sfbp)[LgGT<NW>::NP], const LgGId &id)
+                                                         XP &xp, const SF &sfbp, const LgGId &id)
 {
     int const lane = id.lane;
     float const ifqstep34 = (gi.scalefac_scale == 0) ? (float) 1.29683955465100964055 : (float) 1.68179283050742922612;
@@ -460,9 +484,9 @@ __device__ __forceinline__ float lg_g_amp_scalefac_bands(const LgDevCfg *__restr
 }
 
 /* quantize.c:808 inc_scalefac_scale */
-template <int NW>
-__device__ __forceinline__ float lg_g_inc_scalefac_scale(LgGBand *w, LgQInfo &gi, const LgQConst &qc, float xm_warp, float2 (&xp)[LgGT<NW>::NP],
-                                                         const int (&sfbp)[LgGT<NW>::NP], const LgGId &id)
+template <int NW, class XP, class SF>
+__device__ __forceinline__ float lg_g_inc_scalefac_scale(LgGBand *w, LgQInfo &gi, const LgQConst &qc, float xm_warp, XP &xp,
+                                                         const SF &sfbp, const LgGId &id)
 {
     float const ifqstep34 = (float) 1.29683955465100964055;
     for (int r = 0; r < 2; r++) {
@@ -486,9 +510,9 @@ __device__ __forceinline__ float lg_g_inc_scalefac_scale(LgGBand *w, LgQInfo &gi
 }
 
 /* quantize.c:847 inc_subblock_gain; returns 1 when a window's gain is exhausted */
-template <int NW>
+template <int NW, class XP, class SF>
 __device__ __forceinline__ int lg_g_inc_subblock_gain(const LgDevCfg *__restrict__ c, LgGBand *w, LgQInfo &gi, const LgQConst &qc, float &xm_warp,
-                                                      float2 (&xp)[LgGT<NW>::NP], const int (&sfbp)[LgGT<NW>::NP], const LgGId &id)
+                                                      XP &xp, const SF &sfbp, const LgGId &id)
 {
     int const lane = id.lane;
     int *scalefac = w->sfw;
@@ -525,9 +549,9 @@ __device__ __forceinline__ int lg_g_inc_subblock_gain(const LgDevCfg *__restrict
 }
 
 /* quantize.c:940 balance_noise */
-template <int NW>
+template <int NW, class XP, class SF>
 __device__ __forceinline__ int lg_g_balance_noise(const LgDevCfg *__restrict__ c, LgGBand *w, LgQInfo &gi, const LgQConst &qc, float &xm_warp,
-                                                  float2 (&xp)[LgGT<NW>::NP], const int (&sfbp)[LgGT<NW>::NP], const LgGId &id)
+                                                  XP &xp, const SF &sfbp, const LgGId &id)
 {
     int const lane = id.lane;
     xm_warp = lg_g_amp_scalefac_bands<NW>(c, w, gi, qc, xm_warp, xp, sfbp, id);
@@ -550,16 +574,20 @@ __device__ __forceinline__ int lg_g_balance_noise(const LgDevCfg *__restrict__ c
 /* ---------------------------------------------------------------- outer_loop (quantize.c:1010) + bin_search_StepSize (:367): the state
  * machine of lg_outer_loop, every thread of the group walking through it with the same decisions.  On return gi, ib (the own pairs'
  * quantised values) and the warp's sfbst hold the chosen quantisation. */
-template <int NW>
+template <int NW, class XP, class IB, class SF>
 __device__ __forceinline__ void lg_g_outer_loop(const LgDevCfg *__restrict__ c, LgSmemG<NW> *sm, LgGChan<NW> *cs, LgGBand *w, LgQInfo &gi, const LgQConst &qc,
-                                                int targ_bits, volatile int *old_value, volatile int *current_step, float2 (&xp)[LgGT<NW>::NP], unsigned (&ib)[LgGT<NW>::NP],
-                                                const int (&sfbp)[LgGT<NW>::NP], float xm_warp, int &ring, const LgGId &id)
+                                                int targ_bits, volatile int *old_value, volatile int *current_step, XP &xp, IB &ib,
+                                                const SF &sfbp, float xm_warp, int &ring, const LgGId &id)
 {
     constexpr int NP = LgGT<NW>::NP;
     int const lane = id.lane;
+#if LG_G_LINES_SMEM
+    LgGOwn<unsigned, LgGT<NW>::NT> iv = { reinterpret_cast<unsigned *>(cs->ixw), id.g };       /* zeroed by the caller */
+#else
     unsigned iv[NP];
-#pragma unroll
+LG_G_UNROLL
     for (int j = 0; j < NP; j++) iv[j] = 0u;
+#endif
     int CurrentStep = *current_step, flag_GoneOver = 0, Direction = 0;
     int const start = *old_value;
     gi.global_gain = start;
@@ -603,8 +631,8 @@ __device__ __forceinline__ void lg_g_outer_loop(const LgDevCfg *__restrict__ c, 
             gi.part2_3_length = nBits;
             if (!c->noise_shaping) {                   /* quality 7-9: the step-size search is the whole loop */
                 if (lane == 0) w->best = gi;
-#pragma unroll
-                for (int j = 0; j < NP; j++) ib[j] = iv[j];
+LG_G_UNROLL
+                for (int j = 0; j < NP; j++) if (id.g + LgGT<NW>::NT * j < 288) ib[j] = iv[j];
                 for (int i = lane; i < 40; i += 32) w->sfbst[i] = w->sfw[i];
                 __syncwarp();
                 break;
@@ -643,8 +671,8 @@ __device__ __forceinline__ void lg_g_outer_loop(const LgDevCfg *__restrict__ c, 
             best_noise = noise_info;
             if (lane == 0) w->best = gi;
             best_p23 = gi.part2_3_length;
-#pragma unroll
-            for (int j = 0; j < NP; j++) ib[j] = iv[j];
+LG_G_UNROLL
+            for (int j = 0; j < NP; j++) if (id.g + LgGT<NW>::NT * j < 288) ib[j] = iv[j];
             for (int i = lane; i < 40; i += 32) w->sfbst[i] = w->sfw[i];
             __syncwarp();
         }
@@ -665,9 +693,9 @@ __device__ __forceinline__ void lg_g_outer_loop(const LgDevCfg *__restrict__ c, 
 
 /* ---------------------------------------------------------------- calc_xmin (quantize_pvt.c:589) for a group: the band sums replicated per
  * warp (one lane per band, the reference's order), the highest non-zero line from the own pairs.  xrpow sits in cs->sq while this runs. */
-template <int NW>
+template <int NW, class XR>
 __device__ __forceinline__ void lg_g_calc_xmin(const LgDevCfg *__restrict__ c, LgGChan<NW> *cs, LgGBand *w, LgQConst &qc, const LgXmin *en, const LgXmin *thm,
-                                               float ath_adjust_factor, const float2 (&xr2)[LgGT<NW>::NP], int &ring, const LgGId &id)
+                                               float ath_adjust_factor, const XR &xr2, int &ring, const LgGId &id)
 {
     constexpr int NT = LgGT<NW>::NT, NP = LgGT<NW>::NP;
     int const lane = id.lane;
@@ -702,7 +730,7 @@ __device__ __forceinline__ void lg_g_calc_xmin(const LgDevCfg *__restrict__ c, L
         w->l3_xmin[gsfb] = xmin;
     }
     int k = 0;
-#pragma unroll
+LG_G_UNROLL
     for (int j = 0; j < NP; j++) {
         int const P = id.g + NT * j, i = 2 * P;
         if (P < 288) {
@@ -734,7 +762,7 @@ __device__ __forceinline__ void lg_g_calc_xmin(const LgDevCfg *__restrict__ c, L
             if (sfb < 40) {
                 float tm = 0.f;
                 int const j1 = w->lstart[sfb] + w->width[sfb];
-                for (int j = max(w->lstart[sfb], ilim); j < j1; j++) { float const v = cs->sq[j]; if (v > tm) tm = v; }
+                for (int j = max(w->lstart[sfb], ilim); j < j1; j++) { float const v = LG_G_XRPOW0(cs)[j]; if (v > tm) tm = v; }
                 w->tail_max[sfb] = tm;
             }
         }
@@ -936,23 +964,40 @@ lg_kernel_quantg(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_
                 }
             }
             /* the own line pairs: xr, band index, xrpow (quantize.c:110 init_xrpow); xrpow also into cs->sq for calc_xmin's tail maxima */
+#if LG_G_LINES_SMEM
+            LgGOwn<float2, NT> xp = { reinterpret_cast<float2 *>(cs->xrpow), id.g };
+            LgGOwn<unsigned, NT> ib = { reinterpret_cast<unsigned *>(cs->ixb), id.g };
+            LgGOwnSfb<NT> sfbp = { cs->pair_sfb, id.g };
+#else
             float2 xp[NP];
             unsigned ib[NP];
             int sfbp[NP];
+#endif
             unsigned sgn = 0;                          /* sign bits of the own lines, for the hand-over to the packer */
             int targ = 0;
             {
+#if LG_G_LINES_SMEM
+                LgGOwn<float2, NT> xr2 = { reinterpret_cast<float2 *>(cs->xr), id.g };
+#else
                 float2 xr2[NP];
+#endif
                 float mx = 0.f, amax = 0.f;
                 const float2 *src = reinterpret_cast<const float2 *>(xr_in + (((size_t) stream * 2 * nframes + gb) * 2 + ch) * 576);
                 const uint8_t *map = qc.block_type == LG_SHORT ? cfg->line_sfb_s : cfg->line_sfb_l;
-#pragma unroll
+LG_G_UNROLL
                 for (int j = 0; j < NP; j++) {
                     int const Pp = id.g + NT * j;
+#if !LG_G_LINES_SMEM
                     xr2[j].x = xr2[j].y = 0.f; xp[j].x = xp[j].y = 0.f; ib[j] = 0u; sfbp[j] = 0;
+#endif
                     if (Pp < 288) {
                         xr2[j] = __ldg(src + Pp);
+#if LG_G_LINES_SMEM
+                        ib[j] = 0u;
+                        cs->pair_sfb[Pp] = __ldg(map + 2 * Pp);
+#else
                         sfbp[j] = __ldg(map + 2 * Pp);
+#endif
                         float const t0 = fabsf(xr2[j].x), t1 = fabsf(xr2[j].y);
                         xp[j].x = (float) sqrt((double) t0 * sqrt((double) t0));
                         xp[j].y = (float) sqrt((double) t1 * sqrt((double) t1));
@@ -962,8 +1007,10 @@ lg_kernel_quantg(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_
                         if (t1 > amax) amax = t1;
                         if (xr2[j].x < 0.0f) sgn |= 1u << (2 * j);
                         if (xr2[j].y < 0.0f) sgn |= 2u << (2 * j);
+#if !LG_G_LINES_SMEM
                         *reinterpret_cast<float2 *>(&cs->xr[2 * Pp]) = xr2[j];
                         *reinterpret_cast<float2 *>(&cs->sq[2 * Pp]) = xp[j];
+#endif
                         reinterpret_cast<unsigned *>(cs->ixw)[Pp] = 0u;
                     }
                 }
@@ -999,7 +1046,7 @@ lg_kernel_quantg(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_
             /* the chosen quantisation into shared memory for iteration_finish_one (warp 0) and straight out to the packer */
             {
                 LgGranuleOut *o = gout + (((size_t) stream * 2 * nframes + gb) * 2 + ch);
-#pragma unroll
+LG_G_UNROLL
                 for (int j = 0; j < NP; j++) {
                     int const Pp = id.g + NT * j;
                     if (Pp < 288) {

@@ -153,12 +153,23 @@ long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int 
 long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsamples, unsigned char *out, int out_stride, int *out_bytes);
 long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_stride, int *out_bytes);
 
-/* measurement hooks (bench.py): run the device pipeline once more on the PCM already resident in HBM,
- * without copies or packing; per-kernel CUDA-event times of the last launch in ms [analysis, scan, mdct, quant] */
+/* Pipelined mode (off by default).  A launch ("step") runs on one of two buffer sets; with pipelining on, lamegpu_batch_encode*
+ * leaves its newest step in flight when it returns - the bytes of that step come out of the NEXT call (or the flush) - so that
+ * the host work of a call (staging the next step, splicing the previous one) and the copies run while the device encodes.
+ * The concatenated output per stream is the same either way; like lame_encode_buffer, a call may return 0 bytes.
+ * Turning it off completes what is in flight.  0 = ok. */
+int  lamegpu_batch_set_pipelined(lamegpu_batch *b, int on);
+
+/* measurement hooks (bench.py): lamegpu_batch_stage_packed lays nframes frames per stream into the engine (one full step per buffer set,
+ * then the streams are reset); lamegpu_batch_run_device_steps runs `steps` device-only steps on them back to back - persistent streams,
+ * consecutive steps overlapping as in production - and returns the device time per step in ms (first kernel's start to last kernel's
+ * end, CUDA events; < 0 on error); lamegpu_batch_rerun_device = one step on freshly reset streams, after which lamegpu_batch_kernel_ms
+ * gives that step's per-kernel times [analysis, scan, mdct, quantise, pack] and lamegpu_batch_step_ms its first-kernel-to-last time */
 int  lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes);
+float lamegpu_batch_run_device_steps(lamegpu_batch *b, int nframes, int steps);
 int  lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes);
-int  lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5]);   /* analysis, scan, mdct, quantise, pack: summed over the launch's pieces */
-float lamegpu_batch_step_ms(const lamegpu_batch *b);                  /* first kernel start to last kernel end of the last launch */
+int  lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5]);
+float lamegpu_batch_step_ms(const lamegpu_batch *b);
 long lamegpu_batch_kernel_launches(const lamegpu_batch *b);
 int  lamegpu_batch_set_threads(lamegpu_batch *b, int nthreads);
 long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap);   /* tests: intermediate device buffers */

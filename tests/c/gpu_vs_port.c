@@ -36,6 +36,7 @@ int main(int argc, char **argv)
     int const out_sr = getenv("LP_OUT_SR") ? atoi(getenv("LP_OUT_SR")) : 0; /* explicit output rate, 0 = automatic (resampling when it differs from sr) */
     float const qfrac = getenv("LP_VBRQ_FRAC") ? (float) atof(getenv("LP_VBRQ_FRAC")) : 0.f;  /* VBR quality = brate + this */
     b = lamegpu_batch_open_vq(sr, out_sr, 2, (float) brate + qfrac, mode, quality, vbr, S, FPL, 0);
+    if (b && getenv("LP_PIPELINED")) lamegpu_batch_set_pipelined(b, 1);      /* bytes lag one step behind; the flush brings everything out */
     if (!b) { printf("batch open failed\n"); return 2; }
     for (i = 0; i < n; i += chunk) {
         int c = n - i < chunk ? n - i : chunk;
@@ -49,7 +50,7 @@ int main(int argc, char **argv)
     for (s = 0; s < S; s++) { po[s] = out[s] + olen[s]; ocap[s] = cap - olen[s]; }
     frames += lamegpu_batch_flush(b, po, ocap, ob);
     for (s = 0; s < S; s++) olen[s] += ob[s];
-    { float ms[4]; lamegpu_batch_kernel_ms(b, ms); printf("last launch kernel ms: analysis %.3f scan %.3f mdct %.3f quant %.3f\n", ms[0], ms[1], ms[2], ms[3]); }
+    { float ms[5]; lamegpu_batch_kernel_ms(b, ms); printf("last launch kernel ms: analysis %.3f scan %.3f mdct %.3f quant %.3f\n", ms[0], ms[1], ms[2], ms[3]); }
     lamegpu_batch_close(b);
     for (s = 0; s < S; s++) {
         lp_encoder *e = lp_open_vq(sr, out_sr, 2, brate, mode < 0 ? LP_MODE_NOT_SET : mode, quality, vbr, (vbr == 4 || vbr == 2) ? ((float) brate + qfrac) - (float) brate : 0.f);
