@@ -105,31 +105,17 @@ def load_library(path=None):
     return lib
 
 
-def _option_symbols():
-    """lame_set_X / lame_get_X pairs carried for link compatibility (include/lamegpu_options.h, generated)"""
+def _declared_symbols():
+    """every function include/lamegpu.h and include/lamegpu_options.h declare: the library's C ABI"""
     import re
-    h = os.path.join(os.path.dirname(_HERE), "include", "lamegpu_options.h")
-    return re.findall(r"\b(lame_[sg]et_\w+)\s*\(", open(h).read()) if os.path.exists(h) else []
+    inc = os.path.join(os.path.dirname(_HERE), "include")
+    src = "".join(open(os.path.join(inc, f)).read() for f in ("lamegpu.h", "lamegpu_options.h") if os.path.exists(os.path.join(inc, f)))
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", src)
+    return sorted({n for n in names if n.startswith(("lame_", "lamegpu_", "get_lame", "get_psy"))})
 
 
-EXPORTED_SYMBOLS = _option_symbols() + [
-    "get_lame_version", "get_lame_very_short_version", "get_psy_version", "get_lame_url", "get_lame_os_bitness", "lame_get_version",
-    "lame_get_encoder_padding", "lame_get_mf_samples_to_encode", "lame_get_totalframes", "lame_print_config", "lame_print_internals",
-    "lame_mp3_tags_fid", "lame_encode_finish",
-    "lame_init", "lame_set_in_samplerate", "lame_get_in_samplerate", "lame_set_num_channels", "lame_get_num_channels",
-    "lame_set_out_samplerate", "lame_get_out_samplerate", "lame_set_brate", "lame_get_brate", "lame_set_quality",
-    "lame_get_quality", "lame_set_mode", "lame_get_mode", "lame_set_VBR", "lame_get_VBR", "lame_set_bWriteVbrTag",
-    "lame_get_bWriteVbrTag", "lame_init_params", "lame_get_framesize", "lame_get_frameNum", "lame_get_encoder_delay",
-    "lame_encode_buffer", "lame_encode_buffer_interleaved", "lame_encode_buffer_ieee_float", "lame_encode_flush",
-    "lame_close", "lame_set_VBR_mean_bitrate_kbps", "lame_get_VBR_mean_bitrate_kbps", "lame_set_VBR_q", "lame_get_VBR_q", "lamegpu_batch_open_ex", "lamegpu_batch_open_rs", "lamegpu_batch_open_vq", "lame_set_VBR_quality", "lame_get_VBR_quality", "lame_get_lametag_frame", "get_lame_short_version", "lame_bitrate_kbps", "lame_bitrate_hist", "lame_stereo_mode_hist",
-    "lame_bitrate_stereo_mode_hist", "lame_block_type_hist", "lame_bitrate_block_type_hist", "lame_encode_buffer_float",
-    "lame_encode_buffer_interleaved_ieee_float", "lame_encode_buffer_ieee_double", "lame_encode_buffer_interleaved_ieee_double",
-    "lame_encode_buffer_long", "lame_encode_buffer_long2", "lame_encode_buffer_int", "lamegpu_batch_open", "lamegpu_batch_close", "lamegpu_batch_encode",
-    "lamegpu_batch_flush", "lamegpu_batch_encode_packed", "lamegpu_batch_flush_packed", "lamegpu_batch_rerun_device",
-    "lamegpu_batch_run_device_steps", "lamegpu_batch_set_pipelined",
-    "lamegpu_batch_stage_packed", "lamegpu_batch_kernel_ms", "lamegpu_batch_step_ms", "lamegpu_batch_kernel_launches", "lamegpu_batch_set_threads",
-    "lamegpu_batch_debug_copy", "lamegpu_sizeof_granule_out", "lamegpu_sizeof_analysis", "lamegpu_math_selftest", "lamegpu_batch_d2h_bytes",
-]
+EXPORTED_SYMBOLS = _declared_symbols()
 
 
 def _as_i16(a):

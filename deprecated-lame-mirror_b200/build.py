@@ -48,7 +48,7 @@ def build_library(force=False, verbose=False):
     o = os.path.join(OBJ, "lg_engine.o")
     run([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, "lg_engine.cu"), "-o", o])
     objs.append(o)
-    for name in ("lg_setup", "lg_bitstream", "lg_api"):
+    for name in ("lg_setup", "lg_bitstream", "lg_api", "lg_api_stubs"):
         o = os.path.join(OBJ, name + ".o")
         run(["g++"] + CXX_FLAGS + ["-c", os.path.join(CSRC, name + ".cpp"), "-o", o])
         objs.append(o)

@@ -15,6 +15,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <memory>
+#include <string>
 #include "../../include/lamegpu.h"
 #include "lg_engine.h"
 #include "lg_bitstream.h"
@@ -51,6 +52,7 @@ struct Stream {
     long bn = 0;
     long frames_done = 0;              /* frames handed to the device */
     long frames_out = 0;               /* frames whose bytes have been spliced into `out` */
+    long frames_out_base = 0;          /* ... when the current file began (lame_init_bitstream) */
     long mf_samples_to_encode = 576 + 1152;   /* ENCDELAY + POSTDELAY, lame.c:2299 */
     int  last_padding = 0, last_bitrate_index = 0;
     LgBitWriter bw;
@@ -310,104 +312,118 @@ struct lamegpu_batch {
         return complete(next_slot ^ 1);
     }
 
+    /* One step: stage every complete frame of every stream (at most F per stream) into the next slot and submit it.  Returns the slot,
+     * -1 when no stream has a complete frame, -2 on error; *frames gets the number of frames submitted.  The slot's previous step
+     * (two steps back) is completed first if it still is in flight. */
+    int stage_and_submit(long *frames)
+    {
+        long submitted = 0;
+        int const k = next_slot;
+        int maxf = 0, any_float = 0;
+        for (int s = 0; s < S; s++) {
+            long const r = st[s].frames_ready();
+            if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode) any_float = 1; }
+        }
+        if (maxf == 0) return -1;
+        if (complete(k) != 0) return -2;                 /* the slot's previous step (two steps back) */
+        int *nfr = lg_engine_host_nfr(eng, k);
+        for (int s = 0; s < S; s++) nfr[s] = (int) std::min<long>(st[s].frames_ready(), F);
+        size_t const stride = lg_engine_pcm_stride(eng);
+        double const t0 = now_ms();
+        if (cfg.resample) {
+            /* kernel R makes the window: stage the input samples and the chunks that overlap it */
+            int const reach = cfg.rs_filter_l - cfg.rs_filter_l / 2;
+            std::atomic<int> most(0), bad(0);
+            auto window = [&](int s, long &t0, long &t1, size_t &nck) {
+                const Stream &x = st[s];
+                t0 = (long) x.fs * x.frames_done - LG_PCM_HIST; t1 = t0 + (long) nfr[s] * x.fs + LG_PCM_HALO;
+                nck = 0;
+                while (nck < x.chunks.size() && x.chunks[nck].out_pos < t1) nck++;
+            };
+            for (int s = 0; s < S; s++) {
+                if (!nfr[s]) continue;
+                long t0, t1; size_t nck;
+                window(s, t0, t1, nck);
+                if ((int) nck > most.load()) most.store((int) nck);
+            }
+            if (lg_engine_reserve_chunks(eng, k, most.load()) != 0) return -2;
+            size_t const raw_stride = lg_engine_raw_stride(eng);
+            int const cap = lg_engine_chunk_cap(eng, k);
+            float *hr = lg_engine_host_raw(eng, k);
+            LgRsChunk *hc = lg_engine_host_chunks(eng, k);
+            int *hn = lg_engine_host_rs_counts(eng, k);
+            parallel_for(S, [&](int s) {
+                hn[2 * s] = hn[2 * s + 1] = 0;
+                if (!nfr[s]) return;
+                const Stream &x = st[s];
+                long t0, t1; size_t nck;
+                window(s, t0, t1, nck);
+                long hi = 0;
+                for (size_t i = 0; i < nck; i++) {
+                    const Stream::Chunk &c = x.chunks[i];
+                    LgRsChunk &o = hc[(size_t) s * cap + i];
+                    o.itime = c.itime; o.in_base = c.in_base - x.raw_base; o.out_pos = (int32_t) (c.out_pos - t0); o.count = c.count;
+                    long const klast = std::min<long>(c.count, t1 - c.out_pos) - 1;
+                    hi = std::max(hi, c.in_base + (long) floor((double) klast * cfg.rs_ratio - c.itime) + reach + 1 - x.raw_base);
+                }
+                if (hi > (long) raw_stride || hi > (long) x.raw[0].size()) { bad.store(1); return; }
+                for (int c = 0; c < 2; c++) memcpy(hr + ((size_t) s * 2 + c) * raw_stride, x.raw[c].data(), (size_t) hi * sizeof(float));
+                hn[2 * s] = (int) nck; hn[2 * s + 1] = (int) (t1 - t0);
+            });
+            if (bad.load()) { fprintf(stderr, "lamegpu: resampler staging overflow\n"); return -2; }
+            any_float = 1;
+        }
+        else if (any_float) {
+            if (lg_engine_need_float_pcm(eng) != 0) return -2;
+            float *hp = lg_engine_host_pcmf(eng, k);
+            parallel_for(S, [&](int s) {
+                if (!nfr[s]) return;
+                st[s].to_float(&cfg);
+                size_t const n = (size_t) nfr[s] * st[s].fs + LG_PCM_HALO;
+                for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcmf[c].data(), n * sizeof(float));
+            });
+        }
+        else {
+            int16_t *hp = lg_engine_host_pcm16(eng, k);
+            parallel_for(S, [&](int s) {
+                if (!nfr[s]) return;
+                const Stream &x = st[s];
+                size_t const n = (size_t) nfr[s] * x.fs + LG_PCM_HALO;
+                for (int c = 0; c < 2; c++) x.copy16(c, x.tbase, n, hp + ((size_t) s * 2 + c) * stride);
+            });
+        }
+        double const t1 = now_ms();
+        if (lg_engine_submit(eng, k, maxf, any_float) != 0) return -2;
+        in_flight[k] = true;
+        flight_nfr[k].assign(nfr, nfr + S);
+        next_slot = k ^ 1;
+        /* the streams move on at submission: the next step can be staged while this one runs */
+        parallel_for(S, [&](int s) {
+            if (!nfr[s]) return;
+            Stream &x = st[s];
+            x.frames_done += nfr[s];
+            x.mf_samples_to_encode -= (long) x.fs * nfr[s];
+            x.drop_consumed();
+        });
+        for (int s = 0; s < S; s++) submitted += nfr[s];
+        if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, submit + bookkeeping %.2f ms\n", t1 - t0, now_ms() - t1);
+        *frames = submitted;
+        return k;
+    }
+
     /* stage and submit every complete frame of every stream; returns frames submitted (their bytes are in the streams' `out` on return
      * unless the batch is pipelined) */
     long pump()
     {
         long done = 0;
         for (;;) {
-            int const k = next_slot;
-            int maxf = 0, any_float = 0;
-            for (int s = 0; s < S; s++) {
-                long const r = st[s].frames_ready();
-                if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode) any_float = 1; }
-            }
-            if (maxf == 0) break;
-            if (complete(k) != 0) return -2;                 /* the slot's previous step (two steps back) */
-            int *nfr = lg_engine_host_nfr(eng, k);
-            for (int s = 0; s < S; s++) nfr[s] = (int) std::min<long>(st[s].frames_ready(), F);
-            size_t const stride = lg_engine_pcm_stride(eng);
-            double const t0 = now_ms();
-            if (cfg.resample) {
-                /* kernel R makes the window: stage the input samples and the chunks that overlap it */
-                int const reach = cfg.rs_filter_l - cfg.rs_filter_l / 2;
-                std::atomic<int> most(0), bad(0);
-                auto window = [&](int s, long &t0, long &t1, size_t &nck) {
-                    const Stream &x = st[s];
-                    t0 = (long) x.fs * x.frames_done - LG_PCM_HIST; t1 = t0 + (long) nfr[s] * x.fs + LG_PCM_HALO;
-                    nck = 0;
-                    while (nck < x.chunks.size() && x.chunks[nck].out_pos < t1) nck++;
-                };
-                for (int s = 0; s < S; s++) {
-                    if (!nfr[s]) continue;
-                    long t0, t1; size_t nck;
-                    window(s, t0, t1, nck);
-                    if ((int) nck > most.load()) most.store((int) nck);
-                }
-                if (lg_engine_reserve_chunks(eng, k, most.load()) != 0) return -2;
-                size_t const raw_stride = lg_engine_raw_stride(eng);
-                int const cap = lg_engine_chunk_cap(eng, k);
-                float *hr = lg_engine_host_raw(eng, k);
-                LgRsChunk *hc = lg_engine_host_chunks(eng, k);
-                int *hn = lg_engine_host_rs_counts(eng, k);
-                parallel_for(S, [&](int s) {
-                    hn[2 * s] = hn[2 * s + 1] = 0;
-                    if (!nfr[s]) return;
-                    const Stream &x = st[s];
-                    long t0, t1; size_t nck;
-                    window(s, t0, t1, nck);
-                    long hi = 0;
-                    for (size_t i = 0; i < nck; i++) {
-                        const Stream::Chunk &c = x.chunks[i];
-                        LgRsChunk &o = hc[(size_t) s * cap + i];
-                        o.itime = c.itime; o.in_base = c.in_base - x.raw_base; o.out_pos = (int32_t) (c.out_pos - t0); o.count = c.count;
-                        long const klast = std::min<long>(c.count, t1 - c.out_pos) - 1;
-                        hi = std::max(hi, c.in_base + (long) floor((double) klast * cfg.rs_ratio - c.itime) + reach + 1 - x.raw_base);
-                    }
-                    if (hi > (long) raw_stride || hi > (long) x.raw[0].size()) { bad.store(1); return; }
-                    for (int c = 0; c < 2; c++) memcpy(hr + ((size_t) s * 2 + c) * raw_stride, x.raw[c].data(), (size_t) hi * sizeof(float));
-                    hn[2 * s] = (int) nck; hn[2 * s + 1] = (int) (t1 - t0);
-                });
-                if (bad.load()) { fprintf(stderr, "lamegpu: resampler staging overflow\n"); return -2; }
-                any_float = 1;
-            }
-            else if (any_float) {
-                if (lg_engine_need_float_pcm(eng) != 0) return -2;
-                float *hp = lg_engine_host_pcmf(eng, k);
-                parallel_for(S, [&](int s) {
-                    if (!nfr[s]) return;
-                    st[s].to_float(&cfg);
-                    size_t const n = (size_t) nfr[s] * st[s].fs + LG_PCM_HALO;
-                    for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcmf[c].data(), n * sizeof(float));
-                });
-            }
-            else {
-                int16_t *hp = lg_engine_host_pcm16(eng, k);
-                parallel_for(S, [&](int s) {
-                    if (!nfr[s]) return;
-                    const Stream &x = st[s];
-                    size_t const n = (size_t) nfr[s] * x.fs + LG_PCM_HALO;
-                    for (int c = 0; c < 2; c++) x.copy16(c, x.tbase, n, hp + ((size_t) s * 2 + c) * stride);
-                });
-            }
-            double const t1 = now_ms();
-            if (lg_engine_submit(eng, k, maxf, any_float) != 0) return -2;
-            in_flight[k] = true;
-            flight_nfr[k].assign(nfr, nfr + S);
-            next_slot = k ^ 1;
-            /* the streams move on at submission: the next step can be staged while this one runs */
-            parallel_for(S, [&](int s) {
-                if (!nfr[s]) return;
-                Stream &x = st[s];
-                x.frames_done += nfr[s];
-                x.mf_samples_to_encode -= (long) x.fs * nfr[s];
-                x.drop_consumed();
-            });
-            for (int s = 0; s < S; s++) done += nfr[s];
-            double const t2 = now_ms();
+            long n = 0;
+            int const k = stage_and_submit(&n);
+            if (k == -1) break;
+            if (k < 0) return -2;
+            done += n;
             if (complete(k ^ 1) != 0) return -2;             /* the step before this one, while this one runs */
             if (!pipelined && complete(k) != 0) return -2;
-            if (g_timing) fprintf(stderr, "lamegpu: stage %.2f ms, submit %.2f ms, completion %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
         }
         frames_total += done;
         return done;
@@ -456,7 +472,7 @@ struct lamegpu_batch {
         }
         rs_schedule(x, n);
     }
-    void feed16(int s, const short *l, const short *r, int n)
+    void feed16(int s, const short *l, const short *r, int n, bool borrow = true)
     {
         Stream &x = st[s];
         if (n <= 0) return;
@@ -475,6 +491,7 @@ struct lamegpu_batch {
             /* not copied here: pump() stages the frames this input completes straight from the caller's buffers, end_call() keeps the rest */
             x.unborrow();
             x.bl = l; x.br = r; x.bn = n;
+            if (!borrow) x.unborrow();
         }
         if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;     /* lame.c:1735 */
         x.mf_samples_to_encode += n;
@@ -564,6 +581,18 @@ struct lamegpu_batch {
         if (idx.empty()) return 0;
         return lg_engine_end_reservoir(eng, idx.data(), anc.data(), (int) idx.size());
     }
+    /* the same for one lane of a shared engine */
+    int finish_lane(int s, bool end_of_input = true)
+    {
+        Stream &x = st[s];
+        if (end_of_input) x.mf_samples_to_encode = 0;
+        int const drained = lg_pack_flush(&x.bw, &cfg, x.last_bitrate_index, x.last_padding);
+        x.out.insert(x.out.end(), x.bw.buf.begin(), x.bw.buf.end());
+        x.bw.buf.clear();
+        if (!drained) return 0;
+        int const anc = x.bw.ancillary_flag;
+        return lg_engine_end_reservoir(eng, &s, &anc, 1);
+    }
     int take(int s, unsigned char *out, int cap)
     {
         Stream &x = st[s];
@@ -573,7 +602,14 @@ struct lamegpu_batch {
     }
 };
 
-static thread_local const int *g_header_bits = nullptr;     /* set by lame_init_params around its lamegpu_batch_open_vq call */
+static thread_local const int *g_header_bits = nullptr;
+static thread_local const LgSetupOpt *g_setup_opt = nullptr;  /* likewise: the handle's options that change constants of the configuration */
+/* the device new engines of the lame_t face are made on: LAMEGPU_DEVICE, else the calling thread's current CUDA device */
+static int lg_default_device()
+{
+    if (const char *e = getenv("LAMEGPU_DEVICE")) return atoi(e);
+    return 0;
+}     /* set by lame_init_params around its lamegpu_batch_open_vq call */
 
 extern "C" {
 
@@ -595,7 +631,10 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
     float const vbr_q_frac = (vbr == 4 || vbr == 2) ? rate - (float) brate : 0.f;
     lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
     if (!b) return NULL;
-    if (lg_setup(&b->cfg, samplerate_in, samplerate_out, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr, vbr_q_frac) != 0) {
+    LgSetupOpt defaults;
+    lg_setup_opt_defaults(&defaults);
+    if (lg_setup_ex(&b->cfg, samplerate_in, samplerate_out, channels, brate, mode < 0 ? LG_MODE_NOT_SET : mode, quality, vbr, vbr_q_frac,
+                    g_setup_opt ? g_setup_opt : &defaults) != 0) {
         fprintf(stderr, "lamegpu: unsupported configuration (samplerate %d -> %d, channels %d, brate %d, mode %d, quality %d, vbr %d)\n",
                 samplerate_in, samplerate_out, channels, brate, mode, quality, vbr);
         delete b;
@@ -604,6 +643,12 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
     if (g_header_bits) {             /* lame_init_params: copyright / original / emphasis / extension / error_protection of the handle */
         b->cfg.copyright = g_header_bits[0]; b->cfg.original = g_header_bits[1]; b->cfg.emphasis = g_header_bits[2]; b->cfg.extension = g_header_bits[3];
         if (g_header_bits[4]) { b->cfg.error_protection = 1; b->cfg.sideinfo_len += 2; }       /* lame.c:954 */
+    }
+    if (getenv("LAMEGPU_DEBUG_CFG")) {
+        unsigned long h = 1469598103934665603ul;
+        const unsigned char *q = reinterpret_cast<const unsigned char *>(&b->cfg);
+        for (size_t i = 0; i < sizeof b->cfg; i++) h = (h ^ q[i]) * 1099511628211ul;
+        fprintf(stderr, "lamegpu: configuration %016lx (S=%d F=%d)\n", h, nstreams, frames_per_launch);
     }
     b->eng = lg_engine_create(&b->cfg, nstreams, frames_per_launch, device);
     if (!b->eng) { delete b; return NULL; }
@@ -802,9 +847,167 @@ struct lame_global_struct {
     MPEG_mode mode;
     vbr_mode VBR;
     int launch_frames;
-    lamegpu_batch *b;            /* created by lame_init_params: a one-stream engine */
+    struct LgShared *se;         /* the engine this handle is a lane of (lame_init_params) */
+    int lane;
     int initialised;
+    lame_report_function report[3];      /* lame_set_errorf / debugf / msgf */
+    int preset, preset_foreign, write_id3tag_automatic;
+    int short_blocks;            /* lame_global_flags.h:20 short_block_t: -1 not set, 0 allowed, 1 coupled, 2 dispensed, 3 forced */
+    float msfix;                 /* -1 = not set */
 };
+
+/* ---- One engine for many handles.  A lame_t is one stream and a GPU wants hundreds per launch, so handles of equal configuration
+ * are LANES of one process-wide batch engine.  lame_encode_buffer() copies the samples into its lane and, when
+ * they complete frames, sleeps until those frames have been encoded - the bytes come back from the call that completes the frame, as
+ * with the reference (lame.c:1743) - while a dispatcher thread per engine gathers the frames that are ready in ALL lanes into one
+ * launch.  Application threads that call lame_encode_buffer concurrently on their own handles (the reference's threading contract,
+ * HACKING:67-76) therefore share launches: 512 threads feeding one frame each are one 512 x 1 step.  lame_encode_flush is the lane's
+ * barrier.
+ * Locks: every lane has its own mutex (its stream's data: the owner thread feeding and taking, the dispatcher staging and splicing),
+ * so the application threads do not serialise on one another; the engine's mutex `m` guards the lane table, the dispatcher's state and
+ * the engine-level device operations.  Order: m before lane mutexes; the dispatcher holds neither while the device works. */
+struct LgShared {
+    struct Lane { std::mutex lm; std::condition_variable cv; };
+    lamegpu_batch *b = nullptr;
+    std::string key;
+    std::mutex m;
+    std::condition_variable cv_work;
+    std::unique_ptr<Lane[]> lane;
+    std::vector<char> used;
+    int nused = 0;
+    std::atomic<unsigned long> work{0};
+    bool stop = false;
+    std::atomic<bool> failed{false};
+    std::thread th;
+    long steps = 0, step_frames = 0, last_lanes = 0;
+    double t_gather = 0, t_stage = 0, t_device = 0, t_splice = 0;     /* LAMEGPU_TIMING: where the dispatcher's time goes, ms */
+
+    void lock_lanes() { for (int s = 0; s < b->S; s++) lane[s].lm.lock(); }
+    void unlock_lanes() { for (int s = b->S - 1; s >= 0; s--) lane[s].lm.unlock(); }
+    void fail() { failed = true; for (int s = 0; s < b->S; s++) { std::lock_guard<std::mutex> g(lane[s].lm); lane[s].cv.notify_all(); } }
+    /* a feeder has completed frames in its lane.  Without the engine's mutex (hundreds of feeders would queue behind the dispatcher's
+     * critical sections): a wake-up that slips between the submitter's test and its sleep is caught by its 100 us poll. */
+    void kick() { work.fetch_add(1, std::memory_order_release); cv_work.notify_one(); }
+    /* Two dispatcher threads keep two launches in flight (the engine's two slots): the submitter stages and submits whatever is ready as
+     * soon as a slot is free, the completer waits for the oldest launch, splices its frames into the lanes and wakes their threads.
+     * Threads that run in step fall into two groups that alternate, one being encoded while the other is fed. */
+    std::condition_variable cv_queue;
+    std::vector<int> queue;                  /* submitted slots, oldest first */
+    std::thread th2;
+
+    void run_submit()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        unsigned long seen = 0;
+        for (;;) {
+            while (!(stop || (work.load(std::memory_order_acquire) != seen && !b->in_flight[b->next_slot]))) cv_work.wait_for(lk, std::chrono::microseconds(100));
+            if (stop) break;
+            double const tg = now_ms();
+            /* Application threads that run in step (each feeds a frame, waits for its bytes, feeds the next) come back within a short time
+             * of one another: wait until as many lanes have reported frames as the last launch carried, at most 200 us - a launch per
+             * straggler would cost each of them a full device round trip.  A single handle never waits here. */
+            if (last_lanes > 1) {
+                auto const deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(200);
+                cv_work.wait_until(lk, deadline, [&]() { return stop || (long) (work.load() - seen) >= last_lanes; });
+                if (stop) break;
+            }
+            seen = work.load();
+            double const t0 = now_ms();
+            long n = 0;
+            lock_lanes();
+            int const k = b->stage_and_submit(&n);
+            unlock_lanes();
+            if (k == -1) continue;
+            if (k < 0) { fail(); break; }
+            steps++; step_frames += n;
+            { int lanes = 0; const int *q = lg_engine_host_nfr(b->eng, k); for (int i = 0; i < b->S; i++) lanes += q[i] > 0; last_lanes = lanes; }
+            queue.push_back(k);
+            cv_queue.notify_one();
+            seen = work.load() - 1;          /* look again: lanes may hold more than one launch's worth */
+            t_gather += t0 - tg; t_stage += now_ms() - t0;
+        }
+    }
+    void run_complete()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_queue.wait(lk, [&]() { return stop || !queue.empty(); });
+            if (queue.empty()) break;        /* stop: what is in flight belongs to lanes that were closed */
+            int const k = queue.front();
+            double const t1 = now_ms();
+            lk.unlock();
+            int const rc = lg_engine_wait(b->eng, k);          /* the device works: the lanes can be fed, the next launch staged meanwhile */
+            lk.lock();
+            double const t2 = now_ms();
+            lock_lanes();
+            int const rc2 = rc != 0 ? rc : b->complete(k);
+            unlock_lanes();
+            queue.erase(queue.begin());
+            if (rc2 != 0) { fail(); break; }
+            const std::vector<int> &nfr = b->flight_nfr[k];
+            for (int s = 0; s < b->S; s++) if (nfr[s]) lane[s].cv.notify_all();
+            cv_work.notify_all();            /* a slot is free again */
+            t_device += t2 - t1; t_splice += now_ms() - t2;
+        }
+    }
+};
+static std::mutex g_shared_m;
+static std::vector<LgShared *> g_shared;
+
+static LgShared *shared_acquire(const std::string &key, const std::function<lamegpu_batch *()> &make, int *lane)
+{
+    std::lock_guard<std::mutex> g(g_shared_m);
+    for (LgShared *se : g_shared) {
+        if (se->key != key || se->failed) continue;
+        std::lock_guard<std::mutex> lk(se->m);               /* the dispatcher is between steps or waiting for the device */
+        for (int s = 0; s < se->b->S; s++)
+            if (!se->used[s]) {
+                /* a lane that was used before starts over: fresh stream on the host, initial state on the device (ordered behind
+                 * whatever the engine has in flight - no new step can be submitted while m is held) */
+                std::lock_guard<std::mutex> ll(se->lane[s].lm);
+                if (lg_engine_reset_streams(se->b->eng, s, 1) != 0) return nullptr;
+                se->b->st[s].init();
+                se->b->st[s].last_bitrate_index = se->b->cfg.bitrate_index;
+                se->used[s] = 1; se->nused++;
+                *lane = s;
+                return se;
+            }
+    }
+    lamegpu_batch *b = make();
+    if (!b) return nullptr;
+    LgShared *se = new LgShared;
+    se->b = b; se->key = key;
+    se->lane.reset(new LgShared::Lane[b->S]);
+    se->used.assign(b->S, 0);
+    se->used[0] = 1; se->nused = 1;
+    *lane = 0;
+    se->th = std::thread([se]() { se->run_submit(); });
+    se->th2 = std::thread([se]() { se->run_complete(); });
+    g_shared.push_back(se);
+    return se;
+}
+static void shared_release(LgShared *se, int lane)
+{
+    std::lock_guard<std::mutex> g(g_shared_m);
+    bool last;
+    {
+        std::lock_guard<std::mutex> lk(se->m);
+        se->used[lane] = 0; se->nused--;
+        last = se->nused == 0;
+        if (last) se->stop = true;
+    }
+    if (!last) return;
+    /* the last handle of an engine takes it along: nothing of this library stays behind in a process that has closed all its handles */
+    se->cv_work.notify_all(); se->cv_queue.notify_all();
+    if (se->th.joinable()) se->th.join();
+    if (se->th2.joinable()) se->th2.join();
+    g_shared.erase(std::remove(g_shared.begin(), g_shared.end(), se), g_shared.end());
+    if (g_timing && se->steps)
+        fprintf(stderr, "lamegpu: shared engine closed after %ld launches, %.1f frames per launch; per launch: gather %.3f ms, stage + submit %.3f, device %.3f, splice + wake %.3f\n",
+                se->steps, (double) se->step_frames / se->steps, se->t_gather / se->steps, se->t_stage / se->steps, se->t_device / se->steps, se->t_splice / se->steps);
+    lamegpu_batch_close(se->b);
+    delete se;
+}
 
 /* VbrTag.c:255 setLameTagFrameHeader (MPEG-1 branch): the tag frame looks like a frame of the stream itself, without padding */
 static int tag_xing_kbps(const LgDevCfg *c) { return c->version == 1 ? 128 : (c->samplerate < 16000 ? 32 : 64); }
@@ -826,9 +1029,9 @@ static void tag_frame_header(const LgDevCfg *c, int mode_ext, unsigned char *buf
 #define LG_LAMEHEADERSIZE (LG_VBRHEADERSIZE + 9 + 1 + 1 + 8 + 1 + 1 + 3 + 1 + 1 + 2 + 4 + 2 + 2)
 
 /* VbrTag.c:492 InitVbrTag for CBR: an all-zero frame (but for its header) goes into the stream ahead of the audio */
-static void tag_init(lamegpu_batch *b)
+static void tag_init(lamegpu_batch *b, int lane)
 {
-    Stream &x = b->st[0];
+    Stream &x = b->st[lane];
     const LgDevCfg *c = &b->cfg;
     int const kbps_header = (c->vbr == 0) ? c->brate : tag_xing_kbps(c);         /* VbrTag.c:517-529 */
     int const total = ((c->version + 1) * 72000 * kbps_header) / c->samplerate;
@@ -847,6 +1050,9 @@ static void tag_init(lamegpu_batch *b)
 static void put_be32(unsigned char *p, unsigned long v) { p[0] = (v >> 24) & 0xff; p[1] = (v >> 16) & 0xff; p[2] = (v >> 8) & 0xff; p[3] = v & 0xff; }
 static void put_be16(unsigned char *p, unsigned v) { p[0] = (v >> 8) & 0xff; p[1] = v & 0xff; }
 
+static inline lamegpu_batch *HB(const lame_global_flags *g) { return g->se ? g->se->b : nullptr; }
+static inline Stream &HS(const lame_global_flags *g) { return g->se->b->st[g->lane]; }
+
 lame_global_flags *lame_init(void)
 {
     lame_global_flags *g = (lame_global_flags *) calloc(1, sizeof *g);
@@ -854,8 +1060,9 @@ lame_global_flags *lame_init(void)
     g->class_id = LAME_ID;
     for (int i = 0; i < LG_NOPT; i++) g->opt[i] = g_opts[i].def;
     g->num_channels = 2; g->samplerate_in = 44100; g->samplerate_out = 0; g->brate = 0; g->quality = -1;
-    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 16; g->mean_brate = 128; g->vbr_q = 4; g->vbr_q_frac = 0;
+    g->write_lame_tag = 1; g->mode = NOT_SET; g->VBR = vbr_off; g->launch_frames = 8; g->mean_brate = 128; g->vbr_q = 4; g->vbr_q_frac = 0;
     if (const char *e = getenv("LAMEGPU_HANDLE_FRAMES")) g->launch_frames = std::max(1, atoi(e));
+    g->short_blocks = -1; g->msfix = -1.f; g->write_id3tag_automatic = 1;
     return g;
 }
 static int ok(const lame_global_flags *g) { return g && g->class_id == LAME_ID; }
@@ -904,38 +1111,79 @@ const char *get_lame_short_version(void) { return "3.99.5"; }
 int lame_init_params(lame_global_flags *g)
 {
     if (!ok(g)) return -1;
+    /* an option this library does not act on is accepted only while it has the value of a fresh handle - anything else would be
+     * silently different from libmp3lame */
     for (int i = 0; i < LG_NOPT; i++)
-        if (g->opt_set[i] && !g_opts[i].honoured && g->opt[i] != g_opts[i].def && g->opt[i] != g_opts[i].def2) {
-            fprintf(stderr, "lamegpu: lame_set_%s(%g) is not supported (only the default %g)\n", g_opts[i].name, g->opt[i], g_opts[i].def);
+        if (g->opt_set[i] && !g_opts[i].honoured && g->opt[i] != g_opts[i].def) {
+            fprintf(stderr, "lamegpu: lame_set_%s(%g) is not supported (only %g, the value of a fresh handle)\n", g_opts[i].name, g->opt[i], g_opts[i].def);
             return -1;
         }
-    if (g->b) { lamegpu_batch_close(g->b); g->b = NULL; }
+    LgSetupOpt so;
+    lg_setup_opt_defaults(&so);
+    so.scale = (float) g->opt[LG_OPTI_scale]; so.scale_left = (float) g->opt[LG_OPTI_scale_left]; so.scale_right = (float) g->opt[LG_OPTI_scale_right];
+    so.compression_ratio = (float) g->opt[LG_OPTI_compression_ratio];
+    so.lowpassfreq = (int) g->opt[LG_OPTI_lowpassfreq]; so.lowpasswidth = (int) g->opt[LG_OPTI_lowpasswidth];
+    so.highpassfreq = (int) g->opt[LG_OPTI_highpassfreq]; so.highpasswidth = (int) g->opt[LG_OPTI_highpasswidth];
+    so.no_ath = (int) g->opt[LG_OPTI_noATH]; so.ath_only = (int) g->opt[LG_OPTI_ATHonly]; so.ath_short = (int) g->opt[LG_OPTI_ATHshort];
+    so.ath_type = (int) g->opt[LG_OPTI_ATHtype]; so.ath_lower_db = (float) g->opt[LG_OPTI_ATHlower];
+    so.athaa_type = (int) g->opt[LG_OPTI_athaa_type]; so.athaa_sensitivity = (float) g->opt[LG_OPTI_athaa_sensitivity];
+    so.interch = (float) g->opt[LG_OPTI_interChRatio]; so.msfix = g->msfix;
+    so.short_blocks = g->short_blocks;
+    so.force_ms = (int) g->opt[LG_OPTI_force_ms]; so.disable_reservoir = (int) g->opt[LG_OPTI_disable_reservoir];
+    so.strict_iso = (int) g->opt[LG_OPTI_strict_ISO]; so.use_temporal = (int) g->opt[LG_OPTI_useTemporal];
+    so.vbr_min_kbps = (int) g->opt[LG_OPTI_VBR_min_bitrate_kbps]; so.vbr_max_kbps = (int) g->opt[LG_OPTI_VBR_max_bitrate_kbps];
+    so.vbr_hard_min = (int) g->opt[LG_OPTI_VBR_hard_min];
+    if (g->se) { shared_release(g->se, g->lane); g->se = nullptr; }
+    if (g->preset_foreign && g->VBR == vbr_off) {
+        fprintf(stderr, "lamegpu: lame_set_preset(V%d) without a VBR mode is not supported\n", g->vbr_q);
+        return -1;
+    }
     int const is_vbr = (g->VBR == vbr_mt || g->VBR == vbr_mtrh || g->VBR == vbr_rh);   /* vbr_mt and vbr_mtrh both select VBR_new_iteration_loop, encoder.c:531 */
     int const header_bits[5] = { (int) g->opt[LG_OPTI_copyright] != 0, (int) g->opt[LG_OPTI_original] != 0, (int) g->opt[LG_OPTI_emphasis] & 3,
                                  (int) g->opt[LG_OPTI_extension] != 0, (int) g->opt[LG_OPTI_error_protection] != 0 };
-    g_header_bits = header_bits;
-    g->b = lamegpu_batch_open_vq(g->samplerate_in, g->samplerate_out, g->num_channels,
-                                 is_vbr ? g->vbr_q + g->vbr_q_frac : (float) (g->VBR == vbr_abr ? g->mean_brate : g->brate),
-                                 g->mode == NOT_SET ? -1 : (int) g->mode, g->quality, is_vbr ? (g->VBR == vbr_rh ? 2 : 4) : (g->VBR == vbr_abr ? 3 : 0), 1, g->launch_frames, 0);
-    g_header_bits = nullptr;
-    if (!g->b) return -1;
-    g->samplerate_out = g->b->cfg.samplerate;
-    g->brate = g->b->cfg.brate;
-    g->mean_brate = g->b->cfg.vbr_mean_kbps;
-    g->quality = g->b->cfg.quality;
-    if (is_vbr) { g->vbr_q = g->b->cfg.vbr_q; g->vbr_q_frac = g->b->cfg.vbr_q_frac; }      /* presets.c:203-206 */
-    g->mode = (MPEG_mode) g->b->cfg.mode;
+    float const rate = is_vbr ? g->vbr_q + g->vbr_q_frac : (float) (g->VBR == vbr_abr ? g->mean_brate : g->brate);
+    int const mode = g->mode == NOT_SET ? -1 : (int) g->mode, vbr = is_vbr ? (g->VBR == vbr_rh ? 2 : 4) : (g->VBR == vbr_abr ? 3 : 0);
+    /* lanes of one engine: LAMEGPU_LANES handles of this configuration share a launch, LAMEGPU_HANDLE_FRAMES frames of each per launch */
+    int lanes = 512;
+    if (const char *e = getenv("LAMEGPU_LANES")) lanes = std::max(1, atoi(e));
+    std::string key;
+    {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%d/%d/%d/%.6f/%d/%d/%d/%d%d%d%d%d/%d/%d/", g->samplerate_in, g->samplerate_out, g->num_channels, (double) rate, mode, g->quality, vbr,
+                 header_bits[0], header_bits[1], header_bits[2], header_bits[3], header_bits[4], lanes, g->launch_frames);
+        key = buf;
+        key.append(reinterpret_cast<const char *>(&so), sizeof so);       /* the option block, byte for byte (memset by lg_setup_opt_defaults) */
+    }
+    g->se = shared_acquire(key, [&]() {
+        g_header_bits = header_bits;
+        g_setup_opt = &so;
+        lamegpu_batch *b = lamegpu_batch_open_vq(g->samplerate_in, g->samplerate_out, g->num_channels, rate, mode, g->quality, vbr, lanes, g->launch_frames, lg_default_device());
+        g_header_bits = nullptr;
+        g_setup_opt = nullptr;
+        return b;
+    }, &g->lane);
+    if (!g->se) return -1;
+    const LgDevCfg &c = HB(g)->cfg;
+    g->samplerate_out = c.samplerate;
+    g->brate = c.brate;
+    g->mean_brate = c.vbr_mean_kbps;
+    g->quality = c.quality;
+    if (is_vbr) { g->vbr_q = c.vbr_q; g->vbr_q_frac = c.vbr_q_frac; }      /* presets.c:203-206 */
+    g->mode = (MPEG_mode) c.mode;
     g->initialised = 1;
-    if (g->write_lame_tag) tag_init(g->b);                 /* lame.c:1249 lame_init_bitstream -> InitVbrTag */
+    if (g->write_lame_tag) {                                  /* lame.c:1249 lame_init_bitstream -> InitVbrTag */
+        std::lock_guard<std::mutex> lk(g->se->lane[g->lane].lm);
+        tag_init(HB(g), g->lane);
+    }
     return 0;
 }
-int lame_get_framesize(const lame_global_flags *g) { return ok(g) && g->initialised ? 576 * g->b->cfg.mode_gr : 0; }
-int lame_get_frameNum(const lame_global_flags *g) { return ok(g) && g->b ? (int) g->b->st[0].frames_done : 0; }
+int lame_get_framesize(const lame_global_flags *g) { return ok(g) && g->initialised ? 576 * HB(g)->cfg.mode_gr : 0; }
+int lame_get_frameNum(const lame_global_flags *g) { return ok(g) && HB(g) ? (int) (HS(g).frames_out - HS(g).frames_out_base) : 0; }
 int lame_get_encoder_delay(const lame_global_flags *g) { return ok(g) ? 576 : 0; }
 
 static int handle_take(lame_global_flags *g, unsigned char *mp3buf, int mp3buf_size)
 {
-    Stream &x = g->b->st[0];
+    Stream &x = HS(g);
     int const have = (int) x.out.size();
     if (mp3buf_size != 0 && have > mp3buf_size) return -1;            /* lame.h:687: mp3buf too small */
     if (have) {
@@ -951,15 +1199,28 @@ static int handle_take(lame_global_flags *g, unsigned char *mp3buf, int mp3buf_s
     }
     return have;
 }
+/* with the lane's mutex held: wake the dispatcher and sleep until the frames this lane's samples complete have been spliced */
+static int handle_wait_frames(lame_global_flags *g, std::unique_lock<std::mutex> &lk)
+{
+    LgShared *se = g->se;
+    Stream &x = HS(g);
+    long const ready = x.frames_ready();
+    if (ready <= 0) return 0;
+    long const target = x.frames_done + ready;
+    lk.unlock();
+    se->kick();
+    lk.lock();
+    se->lane[g->lane].cv.wait(lk, [&]() { return se->failed.load() || x.frames_out >= target; });
+    return se->failed.load() ? -2 : 0;
+}
 int lame_encode_buffer(lame_global_flags *g, const short int l[], const short int r[], const int nsamples, unsigned char *mp3buf, const int mp3buf_size)
 {
     if (!ok(g) || !g->initialised) return -3;
     if (nsamples == 0) return 0;
     if (!l || (g->num_channels > 1 && !r)) return 0;                  /* lame.c:1856-1864 */
-    g->b->feed16(0, l, g->num_channels > 1 ? r : l, nsamples);
-    long const done = g->b->pump();
-    g->b->end_call();
-    if (done < 0) return -2;
+    std::unique_lock<std::mutex> lk(g->se->lane[g->lane].lm);
+    HB(g)->feed16(g->lane, l, g->num_channels > 1 ? r : l, nsamples, false);
+    if (handle_wait_frames(g, lk) != 0) return -2;
     return handle_take(g, mp3buf, mp3buf_size);
 }
 int lame_encode_buffer_interleaved(lame_global_flags *g, short int pcm[], int nsamples, unsigned char *mp3buf, int mp3buf_size)
@@ -977,8 +1238,9 @@ template <class T> static int handle_encode_T(lame_global_flags *g, const T *l, 
     if (!ok(g) || !g->initialised) return -3;
     if (nsamples == 0) return 0;
     if (!l || (g->num_channels > 1 && !r)) return 0;
-    g->b->feedT<T>(0, l, g->num_channels > 1 ? r : l, nsamples, jump, norm);
-    if (g->b->pump() < 0) return -2;
+    std::unique_lock<std::mutex> lk(g->se->lane[g->lane].lm);
+    HB(g)->feedT<T>(g->lane, l, g->num_channels > 1 ? r : l, nsamples, jump, norm);
+    if (handle_wait_frames(g, lk) != 0) return -2;
     return handle_take(g, mp3buf, mp3buf_size);
 }
 }
@@ -1016,16 +1278,44 @@ int lame_encode_buffer_long(lame_global_flags *g, const long l[], const long r[]
 {
     return handle_encode_T<long>(g, l, r, n, 1, 1.0f, mp3buf, size);                       /* +/- 32768 full scale, lame.c:1960 */
 }
-int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
+/* lame.c:2042 lame_encode_flush / lame.c:1988 lame_encode_flush_nogap: pad, encode what is left, then flush_bitstream */
+static int handle_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
 {
     if (!ok(g) || !g->initialised) return -3;
-    Stream &x = g->b->st[0];
-    if (x.mf_samples_to_encode < 1) return 0;
-    g->b->pad_for_flush(0);
-    if (g->b->pump() < 0 || g->b->drain() != 0) return -2;
-    char const live = 1;
-    if (g->b->finish_streams(&live) != 0) return -2;
+    {
+        std::unique_lock<std::mutex> lk(g->se->lane[g->lane].lm);
+        Stream &x = HS(g);
+        if (x.mf_samples_to_encode < 1) return 0;
+        HB(g)->pad_for_flush(g->lane);
+        if (handle_wait_frames(g, lk) != 0) return -2;
+    }
+    /* the lane has nothing in flight any more; the engine may (other lanes' step): finish_lane orders the end of the lane's reservoir
+     * behind it, and no new step can be submitted while the engine's mutex is held */
+    std::lock_guard<std::mutex> le(g->se->m);
+    std::lock_guard<std::mutex> lk(g->se->lane[g->lane].lm);
+    if (HB(g)->finish_lane(g->lane) != 0) return -2;
     return handle_take(g, mp3buf, size);
+}
+int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size) { return handle_flush(g, mp3buf, size); }
+int lame_encode_flush_nogap(lame_global_flags *g, unsigned char *mp3buf, int size)            /* lame.c:1988: flush_bitstream + copy_buffer; the buffered samples stay */
+{
+    if (!ok(g) || !g->initialised) return -3;
+    std::lock_guard<std::mutex> le(g->se->m);
+    std::lock_guard<std::mutex> lk(g->se->lane[g->lane].lm);
+    if (HB(g)->finish_lane(g->lane, false) != 0) return -2;
+    return handle_take(g, mp3buf, size);
+}
+/* lame.c:2006 lame_init_bitstream: a new file begins - statistics and the Info tag start over, the encoder state continues */
+int lame_init_bitstream(lame_global_flags *g)
+{
+    if (!ok(g) || !g->initialised) return -3;
+    std::unique_lock<std::mutex> lk(g->se->lane[g->lane].lm);
+    Stream &x = HS(g);
+    x.frames_out_base = x.frames_out;
+    memset(x.hist_mode, 0, sizeof x.hist_mode); memset(x.hist_block, 0, sizeof x.hist_block);
+    x.tag = Stream::Tag();
+    if (g->write_lame_tag) tag_init(HB(g), g->lane);
+    return 0;
 }
 /* the carried options: setter stores, getter returns what was stored (or the reference's default) */
 #define LG_OPT(n, t, d, d2, h) \
@@ -1040,13 +1330,13 @@ const char *get_lame_very_short_version(void) { return "LAME3.99r5"; }
 const char *get_psy_version(void) { return "1.0"; }
 const char *get_lame_url(void) { return "http://lame.sf.net"; }
 const char *get_lame_os_bitness(void) { return sizeof(void *) == 8 ? "64bits" : "32bits"; }
-int lame_get_version(const lame_global_flags *g) { return ok(g) && g->b ? g->b->cfg.version : 0; }            /* 1 = MPEG-1, 0 = MPEG-2/2.5 */
-int lame_get_encoder_padding(const lame_global_flags *g) { return ok(g) && g->b ? g->b->st[0].tag.enc_padding : 0; }
-int lame_get_mf_samples_to_encode(const lame_global_flags *g) { return ok(g) && g->b ? (int) g->b->st[0].mf_samples_to_encode : 0; }
+int lame_get_version(const lame_global_flags *g) { return ok(g) && HB(g) ? HB(g)->cfg.version : 0; }            /* 1 = MPEG-1, 0 = MPEG-2/2.5 */
+int lame_get_encoder_padding(const lame_global_flags *g) { return ok(g) && HB(g) ? HS(g).tag.enc_padding : 0; }
+int lame_get_mf_samples_to_encode(const lame_global_flags *g) { return ok(g) && HB(g) ? (int) HS(g).mf_samples_to_encode : 0; }
 int lame_get_totalframes(const lame_global_flags *g)                                                          /* set_get.c:2121 */
 {
-    if (!ok(g) || !g->b) return 0;
-    unsigned long const fs = 576ul * g->b->cfg.mode_gr;
+    if (!ok(g) || !HB(g)) return 0;
+    unsigned long const fs = 576ul * HB(g)->cfg.mode_gr;
     unsigned long n = (unsigned long) g->opt[LG_OPTI_num_samples];
     if (n == (0ul - 1ul) || n == 4294967295ul) return 0;
     if (g->samplerate_in != g->samplerate_out && g->samplerate_in > 0) n *= (double) g->samplerate_out / g->samplerate_in;
@@ -1057,8 +1347,8 @@ int lame_get_totalframes(const lame_global_flags *g)                            
 }
 void lame_print_config(const lame_global_flags *g)
 {
-    if (!ok(g) || !g->b) return;
-    const LgDevCfg *c = &g->b->cfg;
+    if (!ok(g) || !HB(g)) return;
+    const LgDevCfg *c = &HB(g)->cfg;
     fprintf(stderr, "lamegpu %s: %d Hz -> %d Hz%s, MPEG-%s Layer III, %s, quality %d, lowpass %d Hz\n", get_lame_version(), c->samplerate_in, c->samplerate,
             c->resample ? " (resampled on the device)" : "", c->version == 1 ? "1" : (c->samplerate < 16000 ? "2.5" : "2"),
             c->vbr == 0 ? "CBR" : (c->vbr == 3 ? "ABR" : (c->vbr == 2 ? "VBR (rh)" : "VBR (mtrh)")), c->quality, c->lowpassfreq);
@@ -1067,13 +1357,103 @@ void lame_print_internals(const lame_global_flags *g) { lame_print_config(g); }
 /* lame.c:2234 lame_mp3_tags_fid: the finished Info tag over the placeholder frame at the start of the file (no ID3v2 to skip) */
 void lame_mp3_tags_fid(lame_global_flags *g, FILE *f)
 {
-    if (!ok(g) || !g->b || !f || !g->b->st[0].tag.on) return;
+    if (!ok(g) || !HB(g) || !f || !HS(g).tag.on) return;
     unsigned char buf[2880];
     size_t const n = lame_get_lametag_frame(g, buf, sizeof buf);
     if (n == 0 || n > sizeof buf) return;
     if (fseek(f, 0, SEEK_SET) != 0) { fprintf(stderr, "lamegpu: could not update LAME tag, file not seekable.\n"); return; }
     if (fwrite(buf, 1, n, f) != n) fprintf(stderr, "lamegpu: could not update LAME tag.\n");
 }
+/* ---- the rest of the encoder's exports of include/libmp3lame.sym */
+int lame_get_size_mp3buffer(const lame_global_flags *g)                 /* set_get.c:2042 over bitstream.c:801 compute_flushbits */
+{
+    if (!ok(g) || !g->initialised) return 0;
+    std::lock_guard<std::mutex> lk(g->se->lane[g->lane].lm);
+    const Stream &x = HS(g);
+    const LgDevCfg *c = &HB(g)->cfg;
+    int last_ptr = x.bw.h_ptr - 1;
+    if (last_ptr == -1) last_ptr = LG_MAX_HEADER_BUF - 1;
+    long total = x.bw.header[last_ptr].write_timing - x.bw.totbit;
+    total += 8 * ((c->version + 1) * 72000 * c->bitrate_kbps[x.last_bitrate_index] / c->samplerate + x.last_padding);
+    total = (total % 8) ? 1 + total / 8 : total / 8;
+    return (int) (total + (long) x.out.size() + (long) x.bw.buf.size());
+}
+/* presets.c:320 apply_preset as lame_set_preset (set_get.c:2159) calls it on a handle whose tuning options are untouched: the preset
+ * selects the rate mode and level; the tuning values it forces are the ones lame_init_params derives for that mode and level anyway */
+int lame_set_preset(lame_global_flags *g, int preset)
+{
+    if (!ok(g)) return -1;
+    g->preset = preset;
+    switch (preset) {
+    case 1000 /* R3MIX */: preset = 470; g->VBR = vbr_mtrh; break;
+    case 1006 /* MEDIUM */: case 1007 /* MEDIUM_FAST */: preset = 460; g->VBR = vbr_mtrh; break;
+    case 1001 /* STANDARD */: case 1004 /* STANDARD_FAST */: preset = 480; g->VBR = vbr_mtrh; break;
+    case 1002 /* EXTREME */: case 1005 /* EXTREME_FAST */: preset = 500; g->VBR = vbr_mtrh; break;
+    case 1003 /* INSANE */: g->preset = 320; g->mean_brate = 320; g->brate = 320; g->VBR = vbr_off; return 320;      /* its row scales by 1.00 */
+    default: break;
+    }
+    g->preset = preset;
+    if (preset >= 410 && preset <= 500 && preset % 10 == 0) {            /* V9 = 410 ... V0 = 500 */
+        g->vbr_q = (500 - preset) / 10;
+        if (g->VBR == vbr_off) g->preset_foreign = 1;                    /* VBR tuning forced onto a CBR handle: not modelled, lame_init_params says so */
+        return preset;
+    }
+    if (8 <= preset && preset <= 320) {                                  /* apply_abr_preset */
+        g->VBR = vbr_abr; g->mean_brate = preset; g->brate = preset;
+        /* presets.c:294 is not guarded by `enforce`: the row's input scaling is applied here and again by lame_init_params */
+        float const sc = (float) g->opt[LG_OPTI_scale] * lg_abr_preset_scale(preset);
+        g->opt[LG_OPTI_scale] = sc; g->opt_set[LG_OPTI_scale] = 1;
+        return preset;
+    }
+    g->preset = 0;
+    return preset;
+}
+int lame_set_preset_expopts(lame_global_flags *g, int) { return ok(g) ? 0 : -1; }
+/* set_get.c:1650-1850: block switching, one field behind three setters */
+int lame_set_allow_diff_short(lame_global_flags *g, int v) { if (!ok(g)) return -1; g->short_blocks = v ? 0 : 1; return 0; }
+int lame_get_allow_diff_short(const lame_global_flags *g) { return ok(g) ? (g->short_blocks == 0 ? 1 : 0) : 0; }
+int lame_set_no_short_blocks(lame_global_flags *g, int v) { if (!ok(g) || v < 0 || v > 1) return -1; g->short_blocks = v ? 2 : 0; return 0; }
+int lame_get_no_short_blocks(const lame_global_flags *g) { return ok(g) ? (g->short_blocks < 0 ? -1 : (g->short_blocks == 2 ? 1 : 0)) : -1; }
+int lame_set_force_short_blocks(lame_global_flags *g, int v)
+{
+    if (!ok(g) || v < 0 || v > 1) return -1;
+    if (v == 1) g->short_blocks = 3;
+    else if (g->short_blocks == 3) g->short_blocks = 0;
+    return 0;
+}
+int lame_get_force_short_blocks(const lame_global_flags *g) { return ok(g) ? (g->short_blocks < 0 ? -1 : (g->short_blocks == 3 ? 1 : 0)) : -1; }
+void lame_set_msfix(lame_global_flags *g, double v) { if (ok(g)) g->msfix = (float) v; }          /* set_get.c:1686 */
+float lame_get_msfix(const lame_global_flags *g) { return ok(g) ? g->msfix : 0; }
+int lame_set_errorf(lame_global_flags *g, lame_report_function f) { if (!ok(g)) return -1; g->report[0] = f; return 0; }
+int lame_set_debugf(lame_global_flags *g, lame_report_function f) { if (!ok(g)) return -1; g->report[1] = f; return 0; }
+int lame_set_msgf(lame_global_flags *g, lame_report_function f) { if (!ok(g)) return -1; g->report[2] = f; return 0; }
+int lame_set_asm_optimizations(lame_global_flags *g, int optim, int) { return ok(g) ? optim : -1; }
+void lame_set_write_id3tag_automatic(lame_global_flags *g, int v) { if (ok(g)) g->write_id3tag_automatic = v; }
+int lame_get_write_id3tag_automatic(const lame_global_flags *g) { return ok(g) ? g->write_id3tag_automatic : 1; }
+int lame_init_old(lame_global_flags *) { return -1; }
+void get_lame_version_numerical(lame_version_t *v)
+{
+    if (!v) return;
+    v->major = 3; v->minor = 99; v->alpha = 0; v->beta = 0;
+    v->psy_major = 1; v->psy_minor = 0; v->psy_alpha = 0; v->psy_beta = 0;
+    v->features = "";
+}
+int lame_get_bitrate(int mpeg_version, int table_index)                  /* set_get.c: bitrate_table[version][index] */
+{
+    if (0 <= mpeg_version && mpeg_version <= 2 && 0 <= table_index && table_index <= 15) return lg_table_bitrate(mpeg_version, table_index);
+    return -1;
+}
+int lame_get_samplerate(int mpeg_version, int table_index)
+{
+    if (0 <= mpeg_version && mpeg_version <= 2 && 0 <= table_index && table_index <= 3) return lg_table_samplerate(mpeg_version, table_index);
+    return -1;
+}
+int lame_get_RadioGain(const lame_global_flags *) { return 0; }
+int lame_get_AudiophileGain(const lame_global_flags *) { return 0; }
+float lame_get_PeakSample(const lame_global_flags *) { return 0.f; }
+int lame_get_noclipGainChange(const lame_global_flags *) { return 0; }
+float lame_get_noclipScale(const lame_global_flags *) { return -1.f; }
+
 /* lame.c:2145 lame_encode_finish = lame_encode_flush + lame_close */
 int lame_encode_finish(lame_global_flags *g, unsigned char *mp3buf, int size)
 {
@@ -1086,41 +1466,41 @@ int lame_encode_finish(lame_global_flags *g, unsigned char *mp3buf, int size)
  * stereo mode, gr.ch per bitrate and block type) */
 void lame_bitrate_kbps(const lame_global_flags *g, int bitrate_kbps[14])
 {
-    if (!ok(g) || !g->b) return;
-    for (int i = 0; i < 14; i++) bitrate_kbps[i] = g->b->cfg.bitrate_kbps[i + 1];
+    if (!ok(g) || !HB(g)) return;
+    for (int i = 0; i < 14; i++) bitrate_kbps[i] = HB(g)->cfg.bitrate_kbps[i + 1];
 }
 void lame_bitrate_hist(const lame_global_flags *g, int bitrate_count[14])
 {
-    if (!ok(g) || !g->b) return;
-    for (int i = 0; i < 14; i++) bitrate_count[i] = g->b->st[0].hist_mode[i + 1][4];
+    if (!ok(g) || !HB(g)) return;
+    for (int i = 0; i < 14; i++) bitrate_count[i] = HS(g).hist_mode[i + 1][4];
 }
 void lame_stereo_mode_hist(const lame_global_flags *g, int stmode_count[4])
 {
-    if (!ok(g) || !g->b) return;
-    for (int i = 0; i < 4; i++) stmode_count[i] = g->b->st[0].hist_mode[15][i];
+    if (!ok(g) || !HB(g)) return;
+    for (int i = 0; i < 4; i++) stmode_count[i] = HS(g).hist_mode[15][i];
 }
 void lame_bitrate_stereo_mode_hist(const lame_global_flags *g, int bitrate_stmode_count[14][4])
 {
-    if (!ok(g) || !g->b) return;
-    for (int j = 0; j < 14; j++) for (int i = 0; i < 4; i++) bitrate_stmode_count[j][i] = g->b->st[0].hist_mode[j + 1][i];
+    if (!ok(g) || !HB(g)) return;
+    for (int j = 0; j < 14; j++) for (int i = 0; i < 4; i++) bitrate_stmode_count[j][i] = HS(g).hist_mode[j + 1][i];
 }
 void lame_block_type_hist(const lame_global_flags *g, int btype_count[6])
 {
-    if (!ok(g) || !g->b) return;
-    for (int i = 0; i < 6; i++) btype_count[i] = g->b->st[0].hist_block[15][i];
+    if (!ok(g) || !HB(g)) return;
+    for (int i = 0; i < 6; i++) btype_count[i] = HS(g).hist_block[15][i];
 }
 void lame_bitrate_block_type_hist(const lame_global_flags *g, int bitrate_btype_count[14][6])
 {
-    if (!ok(g) || !g->b) return;
-    for (int j = 0; j < 14; j++) for (int i = 0; i < 6; i++) bitrate_btype_count[j][i] = g->b->st[0].hist_block[j + 1][i];
+    if (!ok(g) || !HB(g)) return;
+    for (int j = 0; j < 14; j++) for (int i = 0; i < 6; i++) bitrate_btype_count[j][i] = HS(g).hist_block[j + 1][i];
 }
 /* VbrTag.c:900 lame_get_lametag_frame (+ :151 Xing_seek_table, :597 PutLameVBR) for the configurations this library
  * encodes: CBR ("Info"), MPEG-1, no CRC, no ReplayGain analysis, no nogap. */
 size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer, size_t size)
 {
-    if (!ok(g) || !g->initialised || !g->b) return 0;
-    const Stream &x = g->b->st[0];
-    const LgDevCfg *c = &g->b->cfg;
+    if (!ok(g) || !g->initialised || !HB(g)) return 0;
+    const Stream &x = HS(g);
+    const LgDevCfg *c = &HB(g)->cfg;
     const Stream::Tag &v = x.tag;
     if (!v.on) return 0;
     if (v.pos <= 0) return 0;
@@ -1197,7 +1577,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
     k += 3;
     p[k++] = nMisc;
     p[k++] = 0;
-    put_be16(p + k, (unsigned) ((c->vbr == 4 || c->vbr == 2) ? 500 - 10 * c->vbr_q : c->vbr_mean_kbps)); k += 2;   /* cfg->preset: apply_preset(...), presets.c:361 */
+    put_be16(p + k, (unsigned) c->preset); k += 2;           /* cfg->preset: what apply_preset was called with, presets.c:361 */
     put_be32(p + k, stream_size); k += 4;
     put_be16(p + k, v.music_crc); k += 2;
     for (int i = 0; i < k; i++) crc = crc16_update(p[i], crc);
@@ -1208,7 +1588,8 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
 int lame_close(lame_global_flags *g)
 {
     if (!ok(g)) return -3;
-    if (g->b) lamegpu_batch_close(g->b);
+    if (g->se) shared_release(g->se, g->lane);
+    g->se = nullptr;
     g->class_id = 0;
     free(g);
     return 0;

@@ -12,10 +12,36 @@
 extern "C" {
 #endif
 typedef struct lg_engine lg_engine;
-/* options that only change host-computed constants of the configuration (lame_set_* of the same name; see lg_setup.cpp) */
-typedef struct LgSetupOpt LgSetupOpt;
+/* libmp3lame options that only change host-computed constants of the configuration (the lame_set_* of the same name), with
+ * the values a fresh lame_init() handle has: "not set" is what lame_init_params and the presets test for (presets.c:34 SET_OPTION) */
+typedef struct LgSetupOpt {
+    float scale, scale_left, scale_right;       /* 1: lame.c:1196-1206 pcm_transform */
+    float compression_ratio;                    /* 0 = not set: lame.c:629 */
+    int   lowpassfreq, lowpasswidth;            /* Hz; 0 = chosen from the rate, -1 = no filter; width -1 = default (lame.c:704, :878) */
+    int   highpassfreq, highpasswidth;          /* Hz; 0 / -1 = none; width -1 = default (lame.c:861) */
+    int   no_ath;                               /* quantize_pvt.c:294: ATH at -200 dB */
+    int   ath_only, ath_short;                  /* only reach the Info tag's "non-optimal" flag in 3.99.5 (VbrTag.c:789) */
+    int   ath_type;                             /* -1 = default: 4, the VBR-new presets force 5 (presets.c:180) */
+    float ath_lower_db;                         /* lame_set_ATHlower; 0 = the preset's */
+    float ath_curve;                            /* -1 = the preset's */
+    int   athaa_type;                           /* -1 = default (3) */
+    float athaa_sensitivity;                    /* 0 = the preset's */
+    float msfix;                                /* -1 = the preset's */
+    float interch;                              /* lame_set_interChRatio; -1 = the preset's */
+    int   short_blocks;                         /* -1 not set, 0 allowed, 1 coupled, 2 dispensed (no_short_blocks), 3 forced (lame_global_flags.h:20) */
+    int   force_ms, disable_reservoir;
+    int   strict_iso;                           /* 0 MDB_DEFAULT, 1 MDB_STRICT_ISO, 2 MDB_MAXIMUM (lame_init: 2); bitstream.c:91 */
+    int   use_temporal;                         /* -1 = default: on, off for VBR-new */
+    int   vbr_min_kbps, vbr_max_kbps, vbr_hard_min;   /* 0 = not set: lame.c:1067-1093, quantize.c:1550 */
+} LgSetupOpt;
+void lg_setup_opt_defaults(LgSetupOpt *o);
+int lg_setup_ex(LgDevCfg *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac,
+                const LgSetupOpt *opt);
 int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out /* 0 = as lame_init_params picks it */, int channels, int brate, int mode, int quality,
              int vbr /* 0 vbr_off, 3 vbr_abr, 4 vbr_mtrh (brate = VBR_q) */, float vbr_q_frac /* VBR quality = VBR_q + this */);
+float lg_abr_preset_scale(int kbps);
+int lg_table_bitrate(int version, int index);
+int lg_table_samplerate(int version, int index);
 lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device);
 void lg_engine_destroy(lg_engine *e);
 int  lg_engine_reset_streams(lg_engine *e, int first, int count);

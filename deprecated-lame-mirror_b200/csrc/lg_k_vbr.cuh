@@ -803,7 +803,7 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
         __syncthreads();
         /* ---- the lowest bitrate that holds the frame (quantize.c:1700-1735), reservoir update */
         {
-            int i = analog_silence ? 1 : c->vbr_min_bitrate_index, bitrate_index;
+            int i = (analog_silence && !c->enforce_min_bitrate) ? 1 : c->vbr_min_bitrate_index, bitrate_index;
             for (; i < c->vbr_max_bitrate_index; i++) if (used_bits <= frameBits[i]) break;
             if (i > c->vbr_max_bitrate_index) i = c->vbr_max_bitrate_index;
             if (pad > 0) {

@@ -271,7 +271,7 @@ lg_kernel_vbrold(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_
             if (lane == 0) sm->used[ch] = my_used;
             __syncthreads();
             used_bits = sm->used[0] + sm->used[1];
-            bitrate_index = analog_silence ? 1 : c->vbr_min_bitrate_index;
+            bitrate_index = (analog_silence && !c->enforce_min_bitrate) ? 1 : c->vbr_min_bitrate_index;
             for (; bitrate_index < max_index; bitrate_index++) if (used_bits <= frameBits[bitrate_index]) break;
             int const full = lg_resv_frame_begin(c, bitrate_index, padding, resv_size, &mean_bits, &resv_max);
             __syncthreads();

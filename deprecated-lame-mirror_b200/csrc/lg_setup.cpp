@@ -11,6 +11,7 @@
 #include <float.h>
 #include <string.h>
 #include "lg_types.h"
+#include "lg_engine.h"
 #include "lg_tables_data.inc"
 
 #define LG_FLOAT_MAX 1e37 /* machine.h:137 (FLT_MAX is not visible there) */
@@ -167,6 +168,12 @@ static void setup_ath_sfb(LgDevCfg *c)
             c->ath_psfb12[sfb] = c->ath_psfb12[sfb] < a ? c->ath_psfb12[sfb] : a;
         }
         c->ath_psfb12[sfb] *= (c->sfb_s[13] - c->sfb_s[12]);
+    }
+    if (c->no_ath) {                                                   /* quantize_pvt.c:294: reduce the ATH to -200 dB */
+        for (sfb = 0; sfb < 22; sfb++) c->ath_l[sfb] = 1E-20;
+        for (sfb = 0; sfb < 6; sfb++) c->ath_psfb21[sfb] = 1E-20;
+        for (sfb = 0; sfb < 13; sfb++) c->ath_s[sfb] = 1E-20;
+        for (sfb = 0; sfb < 6; sfb++) c->ath_psfb12[sfb] = 1E-20;
     }
     c->ath_floor = 10. * log10(ath_mdct(c, -1.));
 }
@@ -607,7 +614,33 @@ static int setup_resampler(LgDevCfg *c)
 
 static void finish_device_tables(LgDevCfg *c);
 
+/* presets.c:294: apply_abr_preset multiplies the handle's scale by its row's factor - every time it runs, so lame_set_preset(kbps)
+ * followed by lame_init_params applies it twice */
+extern "C" float lg_abr_preset_scale(int kbps)
+{
+    static const float sc[17] = { 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.95f, 0.97f, 0.98f, 1.00f, 1.00f };
+    return sc[nearest_full_index(kbps)];
+}
+/* tables.c bitrate_table / samplerate_table rows (0 = MPEG-2, 1 = MPEG-1, 2 = MPEG-2.5) */
+extern "C" int lg_table_bitrate(int version, int index) { return LGT_BITRATE[16 * version + index]; }
+extern "C" int lg_table_samplerate(int version, int index) { return LGT_SAMPLERATE[4 * version + index]; }
+
+extern "C" void lg_setup_opt_defaults(LgSetupOpt *o)
+{
+    memset(o, 0, sizeof *o);
+    o->scale = o->scale_left = o->scale_right = 1.f;
+    o->lowpasswidth = o->highpasswidth = -1;
+    o->ath_type = -1; o->ath_curve = -1.f; o->athaa_type = -1; o->msfix = -1.f; o->interch = -1.f;
+    o->short_blocks = -1; o->strict_iso = 2; o->use_temporal = -1;
+}
 extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac)
+{
+    LgSetupOpt o;
+    lg_setup_opt_defaults(&o);
+    return lg_setup_ex(c, samplerate_in, samplerate_out, channels, brate, mode, quality, vbr, vbr_q_frac, &o);
+}
+extern "C" int lg_setup_ex(LgDevCfg *c, int samplerate_in, int samplerate_out, int channels, int brate, int mode, int quality, int vbr, float vbr_q_frac,
+                           const LgSetupOpt *opt)
 {
     /* presets.c:241 abr_switch_map, the columns the CBR path reads */
     static const struct { int kbps, safejoint; float nsmsfix, st_lrm, st_s, scale, masking_adj, ath_lower, ath_curve, interch; int sfscale; }
@@ -646,7 +679,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
     int vbr_no_lowpass = 0;
     int samplerate = samplerate_out;                                   /* 0 = chosen below the way lame_init_params does */
     float athaa_sensitivity = 0;
-    float scale = 1, maskingadjust, maskingadjust_short, ath_lower_db, attackthre, attackthre_s;
+    float maskingadjust, maskingadjust_short, ath_lower_db, attackthre, attackthre_s;
     double lowpass;
 
     memset(c, 0, sizeof *c);
@@ -655,7 +688,8 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
     c->channels = channels;
     if (channels == 1) mode = LG_MONO;                                 /* lame.c:597 */
     if (mode == LG_MONO) c->channels = 1;
-    c->force_ms = 0;
+    c->force_ms = (mode == LG_MONO) ? 0 : (opt->force_ms != 0);        /* lame.c:603 */
+    float scale = opt->scale;
     if (vbr != 0 && vbr != 2 && vbr != 3 && vbr != 4) return -1;                  /* vbr_off, vbr_abr, vbr_mtrh (lame.h:94) */
     if (vbr == 2) {                                                    /* vbr_rh: `brate` carries VBR_q, no mapping to other rates */
         vbr_q = brate;
@@ -708,9 +742,10 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
         }
     }
     else {
-        if (brate == 0) {                                              /* lame.c:623-644 */
+        if (brate == 0 || opt->compression_ratio > 0) {               /* lame.c:623-644 */
+            float const ratio = opt->compression_ratio > 0 ? opt->compression_ratio : 11.025f;
             if (samplerate == 0) samplerate = map_to_mp3_frequency((int) (0.97 * samplerate_in));
-            brate = samplerate * 16 * c->channels / (1.e3 * 11.025f);
+            brate = samplerate * 16 * c->channels / (1.e3 * ratio);
         }
     }
     /* lame.c:704-762: low-pass from the bitrate */
@@ -725,6 +760,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
         lowpass = a + m * (b - a);
     }
     else if (mode == LG_MONO) lowpass *= 1.5;
+    if (opt->lowpassfreq != 0) lowpass = opt->lowpassfreq;             /* lame.c:704: the automatic choice only when none was asked for */
     c->lowpassfreq = lowpass;
     if (samplerate == 0) {                                             /* lame.c:764-769 */
         if (2 * c->lowpassfreq > samplerate_in) c->lowpassfreq = samplerate_in / 2;
@@ -742,11 +778,7 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
             if (LGT_BITRATE[16 * brow + i] > 0 && abs(LGT_BITRATE[16 * brow + i] - brate) < abs(best - brate)) best = LGT_BITRATE[16 * brow + i];
         brate = best;
     }
-    if (vbr == 3) {                                                    /* lame.c:1088-1093: into the range of this MPEG version */
-        int const hi = LGT_BITRATE[16 * version + (samplerate < 16000 ? 8 : 14)], lo = LGT_BITRATE[16 * version + 1];
-        if (brate > hi) brate = hi;
-        if (brate < lo) brate = lo;
-    }
+    int const preset_brate = brate;                                    /* apply_preset (lame.c:1038) sees the mean bitrate before it is clamped into the index range (:1088-1093) */
     c->samplerate = samplerate;
     c->samplerate_in = samplerate_in;
     if (setup_resampler(c) != 0) return -1;
@@ -758,10 +790,21 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
     /* dual channel (mode 2): two independent channels - no M/S, block types not coupled, its own header code */
     c->mode = mode;
     c->highpass1 = c->highpass2 = 0;
+    if (opt->highpassfreq > 0) {                                       /* lame.c:860-875 */
+        c->highpass1 = 2. * opt->highpassfreq;
+        if (opt->highpasswidth >= 0) c->highpass2 = 2. * (opt->highpassfreq + opt->highpasswidth);
+        else c->highpass2 = (1 + 0.00) * 2. * opt->highpassfreq;
+        c->highpass1 /= samplerate;
+        c->highpass2 /= samplerate;
+    }
     c->lowpass1 = c->lowpass2 = 0;
     if (c->lowpassfreq > 0 && c->lowpassfreq < (samplerate / 2)) {
         c->lowpass2 = 2. * c->lowpassfreq;
-        c->lowpass1 = (1 - 0.00) * 2. * c->lowpassfreq;
+        if (opt->lowpasswidth >= 0) {                                  /* lame.c:880-884 */
+            c->lowpass1 = 2. * (c->lowpassfreq - opt->lowpasswidth);
+            if (c->lowpass1 < 0) c->lowpass1 = 0;
+        }
+        else c->lowpass1 = (1 - 0.00) * 2. * c->lowpassfreq;
         c->lowpass1 /= samplerate;
         c->lowpass2 /= samplerate;
     }
@@ -773,7 +816,26 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
     c->vbr_mean_kbps = brate;
     c->vbr_min_bitrate_index = 1;                                      /* lame.c:1067-1068 */
     c->vbr_max_bitrate_index = samplerate < 16000 ? 8 : 14;            /* 64 kbps with MPEG-2.5 */
-    c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * brate);   /* lame.c:778-784 */
+    c->enforce_min_bitrate = opt->vbr_hard_min != 0;                   /* lame.c:557 */
+    if (vbr != 0) {                                                    /* lame.c:1071-1093: the user's bitrate range, nearest table entries */
+        for (int pass = 0; pass < 2; pass++) {
+            int const want = pass ? opt->vbr_max_kbps : opt->vbr_min_kbps;
+            if (!want) continue;
+            int bestk = LGT_BITRATE[16 * brow + 1], idx = -1;          /* util.c:320 FindNearestBitrate, :360 BitrateIndex */
+            for (i = 1; i <= 14; i++)
+                if (LGT_BITRATE[16 * brow + i] > 0 && abs(LGT_BITRATE[16 * brow + i] - want) < abs(bestk - want)) bestk = LGT_BITRATE[16 * brow + i];
+            for (i = 0; i <= 14; i++) if (LGT_BITRATE[16 * brow + i] > 0 && LGT_BITRATE[16 * brow + i] == bestk) { idx = i; break; }
+            if (idx < 0) return -1;
+            if (pass) c->vbr_max_bitrate_index = idx; else c->vbr_min_bitrate_index = idx;
+        }
+        if (vbr == 3) {
+            int const hi = LGT_BITRATE[16 * version + c->vbr_max_bitrate_index], lo = LGT_BITRATE[16 * version + c->vbr_min_bitrate_index];
+            if (brate > hi) brate = hi;
+            if (brate < lo) brate = lo;
+            c->brate = brate; c->vbr_mean_kbps = brate;
+        }
+    }
+    c->compression_ratio = samplerate * 16 * c->channels / (1.e3 * (vbr == 3 ? preset_brate : brate));   /* lame.c:839-846, before the clamp of :1085 */
     for (i = 0; i < 16; i++) c->bitrate_kbps[i] = LGT_BITRATE[16 * version + i];
     c->vbr_q = vbr_q;
     c->vbr_q_frac = (vbr == 4 || vbr == 2) ? vbr_q_frac : 0.f;
@@ -810,15 +872,22 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
             attackthre_s = VLERP(st_s);
             maskingadjust = VLERP(madj);
             maskingadjust_short = VLERP(madj_s);
-            ath_lower_db = VLERP(ath_lower);
-            c->athcurve = VLERP(ath_curve);
-            athaa_sensitivity = VLERP(ath_sens);
-            c->interch = VLERP(interch);
-            if (!(c->interch > 0)) c->interch = 0;
+            /* presets.c:34 SET_OPTION: the preset's value unless the option was set (differs from its "unset" value) */
+            ath_lower_db = (fabs(opt->ath_lower_db - 0) > 0) ? opt->ath_lower_db : VLERP(ath_lower);
+            c->athcurve = (fabs(opt->ath_curve - -1) > 0) ? opt->ath_curve : VLERP(ath_curve);
+            athaa_sensitivity = (fabs(opt->athaa_sensitivity - 0) > 0) ? opt->athaa_sensitivity : VLERP(ath_sens);
+            c->interch = opt->interch;
+            if (VLERP(interch) > 0 && !(fabs(opt->interch - -1) > 0)) c->interch = VLERP(interch);      /* presets.c:185-187 */
+            if (c->interch < 0) c->interch = 0;                        /* lame.c:1158 */
             sfb21mod = sfb21mod + x * (VP(n).sfb21mod - sfb21mod);
-            c->msfix = VLERP(msfix);
+            c->msfix = (fabs(opt->msfix - -1) > 0) ? opt->msfix : VLERP(msfix);
+            if (c->msfix < 0) c->msfix = 0;                            /* lame.c:1143 */
             c->minval = VLERP(minval);
-            c->athfixpoint = VLERP(ath_fixpoint);
+            {   /* presets.c:208-212: the fixpoint follows the input scaling */
+                double const ax = fabs(opt->scale);
+                double const y = (ax > 0.f) ? (10.f * log10(ax)) : 0.f;
+                c->athfixpoint = VLERP(ath_fixpoint) - y;
+            }
 #undef VLERP
             if (VP(vbr_q).safejoint > 0) exp_nspsytune |= 2;
 #undef VP
@@ -837,25 +906,29 @@ extern "C" int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out, int 
         goto presets_done;
     }
     /* presets.c:216 apply_abr_preset(brate) with every option still at its default */
-    r = nearest_full_index(brate);
+    r = nearest_full_index(preset_brate);
     if (pm[r].safejoint > 0) exp_nspsytune |= 2;
     c->noise_shaping = pm[r].sfscale > 0 ? 2 : 0;
     c->quant_comp = 9;
     c->quant_comp_short = 9;
-    c->msfix = pm[r].nsmsfix;
+    c->msfix = (fabs(opt->msfix - -1) > 0) ? opt->msfix : pm[r].nsmsfix;
+    if (c->msfix < 0) c->msfix = 0;
     attackthre = pm[r].st_lrm;
     attackthre_s = pm[r].st_s;
-    scale = scale * pm[r].scale;
+    scale = scale * pm[r].scale;                                       /* presets.c:294: on top of the user's scale */
     maskingadjust = pm[r].masking_adj;
     if (pm[r].masking_adj > 0) maskingadjust_short = pm[r].masking_adj * .9;
     else maskingadjust_short = pm[r].masking_adj * 1.1;
-    ath_lower_db = pm[r].ath_lower;
-    c->athcurve = pm[r].ath_curve;
-    c->interch = pm[r].interch;
+    ath_lower_db = (fabs(opt->ath_lower_db - 0) > 0) ? opt->ath_lower_db : pm[r].ath_lower;
+    c->athcurve = (fabs(opt->ath_curve - -1) > 0) ? opt->ath_curve : pm[r].ath_curve;
+    c->interch = (fabs(opt->interch - -1) > 0) ? opt->interch : pm[r].interch;
+    if (c->interch < 0) c->interch = 0;
+    athaa_sensitivity = opt->athaa_sensitivity;
     c->minval = 5. * (pm[r].kbps / 320.);
 
     c->sfb21_extra = 0;
 presets_done:
+    c->preset = (vbr == 4 || vbr == 2) ? 500 - 10 * vbr_q : preset_brate;     /* lame.c:983, :1038 */
     c->mask_adjust = maskingadjust;
     c->mask_adjust_short = maskingadjust_short;
     c->substep_shaping = 0;
@@ -866,11 +939,19 @@ presets_done:
     if (quality == 8) quality = 7;
     c->quality = quality;
     if (setup_quality(c, quality) < 0) return -1;
-    c->ath_use_adjust = 3;
+    c->ath_use_adjust = opt->athaa_type < 0 ? 3 : opt->athaa_type;      /* lame.c:1104-1107 */
     c->ath_aa_sensitivity_p = pow(10.0, athaa_sensitivity / -10.0);
-    c->short_blocks = (c->mode == LG_JOINT || c->mode == LG_STEREO) ? 1 /* coupled */ : 0 /* allowed */;
-    c->athtype = (vbr == 4) ? 5 : 4;                                    /* presets.c:170 */
-    c->use_temporal = (vbr == 4) ? 0 : 1;                               /* lame.c:979-981 */
+    {   /* lame.c:1115-1133: not set -> allowed; allowed becomes coupled in the two stereo modes */
+        int sb = opt->short_blocks;
+        if (sb < 0) sb = 0;
+        if (sb == 0 && (c->mode == LG_JOINT || c->mode == LG_STEREO)) sb = 1;
+        c->short_blocks = sb;
+    }
+    c->athtype = (vbr == 4) ? 5 : (opt->ath_type < 0 ? 4 : opt->ath_type);   /* presets.c:180 forces 5; lame.c:1149 */
+    c->use_temporal = opt->use_temporal >= 0 ? (opt->use_temporal != 0) : ((vbr == 4) ? 0 : 1);      /* lame.c:979-981, :1161 */
+    c->no_ath = opt->no_ath != 0;
+    c->ath_only = opt->ath_only != 0 || opt->ath_short != 0;
+    c->disable_reservoir = opt->disable_reservoir != 0;
     c->ath_offset_db = 0 - ath_lower_db;
     c->ath_offset_factor = powf(10.f, c->ath_offset_db * 0.1f);
     c->use_safe_joint_stereo = exp_nspsytune & 2;
@@ -882,6 +963,8 @@ presets_done:
     {
         float m[2][2] = { {1.0f, 0.0f}, {0.0f, 1.0f} };
         m[0][0] *= scale; m[0][1] *= scale; m[1][0] *= scale; m[1][1] *= scale;
+        m[0][0] *= opt->scale_left; m[0][1] *= opt->scale_left;
+        m[1][0] *= opt->scale_right; m[1][1] *= opt->scale_right;
         if (channels == 2 && c->channels == 1) {
             m[0][0] = 0.5f * (m[0][0] + m[1][0]);
             m[0][1] = 0.5f * (m[0][1] + m[1][1]);
@@ -892,7 +975,10 @@ presets_done:
     c->frac_spf = (vbr == 0) ? ((version + 1) * 72000L * brate) % samplerate : 0;      /* lame.c:1245 */
     setup_quantizer_tables(c);
     setup_psy(c, attackthre, attackthre_s, (vbr == 4 || vbr == 2) ? vbr_q : 4, (vbr == 4 || vbr == 2) ? vbr_q_frac : 0.f);
-    c->buffer_constraint = 7680 * (version + 1);                       /* bitstream.c:119 MDB_MAXIMUM */
+    /* bitstream.c:91 get_max_frame_buffer_size_by_constraint (the handle's default is MDB_MAXIMUM, lame.c:2341) */
+    if (opt->strict_iso == 2) c->buffer_constraint = 7680 * (version + 1);
+    else if (opt->strict_iso == 1) c->buffer_constraint = 8 * ((version + 1) * 72000 * LGT_BITRATE[16 * version + (samplerate < 16000 ? 8 : 14)] / samplerate);
+    else c->buffer_constraint = 8 * 1440;
     finish_device_tables(c);
     return 0;
 }

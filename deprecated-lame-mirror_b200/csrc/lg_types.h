@@ -63,7 +63,9 @@ typedef struct {
     int   noise_shaping, noise_shaping_amp, noise_shaping_stop, subblock_gain, use_best_huffman,
           full_outer_loop, quant_comp, quant_comp_short, substep_shaping, sfb21_extra,
           use_temporal, short_blocks, force_ms, use_safe_joint_stereo, disable_reservoir,
-          error_protection, copyright, original, extension, emphasis, athtype, ath_use_adjust;
+          error_protection, copyright, original, extension, emphasis, athtype, ath_use_adjust,
+          enforce_min_bitrate /* lame_set_VBR_hard_min: silent frames keep the minimum bitrate too */, ath_only, no_ath,
+          preset /* what apply_preset was last called with: goes into the LAME tag (VbrTag.c:713) */;
     float msfix, ath_offset_db, ath_offset_factor, athcurve, athfixpoint, minval, interch;
     float mask_adjust, mask_adjust_short, pcm_transform[2][2], lowpass1, lowpass2, highpass1, highpass2;
     float adjust_bass_db, adjust_alto_db, adjust_treble_db, adjust_sfb21_db;

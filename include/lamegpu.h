@@ -19,6 +19,7 @@
 #define LAMEGPU_H
 #include <stddef.h>
 #include <stdio.h>
+#include <stdarg.h>
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -31,6 +32,12 @@ typedef lame_global_flags *lame_t;
 typedef enum vbr_mode_e { vbr_off = 0, vbr_mt, vbr_rh, vbr_abr, vbr_mtrh, vbr_max_indicator, vbr_default = vbr_mtrh } vbr_mode; /* lame.h:49-57 */
 typedef enum MPEG_mode_e { STEREO = 0, JOINT_STEREO, DUAL_CHANNEL, MONO, NOT_SET, MAX_INDICATOR } MPEG_mode;               /* lame.h:61-68 */
 typedef enum Padding_type_e { PAD_NO = 0, PAD_ALL, PAD_ADJUST, PAD_MAX_INDICATOR } Padding_type;                             /* lame.h:72-77 */
+typedef void (*lame_report_function)(const char *format, va_list ap);                                                        /* lame.h:38 */
+typedef struct {                                                                                                             /* lame.h:655-669 */
+    int major, minor, alpha, beta;
+    int psy_major, psy_minor, psy_alpha, psy_beta;
+    const char *features;
+} lame_version_t;
 
 lame_global_flags *lame_init(void);                                                  /* lame.h:168  NULL on OOM */
 int  lame_set_in_samplerate(lame_global_flags *, int);                               /* lame.h:188 */
@@ -83,6 +90,36 @@ int  lame_encode_buffer_long2(lame_global_flags *, const long pcm_l[], const lon
 int  lame_encode_buffer_int(lame_global_flags *, const int pcm_l[], const int pcm_r[], const int nsamples,
                             unsigned char *mp3buf, const int mp3buf_size);           /* lame.h:831  +/-MAX_INT full scale */
 int  lame_encode_flush(lame_global_flags *, unsigned char *mp3buf, int size);        /* lame.h:856 */
+int  lame_encode_flush_nogap(lame_global_flags *, unsigned char *mp3buf, int size);  /* lame.h:878  flush_bitstream without the end-of-input padding */
+int  lame_init_bitstream(lame_global_flags *);                                       /* lame.h:890  a new file after a nogap flush: statistics and tag start over */
+int  lame_get_size_mp3buffer(const lame_global_flags *);                             /* lame.h:594  bytes a nogap flush would hand out now */
+int  lame_set_preset(lame_global_flags *, int preset);                               /* lame.h:359  V0..V9, 8..320 (ABR), STANDARD / EXTREME / MEDIUM / INSANE / R3MIX */
+int  lame_set_preset_expopts(lame_global_flags *, int);                              /* lame.h:1304 obsolete: does nothing */
+int  lame_set_errorf(lame_global_flags *, lame_report_function);                     /* lame.h:346 */
+int  lame_set_debugf(lame_global_flags *, lame_report_function);                     /* lame.h:347 */
+int  lame_set_msgf(lame_global_flags *, lame_report_function);                       /* lame.h:348 */
+int  lame_set_no_short_blocks(lame_global_flags *, int);                             /* lame.h:399  three views of one field, set_get.c:1650-1850 */
+int  lame_get_no_short_blocks(const lame_global_flags *);
+int  lame_set_force_short_blocks(lame_global_flags *, int);                          /* lame.h:403 */
+int  lame_get_force_short_blocks(const lame_global_flags *);
+int  lame_set_allow_diff_short(lame_global_flags *, int);                            /* lame.h:392 */
+int  lame_get_allow_diff_short(const lame_global_flags *);
+void lame_set_msfix(lame_global_flags *, double);                                    /* lame.h:424 */
+float lame_get_msfix(const lame_global_flags *);                                     /* lame.h:425 */
+int  lame_set_asm_optimizations(lame_global_flags *, int optim, int mode);           /* lame.h:334  no CPU SIMD paths here: accepted, no effect */
+void lame_set_write_id3tag_automatic(lame_global_flags *, int);                      /* lame.h:1266 */
+int  lame_get_write_id3tag_automatic(const lame_global_flags *);                     /* lame.h:1267 */
+int  lame_init_old(lame_global_flags *);                                             /* lame.h:1278 obsolete initialiser of a caller-allocated struct: -1 */
+void get_lame_version_numerical(lame_version_t *);                                   /* lame.h:671 */
+int  lame_get_bitrate(int mpeg_version, int table_index);                            /* lame.h:1308 */
+int  lame_get_samplerate(int mpeg_version, int table_index);                         /* lame.h:1309 */
+/* ReplayGain analysis is outside the hot path (off by default in the library, lame.c:2386): the getters
+ * report "not computed" as the reference does without the analysis */
+int  lame_get_RadioGain(const lame_global_flags *);                                  /* lame.h:610 */
+int  lame_get_AudiophileGain(const lame_global_flags *);                             /* lame.h:613 */
+float lame_get_PeakSample(const lame_global_flags *);                                /* lame.h:616 */
+int  lame_get_noclipGainChange(const lame_global_flags *);                           /* lame.h:620 */
+float lame_get_noclipScale(const lame_global_flags *);                               /* lame.h:625 */
 /* Info tag (CBR): lame_set_bWriteVbrTag(1) - the reference's default - puts the all-zero placeholder frame ahead of
  * the audio; after lame_encode_flush this returns the finished tag frame to be written at offset 0 (VbrTag.c:900) */
 size_t lame_get_lametag_frame(const lame_global_flags *, unsigned char *buffer, size_t size); /* lame.h:970 */

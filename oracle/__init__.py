@@ -24,6 +24,7 @@ def build(verbose=False):
     targets = ["port"]
     if os.path.exists(os.path.join(REFERENCE_ROOT, "libmp3lame", "lame.c")):
         targets.append("ref")
+        targets.append("frontend")      # the reference's own `lame` program linked against the reference and against the product library
     subprocess.run(["make", "-C", HERE, "-j8"] + targets, check=True,
                    stdout=None if verbose else subprocess.DEVNULL, stderr=None if verbose else subprocess.DEVNULL)
     return os.path.exists(PORT_SO), os.path.exists(REF_SO)

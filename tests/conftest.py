@@ -9,6 +9,10 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# handles of the libmp3lame face are lanes of a shared engine (512 by default): the tests make a handle or two at a time
+os.environ.setdefault("LAMEGPU_LANES", "8")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

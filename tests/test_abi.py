@@ -45,23 +45,33 @@ def test_library_contains_sm100a_kernels(lib):
 
 
 def test_carried_options_accept_defaults_only(lib):
-    """the lame_set_X / lame_get_X pairs of libmp3lame that this library does not act on: the value is stored and read back, and
-    lame_init_params refuses it when it is not the reference's default (checked before any GPU work)"""
+    """the lame_set_X / lame_get_X pairs of libmp3lame that this library does not act on (free format, ReplayGain, the decoder, ...): the
+    value is stored and read back, and lame_init_params refuses it when it is not what a fresh handle has - before any GPU work.  The
+    honoured ones (filters, scaling, ATH, reservoir, ...) are checked against the reference on the GPU (tests/test_frontend_dropin.py)."""
     import ctypes
     L = lib.load_library()
-    for fn, res, arg in (("lame_set_lowpassfreq", None, ctypes.c_int), ("lame_get_lowpassfreq", ctypes.c_int, None), ("lame_set_scale", None, ctypes.c_float),
-                         ("lame_get_scale", ctypes.c_float, None), ("lame_set_disable_reservoir", None, ctypes.c_int), ("lame_set_copyright", None, ctypes.c_int),
-                         ("lame_get_copyright", ctypes.c_int, None), ("lame_get_original", ctypes.c_int, None)):
+    for fn, res, arg in (("lame_set_free_format", None, ctypes.c_int), ("lame_get_free_format", ctypes.c_int, None), ("lame_set_findReplayGain", None, ctypes.c_int),
+                         ("lame_set_quant_comp", None, ctypes.c_int), ("lame_get_quant_comp", ctypes.c_int, None), ("lame_set_copyright", None, ctypes.c_int),
+                         ("lame_get_copyright", ctypes.c_int, None), ("lame_get_original", ctypes.c_int, None), ("lame_get_useTemporal", ctypes.c_int, None),
+                         ("lame_set_experimentalZ", None, ctypes.c_int)):
         f = getattr(L, fn)
         f.restype = res if res else ctypes.c_int
         f.argtypes = [ctypes.c_void_p] + ([arg] if arg else [])
-    h = L.lame_init()
-    assert L.lame_get_lowpassfreq(h) == 0 and L.lame_get_scale(h) == 1.0 and L.lame_get_original(h) == 1
-    assert L.lame_set_disable_reservoir(h, 0) == 0 and L.lame_set_scale(h, 1.0) == 0 and L.lame_set_copyright(h, 1) == 0
-    assert L.lame_get_copyright(h) == 1
-    assert L.lame_set_lowpassfreq(h, 12345) == 0 and L.lame_get_lowpassfreq(h) == 12345
-    assert L.lame_init_params(h) == -1           # a low-pass other than the default is not implemented: refused, loudly
-    L.lame_close(h)
+    for setter, value in (("lame_set_free_format", 1), ("lame_set_findReplayGain", 1), ("lame_set_quant_comp", 3), ("lame_set_experimentalZ", 1)):
+        h = ctypes.c_void_p(L.lame_init())
+        assert L.lame_get_free_format(h) == 0 and L.lame_get_original(h) == 1 and L.lame_get_quant_comp(h) == -1 and L.lame_get_useTemporal(h) == -1
+        assert L.lame_set_copyright(h, 1) == 0 and L.lame_get_copyright(h) == 1
+        assert getattr(L, setter)(h, value) == 0
+        assert L.lame_init_params(h) == -1           # refused, loudly - never a silently different stream
+        L.lame_close(h)
+
+
+def test_whole_libmp3lame_export_list_is_present(lib):
+    """include/libmp3lame.sym of the reference (232 symbols; committed copy of the list in tests/golden/)"""
+    want = {l.strip() for l in open(os.path.join(ROOT, "tests", "golden", "libmp3lame.sym")) if l.strip()}
+    out = subprocess.run(["nm", "-D", "--defined-only", lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines()}
+    assert len(want) == 232 and not (want - exported), sorted(want - exported)
 
 
 def test_signatures_bind(lib):

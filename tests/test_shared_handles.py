@@ -1,0 +1,52 @@
+"""Handles of the libmp3lame face are lanes of one shared batch engine: application threads that each drive
+their own lame_t concurrently - the reference's threading contract, HACKING:67-76 - share GPU launches.  tests/c/handles_mt.cpp runs
+T threads x (lame_init .. lame_encode_buffer in small calls .. lame_encode_flush .. lame_close) and compares every stream byte for
+byte with the same calls made to the reference library."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from conftest import ROOT
+
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libmp3lame_ref.so")
+
+
+@pytest.fixture(scope="module")
+def mt_emu(oracle_mod, tmp_path_factory):
+    if not os.path.exists(REF_SO):
+        pytest.skip("needs the reference build (oracle/_ref)")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu")], check=True, capture_output=True)
+    exe = str(tmp_path_factory.mktemp("bin") / "handles_mt_emu")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-w", os.path.join(ROOT, "tests", "c", "handles_mt.cpp"), "-o", exe, "-L" + os.path.join(ROOT, "tests", "emu"),
+                    "-llamegpu_emu", "-ldl", "-lpthread", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "tests", "emu")], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("args,lanes", [("6 4 1152 128", 8), ("5 4 700 112 {ref} 3 4", 2)])
+def test_threads_with_own_handles_share_an_engine_emulated(mt_emu, args, lanes):
+    """more threads than lanes too: a second engine of the same configuration is made for the overflow"""
+    a = args.format(ref=REF_SO).split()
+    if len(a) == 4:
+        a.append(REF_SO)
+    r = subprocess.run([mt_emu] + a, capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, LAMEGPU_LANES=str(lanes)))
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads,frames,chunk,floor", [(512, 96, 1152, 8.0e4), (512, 96, 2304, 1.2e5), (64, 24, 4608, 0.0), (300, 16, 1000, 0.0)])
+def test_512_threads_with_own_handles_on_the_gpu(threads, frames, chunk, floor):
+    """512 threads x own lame_t x 1152-sample lame_encode_buffer calls: byte-identical per stream, and - the point of sharing the engine -
+    an aggregate rate that one engine per handle cannot reach (round 1: 1.6e3 frames/s per handle = 8e5 only if 512 GPUs' worth of
+    engines could run side by side; measured here on a 16-core box: 1.3e5 frames/s with one-frame calls, 2.0e5 with two-frame calls -
+    every call of every thread is a full device round trip, about 1 ms, and 512 blocked threads have to be woken per round)"""
+    exe = os.path.join(ROOT, "tests", "c", "bin", "handles_mt")
+    if not (os.path.exists(exe) and os.path.exists(REF_SO)):
+        pytest.skip("tests/c/bin/handles_mt and oracle/_ref travel with the repository snapshot; not built here")
+    r = subprocess.run([exe, str(threads), str(frames), str(chunk), "128", REF_SO], capture_output=True, text=True, cwd=ROOT, timeout=900,
+                       env=dict(os.environ, LAMEGPU_LANES="512"))
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
+    rate = float(re.search(r"= (\d+) frames/s", r.stdout).group(1))
+    print(r.stdout.strip())
+    assert rate >= floor, "aggregate %.0f frames/s" % rate

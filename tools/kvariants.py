@@ -12,7 +12,7 @@ for spec in sys.argv[1:]:
     tag, _, flags = spec.partition(":")
     o = os.path.join(out, "eng_%s.o" % tag)
     subprocess.run(["nvcc"] + B.NVCC_FLAGS + flags.split() + ["-c", os.path.join(B.CSRC, "lg_engine.cu"), "-o", o], check=True)
-    objs = [o] + [os.path.join(B.OBJ, n + ".o") for n in ("lg_setup", "lg_bitstream", "lg_api")]
+    objs = [o] + [os.path.join(B.OBJ, n + ".o") for n in ("lg_setup", "lg_bitstream", "lg_api", "lg_api_stubs")]
     so = os.path.join(out, "lib_%s.so" % tag)
     subprocess.run(["nvcc", "-shared", "-o", so] + objs + ["-lpthread"], check=True, stderr=subprocess.DEVNULL)
     os.remove(o)
