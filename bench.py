@@ -267,7 +267,14 @@ def main():
     # the global job is world*S independent streams; this rank owns a contiguous shard of them
     lo, hi = shard_range(world * S, rank, world)
     assert hi - lo == S
-    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=local, vbr=VBR)
+    # `python bench.py --gpus N` without torchrun: ONE process drives N GPUs through the library itself (device = -1: the batch spans the
+    # devices, one engine and one host thread per device); under torchrun every rank has its own GPU
+    ngpu_here = args.gpus if (world == 1 and args.gpus > 1) else 1
+    dev = local
+    if ngpu_here > 1:
+        os.environ["LAMEGPU_DEVICES"] = str(ngpu_here)
+        dev, S = -1, S * ngpu_here
+    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=dev, vbr=VBR)
     pcm = noise_pcm(S, nsamp + 224, 1000 + rank)            # +224: the first launch needs 1152*F + 224 user samples
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -303,12 +310,12 @@ def main():
 
     # ---------------- e2e: public API, host buffers in, MP3 bytes out
     enc.close()
-    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=local, vbr=VBR)
+    enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=dev, vbr=VBR)
     # The batch is pipelined: a call stages its PCM from the caller's buffers into pinned memory and submits the step; while the device
     # encodes it, the previous step's bytes are spliced and handed over.  That host work is memcpy-class and hidden under the device
     # step, so a few host threads per rank do (round 1 needed 16 and lost 15 % at eight ranks on 32 cores).
     cores = os.cpu_count() or 1
-    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    local_world = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))) * ngpu_here
     host_threads = int(os.environ.get("LAMEGPU_THREADS", max(2, min(4, cores // local_world))))
     enc.set_threads(host_threads)
     enc.set_pipelined(True)
@@ -335,7 +342,7 @@ def main():
     log('e2e done %.1f ms' % e2e_ms)
     e2e_frames_all, e2e_ms_max = reduce_over_ranks(float(e2e_frames), e2e_ms)
     lib = lame_b200.load_library()
-    h2d = S * 2 * (F * 1152 + 1328) * 2 + S * 4
+    h2d = S * 2 * (F * 1152 + 1328) * 2 + S * 4             # all devices of this process
     d2h = int(lib.lamegpu_batch_d2h_bytes(enc._h))
     enc.close()
 
@@ -343,6 +350,7 @@ def main():
         peak, peak_src = measured_hbm_peak()
         q_ms = kms[3] / args.steps
         qname = {4: "lg_kernel_vbr", 2: "lg_kernel_vbrold"}.get(VBR, "lg_kernel_quantg" if (QUALITY < 0 or 3 <= QUALITY <= 6) and S <= 592 else "lg_kernel_quant")
+        S //= ngpu_here                                       # per GPU from here on: the kernel figures are one device's
         headline = (S, F, SIGNAL, BRATE, VBR, QUALITY) == (512, 8, "noise", 128, 0, -1)
         achieved = ALG_BYTES_QUANT * S * F / (q_ms * 1e-3) / 1e9
         a_ms = (kms[0] + kms[1] + kms[2]) / args.steps
@@ -362,12 +370,12 @@ def main():
                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/)",
                "algorithmic_bytes_per_launch": ALG_BYTES_QUANT * S * F, "avg_launch_ms": q_ms}
         line = {
-            "metric": "mp3_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": "mp3_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world * ngpu_here, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": bench_config(S, F),
-            "notes": {"l2": "no explicit flush: steps run back to back on persistent streams; a step touches ~215 MB (two alternating buffer sets) > 126 MB L2",
-                      "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % world,
+            "config": bench_config(S // ngpu_here, F),
+            "notes": {"process_model": "one process per GPU (torchrun)" if ngpu_here == 1 else "one process, %d GPUs through lamegpu_batch_open(device = -1)" % ngpu_here,"l2": "no explicit flush: steps run back to back on persistent streams; a step touches ~215 MB (two alternating buffer sets) > 126 MB L2",
+                      "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % (world * ngpu_here),
                       "value": "K pipelined steps on persistent streams, first kernel start to last kernel end (CUDA events) / K"},
             "e2e": {"value": e2e_frames_all / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes": total_bytes,

@@ -87,6 +87,7 @@ def load_library(path=None):
         "lamegpu_batch_rerun_device": (c_int, [c_void_p, c_int]),
         "lamegpu_batch_run_device_steps": (ctypes.c_float, [c_void_p, c_int, c_int]),
         "lamegpu_batch_set_pipelined": (c_int, [c_void_p, c_int]),
+        "lamegpu_batch_devices": (c_int, [c_void_p]),
         "lamegpu_batch_stage_packed": (c_int, [c_void_p, c_void_p, c_int]),
         "lamegpu_batch_kernel_ms": (c_int, [c_void_p, P(ctypes.c_float)]),
         "lamegpu_batch_step_ms": (ctypes.c_float, [c_void_p]),

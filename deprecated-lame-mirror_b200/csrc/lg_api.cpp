@@ -243,6 +243,21 @@ private:
 } // namespace
 
 struct lamegpu_batch {
+    /* device = -1 with several GPUs visible: the batch is a set of parts, one engine per device, each with a contiguous share of the
+     * streams; every call fans out to the parts on one host thread per device (streams are independent: no exchange between parts) */
+    std::vector<lamegpu_batch *> parts;
+    std::vector<int> part_first;
+    template <class Fn> long fan_out(const Fn &fn)      /* fn(part index) -> long; returns the sum, or the first negative result */
+    {
+        std::vector<long> r(parts.size(), 0);
+        std::vector<std::thread> th;
+        for (size_t p = 1; p < parts.size(); p++) th.emplace_back([&, p]() { r[p] = fn((int) p); });
+        r[0] = fn(0);
+        for (auto &t : th) t.join();
+        long sum = 0;
+        for (long v : r) { if (v < 0) return v; sum += v; }
+        return sum;
+    }
     LgDevCfg cfg;
     lg_engine *eng = nullptr;
     int S = 0, F = 0, nthreads = 1;
@@ -629,6 +644,23 @@ lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int 
 {
     int const brate = (int) rate;
     float const vbr_q_frac = (vbr == 4 || vbr == 2) ? rate - (float) brate : 0.f;
+    if (device < 0) {
+        /* all visible GPUs (LAMEGPU_DEVICES limits their number): stream s goes to part s * n / nstreams */
+        int n = lg_device_count();
+        if (const char *e = getenv("LAMEGPU_DEVICES")) n = std::min(n, std::max(1, atoi(e)));
+        if (n > nstreams) n = nstreams;
+        if (n <= 1) return lamegpu_batch_open_vq(samplerate_in, samplerate_out, channels, rate, mode, quality, vbr, nstreams, frames_per_launch, 0);
+        lamegpu_batch *c = new (std::nothrow) lamegpu_batch;
+        if (!c) return NULL;
+        for (int d = 0; d < n; d++) {
+            int const lo = (int) ((long) nstreams * d / n), hi = (int) ((long) nstreams * (d + 1) / n);
+            lamegpu_batch *p = lamegpu_batch_open_vq(samplerate_in, samplerate_out, channels, rate, mode, quality, vbr, hi - lo, frames_per_launch, d);
+            if (!p) { for (auto *q : c->parts) lamegpu_batch_close(q); delete c; return NULL; }
+            c->parts.push_back(p); c->part_first.push_back(lo);
+        }
+        c->cfg = c->parts[0]->cfg; c->S = nstreams; c->F = frames_per_launch; c->nthreads = c->parts[0]->nthreads;
+        return c;
+    }
     lamegpu_batch *b = new (std::nothrow) lamegpu_batch;
     if (!b) return NULL;
     LgSetupOpt defaults;
@@ -673,16 +705,28 @@ lamegpu_batch *lamegpu_batch_open(int samplerate, int channels, int brate, int m
 void lamegpu_batch_close(lamegpu_batch *b)
 {
     if (!b) return;
+    if (!b->parts.empty()) { for (auto *p : b->parts) lamegpu_batch_close(p); delete b; return; }
     lg_engine_destroy(b->eng);
     delete b;
 }
 
-int lamegpu_batch_set_threads(lamegpu_batch *b, int n) { if (!b || n < 1) return -1; b->nthreads = n; return 0; }
+int lamegpu_batch_set_threads(lamegpu_batch *b, int n)
+{
+    if (!b || n < 1) return -1;
+    for (auto *p : b->parts) p->nthreads = n;
+    b->nthreads = n;
+    return 0;
+}
 
 long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const short *const *pcm_r, const int *nsamples,
                           unsigned char *const *out, const int *out_cap, int *out_bytes)
 {
     if (!b) return -3;
+    if (!b->parts.empty())
+        return b->fan_out([&](int p) {
+            int const f = b->part_first[p];
+            return lamegpu_batch_encode(b->parts[p], pcm_l + f, pcm_r ? pcm_r + f : NULL, nsamples + f, out ? out + f : NULL, out_cap ? out_cap + f : NULL, out_bytes + f);
+        });
     b->parallel_for(b->S, [&](int s) { b->feed16(s, pcm_l[s], pcm_r ? pcm_r[s] : NULL, nsamples[s]); });
     long const done = b->pump();
     b->end_call();
@@ -694,6 +738,8 @@ long lamegpu_batch_encode(lamegpu_batch *b, const short *const *pcm_l, const sho
 long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int *out_cap, int *out_bytes)
 {
     if (!b) return -3;
+    if (!b->parts.empty())
+        return b->fan_out([&](int p) { int const f = b->part_first[p]; return lamegpu_batch_flush(b->parts[p], out ? out + f : NULL, out_cap ? out_cap + f : NULL, out_bytes + f); });
     std::vector<char> live(b->S);
     for (int s = 0; s < b->S; s++) {
         live[s] = b->st[s].mf_samples_to_encode >= 1;         /* lame.c:2067: "was flush already called?" */
@@ -710,6 +756,11 @@ long lamegpu_batch_flush(lamegpu_batch *b, unsigned char *const *out, const int 
 long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsamples, unsigned char *out, int out_stride, int *out_bytes)
 {
     if (!b) return -3;
+    if (!b->parts.empty())
+        return b->fan_out([&](int p) {
+            size_t const f = (size_t) b->part_first[p];
+            return lamegpu_batch_encode_packed(b->parts[p], pcm + f * 2 * (size_t) nsamples, nsamples, out + f * (size_t) out_stride, out_stride, out_bytes + f);
+        });
     double const t0 = now_ms();
     b->parallel_for(b->S, [&](int s) { b->feed16(s, pcm + ((size_t) s * 2) * nsamples, pcm + ((size_t) s * 2 + 1) * nsamples, nsamples); });
     double const t1 = now_ms();
@@ -725,6 +776,8 @@ long lamegpu_batch_encode_packed(lamegpu_batch *b, const short *pcm, int nsample
 long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_stride, int *out_bytes)
 {
     if (!b) return -3;
+    if (!b->parts.empty())
+        return b->fan_out([&](int p) { size_t const f = (size_t) b->part_first[p]; return lamegpu_batch_flush_packed(b->parts[p], out + f * (size_t) out_stride, out_stride, out_bytes + f); });
     std::vector<unsigned char *> po(b->S);
     std::vector<int> cap(b->S, out_stride);
     for (int s = 0; s < b->S; s++) po[s] = out + (size_t) s * out_stride;
@@ -734,6 +787,7 @@ long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_st
 int lamegpu_batch_set_pipelined(lamegpu_batch *b, int on)
 {
     if (!b) return -1;
+    if (!b->parts.empty()) return (int) b->fan_out([&](int p) { return (long) lamegpu_batch_set_pipelined(b->parts[p], on); });
     if (!on && b->drain() != 0) return -2;
     b->pipelined = on != 0;
     return 0;
@@ -745,6 +799,10 @@ int lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes)
     /* lay `nframes` frames of every stream (from a fresh stream start) into both slots' pinned staging buffers and run one full step
      * on each, so that the device buffers hold inputs; used to measure the device pipeline with inputs resident in HBM */
     if (!b || nframes < 1 || nframes > b->F) return -1;
+    if (!b->parts.empty()) {
+        size_t const per_stream = 2 * ((size_t) nframes * b->parts[0]->st[0].fs + LG_PCM_HALO - LG_PCM_HIST - 528);
+        return (int) b->fan_out([&](int p) { return (long) lamegpu_batch_stage_packed(b->parts[p], pcm + (size_t) b->part_first[p] * per_stream, nframes); });
+    }
     if (b->drain() != 0) return -1;
     size_t const stride = lg_engine_pcm_stride(b->eng);
     size_t const nsamp = (size_t) nframes * b->st[0].fs + LG_PCM_HALO - LG_PCM_HIST - 528;   /* user samples consumed */
@@ -769,6 +827,13 @@ int lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes)
 float lamegpu_batch_run_device_steps(lamegpu_batch *b, int nframes, int steps)
 {
     if (!b || steps < 1) return -1.f;
+    if (!b->parts.empty()) {                                  /* all devices at once; the slowest one's time per step */
+        std::vector<float> ms(b->parts.size(), 0.f);
+        b->fan_out([&](int p) { ms[p] = lamegpu_batch_run_device_steps(b->parts[p], nframes, steps); return 0L; });
+        float worst = 0.f;
+        for (float v : ms) { if (v < 0.f) return v; worst = std::max(worst, v); }
+        return worst;
+    }
     if (b->drain() != 0) return -1.f;
     for (int i = 0; i < 5; i++) b->acc_ms[i] = 0;
     b->acc_n = 0;
@@ -794,6 +859,7 @@ float lamegpu_batch_run_device_steps(lamegpu_batch *b, int nframes, int steps)
 int lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes)
 {
     if (!b) return -1;
+    if (!b->parts.empty()) return (int) b->fan_out([&](int p) { return (long) lamegpu_batch_rerun_device(b->parts[p], nframes); });
     if (b->drain() != 0) return -1;
     if (lg_engine_reset_streams(b->eng, 0, b->S) != 0) return -1;
     if (lg_engine_run_device(b->eng, 0, nframes, 0) != 0) return -1;
@@ -803,20 +869,34 @@ int lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes)
 int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5])
 {
     if (!b) return -1;
+    if (!b->parts.empty()) return lamegpu_batch_kernel_ms(b->parts[0], ms);
     if (b->acc_n > 0) { for (int i = 0; i < 5; i++) ms[i] = (float) (b->acc_ms[i] / b->acc_n); return 0; }   /* mean over the last run of device steps */
     const float *m = lg_engine_last_kernel_ms(b->eng);
     for (int i = 0; i < 5; i++) ms[i] = m[i];
     return 0;
 }
 /* device time of the last launch from the start of its first kernel to the end of its last (the pieces' kernels overlap) */
-float lamegpu_batch_step_ms(const lamegpu_batch *b) { return b ? lg_engine_last_kernel_ms(b->eng)[7] : 0.f; }
-long lamegpu_batch_kernel_launches(const lamegpu_batch *b) { return b ? lg_engine_launch_count(b->eng) : 0; }
-long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap) { return b ? lg_engine_debug_copy(b->eng, what, dst, cap) : -1; }
+float lamegpu_batch_step_ms(const lamegpu_batch *b) { return !b ? 0.f : (b->parts.empty() ? lg_engine_last_kernel_ms(b->eng)[7] : lamegpu_batch_step_ms(b->parts[0])); }
+long lamegpu_batch_kernel_launches(const lamegpu_batch *b)
+{
+    if (!b) return 0;
+    if (b->parts.empty()) return lg_engine_launch_count(b->eng);
+    long n = 0;
+    for (auto *p : b->parts) n += lamegpu_batch_kernel_launches(p);
+    return n;
+}
+long lamegpu_batch_debug_copy(lamegpu_batch *b, int what, void *dst, size_t cap)
+{
+    if (!b) return -1;
+    return lg_engine_debug_copy(b->parts.empty() ? b->eng : b->parts[0]->eng, what, dst, cap);
+}
+int lamegpu_batch_devices(const lamegpu_batch *b) { return !b ? 0 : (b->parts.empty() ? 1 : (int) b->parts.size()); }
 size_t lamegpu_sizeof_granule_out(void) { return sizeof(LgGranuleOut); }
 /* bytes one launch copies device -> host: frame records, payload bytes, headers */
 long lamegpu_batch_d2h_bytes(const lamegpu_batch *b)
 {
     if (!b) return 0;
+    if (!b->parts.empty()) { long n = 0; for (auto *p : b->parts) n += lamegpu_batch_d2h_bytes(p); return n; }
     return (long) ((size_t) b->S * b->F * sizeof(LgFrameOut) + (size_t) b->S * lg_engine_pay_stride(b->eng) + (size_t) b->S * b->F * LG_HDR_STRIDE);
 }
 size_t lamegpu_sizeof_analysis(void) { return sizeof(LgAnalysis); }

@@ -228,6 +228,18 @@ extern "C" int lg_engine_end_reservoir(lg_engine *e, const int *streams, const i
     return 0;
 }
 
+extern "C" int lg_device_count(void)
+{
+#ifdef LG_EMULATE
+    int n = 1;
+    if (const char *e = getenv("LAMEGPU_EMU_DEVICES")) n = atoi(e);      /* tests: several emulated "devices" */
+    return n;
+#else
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+#endif
+}
+
 extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device)
 {
     if (nstreams < 1 || max_frames < 1) return NULL;

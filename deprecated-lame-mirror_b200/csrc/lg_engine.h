@@ -42,6 +42,7 @@ int lg_setup(LgDevCfg *c, int samplerate_in, int samplerate_out /* 0 = as lame_i
 float lg_abr_preset_scale(int kbps);
 int lg_table_bitrate(int version, int index);
 int lg_table_samplerate(int version, int index);
+int lg_device_count(void);
 lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, int device);
 void lg_engine_destroy(lg_engine *e);
 int  lg_engine_reset_streams(lg_engine *e, int first, int count);

@@ -173,6 +173,10 @@ lamegpu_batch *lamegpu_batch_open_rs(int samplerate_in, int samplerate_out, int 
 lamegpu_batch *lamegpu_batch_open_vq(int samplerate_in, int samplerate_out, int channels, float rate, int mode, int quality,
                                      int vbr, int nstreams, int frames_per_launch, int device);
 void lamegpu_batch_close(lamegpu_batch *b);
+/* device = -1 in any lamegpu_batch_open*: the batch spans ALL visible GPUs of the process (LAMEGPU_DEVICES limits their number) - stream s
+ * lives on device s * n / nstreams, one engine and one host thread per device, no exchange between devices (streams are independent,
+ * SURVEY.md section 8e).  Every lamegpu_batch_* call then works on all devices at once.  Returns the number of devices of the batch. */
+int  lamegpu_batch_devices(const lamegpu_batch *b);
 
 /* Feed nsamples[i] samples to stream i (pcm_l[i]/pcm_r[i]; pcm_r may be NULL for mono) and encode every
  * frame that became complete.  Bytes produced for stream i are appended at out[i] (capacity out_cap[i]);

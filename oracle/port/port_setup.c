@@ -624,12 +624,13 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
     /* presets.c:99 vbr_mt_psy_switch_map: st_lrm, st_s, masking_adj (long = short but rows 6), ath_lower, ath_curve, ath_sensitivity,
      * interch, safejoint, sfb21mod, msfix, minval, ath_fixpoint; expY = (q >= 3) */
     static const struct { float st_lrm, st_s, madj, madj_s, ath_lower, ath_curve, ath_sens, interch; int safejoint, sfb21mod; float msfix, minval, ath_fixpoint; }
-    vm[10] = {
+    vm[11] = {
         {4.20, 25.0, -6.8, -6.8, 7.1, 1, 0, 0, 2, 31, 1.000, 5, 100}, {4.20, 25.0, -4.8, -4.8, 5.4, 1.4, -1, 0, 2, 27, 1.122, 5, 98},
         {4.20, 25.0, -2.6, -2.6, 3.7, 2.0, -3, 0, 2, 23, 1.288, 5, 97}, {4.20, 25.0, -1.6, -1.6, 2.0, 2.0, -5, 0, 2, 18, 1.479, 5, 96},
         {4.20, 25.0, -0.0, -0.0, 0.0, 2.0, -8, 0, 2, 12, 1.698, 5, 95}, {4.20, 25.0, 1.3, 1.3, -6, 3.5, -11, 0, 2, 8, 1.950, 5, 94.2},
         {4.50, 100.0, 2.2, 2.3, -12.0, 6.0, -14, 0, 2, 4, 2.239, 3, 93.9}, {4.80, 200.0, 2.7, 2.7, -18.0, 9.0, -17, 0, 2, 0, 2.570, 1, 93.6},
-        {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3} },
+        {5.30, 300.0, 2.8, 2.8, -21.0, 10.0, -23, 0.0002, 0, 0, 2.951, 0, 93.3}, {6.60, 300.0, 2.8, 2.8, -23.0, 11.0, -25, 0.0006, 0, 0, 3.388, 0, 93.3},
+        {25.00, 300.0, 2.8, 2.8, -25.0, 12.0, -27, 0.0025, 0, 0, 3.500, 0, 93.3} },                 /* level 10: what level 9 interpolates towards (presets.c:124) */
     /* presets.c:88 vbr_old_switch_map (vbr_rh), same columns, levels 0..10 */
     vo[11] = {
         {5.20, 125.0, -4.2, -6.3, 4.8, 1, 0, 0, 2, 21, 0.97, 5, 100}, {5.30, 125.0, -3.6, -5.6, 4.5, 1.5, 0, 0, 2, 21, 1.35, 5, 100},
@@ -801,7 +802,6 @@ int lp_setup(lp_config *c, int samplerate_in, int samplerate_out, int channels, 
             int const n = vbr_q + 1;
 #define VP(i) (vbr == 4 ? vm[i] : vo[i])
             int sfb21mod = VP(vbr_q).sfb21mod;
-            if (vbr == 4 && vbr_q > 8) return -1;                       /* the table row of level 10 is not carried for vbr_mtrh (never reached: -V9 is remapped) */
 #define VLERP(f) (VP(vbr_q).f + x * (VP(n).f - VP(vbr_q).f))
             attackthre = VLERP(st_lrm);
             attackthre_s = VLERP(st_s);

@@ -35,7 +35,9 @@ int main(int argc, char **argv)
     int const vbr = getenv("LP_VBR") ? atoi(getenv("LP_VBR")) : 0;          /* 0 = CBR, 3 = ABR with mean bitrate `brate` */
     int const out_sr = getenv("LP_OUT_SR") ? atoi(getenv("LP_OUT_SR")) : 0; /* explicit output rate, 0 = automatic (resampling when it differs from sr) */
     float const qfrac = getenv("LP_VBRQ_FRAC") ? (float) atof(getenv("LP_VBRQ_FRAC")) : 0.f;  /* VBR quality = brate + this */
-    b = lamegpu_batch_open_vq(sr, out_sr, 2, (float) brate + qfrac, mode, quality, vbr, S, FPL, 0);
+    int const device = getenv("LP_DEVICE") ? atoi(getenv("LP_DEVICE")) : 0;  /* -1 = the batch spans all visible devices */
+    b = lamegpu_batch_open_vq(sr, out_sr, 2, (float) brate + qfrac, mode, quality, vbr, S, FPL, device);
+    if (b && device < 0) printf("batch spans %d device(s)\n", lamegpu_batch_devices(b));
     if (b && getenv("LP_PIPELINED")) lamegpu_batch_set_pipelined(b, 1);      /* bytes lag one step behind; the flush brings everything out */
     if (!b) { printf("batch open failed\n"); return 2; }
     for (i = 0; i < n; i += chunk) {

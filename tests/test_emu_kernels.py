@@ -147,3 +147,20 @@ def test_emulated_sample_type_entry_points(emu_bin, oracle_mod):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sample_types_check.py"), os.path.join(ROOT, "tests", "emu", "liblamegpu_emu.so")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "SAMPLE TYPES IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("args,env", [("5 12 4 128 -1 -1 44100 1152", dict(LAMEGPU_EMU_DEVICES="3")),
+                                      ("4 10 4 2 -1 -1 44100 777", dict(LAMEGPU_EMU_DEVICES="2", LP_VBR="4", LP_PIPELINED="1"))])
+def test_batch_spanning_several_devices(emu_bin, args, env):
+    """lamegpu_batch_open(device = -1): one engine and one host thread per device, contiguous shares of the streams (here: emulated devices)"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, LP_DEVICE="-1", **env))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout and "batch spans %s device(s)" % env["LAMEGPU_EMU_DEVICES"] in r.stdout
+
+
+@pytest.mark.parametrize("args", ["4 24 8 128 -1 -1 44100 1152", "3 16 3 192 0 5 48000 777"])
+def test_pipelined_batch_matches_port(emu_bin, args):
+    """lamegpu_batch_set_pipelined: the newest step stays in flight between calls, its bytes come out of the next call or the flush"""
+    r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, LP_PIPELINED="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "IDENTICAL" in r.stdout

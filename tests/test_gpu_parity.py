@@ -498,3 +498,171 @@ def test_device_libm_restatements_match_host_libm(lib):
     x = np.concatenate([np.full(n, 10.0), rng.uniform(0.001, 1000, n)])
     want = np.array([math.pow(a, b) for a, b in zip(x, y)], np.float64)
     assert np.array_equal(device(3, x, y).view(np.uint64), want.view(np.uint64))
+
+
+# ---------------------------------------------------------------- round 2
+def reference_all(oracle_mod, pcm, **kw):
+    """the reference on every stream of `pcm` [S][2][n], on all host cores (ctypes releases the GIL inside libmp3lame)"""
+    from concurrent.futures import ThreadPoolExecutor
+    Enc = oracle_mod.RefEncoder if oracle_mod.have_ref() else oracle_mod.PortEncoder
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        return list(pool.map(lambda s: Enc(**kw).encode_all(pcm[s, 0], pcm[s, 1]), range(pcm.shape[0])))
+
+
+def tones(S, n, seed):
+    t = np.arange(n) / 44100.0
+    base = np.stack([8000 * np.sin(2 * np.pi * 440 * t) + 4000 * np.sin(2 * np.pi * 3300 * t), 8000 * np.sin(2 * np.pi * 554.37 * t) + 3000 * np.sin(2 * np.pi * 7000 * t)])
+    rng = np.random.default_rng(seed)
+    out = np.empty((S, 2, n), dtype=np.int16)
+    for s0 in range(0, S, 256):
+        s1 = min(S, s0 + 256)
+        out[s0:s1] = np.rint(rng.integers(-1000, 1001, size=(s1 - s0, 2, n)) + base[None])
+    return out
+
+
+def test_config1_every_stream_byte_exact(lib, oracle_mod):
+    """BASELINE configs[1] (512 streams x 8 frames, white noise, CBR 128): EVERY stream against the reference, two calls + flush, pipelined"""
+    S, F = 512, 8
+    rng = np.random.default_rng(4321)
+    pcm = rng.integers(-12000, 12001, size=(S, 2, 2 * F * 1152), dtype=np.int16)
+    enc = lib.BatchEncoder(S, frames_per_launch=F)
+    enc.set_pipelined(True)
+    _, a = enc.encode(pcm[:, :, :F * 1152])
+    _, b = enc.encode(pcm[:, :, F * 1152:])
+    _, c = enc.flush()
+    enc.close()
+    want = reference_all(oracle_mod, pcm, samplerate=44100, channels=2, brate=128)
+    bad = [s for s in range(S) if a[s] + b[s] + c[s] != want[s]]
+    assert not bad, bad[:8]
+
+
+def test_config3_vbr_v2_262144_frames_every_stream_byte_exact(lib, oracle_mod):
+    """BASELINE configs[3] at its stated size: 262 144 frames = 4096 streams x 64 frames, VBR -V2 (vbr_mtrh), the tone + noise mix; every stream
+    byte for byte against the reference - exact, not tolerance-matched"""
+    S, F = 4096, 64
+    pcm = tones(S, F * 1152, 31)
+    enc = lib.BatchEncoder(S, 44100, 2, 2, -1, -1, frames_per_launch=F, vbr=lib.VBR_MTRH)
+    n1, a = enc.encode(pcm)
+    n2, b = enc.flush()
+    enc.close()
+    assert n1 + n2 == S * (F + 1)
+    want = reference_all(oracle_mod, pcm, samplerate=44100, channels=2, brate=2, vbr=4)
+    bad = [s for s in range(S) if a[s] + b[s] != want[s]]
+    assert not bad, (len(bad), bad[:8])
+
+
+def test_config2_every_stream_byte_exact(lib, oracle_mod):
+    """BASELINE configs[2]: 65 536 frames = 2048 streams x 32 frames, CBR 320 joint stereo; every stream against the reference"""
+    S, F = 2048, 32
+    pcm = tones(S, F * 1152, 77)
+    enc = lib.BatchEncoder(S, 44100, 2, 320, 1, -1, frames_per_launch=F)
+    _, a = enc.encode(pcm)
+    _, b = enc.flush()
+    enc.close()
+    want = reference_all(oracle_mod, pcm, samplerate=44100, channels=2, brate=320, mode=1)
+    bad = [s for s in range(S) if a[s] + b[s] != want[s]]
+    assert not bad, (len(bad), bad[:8])
+
+
+def test_testcase_wav_full_length_with_tag(lib, oracle_mod):
+    """configs[0]: all 25 000 samples of the reference's testcase.wav through the libmp3lame face with the Info tag (the file `lame -b 128` writes)"""
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build")
+    x = make_signal("testcase", 25000)
+    r = oracle_mod.RefEncoder(44100, 2, 128, write_tag=True)
+    want = r.encode(x[0], x[1]) + r.flush()
+    want_tag = r.lametag_frame()
+    r.close()
+    e = lib.Encoder(44100, 2, 128, write_tag=True)
+    got = b""
+    for pos in range(0, 25000, 1152):
+        got += e.encode(x[0, pos:pos + 1152], x[1, pos:pos + 1152])
+    got += e.flush()
+    tag = e.lametag_frame()
+    e.close()
+    assert got == want and tag == want_tag and len(got) == 10030
+
+
+@pytest.mark.parametrize("kw", [dict(brate=128), dict(brate=320, mode=1), dict(brate=2, vbr=4), dict(brate=128, vbr=3), dict(brate=64)])
+def test_encoding_continues_after_a_flush(lib, oracle_mod, kw):
+    """lame_encode_flush ends the bit reservoir (flush_bitstream, bitstream.c:886-889: ResvSize = 0, main_data_begin = 0) - on the device too:
+    samples fed after a flush are encoded as the reference encodes them (advisor finding of round 1: main_data_begin went stale)"""
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build")
+    x = make_signal("click", 40 * 1152, seed=11)
+    cut = 17 * 1152 + 300
+    r = oracle_mod.RefEncoder(44100, 2, **kw)
+    want = r.encode(x[0, :cut], x[1, :cut]) + r.flush() + r.encode(x[0, cut:], x[1, cut:]) + r.flush()
+    r.close()
+    e = lib.Encoder(44100, 2, kw["brate"], vbr=kw.get("vbr", 0), mode=kw.get("mode", -1))
+    got = e.encode(x[0, :cut], x[1, :cut]) + e.flush() + e.encode(x[0, cut:], x[1, cut:]) + e.flush()
+    e.close()
+    assert got == want
+    S = 6
+    pcm = np.stack([make_signal(("click", "noise", "gap")[s % 3], 40 * 1152, seed=20 + s) for s in range(S)])
+    b = lib.BatchEncoder(S, 44100, 2, kw["brate"], kw.get("mode", -1), -1, frames_per_launch=5, vbr=kw.get("vbr", 0))
+    _, p1 = b.encode(pcm[:, :, :cut]); _, p2 = b.flush(); _, p3 = b.encode(pcm[:, :, cut:]); _, p4 = b.flush()
+    b.close()
+    for s in range(S):
+        r = oracle_mod.RefEncoder(44100, 2, **kw)
+        w = r.encode(pcm[s, 0, :cut], pcm[s, 1, :cut]) + r.flush() + r.encode(pcm[s, 0, cut:], pcm[s, 1, cut:]) + r.flush()
+        r.close()
+        assert p1[s] + p2[s] + p3[s] + p4[s] == w, s
+
+
+def test_vbr_level_9_with_explicit_output_rate(lib, oracle_mod):
+    """VBR-new level 9 kept at 44.1 kHz by lame_set_out_samplerate: the preset interpolates towards row 10 of vbr_mt_psy_switch_map (presets.c:124)"""
+    if not oracle_mod.have_ref():
+        pytest.skip("needs the reference build")
+    x = make_signal("click", 20 * 1152, seed=5)
+    for q in (9, 8.5):
+        want = oracle_mod.RefEncoder(44100, 2, q, vbr=4, out_samplerate=44100).encode_all(x[0], x[1])
+        enc = lib.BatchEncoder(1, 44100, 2, q, -1, -1, frames_per_launch=8, vbr=lib.VBR_MTRH, out_samplerate=44100)
+        _, a = enc.encode(x[None]); _, b = enc.flush(); enc.close()
+        assert a[0] + b[0] == want, q
+
+
+def test_engines_driven_from_other_threads_and_side_by_side(lib, oracle_mod):
+    """an engine made on one thread and used from another, and two 512-stream encoders running concurrently on one device (round 1: kernels
+    waiting inside the kernel for flags could fill the SMs; now nothing waits on the device) - every entry point selects the engine's device"""
+    import threading
+    S, F = 512, 8
+    rng = np.random.default_rng(77)
+    pcm = [rng.integers(-12000, 12001, size=(S, 2, F * 1152), dtype=np.int16) for _ in range(2)]
+    encs = [lib.BatchEncoder(S, frames_per_launch=F) for _ in range(2)]          # made on the main thread
+    res = [None, None]
+
+    def work(i):
+        out = [b""] * S
+        for rep in range(3):
+            _, a = encs[i].encode(pcm[i])
+            out = [o + x for o, x in zip(out, a)]
+        _, b = encs[i].flush()
+        res[i] = [o + x for o, x in zip(out, b)]
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for e in encs:
+        e.close()
+    for i in range(2):
+        assert res[i] is not None
+        for s in (0, 100, 511):
+            x = np.concatenate([pcm[i][s]] * 3, axis=1)
+            assert res[i][s] == oracle_bytes(oracle_mod, x), (i, s)
+
+
+def test_batch_over_all_visible_gpus(lib, oracle_mod):
+    """device = -1: one batch, every GPU of the process, streams in contiguous shares (needs two GPUs: gpurun --gpus 2)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("one GPU visible")
+    S, F = 64, 6
+    pcm = np.stack([make_signal(("noise", "click", "sine", "gap")[s % 4], F * 1152, seed=300 + s) for s in range(S)])
+    enc = lib.BatchEncoder(S, frames_per_launch=4, device=-1)
+    assert lib.load_library().lamegpu_batch_devices(enc._h) == torch.cuda.device_count()
+    _, a = enc.encode(pcm); _, b = enc.flush(); enc.close()
+    for s in range(S):
+        assert a[s] + b[s] == oracle_bytes(oracle_mod, pcm[s]), s
