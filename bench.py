@@ -276,6 +276,7 @@ def main():
         dev, S = -1, S * ngpu_here
     enc = lame_b200.BatchEncoder(S, 44100, 2, BRATE, -1, QUALITY, frames_per_launch=F, device=dev, vbr=VBR)
     pcm = noise_pcm(S, nsamp + 224, 1000 + rank)            # +224: the first launch needs 1152*F + 224 user samples
+    ring = noise_pcm(S, 2 * nsamp, 3000 + rank)             # a periodic signal of 2F frames per stream for the device-only steps
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier():
@@ -285,7 +286,7 @@ def main():
 
     log('engine created')
     # ---------------- value: device pipeline, inputs resident in HBM, persistent streams, steps back to back
-    enc.stage(pcm, F)                                        # H2D once + one (untimed) full step per buffer set
+    enc.stage(ring, F)                                       # H2D once + one (untimed) full step per buffer set: the two sets hold the ring's halves
     log('staged')
     sampler = ClockSampler(local)
     sampler.start()

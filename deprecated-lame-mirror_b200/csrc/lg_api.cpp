@@ -796,30 +796,43 @@ int lamegpu_batch_set_pipelined(lamegpu_batch *b, int on)
 /* bench hooks */
 int lamegpu_batch_stage_packed(lamegpu_batch *b, const short *pcm, int nframes)
 {
-    /* lay `nframes` frames of every stream (from a fresh stream start) into both slots' pinned staging buffers and run one full step
-     * on each, so that the device buffers hold inputs; used to measure the device pipeline with inputs resident in HBM */
+    /* Lay a RING of 2 x nframes frames per stream into the engine for lamegpu_batch_run_device_steps: pcm is [S][2][2 * nframes * fs] (fs =
+     * samples per frame); the window of buffer set k is the ring from sample k * nframes * fs - 576 on, nframes * fs + 1328 samples long,
+     * so that alternating the two sets walks a periodic signal without a seam - every device step then sees what a long stream sees
+     * (the first step's history is the ring's end).  One full step per buffer set brings the windows into device memory. */
     if (!b || nframes < 1 || nframes > b->F) return -1;
     if (!b->parts.empty()) {
-        size_t const per_stream = 2 * ((size_t) nframes * b->parts[0]->st[0].fs + LG_PCM_HALO - LG_PCM_HIST - 528);
+        size_t const per_stream = 2 * (2 * (size_t) nframes * b->parts[0]->st[0].fs);
         return (int) b->fan_out([&](int p) { return (long) lamegpu_batch_stage_packed(b->parts[p], pcm + (size_t) b->part_first[p] * per_stream, nframes); });
     }
     if (b->drain() != 0) return -1;
     size_t const stride = lg_engine_pcm_stride(b->eng);
-    size_t const nsamp = (size_t) nframes * b->st[0].fs + LG_PCM_HALO - LG_PCM_HIST - 528;   /* user samples consumed */
-    for (int k = 0; k < lg_engine_slots(b->eng); k++) {
+    long const n = (long) nframes * b->st[0].fs, ring = 2 * n;
+    /* four staging steps: set 0 with silence for everything the first granule's analysis treats as "the granule before" (a stream's true
+     * start, which is what the fresh state stands for: the psycho-acoustic analysis runs 701 samples ahead of the frame, so that is the
+     * history plus the first 722 samples), set 1, then set 0 again with the ring's end for history and set 1 once more - from here on the
+     * state and the windows belong to one long stream */
+    for (int pass = 0; pass < 2 * lg_engine_slots(b->eng); pass++) {
+        int const k = pass % lg_engine_slots(b->eng);
         int16_t *hp = lg_engine_host_pcm16(b->eng, k);
         int *nfr = lg_engine_host_nfr(b->eng, k);
+        long const start = ((k & 1) * n - LG_PCM_HIST + ring) % ring;
         for (int s = 0; s < b->S; s++) {
             nfr[s] = nframes;
             for (int c = 0; c < 2; c++) {
                 int16_t *d = hp + ((size_t) s * 2 + c) * stride;
-                memset(d, 0, (LG_PCM_HIST + 528) * sizeof(int16_t));
-                memcpy(d + LG_PCM_HIST + 528, pcm + ((size_t) s * 2 + c) * nsamp, nsamp * sizeof(int16_t));
+                const short *src = pcm + ((size_t) s * 2 + c) * (size_t) ring;
+                for (long i = 0, pos = start; i < n + LG_PCM_HALO; ) {
+                    long const run = std::min<long>(ring - pos, n + LG_PCM_HALO - i);
+                    memcpy(d + i, src + pos, (size_t) run * sizeof(int16_t));
+                    i += run; pos = (pos + run) % ring;
+                }
+                if (pass == 0) memset(d, 0, (size_t) (LG_PCM_HIST + 736) * sizeof(int16_t));
             }
         }
         if (lg_engine_submit(b->eng, k, nframes, 0) != 0 || lg_engine_wait(b->eng, k) != 0) return -1;
     }
-    return lg_engine_reset_streams(b->eng, 0, b->S);
+    return 0;
 }
 /* `steps` device-only steps on the staged input, back to back on alternating slots, the streams' state carried from step to step
  * (persistent streams: no reset in between).  Returns the device time per step in ms: first kernel's start to last kernel's end over
@@ -856,15 +869,22 @@ float lamegpu_batch_run_device_steps(lamegpu_batch *b, int nframes, int steps)
     float const ms = lg_engine_marked_ms(b->eng);
     return ms < 0.f ? ms : ms / (float) steps;
 }
+/* one more pass over the staged ring: both buffer sets (so that the streams stay where a long stream would be), one step at a time -
+ * lamegpu_batch_kernel_ms then gives each kernel's time with the device to itself */
 int lamegpu_batch_rerun_device(lamegpu_batch *b, int nframes)
 {
     if (!b) return -1;
     if (!b->parts.empty()) return (int) b->fan_out([&](int p) { return (long) lamegpu_batch_rerun_device(b->parts[p], nframes); });
     if (b->drain() != 0) return -1;
-    if (lg_engine_reset_streams(b->eng, 0, b->S) != 0) return -1;
-    if (lg_engine_run_device(b->eng, 0, nframes, 0) != 0) return -1;
+    for (int i = 0; i < 5; i++) b->acc_ms[i] = 0;
     b->acc_n = 0;
-    return lg_engine_wait(b->eng, 0);
+    for (int k = 0; k < lg_engine_slots(b->eng); k++) {
+        if (lg_engine_run_device(b->eng, k, nframes, 0) != 0 || lg_engine_wait(b->eng, k) != 0) return -1;
+        const float *m = lg_engine_last_kernel_ms(b->eng);
+        for (int i = 0; i < 5; i++) b->acc_ms[i] += m[i];
+        b->acc_n++;
+    }
+    return 0;
 }
 int lamegpu_batch_kernel_ms(const lamegpu_batch *b, float ms[5])
 {

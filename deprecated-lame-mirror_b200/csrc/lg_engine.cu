@@ -103,6 +103,7 @@ struct lg_engine {
     lgStream_t stream, stream2;
     int dense;                        /* more than four streams per SM: the one-warp kernel D in its seven-CTAs-per-SM build */
     int group_nw;                     /* > 0: kernel D in its group form (lg_k_quantg.cuh) with this many warps per granule.channel */
+    int gate;                         /* kernel A of a step waits for the launch of kernel D of the step before (lg_submit) */
 #ifndef LG_EMULATE
     cudaEvent_t ev_mark[2];
 #endif
@@ -275,6 +276,8 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
         if (e->dense) e->group_nw = 0;
     }
 #endif
+    e->gate = 1;
+    if (const char *ga = getenv("LAMEGPU_GATE")) e->gate = atoi(ga) != 0;
     if (const char *ge = getenv("LAMEGPU_GROUP_NW")) e->group_nw = group_ok ? atoi(ge) : 0;
     if (e->group_nw < 0 || e->group_nw > 3 || e->group_nw == 1) e->group_nw = group_ok ? 2 : 0;
     e->pcm_stride = (size_t) max_frames * 1152 + LG_PCM_HALO;
@@ -346,6 +349,9 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     cudaFuncSetAttribute(lg_kernel_vbr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemV));
     cudaFuncSetAttribute(lg_kernel_vbrold<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
     cudaFuncSetAttribute(lg_kernel_vbrold<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemO));
+    /* The shared-memory carve-out is left to the driver.  Round 1 forced the largest one on every kernel so that a kernel could be placed
+     * next to a resident one of the other stream without reconfiguring the SM; with whole steps overlapping (not pieces waiting inside
+     * kernel D) that measures worse: 8.4 against 7.7 ms per pipelined 512 x 8 step - kernel D loses L1 for its tables. */
     if (getenv("LAMEGPU_DEBUG_OCC")) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lg_kernel_quantg<2>, 128, sizeof(LgSmemG<2>));
@@ -498,6 +504,11 @@ static int lg_submit(lg_engine *e, int k, int nframes, int use_float, int with_c
     const float *pf = use_float ? e->d_pcmf : NULL;
     int const nslot = mgr * nframes + 1;
 #ifndef LG_EMULATE
+    /* Start gate: kernel A of this step may not reach the device before kernel D of the step before it (the other slot) has been launched.
+     * Both hang on that step's kernel C; without the gate A - next in line on the analysis stream - takes the machine first and D's first
+     * wave starts late by all of A's run time, so that the overlap gains nothing (step = sum of the kernels, measured).  With it D, on the
+     * high-priority stream, fills every SM first and A runs in the room D's last, partial wave leaves (7.20 -> 6.57 ms per step at 512 x 8; LAMEGPU_GATE=0 switches it off). */
+    if (e->gate) LG_CHECK(cudaStreamWaitEvent(e->stream, e->slot[k ^ 1].ev[4], 0));
     cudaEventRecord(t.ev[0], e->stream);
 #endif
     LG_LAUNCH(lg_kernel_analysis, (int) S * nslot, 128, sizeof(LgSmemA), e->stream,

@@ -33,6 +33,8 @@ struct LgSmemA {
     float wl[2][LG_BLK];
     float ws[2][3][LG_BLK_S];
     float hpf[2][576];
+    float hpf_prev[2][384];          /* the same for the last six sub-blocks of the granule before (for the short-block decision) */
+    int   may_attack[4];
     float fe[4][520];
     float fes[4][3][132];
     float eb[4][LG_CBANDS], mx[4][LG_CBANDS], av[4][LG_CBANDS];
@@ -347,7 +349,84 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
     }
     __syncthreads();
 
-    /* phase 2 */
+    LgAnalysis *out = ana + (size_t) stream * (nslots - 1) + (slot > 0 ? slot - 1 : 0);
+    int const n_chn_psy = (cfg->mode == LG_JOINT) ? 4 : nch;
+    int has_short = 0;
+
+    /* phase 2: psymodel.c:778-795 high-pass FIR, then :831-838 sub-block peaks - and from the peaks whether this granule can switch to
+     * short blocks at all.  The FIR also runs over the last six sub-blocks of the granule before (the window holds those samples): the
+     * reference compares this granule's first peaks with sub-blocks 4..8 of that granule (last_en_subshort), and an attack it found in
+     * sub-block 5 of that granule (against sub-block 3) forces short blocks here (last_attacks == ns_attacks[2] == 3, psymodel.c:904). */
+    if (slot > 0) {
+        float const k0 = -8.65163e-18 * 2, k1 = -0.00851586 * 2, k2 = -6.74764e-18 * 2, k3 = 0.0209036 * 2,
+                    k4 = -3.36639e-17 * 2, k5 = -0.0438162 * 2, k6 = -1.54175e-17 * 2, k7 = 0.0931738 * 2,
+                    k8 = -5.52212e-17 * 2, k9 = -0.313819 * 2;
+        for (int o = tid; o < 2 * (576 + 384); o += 128) {
+            int const ch = o / (576 + 384), q = o % (576 + 384);
+            int const i = q < 576 ? q : q - 576 + 192 - 576;          /* own samples 0..575, then -384..-1 */
+            float r = 0.0f;
+            if (ch < nch) {
+                const float *x = sm->pcm[ch];
+                int const B = 304 + 576 - 350 - 21 + 192 + i;
+#define F(j) x[LG_PADIDX(B + (j))]
+                float sum1 = F(10), sum2 = 0.0f;
+                sum1 += k0 * (F(0) + F(21)); sum2 += k1 * (F(1) + F(20));
+                sum1 += k2 * (F(2) + F(19)); sum2 += k3 * (F(3) + F(18));
+                sum1 += k4 * (F(4) + F(17)); sum2 += k5 * (F(5) + F(16));
+                sum1 += k6 * (F(6) + F(15)); sum2 += k7 * (F(7) + F(14));
+                sum1 += k8 * (F(8) + F(13)); sum2 += k9 * (F(9) + F(12));
+#undef F
+                r = sum1 + sum2;
+            }
+            if (q < 576) sm->hpf[ch][q] = r; else sm->hpf_prev[ch][q - 576] = r;
+        }
+        __syncthreads();
+        if (warp < n_chn_psy) {
+            int const chn = warp;
+            float pk[15];                                             /* [0..5]: sub-blocks 3..8 of the granule before, [6..14]: this granule's nine */
+            for (int i = 0; i < 15; i++) {
+                const float *h0 = i < 6 ? &sm->hpf_prev[0][64 * i] : &sm->hpf[0][64 * (i - 6)];
+                const float *h1 = i < 6 ? &sm->hpf_prev[1][64 * i] : &sm->hpf[1][64 * (i - 6)];
+                float p = 1.f;
+                for (int k = lane; k < 64; k += 32) {
+                    float const l = h0[k], r = h1[k];
+                    float v = (chn == 0) ? l : (chn == 1) ? r : (chn == 2) ? (l + r) : (l - r);
+                    v = fabsf(v);
+                    if (p < v) p = v;
+                }
+                for (int d = 16; d > 0; d >>= 1) {
+                    float const q = __shfl_xor_sync(LG_FULL, p, d);
+                    if (p < q) p = q;
+                }
+                pk[i] = p;
+                if (lane == 0 && i >= 6) out->en_subshort[chn][i - 6] = p;
+            }
+            if (lane == 0) {
+                /* psymodel.c:822-872: attack_intensity against the threshold, before any of the rules that take attacks away again */
+                float const x = cfg->attack_threshold[chn];
+                int hit = 0;
+                for (int i = 0; i < 3; i++) hit |= (pk[i + 3] / pk[i + 1]) > x;                /* last_en_subshort[i + 6] / [i + 4] */
+                for (int i = -4; i < 9; i++) {
+                    /* i = -4: sub-block 5 of the granule before against its sub-block 3 - what that granule's ns_attacks[2] == 3 came from */
+                    if (i == -3) i = 0;
+                    float p = pk[6 + i];
+                    float const e = pk[6 + i - 2];
+                    if (p > e) p = p / e;
+                    else if (e > p * 10.0f) p = e / (p * 10.0f);
+                    else p = 0.0f;
+                    hit |= p > x;
+                }
+                sm->may_attack[chn] = hit;
+            }
+        }
+        __syncthreads();
+        for (int chn = 0; chn < n_chn_psy; chn++) has_short |= sm->may_attack[chn];
+        if (cfg->short_blocks == 3) has_short = 1;                    /* forced */
+        if (cfg->short_blocks == 2) has_short = 0;                    /* dispensed: kernel B never looks */
+        if (tid == 0) { out->has_short = has_short; out->pad_ = 0; }
+    }
+
+    /* phase 3 */
     if (warp < 2) {
         int const ch = warp;
         if (ch < nch) {
@@ -368,7 +447,7 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
                 }
             }
             __syncwarp();
-            if (slot > 0) lg_fft_short_warp(sm->ws[ch], sm->pcm[ch], 304, cfg, lane);
+            if (slot > 0 && has_short) lg_fft_short_warp(sm->ws[ch], sm->pcm[ch], 304, cfg, lane);
         }
     }
     else if (slot > 0) {
@@ -377,52 +456,6 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
     }
     if (slot == 0) return;
     __syncthreads();
-
-    LgAnalysis *out = ana + (size_t) stream * (nslots - 1) + (slot - 1);
-    int const n_chn_psy = (cfg->mode == LG_JOINT) ? 4 : nch;
-
-    /* phase 3: psymodel.c:778-795 high-pass FIR, then :831-838 sub-block peaks */
-    {
-        float const k0 = -8.65163e-18 * 2, k1 = -0.00851586 * 2, k2 = -6.74764e-18 * 2, k3 = 0.0209036 * 2,
-                    k4 = -3.36639e-17 * 2, k5 = -0.0438162 * 2, k6 = -1.54175e-17 * 2, k7 = 0.0931738 * 2,
-                    k8 = -5.52212e-17 * 2, k9 = -0.313819 * 2;
-        for (int o = tid; o < 2 * 576; o += 128) {
-            int const ch = o / 576, i = o % 576;
-            float r = 0.0f;
-            if (ch < nch) {
-                const float *x = sm->pcm[ch];
-                int const B = 304 + 576 - 350 - 21 + 192 + i;
-#define F(j) x[LG_PADIDX(B + (j))]
-                float sum1 = F(10), sum2 = 0.0f;
-                sum1 += k0 * (F(0) + F(21)); sum2 += k1 * (F(1) + F(20));
-                sum1 += k2 * (F(2) + F(19)); sum2 += k3 * (F(3) + F(18));
-                sum1 += k4 * (F(4) + F(17)); sum2 += k5 * (F(5) + F(16));
-                sum1 += k6 * (F(6) + F(15)); sum2 += k7 * (F(7) + F(14));
-                sum1 += k8 * (F(8) + F(13)); sum2 += k9 * (F(9) + F(12));
-#undef F
-                r = sum1 + sum2;
-            }
-            sm->hpf[ch][i] = r;
-        }
-    }
-    __syncthreads();
-    if (warp < n_chn_psy) {
-        int const chn = warp;
-        for (int i = 0; i < 9; i++) {
-            float p = 1.f;
-            for (int k = lane; k < 64; k += 32) {
-                float const l = sm->hpf[0][64 * i + k], r = sm->hpf[1][64 * i + k];
-                float v = (chn == 0) ? l : (chn == 1) ? r : (chn == 2) ? (l + r) : (l - r);
-                v = fabsf(v);
-                if (p < v) p = v;
-            }
-            for (int d = 16; d > 0; d >>= 1) {
-                float const q = __shfl_xor_sync(LG_FULL, p, d);
-                if (p < q) p = q;
-            }
-            if (lane == 0) out->en_subshort[chn][i] = p;
-        }
-    }
 
     /* phase 4: line energies */
     {
@@ -440,7 +473,7 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
             }
             sm->fe[chn][m] = (m == 0) ? re * re : (re * re + im * im) * 0.5f;
         }
-        for (int o = tid; o < 4 * 3 * LG_HBLK_S; o += 128) {
+        for (int o = tid; has_short && o < 4 * 3 * LG_HBLK_S; o += 128) {
             int const chn = o / (3 * LG_HBLK_S), sbk = (o / LG_HBLK_S) % 3, m = o % LG_HBLK_S;
             if (chn >= n_chn_psy) continue;
             int const m2 = (m == 0) ? 0 : LG_BLK_S - m;
@@ -476,7 +509,7 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
                                 out->ecb_l[chn], out->lim_l[chn], lane);
         for (int b = lane; b < LG_CBANDS; b += 32) out->eb_l[chn][b] = sm->eb[chn][b];
         __syncwarp();
-        for (int sbk = 0; sbk < 3; sbk++) {
+        for (int sbk = 0; has_short && sbk < 3; sbk++) {
             float *thr = out->thr_s[sbk][chn];
             lg_partition_and_spread(cfg, &cfg->s, sm->fes[chn][sbk], sm->eb[chn], sm->mx[chn], sm->av[chn], sm->midx[chn],
                                     thr, sm->av[chn] /* reuse as clamp scratch */, lane);

@@ -879,8 +879,14 @@ __device__ __noinline__ void lg_g_frame_end(const LgDevCfg *__restrict__ cfg, Lg
     b.resv_size = resv_size;
 }
 
+/* Four CTAs per SM (512 streams on 148 SMs: 3.46).  Asking for five (96 registers, so that the next step's analysis kernels find room on
+ * every SM underneath this kernel) was measured and is worse: 8.03 against 7.68 ms per pipelined step - the overlap buys almost nothing
+ * (serial sum of the kernels: 7.81 ms), the registers cost this kernel 5 %. */
+#ifndef LG_G_MINBLOCKS
+#define LG_G_MINBLOCKS(NW) 4
+#endif
 template <int NW>
-__global__ void __launch_bounds__(64 * NW, 4)
+__global__ void __launch_bounds__(64 * NW, LG_G_MINBLOCKS(NW))
 lg_kernel_quantg(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy, const LgFrameCtl *__restrict__ frm,
                  LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout, LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes)
 {

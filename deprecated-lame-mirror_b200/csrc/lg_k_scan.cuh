@@ -215,6 +215,16 @@ __device__ __forceinline__ void lg_adjust_ath(const LgDevCfg *__restrict__ cfg, 
     }
 }
 
+/* corrupted state: stop with an error instead of encoding something else than the reference (the reference asserts in such places) */
+__device__ __forceinline__ void lg_scan_inconsistent()
+{
+#ifdef LG_EMULATE
+    abort();
+#else
+    __trap();
+#endif
+}
+
 __global__ void __launch_bounds__(32)
 lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ ana, LgPsyOut *__restrict__ psy,
                LgFrameCtl *__restrict__ frm, LgStreamState *__restrict__ state,
@@ -240,10 +250,13 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
     for (int gb = mgr * f0; gb < mgr * my_frames; gb++) {
         const LgAnalysis *A = &sm->A;
         {
-            static_assert(sizeof(LgAnalysis) % 8 == 0, "LgAnalysis is copied in 8-byte words");
-            const float2 *src = reinterpret_cast<const float2 *>(ana + (size_t) stream * 2 * nframes + gb);
+            static_assert(sizeof(LgAnalysis) % 8 == 0 && LG_ANALYSIS_LONG_BYTES % 8 == 0, "LgAnalysis is copied in 8-byte words");
+            const LgAnalysis *rec = ana + (size_t) stream * 2 * nframes + gb;
+            const float2 *src = reinterpret_cast<const float2 *>(rec);
             float2 *dst = reinterpret_cast<float2 *>(&sm->A);
-            for (int i = lane; i < (int) (sizeof(LgAnalysis) / 8); i += 32) dst[i] = __ldg(src + i);
+            /* the short-block part (two thirds of the record) only where kernel A found that the granule can switch to short blocks */
+            int const words = (int) ((__ldg(&rec->has_short) ? sizeof(LgAnalysis) : LG_ANALYSIS_LONG_BYTES) / 8);
+            for (int i = lane; i < words; i += 32) dst[i] = __ldg(src + i);
         }
         __syncwarp();
         LgPsyOut *P = psy + (size_t) stream * 2 * nframes + gb;
@@ -340,6 +353,7 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
         __syncwarp();
         /* (g) short blocks (psymodel.c:1470-1500); kernel A already produced min(ecb, clamp) */
         if (!(ul0 && ul1)) {
+            if (!A->has_short) lg_scan_inconsistent();         /* kernel A's test is a superset of the attack detection above: cannot happen */
             for (int sblock = 0; sblock < 3; sblock++) {
                 for (int chn = 0; chn < n_chn_psy; ++chn) {
                     int const ul = (chn & 1) ? ul1 : ul0;

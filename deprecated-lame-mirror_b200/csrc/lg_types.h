@@ -116,17 +116,23 @@ typedef struct {
     int32_t out_pos, count;
 } LgRsChunk;
 
-/* ---- stage A (stateless analysis) -> stage B (ordered scan) */
+/* ---- stage A (stateless analysis) -> stage B (ordered scan).  The head and the long-block part are always written and read; the
+ * short-block part (two thirds of the record) only for granules that can switch to short blocks: kernel A decides that from the
+ * sub-block peaks of the granule and of the one before it, a superset of the reference's attack detection (psymodel.c:759-935 only ever
+ * REMOVES attacks after comparing the peak ratios with the threshold), as the reference skips its short-block FFTs and masking for
+ * long-block granules (psymodel.c:1474 vbrpsy_skip_masking_s) */
 typedef struct {
+    float en_subshort[4][12];           /* 9 sub-block peaks of the high-passed signal (psymodel.c:831) */
+    float tot_ener[4];
+    float loudness[2];
+    int   has_short, pad_;
     float eb_l[4][LG_CBANDS];           /* partition energies, long FFT, L R M S */
     float ecb_l[4][LG_CBANDS];          /* spread threshold before pre-echo control (psymodel.c:1185) */
     float lim_l[4][LG_CBANDS];          /* max*minval*avg_mask clamp (psymodel.c:1240) */
     float eb_s[3][4][LG_CBANDS];
     float thr_s[3][4][LG_CBANDS];       /* min(ecb, clamp) for the three short windows */
-    float en_subshort[4][12];           /* 9 sub-block peaks of the high-passed signal (psymodel.c:831) */
-    float tot_ener[4];
-    float loudness[2];
 } LgAnalysis;
+#define LG_ANALYSIS_LONG_BYTES (sizeof(LgAnalysis) - 2 * 3 * 4 * LG_CBANDS * sizeof(float))
 
 typedef struct { float l[LG_SBMAX_L]; float s[LG_SBMAX_S][3]; } LgXmin;
 

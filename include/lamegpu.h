@@ -201,8 +201,9 @@ long lamegpu_batch_flush_packed(lamegpu_batch *b, unsigned char *out, int out_st
  * Turning it off completes what is in flight.  0 = ok. */
 int  lamegpu_batch_set_pipelined(lamegpu_batch *b, int on);
 
-/* measurement hooks (bench.py): lamegpu_batch_stage_packed lays nframes frames per stream into the engine (one full step per buffer set,
- * then the streams are reset); lamegpu_batch_run_device_steps runs `steps` device-only steps on them back to back - persistent streams,
+/* measurement hooks (bench.py): lamegpu_batch_stage_packed lays a ring of 2 x nframes frames per stream (pcm = [S][2][2 * nframes * 1152]) into
+ * the engine's two buffer sets so that alternating them walks a periodic signal without a seam (one full step per buffer set, then the
+ * streams are reset); lamegpu_batch_run_device_steps runs `steps` device-only steps on them back to back - persistent streams,
  * consecutive steps overlapping as in production - and returns the device time per step in ms (first kernel's start to last kernel's
  * end, CUDA events; < 0 on error); lamegpu_batch_rerun_device = one step on freshly reset streams, after which lamegpu_batch_kernel_ms
  * gives that step's per-kernel times [analysis, scan, mdct, quantise, pack] and lamegpu_batch_step_ms its first-kernel-to-last time */

@@ -1,0 +1,6 @@
+#!/bin/bash
+O=gpurun_out/r2_15; mkdir -p $O
+L=deprecated-lame-mirror_b200/liblamegpu.so
+timeout 300 python tools/kbench.py $L 512 8 10 2>&1 | tail -1 | cut -c1-260 | tee -a $O/kbench.txt
+timeout 300 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 | tee $O/bench1.json
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3 | tee $O/pytest.txt
