@@ -374,10 +374,13 @@ def main():
             "metric": "mp3_frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world * ngpu_here, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": bench_config(S // ngpu_here, F),
-            "notes": {"process_model": "one process per GPU (torchrun)" if ngpu_here == 1 else "one process, %d GPUs through lamegpu_batch_open(device = -1)" % ngpu_here,"l2": "no explicit flush: steps run back to back on persistent streams; a step touches ~215 MB (two alternating buffer sets) > 126 MB L2",
+            "config": bench_config(S, F),
+            "notes": {"process_model": "one process per GPU (torchrun)" if ngpu_here == 1 else "one process, %d GPUs through lamegpu_batch_open(device = -1)" % ngpu_here,
+                      "l2": "no explicit flush: steps run back to back on persistent streams; a step touches ~215 MB (two alternating buffer sets) > 126 MB L2",
                       "parallelism": "streams sharded over %d GPU(s), no collective on the data path" % (world * ngpu_here),
-                      "value": "K pipelined steps on persistent streams, first kernel start to last kernel end (CUDA events) / K"},
+                      "value": "K pipelined steps on persistent streams, first kernel start to last kernel end (CUDA events) / K",
+                      "kernel_times": "kernel A of step i+1 is gated behind the launch of kernel D of step i and runs in the room D's last wave leaves, so its "
+                                      "event-to-event time (kernels_ms_per_step.analysis) is mostly waiting; alone it takes 0.73 ms (profiles/)"},
             "e2e": {"value": e2e_frames_all / (e2e_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms_max / args.steps, "mp3_bytes": total_bytes,
                     "note": "lamegpu_batch_encode_packed, pipelined (lamegpu_batch_set_pipelined): caller's PCM -> pinned staging -> H2D -> kernels -> D2H of packed "
