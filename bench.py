@@ -306,6 +306,10 @@ def main():
     clocks = sampler.stop()
     launches = enc.kernel_launches() - launches0
     log('device timing done: %s' % (kms / args.steps))
+    alone = np.zeros(5)                                      # outside the timed region: every kernel with the device to itself (two steps, one at a time)
+    for _ in range(3):
+        enc.rerun_device(F)
+        alone += np.array(enc.kernel_ms()) / 3
     frames_dev, dev_ms_max = reduce_over_ranks(float(S * F * args.steps), dev_ms)
     value = frames_dev / (dev_ms_max * 1e-3)
 
@@ -354,7 +358,7 @@ def main():
         S //= ngpu_here                                       # per GPU from here on: the kernel figures are one device's
         headline = (S, F, SIGNAL, BRATE, VBR, QUALITY) == (512, 8, "noise", 128, 0, -1)
         achieved = ALG_BYTES_QUANT * S * F / (q_ms * 1e-3) / 1e9
-        a_ms = (kms[0] + kms[1] + kms[2]) / args.steps
+        a_ms = float(alone[0] + alone[1] + alone[2])               # the three kernels' own run times (in the pipeline kernel A's event time is mostly waiting)
         prof = ncu_profile(qname) if headline else None
         sm_hz = 1e6 * (clocks.get("sm_mhz") or 1965.0)
         issue_peak = 148 * 4 * sm_hz                          # one warp instruction per scheduler per cycle
@@ -390,6 +394,8 @@ def main():
             "roofline_hbm": hbm,
             "kernels_ms_per_step": {"analysis": kms[0] / args.steps, "scan": kms[1] / args.steps, "mdct": kms[2] / args.steps, "quant": q_ms,
                                     "pack": kms[4] / args.steps,
+                                    "alone": {"analysis": float(alone[0]), "scan": float(alone[1]), "mdct": float(alone[2]), "quant": float(alone[3]),
+                                              "pack": float(alone[4])},
                                     "note": "CUDA events around each kernel; analysis/scan/mdct of step i+1 run under the quantiser of step i, so ms_per_step is less than their sum"},
             "roofline_mdct_psy": {"bound": "hbm", "kernels": "analysis+scan+mdct", "achieved": ALG_BYTES_ANALYSIS * S * F / (a_ms * 1e-3) / 1e9,
                                   "peak": peak, "unit": "GB/s", "frac": ALG_BYTES_ANALYSIS * S * F / (a_ms * 1e-3) / 1e9 / peak},
