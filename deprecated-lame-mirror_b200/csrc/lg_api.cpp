@@ -17,6 +17,7 @@
 #include <memory>
 #include <string>
 #include "../../include/lamegpu.h"
+#include <type_traits>
 #include "lg_engine.h"
 #include "lg_bitstream.h"
 
@@ -32,15 +33,24 @@ static const bool g_timing = getenv("LAMEGPU_TIMING") != nullptr;
  * timeline holds 1152*k + 1904 samples (calcNeeded, lame.c:1627). */
 struct Stream {
     std::vector<int16_t> pcm16[2];     /* timeline samples from index tbase on */
-    std::vector<float> pcmf[2];        /* same, already through pcm_transform, once a float entry point was used */
+    std::vector<float> pcmf[2];        /* same, already through pcm_transform: a stream whose calls mixed sample types (float_mode) */
     bool float_mode = false;
+    /* same in the caller's own sample type (lame_encode_buffer_int / _long / _float / _ieee_double ...): raw elements of nat_esz bytes; the
+     * device converts them and applies nat_scale * pcm_transform (lame.c:1797-1834) */
+    std::vector<unsigned char> nat[2];
+    int  nat_kind = 0, nat_esz = 0;    /* LG_PCM_S32 / F32 / S64 / F64, 0 = not in this mode */
+    float nat_scale = 1.0f;
+    bool fed = false;                  /* samples have arrived: the representation is settled */
     int  fs = 1152, need = 1904;       /* samples per frame (576 per granule) and what a frame needs in the buffer (calcNeeded, lame.c:1627) */
     /* input-rate conversion (util.c:531): the stream's input samples (through pcm_transform) from absolute index
      * raw_base on, the reference's per-call bookkeeping replayed as a list of chunks, the input clock, and the end
      * of the timeline the chunks cover.  The samples themselves are made on the device (kernel R). */
     struct Chunk { double itime; long in_base, out_pos; int count; };
     bool rs_mode = false;
-    std::vector<float> raw[2];
+    std::vector<unsigned char> raw[2]; /* elements of rs_esz bytes in the caller's sample type rs_kind (LG_PCM_DONE: floats transformed here) */
+    int  rs_kind = LG_PCM_S16, rs_esz = 2;
+    float rs_scale = 1.0f;
+    long rawn() const { return (long) (raw[0].size() / (size_t) rs_esz); }
     long raw_base = -LG_RS_HIST;
     std::vector<Chunk> chunks;
     double rs_itime = 0;
@@ -76,15 +86,18 @@ struct Stream {
     void init()
     {
         for (int c = 0; c < 2; c++) { pcm16[c].assign(LG_PCM_HIST + 528, 0); pcmf[c].clear(); }
-        float_mode = false; tbase = -LG_PCM_HIST; frames_done = 0; frames_out = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
+        float_mode = false; nat[0].clear(); nat[1].clear(); nat_kind = nat_esz = 0; nat_scale = 1.0f; fed = false;
+        tbase = -LG_PCM_HIST; frames_done = 0; frames_out = 0; mf_samples_to_encode = 576 + 1152; last_padding = 0;
         bl = br = nullptr; bn = 0;
-        for (int c = 0; c < 2; c++) raw[c].assign(LG_RS_HIST, 0.f);
+        rs_kind = LG_PCM_S16; rs_esz = 2; rs_scale = 1.0f;
+        for (int c = 0; c < 2; c++) raw[c].assign((size_t) LG_RS_HIST * rs_esz, 0);
         raw_base = -LG_RS_HIST; chunks.clear(); rs_itime = 0; rs_tend = 528;
         bw.reset(); out.clear();
         memset(hist_mode, 0, sizeof hist_mode); memset(hist_block, 0, sizeof hist_block);
         tag = Tag();
     }
-    long tend() const { return rs_mode ? rs_tend : tbase + (long) (float_mode ? pcmf[0].size() : pcm16[0].size()) + bn; }
+    long held() const { return (long) (float_mode ? pcmf[0].size() : nat_kind ? nat[0].size() / (size_t) nat_esz : pcm16[0].size()); }
+    long tend() const { return rs_mode ? rs_tend : tbase + held() + bn; }
     /* timeline samples [from, from + n) of channel c as int16 into dst: from the kept samples, then from the borrowed input */
     void copy16(int c, long from, size_t n, int16_t *dst) const
     {
@@ -106,9 +119,34 @@ struct Stream {
         if (have < (long) fs * k + need) return 0;
         return (have - need - (long) fs * k) / fs + 1;
     }
+    template <class T> void nat_to_float(const LgDevCfg *cfg)
+    {
+        size_t const n = nat[0].size() / sizeof(T);
+        float const m00 = nat_scale * cfg->pcm_transform[0][0], m01 = nat_scale * cfg->pcm_transform[0][1];
+        float const m10 = nat_scale * cfg->pcm_transform[1][0], m11 = nat_scale * cfg->pcm_transform[1][1];
+        const T *a = (const T *) nat[0].data(), *b = (const T *) nat[1].data();
+        pcmf[0].resize(n); pcmf[1].resize(n);
+        for (size_t i = 0; i < n; i++) {
+            float const xl = (float) a[i], xr = (float) b[i];
+            pcmf[0][i] = xl * m00 + xr * m01;
+            pcmf[1][i] = xl * m10 + xr * m11;
+        }
+    }
+    /* a stream whose calls mix sample types (or normalisations) falls back to floats converted on the host, as lame.c:1803-1834 does it */
     void to_float(const LgDevCfg *cfg)
     {
         if (float_mode) return;
+        if (nat_kind) {
+            switch (nat_kind) {
+            case LG_PCM_S32: nat_to_float<int32_t>(cfg); break;
+            case LG_PCM_F32: nat_to_float<float>(cfg); break;
+            case LG_PCM_S64: nat_to_float<long long>(cfg); break;
+            default:         nat_to_float<double>(cfg); break;
+            }
+            nat[0].clear(); nat[1].clear(); nat_kind = nat_esz = 0;
+            float_mode = true;
+            return;
+        }
         unborrow();
         size_t const n = pcm16[0].size();
         float const m00 = cfg->pcm_transform[0][0], m01 = cfg->pcm_transform[0][1];
@@ -122,6 +160,13 @@ struct Stream {
         pcm16[0].clear(); pcm16[1].clear();
         float_mode = true;
     }
+    /* a fresh stream (only the zero prefix, which is zero in every type) takes the sample type of its first input */
+    void to_native(int kind, int esz, float scale)
+    {
+        size_t const n = pcm16[0].size();
+        for (int c = 0; c < 2; c++) { nat[c].assign(n * (size_t) esz, 0); pcm16[c].clear(); }
+        nat_kind = kind; nat_esz = esz; nat_scale = scale;
+    }
     void drop_consumed()
     {
         long const keep_from = (long) fs * frames_done - LG_PCM_HIST;
@@ -130,9 +175,9 @@ struct Stream {
             size_t n = 0;
             while (n < chunks.size() && chunks[n].out_pos + chunks[n].count <= keep_from) n++;
             chunks.erase(chunks.begin(), chunks.begin() + n);
-            long const from = (chunks.empty() ? raw_base + (long) raw[0].size() : chunks[0].in_base) - LG_RS_HIST;
+            long const from = (chunks.empty() ? raw_base + rawn() : chunks[0].in_base) - LG_RS_HIST;
             if (from > raw_base) {
-                for (int c = 0; c < 2; c++) raw[c].erase(raw[c].begin(), raw[c].begin() + (from - raw_base));
+                for (int c = 0; c < 2; c++) raw[c].erase(raw[c].begin(), raw[c].begin() + (from - raw_base) * rs_esz);
                 raw_base = from;
             }
             return;
@@ -140,6 +185,7 @@ struct Stream {
         long const d = keep_from - tbase;
         if (d <= 0) return;
         if (float_mode) for (int c = 0; c < 2; c++) pcmf[c].erase(pcmf[c].begin(), pcmf[c].begin() + d);
+        else if (nat_kind) for (int c = 0; c < 2; c++) nat[c].erase(nat[c].begin(), nat[c].begin() + d * nat_esz);
         else {
             long const have = (long) pcm16[0].size();
             if (d <= have) for (int c = 0; c < 2; c++) pcm16[c].erase(pcm16[c].begin(), pcm16[c].begin() + d);
@@ -337,7 +383,7 @@ struct lamegpu_batch {
         int maxf = 0, any_float = 0;
         for (int s = 0; s < S; s++) {
             long const r = st[s].frames_ready();
-            if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode) any_float = 1; }
+            if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode || st[s].nat_kind) any_float = 1; }
         }
         if (maxf == 0) return -1;
         if (complete(k) != 0) return -2;                 /* the slot's previous step (two steps back) */
@@ -364,13 +410,20 @@ struct lamegpu_batch {
             if (lg_engine_reserve_chunks(eng, k, most.load()) != 0) return -2;
             size_t const raw_stride = lg_engine_raw_stride(eng);
             int const cap = lg_engine_chunk_cap(eng, k);
-            float *hr = lg_engine_host_raw(eng, k);
+            int esz = 4;
+            for (int s = 0; s < S; s++) if (nfr[s] && st[s].rs_esz > esz) esz = st[s].rs_esz;
+            if (lg_engine_need_raw(eng, esz) != 0) return -2;
+            esz = lg_engine_raw_esz(eng);
+            char *hr = (char *) lg_engine_host_raw(eng, k);
+            LgPcmKind *hk = lg_engine_host_kinds(eng, k);
             LgRsChunk *hc = lg_engine_host_chunks(eng, k);
             int *hn = lg_engine_host_rs_counts(eng, k);
             parallel_for(S, [&](int s) {
                 hn[2 * s] = hn[2 * s + 1] = 0;
+                hk[s].kind = LG_PCM_S16; hk[s].scale = 1.0f;
                 if (!nfr[s]) return;
                 const Stream &x = st[s];
+                hk[s].kind = x.rs_kind; hk[s].scale = x.rs_scale;
                 long t0, t1; size_t nck;
                 window(s, t0, t1, nck);
                 long hi = 0;
@@ -381,22 +434,36 @@ struct lamegpu_batch {
                     long const klast = std::min<long>(c.count, t1 - c.out_pos) - 1;
                     hi = std::max(hi, c.in_base + (long) floor((double) klast * cfg.rs_ratio - c.itime) + reach + 1 - x.raw_base);
                 }
-                if (hi > (long) raw_stride || hi > (long) x.raw[0].size()) { bad.store(1); return; }
-                for (int c = 0; c < 2; c++) memcpy(hr + ((size_t) s * 2 + c) * raw_stride, x.raw[c].data(), (size_t) hi * sizeof(float));
+                if (hi > (long) raw_stride || hi > x.rawn()) { bad.store(1); return; }
+                for (int c = 0; c < 2; c++) memcpy(hr + ((size_t) s * 2 + c) * raw_stride * (size_t) esz, x.raw[c].data(), (size_t) hi * x.rs_esz);
                 hn[2 * s] = (int) nck; hn[2 * s + 1] = (int) (t1 - t0);
             });
             if (bad.load()) { fprintf(stderr, "lamegpu: resampler staging overflow\n"); return -2; }
             any_float = 1;
         }
         else if (any_float) {
-            if (lg_engine_need_float_pcm(eng) != 0) return -2;
-            float *hp = lg_engine_host_pcmf(eng, k);
+            /* some stream is not int16: every stream's row goes out in the stream's own sample type, kernel A converts */
+            int esz = 4;
+            for (int s = 0; s < S; s++) if (nfr[s] && st[s].nat_esz > esz) esz = st[s].nat_esz;
+            if (lg_engine_need_native_pcm(eng, esz) != 0) return -2;
+            esz = lg_engine_native_esz(eng);
+            char *hp = (char *) lg_engine_host_pcmn(eng, k);
+            LgPcmKind *hk = lg_engine_host_kinds(eng, k);
             parallel_for(S, [&](int s) {
+                hk[s].kind = LG_PCM_S16; hk[s].scale = 1.0f;
                 if (!nfr[s]) return;
-                st[s].to_float(&cfg);
-                size_t const n = (size_t) nfr[s] * st[s].fs + LG_PCM_HALO;
-                for (int c = 0; c < 2; c++) memcpy(hp + ((size_t) s * 2 + c) * stride, st[s].pcmf[c].data(), n * sizeof(float));
+                const Stream &x = st[s];
+                size_t const n = (size_t) nfr[s] * x.fs + LG_PCM_HALO;
+                for (int c = 0; c < 2; c++) {
+                    char *row = hp + ((size_t) s * 2 + c) * stride * (size_t) esz;
+                    if (x.float_mode) memcpy(row, x.pcmf[c].data(), n * sizeof(float));
+                    else if (x.nat_kind) memcpy(row, x.nat[c].data(), n * (size_t) x.nat_esz);
+                    else x.copy16(c, x.tbase, n, (int16_t *) row);
+                }
+                if (x.float_mode) hk[s].kind = LG_PCM_DONE;
+                else if (x.nat_kind) { hk[s].kind = x.nat_kind; hk[s].scale = x.nat_scale; }
             });
+            any_float = 2;
         }
         else {
             int16_t *hp = lg_engine_host_pcm16(eng, k);
@@ -452,7 +519,7 @@ struct lamegpu_batch {
     {
         double const ratio = cfg.rs_ratio;
         int const filter_l = cfg.rs_filter_l, reach = filter_l - filter_l / 2;
-        long in_ptr = x.raw_base + (long) x.raw[0].size() - n;
+        long in_ptr = x.raw_base + x.rawn() - n;
         int remaining = n;
         while (remaining > 0) {
             double const itime = x.rs_itime;
@@ -474,16 +541,63 @@ struct lamegpu_batch {
             x.mf_samples_to_encode += count;
         }
     }
+    /* the resampler's input keeps the caller's sample type too (kernel R converts); a stream that mixes types falls back to floats
+     * transformed here */
+    template <class T> static void raw_to_done(Stream &x, const LgDevCfg &cfg)
+    {
+        size_t const n = (size_t) x.rawn();
+        float const m00 = x.rs_scale * cfg.pcm_transform[0][0], m01 = x.rs_scale * cfg.pcm_transform[0][1];
+        float const m10 = x.rs_scale * cfg.pcm_transform[1][0], m11 = x.rs_scale * cfg.pcm_transform[1][1];
+        std::vector<unsigned char> o[2];
+        o[0].resize(n * sizeof(float)); o[1].resize(n * sizeof(float));
+        const T *a = (const T *) x.raw[0].data(), *b = (const T *) x.raw[1].data();
+        for (size_t i = 0; i < n; i++) {
+            float const xl = (float) a[i], xr = (float) b[i];
+            ((float *) o[0].data())[i] = xl * m00 + xr * m01;
+            ((float *) o[1].data())[i] = xl * m10 + xr * m11;
+        }
+        x.raw[0].swap(o[0]); x.raw[1].swap(o[1]);
+        x.rs_kind = LG_PCM_DONE; x.rs_esz = 4; x.rs_scale = 1.0f;
+    }
     template <class T> void feed_rs(Stream &x, const T *l, const T *r, int n, int jump, float scale)
     {
-        float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
-        float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
-        size_t const at = x.raw[0].size();
-        x.raw[0].resize(at + n); x.raw[1].resize(at + n);
-        for (int i = 0; i < n; i++) {
-            float const xl = (float) l[(size_t) i * jump], xr = (float) r[(size_t) i * jump];
-            x.raw[0][at + i] = xl * m00 + xr * m01;
-            x.raw[1][at + i] = xl * m10 + xr * m11;
+        int const kind = std::is_same<T, float>::value ? LG_PCM_F32 : std::is_same<T, double>::value ? LG_PCM_F64
+                       : sizeof(T) == 8 ? LG_PCM_S64 : sizeof(T) == 4 ? LG_PCM_S32 : LG_PCM_S16;
+        if (!x.fed) {                                      /* only zeros so far: they are zero in every type */
+            size_t const have = (size_t) x.rawn();
+            x.rs_kind = kind; x.rs_esz = (int) sizeof(T); x.rs_scale = scale;
+            for (int c = 0; c < 2; c++) x.raw[c].assign(have * sizeof(T), 0);
+            x.fed = true;
+        }
+        if (x.rs_kind == kind && x.rs_scale == scale) {
+            size_t const at = x.raw[0].size();
+            for (int c = 0; c < 2; c++) {
+                x.raw[c].resize(at + (size_t) n * sizeof(T));
+                T *d = (T *) (x.raw[c].data() + at);
+                const T *src = c ? r : l;
+                if (jump == 1) memcpy(d, src, (size_t) n * sizeof(T));
+                else for (int i = 0; i < n; i++) d[i] = src[(size_t) i * jump];
+            }
+        }
+        else {
+            switch (x.rs_kind) {
+            case LG_PCM_S16: raw_to_done<int16_t>(x, cfg); break;
+            case LG_PCM_S32: raw_to_done<int32_t>(x, cfg); break;
+            case LG_PCM_F32: raw_to_done<float>(x, cfg); break;
+            case LG_PCM_S64: raw_to_done<long long>(x, cfg); break;
+            case LG_PCM_F64: raw_to_done<double>(x, cfg); break;
+            default: break;
+            }
+            float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
+            float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
+            size_t const at = x.raw[0].size();
+            x.raw[0].resize(at + (size_t) n * sizeof(float)); x.raw[1].resize(at + (size_t) n * sizeof(float));
+            float *d0 = (float *) (x.raw[0].data() + at), *d1 = (float *) (x.raw[1].data() + at);
+            for (int i = 0; i < n; i++) {
+                float const xl = (float) l[(size_t) i * jump], xr = (float) r[(size_t) i * jump];
+                d0[i] = xl * m00 + xr * m01;
+                d1[i] = xl * m10 + xr * m11;
+            }
         }
         rs_schedule(x, n);
     }
@@ -493,6 +607,8 @@ struct lamegpu_batch {
         if (n <= 0) return;
         if (!r) r = l;
         if (x.rs_mode) { feed_rs<short>(x, l, r, n, 1, 1.0f); return; }
+        if (x.nat_kind) x.to_float(&cfg);                                      /* int16 after another sample type: mixed */
+        x.fed = true;
         if (x.float_mode) {
             float const m00 = cfg.pcm_transform[0][0], m01 = cfg.pcm_transform[0][1];
             float const m10 = cfg.pcm_transform[1][0], m11 = cfg.pcm_transform[1][1];
@@ -522,15 +638,32 @@ struct lamegpu_batch {
         if (n <= 0) return;
         if (!r) r = l;
         if (x.rs_mode) { feed_rs<T>(x, l, r, n, jump, scale); return; }
-        x.to_float(&cfg);
-        float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
-        float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
-        size_t const at = x.pcmf[0].size();
-        x.pcmf[0].resize(at + n); x.pcmf[1].resize(at + n);
-        for (int i = 0; i < n; i++) {
-            float const xl = (float) l[(size_t) i * jump], xr = (float) r[(size_t) i * jump];
-            x.pcmf[0][at + i] = xl * m00 + xr * m01;
-            x.pcmf[1][at + i] = xl * m10 + xr * m11;
+        /* the stream keeps the caller's sample type and the device converts (kernel A, phase 1) - as long as all of a stream's calls bring
+         * the same type and normalisation; otherwise it falls back to floats converted here */
+        int const kind = std::is_same<T, float>::value ? LG_PCM_F32 : std::is_same<T, double>::value ? LG_PCM_F64 : sizeof(T) == 8 ? LG_PCM_S64 : LG_PCM_S32;
+        if (!x.fed && !x.float_mode && !x.nat_kind) { x.unborrow(); x.to_native(kind, (int) sizeof(T), scale); }
+        x.fed = true;
+        if (x.nat_kind == kind && x.nat_scale == scale && x.nat_esz == (int) sizeof(T)) {
+            size_t const at = x.nat[0].size();
+            for (int c = 0; c < 2; c++) {
+                x.nat[c].resize(at + (size_t) n * sizeof(T));
+                T *d = (T *) (x.nat[c].data() + at);
+                const T *src = c ? r : l;
+                if (jump == 1) memcpy(d, src, (size_t) n * sizeof(T));
+                else for (int i = 0; i < n; i++) d[i] = src[(size_t) i * jump];
+            }
+        }
+        else {
+            x.to_float(&cfg);
+            float const m00 = scale * cfg.pcm_transform[0][0], m01 = scale * cfg.pcm_transform[0][1];
+            float const m10 = scale * cfg.pcm_transform[1][0], m11 = scale * cfg.pcm_transform[1][1];
+            size_t const at = x.pcmf[0].size();
+            x.pcmf[0].resize(at + n); x.pcmf[1].resize(at + n);
+            for (int i = 0; i < n; i++) {
+                float const xl = (float) l[(size_t) i * jump], xr = (float) r[(size_t) i * jump];
+                x.pcmf[0][at + i] = xl * m00 + xr * m01;
+                x.pcmf[1][at + i] = xl * m10 + xr * m11;
+            }
         }
         if (x.mf_samples_to_encode < 1) x.mf_samples_to_encode = 576 + 1152;
         x.mf_samples_to_encode += n;
@@ -558,7 +691,7 @@ struct lamegpu_batch {
                 bunch *= cfg.rs_ratio;
                 if (bunch > 1152) bunch = 1152;
                 if (bunch < 1) bunch = 1;
-                for (int c = 0; c < 2; c++) x.raw[c].insert(x.raw[c].end(), (size_t) bunch, 0.f);
+                for (int c = 0; c < 2; c++) x.raw[c].insert(x.raw[c].end(), (size_t) bunch * x.rs_esz, (unsigned char) 0);
                 rs_schedule(x, bunch);
                 long const ready = x.rs_tend >= (long) fs * virt_done + x.need ? (x.rs_tend - x.need - (long) fs * virt_done) / fs + 1 : 0;
                 if (ready > 0) frames_left -= 1;
@@ -576,6 +709,7 @@ struct lamegpu_batch {
         long const need = fs * last + x.need - x.tend();
         if (need > 0) {
             if (x.float_mode) for (int c = 0; c < 2; c++) x.pcmf[c].insert(x.pcmf[c].end(), (size_t) need, 0.f);
+            else if (x.nat_kind) for (int c = 0; c < 2; c++) x.nat[c].insert(x.nat[c].end(), (size_t) need * x.nat_esz, (unsigned char) 0);
             else for (int c = 0; c < 2; c++) x.pcm16[c].insert(x.pcm16[c].end(), (size_t) need, (int16_t) 0);
         }
     }

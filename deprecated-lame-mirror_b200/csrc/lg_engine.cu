@@ -73,9 +73,10 @@ struct LgSlot {
     LgGranuleOut *d_gout; LgFrameOut *d_fout;
     unsigned char *d_pay, *d_hdr;
     int *d_nfr;
-    int16_t *h_pcm16; float *h_pcmf; int *h_nfr;
+    int16_t *h_pcm16; int *h_nfr;
+    char *h_pcmn; LgPcmKind *h_kind;  /* native sample types: rows of pcmn_esz-byte elements, every stream in its own type */
     LgFrameOut *h_fout; unsigned char *h_pay, *h_hdr;
-    float *h_raw; LgRsChunk *h_rsc; LgRsStream *h_rss;
+    char *h_raw; LgRsChunk *h_rsc; LgRsStream *h_rss;      /* h_raw: the resampler's input, rows of raw_esz-byte elements in the stream's own sample type */
     int chunk_cap;
 #ifndef LG_EMULATE
     cudaEvent_t ev[10];               /* 0 start (analysis stream), 1 after A, 2 after B, 3 after C, 4 before D (quantiser stream), 5 after D, 6 after E, 7 results on the host, 8/9 around R */
@@ -89,13 +90,14 @@ struct lg_engine {
     LgDevCfg *dcfg;
     int S, F, device;
     size_t pcm_stride;                /* samples per channel per stream */
-    int16_t *d_pcm16; float *d_pcmf;
+    int16_t *d_pcm16; float *d_pcmf;  /* d_pcmf: the resampler's output */
+    char *d_pcmn; LgPcmKind *d_kind; int pcmn_esz;
     float *d_sb;
     LgAnalysis *d_ana;
     size_t pay_stride;
     LgStreamState *d_state, *d_state0;   /* d_state0: S copies of the initial state, for one-copy resets */
     size_t raw_stride; int chunk_cap;
-    float *d_raw; LgRsChunk *d_rsc; LgRsStream *d_rss;
+    char *d_raw; int raw_esz; LgRsChunk *d_rsc; LgRsStream *d_rss;
     LgSlot slot[LG_SLOTS];
     /* two CUDA streams: `stream` carries the copies in and the stateless/scan kernels (R, A, B, C), `stream2` the quantiser, the packer
      * and the copies out (D, E); events order slot k's D behind its C and its next A-B-C behind its previous D2H.  Nothing waits
@@ -118,7 +120,9 @@ extern "C" int lg_engine_device(const lg_engine *e) { return e->device; }
 extern "C" int lg_engine_slots(const lg_engine *) { return LG_SLOTS; }
 extern "C" size_t lg_engine_pcm_stride(const lg_engine *e) { return e->pcm_stride; }
 extern "C" int16_t *lg_engine_host_pcm16(lg_engine *e, int k) { return e->slot[k].h_pcm16; }
-extern "C" float *lg_engine_host_pcmf(lg_engine *e, int k) { return e->slot[k].h_pcmf; }
+extern "C" void *lg_engine_host_pcmn(lg_engine *e, int k) { return e->slot[k].h_pcmn; }
+extern "C" LgPcmKind *lg_engine_host_kinds(lg_engine *e, int k) { return e->slot[k].h_kind; }
+extern "C" int lg_engine_native_esz(const lg_engine *e) { return e->pcmn_esz; }
 extern "C" int *lg_engine_host_nfr(lg_engine *e, int k) { return e->slot[k].h_nfr; }
 extern "C" const unsigned char *lg_engine_host_pay(const lg_engine *e, int k) { return e->slot[k].h_pay; }
 extern "C" const unsigned char *lg_engine_host_hdr(const lg_engine *e, int k) { return e->slot[k].h_hdr; }
@@ -127,7 +131,8 @@ extern "C" const LgFrameOut *lg_engine_host_fout(const lg_engine *e, int k) { re
 extern "C" const float *lg_engine_last_kernel_ms(const lg_engine *e) { return e->last_ms; }
 extern "C" long lg_engine_launch_count(const lg_engine *e) { return e->launches; }
 extern "C" size_t lg_engine_raw_stride(const lg_engine *e) { return e->raw_stride; }
-extern "C" float *lg_engine_host_raw(lg_engine *e, int k) { return e->slot[k].h_raw; }
+extern "C" void *lg_engine_host_raw(lg_engine *e, int k) { return e->slot[k].h_raw; }
+extern "C" int lg_engine_raw_esz(const lg_engine *e) { return e->raw_esz; }
 extern "C" LgRsChunk *lg_engine_host_chunks(lg_engine *e, int k) { return e->slot[k].h_rsc; }
 extern "C" int *lg_engine_host_rs_counts(lg_engine *e, int k) { return (int *) e->slot[k].h_rss; }
 extern "C" int lg_engine_chunk_cap(const lg_engine *e, int k) { return e->slot[k].chunk_cap; }
@@ -160,14 +165,14 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->stream2) cudaStreamSynchronize(e->stream2);
 #endif
-    lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_sb); lg_dev_free(e->d_ana);
+    lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_pcmn); lg_dev_free(e->d_kind); lg_dev_free(e->d_sb); lg_dev_free(e->d_ana);
     lg_dev_free(e->d_state); lg_dev_free(e->d_state0);
     lg_dev_free(e->d_raw); lg_dev_free(e->d_rsc); lg_dev_free(e->d_rss);
     for (int k = 0; k < LG_SLOTS; k++) {
         LgSlot &t = e->slot[k];
         lg_dev_free(t.d_psy); lg_dev_free(t.d_frm); lg_dev_free(t.d_xr); lg_dev_free(t.d_gout); lg_dev_free(t.d_fout); lg_dev_free(t.d_pay); lg_dev_free(t.d_hdr);
         lg_dev_free(t.d_nfr);
-        lg_host_free(t.h_pcm16); lg_host_free(t.h_pcmf); lg_host_free(t.h_nfr); lg_host_free(t.h_pay); lg_host_free(t.h_hdr); lg_host_free(t.h_fout);
+        lg_host_free(t.h_pcm16); lg_host_free(t.h_pcmn); lg_host_free(t.h_kind); lg_host_free(t.h_nfr); lg_host_free(t.h_pay); lg_host_free(t.h_hdr); lg_host_free(t.h_fout);
         lg_host_free(t.h_raw); lg_host_free(t.h_rsc); lg_host_free(t.h_rss);
 #ifndef LG_EMULATE
         for (int i = 0; i < 10; i++) if (t.ev[i]) cudaEventDestroy(t.ev[i]);
@@ -294,11 +299,13 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     bad |= lg_dev_malloc((void **) &e->d_ana, S * 2 * F * sizeof(LgAnalysis));
     bad |= lg_dev_malloc((void **) &e->d_state, S * sizeof(LgStreamState));
     bad |= lg_dev_malloc((void **) &e->d_state0, S * sizeof(LgStreamState));
+    bad |= lg_dev_malloc((void **) &e->d_kind, S * sizeof(LgPcmKind));
     if (cfg->resample) {
         /* inputs behind one window: its own samples, one more reference call (<= 1152 outputs) before it, the filter taps */
         e->raw_stride = (size_t) ceil((double) (e->pcm_stride + 1152) * cfg->rs_ratio) + 128;
         e->chunk_cap = 2 * max_frames + 16;
-        bad |= lg_dev_malloc((void **) &e->d_raw, S * 2 * e->raw_stride * sizeof(float));
+        e->raw_esz = 4;
+        bad |= lg_dev_malloc((void **) &e->d_raw, S * 2 * e->raw_stride * (size_t) e->raw_esz);
         bad |= lg_dev_malloc((void **) &e->d_rsc, S * e->chunk_cap * sizeof(LgRsChunk));
         bad |= lg_dev_malloc((void **) &e->d_rss, S * sizeof(LgRsStream));
         bad |= lg_dev_malloc((void **) &e->d_pcmf, S * 2 * e->pcm_stride * sizeof(float));
@@ -315,12 +322,13 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
         bad |= lg_dev_malloc((void **) &t.d_nfr, S * sizeof(int));
         bad |= lg_host_malloc((void **) &t.h_pcm16, S * 2 * e->pcm_stride * sizeof(int16_t));
         bad |= lg_host_malloc((void **) &t.h_nfr, S * sizeof(int));
+        bad |= lg_host_malloc((void **) &t.h_kind, S * sizeof(LgPcmKind));
         bad |= lg_host_malloc((void **) &t.h_pay, S * e->pay_stride);
         bad |= lg_host_malloc((void **) &t.h_hdr, S * F * LG_HDR_STRIDE);
         bad |= lg_host_malloc((void **) &t.h_fout, S * F * sizeof(LgFrameOut));
         if (cfg->resample) {
             t.chunk_cap = e->chunk_cap;
-            bad |= lg_host_malloc((void **) &t.h_raw, S * 2 * e->raw_stride * sizeof(float));
+            bad |= lg_host_malloc((void **) &t.h_raw, S * 2 * e->raw_stride * (size_t) e->raw_esz);
             bad |= lg_host_malloc((void **) &t.h_rsc, S * e->chunk_cap * sizeof(LgRsChunk));
             bad |= lg_host_malloc((void **) &t.h_rss, S * sizeof(LgRsStream));
         }
@@ -381,14 +389,45 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     return e;
 }
 
-/* float staging is allocated on first use (only the float/int32/double entry points need it) */
-extern "C" int lg_engine_need_float_pcm(lg_engine *e)
+/* The native-type PCM window (lame_encode_buffer_int / _long / _float / _ieee_double ...: the caller's samples go to the device as they
+ * are, kernel A converts) is allocated on first use, with rows of `esz`-byte elements (4, or 8 once a stream brings long or double
+ * samples); growing it waits for the steps in flight.  The caller restages the slot it is filling. */
+extern "C" int lg_engine_need_native_pcm(lg_engine *e, int esz)
 {
-    if (e->slot[0].h_pcmf) return 0;
+    if (esz != 4 && esz != 8) return -1;
+    if (e->pcmn_esz >= esz) return 0;
     LgDeviceScope dev(e->device);
-    size_t const n = (size_t) e->S * 2 * e->pcm_stride * sizeof(float);
-    for (int k = 0; k < LG_SLOTS; k++) if (lg_host_malloc((void **) &e->slot[k].h_pcmf, n)) return -1;
-    if (!e->d_pcmf && lg_dev_malloc((void **) &e->d_pcmf, n)) return -1;
+#ifndef LG_EMULATE
+    LG_CHECK(cudaStreamSynchronize(e->stream));           /* no H2D copy or kernel A may still read the old window */
+#endif
+    size_t const n = (size_t) e->S * 2 * e->pcm_stride * (size_t) esz;
+    for (int k = 0; k < LG_SLOTS; k++) {
+        lg_host_free(e->slot[k].h_pcmn); e->slot[k].h_pcmn = NULL;
+        if (lg_host_malloc((void **) &e->slot[k].h_pcmn, n)) return -1;
+    }
+    lg_dev_free(e->d_pcmn); e->d_pcmn = NULL;
+    if (lg_dev_malloc((void **) &e->d_pcmn, n)) return -1;
+    e->pcmn_esz = esz;
+    return 0;
+}
+/* the same for the resampler's input window (4-byte elements to begin with) */
+extern "C" int lg_engine_need_raw(lg_engine *e, int esz)
+{
+    if (esz != 4 && esz != 8) return -1;
+    if (!e->hcfg.resample) return -1;
+    if (e->raw_esz >= esz) return 0;
+    LgDeviceScope dev(e->device);
+#ifndef LG_EMULATE
+    LG_CHECK(cudaStreamSynchronize(e->stream));
+#endif
+    size_t const n = (size_t) e->S * 2 * e->raw_stride * (size_t) esz;
+    for (int k = 0; k < LG_SLOTS; k++) {
+        lg_host_free(e->slot[k].h_raw); e->slot[k].h_raw = NULL;
+        if (lg_host_malloc((void **) &e->slot[k].h_raw, n)) return -1;
+    }
+    lg_dev_free(e->d_raw); e->d_raw = NULL;
+    if (lg_dev_malloc((void **) &e->d_raw, n)) return -1;
+    e->raw_esz = esz;
     return 0;
 }
 
@@ -454,7 +493,7 @@ static void lg_launch_quant_pack(lg_engine *e, LgSlot &t)
 /* One step on slot k, asynchronous: [H2D of the staged inputs,] kernels R A B C on the analysis stream, D E [and the D2H of the packed
  * frames] on the quantiser stream.  nframes = max over streams of the slot's frame counts.  with_copies = 0: the bench's device-only step
  * on what a previous lg_engine_submit left in device memory. */
-static int lg_submit(lg_engine *e, int k, int nframes, int use_float, int with_copies)
+static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 window, 1 the resampler's floats, 2 native types */, int with_copies)
 {
     if (k < 0 || k >= LG_SLOTS || nframes < 1 || nframes > e->F) return -1;
     LgDeviceScope dev(e->device);
@@ -468,7 +507,8 @@ static int lg_submit(lg_engine *e, int k, int nframes, int use_float, int with_c
 #endif
     if (e->hcfg.resample) {
         if (with_copies) {
-            LG_COPY_H2D(e->d_raw, t.h_raw, S * 2 * e->raw_stride * sizeof(float), e->stream);
+            LG_COPY_H2D(e->d_raw, t.h_raw, S * 2 * e->raw_stride * (size_t) e->raw_esz, e->stream);
+            LG_COPY_H2D(e->d_kind, t.h_kind, S * sizeof(LgPcmKind), e->stream);
             if (t.chunk_cap == e->chunk_cap) LG_COPY_H2D(e->d_rsc, t.h_rsc, S * e->chunk_cap * sizeof(LgRsChunk), e->stream);
             else for (size_t s = 0; s < S; s++) LG_COPY_H2D(e->d_rsc + s * e->chunk_cap, t.h_rsc + s * t.chunk_cap, (size_t) t.chunk_cap * sizeof(LgRsChunk), e->stream);
             LG_COPY_H2D(e->d_rss, t.h_rss, S * sizeof(LgRsStream), e->stream);
@@ -478,30 +518,32 @@ static int lg_submit(lg_engine *e, int k, int nframes, int use_float, int with_c
 #ifndef LG_EMULATE
         cudaEventRecord(t.ev[8], e->stream);
 #endif
-        LG_LAUNCH(lg_kernel_resample, (int) S * tiles, 256, 0, e->stream, e->dcfg, e->d_raw, (int) e->raw_stride, e->d_rsc, e->chunk_cap, e->d_rss,
+        LG_LAUNCH(lg_kernel_resample, (int) S * tiles, 256, 0, e->stream, e->dcfg, e->d_raw, (int) e->raw_stride, e->raw_esz, e->d_kind, e->d_rsc, e->chunk_cap, e->d_rss,
                   e->d_pcmf, (int) e->pcm_stride, tiles);
 #ifndef LG_EMULATE
         cudaEventRecord(t.ev[9], e->stream);
 #endif
         e->launches += 1;
-        use_float = 1;
+        mode = 1;
     }
+    else if (mode == 1) return -1;                            /* floats come from kernel R only */
     else if (with_copies) {
-        if (use_float && !t.h_pcmf) return -1;
+        if (mode == 2 && !t.h_pcmn) return -1;
         /* samples [0, 576*mgr*nframes + halo) of every channel row */
         size_t const n = (size_t) 576 * mgr * nframes + LG_PCM_HALO;
-        size_t const esz = use_float ? sizeof(float) : sizeof(int16_t);
-        char *dst = use_float ? (char *) e->d_pcmf : (char *) e->d_pcm16;
-        const char *src = use_float ? (const char *) t.h_pcmf : (const char *) t.h_pcm16;
+        size_t const esz = mode == 2 ? (size_t) e->pcmn_esz : sizeof(int16_t);
+        char *dst = mode == 2 ? e->d_pcmn : (char *) e->d_pcm16;
+        const char *src = mode == 2 ? t.h_pcmn : (const char *) t.h_pcm16;
 #ifdef LG_EMULATE
         for (size_t r = 0; r < S * 2; r++) memcpy(dst + r * e->pcm_stride * esz, src + r * e->pcm_stride * esz, n * esz);
 #else
         LG_CHECK(cudaMemcpy2DAsync(dst, e->pcm_stride * esz, src, e->pcm_stride * esz, n * esz, S * 2, cudaMemcpyHostToDevice, e->stream));
 #endif
+        if (mode == 2) LG_COPY_H2D(e->d_kind, t.h_kind, S * sizeof(LgPcmKind), e->stream);
     }
     if (with_copies) LG_COPY_H2D(t.d_nfr, t.h_nfr, S * sizeof(int), e->stream);
-    const int16_t *p16 = use_float ? NULL : e->d_pcm16;
-    const float *pf = use_float ? e->d_pcmf : NULL;
+    const int16_t *p16 = mode == 0 ? e->d_pcm16 : NULL;
+    const float *pf = mode == 1 ? e->d_pcmf : NULL;
     int const nslot = mgr * nframes + 1;
 #ifndef LG_EMULATE
     /* Start gate: kernel A of this step may not reach the device before kernel D of the step before it (the other slot) has been launched.
@@ -512,7 +554,7 @@ static int lg_submit(lg_engine *e, int k, int nframes, int use_float, int with_c
     cudaEventRecord(t.ev[0], e->stream);
 #endif
     LG_LAUNCH(lg_kernel_analysis, (int) S * nslot, 128, sizeof(LgSmemA), e->stream,
-              e->dcfg, p16, (int) e->pcm_stride, pf, e->d_sb, e->d_ana, t.d_nfr, 2 * (int) F + 1, 0, nslot);
+              e->dcfg, p16, (int) e->pcm_stride, pf, e->d_pcmn, e->pcmn_esz, e->d_kind, e->d_sb, e->d_ana, t.d_nfr, 2 * (int) F + 1, 0, nslot);
 #ifndef LG_EMULATE
     cudaEventRecord(t.ev[1], e->stream);
 #endif
@@ -539,8 +581,8 @@ static int lg_submit(lg_engine *e, int k, int nframes, int use_float, int with_c
     t.in_flight = 1; t.nframes = nframes;
     return 0;
 }
-extern "C" int lg_engine_submit(lg_engine *e, int k, int nframes, int use_float) { return lg_submit(e, k, nframes, use_float, 1); }
-extern "C" int lg_engine_run_device(lg_engine *e, int k, int nframes, int use_float) { return lg_submit(e, k, nframes, use_float, 0); }
+extern "C" int lg_engine_submit(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 1); }
+extern "C" int lg_engine_run_device(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 0); }
 
 /* block until slot k's step has finished and its results are in the slot's host buffers; fills the kernel times of that step */
 extern "C" int lg_engine_wait(lg_engine *e, int k)

@@ -47,12 +47,12 @@ lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int max_frames, i
 void lg_engine_destroy(lg_engine *e);
 int  lg_engine_reset_streams(lg_engine *e, int first, int count);
 int  lg_engine_end_reservoir(lg_engine *e, const int *streams, const int *ancillary_flags, int n);
-int  lg_engine_need_float_pcm(lg_engine *e);
+int  lg_engine_need_native_pcm(lg_engine *e, int esz);
 int  lg_engine_reserve_chunks(lg_engine *e, int slot, int per_stream);
 int  lg_engine_slots(const lg_engine *e);
 int  lg_engine_device(const lg_engine *e);
-int  lg_engine_submit(lg_engine *e, int slot, int nframes, int use_float);
-int  lg_engine_run_device(lg_engine *e, int slot, int nframes, int use_float);
+int  lg_engine_submit(lg_engine *e, int slot, int nframes, int mode);      /* mode: 0 int16 window, 1 resampled, 2 native sample types */
+int  lg_engine_run_device(lg_engine *e, int slot, int nframes, int mode);
 int  lg_engine_wait(lg_engine *e, int slot);
 int  lg_engine_in_flight(const lg_engine *e, int slot);
 int  lg_engine_mark(lg_engine *e, int which);
@@ -65,9 +65,13 @@ size_t lg_engine_raw_stride(const lg_engine *e);
 size_t lg_engine_pay_stride(const lg_engine *e);
 /* slot buffers (pinned host memory) */
 int16_t *lg_engine_host_pcm16(lg_engine *e, int slot);
-float *lg_engine_host_pcmf(lg_engine *e, int slot);
+void *lg_engine_host_pcmn(lg_engine *e, int slot);
+LgPcmKind *lg_engine_host_kinds(lg_engine *e, int slot);
+int  lg_engine_native_esz(const lg_engine *e);
 int *lg_engine_host_nfr(lg_engine *e, int slot);
-float *lg_engine_host_raw(lg_engine *e, int slot);
+void *lg_engine_host_raw(lg_engine *e, int slot);
+int  lg_engine_raw_esz(const lg_engine *e);
+int  lg_engine_need_raw(lg_engine *e, int esz);
 LgRsChunk *lg_engine_host_chunks(lg_engine *e, int slot);
 int *lg_engine_host_rs_counts(lg_engine *e, int slot);          /* per stream: { nchunks, win_n } */
 int  lg_engine_chunk_cap(const lg_engine *e, int slot);

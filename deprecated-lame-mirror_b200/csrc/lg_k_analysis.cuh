@@ -314,7 +314,8 @@ __device__ __forceinline__ void lg_partition_and_spread(const LgDevCfg *__restri
 
 __global__ void __launch_bounds__(128)
 lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__ pcm, int pcm_stride /* samples per channel */,
-                   const float *__restrict__ pcmf, float *__restrict__ sb, LgAnalysis *__restrict__ ana,
+                   const float *__restrict__ pcmf, const void *__restrict__ pcmn, int pcmn_esz /* bytes per element of a row of pcmn */,
+                   const LgPcmKind *__restrict__ kinds, float *__restrict__ sb, LgAnalysis *__restrict__ ana,
                    const int *__restrict__ nfr, int nslots /* 2F+1, F = frames per launch */, int slot0, int cnt /* this launch: slots slot0 .. slot0+cnt-1 */)
 {
     LG_DYN_SMEM(LgSmemA, sm);
@@ -338,12 +339,35 @@ lg_kernel_analysis(const LgDevCfg *__restrict__ cfg, const int16_t *__restrict__
                 sm->pcm[1][LG_PADIDX(i)] = v;
             }
         }
-        else {      /* samples already converted by the host (float/int32/double entry points, lame.c:1803-1834) */
+        else if (pcmf) {      /* the resampler's output (kernel R) */
             const float *p0 = pcmf + (size_t) stream * 2 * pcm_stride + 576 * slot;
             const float *p1 = p0 + pcm_stride;
             for (int i = tid; i < LG_GR_SPAN; i += 128) {
                 sm->pcm[0][LG_PADIDX(i)] = p0[i];
                 sm->pcm[1][LG_PADIDX(i)] = p1[i];
+            }
+        }
+        else {                /* the caller's own sample type, every stream its own (lame.c:1803-1834): convert to sample_t, then the matrix */
+            LgPcmKind const kd = kinds[stream];
+            float const s = kd.scale;                                /* lame.c:1797-1800: m = s * pcm_transform, in float */
+            float const n00 = s * m00, n01 = s * m01, n10 = s * m10, n11 = s * m11;
+            const char *r0 = (const char *) pcmn + (size_t) stream * 2 * pcm_stride * pcmn_esz;
+            const char *r1 = r0 + (size_t) pcm_stride * pcmn_esz;
+            for (int i = tid; i < LG_GR_SPAN; i += 128) {
+                int const q = 576 * slot + i;
+                float xl, xr;
+                switch (kd.kind) {
+                case LG_PCM_S16: xl = (float) ((const int16_t *) r0)[q]; xr = (float) ((const int16_t *) r1)[q]; break;
+                case LG_PCM_S32: xl = (float) ((const int32_t *) r0)[q]; xr = (float) ((const int32_t *) r1)[q]; break;
+                case LG_PCM_S64: xl = (float) ((const long long *) r0)[q]; xr = (float) ((const long long *) r1)[q]; break;
+                case LG_PCM_F64: xl = (float) ((const double *) r0)[q]; xr = (float) ((const double *) r1)[q]; break;
+                default:         xl = ((const float *) r0)[q]; xr = ((const float *) r1)[q]; break;
+                }
+                if (kd.kind == LG_PCM_DONE) { sm->pcm[0][LG_PADIDX(i)] = xl; sm->pcm[1][LG_PADIDX(i)] = xr; }
+                else {
+                    sm->pcm[0][LG_PADIDX(i)] = xl * n00 + xr * n01;
+                    sm->pcm[1][LG_PADIDX(i)] = xl * n10 + xr * n11;
+                }
             }
         }
     }

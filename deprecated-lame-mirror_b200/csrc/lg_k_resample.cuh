@@ -9,8 +9,10 @@
 // a list of *chunks* (one per reference call).  Every output sample is then independent: thread = one sample of the
 // launch's PCM window, both channels, so the kernel is a plain 32/33-tap FIR with a per-sample filter choice.
 //
-//   raw   f32 [S][2][raw_stride]   the stream's input samples (already through pcm_transform), element 0 = the
-//                                  oldest sample any chunk of this launch can touch (zeros before the stream began)
+//   raw   [S][2][raw_stride] elements of raw_esz bytes: the stream's input samples in the caller's own sample type
+//                                  (kinds[stream]; converted and put through s * pcm_transform here, lame.c:1797-1834, or floats
+//                                  the host already transformed for a stream that mixed types), element 0 = the oldest sample any
+//                                  chunk of this launch can touch (zeros before the stream began)
 //   chunk LgRsChunk [S][chunk_cap] chunks overlapping the window, ascending; positions relative to the window/raw
 //   out   f32 [S][2][pcm_stride]   the float PCM window kernel A reads (timeline samples, zero where no chunk covers)
 //
@@ -23,7 +25,7 @@ typedef struct {
 } LgRsStream;
 
 __global__ void __launch_bounds__(256)
-lg_kernel_resample(const LgDevCfg *__restrict__ cfg, const float *__restrict__ raw, int raw_stride,
+lg_kernel_resample(const LgDevCfg *__restrict__ cfg, const void *__restrict__ raw, int raw_stride, int raw_esz, const LgPcmKind *__restrict__ kinds,
                    const LgRsChunk *__restrict__ chunks, int chunk_cap, const LgRsStream *__restrict__ rss,
                    float *__restrict__ out, int pcm_stride, int tiles)
 {
@@ -55,11 +57,28 @@ lg_kernel_resample(const LgDevCfg *__restrict__ cfg, const float *__restrict__ r
         t = t + (float) bpc;
         int const joff = (int) floor((double) t + .5);
         const float *f = cfg->rs_filt + joff * LG_RS_TAPS;
-        const float *r0 = raw + (size_t) stream * 2 * raw_stride + c.in_base + j - filter_l / 2, *r1 = r0 + raw_stride;
+        LgPcmKind const kd = kinds[stream];
+        float const sc = kd.scale;
+        float const n00 = sc * cfg->pcm_transform[0][0], n01 = sc * cfg->pcm_transform[0][1];
+        float const n10 = sc * cfg->pcm_transform[1][0], n11 = sc * cfg->pcm_transform[1][1];
+        const char *b0 = (const char *) raw + (size_t) stream * 2 * raw_stride * raw_esz, *b1 = b0 + (size_t) raw_stride * raw_esz;
+        long const at = (long) c.in_base + j - filter_l / 2;
         for (int i = 0; i <= filter_l; ++i) {
             float const fi = f[i];
-            x0 = x0 + r0[i] * fi;
-            x1 = x1 + r1[i] * fi;
+            float xl, xr;
+            switch (kd.kind) {
+            case LG_PCM_S16: xl = (float) ((const int16_t *) b0)[at + i]; xr = (float) ((const int16_t *) b1)[at + i]; break;
+            case LG_PCM_S32: xl = (float) ((const int32_t *) b0)[at + i]; xr = (float) ((const int32_t *) b1)[at + i]; break;
+            case LG_PCM_S64: xl = (float) ((const long long *) b0)[at + i]; xr = (float) ((const long long *) b1)[at + i]; break;
+            case LG_PCM_F64: xl = (float) ((const double *) b0)[at + i]; xr = (float) ((const double *) b1)[at + i]; break;
+            default:         xl = ((const float *) b0)[at + i]; xr = ((const float *) b1)[at + i]; break;
+            }
+            if (kd.kind != LG_PCM_DONE) {
+                float const u = xl * n00 + xr * n01, v = xl * n10 + xr * n11;
+                xl = u; xr = v;
+            }
+            x0 = x0 + xl * fi;
+            x1 = x1 + xr * fi;
         }
     }
     o0[w] = x0;

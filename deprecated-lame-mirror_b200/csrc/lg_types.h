@@ -42,6 +42,11 @@
 #define LG_GR_SPAN 1328                 /* samples one granule's analysis touches: [576g+576, 576g+1904) */
 
 enum { LG_NORM = 0, LG_START = 1, LG_SHORT = 2, LG_STOP = 3 };
+/* What a stream's row of the native PCM window holds (lame.c:1803-1834 COPY_AND_TRANSFORM's T) and the entry point's normalisation
+ * factor s (lame.c:1884-1960); kernel A converts to sample_t and applies s * pcm_transform.  LG_PCM_DONE: floats the host has already
+ * transformed (a stream whose calls mixed sample types). */
+enum { LG_PCM_S16 = 0, LG_PCM_DONE = 1, LG_PCM_S32 = 2, LG_PCM_F32 = 3, LG_PCM_S64 = 4, LG_PCM_F64 = 5 };
+typedef struct { int kind; float scale; } LgPcmKind;
 enum { LG_STEREO = 0, LG_JOINT = 1, LG_DUAL = 2, LG_MONO = 3, LG_MODE_NOT_SET = 4 };
 
 /* partition-band constants (reference PsyConst_CB2SB_t, util.h:188) */
