@@ -99,10 +99,10 @@ struct lg_engine {
     size_t raw_stride; int chunk_cap;
     char *d_raw; int raw_esz; LgRsChunk *d_rsc; LgRsStream *d_rss;
     LgSlot slot[LG_SLOTS];
-    /* two CUDA streams: `stream` carries the copies in and the stateless/scan kernels (R, A, B, C), `stream2` the quantiser, the packer
-     * and the copies out (D, E); events order slot k's D behind its C and its next A-B-C behind its previous D2H.  Nothing waits
-     * inside a kernel. */
-    lgStream_t stream, stream2;
+    /* three CUDA streams: `stream` carries the copies in and the stateless/scan kernels (R, A, B, C), `stream2` the quantiser (D) and
+     * `stream3` the packer and the copies out (E, D2H), so that the next step's kernel D follows this step's directly; events order slot
+     * k's D behind its C, its E behind its D, and its next A-B-C behind its previous D2H.  Nothing waits inside a kernel. */
+    lgStream_t stream, stream2, stream3;
     int dense;                        /* more than four streams per SM: the one-warp kernel D in its seven-CTAs-per-SM build */
     int group_nw;                     /* > 0: kernel D in its group form (lg_k_quantg.cuh) with this many warps per granule.channel */
     int gate;                         /* kernel A of a step waits for the launch of kernel D of the step before (lg_submit) */
@@ -164,6 +164,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
 #ifndef LG_EMULATE
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->stream2) cudaStreamSynchronize(e->stream2);
+    if (e->stream3) cudaStreamSynchronize(e->stream3);
 #endif
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_pcmn); lg_dev_free(e->d_kind); lg_dev_free(e->d_sb); lg_dev_free(e->d_ana);
     lg_dev_free(e->d_state); lg_dev_free(e->d_state0);
@@ -182,6 +183,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     for (int i = 0; i < 2; i++) if (e->ev_mark[i]) cudaEventDestroy(e->ev_mark[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->stream3) cudaStreamDestroy(e->stream3);
 #endif
     free(e);
 }
@@ -342,6 +344,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+        if (cudaStreamCreateWithPriority(&e->stream3, cudaStreamNonBlocking, hi) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     }
     for (int k = 0; k < LG_SLOTS; k++) for (int i = 0; i < 10; i++) cudaEventCreate(&e->slot[k].ev[i]);
     for (int i = 0; i < 2; i++) cudaEventCreate(&e->ev_mark[i]);
@@ -360,6 +363,14 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     /* The shared-memory carve-out is left to the driver.  Round 1 forced the largest one on every kernel so that a kernel could be placed
      * next to a resident one of the other stream without reconfiguring the SM; with whole steps overlapping (not pieces waiting inside
      * kernel D) that measures worse: 8.4 against 7.7 ms per pipelined 512 x 8 step - kernel D loses L1 for its tables. */
+    if (const char *co = getenv("LAMEGPU_CARVEOUT")) {           /* experiment knob: one shared-memory carve-out (percent) for every kernel */
+        int const pct = atoi(co);
+        cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(lg_kernel_scan, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(lg_kernel_mdct, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(lg_kernel_quantg<2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(lg_kernel_pack, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    }
     if (getenv("LAMEGPU_DEBUG_OCC")) {
         int nb = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lg_kernel_quantg<2>, 128, sizeof(LgSmemG<2>));
@@ -482,10 +493,11 @@ static void lg_launch_quant_pack(lg_engine *e, LgSlot &t)
     }
 #ifndef LG_EMULATE
     cudaEventRecord(t.ev[5], e->stream2);
+    cudaStreamWaitEvent(e->stream3, t.ev[5], 0);
 #endif
-    LG_LAUNCH(lg_kernel_pack, S * F, 128, sizeof(LgSmemE), e->stream2, e->dcfg, t.d_gout, t.d_fout, t.d_pay, (int) e->pay_stride, t.d_hdr, t.d_nfr, F, 0, F);
+    LG_LAUNCH(lg_kernel_pack, S * F, 128, sizeof(LgSmemE), e->stream3, e->dcfg, t.d_gout, t.d_fout, t.d_pay, (int) e->pay_stride, t.d_hdr, t.d_nfr, F, 0, F);
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[6], e->stream2);
+    cudaEventRecord(t.ev[6], e->stream3);
 #endif
     e->launches += 2;
 }
@@ -570,12 +582,12 @@ static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 windo
     e->launches += 3;
     lg_launch_quant_pack(e, t);
     if (with_copies) {
-        LG_COPY_D2H(t.h_fout, t.d_fout, S * F * sizeof(LgFrameOut), e->stream2);
-        LG_COPY_D2H(t.h_pay, t.d_pay, S * e->pay_stride, e->stream2);
-        LG_COPY_D2H(t.h_hdr, t.d_hdr, S * F * LG_HDR_STRIDE, e->stream2);
+        LG_COPY_D2H(t.h_fout, t.d_fout, S * F * sizeof(LgFrameOut), e->stream3);
+        LG_COPY_D2H(t.h_pay, t.d_pay, S * e->pay_stride, e->stream3);
+        LG_COPY_D2H(t.h_hdr, t.d_hdr, S * F * LG_HDR_STRIDE, e->stream3);
     }
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[7], e->stream2);
+    cudaEventRecord(t.ev[7], e->stream3);
     if (cudaGetLastError() != cudaSuccess) { fprintf(stderr, "lamegpu: kernel launch failed\n"); return -1; }
 #endif
     t.in_flight = 1; t.nframes = nframes;
@@ -611,7 +623,7 @@ extern "C" int lg_engine_mark(lg_engine *e, int which)
 {
 #ifndef LG_EMULATE
     LgDeviceScope dev(e->device);
-    LG_CHECK(cudaEventRecord(e->ev_mark[which ? 1 : 0], which ? e->stream2 : e->stream));
+    LG_CHECK(cudaEventRecord(e->ev_mark[which ? 1 : 0], which ? e->stream3 : e->stream));
 #else
     (void) e; (void) which;
 #endif

@@ -34,10 +34,17 @@ struct __attribute__((aligned(16))) LgGBand {            /* band-level work set:
 /* experiment: the own lines stay in shared memory (every thread its own elements, no extra barriers) and the loops over them are
  * rolled - smaller code (the search loop has to fit the 32 KB instruction cache) and fewer registers against less ILP */
 #define LG_G_UNROLL _Pragma("unroll 1")
+#ifndef LG_G_HOT_UNROLL
+#define LG_G_HOT_UNROLL 1
+#endif
+#define LG_G_PRAGMA_(x) _Pragma(#x)
+#define LG_G_PRAGMA(x) LG_G_PRAGMA_(x)
+#define LG_G_UNROLL_HOT LG_G_PRAGMA(unroll LG_G_HOT_UNROLL)
 template <class T, int NT> struct LgGOwn { T *base; int g; __device__ __forceinline__ T &operator[](int j) const { return base[g + NT * j]; } };
 template <int NT> struct LgGOwnSfb { const uint8_t *base; int g; __device__ __forceinline__ int operator[](int j) const { return base[g + NT * j]; } };
 #else
 #define LG_G_UNROLL _Pragma("unroll")
+#define LG_G_UNROLL_HOT _Pragma("unroll")
 #endif
 template <int NW> struct __attribute__((aligned(16))) LgGChan : LgGBand {      /* the base is warp 0's replica */
     float xr[576], sq[576];
@@ -141,7 +148,7 @@ __device__ __forceinline__ int lg_g_count_bits(const LgDevCfg *__restrict__ c, L
         __syncwarp();
         float const compareval0 = (1.0f - 0.4054f) / istep;
         const float *adj = c->adj43asm;
-LG_G_UNROLL
+LG_G_UNROLL_HOT
         for (int j = 0; j < NP; j++) {
             int const P = id.g + NT * j, i = 2 * P;
             if (P < plim) {
@@ -239,7 +246,7 @@ LG_G_UNROLL
         }
     }
     int m0 = 0, m1 = 0, m2 = 0;
-LG_G_UNROLL
+LG_G_UNROLL_HOT
     for (int j = 0; j < NP; j++) {
         int const i = 2 * (id.g + NT * j);
         if (i < bigv) {
@@ -270,7 +277,7 @@ LG_G_UNROLL
     int const b0 = __shfl_sync(LG_FULL, R.base, 0), b1 = __shfl_sync(LG_FULL, R.base, 1), b2 = __shfl_sync(LG_FULL, R.base, 2);
     unsigned acc0 = 0, acc1 = 0, acc2 = 0, n15 = 0;
     const uint32_t *pk = c->huff_pk;
-LG_G_UNROLL
+LG_G_UNROLL_HOT
     for (int j = 0; j < NP; j++) {
         int const i = 2 * (id.g + NT * j);
         if (i < bigv) {
@@ -349,7 +356,7 @@ __device__ __forceinline__ void lg_g_calc_noise(const LgDevCfg *__restrict__ c, 
     __syncwarp();
     if (need) {
         int const plim = 32 * qc.jn;
-LG_G_UNROLL
+LG_G_UNROLL_HOT
         for (int j = 0; j < NP; j++) {
             int const P = id.g + NT * j, i = 2 * P;
             if (P < plim) {
@@ -439,7 +446,7 @@ __device__ __forceinline__ float lg_g_scale_bands(LgGBand *w, float xm_warp, int
         }
     }
     int const plim = 32 * jn;
-LG_G_UNROLL
+LG_G_UNROLL_HOT
     for (int j = 0; j < NP; j++) {
         if (id.g + NT * j < plim) {
             float const f = fac[sfbp[j]];
@@ -885,8 +892,13 @@ __device__ __noinline__ void lg_g_frame_end(const LgDevCfg *__restrict__ cfg, Lg
 #ifndef LG_G_MINBLOCKS
 #define LG_G_MINBLOCKS(NW) 4
 #endif
+#ifdef LG_G_MAXNREG
+#define LG_G_BOUNDS(NW) __maxnreg__(LG_G_MAXNREG)
+#else
+#define LG_G_BOUNDS(NW) __launch_bounds__(64 * NW, LG_G_MINBLOCKS(NW))
+#endif
 template <int NW>
-__global__ void __launch_bounds__(64 * NW, LG_G_MINBLOCKS(NW))
+__global__ void LG_G_BOUNDS(NW)
 lg_kernel_quantg(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in, const LgPsyOut *__restrict__ psy, const LgFrameCtl *__restrict__ frm,
                  LgGranuleOut *__restrict__ gout, LgFrameOut *__restrict__ fout, LgStreamState *__restrict__ state, const int *__restrict__ nfr, int nframes)
 {
