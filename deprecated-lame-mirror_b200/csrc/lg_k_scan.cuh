@@ -23,6 +23,11 @@ struct LgSmemB {
     float frame_tot[2][4];
     int   frame_bt[2][2];
     float bcast[4];
+    /* convert_partition2scalefac's walk over the partitions is fixed by the band tables: where every scalefactor band's sum starts and
+     * ends, so that the bands can be summed side by side (lg_p2s_plan / lg_p2s_band); one plan each for long, long->short, short */
+    uint8_t p2s_prev[3][LG_SBMAX_L], p2s_first[3][LG_SBMAX_L], p2s_cur[3][LG_SBMAX_L], p2s_kind[3][LG_SBMAX_L];
+    LgXmin pe_en[4], pe_thm[4];       /* the delayed ratios handed to the caller, kept for the perceptual entropy */
+    float log_table[513];             /* LgDevCfg.log_table (util.c:977 fast_log2) */
     /* the stream's carried state and the current granule's analysis record live in shared memory while the warp walks
      * the stream: the scan is a chain of dependent steps, so every global load would be paid in full latency */
     LgStreamState st;
@@ -52,8 +57,52 @@ __device__ __forceinline__ void lg_partition2sfb(const LgBands *__restrict__ gd,
     for (; sb < n; ++sb) { enn_out[sb * out_stride] = 0; thm_out[sb * out_stride] = 0; }
 }
 
+/* The same sums, one scalefactor band at a time.  The serial walk above visits the partitions in a way that depends only on bo[] and
+ * npart: band sb starts from the boundary partition of the band before it (weight 1 - bo_weight[sb-1]), adds the whole partitions
+ * [first, cur) one by one in ascending order and ends with bo_weight[sb] of partition cur - or, for the band that reaches npart, without
+ * that last term; the bands after it are zero.  lg_p2s_plan replays the integer part of the walk once per kernel; lg_p2s_band then
+ * does the floating-point part of one band in exactly the order of the serial loop, so the bands can go to different lanes. */
+enum { LG_P2S_NORMAL = 0, LG_P2S_LAST = 1, LG_P2S_ZERO = 2 };
+__device__ __forceinline__ void lg_p2s_plan(const LgBands *__restrict__ gd, uint8_t *prev, uint8_t *first, uint8_t *cur, uint8_t *kind)
+{
+    int const n = gd->n_sb, npart = gd->npart;
+    int sb, b;
+    for (sb = b = 0; sb < n; ++b, ++sb) {
+        int const bo_sb = gd->bo[sb];
+        int const b_lim = bo_sb < npart ? bo_sb : npart;
+        prev[sb] = (uint8_t) (b > 0 ? b - 1 : 0);
+        first[sb] = (uint8_t) b;
+        if (b < b_lim) b = b_lim;
+        cur[sb] = (uint8_t) b;
+        if (b >= npart) { kind[sb] = LG_P2S_LAST; ++sb; break; }
+        kind[sb] = LG_P2S_NORMAL;
+    }
+    for (; sb < n; ++sb) { prev[sb] = first[sb] = cur[sb] = 0; kind[sb] = LG_P2S_ZERO; }
+}
+__device__ __forceinline__ void lg_p2s_band(const LgBands *__restrict__ gd, const uint8_t *prev, const uint8_t *first, const uint8_t *cur,
+                                            const uint8_t *kind, const float *eb, const float *thr, int sb, float *enn_out, float *thm_out)
+{
+    int const k = kind[sb];
+    float enn = 0.0f, thmm = 0.0f;
+    if (k != LG_P2S_ZERO) {
+        if (sb > 0) {
+            float const w_next = 1.0f - gd->bo_weight[sb - 1];
+            enn = w_next * eb[prev[sb]];
+            thmm = w_next * thr[prev[sb]];
+        }
+        int const c = cur[sb];
+        for (int b = first[sb]; b < c; b++) { enn += eb[b]; thmm += thr[b]; }
+        if (k == LG_P2S_NORMAL) {
+            float const w_curr = gd->bo_weight[sb];
+            enn += w_curr * eb[c];
+            thmm += w_curr * thr[c];
+        }
+    }
+    *enn_out = enn; *thm_out = thmm;
+}
+
 /* psymodel.c:503 pecalc_l / :458 pecalc_s */
-__device__ __forceinline__ float lg_pecalc_l(const LgDevCfg *__restrict__ c, const LgXmin *en, const LgXmin *thm, float masking_lower)
+__device__ __forceinline__ float lg_pecalc_l(const float *log_table, const LgXmin *en, const LgXmin *thm, float masking_lower)
 {
     const float regcoef_l[21] = { 6.8, 5.8, 5.8, 6.4, 6.5, 9.9, 12.1, 14.4, 15, 18.9, 21.6, 26.9, 34.2, 40.2,
         46.8, 56.5, 60.7, 73.9, 85.7, 93.4, 126.1 };
@@ -65,13 +114,13 @@ __device__ __forceinline__ float lg_pecalc_l(const LgDevCfg *__restrict__ c, con
             float const e = en->l[sb];
             if (e > x) {
                 if (e > x * 1e10f) pe_l = (float) (pe_l + regcoef_l[sb] * (10.0f * LG_LOG10_D));
-                else pe_l = (float) (pe_l + regcoef_l[sb] * LG_FAST_LOG10_D(c->log_table, e / x));
+                else pe_l = (float) (pe_l + regcoef_l[sb] * LG_FAST_LOG10_SMEM_D(log_table, e / x));
             }
         }
     }
     return pe_l;
 }
-__device__ __forceinline__ float lg_pecalc_s(const LgDevCfg *__restrict__ c, const LgXmin *en, const LgXmin *thm, float masking_lower)
+__device__ __forceinline__ float lg_pecalc_s(const float *log_table, const LgXmin *en, const LgXmin *thm, float masking_lower)
 {
     const float regcoef_s[12] = { 11.8, 13.6, 17.2, 32, 46.5, 51.3, 57.5, 67.1, 71.5, 84.6, 97.6, 130 };
     float pe_s = 1236.28f / 4;
@@ -83,7 +132,7 @@ __device__ __forceinline__ float lg_pecalc_s(const LgDevCfg *__restrict__ c, con
                 float const e = en->s[sb][sblock];
                 if (e > x) {
                     if (e > x * 1e10f) pe_s = (float) (pe_s + regcoef_s[sb] * (10.0f * LG_LOG10_D));
-                    else pe_s = (float) (pe_s + regcoef_s[sb] * LG_FAST_LOG10_D(c->log_table, e / x));
+                    else pe_s = (float) (pe_s + regcoef_s[sb] * LG_FAST_LOG10_SMEM_D(log_table, e / x));
                 }
             }
         }
@@ -239,6 +288,11 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
         int *dst = reinterpret_cast<int *>(st);
         for (int i = lane; i < (int) (sizeof(LgStreamState) / 4); i += 32) dst[i] = src[i];
     }
+    for (int i = lane; i < 513; i += 32) sm->log_table[i] = cfg->log_table[i];
+    if (lane < 3) {
+        const LgBands *g = lane == 0 ? &cfg->l : (lane == 1 ? &cfg->l2s : &cfg->s);
+        lg_p2s_plan(g, sm->p2s_prev[lane], sm->p2s_first[lane], sm->p2s_cur[lane], sm->p2s_kind[lane]);
+    }
     __syncwarp();
     const LgBands *gdl = &cfg->l, *gds = &cfg->s;
     int const nch = cfg->channels;
@@ -268,8 +322,11 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
         for (int i = lane; i < 4 * 39; i += 32) (&sm->last_thm_s[0][0][0])[i] = (&st->thm[i / 39].s[0][0])[i % 39];
         for (int i = lane; i < 4 * 61; i += 32) {
             int const chn = i / 61, k = i % 61;
-            ((float *) &P->en[chn])[k] = ((const float *) &st->en[chn])[k];
-            ((float *) &P->thm[chn])[k] = ((const float *) &st->thm[chn])[k];
+            float const e_old = ((const float *) &st->en[chn])[k], t_old = ((const float *) &st->thm[chn])[k];
+            ((float *) &P->en[chn])[k] = e_old;
+            ((float *) &P->thm[chn])[k] = t_old;
+            ((float *) &sm->pe_en[chn])[k] = e_old;
+            ((float *) &sm->pe_thm[chn])[k] = t_old;
         }
         __syncwarp();
         /* (c) attack detection, one lane per channel */
@@ -335,19 +392,20 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                 lg_ms_threshold(sm->eb, sm->thr, gdl->mld_cb[b], cfg->ath_cb_l[b], ath_factor, cfg->msfix, b);
             __syncwarp();
         }
-        /* (f) partitions -> scalefactor bands, long and long->short (psymodel.c:411, :421): 8 serial jobs on 8 lanes */
-        if (lane < 2 * n_chn_psy) {
-            int const chn = lane >> 1;
-            if ((lane & 1) == 0) lg_partition2sfb(gdl, sm->eb[chn], sm->thr[chn], st->en[chn].l, st->thm[chn].l, 1);
+        /* (f) partitions -> scalefactor bands, long and long->short (psymodel.c:411, :421): one job per channel and band, side by side */
+        for (int job = lane; job < n_chn_psy * (LG_SBMAX_L + LG_SBMAX_S); job += 32) {
+            int const chn = job / (LG_SBMAX_L + LG_SBMAX_S), q = job % (LG_SBMAX_L + LG_SBMAX_S);
+            float enn, thmm;
+            if (q < LG_SBMAX_L) {
+                lg_p2s_band(gdl, sm->p2s_prev[0], sm->p2s_first[0], sm->p2s_cur[0], sm->p2s_kind[0], sm->eb[chn], sm->thr[chn], q, &enn, &thmm);
+                st->en[chn].l[q] = enn; st->thm[chn].l[q] = thmm;
+            }
             else {
-                float enn[LG_SBMAX_S], thm[LG_SBMAX_S];
-                lg_partition2sfb(&cfg->l2s, sm->eb[chn], sm->thr[chn], enn, thm, 1);
-                for (int sb = 0; sb < LG_SBMAX_S; ++sb) {
-                    float const scale = (float) (1. / 64.f);
-                    float const tmp_enn = enn[sb];
-                    float const tmp_thm = thm[sb] * scale;
-                    for (int k = 0; k < 3; ++k) { st->en[chn].s[sb][k] = tmp_enn; st->thm[chn].s[sb][k] = tmp_thm; }
-                }
+                int const sb = q - LG_SBMAX_L;
+                lg_p2s_band(&cfg->l2s, sm->p2s_prev[1], sm->p2s_first[1], sm->p2s_cur[1], sm->p2s_kind[1], sm->eb[chn], sm->thr[chn], sb, &enn, &thmm);
+                float const scale = (float) (1. / 64.f);
+                float const tmp_thm = thmm * scale;
+                for (int k = 0; k < 3; ++k) { st->en[chn].s[sb][k] = enn; st->thm[chn].s[sb][k] = tmp_thm; }
             }
         }
         __syncwarp();
@@ -378,9 +436,11 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
                         lg_ms_threshold(sm->eb, sm->thr, gds->mld_cb[b], cfg->ath_cb_s[b], ath_factor, cfg->msfix, b);
                     __syncwarp();
                 }
-                if (lane < n_chn_psy) {
-                    int const ul = (lane & 1) ? ul1 : ul0;
-                    if (!ul) lg_partition2sfb(gds, sm->eb[lane], sm->thr[lane], &st->en[lane].s[0][sblock], &st->thm[lane].s[0][sblock], 3);
+                for (int job = lane; job < n_chn_psy * LG_SBMAX_S; job += 32) {
+                    int const chn = job / LG_SBMAX_S, sb = job % LG_SBMAX_S;
+                    int const ul = (chn & 1) ? ul1 : ul0;
+                    if (!ul) lg_p2s_band(gds, sm->p2s_prev[2], sm->p2s_first[2], sm->p2s_cur[2], sm->p2s_kind[2], sm->eb[chn], sm->thr[chn], sb,
+                                         &st->en[chn].s[sb][sblock], &st->thm[chn].s[sb][sblock]);
                 }
                 __syncwarp();
             }
@@ -439,8 +499,8 @@ lg_kernel_scan(const LgDevCfg *__restrict__ cfg, const LgAnalysis *__restrict__ 
             int type;
             if (lane > 1) type = (btd[0] == LG_SHORT || btd[1] == LG_SHORT) ? LG_SHORT : LG_NORM;
             else type = btd[lane];
-            float const v = (type == LG_SHORT) ? lg_pecalc_s(cfg, &P->en[lane], &P->thm[lane], qml)
-                                                : lg_pecalc_l(cfg, &P->en[lane], &P->thm[lane], qml);
+            float const v = (type == LG_SHORT) ? lg_pecalc_s(sm->log_table, &sm->pe_en[lane], &sm->pe_thm[lane], qml)
+                                                : lg_pecalc_l(sm->log_table, &sm->pe_en[lane], &sm->pe_thm[lane], qml);
             P->pe[lane] = v;
             sm->frame_pe[gr][lane] = v;
             sm->frame_tot[gr][lane] = P->tot_ener[lane];

@@ -241,7 +241,20 @@ __device__ __forceinline__ float lg_fast_log2(const float *__restrict__ log_tabl
     log2val += __ldg(&log_table[mantisse]) * (1.0f - partial) + __ldg(&log_table[mantisse + 1]) * partial;
     return log2val;
 }
+/* the same with the table in shared memory */
+__device__ __forceinline__ float lg_fast_log2_smem(const float *log_table, float x)
+{
+    int const fi = __float_as_int(x);
+    int mantisse = fi & 0x7fffff;
+    float log2val = (float) (((fi >> 23) & 0xFF) - 0x7f);
+    float partial = (float) (mantisse & ((1 << (23 - 9)) - 1));
+    partial *= 1.0f / ((1 << (23 - 9)));
+    mantisse >>= (23 - 9);
+    log2val += log_table[mantisse] * (1.0f - partial) + log_table[mantisse + 1] * partial;
+    return log2val;
+}
 /* util.h:96 FAST_LOG10 / FAST_LOG10_X are double-valued expressions */
+#define LG_FAST_LOG10_SMEM_D(tab, x) ((double) lg_fast_log2_smem(tab, x) * (LG_LOG2_D / LG_LOG10_D))
 #define LG_FAST_LOG10_D(tab, x) ((double) lg_fast_log2(tab, x) * (LG_LOG2_D / LG_LOG10_D))
 #define LG_FAST_LOG10_X_D(tab, x, y) ((double) lg_fast_log2(tab, x) * (LG_LOG2_D / LG_LOG10_D * (y)))
 

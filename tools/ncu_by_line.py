@@ -32,6 +32,7 @@ agg = {}
 ti = ts = 0
 stall_cols = [c for c in rows[0].keys() if c.startswith("stall_") and "Not Issued" not in c]
 for r in rows:
+    if not re.match(r"^(0x)?[0-9a-f]+$", r["Address"] or ""): break       # the next kernel's table
     off = int(r["Address"], 16) - a0
     key = off2line.get(off, ("?", 0))
     ie = int(r["Instructions Executed"] or 0); sm = int(r["# Samples"] or 0)
