@@ -10,5 +10,5 @@ ncu --set full --clock-control none --import-source on -k regex:lg_kernel_quantg
 ncu --set full --clock-control none --import-source on -k regex:"lg_kernel_analysis|lg_kernel_scan|lg_kernel_mdct|lg_kernel_pack" -s 24 -c 4 -f -o $O/r2_others python tools/kbench.py $L 512 8 2 > /dev/null 2>&1
 ls -la $O/*.ncu-rep
 for t in "512 32 1152" "512 32 2304" "64 64 1152" "1 256 1152"; do LAMEGPU_LANES=512 timeout 300 tests/c/bin/handles_mt $t 128 oracle/_ref/libmp3lame_ref.so 2>&1 | tail -1 | tee -a $O/handles.txt; done
-LAMEGPU_FULL_SWEEP=1 timeout 1200 python -m pytest tests/test_frontend_dropin.py -m gpu -x -q 2>&1 | tail -3 | tee $O/full_sweep.txt
+if [ -n "$FULL_SWEEP" ]; then LAMEGPU_FULL_SWEEP=1 timeout 1200 python -m pytest tests/test_frontend_dropin.py -m gpu -x -q 2>&1 | tail -3 | tee $O/full_sweep.txt; fi
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee $O/pytest_gpu.txt
