@@ -79,9 +79,10 @@ struct LgSlot {
     char *h_raw; LgRsChunk *h_rsc; LgRsStream *h_rss;      /* h_raw: the resampler's input, rows of raw_esz-byte elements in the stream's own sample type */
     int chunk_cap;
 #ifndef LG_EMULATE
+    cudaEvent_t evp[4][4];            /* per part of the analysis (lg_submit): 0 its kernel A done, 1 its kernel B starts, 2 B done, 3 C done */
     cudaEvent_t ev[10];               /* 0 start (analysis stream), 1 after A, 2 after B, 3 after C, 4 before D (quantiser stream), 5 after D, 6 after E, 7 results on the host, 8/9 around R */
 #endif
-    int in_flight, nframes;
+    int in_flight, nframes, parts;
     float ms[8];                      /* A, B, C, D, E, R, -, start of A to end of E */
 };
 
@@ -102,7 +103,8 @@ struct lg_engine {
     /* three CUDA streams: `stream` carries the copies in and the stateless/scan kernels (R, A, B, C), `stream2` the quantiser (D) and
      * `stream3` the packer and the copies out (E, D2H), so that the next step's kernel D follows this step's directly; events order slot
      * k's D behind its C, its E behind its D, and its next A-B-C behind its previous D2H.  Nothing waits inside a kernel. */
-    lgStream_t stream, stream2, stream3;
+    lgStream_t stream, stream2, stream3, stream4;
+    int ana_split;                    /* parts the analysis of a step is cut into along the frames (lg_submit) */
     int dense;                        /* more than four streams per SM: the one-warp kernel D in its seven-CTAs-per-SM build */
     int group_nw;                     /* > 0: kernel D in its group form (lg_k_quantg.cuh) with this many warps per granule.channel */
     int gate;                         /* kernel A of a step waits for the launch of kernel D of the step before (lg_submit) */
@@ -165,6 +167,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->stream2) cudaStreamSynchronize(e->stream2);
     if (e->stream3) cudaStreamSynchronize(e->stream3);
+    if (e->stream4) cudaStreamSynchronize(e->stream4);
 #endif
     lg_dev_free(e->dcfg); lg_dev_free(e->d_pcm16); lg_dev_free(e->d_pcmf); lg_dev_free(e->d_pcmn); lg_dev_free(e->d_kind); lg_dev_free(e->d_sb); lg_dev_free(e->d_ana);
     lg_dev_free(e->d_state); lg_dev_free(e->d_state0);
@@ -177,6 +180,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
         lg_host_free(t.h_raw); lg_host_free(t.h_rsc); lg_host_free(t.h_rss);
 #ifndef LG_EMULATE
         for (int i = 0; i < 10; i++) if (t.ev[i]) cudaEventDestroy(t.ev[i]);
+        for (int i = 0; i < 16; i++) if (t.evp[i / 4][i % 4]) cudaEventDestroy(t.evp[i / 4][i % 4]);
 #endif
     }
 #ifndef LG_EMULATE
@@ -184,6 +188,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
     if (e->stream3) cudaStreamDestroy(e->stream3);
+    if (e->stream4) cudaStreamDestroy(e->stream4);
 #endif
     free(e);
 }
@@ -198,6 +203,7 @@ extern "C" int lg_engine_reset_streams(lg_engine *e, int first, int count)
     memcpy(e->d_state + first, e->d_state0 + first, (size_t) count * sizeof(LgStreamState));
 #else
     LG_CHECK(cudaStreamSynchronize(e->stream2));
+    LG_CHECK(cudaStreamSynchronize(e->stream4));
     LG_CHECK(cudaMemcpyAsync(e->d_state + first, e->d_state0 + first, (size_t) count * sizeof(LgStreamState), cudaMemcpyDeviceToDevice, e->stream));
     LG_CHECK(cudaStreamSynchronize(e->stream));
 #endif
@@ -284,6 +290,8 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     }
 #endif
     e->gate = 1;
+    e->ana_split = 1;                      /* measured: 2 or 4 parts change nothing (6.39 / 6.42 / 6.39 ms per step): what stands behind kernel D is kernel A's own remainder */
+    if (const char *sp = getenv("LAMEGPU_ANA_SPLIT")) e->ana_split = atoi(sp) < 1 ? 1 : (atoi(sp) > 4 ? 4 : atoi(sp));
     if (const char *ga = getenv("LAMEGPU_GATE")) e->gate = atoi(ga) != 0;
     if (const char *ge = getenv("LAMEGPU_GROUP_NW")) e->group_nw = group_ok ? atoi(ge) : 0;
     if (e->group_nw < 0 || e->group_nw > 3 || e->group_nw == 1) e->group_nw = group_ok ? 2 : 0;
@@ -340,6 +348,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
     memcpy(e->dcfg, cfg, sizeof *cfg);
 #else
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+    if (cudaStreamCreateWithFlags(&e->stream4, cudaStreamNonBlocking) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     {   /* the quantiser is the critical path: its stream gets the highest priority, so its CTAs are placed before those of the next step's analysis */
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -347,6 +356,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
         if (cudaStreamCreateWithPriority(&e->stream3, cudaStreamNonBlocking, hi) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     }
     for (int k = 0; k < LG_SLOTS; k++) for (int i = 0; i < 10; i++) cudaEventCreate(&e->slot[k].ev[i]);
+    for (int k = 0; k < LG_SLOTS; k++) for (int i = 0; i < 16; i++) cudaEventCreate(&e->slot[k].evp[i / 4][i % 4]);
     for (int i = 0; i < 2; i++) cudaEventCreate(&e->ev_mark[i]);
     if (cudaMemcpy(e->dcfg, cfg, sizeof *cfg, cudaMemcpyHostToDevice) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     cudaFuncSetAttribute(lg_kernel_analysis, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sizeof(LgSmemA));
@@ -563,23 +573,40 @@ static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 windo
      * wave starts late by all of A's run time, so that the overlap gains nothing (step = sum of the kernels, measured).  With it D, on the
      * high-priority stream, fills every SM first and A runs in the room D's last, partial wave leaves (7.20 -> 6.57 ms per step at 512 x 8; LAMEGPU_GATE=0 switches it off). */
     if (e->gate) LG_CHECK(cudaStreamWaitEvent(e->stream, e->slot[k ^ 1].ev[4], 0));
+    LG_CHECK(cudaStreamWaitEvent(e->stream, e->slot[k ^ 1].ev[3], 0));     /* the step before has read the analysis records and subband samples */
     cudaEventRecord(t.ev[0], e->stream);
 #endif
-    LG_LAUNCH(lg_kernel_analysis, (int) S * nslot, 128, sizeof(LgSmemA), e->stream,
-              e->dcfg, p16, (int) e->pcm_stride, pf, e->d_pcmn, e->pcmn_esz, e->d_kind, e->d_sb, e->d_ana, t.d_nfr, 2 * (int) F + 1, 0, nslot);
+    /* The analysis is cut into parts along the frames: kernel A part by part on the analysis stream, kernels B and C of a part on a
+     * second stream behind that part's A - the scan (one warp per stream, all latency) of part p runs under kernel A of part p + 1, and
+     * only the last part's B and C are left standing behind A (and, in the pipeline, behind the end of the step before's kernel D). */
+    int const parts = nframes < e->ana_split ? nframes : e->ana_split;
+    t.parts = parts;
+    for (int p = 0; p < parts; p++) {
+        int const f0 = (int) ((long) nframes * p / parts), f1 = (int) ((long) nframes * (p + 1) / parts);
+        int const s0 = p == 0 ? 0 : 1 + mgr * f0, s1 = 1 + mgr * f1;        /* slot 0 = the granule before the launch */
+        LG_LAUNCH(lg_kernel_analysis, (int) S * (s1 - s0), 128, sizeof(LgSmemA), e->stream,
+                  e->dcfg, p16, (int) e->pcm_stride, pf, e->d_pcmn, e->pcmn_esz, e->d_kind, e->d_sb, e->d_ana, t.d_nfr, 2 * (int) F + 1, s0, s1 - s0);
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[1], e->stream);
+        cudaEventRecord(t.evp[p][0], e->stream);
+        if (p == parts - 1) cudaEventRecord(t.ev[1], e->stream);
+        LG_CHECK(cudaStreamWaitEvent(e->stream4, t.evp[p][0], 0));
+        cudaEventRecord(t.evp[p][1], e->stream4);
 #endif
-    LG_LAUNCH(lg_kernel_scan, (int) S, 32, sizeof(LgSmemB), e->stream, e->dcfg, e->d_ana, t.d_psy, t.d_frm, e->d_state, t.d_nfr, (int) F, 0, nframes);
+        LG_LAUNCH(lg_kernel_scan, (int) S, 32, sizeof(LgSmemB), e->stream4, e->dcfg, e->d_ana, t.d_psy, t.d_frm, e->d_state, t.d_nfr, (int) F, f0, f1);
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[2], e->stream);
+        cudaEventRecord(t.evp[p][2], e->stream4);
 #endif
-    LG_LAUNCH(lg_kernel_mdct, (int) S * mgr * nframes, 64, sizeof(LgSmemC), e->stream, e->dcfg, e->d_sb, t.d_psy, t.d_frm, t.d_xr, t.d_nfr, (int) F, 0, mgr * nframes);
+        LG_LAUNCH(lg_kernel_mdct, (int) S * mgr * (f1 - f0), 64, sizeof(LgSmemC), e->stream4, e->dcfg, e->d_sb, t.d_psy, t.d_frm, t.d_xr, t.d_nfr, (int) F,
+                  mgr * f0, mgr * (f1 - f0));
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[3], e->stream);
+        cudaEventRecord(t.evp[p][3], e->stream4);
+#endif
+        e->launches += 3;
+    }
+#ifndef LG_EMULATE
+    cudaEventRecord(t.ev[3], e->stream4);
     LG_CHECK(cudaStreamWaitEvent(e->stream2, t.ev[3], 0));
 #endif
-    e->launches += 3;
     lg_launch_quant_pack(e, t);
     if (with_copies) {
         LG_COPY_D2H(t.h_fout, t.d_fout, S * F * sizeof(LgFrameOut), e->stream3);
@@ -606,7 +633,12 @@ extern "C" int lg_engine_wait(lg_engine *e, int k)
 #ifndef LG_EMULATE
     LG_CHECK(cudaEventSynchronize(t.ev[7]));
     static const int first[5] = { 0, 1, 2, 4, 5 };
-    for (int i = 0; i < 5; i++) { float ms = 0; cudaEventElapsedTime(&ms, t.ev[first[i]], t.ev[first[i] + 1]); t.ms[i] = ms; }
+    for (int i = 0; i < 5; i++) { float ms = 0; if (i != 1 && i != 2) cudaEventElapsedTime(&ms, t.ev[first[i]], t.ev[first[i] + 1]); t.ms[i] = ms; }
+    for (int p = 0; p < t.parts; p++) {                     /* kernels B and C: the sum over the parts */
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t.evp[p][1], t.evp[p][2]); t.ms[1] += ms;
+        cudaEventElapsedTime(&ms, t.evp[p][2], t.evp[p][3]); t.ms[2] += ms;
+    }
     t.ms[5] = 0.f;
     if (e->hcfg.resample) { float ms = 0; cudaEventElapsedTime(&ms, t.ev[8], t.ev[9]); t.ms[5] = ms; }
     { float ms = 0; cudaEventElapsedTime(&ms, t.ev[0], t.ev[6]); t.ms[7] = ms; }
