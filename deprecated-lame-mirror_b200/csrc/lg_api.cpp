@@ -475,7 +475,14 @@ struct lamegpu_batch {
             });
         }
         double const t1 = now_ms();
-        if (lg_engine_submit(eng, k, maxf, any_float) != 0) return -2;
+        /* a step that shares no stream with the step still in flight (the lanes of lame_t handles: a lane is not gathered again before its
+         * frames are back) need not queue its quantiser behind that step's */
+        bool independent = in_flight[k ^ 1];
+        if (independent) {
+            const std::vector<int> &other = flight_nfr[k ^ 1];
+            for (int s = 0; s < S && independent; s++) if (nfr[s] && other[s]) independent = false;
+        }
+        if ((independent ? lg_engine_submit_independent(eng, k, maxf, any_float) : lg_engine_submit(eng, k, maxf, any_float)) != 0) return -2;
         in_flight[k] = true;
         flight_nfr[k].assign(nfr, nfr + S);
         next_slot = k ^ 1;

@@ -103,7 +103,7 @@ struct lg_engine {
     /* three CUDA streams: `stream` carries the copies in and the stateless/scan kernels (R, A, B, C), `stream2` the quantiser (D) and
      * `stream3` the packer and the copies out (E, D2H), so that the next step's kernel D follows this step's directly; events order slot
      * k's D behind its C, its E behind its D, and its next A-B-C behind its previous D2H.  Nothing waits inside a kernel. */
-    lgStream_t stream, stream2, stream3, stream4;
+    lgStream_t stream, stream2, stream2b, stream3, stream4;   /* stream2b: kernel D of the odd slot (see lg_submit: independent steps) */
     int ana_split;                    /* parts the analysis of a step is cut into along the frames (lg_submit) */
     int dense;                        /* more than four streams per SM: the one-warp kernel D in its seven-CTAs-per-SM build */
     int group_nw;                     /* > 0: kernel D in its group form (lg_k_quantg.cuh) with this many warps per granule.channel */
@@ -166,6 +166,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
 #ifndef LG_EMULATE
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->stream2) cudaStreamSynchronize(e->stream2);
+    if (e->stream2b) cudaStreamSynchronize(e->stream2b);
     if (e->stream3) cudaStreamSynchronize(e->stream3);
     if (e->stream4) cudaStreamSynchronize(e->stream4);
 #endif
@@ -187,6 +188,7 @@ extern "C" void lg_engine_destroy(lg_engine *e)
     for (int i = 0; i < 2; i++) if (e->ev_mark[i]) cudaEventDestroy(e->ev_mark[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->stream2b) cudaStreamDestroy(e->stream2b);
     if (e->stream3) cudaStreamDestroy(e->stream3);
     if (e->stream4) cudaStreamDestroy(e->stream4);
 #endif
@@ -203,6 +205,7 @@ extern "C" int lg_engine_reset_streams(lg_engine *e, int first, int count)
     memcpy(e->d_state + first, e->d_state0 + first, (size_t) count * sizeof(LgStreamState));
 #else
     LG_CHECK(cudaStreamSynchronize(e->stream2));
+    LG_CHECK(cudaStreamSynchronize(e->stream2b));
     LG_CHECK(cudaStreamSynchronize(e->stream4));
     LG_CHECK(cudaMemcpyAsync(e->d_state + first, e->d_state0 + first, (size_t) count * sizeof(LgStreamState), cudaMemcpyDeviceToDevice, e->stream));
     LG_CHECK(cudaStreamSynchronize(e->stream));
@@ -230,6 +233,7 @@ extern "C" int lg_engine_end_reservoir(lg_engine *e, const int *streams, const i
     for (int i = 0; i < n; i++) { LgStreamState *s = e->d_state + streams[i]; s->resv_size = 0; s->main_data_begin = 0; s->ancillary_flag = ancillary_flags[i]; }
 #else
     LG_CHECK(cudaStreamSynchronize(e->stream2));           /* the flushed frames have been quantised */
+    LG_CHECK(cudaStreamSynchronize(e->stream2b));
     int *d = nullptr;
     LG_CHECK(cudaMalloc(&d, (size_t) 2 * n * sizeof(int)));
     cudaMemcpyAsync(d, streams, (size_t) n * sizeof(int), cudaMemcpyHostToDevice, e->stream2);
@@ -353,6 +357,7 @@ extern "C" lg_engine *lg_engine_create(const LgDevCfg *cfg, int nstreams, int ma
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
+        if (cudaStreamCreateWithPriority(&e->stream2b, cudaStreamNonBlocking, hi) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
         if (cudaStreamCreateWithPriority(&e->stream3, cudaStreamNonBlocking, hi) != cudaSuccess) { lg_engine_destroy(e); return NULL; }
     }
     for (int k = 0; k < LG_SLOTS; k++) for (int i = 0; i < 10; i++) cudaEventCreate(&e->slot[k].ev[i]);
@@ -476,33 +481,33 @@ extern "C" int lg_engine_reserve_chunks(lg_engine *e, int k, int per_stream)
 }
 
 /* kernels D (or D', D'') and E of slot k on the quantiser stream */
-static void lg_launch_quant_pack(lg_engine *e, LgSlot &t)
+static void lg_launch_quant_pack(lg_engine *e, LgSlot &t, lgStream_t ds)
 {
     int const S = e->S, F = e->F;
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[4], e->stream2);
+    cudaEventRecord(t.ev[4], ds);
 #endif
     if (e->hcfg.vbr == 4)
-        LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), e->stream2, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, e->d_state, t.d_nfr, F);
+        LG_LAUNCH(lg_kernel_vbr, S, 128, sizeof(LgSmemV), ds, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, e->d_state, t.d_nfr, F);
     else if (e->hcfg.vbr == 2 && (e->hcfg.substep_shaping & 2))
-        LG_LAUNCH(lg_kernel_vbrold<1>, S, 64, sizeof(LgSmemO), e->stream2, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, e->d_state, t.d_nfr, F);
+        LG_LAUNCH(lg_kernel_vbrold<1>, S, 64, sizeof(LgSmemO), ds, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, e->d_state, t.d_nfr, F);
     else if (e->hcfg.vbr == 2)
-        LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), e->stream2, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, e->d_state, t.d_nfr, F);
+        LG_LAUNCH(lg_kernel_vbrold<0>, S, 64, sizeof(LgSmemO), ds, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, e->d_state, t.d_nfr, F);
     else if (e->group_nw > 0) {
-#define LG_LAUNCH_G(NWV) LG_LAUNCH(lg_kernel_quantg<NWV>, S, 64 * NWV, sizeof(LgSmemG<NWV>), e->stream2, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, \
+#define LG_LAUNCH_G(NWV) LG_LAUNCH(lg_kernel_quantg<NWV>, S, 64 * NWV, sizeof(LgSmemG<NWV>), ds, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, \
                                    e->d_state, t.d_nfr, F)
         if (e->group_nw == 2) LG_LAUNCH_G(2); else LG_LAUNCH_G(3);
 #undef LG_LAUNCH_G
     }
     else {
         int const fl = ((e->hcfg.substep_shaping & 2) ? 1 : 0) | (e->dense ? 4 : 0);
-#define LG_LAUNCH_D(FLV) LG_LAUNCH(lg_kernel_quant<FLV>, S, 64, sizeof(LgSmemD), e->stream2, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, \
+#define LG_LAUNCH_D(FLV) LG_LAUNCH(lg_kernel_quant<FLV>, S, 64, sizeof(LgSmemD), ds, e->dcfg, t.d_xr, t.d_psy, t.d_frm, t.d_gout, t.d_fout, \
                                    e->d_state, t.d_nfr, F, 0, F)
         if (fl == 0) LG_LAUNCH_D(0); else if (fl == 1) LG_LAUNCH_D(1); else if (fl == 4) LG_LAUNCH_D(4); else LG_LAUNCH_D(5);
 #undef LG_LAUNCH_D
     }
 #ifndef LG_EMULATE
-    cudaEventRecord(t.ev[5], e->stream2);
+    cudaEventRecord(t.ev[5], ds);
     cudaStreamWaitEvent(e->stream3, t.ev[5], 0);
 #endif
     LG_LAUNCH(lg_kernel_pack, S * F, 128, sizeof(LgSmemE), e->stream3, e->dcfg, t.d_gout, t.d_fout, t.d_pay, (int) e->pay_stride, t.d_hdr, t.d_nfr, F, 0, F);
@@ -515,7 +520,8 @@ static void lg_launch_quant_pack(lg_engine *e, LgSlot &t)
 /* One step on slot k, asynchronous: [H2D of the staged inputs,] kernels R A B C on the analysis stream, D E [and the D2H of the packed
  * frames] on the quantiser stream.  nframes = max over streams of the slot's frame counts.  with_copies = 0: the bench's device-only step
  * on what a previous lg_engine_submit left in device memory. */
-static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 window, 1 the resampler's floats, 2 native types */, int with_copies)
+static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 window, 1 the resampler's floats, 2 native types */, int with_copies,
+                     int independent /* no stream of this step has frames in the step of the other slot */)
 {
     if (k < 0 || k >= LG_SLOTS || nframes < 1 || nframes > e->F) return -1;
     LgDeviceScope dev(e->device);
@@ -605,9 +611,16 @@ static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 windo
     }
 #ifndef LG_EMULATE
     cudaEventRecord(t.ev[3], e->stream4);
-    LG_CHECK(cudaStreamWaitEvent(e->stream2, t.ev[3], 0));
 #endif
-    lg_launch_quant_pack(e, t);
+    /* Kernel D of consecutive steps is ordered (a stream's reservoir and step-size memory pass from one to the next) - unless the two
+     * steps share no stream, as happens behind the lame_t handles, where a launch gathers the lanes that are not in flight: then the
+     * two kernels D, each all latency, run side by side on their own CUDA streams. */
+    lgStream_t const ds = (k & 1) ? e->stream2b : e->stream2;
+#ifndef LG_EMULATE
+    LG_CHECK(cudaStreamWaitEvent(ds, t.ev[3], 0));
+    if (!independent) LG_CHECK(cudaStreamWaitEvent(ds, e->slot[k ^ 1].ev[5], 0));
+#endif
+    lg_launch_quant_pack(e, t, ds);
     if (with_copies) {
         LG_COPY_D2H(t.h_fout, t.d_fout, S * F * sizeof(LgFrameOut), e->stream3);
         LG_COPY_D2H(t.h_pay, t.d_pay, S * e->pay_stride, e->stream3);
@@ -620,8 +633,9 @@ static int lg_submit(lg_engine *e, int k, int nframes, int mode /* 0 int16 windo
     t.in_flight = 1; t.nframes = nframes;
     return 0;
 }
-extern "C" int lg_engine_submit(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 1); }
-extern "C" int lg_engine_run_device(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 0); }
+extern "C" int lg_engine_submit(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 1, 0); }
+extern "C" int lg_engine_submit_independent(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 1, 1); }
+extern "C" int lg_engine_run_device(lg_engine *e, int k, int nframes, int mode) { return lg_submit(e, k, nframes, mode, 0, 0); }
 
 /* block until slot k's step has finished and its results are in the slot's host buffers; fills the kernel times of that step */
 extern "C" int lg_engine_wait(lg_engine *e, int k)

@@ -53,6 +53,9 @@ int  lg_engine_slots(const lg_engine *e);
 int  lg_engine_device(const lg_engine *e);
 int  lg_engine_submit(lg_engine *e, int slot, int nframes, int mode);      /* mode: 0 int16 window, 1 resampled, 2 native sample types */
 int  lg_engine_run_device(lg_engine *e, int slot, int nframes, int mode);
+/* the same as lg_engine_submit for a step none of whose streams has frames in the step in flight in the other slot: its quantiser need not
+ * wait for that step's */
+int  lg_engine_submit_independent(lg_engine *e, int slot, int nframes, int mode);
 int  lg_engine_wait(lg_engine *e, int slot);
 int  lg_engine_in_flight(const lg_engine *e, int slot);
 int  lg_engine_mark(lg_engine *e, int which);

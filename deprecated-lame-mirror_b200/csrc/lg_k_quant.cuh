@@ -1504,6 +1504,7 @@ lg_kernel_quant(const LgDevCfg *__restrict__ cfg, const float *LG_XR xr_in, cons
     int anc_flag = st->ancillary_flag, pay_off = 0;
 
     int const my_frames = min(nfr[stream], f1);
+    if (my_frames <= 0) return;                        /* nothing of this stream in this step: its state is not ours to write back (another step's kernel may own it) */
     int const mgr = cfg->mode_gr;                      /* granules per frame: 2 (MPEG-1) or 1 (MPEG-2/2.5) */
     if (f0 > 0 && f0 < my_frames) {                     /* a later piece of the batch: the payload continues behind the previous frame's */
         const LgFrameOut *pf = fout + (size_t) stream * nframes + (f0 - 1);

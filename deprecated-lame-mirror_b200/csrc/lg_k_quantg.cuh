@@ -921,6 +921,7 @@ lg_kernel_quantg(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_
     LgGBand *w = id.wid == 0 ? static_cast<LgGBand *>(cs) : &cs->rep[id.wid - 1];
     int ring = 0;
     int const my_frames = min(nfr[stream], nframes);
+    if (my_frames <= 0) return;                        /* nothing of this stream in this step: its state is not ours to write back (another step's kernel may own it) */
     int const mgr = cfg->mode_gr;
     LgGBudget bud;
     for (int i = threadIdx.x; i < 576; i += 2 * NT) sm->bv_scf[i] = cfg->bv_scf[i];

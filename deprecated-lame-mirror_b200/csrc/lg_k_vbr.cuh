@@ -534,6 +534,7 @@ lg_kernel_vbr(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_in,
     int const mgr = cfg->mode_gr;                 /* MPEG-2/2.5: one granule per frame, warps 2 and 3 stay idle */
     int const active = ch < nch && gr < mgr;
     int const my_frames = nfr[stream];
+    if (my_frames <= 0) return;                        /* nothing of this stream in this step: its state is not ours to write back (another step's kernel may own it) */
     for (int frame = 0; frame < my_frames; frame++) {
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;

@@ -103,6 +103,7 @@ lg_kernel_vbrold(const LgDevCfg *__restrict__ cfg, const float *__restrict__ xr_
     int const max_index = c->vbr_max_bitrate_index;
 
     int const my_frames = nfr[stream];
+    if (my_frames <= 0) return;                        /* nothing of this stream in this step: its state is not ours to write back (another step's kernel may own it) */
     for (int frame = 0; frame < my_frames; frame++) {
         const LgFrameCtl *F = frm + (size_t) stream * nframes + frame;
         int const padding = F->padding, mode_ext = F->mode_ext;
