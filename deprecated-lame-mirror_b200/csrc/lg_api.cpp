@@ -1185,8 +1185,10 @@ struct LgShared {
             unlock_lanes();
             queue.erase(queue.begin());
             if (rc2 != 0) { fail(); break; }
+            /* wake the lanes' threads - a system call each - on the worker pool: several hundred in a row cost this thread more than
+             * the splice did */
             const std::vector<int> &nfr = b->flight_nfr[k];
-            for (int s = 0; s < b->S; s++) if (nfr[s]) lane[s].cv.notify_all();
+            b->parallel_for(b->S, [&](int s) { if (nfr[s]) lane[s].cv.notify_all(); });
             cv_work.notify_all();            /* a slot is free again */
             t_device += t2 - t1; t_splice += now_ms() - t2;
         }
