@@ -69,7 +69,8 @@ def chunked(fn, arrs, n, step, interleaved=False):
 def main(path):
     L = lame_b200._lib = lame_b200.load_library(os.path.abspath(path))
     R = ctypes.CDLL(oracle.REF_SO)
-    x = make_signal("click", 20 * 1152, seed=9)
+    quick = os.environ.get("SAMPLE_TYPES_QUICK") == "1"      # the CPU suite's run over the SIMT emulator: shorter signal, fewer repeats
+    x = make_signal("click", (7 if quick else 20) * 1152, seed=9)
     n = x.shape[1]
     cases = {
         "lame_encode_buffer_float": ([x[0].astype(np.float32) * 0.7, x[1].astype(np.float32) * 0.7], False),
@@ -109,7 +110,7 @@ def main(path):
     assert a == b, "mixed"
     print("mixed types in one stream", len(a), "identical")
     # the same through the resampler (32 kHz in, 44.1 kHz out): its input window keeps the caller's type as well (kernel R converts)
-    for name, calls in list(per_type.items()) + [("mixed", mixed)]:
+    for name, calls in (list(per_type.items())[1:3] if quick else list(per_type.items())) + [("mixed", mixed)]:
         a, b = run_calls(L, calls, 32000, 44100), run_calls(R, calls, 32000, 44100)
         assert a == b, "resampled " + name
         print("resampled", name, len(a), "identical")

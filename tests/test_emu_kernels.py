@@ -145,7 +145,7 @@ def test_emulated_sample_type_entry_points(emu_bin, oracle_mod):
     if not oracle_mod.have_ref():
         pytest.skip("needs the reference build (oracle/_ref)")
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "sample_types_check.py"), os.path.join(ROOT, "tests", "emu", "liblamegpu_emu.so")],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, SAMPLE_TYPES_QUICK="1"))
     assert r.returncode == 0 and "SAMPLE TYPES IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
