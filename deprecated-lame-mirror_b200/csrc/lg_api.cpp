@@ -249,7 +249,6 @@ public:
     void run(int n, const std::function<void(int)> &fn)
     {
         if (n_ <= 1 || n <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
-        std::lock_guard<std::mutex> one(run_m_);         /* callers on different threads (the handles' two dispatchers) take turns */
         {
             std::lock_guard<std::mutex> g(m_);
             fn_ = &fn; total_ = n; next_.store(0); active_ = (int) th_.size(); gen_++;
@@ -278,7 +277,7 @@ private:
     }
     int n_;
     std::vector<std::thread> th_;
-    std::mutex m_, run_m_;
+    std::mutex m_;
     std::condition_variable cv_, done_;
     const std::function<void(int)> *fn_ = nullptr;
     std::atomic<int> next_{0};
@@ -327,7 +326,7 @@ struct lamegpu_batch {
     bool pipelined = false;
     double acc_ms[5] = { 0, 0, 0, 0, 0 };   /* per-kernel device times summed over the steps of the last lamegpu_batch_run_device_steps */
     int acc_n = 0;
-    std::atomic<bool> in_flight[2] = { { false }, { false } };    /* cleared when the slot's frames have been spliced (the handles' completer runs beside the submitter) */
+    bool in_flight[2] = { false, false };
     std::vector<int> flight_nfr[2];
 
     /* wait for slot k's step and splice its frames into the streams */
@@ -337,6 +336,7 @@ struct lamegpu_batch {
         double const t0 = now_ms();
         if (lg_engine_wait(eng, k) != 0) return -2;
         double const t1 = now_ms();
+        in_flight[k] = false;
         const int *nfr = flight_nfr[k].data();
         const LgFrameOut *fo = lg_engine_host_fout(eng, k);
         const unsigned char *pay = lg_engine_host_pay(eng, k), *hdr = lg_engine_host_hdr(eng, k);
@@ -363,7 +363,6 @@ struct lamegpu_batch {
             x.bw.buf.clear();
             x.frames_out += nfr[s];
         });
-        in_flight[k] = false;
         if (g_timing) fprintf(stderr, "lamegpu: slot %d: waited %.2f ms for the device, splice %.2f ms\n", k, t1 - t0, now_ms() - t1);
         return 0;
     }
@@ -377,20 +376,19 @@ struct lamegpu_batch {
     /* One step: stage every complete frame of every stream (at most F per stream) into the next slot and submit it.  Returns the slot,
      * -1 when no stream has a complete frame, -2 on error; *frames gets the number of frames submitted.  The slot's previous step
      * (two steps back) is completed first if it still is in flight. */
-    int stage_and_submit(long *frames, const std::vector<char> *skip = nullptr /* streams not to look at: their frames are in flight */)
+    int stage_and_submit(long *frames)
     {
         long submitted = 0;
         int const k = next_slot;
         int maxf = 0, any_float = 0;
         for (int s = 0; s < S; s++) {
-            if (skip && (*skip)[s]) continue;
             long const r = st[s].frames_ready();
             if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode || st[s].nat_kind) any_float = 1; }
         }
         if (maxf == 0) return -1;
         if (complete(k) != 0) return -2;                 /* the slot's previous step (two steps back) */
         int *nfr = lg_engine_host_nfr(eng, k);
-        for (int s = 0; s < S; s++) nfr[s] = (skip && (*skip)[s]) ? 0 : (int) std::min<long>(st[s].frames_ready(), F);
+        for (int s = 0; s < S; s++) nfr[s] = (int) std::min<long>(st[s].frames_ready(), F);
         size_t const stride = lg_engine_pcm_stride(eng);
         double const t0 = now_ms();
         if (cfg.resample) {
@@ -1142,7 +1140,6 @@ struct LgShared {
     {
         std::unique_lock<std::mutex> lk(m);
         unsigned long seen = 0;
-        std::vector<char> skip;
         for (;;) {
             while (!(stop || (work.load(std::memory_order_acquire) != seen && !b->in_flight[b->next_slot]))) cv_work.wait_for(lk, std::chrono::microseconds(100));
             if (stop) break;
@@ -1158,14 +1155,9 @@ struct LgShared {
             seen = work.load();
             double const t0 = now_ms();
             long n = 0;
-            /* the lanes whose frames are in flight in the other slot are left alone (they cannot have new frames: their threads wait for
-             * these) - the completer may be splicing them at this moment, under their own locks */
-            int const other = b->next_slot ^ 1;
-            skip.assign(b->S, 0);
-            if (b->in_flight[other]) for (int s = 0; s < b->S; s++) skip[s] = b->flight_nfr[other][s] > 0;
-            for (int s = 0; s < b->S; s++) if (!skip[s]) lane[s].lm.lock();
-            int const k = b->stage_and_submit(&n, &skip);
-            for (int s = b->S - 1; s >= 0; s--) if (!skip[s]) lane[s].lm.unlock();
+            lock_lanes();
+            int const k = b->stage_and_submit(&n);
+            unlock_lanes();
             if (k == -1) continue;
             if (k < 0) { fail(); break; }
             steps++; step_frames += n;
@@ -1186,18 +1178,17 @@ struct LgShared {
             double const t1 = now_ms();
             lk.unlock();
             int const rc = lg_engine_wait(b->eng, k);          /* the device works: the lanes can be fed, the next launch staged meanwhile */
-            double const t2 = now_ms();
-            /* splice under the locks of this launch's lanes only, beside the submitter (which stages other lanes into the other slot) */
-            std::vector<int> const nfr = b->flight_nfr[k];     /* a copy: the slot is the submitter's again as soon as the splice is done */
-            for (int s = 0; s < b->S; s++) if (nfr[s]) lane[s].lm.lock();
-            int const rc2 = rc != 0 ? rc : b->complete(k);
-            for (int s = b->S - 1; s >= 0; s--) if (nfr[s]) lane[s].lm.unlock();
-            /* wake the lanes' threads - a system call each - on the worker pool: several hundred in a row cost this thread more than
-             * the splice did */
-            if (rc2 == 0) b->parallel_for(b->S, [&](int s) { if (nfr[s]) lane[s].cv.notify_all(); });
             lk.lock();
+            double const t2 = now_ms();
+            lock_lanes();
+            int const rc2 = rc != 0 ? rc : b->complete(k);
+            unlock_lanes();
             queue.erase(queue.begin());
             if (rc2 != 0) { fail(); break; }
+            /* wake the lanes' threads - a system call each - on the worker pool: several hundred in a row cost this thread more than
+             * the splice did */
+            const std::vector<int> &nfr = b->flight_nfr[k];
+            b->parallel_for(b->S, [&](int s) { if (nfr[s]) lane[s].cv.notify_all(); });
             cv_work.notify_all();            /* a slot is free again */
             t_device += t2 - t1; t_splice += now_ms() - t2;
         }
