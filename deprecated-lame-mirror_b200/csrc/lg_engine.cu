@@ -688,13 +688,14 @@ extern "C" float lg_engine_marked_ms(lg_engine *e)
 }
 
 /* test/debug hook: copy an intermediate device buffer to the host.
- * what: 0 sb, 1 ana, 2 psy, 3 frm, 4 xr, 5 gout, 6 fout, 7 state */
+ * what: 0 sb, 1 ana, 2 psy, 3 frm, 4 xr, 5 gout, 6 fout, 7 state, 8 the configuration's fast_log2 table (host copy) */
 extern "C" long lg_engine_debug_copy(lg_engine *e, int what, void *dst, size_t cap)
 {
     size_t const S = e->S, F = e->F;
     LgDeviceScope dev(e->device);
     const LgSlot &t = e->slot[0];
     const void *src = NULL; size_t n = 0;
+    if (what == 8) { n = sizeof e->hcfg.log_table < cap ? sizeof e->hcfg.log_table : cap; memcpy(dst, e->hcfg.log_table, n); return (long) n; }
     switch (what) {
     case 0: src = e->d_sb; n = S * (2 * F + 1) * 2 * 576 * sizeof(float); break;
     case 1: src = e->d_ana; n = S * 2 * F * sizeof(LgAnalysis); break;

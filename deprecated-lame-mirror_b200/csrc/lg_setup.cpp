@@ -480,7 +480,9 @@ static void setup_psy(LgDevCfg *c, float attackthre, float attackthre_s, int vbr
     memcpy(&c->l2s, &c->l, sizeof c->l2s);
     setup_partitions(&c->l2s, sfreq, LG_BLK, 192, LG_SBMAX_S, c->sfb_s);
 
-    for (j = 0; j < 513; j++) c->log_table[j] = log(1.0f + j / (float) 512) / log(2.0f);
+    /* util.c:962 init_log_table: C's log() takes the float argument as a double (C++ would pick the float overload: 141 of the 513 entries
+     * then come out one ulp off - seen as one stream in 512 differing after 170 frames, round 2) */
+    for (j = 0; j < 513; j++) c->log_table[j] = (float) (::log((double) (1.0f + j / (float) 512)) / ::log((double) 2.0f));
 }
 
 /* lame.c:363 lame_init_qval */

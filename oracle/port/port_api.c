@@ -152,7 +152,7 @@ static int encode_frame(lp_encoder *e, const float *inbuf_l, const float *inbuf_
             }
         }
     }
-    if (getenv("LP_DEBUG")) fprintf(stderr, "port frame %d: pe %g %g %g %g peMS %g %g %g %g bt %d %d %d %d\n", e->frame_number, pe[0][0], pe[0][1], pe[1][0], pe[1][1], pe_MS[0][0], pe_MS[0][1], pe_MS[1][0], pe_MS[1][1], e->tt[0][0].block_type, e->tt[0][1].block_type, e->tt[1][0].block_type, e->tt[1][1].block_type);
+    if (getenv("LP_DEBUG")) fprintf(stderr, "port frame %d: pe %.9g %.9g %.9g %.9g peMS %.9g %.9g %.9g %.9g bt %d %d %d %d\n", e->frame_number, pe[0][0], pe[0][1], pe[1][0], pe[1][1], pe_MS[0][0], pe_MS[0][1], pe_MS[1][0], pe_MS[1][1], e->tt[0][0].block_type, e->tt[0][1].block_type, e->tt[1][0].block_type, e->tt[1][1].block_type);
     adjust_ath(e);
     lp_mdct_sub48(e, inbuf[0], inbuf[1]);
     e->mode_ext = 0;
@@ -178,6 +178,8 @@ static int encode_frame(lp_encoder *e, const float *inbuf_l, const float *inbuf_
     f = (670 * 5 * cfg->mode_gr * cfg->channels) / f;
     for (gr = 0; gr < cfg->mode_gr; gr++)
         for (ch = 0; ch < cfg->channels; ch++) pe_use[gr][ch] *= f;
+    if (getenv("LP_DEBUG")) { fprintf(stderr, "port frame %d: pefir", e->frame_number); for (i = 0; i < 19; i++) fprintf(stderr, " %.9g", e->pefirbuf[i]); fprintf(stderr, "\n"); }
+    if (getenv("LP_DEBUG")) fprintf(stderr, "port frame %d: pe_use %.9g %.9g %.9g %.9g f %.9g mer %.9g %.9g\n", e->frame_number, pe_use[0][0], pe_use[0][1], pe_use[1][0], pe_use[1][1], f, ms_ener_ratio[0], ms_ener_ratio[1]);
     memcpy(e->last_pe, pe_use, sizeof e->last_pe);
     if (cfg->vbr == 3) lp_abr_iteration_loop(e, pe_use, ms_ener_ratio, masking);      /* encoder.c:520-538 */
     else if (cfg->vbr == 4) lp_vbr_new_iteration_loop(e, pe_use, ms_ener_ratio, masking);

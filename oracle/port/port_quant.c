@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "lame_port.h"
 #include "port_tables.inc"
 
@@ -16,6 +18,15 @@
 #define FAST_LOG10_X_D(c, x, y) (lp_fast_log2(c, x) * (LOG2_D / LOG10_D * (y)))
 
 typedef struct { float over_noise, tot_noise, max_noise; int over_count, over_SSD, bits; } noise_result;
+
+/* test aid: LP_TRACE_FRAME=<n> prints the bit targets and every noise-shaping round of frame n to stderr (compared by hand with
+ * the same trace of the device code under the emulator, LG_TRACE_FRAME) */
+static int lp_trace_on(const lp_encoder *e)
+{
+    static int want = -2;
+    if (want == -2) { const char *v = getenv("LP_TRACE_FRAME"); want = v ? atoi(v) : -1; }
+    return want >= 0 && e->frame_number == want;
+}
 typedef struct { int global_gain, sfb_count1, step[39]; float noise[39], noise_log[39]; } noise_cache;
 
 static const uint8_t *hlen_of(int t) { return LGT_HUFF_LEN + LGT_HUFF_OFF[t]; }
@@ -1104,6 +1115,8 @@ static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float
     if (!cfg->noise_shaping) return 100;
     memset(&prev_noise, 0, sizeof prev_noise);
     (void) calc_noise(cfg, gi, l3_xmin, distort, &best_noise_info, &prev_noise);
+    if (lp_trace_on(e)) fprintf(stderr, "T ch%d start targ %d gg %d p23 %d over %d tot %.9g ovn %.9g max %.9g\n", ch, targ_bits, gi->global_gain, gi->part2_3_length,
+                                best_noise_info.over_count, best_noise_info.tot_noise, best_noise_info.over_noise, best_noise_info.max_noise);
     best_noise_info.bits = gi->part2_3_length;
     gi_w = *gi;
     age = 0;
@@ -1133,6 +1146,8 @@ static int outer_loop(lp_encoder *e, lp_granule *gi, const float *l3_xmin, float
             (void) calc_noise(cfg, &gi_w, l3_xmin, distort, &noise_info, &prev_noise);
             noise_info.bits = gi_w.part2_3_length;
             better = quant_compare(&best_noise_info, &noise_info);
+            if (lp_trace_on(e)) fprintf(stderr, "T ch%d round gg %d p23 %d over %d tot %.9g ovn %.9g max %.9g ssd %d better %d\n", ch, gi_w.global_gain, gi_w.part2_3_length,
+                                        noise_info.over_count, noise_info.tot_noise, noise_info.over_noise, noise_info.max_noise, noise_info.over_SSD, better);
             if (better) {
                 best_part2_3_length = gi->part2_3_length;
                 best_noise_info = noise_info;

@@ -5,7 +5,7 @@
  * Every stream is compared byte for byte with the same calls made to the checker named by argv[5]: the reference library itself
  * (oracle/_ref/libmp3lame_ref.so, loaded with dlopen so that its lame_* symbols do not collide with the product's).
  *
- * usage: handles_mt <threads> <frames_per_stream> <chunk_samples> <brate> <checker.so> [vbr_mode vbr_q]
+ * usage: handles_mt <threads> <frames_per_stream> <chunk_samples> <brate> <checker.so> [vbr_mode vbr_q [first_stream]]
  * prints "IDENTICAL n/n streams, <frames/s aggregate>" or the first mismatch; exit code 0 only when every stream is identical. */
 #include <stdio.h>
 #include <stdlib.h>
@@ -57,6 +57,7 @@ int main(int argc, char **argv)
     int const brate = argc > 4 ? atoi(argv[4]) : 128;
     const char *checker = argc > 5 ? argv[5] : "oracle/_ref/libmp3lame_ref.so";
     int const vbr = argc > 6 ? atoi(argv[6]) : 0, vbr_q = argc > 7 ? atoi(argv[7]) : 4;
+    int const first = argc > 8 ? atoi(argv[8]) : 0;         /* thread s encodes the signal of stream first + s */
     int const n = NF * 1152, cap = n * 5 / 4 + 7200 + 65536;
     void *h = dlopen(checker, RTLD_NOW | RTLD_LOCAL | RTLD_DEEPBIND)   /* DEEPBIND: the checker's own lame_* calls must stay inside it */;
     if (!h) { fprintf(stderr, "cannot load the checker %s: %s\n", checker, dlerror()); return 2; }
@@ -74,7 +75,7 @@ int main(int argc, char **argv)
 
     std::vector<std::vector<short>> L(T), Rr(T);
     std::vector<std::vector<unsigned char>> got(T), want(T);
-    for (int s = 0; s < T; s++) make_pcm(s, n, L[s], Rr[s]);
+    for (int s = 0; s < T; s++) make_pcm(first + s, n, L[s], Rr[s]);
     /* the handles are made before the clock starts (the first one creates the engine), as an application would */
     std::vector<lame_global_flags *> g(T);
     for (int s = 0; s < T; s++) {

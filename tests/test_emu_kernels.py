@@ -164,3 +164,28 @@ def test_pipelined_batch_matches_port(emu_bin, args):
     r = subprocess.run([emu_bin] + args.split(), capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, LP_PIPELINED="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "IDENTICAL" in r.stdout
+
+
+def test_fast_log2_table_is_the_c_one(emu_bin):
+    """util.c:962 init_log_table computes log(1.0f + j/512.f) / log(2.0f) in C: the float argument goes to the double log().  The host
+    setup is C++, where log(float) is the float overload - 141 of the 513 entries one ulp off, which showed as one stream in 512
+    differing from the reference after 170 frames (white noise, handles_mt stream 495).  The table of the configuration must be C's."""
+    import ctypes
+    import sys
+    import numpy as np
+    code = r'''
+import sys, ctypes, numpy as np
+sys.path.insert(0, %r)
+import lame_b200
+lame_b200._lib = lame_b200.load_library(%r)
+enc = lame_b200.BatchEncoder(1, 44100, 2, 128, -1, -1, frames_per_launch=1)
+t = np.zeros(513, dtype=np.float32)
+n = lame_b200._lib.lamegpu_batch_debug_copy(enc._h, 8, t.ctypes.data, t.nbytes)
+assert n == t.nbytes, n
+j = np.arange(513, dtype=np.float32)
+want = (np.log((np.float32(1.0) + j / np.float32(512)).astype(np.float64)) / np.log(np.float64(np.float32(2.0)))).astype(np.float32)
+bad = int((t != want).sum())
+print("LOG TABLE", "IDENTICAL" if bad == 0 else "DIFFERENT %%d" %% bad)
+''' % (ROOT, os.path.join(ROOT, "tests", "emu", "liblamegpu_emu.so"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "LOG TABLE IDENTICAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -50,3 +50,16 @@ def test_512_threads_with_own_handles_on_the_gpu(threads, frames, chunk, floor):
     rate = float(re.search(r"= (\d+) frames/s", r.stdout).group(1))
     print(r.stdout.strip())
     assert rate >= floor, "aggregate %.0f frames/s" % rate
+
+
+@pytest.mark.gpu
+def test_long_streams_stay_identical():
+    """24 streams x 300 frames through the handles (one frame per call), among them the white-noise stream whose frame 170 was the first
+    to show the one-ulp error of a C++-computed fast_log2 table (handles_mt stream 495): a perceptual entropy one ulp off moves a
+    bit target by one bit nine frames later.  Long streams find what 8-frame tests cannot."""
+    exe = os.path.join(ROOT, "tests", "c", "bin", "handles_mt")
+    if not (os.path.exists(exe) and os.path.exists(REF_SO)):
+        pytest.skip("tests/c/bin/handles_mt and oracle/_ref travel with the repository snapshot; not built here")
+    r = subprocess.run([exe, "24", "300", "1152", "128", REF_SO, "0", "4", "480"], capture_output=True, text=True, cwd=ROOT, timeout=900,
+                       env=dict(os.environ, LAMEGPU_LANES="512"))
+    assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
