@@ -324,6 +324,11 @@ struct lamegpu_batch {
      * splicing the previous one - runs while the device works. */
     int next_slot = 0;
     bool pipelined = false;
+    /* the handles' engine (LgShared): a launch that gathers crowd_lanes lanes or more takes at most crowd_cap frames of each.  A
+     * launch lasts as long as its longest lane (kernels B and D walk a stream's frames one after the other), so lanes with one frame
+     * next to lanes with four leave the device three quarters idle; the frames held back go into the next launch, which is staged
+     * while this one runs.  0 = off (the batch calls: every stream brings the same number of frames). */
+    int crowd_cap = 0, crowd_lanes = 0;
     double acc_ms[5] = { 0, 0, 0, 0, 0 };   /* per-kernel device times summed over the steps of the last lamegpu_batch_run_device_steps */
     int acc_n = 0;
     bool in_flight[2] = { false, false };
@@ -380,15 +385,17 @@ struct lamegpu_batch {
     {
         long submitted = 0;
         int const k = next_slot;
-        int maxf = 0, any_float = 0;
+        int maxf = 0, any_float = 0, lanes_ready = 0;
         for (int s = 0; s < S; s++) {
             long const r = st[s].frames_ready();
-            if (r > 0) { maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode || st[s].nat_kind) any_float = 1; }
+            if (r > 0) { lanes_ready++; maxf = std::max<int>(maxf, (int) std::min<long>(r, F)); if (st[s].float_mode || st[s].nat_kind) any_float = 1; }
         }
         if (maxf == 0) return -1;
+        int const cap = (crowd_cap > 0 && lanes_ready >= crowd_lanes) ? std::min(crowd_cap, F) : F;
+        maxf = std::min(maxf, cap);
         if (complete(k) != 0) return -2;                 /* the slot's previous step (two steps back) */
         int *nfr = lg_engine_host_nfr(eng, k);
-        for (int s = 0; s < S; s++) nfr[s] = (int) std::min<long>(st[s].frames_ready(), F);
+        for (int s = 0; s < S; s++) nfr[s] = (int) std::max<long>(0, std::min<long>(st[s].frames_ready(), cap));
         size_t const stride = lg_engine_pcm_stride(eng);
         double const t0 = now_ms();
         if (cfg.resample) {
@@ -683,16 +690,18 @@ struct lamegpu_batch {
         if (x.mf_samples_to_encode < 1) return;
         if (x.rs_mode) {
             /* lame.c:2077-2117 with resampling: zero samples go in, in bunches sized from the fill of the frame buffer,
-             * until the frames counted at the start have come out.  Every frame that is ready has been encoded
-             * (pump() runs after each feed), so the buffer fill is what the timeline holds beyond them. */
-            int samples_to_encode = (int) (x.mf_samples_to_encode - 1152);
-            samples_to_encode += 16. / cfg.rs_ratio;
+             * until the frames counted at the start have come out.  The reference has encoded every complete frame by now; here
+             * some may still wait for their launch (a handle's lane with calls outstanding): they count as done, the buffer fill
+             * is what the timeline holds beyond them. */
             int const fs = x.fs;
+            long const waiting = x.frames_ready();
+            int samples_to_encode = (int) (x.mf_samples_to_encode - (long) fs * waiting - 1152);
+            samples_to_encode += 16. / cfg.rs_ratio;
             int end_padding = fs - (samples_to_encode % fs);
             if (end_padding < 576) end_padding += fs;
             x.tag.enc_padding = end_padding;
             int frames_left = (samples_to_encode + end_padding) / fs;
-            long virt_done = x.frames_done;                 /* frames the reference would have encoded so far */
+            long virt_done = x.frames_done + waiting;       /* frames the reference would have encoded so far */
             while (frames_left > 0) {
                 int bunch = (int) (x.need - (x.rs_tend - (long) fs * virt_done));
                 bunch *= cfg.rs_ratio;
@@ -1220,6 +1229,12 @@ static LgShared *shared_acquire(const std::string &key, const std::function<lame
     if (!b) return nullptr;
     LgShared *se = new LgShared;
     se->b = b; se->key = key;
+    {
+        /* measured with 512 threads (profiles/r2_handles.txt): no cap 2.65e5 frames/s, 3 -> 3.6e5, 2 -> 3.8e5, 1 -> 3.3e5 */
+        const char *e = getenv("LAMEGPU_HANDLE_CROWD_CAP"), *e2 = getenv("LAMEGPU_HANDLE_CROWD_LANES");
+        b->crowd_cap = e ? std::max(0, atoi(e)) : 2;
+        b->crowd_lanes = e2 ? std::max(1, atoi(e2)) : 128;
+    }
     se->lane.reset(new LgShared::Lane[b->S]);
     se->used.assign(b->S, 0);
     se->used[0] = 1; se->nused = 1;
@@ -1293,6 +1308,7 @@ static void tag_init(lamegpu_batch *b, int lane)
 static void put_be32(unsigned char *p, unsigned long v) { p[0] = (v >> 24) & 0xff; p[1] = (v >> 16) & 0xff; p[2] = (v >> 8) & 0xff; p[3] = v & 0xff; }
 static void put_be16(unsigned char *p, unsigned v) { p[0] = (v >> 8) & 0xff; p[1] = v & 0xff; }
 
+static int handle_quiesce(lame_global_flags *g);
 static inline lamegpu_batch *HB(const lame_global_flags *g) { return g->se ? g->se->b : nullptr; }
 static inline Stream &HS(const lame_global_flags *g) { return g->se->b->st[g->lane]; }
 
@@ -1376,7 +1392,7 @@ int lame_init_params(lame_global_flags *g)
     so.strict_iso = (int) g->opt[LG_OPTI_strict_ISO]; so.use_temporal = (int) g->opt[LG_OPTI_useTemporal];
     so.vbr_min_kbps = (int) g->opt[LG_OPTI_VBR_min_bitrate_kbps]; so.vbr_max_kbps = (int) g->opt[LG_OPTI_VBR_max_bitrate_kbps];
     so.vbr_hard_min = (int) g->opt[LG_OPTI_VBR_hard_min];
-    if (g->se) { shared_release(g->se, g->lane); g->se = nullptr; }
+    if (g->se) { (void) handle_quiesce(g); shared_release(g->se, g->lane); g->se = nullptr; }
     if (g->preset_foreign && g->VBR == vbr_off) {
         fprintf(stderr, "lamegpu: lame_set_preset(V%d) without a VBR mode is not supported\n", g->vbr_q);
         return -1;
@@ -1442,19 +1458,43 @@ static int handle_take(lame_global_flags *g, unsigned char *mp3buf, int mp3buf_s
     }
     return have;
 }
-/* with the lane's mutex held: wake the dispatcher and sleep until the frames this lane's samples complete have been spliced */
-static int handle_wait_frames(lame_global_flags *g, std::unique_lock<std::mutex> &lk)
+/* How many frames of a handle may be outstanding when lame_encode_buffer returns.  1 = the call returns the bytes of the frames its own
+ * samples completed (the reference's timing, lame.c:1743) - every call of every thread then is a device round trip with a sleep and a
+ * wake-up.  d > 1 = the call returns once all but the newest d - 1 frames are back, with whatever bytes have arrived: the lane's next
+ * frame is already staged when the previous one completes, launches carry more than one frame per lane, and the caller seldom sleeps.
+ * The stream is the same byte for byte; bytes reach the caller up to d - 1 frames later (libmp3lame's contract allows a call to return
+ * 0 bytes, lame.h:687-699), lame_encode_flush collects the rest, and whatever reads a lane's final state waits for it (handle_quiesce).
+ * Default 5 (measured, profiles/r2_handles.txt, 512 threads x 1152-sample calls: depth 1 2.07e5 frames/s, 3 -> 2.54e5, and with the
+ * crowded launches capped at two frames per lane - lamegpu_batch::crowd_cap - 3 -> 3.1e5, 5 -> 3.8e5; one thread 976 -> 1339);
+ * LAMEGPU_HANDLE_DEPTH=1 restores the synchronous call.  Read once. */
+static long handle_depth()
+{
+    static long const d = []() { const char *e = getenv("LAMEGPU_HANDLE_DEPTH"); return e ? std::max(1L, atol(e)) : 5L; }();
+    return d;
+}
+/* with the lane's mutex held: wake the dispatcher and sleep until the frames this lane's samples complete have been spliced - all of
+ * them (`all`: flush, close and whatever else reads the lane's final state) or all but the newest handle_depth() - 1 */
+static int handle_wait_frames(lame_global_flags *g, std::unique_lock<std::mutex> &lk, bool all = false)
 {
     LgShared *se = g->se;
     Stream &x = HS(g);
-    long const ready = x.frames_ready();
-    if (ready <= 0) return 0;
-    long const target = x.frames_done + ready;
-    lk.unlock();
-    se->kick();
-    lk.lock();
+    long const ready = std::max<long>(0, x.frames_ready());
+    long const target = x.frames_done + ready - (all ? 0 : handle_depth() - 1);
+    if (ready > 0) {
+        lk.unlock();
+        se->kick();
+        lk.lock();
+    }
+    if (x.frames_out >= target) return se->failed.load() ? -2 : 0;
     se->lane[g->lane].cv.wait(lk, [&]() { return se->failed.load() || x.frames_out >= target; });
     return se->failed.load() ? -2 : 0;
+}
+/* nothing of this lane staged or in flight any more (before its state is read as final or the lane given back) */
+static int handle_quiesce(lame_global_flags *g)
+{
+    if (!g->se) return 0;
+    std::unique_lock<std::mutex> lk(g->se->lane[g->lane].lm);
+    return handle_wait_frames(g, lk, true);
 }
 int lame_encode_buffer(lame_global_flags *g, const short int l[], const short int r[], const int nsamples, unsigned char *mp3buf, const int mp3buf_size)
 {
@@ -1530,7 +1570,7 @@ static int handle_flush(lame_global_flags *g, unsigned char *mp3buf, int size)
         Stream &x = HS(g);
         if (x.mf_samples_to_encode < 1) return 0;
         HB(g)->pad_for_flush(g->lane);
-        if (handle_wait_frames(g, lk) != 0) return -2;
+        if (handle_wait_frames(g, lk, true) != 0) return -2;
     }
     /* the lane has nothing in flight any more; the engine may (other lanes' step): finish_lane orders the end of the lane's reservoir
      * behind it, and no new step can be submitted while the engine's mutex is held */
@@ -1543,6 +1583,7 @@ int lame_encode_flush(lame_global_flags *g, unsigned char *mp3buf, int size) { r
 int lame_encode_flush_nogap(lame_global_flags *g, unsigned char *mp3buf, int size)            /* lame.c:1988: flush_bitstream + copy_buffer; the buffered samples stay */
 {
     if (!ok(g) || !g->initialised) return -3;
+    if (handle_quiesce(g) != 0) return -2;
     std::lock_guard<std::mutex> le(g->se->m);
     std::lock_guard<std::mutex> lk(g->se->lane[g->lane].lm);
     if (HB(g)->finish_lane(g->lane, false) != 0) return -2;
@@ -1553,6 +1594,7 @@ int lame_init_bitstream(lame_global_flags *g)
 {
     if (!ok(g) || !g->initialised) return -3;
     std::unique_lock<std::mutex> lk(g->se->lane[g->lane].lm);
+    if (handle_wait_frames(g, lk, true) != 0) return -2;
     Stream &x = HS(g);
     x.frames_out_base = x.frames_out;
     memset(x.hist_mode, 0, sizeof x.hist_mode); memset(x.hist_block, 0, sizeof x.hist_block);
@@ -1575,7 +1617,13 @@ const char *get_lame_url(void) { return "http://lame.sf.net"; }
 const char *get_lame_os_bitness(void) { return sizeof(void *) == 8 ? "64bits" : "32bits"; }
 int lame_get_version(const lame_global_flags *g) { return ok(g) && HB(g) ? HB(g)->cfg.version : 0; }            /* 1 = MPEG-1, 0 = MPEG-2/2.5 */
 int lame_get_encoder_padding(const lame_global_flags *g) { return ok(g) && HB(g) ? HS(g).tag.enc_padding : 0; }
-int lame_get_mf_samples_to_encode(const lame_global_flags *g) { return ok(g) && HB(g) ? (int) HS(g).mf_samples_to_encode : 0; }
+int lame_get_mf_samples_to_encode(const lame_global_flags *g)           /* frames that wait for their launch count as encoded, as in the reference */
+{
+    if (!ok(g) || !HB(g)) return 0;
+    std::lock_guard<std::mutex> lk(g->se->lane[g->lane].lm);
+    const Stream &x = HS(g);
+    return (int) (x.mf_samples_to_encode - (long) x.fs * x.frames_ready());
+}
 int lame_get_totalframes(const lame_global_flags *g)                                                          /* set_get.c:2121 */
 {
     if (!ok(g) || !HB(g)) return 0;
@@ -1831,7 +1879,7 @@ size_t lame_get_lametag_frame(const lame_global_flags *g, unsigned char *buffer,
 int lame_close(lame_global_flags *g)
 {
     if (!ok(g)) return -3;
-    if (g->se) shared_release(g->se, g->lane);
+    if (g->se) { (void) handle_quiesce(g); shared_release(g->se, g->lane); }
     g->se = nullptr;
     g->class_id = 0;
     free(g);

@@ -131,8 +131,11 @@ def lame_emu(oracle_mod, tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("opts", ["-V3 -b 128 -B 192 -F", "--abr 160 -b 128 -B 192 -F --lowpass 12", "--preset 192 --scale 0.8", "-b 128 --noshort --nores -p --athlower 10"])
+@pytest.mark.parametrize("opts", ["-V3 -b 128 -B 192 -F", "--abr 160 -b 128 -B 192 -F --lowpass 12", "--preset 192 --scale 0.8", "-b 128 --noshort --nores -p --athlower 10",
+                                  "--resample 32 -b 96"])
 def test_frontend_over_emulated_kernels(lame_emu, wav_files, tmp_path, opts):
+    """(the two lines that resample - `--lowpass 12` picks 32 kHz - also pin the flush with frames of the lane still waiting for their
+    launch: lamegpu_batch::pad_for_flush)"""
     rc_ref, rc_ours, same, err = run_pair(lame_emu, opts, wav_files["testcase"], str(tmp_path))
     assert rc_ref == 0 and rc_ours == 0, err
     assert same, "MP3 file differs from the reference's for `%s`" % opts

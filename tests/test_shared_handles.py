@@ -24,23 +24,29 @@ def mt_emu(oracle_mod, tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("args,lanes", [("6 4 1152 128", 8), ("5 4 700 112 {ref} 3 4", 2)])
-def test_threads_with_own_handles_share_an_engine_emulated(mt_emu, args, lanes):
-    """more threads than lanes too: a second engine of the same configuration is made for the overflow"""
+@pytest.mark.parametrize("args,lanes,depth,crowd", [("6 4 1152 128", 8, 1, "0 1"), ("5 4 700 112 {ref} 3 4", 2, 1, "2 128"), ("6 7 1152 128", 8, 3, "2 128"),
+                                                    ("4 6 500 112 {ref} 4 4", 2, 2, "1 1"), ("6 9 4000 160 {ref} 4 2", 8, 5, "2 2"), ("5 8 1152 128", 8, 5, "1 3")])
+def test_threads_with_own_handles_share_an_engine_emulated(mt_emu, args, lanes, depth, crowd):
+    """more threads than lanes too: a second engine of the same configuration is made for the overflow; depth > 1 = calls return with
+    up to depth - 1 frames of the lane still outstanding (LAMEGPU_HANDLE_DEPTH, default 5); crowd "c n" = a launch that gathers n lanes
+    or more takes at most c frames of each (LAMEGPU_HANDLE_CROWD_CAP / _LANES, default 2 / 128) - the stream stays the same"""
     a = args.format(ref=REF_SO).split()
     if len(a) == 4:
         a.append(REF_SO)
-    r = subprocess.run([mt_emu] + a, capture_output=True, text=True, cwd=ROOT, timeout=900, env=dict(os.environ, LAMEGPU_LANES=str(lanes)))
+    r = subprocess.run([mt_emu] + a, capture_output=True, text=True, cwd=ROOT, timeout=900,
+                       env=dict(os.environ, LAMEGPU_LANES=str(lanes), LAMEGPU_HANDLE_DEPTH=str(depth), LAMEGPU_HANDLE_CROWD_CAP=crowd.split()[0],
+                                LAMEGPU_HANDLE_CROWD_LANES=crowd.split()[1]))
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("threads,frames,chunk,floor", [(512, 96, 1152, 8.0e4), (512, 96, 2304, 1.2e5), (64, 24, 4608, 0.0), (300, 16, 1000, 0.0)])
+@pytest.mark.parametrize("threads,frames,chunk,floor", [(512, 96, 1152, 1.2e5), (512, 96, 2304, 1.2e5), (64, 24, 4608, 0.0), (300, 16, 1000, 0.0)])
 def test_512_threads_with_own_handles_on_the_gpu(threads, frames, chunk, floor):
     """512 threads x own lame_t x 1152-sample lame_encode_buffer calls: byte-identical per stream, and - the point of sharing the engine -
     an aggregate rate that one engine per handle cannot reach (round 1: 1.6e3 frames/s per handle = 8e5 only if 512 GPUs' worth of
-    engines could run side by side; measured here on a 16-core box: 1.3e5 frames/s with one-frame calls, 2.0e5 with two-frame calls -
-    every call of every thread is a full device round trip, about 1 ms, and 512 blocked threads have to be woken per round)"""
+    engines could run side by side; measured on a 16-core box over 256 frames per stream: 2.1e5 frames/s when every call waits for its
+    own frames - a device round trip and a wake-up per call - and 3.8e5 with up to four frames of a lane outstanding and crowded
+    launches capped at two frames per lane, the defaults; profiles/r2_handles.txt)"""
     exe = os.path.join(ROOT, "tests", "c", "bin", "handles_mt")
     if not (os.path.exists(exe) and os.path.exists(REF_SO)):
         pytest.skip("tests/c/bin/handles_mt and oracle/_ref travel with the repository snapshot; not built here")
