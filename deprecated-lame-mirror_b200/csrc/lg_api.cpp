@@ -1233,7 +1233,7 @@ static LgShared *shared_acquire(const std::string &key, const std::function<lame
         /* measured with 512 threads (profiles/r2_handles.txt): no cap 2.65e5 frames/s, 3 -> 3.6e5, 2 -> 3.8e5, 1 -> 3.3e5 */
         const char *e = getenv("LAMEGPU_HANDLE_CROWD_CAP"), *e2 = getenv("LAMEGPU_HANDLE_CROWD_LANES");
         b->crowd_cap = e ? std::max(0, atoi(e)) : 2;
-        b->crowd_lanes = e2 ? std::max(1, atoi(e2)) : 128;
+        b->crowd_lanes = e2 ? std::max(1, atoi(e2)) : 32;        /* 64 threads: 3.9e4 frames/s without the cap, 6.6e4 with it */
     }
     se->lane.reset(new LgShared::Lane[b->S]);
     se->used.assign(b->S, 0);

@@ -24,12 +24,12 @@ def mt_emu(oracle_mod, tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("args,lanes,depth,crowd", [("6 4 1152 128", 8, 1, "0 1"), ("5 4 700 112 {ref} 3 4", 2, 1, "2 128"), ("6 7 1152 128", 8, 3, "2 128"),
+@pytest.mark.parametrize("args,lanes,depth,crowd", [("6 4 1152 128", 8, 1, "0 1"), ("5 4 700 112 {ref} 3 4", 2, 1, "2 32"), ("6 7 1152 128", 8, 3, "2 32"),
                                                     ("4 6 500 112 {ref} 4 4", 2, 2, "1 1"), ("6 9 4000 160 {ref} 4 2", 8, 5, "2 2"), ("5 8 1152 128", 8, 5, "1 3")])
 def test_threads_with_own_handles_share_an_engine_emulated(mt_emu, args, lanes, depth, crowd):
     """more threads than lanes too: a second engine of the same configuration is made for the overflow; depth > 1 = calls return with
     up to depth - 1 frames of the lane still outstanding (LAMEGPU_HANDLE_DEPTH, default 5); crowd "c n" = a launch that gathers n lanes
-    or more takes at most c frames of each (LAMEGPU_HANDLE_CROWD_CAP / _LANES, default 2 / 128) - the stream stays the same"""
+    or more takes at most c frames of each (LAMEGPU_HANDLE_CROWD_CAP / _LANES, default 2 / 32) - the stream stays the same"""
     a = args.format(ref=REF_SO).split()
     if len(a) == 4:
         a.append(REF_SO)
