@@ -39,8 +39,39 @@ def test_threads_with_own_handles_share_an_engine_emulated(mt_emu, args, lanes, 
     assert r.returncode == 0 and "IDENTICAL" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
 
 
+@pytest.fixture(scope="module")
+def edges_emu(oracle_mod, tmp_path_factory):
+    if not os.path.exists(REF_SO):
+        pytest.skip("needs the reference build (oracle/_ref)")
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "emu")], check=True, capture_output=True)
+    exe = str(tmp_path_factory.mktemp("bin") / "handle_edges_emu")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-w", os.path.join(ROOT, "tests", "c", "handle_edges.cpp"), "-o", exe, "-L" + os.path.join(ROOT, "tests", "emu"),
+                    "-llamegpu_emu", "-ldl", "-lpthread", "-lm", "-Wl,-rpath," + os.path.join(ROOT, "tests", "emu")], check=True)
+    return exe
+
+
+@pytest.mark.parametrize("chunk,depth", [(1152, 5), (700, 5), (2500, 3), (1152, 1)])
+def test_calls_that_end_or_read_a_lane_with_frames_outstanding_emulated(edges_emu, chunk, depth):
+    """tests/c/handle_edges.cpp: encoding on after lame_encode_flush, lame_encode_flush_nogap + lame_init_bitstream in mid-stream
+    (lame.c:1988, :2006), lame_close without a flush and the lane's next owner, lame_get_mf_samples_to_encode after every call - each
+    sequence made to the product (emulated kernels) and to the reference library, bytes and values compared"""
+    r = subprocess.run([edges_emu, REF_SO, str(chunk)], capture_output=True, text=True, cwd=ROOT, timeout=900,
+                       env=dict(os.environ, LAMEGPU_LANES="2", LAMEGPU_HANDLE_DEPTH=str(depth)))
+    assert r.returncode == 0 and "IDENTICAL 4/4" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("threads,frames,chunk,floor", [(512, 96, 1152, 1.2e5), (512, 96, 2304, 1.2e5), (64, 24, 4608, 0.0), (300, 16, 1000, 0.0)])
+@pytest.mark.parametrize("chunk", [1152, 700])
+def test_calls_that_end_or_read_a_lane_with_frames_outstanding_on_the_gpu(chunk):
+    exe = os.path.join(ROOT, "tests", "c", "bin", "handle_edges")
+    if not (os.path.exists(exe) and os.path.exists(REF_SO)):
+        pytest.skip("tests/c/bin/handle_edges and oracle/_ref travel with the repository snapshot; not built here")
+    r = subprocess.run([exe, REF_SO, str(chunk)], capture_output=True, text=True, cwd=ROOT, timeout=300, env=dict(os.environ, LAMEGPU_LANES="8"))
+    assert r.returncode == 0 and "IDENTICAL 4/4" in r.stdout, r.stdout[-1000:] + r.stderr[-1000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("threads,frames,chunk,floor", [(512, 96, 1152, 8.0e4), (512, 96, 2304, 1.2e5), (64, 24, 4608, 0.0), (300, 16, 1000, 0.0)])
 def test_512_threads_with_own_handles_on_the_gpu(threads, frames, chunk, floor):
     """512 threads x own lame_t x 1152-sample lame_encode_buffer calls: byte-identical per stream, and - the point of sharing the engine -
     an aggregate rate that one engine per handle cannot reach (round 1: 1.6e3 frames/s per handle = 8e5 only if 512 GPUs' worth of
