@@ -1,7 +1,7 @@
 /* Test harness: the calls of the libmp3lame face that read or end a handle's state while frames of its lane may still be outstanding
  * (lame_encode_buffer returns with up to LAMEGPU_HANDLE_DEPTH - 1 frames not yet back, lg_api.cpp handle_wait_frames): encoding on
  * after lame_encode_flush, lame_encode_flush_nogap + lame_init_bitstream in mid-stream (lame.c:1988, :2006), lame_close without a
- * flush and the lane's next owner, lame_get_mf_samples_to_encode after every call.  Every sequence is made to the product library
+ * flush and the lane's next owner, lame_get_mf_samples_to_encode after every call, a flush right behind a call on a resampled stream.  Every sequence is made to the product library
  * (linked) and to the checker named by argv[1] - the reference library, loaded with dlopen - and the bytes are compared.
  * usage: handle_edges <checker.so> [chunk_samples]; exit code 0 only when every scenario is identical. */
 #include <stdio.h>
@@ -18,6 +18,7 @@ struct Api {
     void *(*init)(void);
     int (*set_brate)(void *, int);
     int (*set_tag)(void *, int);
+    int (*set_out_rate)(void *, int);
     int (*init_params)(void *);
     int (*encode)(void *, const short *, const short *, int, unsigned char *, int);
     int (*flush)(void *, unsigned char *, int);
@@ -30,6 +31,7 @@ static Api product()
 {
     Api a;
     a.init = (void *(*)(void)) lame_init; a.set_brate = (int (*)(void *, int)) lame_set_brate; a.set_tag = (int (*)(void *, int)) lame_set_bWriteVbrTag;
+    a.set_out_rate = (int (*)(void *, int)) lame_set_out_samplerate;
     a.init_params = (int (*)(void *)) lame_init_params; a.encode = (int (*)(void *, const short *, const short *, int, unsigned char *, int)) lame_encode_buffer;
     a.flush = (int (*)(void *, unsigned char *, int)) lame_encode_flush; a.flush_nogap = (int (*)(void *, unsigned char *, int)) lame_encode_flush_nogap;
     a.init_bitstream = (int (*)(void *)) lame_init_bitstream; a.mf_left = (int (*)(const void *)) lame_get_mf_samples_to_encode; a.close = (int (*)(void *)) lame_close;
@@ -39,7 +41,7 @@ static Api checker(void *h)
 {
     Api a;
     a.init = (void *(*)(void)) dlsym(h, "lame_init"); a.set_brate = (int (*)(void *, int)) dlsym(h, "lame_set_brate");
-    a.set_tag = (int (*)(void *, int)) dlsym(h, "lame_set_bWriteVbrTag"); a.init_params = (int (*)(void *)) dlsym(h, "lame_init_params");
+    a.set_tag = (int (*)(void *, int)) dlsym(h, "lame_set_bWriteVbrTag"); a.set_out_rate = (int (*)(void *, int)) dlsym(h, "lame_set_out_samplerate"); a.init_params = (int (*)(void *)) dlsym(h, "lame_init_params");
     a.encode = (int (*)(void *, const short *, const short *, int, unsigned char *, int)) dlsym(h, "lame_encode_buffer");
     a.flush = (int (*)(void *, unsigned char *, int)) dlsym(h, "lame_encode_flush"); a.flush_nogap = (int (*)(void *, unsigned char *, int)) dlsym(h, "lame_encode_flush_nogap");
     a.init_bitstream = (int (*)(void *)) dlsym(h, "lame_init_bitstream"); a.mf_left = (int (*)(const void *)) dlsym(h, "lame_get_mf_samples_to_encode");
@@ -50,10 +52,11 @@ static std::vector<short> L, R;
 static int chunk = 1152;
 static const int CAP = 1 << 17;
 
-static void *open_handle(const Api &a, int brate, int tag)
+static void *open_handle(const Api &a, int brate, int tag, int out_rate = 0)
 {
     void *g = a.init();
     a.set_brate(g, brate); a.set_tag(g, tag);
+    if (out_rate) a.set_out_rate(g, out_rate);
     if (a.init_params(g) != 0) { fprintf(stderr, "lame_init_params failed\n"); exit(2); }
     return g;
 }
@@ -120,6 +123,18 @@ static Bytes samples_left_after_every_call(const Api &a)
     return rec;
 }
 
+/* 44.1 -> 32 kHz: the flush pads in bunches sized from what the reference has encoded by then (lame.c:2077-2117); here the frames of
+ * the last calls still wait for their launch when the flush begins (both slots of the engine busy with the calls before them) */
+static Bytes flush_behind_resampled_calls(const Api &a)
+{
+    Bytes out, buf(CAP);
+    void *g = open_handle(a, 96, 1, 32000);
+    feed(a, g, 0, 14 * 1152 + 123, out);
+    take(a.flush(g, buf.data(), CAP), buf, out);
+    a.close(g);
+    return out;
+}
+
 int main(int argc, char **argv)
 {
     const char *so = argc > 1 ? argv[1] : "oracle/_ref/libmp3lame_ref.so";
@@ -137,7 +152,8 @@ int main(int argc, char **argv)
     }
     struct { const char *name; Bytes (*run)(const Api &); } const cases[] = {
         { "encode after flush", encode_after_flush }, { "flush_nogap + init_bitstream", nogap_and_new_bitstream },
-        { "close without flush, lane reused", close_without_flush_then_next_owner }, { "mf_samples_to_encode per call", samples_left_after_every_call } };
+        { "close without flush, lane reused", close_without_flush_then_next_owner }, { "mf_samples_to_encode per call", samples_left_after_every_call },
+        { "flush behind resampled calls", flush_behind_resampled_calls } };
     int bad = 0;
     for (auto const &c : cases) {
         Bytes const a = c.run(ours), b = c.run(ref);
@@ -145,7 +161,7 @@ int main(int argc, char **argv)
         printf("%s: %s (%zu bytes against %zu)\n", c.name, same ? "identical" : "DIFFERENT", a.size(), b.size());
         bad += !same;
     }
-    if (bad) { printf("DIFFERENT: %d of 4 scenarios\n", bad); return 1; }
-    printf("IDENTICAL 4/4 scenarios (%d-sample calls)\n", chunk);
+    if (bad) { printf("DIFFERENT: %d of 5 scenarios\n", bad); return 1; }
+    printf("IDENTICAL 5/5 scenarios (%d-sample calls)\n", chunk);
     return 0;
 }
