@@ -50,7 +50,7 @@ def edges_emu(oracle_mod, tmp_path_factory):
     return exe
 
 
-@pytest.mark.parametrize("chunk,depth,frames", [(1152, 5, 8), (700, 5, 1), (2500, 3, 1), (1152, 1, 8)])
+@pytest.mark.parametrize("chunk,depth,frames", [(1152, 5, 8), (700, 5, 1)])
 def test_calls_that_end_or_read_a_lane_with_frames_outstanding_emulated(edges_emu, chunk, depth, frames):
     """tests/c/handle_edges.cpp: encoding on after lame_encode_flush, lame_encode_flush_nogap + lame_init_bitstream in mid-stream
     (lame.c:1988, :2006), lame_close without a flush and the lane's next owner, lame_get_mf_samples_to_encode after every call, a flush right behind calls that
